@@ -1,0 +1,210 @@
+"""Deterministic inputs / weights of the golden cases.
+
+Shared by tests/golden/make_golden.py (which runs the REFERENCE on them, in the authoring
+container only) and by the parity tests (which run the oracle and the CUDA path on them).
+Everything is drawn from numpy's PCG64 ``default_rng(seed)`` and rounded to bf16-representable
+fp32 values so that the bf16 CUDA path and the fp32 reference see *identical* weights and inputs.
+Each fixture stores ``input_checksum`` so a drift of the generator is detected, not silently absorbed.
+"""
+import math
+
+import numpy as np
+import torch
+
+
+def bf16r(a):
+    """Round an fp32 numpy array to the nearest bf16-representable fp32 values."""
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).bfloat16().float().numpy()
+
+
+def normal(rng, shape, std=1.0, round_bf16=True):
+    a = rng.standard_normal(shape, dtype=np.float32) * np.float32(std)
+    return bf16r(a) if round_bf16 else a
+
+
+def attn_weights(rng, C, ctx_dim, lora_rank=0, lora_alpha=None, lora_layers=("q", "k", "v", "out")):
+    """Weights of one SD-1.5 attention module (+ optional DoRA adapters)."""
+    w = {
+        "to_q": normal(rng, (C, C), 1 / math.sqrt(C)),
+        "to_k": normal(rng, (C, ctx_dim), 1 / math.sqrt(ctx_dim)),
+        "to_v": normal(rng, (C, ctx_dim), 1 / math.sqrt(ctx_dim)),
+        "to_out_w": normal(rng, (C, C), 1 / math.sqrt(C)),
+        "to_out_b": normal(rng, (C,), 0.02),
+        "cross_attn_scale_factor": np.float32(0.8),
+    }
+    if lora_rank:
+        s = (lora_alpha if lora_alpha is not None else lora_rank / 8) / lora_rank
+        for name in lora_layers:
+            base = {"q": "to_q", "k": "to_k", "v": "to_v", "out": "to_out_w"}[name]
+            W = w[base]
+            A = normal(rng, (lora_rank, W.shape[1]), 1 / math.sqrt(W.shape[1]))
+            B = normal(rng, (W.shape[0], lora_rank), 0.02)          # non-zero so the branch is exercised
+            mag = np.linalg.norm(W + s * (B @ A), axis=1) * (1 + 0.1 * rng.standard_normal(W.shape[0]))
+            w["lora_" + name] = (A, B, mag.astype(np.float32))
+        w["lora_scaling"] = np.float32(s)
+    return w
+
+
+def img_mask(rng, B, size=64, zero_instance=None):
+    m = (rng.random((B, 1, size, size)) > 0.3).astype(np.float32)
+    if zero_instance is not None:
+        m[zero_instance] = 0
+    return m
+
+
+def subj_indices(B, first=4, n=16):
+    ib = np.repeat(np.arange(B), n).astype(np.int64)
+    in_ = np.tile(np.arange(first, first + n), B).astype(np.int64)
+    return ib, in_
+
+
+# name -> spec of the attention-processor cases (surface 1, dalc:192-364)
+PROC_CASES = {
+    # BASELINE config 1 shapes at reduced token count (N=256 = 16x16 map): C=320, 8 heads x 40, ctx 77x768
+    "proc_cross_fast":      dict(seed=11, B=2, N=256, C=320, S=77, cross=True),
+    "proc_cross_capture":   dict(seed=12, B=2, N=64, C=320, S=77, cross=True, capture=True),
+    "proc_cross_norm_lora": dict(seed=13, B=2, N=128, C=320, S=77, cross=True, capture=True, normalize=True,
+                                 lora_rank=8, lora_alpha=1, enable_lora=True, subj=True),
+    "proc_cross_norm_lora_qupd": dict(seed=14, B=2, N=64, C=320, S=97, cross=True, capture=True, normalize=True,
+                                      lora_rank=16, lora_alpha=2, enable_lora=True, subj=True, q_upd=True),
+    "proc_cross_mix_lora":  dict(seed=15, B=2, N=64, C=320, S=77, cross=True, capture=True, mix=True,
+                                 lora_rank=8, lora_alpha=1, enable_lora=True),
+    "proc_self_fast":       dict(seed=16, B=2, N=256, C=320),
+    "proc_self_mask":       dict(seed=17, B=2, N=256, C=320, mask=True),
+    "proc_self_mask_dropped": dict(seed=18, B=2, N=256, C=320, mask=True, zero_instance=1),
+    "proc_cross_capture_d80": dict(seed=19, B=1, N=64, C=640, S=77, cross=True, capture=True),
+    "proc_self_d160":       dict(seed=20, B=2, N=64, C=1280),
+    "proc_cross_d160_ragged": dict(seed=21, B=1, N=36, C=1280, S=77, cross=True),
+}
+
+
+def build_proc_case(name):
+    sp = PROC_CASES[name]
+    rng = np.random.default_rng(sp["seed"])
+    B, N, C = sp["B"], sp["N"], sp["C"]
+    cross = sp.get("cross", False)
+    ctx_dim = 768 if cross else C
+    case = dict(spec=sp)
+    case["w"] = attn_weights(rng, C, ctx_dim, sp.get("lora_rank", 0), sp.get("lora_alpha"))
+    case["hidden_states"] = normal(rng, (B, N, C))
+    case["encoder_hidden_states"] = normal(rng, (B, sp["S"], 768)) if cross else None
+    case["img_mask"] = img_mask(rng, B, 64, sp.get("zero_instance")) if sp.get("mask") else None
+    case["subj_indices"] = subj_indices(B) if sp.get("subj") else None
+    return case
+
+
+LDM_CASES = {
+    "ldm_self_mask":  dict(seed=31, B=2, N=256, C=320, mask=True),
+    "ldm_cross_save": dict(seed=32, B=2, N=64, C=320, S=77, cross=True, save=True),
+    "ldm_block":      dict(seed=33, B=2, N=256, C=320, S=77, block=True, mask=True),
+    "ldm_block_d80":  dict(seed=34, B=1, N=64, C=640, S=77, block=True),
+}
+
+
+def build_ldm_case(name):
+    sp = LDM_CASES[name]
+    rng = np.random.default_rng(sp["seed"])
+    B, N, C = sp["B"], sp["N"], sp["C"]
+    case = dict(spec=sp)
+    case["x"] = normal(rng, (B, N, C))
+    side = int(math.sqrt(N))
+    case["mask"] = img_mask(rng, B, side) if sp.get("mask") else None
+    if sp.get("block"):
+        w = {"attn1": attn_weights(rng, C, C), "attn2": attn_weights(rng, C, 768)}
+        for i in (1, 2, 3):
+            w[f"norm{i}_w"] = bf16r(1 + 0.1 * rng.standard_normal(C))
+            w[f"norm{i}_b"] = normal(rng, (C,), 0.05)
+        w["ff_proj_w"] = normal(rng, (8 * C, C), 1 / math.sqrt(C))
+        w["ff_proj_b"] = normal(rng, (8 * C,), 0.02)
+        w["ff_out_w"] = normal(rng, (C, 4 * C), 1 / math.sqrt(4 * C))
+        w["ff_out_b"] = normal(rng, (C,), 0.02)
+        case["w"] = w
+        case["context"] = normal(rng, (B, sp["S"], 768))
+    else:
+        cross = sp.get("cross", False)
+        case["w"] = attn_weights(rng, C, 768 if cross else C)
+        case["context"] = normal(rng, (B, sp["S"], 768)) if cross else None
+    return case
+
+
+# SubjBasisGenerator / CLIP-shaped encoder (surface 3).  E=768, 12 heads x 64, MLP 3072, 77 positions.
+SBG_CASES = {
+    "mkv_m1":   dict(seed=41, BS=2, T=77, mult=1, layers=0),
+    "mkv_m2":   dict(seed=42, BS=2, T=77, mult=2, layers=0),
+    "sbg_m1":   dict(seed=43, BS=2, layers=12, mults=[1] * 12),
+    "sbg_m2":   dict(seed=44, BS=3, layers=12, mults=[2] * 12, cfg=0.7),
+    "sbg_mixed_sfx": dict(seed=45, BS=1, layers=12, mults=[1, 1, 2, 2, 4, 4, 1, 1, 2, 2, 1, 1], n_sfx=4),
+}
+E, HEADS, MLP, VOCAB, NPOS = 768, 12, 3072, 49408, 77
+TEMPLATE_IDS = [49406, 1125, 539, 320] + [267] * 18 + [49407] * 55
+
+
+def clip_layer_weights(rng, mult):
+    s = 1 / math.sqrt(E)
+    w = {"num_heads": HEADS}
+    for p, rows in (("q", E), ("k", E * mult), ("v", E * mult), ("o", E)):
+        w[p + "_w"] = normal(rng, (rows, E), s)
+        w[p + "_b"] = normal(rng, (rows,), 0.02)
+    for ln in ("ln1", "ln2"):
+        w[ln + "_w"] = bf16r(1 + 0.1 * rng.standard_normal(E))
+        w[ln + "_b"] = normal(rng, (E,), 0.05)
+    w["fc1_w"] = normal(rng, (MLP, E), s)
+    w["fc1_b"] = normal(rng, (MLP,), 0.02)
+    w["fc2_w"] = normal(rng, (E, MLP), 1 / math.sqrt(MLP))
+    w["fc2_b"] = normal(rng, (E,), 0.02)
+    return w
+
+
+def build_sbg_case(name):
+    sp = SBG_CASES[name]
+    rng = np.random.default_rng(sp["seed"])
+    case = dict(spec=sp)
+    if sp["layers"] == 0:
+        case["w"] = clip_layer_weights(rng, sp["mult"])
+        case["x"] = normal(rng, (sp["BS"], sp["T"], E))
+        return case
+    # Only the template's 4 distinct token rows matter; keep the table small but index-compatible.
+    rows = {tid: normal(rng, (E,), 0.02) for tid in (49406, 1125, 539, 320, 267, 49407)}
+    w = {"token_emb_rows": rows,
+         # token_embedding(input_ids) of the 77-token template (subj_basis_generator.py:473-492)
+         "template_embs": np.stack([rows[t] for t in TEMPLATE_IDS]),
+         "pos_emb": normal(rng, (NPOS, E), 0.02),
+         "layers": [clip_layer_weights(rng, m) for m in sp["mults"]],
+         "final_ln_w": bf16r(1 + 0.1 * rng.standard_normal(E)),
+         "final_ln_b": normal(rng, (E,), 0.05),
+         "hidden_state_layer_weights": np.array([[1.0], [2.0], [4.0]], dtype=np.float32),
+         "pad_embeddings": normal(rng, (NPOS, E), 0.02)}
+    if sp.get("n_sfx"):
+        w["static_img_suffix_embs"] = normal(rng, (1, sp["n_sfx"], E), 1.0)
+    case["w"] = w
+    case["faceid2img_prompt_embs"] = normal(rng, (sp["BS"], 16, E), 0.5)
+    return case
+
+
+def checksum(obj):
+    """Order-stable float64 checksum of every array in a (nested) case dict."""
+    if obj is None:
+        return 0.0
+    if isinstance(obj, dict):
+        return float(sum(checksum(obj[k]) * (1 + 0.001 * i) for i, k in enumerate(sorted(obj, key=str)) if k != "spec"))
+    if isinstance(obj, (list, tuple)):
+        return float(sum(checksum(v) * (1 + 0.01 * i) for i, v in enumerate(obj)))
+    a = np.asarray(obj)
+    if a.dtype.kind not in "fiu":
+        return 0.0
+    return float(np.abs(a.astype(np.float64)).sum() + a.astype(np.float64).sum() * 0.5)
+
+
+def to_torch(obj):
+    """numpy -> torch fp32 / int64, recursively (dict / list / tuple preserved)."""
+    if obj is None:
+        return None
+    if isinstance(obj, dict):
+        return {k: (v if k in ("spec", "num_heads") else to_torch(v)) for k, v in obj.items()}
+    if isinstance(obj, tuple):
+        return tuple(to_torch(v) for v in obj)
+    if isinstance(obj, list):
+        return [to_torch(v) for v in obj]
+    if isinstance(obj, (int, float)):
+        return obj
+    return torch.from_numpy(np.ascontiguousarray(obj))

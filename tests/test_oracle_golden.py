@@ -1,0 +1,115 @@
+"""CPU: pin the oracle (oracle/*.py) to the reference's own outputs (tests/golden/*.npz).
+
+The fixtures were produced by tests/golden/make_golden.py, which runs the reference files verbatim from
+/root/reference.  Tolerances are fp32 round-off only: the oracle restates the same
+arithmetic in a different operation order."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases as C
+import oracle
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+ATOL = 2e-5
+
+
+def load(name, case):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    cs = C.checksum({k: v for k, v in case.items() if k != "spec"})
+    assert abs(cs - float(g["input_checksum"])) <= 1e-9 * max(1.0, abs(cs)), \
+        "seeded inputs drifted from the ones the fixture was generated on (numpy RNG stream changed?)"
+    return g
+
+
+def close(a, ref, atol=ATOL, what=""):
+    a = a.detach().numpy() if torch.is_tensor(a) else np.asarray(a)
+    assert a.shape == ref.shape, f"{what}: shape {a.shape} vs {ref.shape}"
+    fin = np.isfinite(ref)
+    assert (np.isfinite(a) == fin).all(), f"{what}: non-finite pattern differs"
+    err = np.abs(a[fin] - ref[fin]).max() if fin.any() else 0.0
+    assert err <= atol, f"{what}: max-abs {err:.3e} > {atol}"
+
+
+def run_oracle_proc(case):
+    sp = case["spec"]
+    t = C.to_torch({k: v for k, v in case.items() if k != "spec"})
+    w = t["w"]
+    return oracle.processor_forward(
+        w, t["hidden_states"], t["encoder_hidden_states"], img_mask=t["img_mask"], subj_indices=t["subj_indices"],
+        heads=8, capture_ca_activations=sp.get("capture", False), normalize_cross_attn=sp.get("normalize", False),
+        mix_attn_mats_in_batch=sp.get("mix", False), enable_lora=sp.get("enable_lora", False),
+        q_lora_updates_query=sp.get("q_upd", False), lora_scaling=float(w.get("lora_scaling", 0.125)))
+
+
+@pytest.mark.parametrize("name", list(C.PROC_CASES))
+def test_processor_oracle_matches_reference(name):
+    case = C.build_proc_case(name)
+    g = load(name, case)
+    out, cache = run_oracle_proc(case)
+    close(out, g["out"], what="out")
+    gold_keys = {k[6:] for k in g.files if k.startswith("cache_")}
+    assert set(cache) == gold_keys
+    for k in gold_keys:
+        close(cache[k], g["cache_" + k], what=k)
+
+
+@pytest.mark.parametrize("name", list(C.LDM_CASES))
+def test_ldm_oracle_matches_reference(name):
+    case = C.build_ldm_case(name)
+    g = load(name, case)
+    sp = case["spec"]
+    t = C.to_torch({k: v for k, v in case.items() if k != "spec"})
+    if sp.get("block"):
+        out = oracle.basic_transformer_block(t["w"], t["x"], context=t["context"], mask=t["mask"])
+        close(out, g["out"], atol=1e-4, what="block out")
+    else:
+        out, cache = oracle.ldm_cross_attention(t["w"], t["x"], context=t["context"], mask=t["mask"],
+                                                save_cross_attn_vars=sp.get("save", False))
+        close(out, g["out"], what="out")
+        for k in (cache or {}):
+            close(cache[k], g["cache_" + k], what=k)
+
+
+@pytest.mark.parametrize("name", list(C.SBG_CASES))
+def test_sbg_oracle_matches_reference(name):
+    case = C.build_sbg_case(name)
+    g = load(name, case)
+    sp = case["spec"]
+    t = C.to_torch({k: v for k, v in case.items() if k != "spec"})
+    if sp["layers"] == 0:
+        out = oracle.clip_mkv_attention(t["w"], t["x"], sp["mult"])
+        close(out, g["out"], what="mkv out")
+    else:
+        out = oracle.sbg_forward(t["w"], t["faceid2img_prompt_embs"], out_id_embs_cfg_scale=sp.get("cfg", 1.0),
+                                 enable_static_img_suffix_embs=bool(sp.get("n_sfx")), multipliers=sp["mults"])
+        close(out, g["out"], atol=2e-4, what="sbg out")
+
+
+def test_two_reference_surfaces_agree():
+    """The diffusers-processor surface and the LDM CrossAttention surface are the same operator
+    (max-abs 1.3e-7); cached q differs only by the C^-1/4 vs d^-1/4 factor (quirk 1)."""
+    case = C.build_proc_case("proc_cross_capture")
+    t = C.to_torch({k: v for k, v in case.items() if k != "spec"})
+    o1, c1 = run_oracle_proc(case)
+    o2, c2 = oracle.ldm_cross_attention(t["w"], t["hidden_states"], context=t["encoder_hidden_states"],
+                                        save_cross_attn_vars=True)
+    assert (o1 - o2).abs().max() < 1e-5
+    assert (c1["attn"] - c2["attn"]).abs().max() < 1e-6
+    Cc, d = 320, 40
+    assert torch.allclose(c1["q"] * (Cc ** 0.25), c2["q"] * (d ** 0.25), atol=1e-5)
+
+
+def test_dora_identity_at_init():
+    """peft DoRA at init (B = 0, m = ||W||_row) is the identity adapter (SURVEY 8c property check)."""
+    g = torch.Generator().manual_seed(0)
+    W, x = torch.randn(24, 16, generator=g), torch.randn(5, 16, generator=g)
+    A, B = torch.randn(4, 16, generator=g), torch.zeros(24, 4)
+    y = oracle.lora_dora_linear(x, W, None, A, B, torch.linalg.norm(W, dim=1), 0.125)
+    assert torch.allclose(y, x @ W.T, atol=1e-5)
+    B = torch.randn(24, 4, generator=g) * 0.1
+    m = torch.linalg.norm(W + 0.125 * B @ A, dim=1)          # m == ||W + sBA||  -> plain LoRA
+    y = oracle.lora_dora_linear(x, W, None, A, B, m, 0.125)
+    assert torch.allclose(y, x @ (W + 0.125 * B @ A).T, atol=1e-5)
