@@ -1,0 +1,21 @@
+"""adaface_b200 -- B200-native (sm_100a) implementation of AdaFace's data-parallel hot path.
+
+Host-side mirrors of the reference's operator surface over the C-ABI library
+``csrc/libadaface_b200.so`` (include/adaface_b200.h):
+
+    AttnProcessor_LoRA_Capture, Attention, LoraDoraLinear, gen_gradient_scaler   (attn_processor.py)
+    CrossAttention, FeedForward, BasicTransformerBlock                          (ldm_attention.py)
+    SubjBasisGenerator, CLIPTextModelWrapper, CLIPAttentionMKV                   (subj_basis_generator.py)
+
+The directory is named ``adaface-dev_b200`` (not importable as is); import it as ``adaface_dev_b200``
+(the alias package at the repository root).
+"""
+from . import _lib, ops  # noqa: F401
+from .attn_processor import (AttnProcessor_LoRA_Capture, Attention, LoraDoraLinear, ScaleGrad, GradientScaler,  # noqa: F401
+                             gen_gradient_scaler, img_mask_to_key_mask)
+from .ldm_attention import CrossAttention, FeedForward, GEGLU, BasicTransformerBlock  # noqa: F401
+from .subj_basis_generator import (SubjBasisGenerator, CLIPTextModelWrapper, CLIPAttentionMKV, CLIPTextConfig,  # noqa: F401
+                                   template_ids)
+from .build import build  # noqa: F401
+
+__version__ = "0.1.0"

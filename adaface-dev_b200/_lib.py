@@ -1,0 +1,61 @@
+"""ctypes binding of libadaface_b200.so -- the C-ABI declared in include/adaface_b200.h.
+
+There is NO fallback: if the CUDA library is missing or a call fails, a RuntimeError is raised."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libadaface_b200.so")
+
+_c = ctypes
+_p, _i64, _i32, _f32 = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_float
+
+# name -> argtypes (mirrors include/adaface_b200.h one to one)
+SIGNATURES = {
+    "adaface_version": [],
+    "adaface_last_error": [],
+    "adaface_launch_count": [],
+    "adaface_proj_lora_fwd": [_p, _i64, _p, _p, _i64, _p, _p, _p, _p, _i64, _i32, _p, _i64, _i32, _i64, _i64, _i64,
+                              _i64, _i32, _p],
+    "adaface_attn_fwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
+                         _p, _i32, _f32, _p],
+    "adaface_attn_cross_capture_fwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64,
+                                       _i64, _i64, _i64, _f32, _p, _p, _p, _p, _i64, _p, _p, _p, _i32, _p],
+    "adaface_qmean": [_p, _i64, _i64, _i64, _i64, _i64, _p, _p],
+    "adaface_capture_chan_major": [_p, _i32, _i64, _i64, _i64, _i64, _i64, _f32, _p, _p],
+    "adaface_layernorm_fwd": [_p, _i32, _i64, _p, _p, _p, _i32, _i64, _i64, _i64, _f32, _p],
+    "adaface_sbg_head_fwd": [_p, _p, _p, _p, _c.POINTER(_f32), _i32, _i64, _p, _p, _p, _i64, _i64, _i64, _f32, _p],
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+            "adaface_b200 has no CPU / PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.argtypes = argtypes
+        fn.restype = _c.c_int
+    lib.adaface_last_error.restype = _c.c_char_p
+    lib.adaface_launch_count.restype = _c.c_int64
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed (status {rc}): {lib.adaface_last_error().decode()}")
+
+
+def launch_count():
+    return int(load().adaface_launch_count())

@@ -1,0 +1,318 @@
+"""Drop-in mirror of the reference's attention processor surface (surface 1).
+
+    AttnProcessor_LoRA_Capture          adaface/diffusers_attn_lora_capture.py:142-364
+    ScaleGrad / GradientScaler / gen_gradient_scaler                          :23-67
+    LoraDoraLinear                      stands in for peft ``lora.Linear(..., use_dora=True)`` (:171-181)
+    Attention                           minimal holder with the attributes the processor reads from a
+                                        diffusers ``Attention`` (:212-342); diffusers itself is not required.
+
+Same constructor, ``reset_attn_cache_and_flags``, ``cached_activations`` and ``__call__`` contract; the
+arithmetic runs in libadaface_b200.so (bf16 in, fp32 accumulate).  There is no PyTorch fallback.
+"""
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+# ------------------------------------------------------------------------------------------------ A5
+class ScaleGrad(torch.autograd.Function):
+    """Identity forward, grad * alpha backward (dalc:23-42)."""
+
+    @staticmethod
+    def forward(ctx, input_, alpha_, debug=False):
+        ctx.save_for_backward(alpha_)
+        return input_.view_as(input_)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (alpha_,) = ctx.saved_tensors
+        return (grad_output * alpha_ if ctx.needs_input_grad[0] else None), None, None
+
+
+class GradientScaler(nn.Module):
+    def __init__(self, alpha=1.0, debug=False):
+        super().__init__()
+        self._alpha = torch.tensor(alpha, requires_grad=False)
+        self._debug = torch.tensor(debug, requires_grad=False)
+
+    def forward(self, input_):
+        return ScaleGrad.apply(input_, self._alpha.to(input_.device), False)
+
+
+def gen_gradient_scaler(alpha, debug=False):
+    """dalc:59-67: alpha == 1 -> Identity, alpha == 0 -> detach, otherwise GradientScaler."""
+    if alpha == 1:
+        return nn.Identity()
+    if alpha > 0:
+        return GradientScaler(alpha, debug=debug)
+    if alpha != 0:
+        raise ValueError("gradient scale must be >= 0")
+    return torch.detach
+
+
+# ------------------------------------------------------------------------------------------------ A4
+class _Magnitude(nn.Module):
+    def __init__(self, w):
+        super().__init__()
+        self.weight = nn.Parameter(w)
+
+
+class LoraDoraLinear(nn.Module):
+    """Parameter container with peft's ``lora.Linear`` layout: ``base_layer``, ``lora_A['default']``,
+    ``lora_B['default']`` (nn.Linear, no bias) and ``lora_magnitude_vector['default'].weight``.
+    Init as peft: A Kaiming-uniform(a=sqrt 5), B zero, magnitude = ||W||_row (identity adapter).
+    The arithmetic is fused into the projection kernel by the processor."""
+
+    def __init__(self, base_layer, adapter_name="default", r=192, lora_alpha=16, use_dora=True, lora_dropout=0.1):
+        super().__init__()
+        if not use_dora:
+            raise NotImplementedError("the reference always uses DoRA (lora_uses_dora=True, dalc:499)")
+        self.base_layer = base_layer
+        self.r, self.lora_alpha, self.scaling = r, lora_alpha, lora_alpha / r
+        self.adapter = adapter_name
+        dev = base_layer.weight.device
+        self.lora_A = nn.ModuleDict({adapter_name: nn.Linear(base_layer.in_features, r, bias=False, device=dev)})
+        self.lora_B = nn.ModuleDict({adapter_name: nn.Linear(r, base_layer.out_features, bias=False, device=dev)})
+        nn.init.kaiming_uniform_(self.lora_A[adapter_name].weight, a=math.sqrt(5))
+        nn.init.zeros_(self.lora_B[adapter_name].weight)
+        mag = torch.linalg.norm(base_layer.weight.detach().float(), dim=1)
+        self.lora_magnitude_vector = nn.ModuleDict({adapter_name: _Magnitude(mag)})
+        self._pack_key, self._pack = None, None
+        # adapter management is neutered on these modules by the reference (dalc:531-532)
+        self.enable_adapters = lambda *a, **k: None
+        self.set_adapter = lambda *a, **k: None
+
+    def pack(self):
+        """bf16 operands of the fused kernel: A [r,in], Bs = s*B [out,r], colscale = m / ||W + s B A||_row (fp32,
+        detached).  Rebuilt only when a parameter changed (training: every step; inference: once)."""
+        A, B = self.lora_A[self.adapter].weight, self.lora_B[self.adapter].weight
+        m, W = self.lora_magnitude_vector[self.adapter].weight, self.base_layer.weight
+        key = tuple((t.data_ptr(), t._version) for t in (A, B, m, W))
+        if key != self._pack_key:
+            with torch.no_grad():
+                Af, Bf = A.float(), B.float()
+                wn = torch.linalg.norm(W.float() + self.scaling * (Bf @ Af), dim=1)
+                self._pack = (A.to(torch.bfloat16).contiguous(), (Bf * self.scaling).to(torch.bfloat16).contiguous(),
+                              (m.float() / wn).contiguous())
+            self._pack_key = key
+        return self._pack
+
+
+class Attention(nn.Module):
+    """The attributes AttnProcessor_LoRA_Capture reads from a diffusers ``Attention``: for SD-1.5
+    all norms are None, to_q/k/v have no bias, to_out = [Linear(bias), Dropout(0)], no residual, rescale 1."""
+
+    def __init__(self, query_dim, cross_attention_dim=None, heads=8, dim_head=64, processor=None, device=None):
+        super().__init__()
+        inner = heads * dim_head
+        ctx = cross_attention_dim if cross_attention_dim is not None else query_dim
+        self.heads = heads
+        self.spatial_norm = self.group_norm = self.norm_cross = self.norm_q = self.norm_k = None
+        self.residual_connection, self.rescale_output_factor = False, 1.0
+        self.to_q = nn.Linear(query_dim, inner, bias=False, device=device)
+        self.to_k = nn.Linear(ctx, inner, bias=False, device=device)
+        self.to_v = nn.Linear(ctx, inner, bias=False, device=device)
+        self.to_out = nn.ModuleList([nn.Linear(inner, query_dim, device=device), nn.Dropout(0.0)])
+        self.processor = processor if processor is not None else AttnProcessor_LoRA_Capture()
+
+    def set_processor(self, processor):
+        self.processor = processor
+
+    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **cross_attention_kwargs):
+        return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states,
+                              attention_mask=attention_mask, **cross_attention_kwargs)
+
+
+# ------------------------------------------------------------------------------------------------ weights
+def _bf16_pack(attn):
+    """bf16 copies of the frozen projection weights, fused where one GEMM can serve several projections.
+    Cached on the ``attn`` module and refreshed when any weight changes (``_version`` / storage)."""
+    ws = (attn.to_q.weight, attn.to_k.weight, attn.to_v.weight, attn.to_out[0].weight)
+    bs = (attn.to_q.bias, attn.to_k.bias, attn.to_v.bias, attn.to_out[0].bias)
+    key = tuple((t.data_ptr(), t._version) for t in ws) + tuple(None if b is None else (b.data_ptr(), b._version) for b in bs)
+    pk = getattr(attn, "_adaface_b200_pack", None)
+    if pk is not None and pk["key"] == key:
+        return pk
+    with torch.no_grad():
+        to16 = lambda t: t.detach().to(torch.bfloat16).contiguous()
+        f32 = lambda t: None if t is None else t.detach().float().contiguous()
+        pk = {"key": key, "wq": to16(ws[0]), "wk": to16(ws[1]), "wv": to16(ws[2]), "wo": to16(ws[3]),
+              "bq": f32(bs[0]), "bk": f32(bs[1]), "bv": f32(bs[2]), "bo": f32(bs[3])}
+        pk["wkv"] = torch.cat([pk["wk"], pk["wv"]], dim=0)
+        pk["bkv"] = None if bs[1] is None and bs[2] is None else torch.cat(
+            [f32(b) if b is not None else torch.zeros(w.shape[0], device=w.device) for b, w in ((bs[1], ws[1]), (bs[2], ws[2]))])
+        if ws[0].shape[1] == ws[1].shape[1]:
+            pk["wqkv"] = torch.cat([pk["wq"], pk["wk"], pk["wv"]], dim=0)
+            pk["bqkv"] = None if all(b is None for b in bs[:3]) else torch.cat(
+                [f32(b) if b is not None else torch.zeros(w.shape[0], device=w.device) for b, w in zip(bs[:3], ws[:3])])
+    attn._adaface_b200_pack = pk
+    return pk
+
+
+def _linear(x2d, w16, bias, lora: Optional[LoraDoraLinear], **kw):
+    """x W^T (+ DoRA-scaled LoRA update) + bias, one fused GEMM launch (+ one skinny launch for T = x A^T)."""
+    if lora is None:
+        return ops.proj(x2d, w16, bias=bias, **kw)
+    A16, Bs16, colscale = lora.pack()
+    t = ops.proj(x2d, A16)
+    return ops.proj(x2d, w16, t=t, bs=Bs16, colscale=colscale, bias=bias, **kw)
+
+
+def img_mask_to_key_mask(img_mask, n_tokens):
+    """dalc:254-273: nearest-resize the [B,1,H,W] mask to sqrt(N) x sqrt(N), use it as a KEY mask, and drop it for
+    the whole batch if any instance's resized mask is all zero -- evaluated on the device (no host sync)."""
+    ms = int(math.sqrt(n_tokens))
+    m = F.interpolate(img_mask.float(), size=(ms, ms), mode="nearest").reshape(img_mask.shape[0], -1) != 0
+    drop = (m.sum(dim=1) == 0).any()
+    return (m | drop).to(torch.uint8).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ A1
+class AttnProcessor_LoRA_Capture(nn.Module):
+    r"""B200-native ``AttnProcessor_LoRA_Capture`` (dalc:142-364); same constructor and call contract."""
+
+    def __init__(self, capture_ca_activations: bool = False, enable_lora: bool = False, lora_uses_dora=True,
+                 lora_proj_layers=None, lora_rank: int = 192, lora_alpha: float = 16, q_lora_updates_query=False,
+                 attn_proc_idx=-1):
+        super().__init__()
+        self.global_enable_lora = enable_lora
+        self.attn_proc_idx = attn_proc_idx
+        self.reset_attn_cache_and_flags(capture_ca_activations, False, False, enable_lora)
+        self.lora_rank, self.lora_alpha = lora_rank, lora_alpha
+        self.lora_scale = self.lora_alpha / self.lora_rank
+        self.q_lora_updates_query = q_lora_updates_query
+        # subject-columns-only capture (optional mode): also emit cached_activations['attn_subj']
+        self.capture_subj_cols_only = False
+        self.to_q_lora = self.to_k_lora = self.to_v_lora = self.to_out_lora = None
+        # Reference quirk 2 (fixed): always defined, so capture works with LoRA globally off (dalc:164-168, 314).
+        self.cross_attn_scale_factor = nn.Parameter(torch.tensor(0.8), requires_grad=True)
+        if self.global_enable_lora:
+            for name, layer in (lora_proj_layers or {}).items():
+                if name not in ("q", "k", "v", "out"):
+                    raise ValueError(f"unknown LoRA projection '{name}'")
+                setattr(self, f"to_{name}_lora", LoraDoraLinear(layer, "default", r=lora_rank, lora_alpha=lora_alpha,
+                                                                use_dora=lora_uses_dora, lora_dropout=0.1))
+
+    def reset_attn_cache_and_flags(self, capture_ca_activations, normalize_cross_attn, mix_attn_mats_in_batch, enable_lora):
+        """dalc:184-190."""
+        self.capture_ca_activations = capture_ca_activations
+        self.normalize_cross_attn = normalize_cross_attn
+        self.mix_attn_mats_in_batch = mix_attn_mats_in_batch
+        self.cached_activations = {}
+        self.enable_lora = enable_lora and self.global_enable_lora
+
+    def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
+                 attention_mask: Optional[torch.Tensor] = None, temb: Optional[torch.Tensor] = None,
+                 img_mask: Optional[torch.Tensor] = None,
+                 subj_indices: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, debug: bool = False, *args,
+                 **kwargs) -> torch.Tensor:
+        for name in ("spatial_norm", "group_norm", "norm_cross", "norm_q", "norm_k"):
+            if getattr(attn, name, None) is not None:
+                raise NotImplementedError(f"attn.{name} is None for every SD-1.5 attention (dalc:211-233); got a module")
+        if attention_mask is not None:
+            raise NotImplementedError("attention_mask is None at every reference call site (SURVEY 8c); use img_mask")
+        if not hidden_states.is_cuda:
+            raise RuntimeError("adaface_b200 AttnProcessor_LoRA_Capture runs on CUDA only (no CPU fallback)")
+
+        residual = hidden_states
+        in_dtype = hidden_states.dtype
+        input_ndim = hidden_states.ndim
+        if input_ndim == 4:                                                          # dalc:217-220
+            bsz, channel, height, width = hidden_states.shape
+            hidden_states = hidden_states.view(bsz, channel, height * width).transpose(1, 2)
+        B, N, C_in = hidden_states.shape
+        H = attn.heads
+        x = hidden_states.to(torch.bfloat16).contiguous()
+        x2d = x.view(B * N, C_in)
+        pk = _bf16_pack(attn)
+        lora = (lambda n: getattr(self, f"to_{n}_lora")) if self.enable_lora else (lambda n: None)
+        is_cross = encoder_hidden_states is not None
+        C = pk["wq"].shape[0]
+        d = C // H
+        sm_scale = 1.0 / math.sqrt(d)
+
+        if not is_cross:
+            # ---- self-attention: one fused QKV GEMM unless a LoRA adapter splits it
+            key_mask = img_mask_to_key_mask(img_mask, N) if img_mask is not None else None
+            if lora("q") is None and lora("k") is None and lora("v") is None and "wqkv" in pk:
+                qkv = ops.proj(x2d, pk["wqkv"], bias=pk["bqkv"]).view(B, N, 3 * C)
+                q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+            else:
+                q = ops.proj(x2d, pk["wq"], bias=pk["bq"]).view(B, N, C)
+                if lora("q") is not None and self.q_lora_updates_query:
+                    q = _linear(x2d, pk["wq"], pk["bq"], lora("q")).view(B, N, C)
+                k = _linear(x2d, pk["wk"], pk["bk"], lora("k")).view(B, N, C)
+                v = _linear(x2d, pk["wv"], pk["bv"], lora("v")).view(B, N, C)
+            o = ops.attention(q, k, v, H, sm_scale, key_mask=key_mask)
+            q2 = q
+        else:
+            ctx = encoder_hidden_states.to(torch.bfloat16).contiguous()
+            S = ctx.shape[1]
+            c2d = ctx.view(B * S, ctx.shape[2])
+            q = ops.proj(x2d, pk["wq"], bias=pk["bq"]).view(B, N, C)                 # dalc:235
+            q2 = q
+            if lora("q") is not None:                                                # dalc:239-249
+                q2 = _linear(x2d, pk["wq"], pk["bq"], lora("q")).view(B, N, C)
+                if self.q_lora_updates_query:
+                    q = q2
+            if lora("k") is None and lora("v") is None:
+                kv = ops.proj(c2d, pk["wkv"], bias=pk["bkv"]).view(B, S, 2 * C)
+                k, v = kv[:, :, :C], kv[:, :, C:]
+            else:
+                k = _linear(c2d, pk["wk"], pk["bk"], lora("k")).view(B, S, C)        # dalc:280-283
+                v = _linear(c2d, pk["wv"], pk["bv"], lora("v")).view(B, S, C)        # dalc:285-288
+            if self.capture_ca_activations or self.normalize_cross_attn:            # dalc:309-315
+                col_flag = qm = subj_cols = None
+                mix = bool(self.mix_attn_mats_in_batch)
+                if mix and B % 2:
+                    raise ValueError("mix_attn_mats_in_batch needs an even batch ordered [sc.., mc..] (dalc:113)")
+                if self.normalize_cross_attn and not mix:
+                    if subj_indices is None:
+                        raise ValueError("normalize_cross_attn=True requires subj_indices (dalc:120)")
+                    ib, in_ = subj_indices
+                    col_flag = torch.zeros((B, S), device=x.device, dtype=torch.uint8)
+                    col_flag[ib.long(), in_.long()] = 1
+                    qm = ops.qmean(q)
+                if self.capture_subj_cols_only and subj_indices is not None:
+                    ib, in_ = subj_indices
+                    n_sub = int(ib.numel() // B)
+                    subj_cols = torch.full((B, n_sub), -1, device=x.device, dtype=torch.int32)
+                    subj_cols[ib.long(), torch.arange(ib.numel(), device=x.device) % n_sub] = in_.to(torch.int32)
+                cap = bool(self.capture_ca_activations)
+                o, prob, score, prob_subj = ops.attention_cross_capture(
+                    q, k, v, H, sm_scale, want_prob=cap, want_score=cap, col_flag=col_flag, qmean=qm,
+                    ca_scale=self.cross_attn_scale_factor.detach().float().reshape(1), mix=mix, subj_cols=subj_cols)
+            else:                                                                    # dalc:320-322
+                o = ops.attention(q, k, v, H, sm_scale)
+                prob = score = prob_subj = None
+
+        out = _linear(o.view(B * N, C), pk["wo"], pk["bo"], lora("out")).view(B, N, -1)   # dalc:328-334
+        hidden_out = out.to(in_dtype)
+        if input_ndim == 4:
+            hidden_out = hidden_out.transpose(-1, -2).reshape(bsz, channel, height, width)
+        if getattr(attn, "residual_connection", False):
+            hidden_out = hidden_out + residual
+        rescale = getattr(attn, "rescale_output_factor", 1.0)
+        if rescale != 1.0:
+            hidden_out = hidden_out / rescale
+
+        if is_cross and self.capture_ca_activations:                                 # dalc:344-362
+            f = math.sqrt(1.0 / math.sqrt(C))     # quirk 1: the scale is taken before the head split => C^-1/4
+            ca = self.cached_activations
+            ca["q"] = ops.chan_major(q, f)
+            ca["q2"] = ca["q"] if q2 is q else ops.chan_major(q2, f)
+            ca["k"] = ops.chan_major(k, f)
+            ca["v"] = ops.chan_major(v, f)
+            ca["attn"], ca["attnscore"] = prob, score
+            ca["attn_out"] = ops.chan_major(out, 1.0) if (input_ndim == 3 and rescale == 1.0 and not getattr(
+                attn, "residual_connection", False)) else hidden_out.float().permute(0, 2, 1).contiguous()
+            if prob_subj is not None:
+                ca["attn_subj"] = prob_subj
+        return hidden_out
+
+    forward = __call__

@@ -1,0 +1,575 @@
+// K2 / K3: flash-style attention on warp-level tensor-core MMA (mma.sync m16n8k16, bf16 -> fp32).
+//
+//  * attn_fwd_kernel<D>: online-softmax attention for SD-1.5 head dims 40/80/160 (+64 for the CLIP-shaped
+//    encoder): self-attention with the optional img_mask key mask (dalc:254-273), fast cross-attention
+//    (dalc:321) and CLIPAttentionMKV's causal multi-K/V attention (arc2face_models.py:170-217).
+//  * attn_cross_capture_kernel<D>: the slow SDPA of dalc:79-139 -- all S <= 128 context keys staged once in
+//    shared memory (cross-attention is HBM-bound), score edits (normalize / mix), exact softmax, optional
+//    probability / score / subject-column capture written with fully coalesced stores.
+//
+// Head dim 40 is padded to 48 only in shared memory (zero columns); HBM layouts stay those of the
+// reference: [B, L, H*d] with heads interleaved.
+#include <math.h>
+
+#include "common.cuh"
+#include "../../include/adaface_b200.h"
+
+namespace adaface {
+
+extern long long g_launch_count;
+
+constexpr int ATT_BM = 64;       // queries per CTA (4 warps x 16 rows)
+constexpr int ATT_BN = 64;       // keys per pipeline stage
+constexpr int ATT_THREADS = 128;
+constexpr float LOG2E = 1.4426950408889634f;
+
+template <int D>
+struct AttDims {
+  static constexpr int DP = (D + 15) / 16 * 16;   // MMA-K padded head dim
+  static constexpr int LD = DP + 8;               // smem row pitch (elements): conflict-free ldmatrix
+  static constexpr int KT = DP / 16;              // k16 steps of Q.K^T
+  static constexpr int NT_O = D / 8;              // n8 tiles of the output
+  static constexpr int CH = D / 8;                // 16-byte chunks per row in HBM
+};
+
+struct AttnParams {
+  const bf16 *q, *k, *v;
+  bf16* o;
+  long long q_sb, q_sn, k_sb, k_sn, v_sb, v_sn, o_sb, o_sn;
+  int B, H, Lq, Lk;
+  const uint8_t* key_mask;
+  int causal_mult;
+  float scale_log2;
+};
+
+// rows [row0, row0+rows) of a [L, H*d] head slice -> smem tile (zero fill beyond L)
+// mult > 1: row j is sub-key (j % mult) of token (j / mult), the sub-keys of a token being `sub` elements apart.
+template <int D>
+__device__ __forceinline__ void load_rows(bf16* s, const bf16* g, long long stride_n, int row0, int L, int rows,
+                                          int mult = 1, int sub = 0) {
+  constexpr int CH = AttDims<D>::CH, LD = AttDims<D>::LD;
+  for (int c = threadIdx.x; c < rows * CH; c += blockDim.x) {
+    const int r = c / CH, ch = c - r * CH;
+    const int gr = row0 + r;
+    const bool ok = gr < L;
+    const int j = ok ? gr : 0;
+    const long long off = mult > 1 ? (long long)(j / mult) * stride_n + (long long)(j % mult) * sub : (long long)j * stride_n;
+    cp_async_16(s + r * LD + ch * 8, g + off + ch * 8, ok);
+  }
+}
+template <int D>
+__device__ __forceinline__ void zero_pad_cols(bf16* s, int rows) {
+  constexpr int DP = AttDims<D>::DP, LD = AttDims<D>::LD;
+  if (DP == D) return;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x)
+    *reinterpret_cast<uint4*>(s + r * LD + D) = make_uint4(0, 0, 0, 0);   // DP - D == 8 elements
+}
+
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams p) {
+  using A = AttDims<D>;
+  constexpr int LD = A::LD, KT = A::KT, NT_O = A::NT_O, NT_S = ATT_BN / 8;
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_att);
+  bf16* sK = sQ + ATT_BM * LD;                // [2][BN][LD]
+  bf16* sV = sK + 2 * ATT_BN * LD;            // [2][BN][LD]
+  uint8_t* sValid = reinterpret_cast<uint8_t*>(sV + 2 * ATT_BN * LD);   // [2][BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = blockIdx.x * ATT_BM, h = blockIdx.y, b = blockIdx.z;
+  const bf16* gq = p.q + (long long)b * p.q_sb + h * D;
+  const bf16* gk = p.k + (long long)b * p.k_sb + h * D;
+  const bf16* gv = p.v + (long long)b * p.v_sb + h * D;
+
+  int n_tiles = (p.Lk + ATT_BN - 1) / ATT_BN;
+  if (p.causal_mult > 0) {
+    const long long last_key = (long long)min(p.Lq, m0 + ATT_BM) * p.causal_mult;   // exclusive
+    n_tiles = min(n_tiles, (int)((last_key + ATT_BN - 1) / ATT_BN));
+  }
+
+  auto load_kv = [&](int tile, int buf) {
+    load_rows<D>(sK + buf * ATT_BN * LD, gk, p.k_sn, tile * ATT_BN, p.Lk, ATT_BN, p.causal_mult, p.H * D);
+    load_rows<D>(sV + buf * ATT_BN * LD, gv, p.v_sn, tile * ATT_BN, p.Lk, ATT_BN, p.causal_mult, p.H * D);
+    if (threadIdx.x < ATT_BN) {
+      const int j = tile * ATT_BN + threadIdx.x;
+      uint8_t ok = j < p.Lk;
+      if (ok && p.key_mask) ok = p.key_mask[(long long)b * p.Lk + j] != 0;
+      sValid[buf * ATT_BN + threadIdx.x] = ok;
+    }
+  };
+
+  zero_pad_cols<D>(sQ, ATT_BM);
+  zero_pad_cols<D>(sK, 2 * ATT_BN);
+  load_rows<D>(sQ, gq, p.q_sn, m0, p.Lq, ATT_BM);
+  load_kv(0, 0);
+  cp_async_commit();
+
+  uint32_t qf[KT][4];
+  float acc_o[NT_O][4];
+#pragma unroll
+  for (int i = 0; i < NT_O; ++i) acc_o[i][0] = acc_o[i][1] = acc_o[i][2] = acc_o[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const int r_lo = m0 + warp * 16 + g;   // query row of c0/c1; c2/c3 belong to r_lo + 8
+
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int buf = tile & 1;
+    if (tile + 1 < n_tiles) {
+      load_kv(tile + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (tile == 0) {
+#pragma unroll
+      for (int kk = 0; kk < KT; ++kk)
+        ldsm_x4(smem_u32(sQ + (warp * 16 + (lane & 15)) * LD + kk * 16 + (lane >> 4) * 8), qf[kk][0], qf[kk][1],
+                qf[kk][2], qf[kk][3]);
+    }
+    const bf16* tK = sK + buf * ATT_BN * LD;
+    const bf16* tV = sV + buf * ATT_BN * LD;
+    const uint8_t* tValid = sValid + buf * ATT_BN;
+
+    float acc_s[NT_S][4];
+#pragma unroll
+    for (int i = 0; i < NT_S; ++i) acc_s[i][0] = acc_s[i][1] = acc_s[i][2] = acc_s[i][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) {
+#pragma unroll
+      for (int np = 0; np < NT_S / 2; ++np) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(smem_u32(tK + (np * 16 + (lane >> 4) * 8 + (lane & 7)) * LD + kk * 16 + ((lane >> 3) & 1) * 8), b0, b1,
+                b2, b3);
+        mma_bf16_16816(acc_s[2 * np], qf[kk], b0, b1);
+        mma_bf16_16816(acc_s[2 * np + 1], qf[kk], b2, b3);
+      }
+    }
+    // scale + masks, running max
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < NT_S; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int cl = nt * 8 + 2 * t + (e & 1);
+        const int r = r_lo + (e >> 1) * 8;
+        bool ok = tValid[cl] != 0;
+        if (p.causal_mult > 0) ok = ok && ((long long)(tile * ATT_BN + cl) < (long long)(r + 1) * p.causal_mult);
+        const float s = ok ? acc_s[nt][e] * p.scale_log2 : -INFINITY;
+        acc_s[nt][e] = s;
+        mx[e >> 1] = fmaxf(mx[e >> 1], s);
+      }
+    }
+    float corr[2], m_use[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
+      mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
+      const float m_new = fmaxf(m_run[i], mx[i]);
+      m_use[i] = (m_new == -INFINITY) ? 0.f : m_new;
+      corr[i] = fast_exp2(m_run[i] - m_use[i]);   // m_run = -inf -> 0
+      m_run[i] = m_new;
+      l_run[i] *= corr[i];
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT_S; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pv = fast_exp2(acc_s[nt][e] - m_use[e >> 1]);
+        acc_s[nt][e] = pv;
+        l_run[e >> 1] += pv;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NT_O; ++i) {
+      acc_o[i][0] *= corr[0];
+      acc_o[i][1] *= corr[0];
+      acc_o[i][2] *= corr[1];
+      acc_o[i][3] *= corr[1];
+    }
+    // O += P V
+#pragma unroll
+    for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+      uint32_t a[4];
+      a[0] = pack_bf16(acc_s[2 * kk][0], acc_s[2 * kk][1]);
+      a[1] = pack_bf16(acc_s[2 * kk][2], acc_s[2 * kk][3]);
+      a[2] = pack_bf16(acc_s[2 * kk + 1][0], acc_s[2 * kk + 1][1]);
+      a[3] = pack_bf16(acc_s[2 * kk + 1][2], acc_s[2 * kk + 1][3]);
+      const bf16* vrow = tV + (kk * 16 + (lane & 15)) * LD;
+#pragma unroll
+      for (int nt = 0; nt + 1 < NT_O; nt += 2) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_trans(smem_u32(vrow + nt * 8 + (lane >> 4) * 8), b0, b1, b2, b3);
+        mma_bf16_16816(acc_o[nt], a, b0, b1);
+        mma_bf16_16816(acc_o[nt + 1], a, b2, b3);
+      }
+      if (NT_O & 1) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(smem_u32(vrow + (NT_O - 1) * 8), b0, b1);
+        mma_bf16_16816(acc_o[NT_O - 1], a, b0, b1);
+      }
+    }
+    __syncthreads();   // everyone done with `buf` before the next iteration's prefetch overwrites it
+  }
+
+  // finalize: O / l, stage through this warp's rows of sQ, coalesced 16-byte stores
+  float inv[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float l = l_run[i];
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    inv[i] = l > 0.f ? 1.f / l : 0.f;
+  }
+  bf16* sO = sQ + warp * 16 * LD;
+  __syncwarp();
+#pragma unroll
+  for (int nt = 0; nt < NT_O; ++nt) {
+    *reinterpret_cast<uint32_t*>(sO + g * LD + nt * 8 + 2 * t) = pack_bf16(acc_o[nt][0] * inv[0], acc_o[nt][1] * inv[0]);
+    *reinterpret_cast<uint32_t*>(sO + (g + 8) * LD + nt * 8 + 2 * t) =
+        pack_bf16(acc_o[nt][2] * inv[1], acc_o[nt][3] * inv[1]);
+  }
+  __syncwarp();
+  bf16* go = p.o + (long long)b * p.o_sb + h * D;
+  for (int c = lane; c < 16 * A::CH; c += 32) {
+    const int r = c / A::CH, ch = c - r * A::CH;
+    const int gr = m0 + warp * 16 + r;
+    if (gr < p.Lq) *reinterpret_cast<uint4*>(go + (long long)gr * p.o_sn + ch * 8) = *reinterpret_cast<const uint4*>(sO + r * LD + ch * 8);
+  }
+}
+
+template <int D>
+static int launch_attn(const AttnParams& p, cudaStream_t stream) {
+  using A = AttDims<D>;
+  constexpr int smem = (ATT_BM + 4 * ATT_BN) * A::LD * 2 + 2 * ATT_BN;
+  static bool configured = false;
+  if (!configured) {
+    AF_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid((p.Lq + ATT_BM - 1) / ATT_BM, p.H, p.B);
+  attn_fwd_kernel<D><<<grid, ATT_THREADS, smem, stream>>>(p);
+  AF_CUDA(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+static int check_view(const char* what, const void* ptr, int64_t sb, int64_t sn, int64_t d) {
+  AF_CHECK(ptr != nullptr, "attention: null %s", what);
+  AF_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && sb % 8 == 0 && sn % 8 == 0 && d % 8 == 0,
+           "attention: %s must be 16-byte aligned with strides / head dim multiples of 8 (sb=%lld sn=%lld d=%lld)", what,
+           (long long)sb, (long long)sn, (long long)d);
+  return 0;
+}
+
+int attn_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn, const void* v,
+             int64_t v_sb, int64_t v_sn, void* o, int64_t o_sb, int64_t o_sn, int64_t B, int64_t H, int64_t Lq,
+             int64_t Lk, int64_t d, const uint8_t* key_mask, int causal_mult, float scale, cudaStream_t stream) {
+  if (check_view("q", q, q_sb, q_sn, d) || check_view("k", k, k_sb, k_sn, d) || check_view("v", v, v_sb, v_sn, d) ||
+      check_view("o", o, o_sb, o_sn, d))
+    return 1;
+  AF_CHECK(B > 0 && H > 0 && Lq > 0 && Lk > 0, "attn_fwd: empty problem B=%lld H=%lld Lq=%lld Lk=%lld", (long long)B,
+           (long long)H, (long long)Lq, (long long)Lk);
+  AF_CHECK(B <= 65535 && H <= 65535, "attn_fwd: B/H exceed grid limits");
+  AF_CHECK(causal_mult >= 0, "attn_fwd: causal_mult must be >= 0");
+  AttnParams p;
+  p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.o = (bf16*)o;
+  p.q_sb = q_sb; p.q_sn = q_sn; p.k_sb = k_sb; p.k_sn = k_sn; p.v_sb = v_sb; p.v_sn = v_sn; p.o_sb = o_sb; p.o_sn = o_sn;
+  p.B = (int)B; p.H = (int)H; p.Lq = (int)Lq; p.Lk = (int)Lk;
+  p.key_mask = key_mask;
+  p.causal_mult = causal_mult;
+  p.scale_log2 = scale * LOG2E;
+  switch (d) {
+    case 40: return launch_attn<40>(p, stream);
+    case 64: return launch_attn<64>(p, stream);
+    case 80: return launch_attn<80>(p, stream);
+    case 160: return launch_attn<160>(p, stream);
+  }
+  set_error("attn_fwd: unsupported head dim %lld (supported: 40, 64, 80, 160)", (long long)d);
+  return 1;
+}
+
+// =============================================================================================
+// K3: cross-attention with capture / normalize / mix.
+constexpr int CAP_BN = 128;   // max context keys
+
+struct CapParams {
+  const bf16 *q, *k, *v;
+  bf16* o;
+  long long q_sb, q_sn, k_sb, k_sn, v_sb, v_sn, o_sb, o_sn;
+  int B, H, Lq, S;
+  float scale;
+  float* prob;
+  float* score;
+  float* prob_subj;
+  const int32_t* subj_cols;
+  int n_subj;
+  const uint8_t* col_flag;
+  const float* qmean;   // [B, H*d]
+  const float* ca_scale;   // device scalar (cross_attn_scale_factor) or null = 1
+  int mix;
+};
+
+template <int D, bool MIX>
+__global__ void __launch_bounds__(ATT_THREADS) attn_cross_capture_kernel(const CapParams p) {
+  using A = AttDims<D>;
+  constexpr int LD = A::LD, KT = A::KT, NT_O = A::NT_O, NT_S = CAP_BN / 8, NI = MIX ? 2 : 1;
+  extern __shared__ __align__(16) uint8_t smem_cap[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_cap);          // [NI][BM][LD]
+  bf16* sK = sQ + NI * ATT_BM * LD;                      // [NI][CAP_BN][LD]
+  bf16* sV = sK + NI * CAP_BN * LD;                      // [NI][CAP_BN][LD]
+  float* sStage = reinterpret_cast<float*>(sV + NI * CAP_BN * LD);   // [4 warps][16][S] (packed rows)
+  float* sColMean = sStage + 4 * 16 * CAP_BN;            // [CAP_BN]
+  uint8_t* sFlag = reinterpret_cast<uint8_t*>(sColMean + CAP_BN);    // [CAP_BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = blockIdx.x * ATT_BM, h = blockIdx.y, b0 = blockIdx.z;
+  const int S = p.S;
+  const int nts = (S + 7) / 8;               // n8 tiles that hold real keys
+  const int half = p.B / 2;
+
+  zero_pad_cols<D>(sQ, NI * ATT_BM);
+  zero_pad_cols<D>(sK, NI * CAP_BN);
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int b = b0 + i * half;
+    load_rows<D>(sQ + i * ATT_BM * LD, p.q + (long long)b * p.q_sb + h * D, p.q_sn, m0, p.Lq, ATT_BM);
+    load_rows<D>(sK + i * CAP_BN * LD, p.k + (long long)b * p.k_sb + h * D, p.k_sn, 0, S, CAP_BN);
+    load_rows<D>(sV + i * CAP_BN * LD, p.v + (long long)b * p.v_sb + h * D, p.v_sn, 0, S, CAP_BN);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // normalize: per-column mean over the queries = scale * qmean . k_j  (dalc:123-126)
+  if (threadIdx.x < CAP_BN) {
+    const int j = threadIdx.x;
+    float cm = 0.f;
+    uint8_t fl = 0;
+    if (!MIX && p.col_flag && j < S && p.col_flag[(long long)b0 * S + j]) {
+      fl = 1;
+      const float* qm = p.qmean + ((long long)b0 * p.H + h) * D;
+      const bf16* kr = sK + j * LD;
+#pragma unroll 8
+      for (int dd = 0; dd < D; ++dd) cm += qm[dd] * __bfloat162float(kr[dd]);
+      cm *= p.scale;
+    }
+    sColMean[j] = cm;
+    sFlag[j] = fl;
+  }
+  __syncthreads();
+
+  // ---- scores
+  float acc_s[NT_S][4];
+#pragma unroll
+  for (int i = 0; i < NT_S; ++i) acc_s[i][0] = acc_s[i][1] = acc_s[i][2] = acc_s[i][3] = 0.f;
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) {
+      uint32_t qf[4];
+      ldsm_x4(smem_u32(sQ + i * ATT_BM * LD + (warp * 16 + (lane & 15)) * LD + kk * 16 + (lane >> 4) * 8), qf[0], qf[1],
+              qf[2], qf[3]);
+#pragma unroll
+      for (int np = 0; np < NT_S / 2; ++np) {
+        if (2 * np < nts) {
+          uint32_t r0, r1, r2, r3;
+          ldsm_x4(smem_u32(sK + i * CAP_BN * LD + (np * 16 + (lane >> 4) * 8 + (lane & 7)) * LD + kk * 16 +
+                           ((lane >> 3) & 1) * 8),
+                  r0, r1, r2, r3);
+          mma_bf16_16816(acc_s[2 * np], qf, r0, r1);
+          mma_bf16_16816(acc_s[2 * np + 1], qf, r2, r3);
+        }
+      }
+    }
+  }
+  const float sc = MIX ? 0.5f * p.scale : p.scale;   // (score_sc + score_mc) / 2, dalc:117
+  const float ca_scale = p.ca_scale ? __ldg(p.ca_scale) : 1.f;
+  float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int nt = 0; nt < NT_S; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = nt * 8 + 2 * t + (e & 1);
+      float s = -INFINITY;
+      if (c < S) {
+        s = acc_s[nt][e] * sc;
+        if (sFlag[c]) s = (s - sColMean[c]) * ca_scale;   // dalc:126-130
+      }
+      acc_s[nt][e] = s;
+      mx[e >> 1] = fmaxf(mx[e >> 1], s);
+    }
+  }
+
+  const int row0 = m0 + warp * 16;
+  const int nrows = max(0, min(16, p.Lq - row0));
+  float* st = sStage + warp * 16 * CAP_BN;
+  auto stage_and_store = [&](float* gbase, bool with_subj) {
+    // registers -> smem [16][S] -> one contiguous, fully coalesced global write per instance
+    __syncwarp();
+#pragma unroll
+    for (int nt = 0; nt < NT_S; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = nt * 8 + 2 * t + (e & 1);
+        if (c < S) st[(g + (e >> 1) * 8) * S + c] = acc_s[nt][e];
+      }
+    }
+    __syncwarp();
+    for (int i = 0; i < NI; ++i) {
+      const int b = b0 + i * half;
+      if (gbase) {
+        float* dst = gbase + (((long long)b * p.H + h) * p.Lq + row0) * S;
+        for (int x = lane; x < nrows * S; x += 32) dst[x] = st[x];
+      }
+      if (with_subj && p.prob_subj) {
+        float* dst = p.prob_subj + (((long long)b * p.H + h) * p.Lq + row0) * p.n_subj;
+        const int32_t* cols = p.subj_cols + (long long)b * p.n_subj;
+        for (int x = lane; x < nrows * p.n_subj; x += 32) {
+          const int r = x / p.n_subj, jj = x - r * p.n_subj;
+          const int c = cols[jj];
+          dst[x] = (c >= 0 && c < S) ? st[r * S + c] : 0.f;
+        }
+      }
+    }
+  };
+  if (p.score) stage_and_store(p.score, false);   // edited score (dalc:139, quirk 3)
+
+  // ---- exact softmax over the S keys
+  float inv[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
+    mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
+  }
+  float sum[2] = {0.f, 0.f};
+#pragma unroll
+  for (int nt = 0; nt < NT_S; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float pv = exp2f((acc_s[nt][e] - mx[e >> 1]) * LOG2E);
+      acc_s[nt][e] = pv;
+      sum[e >> 1] += pv;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 1);
+    sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 2);
+    inv[i] = 1.f / sum[i];
+  }
+#pragma unroll
+  for (int nt = 0; nt < NT_S; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc_s[nt][e] *= inv[e >> 1];
+  }
+  if (p.prob || p.prob_subj) stage_and_store(p.prob, true);
+
+  // ---- O = P V per instance
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    float acc_o[NT_O][4];
+#pragma unroll
+    for (int x = 0; x < NT_O; ++x) acc_o[x][0] = acc_o[x][1] = acc_o[x][2] = acc_o[x][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < CAP_BN / 16; ++kk) {
+      if (2 * kk < nts) {
+        uint32_t a[4];
+        a[0] = pack_bf16(acc_s[2 * kk][0], acc_s[2 * kk][1]);
+        a[1] = pack_bf16(acc_s[2 * kk][2], acc_s[2 * kk][3]);
+        a[2] = pack_bf16(acc_s[2 * kk + 1][0], acc_s[2 * kk + 1][1]);
+        a[3] = pack_bf16(acc_s[2 * kk + 1][2], acc_s[2 * kk + 1][3]);
+        const bf16* vrow = sV + i * CAP_BN * LD + (kk * 16 + (lane & 15)) * LD;
+#pragma unroll
+        for (int nt = 0; nt + 1 < NT_O; nt += 2) {
+          uint32_t r0, r1, r2, r3;
+          ldsm_x4_trans(smem_u32(vrow + nt * 8 + (lane >> 4) * 8), r0, r1, r2, r3);
+          mma_bf16_16816(acc_o[nt], a, r0, r1);
+          mma_bf16_16816(acc_o[nt + 1], a, r2, r3);
+        }
+        if (NT_O & 1) {
+          uint32_t r0, r1;
+          ldsm_x2_trans(smem_u32(vrow + (NT_O - 1) * 8), r0, r1);
+          mma_bf16_16816(acc_o[NT_O - 1], a, r0, r1);
+        }
+      }
+    }
+    bf16* sO = sQ + i * ATT_BM * LD + warp * 16 * LD;   // this warp's own Q rows: no longer needed
+    __syncwarp();
+#pragma unroll
+    for (int nt = 0; nt < NT_O; ++nt) {
+      *reinterpret_cast<uint32_t*>(sO + g * LD + nt * 8 + 2 * t) = pack_bf16(acc_o[nt][0], acc_o[nt][1]);
+      *reinterpret_cast<uint32_t*>(sO + (g + 8) * LD + nt * 8 + 2 * t) = pack_bf16(acc_o[nt][2], acc_o[nt][3]);
+    }
+    __syncwarp();
+    const int b = b0 + i * half;
+    bf16* go = p.o + (long long)b * p.o_sb + h * D;
+    for (int c = lane; c < nrows * A::CH; c += 32) {
+      const int r = c / A::CH, ch = c - r * A::CH;
+      *reinterpret_cast<uint4*>(go + (long long)(row0 + r) * p.o_sn + ch * 8) =
+          *reinterpret_cast<const uint4*>(sO + r * LD + ch * 8);
+    }
+  }
+}
+
+template <int D, bool MIX>
+static int launch_cap(const CapParams& p, cudaStream_t stream) {
+  using A = AttDims<D>;
+  constexpr int NI = MIX ? 2 : 1;
+  constexpr int smem = NI * (ATT_BM + 2 * CAP_BN) * A::LD * 2 + 4 * 16 * CAP_BN * 4 + CAP_BN * 4 + CAP_BN;
+  static_assert(smem <= 227 * 1024, "capture kernel shared memory exceeds the SM");
+  static bool configured = false;
+  if (!configured) {
+    AF_CUDA(cudaFuncSetAttribute(attn_cross_capture_kernel<D, MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid((p.Lq + ATT_BM - 1) / ATT_BM, p.H, MIX ? p.B / 2 : p.B);
+  attn_cross_capture_kernel<D, MIX><<<grid, ATT_THREADS, smem, stream>>>(p);
+  AF_CUDA(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+int attn_cross_capture_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn,
+                           const void* v, int64_t v_sb, int64_t v_sn, void* o, int64_t o_sb, int64_t o_sn, int64_t B,
+                           int64_t H, int64_t Lq, int64_t S, int64_t d, float scale, float* prob, float* score,
+                           float* prob_subj, const int32_t* subj_cols, int64_t n_subj, const uint8_t* col_flag,
+                           const float* qmean, const float* ca_scale, int mix, cudaStream_t stream) {
+  if (check_view("q", q, q_sb, q_sn, d) || check_view("k", k, k_sb, k_sn, d) || check_view("v", v, v_sb, v_sn, d) ||
+      check_view("o", o, o_sb, o_sn, d))
+    return 1;
+  AF_CHECK(B > 0 && H > 0 && Lq > 0 && S > 0, "attn_cross_capture_fwd: empty problem");
+  AF_CHECK(S <= CAP_BN, "attn_cross_capture_fwd: context length %lld exceeds %d keys", (long long)S, CAP_BN);
+  AF_CHECK(B <= 65535 && H <= 65535, "attn_cross_capture_fwd: B/H exceed grid limits");
+  AF_CHECK(!(mix && (B % 2)), "mix_attn_mats_in_batch needs an even batch [sc.., mc..] (dalc:113), got B=%lld",
+           (long long)B);
+  AF_CHECK(!(mix && col_flag), "normalize and mix are mutually exclusive (dalc:108-119: mix wins)");
+  AF_CHECK(!(col_flag && !qmean), "normalize_cross_attn needs qmean (and subj_indices, dalc:120)");
+  AF_CHECK(!(prob_subj && (!subj_cols || n_subj <= 0)), "prob_subj needs subj_cols / n_subj");
+  CapParams p;
+  p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.o = (bf16*)o;
+  p.q_sb = q_sb; p.q_sn = q_sn; p.k_sb = k_sb; p.k_sn = k_sn; p.v_sb = v_sb; p.v_sn = v_sn; p.o_sb = o_sb; p.o_sn = o_sn;
+  p.B = (int)B; p.H = (int)H; p.Lq = (int)Lq; p.S = (int)S;
+  p.scale = scale;
+  p.prob = prob; p.score = score; p.prob_subj = prob_subj; p.subj_cols = subj_cols; p.n_subj = (int)n_subj;
+  p.col_flag = col_flag; p.qmean = qmean; p.ca_scale = ca_scale; p.mix = mix;
+  if (mix) {
+    switch (d) {
+      case 40: return launch_cap<40, true>(p, stream);
+      case 80: return launch_cap<80, true>(p, stream);
+    }
+    set_error("attn_cross_capture_fwd: mix supports head dims 40 and 80, got %lld", (long long)d);
+    return 1;
+  }
+  switch (d) {
+    case 40: return launch_cap<40, false>(p, stream);
+    case 80: return launch_cap<80, false>(p, stream);
+    case 160: return launch_cap<160, false>(p, stream);
+  }
+  set_error("attn_cross_capture_fwd: unsupported head dim %lld (supported: 40, 80, 160)", (long long)d);
+  return 1;
+}
+
+}  // namespace adaface

@@ -1,0 +1,131 @@
+// C-ABI entry points of libadaface_b200.so (declared in include/adaface_b200.h) + host-side helpers.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "../../include/adaface_b200.h"
+
+namespace adaface {
+
+long long g_launch_count = 0;
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// cuTensorMapEncodeTiled is resolved through the runtime so that the library has no link-time
+// dependency on libcuda.so (it must load on a machine without a driver for the symbol-export test).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return 1;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%llu cols=%llu ld=%llu box_rows=%u", (int)r, base,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+    return 1;
+  }
+  return 0;
+}
+
+int proj_lora_fwd(const void*, int64_t, const void*, const void*, int64_t, const void*, const float*, const float*,
+                  const void*, int64_t, int, void*, int64_t, int, int64_t, int64_t, int64_t, int64_t, int, cudaStream_t);
+int attn_fwd(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t, int64_t, void*, int64_t,
+             int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, const uint8_t*, int, float, cudaStream_t);
+int attn_cross_capture_fwd(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t, int64_t,
+                           void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, float, float*, float*,
+                           float*, const int32_t*, int64_t, const uint8_t*, const float*, const float*, int, cudaStream_t);
+int qmean(const void*, int64_t, int64_t, int64_t, int64_t, int64_t, float*, cudaStream_t);
+int capture_chan_major(const void*, int, int64_t, int64_t, int64_t, int64_t, int64_t, float, float*, cudaStream_t);
+int layernorm_fwd(const void*, int, int64_t, const float*, const float*, void*, int, int64_t, int64_t, int64_t, float,
+                  cudaStream_t);
+int sbg_head_fwd(const float*, const float*, const float*, const float*, const float*, int, int64_t, const float*,
+                 const float*, float*, int64_t, int64_t, int64_t, float, cudaStream_t);
+
+}  // namespace adaface
+
+using namespace adaface;
+
+extern "C" {
+
+int adaface_version(void) { return ADAFACE_B200_ABI_VERSION; }
+const char* adaface_last_error(void) { return g_err; }
+int64_t adaface_launch_count(void) { return g_launch_count; }
+
+int adaface_proj_lora_fwd(const void* x, int64_t ldx, const void* w, const void* t, int64_t ldt, const void* bs,
+                          const float* colscale, const float* bias, const void* residual, int64_t ldr,
+                          int residual_dtype, void* y, int64_t ldy, int y_dtype, int64_t M, int64_t N, int64_t K,
+                          int64_t R, int act, void* stream) {
+  return proj_lora_fwd(x, ldx, w, t, ldt, bs, colscale, bias, residual, ldr, residual_dtype, y, ldy, y_dtype, M, N, K, R,
+                       act, (cudaStream_t)stream);
+}
+
+int adaface_attn_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn,
+                     const void* v, int64_t v_sb, int64_t v_sn, void* o, int64_t o_sb, int64_t o_sn, int64_t B,
+                     int64_t H, int64_t Lq, int64_t Lk, int64_t d, const uint8_t* key_mask, int causal_mult,
+                     float scale, void* stream) {
+  return attn_fwd(q, q_sb, q_sn, k, k_sb, k_sn, v, v_sb, v_sn, o, o_sb, o_sn, B, H, Lq, Lk, d, key_mask, causal_mult,
+                  scale, (cudaStream_t)stream);
+}
+
+int adaface_attn_cross_capture_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb,
+                                   int64_t k_sn, const void* v, int64_t v_sb, int64_t v_sn, void* o, int64_t o_sb,
+                                   int64_t o_sn, int64_t B, int64_t H, int64_t Lq, int64_t S, int64_t d, float scale,
+                                   float* prob, float* score, float* prob_subj, const int32_t* subj_cols,
+                                   int64_t n_subj, const uint8_t* col_flag, const float* qmean_,
+                                   const float* ca_scale, int mix, void* stream) {
+  return attn_cross_capture_fwd(q, q_sb, q_sn, k, k_sb, k_sn, v, v_sb, v_sn, o, o_sb, o_sn, B, H, Lq, S, d, scale, prob,
+                                score, prob_subj, subj_cols, n_subj, col_flag, qmean_, ca_scale, mix,
+                                (cudaStream_t)stream);
+}
+
+int adaface_qmean(const void* q, int64_t q_sb, int64_t q_sn, int64_t B, int64_t Lq, int64_t C, float* out,
+                  void* stream) {
+  return qmean(q, q_sb, q_sn, B, Lq, C, out, (cudaStream_t)stream);
+}
+
+int adaface_capture_chan_major(const void* src, int src_dtype, int64_t s_sb, int64_t s_sn, int64_t B, int64_t L,
+                               int64_t C, float factor, float* dst, void* stream) {
+  return capture_chan_major(src, src_dtype, s_sb, s_sn, B, L, C, factor, dst, (cudaStream_t)stream);
+}
+
+int adaface_layernorm_fwd(const void* x, int x_dtype, int64_t ldx, const float* w, const float* b, void* y,
+                          int y_dtype, int64_t ldy, int64_t M, int64_t C, float eps, void* stream) {
+  return layernorm_fwd(x, x_dtype, ldx, w, b, y, y_dtype, ldy, M, C, eps, (cudaStream_t)stream);
+}
+
+int adaface_sbg_head_fwd(const float* h0, const float* h1, const float* h2, const float* h3, const float* wl,
+                         int n_layers, int64_t ldh, const float* w, const float* b, float* out, int64_t ldo,
+                         int64_t M, int64_t C, float eps, void* stream) {
+  return sbg_head_fwd(h0, h1, h2, h3, wl, n_layers, ldh, w, b, out, ldo, M, C, eps, (cudaStream_t)stream);
+}
+
+}  // extern "C"

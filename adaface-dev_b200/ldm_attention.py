@@ -1,0 +1,173 @@
+"""Drop-in mirror of the reference's LDM attention modules (surface 2).
+
+    CrossAttention          ldm/modules/attention.py:146-222
+    GEGLU / FeedForward     ldm/modules/attention.py:31-58
+    BasicTransformerBlock   ldm/modules/attention.py:225-252
+
+Module / parameter names are those of the reference, so SD-1.5 LDM checkpoints load with ``load_state_dict``.
+Inside a block, LayerNorm -> projection GEMMs -> attention -> out-projection(+bias +residual) and
+LayerNorm -> GEGLU GEMM -> out GEMM(+bias +residual) are kernels of libadaface_b200.so; the residual adds are
+folded into the GEMM epilogues.  CUDA only, no fallback.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def _ver(*ts):
+    return tuple(None if t is None else (t.data_ptr(), t._version) for t in ts)
+
+
+def _bf16(t):
+    return t.detach().to(torch.bfloat16).contiguous()
+
+
+def _f32(t):
+    return None if t is None else t.detach().float().contiguous()
+
+
+class CrossAttention(nn.Module):
+    def __init__(self, query_dim, context_dim=None, heads=8, dim_head=64, dropout=0.):
+        super().__init__()
+        inner_dim = dim_head * heads
+        context_dim = context_dim if context_dim is not None else query_dim
+        self.scale = dim_head ** -0.5
+        self.heads = heads
+        self.to_q = nn.Linear(query_dim, inner_dim, bias=False)
+        self.to_k = nn.Linear(context_dim, inner_dim, bias=False)
+        self.to_v = nn.Linear(context_dim, inner_dim, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner_dim, query_dim), nn.Dropout(dropout))
+        if dropout != 0.:
+            raise NotImplementedError("SD-1.5 uses dropout 0 in every attention block")
+        self.save_cross_attn_vars = False
+        self.cached_activations = None
+        self._pack_key, self._pack = None, None
+
+    def _weights(self):
+        ws = (self.to_q.weight, self.to_k.weight, self.to_v.weight, self.to_out[0].weight, self.to_out[0].bias)
+        key = _ver(*ws)
+        if key != self._pack_key:
+            with torch.no_grad():
+                pk = {"wq": _bf16(ws[0]), "wo": _bf16(ws[3]), "bo": _f32(ws[4]),
+                      "wkv": torch.cat([_bf16(ws[1]), _bf16(ws[2])], dim=0)}
+                if ws[0].shape[1] == ws[1].shape[1]:
+                    pk["wqkv"] = torch.cat([pk["wq"], pk["wkv"]], dim=0)
+            self._pack, self._pack_key = pk, key
+        return self._pack
+
+    def _attend(self, x16, context, mask, residual=None, out_dtype=torch.bfloat16):
+        """x16 [B,N,C] bf16 contiguous -> [B,N,query_dim]; ``residual`` is added in the out-projection epilogue."""
+        B, N, Cq = x16.shape
+        H = self.heads
+        pk = self._weights()
+        C = pk["wq"].shape[0]
+        x2d = x16.view(B * N, Cq)
+        prob = score = None
+        if context is None:
+            qkv = ops.proj(x2d, pk["wqkv"]).view(B, N, 3 * C)
+            q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+        else:
+            ctx = context.to(torch.bfloat16).contiguous()
+            S = ctx.shape[1]
+            q = ops.proj(x2d, pk["wq"]).view(B, N, C)
+            kv = ops.proj(ctx.view(B * S, ctx.shape[2]), pk["wkv"]).view(B, S, 2 * C)
+            k, v = kv[:, :, :C], kv[:, :, C:]
+        key_mask = None
+        if mask is not None:                                                      # attention.py:185-194
+            key_mask = (mask.reshape(B, -1) != 0).to(torch.uint8).contiguous()
+        if self.save_cross_attn_vars:
+            if key_mask is not None or k.shape[1] > 128:
+                raise NotImplementedError("capture is only defined for cross-attention contexts (<= 128 keys, no mask)")
+            o, prob, score, _ = ops.attention_cross_capture(q, k, v, H, self.scale, want_prob=True, want_score=True)
+        else:
+            o = ops.attention(q, k, v, H, self.scale, key_mask=key_mask)
+        res2d = None if residual is None else residual.view(B * N, -1)
+        out = ops.proj(o.view(B * N, C), pk["wo"], bias=pk["bo"], residual=res2d, out_dtype=out_dtype).view(B, N, -1)
+        if self.save_cross_attn_vars:                                             # attention.py:207-220
+            if residual is not None:
+                raise RuntimeError("capture with a fused residual would corrupt cached 'attn_out'")
+            self.cached_activations = {"q": ops.chan_major(q, math.sqrt(self.scale)), "attn": prob, "attnscore": score,
+                                       "attn_out": ops.chan_major(out, 1.0)}
+        return out
+
+    def forward(self, x, context=None, mask=None):
+        if not x.is_cuda:
+            raise RuntimeError("adaface_b200 CrossAttention runs on CUDA only (no CPU fallback)")
+        return self._attend(x.to(torch.bfloat16).contiguous(), context, mask).to(x.dtype)
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+
+class FeedForward(nn.Module):
+    """FeedForward(dim, glu=True): net = [GEGLU(dim, 4 dim), Dropout, Linear(4 dim, dim)] (attention.py:41-58)."""
+
+    def __init__(self, dim, dim_out=None, mult=4, glu=True, dropout=0.):
+        super().__init__()
+        if not glu:
+            raise NotImplementedError("SD-1.5 transformer blocks use the gated feed-forward (gated_ff=True)")
+        inner_dim = int(dim * mult)
+        if inner_dim % 64:
+            raise ValueError("GEGLU inner dim must be a multiple of 64 (packed [a|gate] tiles)")
+        self.net = nn.Sequential(GEGLU(dim, inner_dim), nn.Dropout(dropout), nn.Linear(inner_dim, dim_out or dim))
+        self._pack_key, self._pack = None, None
+
+    def _weights(self):
+        p, o = self.net[0].proj, self.net[2]
+        key = _ver(p.weight, p.bias, o.weight, o.bias)
+        if key != self._pack_key:
+            with torch.no_grad():
+                inner = p.weight.shape[0] // 2
+                # pack rows as [a(64) | gate(64)] per 128-column tile so that the epilogue sees both halves
+                idx = torch.arange(inner, device=p.weight.device).view(-1, 64)
+                perm = torch.cat([idx, idx + inner], dim=1).reshape(-1)
+                self._pack = {"w1": _bf16(p.weight[perm]), "b1": _f32(p.bias[perm]), "w2": _bf16(o.weight), "b2": _f32(o.bias)}
+            self._pack_key = key
+        return self._pack
+
+    def _ff(self, h16, residual=None, out_dtype=torch.bfloat16):
+        pk = self._weights()
+        g = ops.proj(h16, pk["w1"], bias=pk["b1"], act=ops.ACT_GEGLU)
+        return ops.proj(g, pk["w2"], bias=pk["b2"], residual=residual, out_dtype=out_dtype)
+
+    def forward(self, x):
+        shp = x.shape
+        y = self._ff(x.to(torch.bfloat16).contiguous().view(-1, shp[-1]))
+        return y.view(*shp[:-1], -1).to(x.dtype)
+
+
+class BasicTransformerBlock(nn.Module):
+    def __init__(self, dim, n_heads, d_head, dropout=0., context_dim=None, gated_ff=True, checkpoint=True):
+        super().__init__()
+        self.attn1 = CrossAttention(query_dim=dim, heads=n_heads, dim_head=d_head, dropout=dropout)
+        self.ff = FeedForward(dim, dropout=dropout, glu=gated_ff)
+        self.attn2 = CrossAttention(query_dim=dim, context_dim=context_dim, heads=n_heads, dim_head=d_head, dropout=dropout)
+        self.norm1, self.norm2, self.norm3 = nn.LayerNorm(dim), nn.LayerNorm(dim), nn.LayerNorm(dim)
+        self.checkpoint = checkpoint     # activation checkpointing is a no-op for the forward-only kernels
+
+    def _ln(self, x2d, norm):
+        return ops.layernorm(x2d, norm.weight.detach().float(), norm.bias.detach().float(), norm.eps)
+
+    def forward(self, x, context=None, mask=None):
+        """attention.py:242-252: x1 = attn1(LN1 x, mask) + x; x2 = x1 + attn2(LN2 x1, ctx); x3 = FF(LN3 x2) + x2."""
+        if not x.is_cuda:
+            raise RuntimeError("adaface_b200 BasicTransformerBlock runs on CUDA only (no CPU fallback)")
+        B, N, C = x.shape
+        x0 = x.to(torch.bfloat16).contiguous()
+        capture = self.attn2.save_cross_attn_vars
+        h = self._ln(x0.view(B * N, C), self.norm1).view(B, N, C)
+        x1 = self.attn1._attend(h, None, mask, residual=x0)
+        h = self._ln(x1.view(B * N, C), self.norm2).view(B, N, C)
+        if capture:      # cached attn_out must be the bare attention output (attention.py:220)
+            x2 = self.attn2._attend(h, context, None) + x1
+        else:
+            x2 = self.attn2._attend(h, context, None, residual=x1)
+        h = self._ln(x2.view(B * N, C), self.norm3)
+        x3 = self.ff._ff(h, residual=x2.view(B * N, C)).view(B, N, C)
+        return x3.to(x.dtype)

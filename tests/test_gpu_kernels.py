@@ -1,0 +1,236 @@
+"""GPU: each kernel of libadaface_b200.so, called through the C-ABI, against a plain fp32 restatement of the
+same op on seeded inputs (edge cases: ragged tiles, masks, strided views, LoRA tails, every epilogue)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+def ops():
+    import adaface_dev_b200 as a
+    return a.ops
+
+
+def rnd(*shape, std=1.0, seed=0, dtype=BF):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * std).to(dtype).cuda()
+
+
+def maxerr(a, b):
+    return (a.float().cpu() - b.float().cpu()).abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------- K1 GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 320, 320), (4096, 320, 320), (154, 640, 768), (1280, 2304, 768),
+                                   (1280, 768, 3072), (77, 24, 320), (1000, 960, 320), (64, 1280, 1280), (130, 200, 72)])
+def test_proj_plain(M, N, K):
+    x, w = rnd(M, K, seed=1), rnd(N, K, std=1 / math.sqrt(K), seed=2)
+    y = ops().proj(x, w)
+    ref = x.float() @ w.float().T
+    assert y.shape == (M, N) and y.dtype == BF
+    assert maxerr(y, ref) < 2e-2 + 1e-2 * ref.abs().max().item() * 0.5
+
+
+@pytest.mark.parametrize("R", [8, 16, 192])
+@pytest.mark.parametrize("M,N,K", [(512, 320, 320), (154, 320, 768), (333, 640, 640)])
+def test_proj_lora_dora_bias(M, N, K, R):
+    """Y = colscale * (X W^T + T Bs^T) + bias with T = X A^T  (SURVEY 8a A4)."""
+    x, w = rnd(M, K, seed=1), rnd(N, K, std=1 / math.sqrt(K), seed=2)
+    A, Bs = rnd(R, K, std=1 / math.sqrt(K), seed=3), rnd(N, R, std=0.05, seed=4)
+    cs, bias = rnd(N, seed=5, dtype=torch.float32).abs() + 0.5, rnd(N, seed=6, dtype=torch.float32)
+    t = ops().proj(x, A)
+    assert maxerr(t, x.float() @ A.float().T) < 2e-2
+    y = ops().proj(x, w, t=t, bs=Bs, colscale=cs, bias=bias)
+    ref = cs * (x.float() @ w.float().T + t.float() @ Bs.float().T) + bias
+    assert maxerr(y, ref) < 3e-2
+
+
+def test_proj_epilogues():
+    M, N, K = 260, 768, 768
+    x, w = rnd(M, K, seed=1), rnd(N, K, std=1 / math.sqrt(K), seed=2)
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    res32, res16 = rnd(M, N, seed=4, dtype=torch.float32), rnd(M, N, seed=5)
+    base = x.float() @ w.float().T + bias
+    y = ops().proj(x, w, bias=bias, residual=res32, out_dtype=torch.float32)
+    assert y.dtype == torch.float32 and maxerr(y, base + res32) < 5e-3
+    y = ops().proj(x, w, bias=bias, residual=res16)
+    assert maxerr(y, base + res16.float()) < 3e-2
+    y = ops().proj(x, w, bias=bias, act=1)
+    assert maxerr(y, base * torch.sigmoid(1.702 * base)) < 2e-2
+    # strided input view (a column slice of a wider buffer) and strided output view
+    wide = rnd(M, 3 * K, seed=7)
+    outbuf = torch.zeros(M, 2 * N, device="cuda", dtype=BF)
+    ops().proj(wide[:, K:2 * K], w, out=outbuf[:, N:])
+    assert maxerr(outbuf[:, N:], wide[:, K:2 * K].float() @ w.float().T) < 2e-2
+    assert outbuf[:, :N].abs().max().item() == 0
+
+
+def test_proj_geglu():
+    """Packed [a(64)|gate(64)] tiles: out = a * gelu(gate)  (ldm/modules/attention.py:31-38)."""
+    M, C = 200, 320
+    x = rnd(M, C, seed=1)
+    W, b = rnd(8 * C, C, std=1 / math.sqrt(C), seed=2), rnd(8 * C, seed=3, dtype=torch.float32)
+    inner = 4 * C
+    idx = torch.arange(inner).view(-1, 64)
+    perm = torch.cat([idx, idx + inner], dim=1).reshape(-1).cuda()
+    y = ops().proj(x, W[perm].contiguous(), bias=b[perm].contiguous(), act=2)
+    h = x.float() @ W.float().T + b
+    ref = h[:, :inner] * F.gelu(h[:, inner:])
+    assert y.shape == (M, inner) and maxerr(y, ref) < 3e-2
+
+
+def test_proj_rejects_bad_input():
+    x, w = rnd(16, 20, seed=1), rnd(8, 20, seed=2)       # K = 20 is not a multiple of 8
+    with pytest.raises(RuntimeError):
+        ops().proj(x, w)
+    with pytest.raises(RuntimeError):
+        ops().proj(x.cpu(), w.cpu())
+
+
+# ------------------------------------------------------------------------------------------- K2 attention
+def ref_attn(q, k, v, H, scale, key_mask=None, causal_mult=0):
+    B, Lq, C = q.shape
+    d = C // H
+    qh = q.float().cpu().view(B, Lq, H, d).transpose(1, 2)
+    kh = k.float().cpu().reshape(B, -1, H, d).transpose(1, 2)
+    vh = v.float().cpu().reshape(B, -1, H, d).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) * scale
+    Lk = kh.shape[2]
+    if key_mask is not None:
+        s = s.masked_fill(~key_mask.cpu().bool()[:, None, None, :], float("-inf"))
+    if causal_mult:
+        i = torch.arange(Lq)[:, None]
+        j = torch.arange(Lk)[None, :]
+        s = s.masked_fill((j // causal_mult) > i, float("-inf"))
+    p = s.softmax(-1)
+    return (p @ vh).transpose(1, 2).reshape(B, Lq, C), s, p
+
+
+@pytest.mark.parametrize("d,Lq,Lk", [(40, 256, 256), (40, 1000, 1000), (40, 77, 300), (80, 192, 130), (160, 64, 64),
+                                     (160, 100, 77), (64, 20, 20), (40, 4096, 77), (40, 1, 1)])
+def test_attention(d, Lq, Lk):
+    B, H = 2, 8 if d != 64 else 12
+    C = H * d
+    q, k, v = rnd(B, Lq, C, seed=1), rnd(B, Lk, C, seed=2), rnd(B, Lk, C, seed=3)
+    o = ops().attention(q, k, v, H, d ** -0.5)
+    ref, _, _ = ref_attn(q, k, v, H, d ** -0.5)
+    assert maxerr(o, ref) < 2e-2
+
+
+def test_attention_fused_qkv_views_and_key_mask():
+    B, N, H, d = 2, 320, 8, 40
+    C = H * d
+    qkv = rnd(B, N, 3 * C, seed=1)
+    q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+    g = torch.Generator().manual_seed(5)
+    mask = (torch.rand(B, N, generator=g) > 0.4).to(torch.uint8).cuda()
+    o = ops().attention(q, k, v, H, d ** -0.5, key_mask=mask)
+    ref, _, _ = ref_attn(q, k, v, H, d ** -0.5, key_mask=mask)
+    assert maxerr(o, ref) < 2e-2
+
+
+@pytest.mark.parametrize("mult,T", [(1, 20), (2, 20), (4, 24), (1, 77), (2, 77), (8, 77)])
+def test_attention_causal_multi_kv(mult, T):
+    """CLIPAttentionMKV: each token carries `mult` keys back to back; key j visible iff j // mult <= i."""
+    B, H, d = 3, 12, 64
+    E = H * d
+    buf = rnd(B, T, E * (1 + 2 * mult), seed=1)
+    q, k, v = buf[:, :, :E], buf[:, :, E:E + E * mult], buf[:, :, E + E * mult:]
+    o = ops().attention(q, k, v, H, d ** -0.5, causal_mult=mult)
+    ref, _, _ = ref_attn(q, k.reshape(B, T * mult, E), v.reshape(B, T * mult, E), H, d ** -0.5, causal_mult=mult)
+    assert maxerr(o, ref) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------- K3 capture
+@pytest.mark.parametrize("d,Lq,S", [(40, 256, 77), (40, 100, 97), (80, 64, 77), (160, 64, 77), (40, 4096, 77), (40, 30, 128)])
+def test_cross_capture_plain(d, Lq, S):
+    B, H = 2, 8
+    C = H * d
+    q, k, v = rnd(B, Lq, C, seed=1), rnd(B, S, C, seed=2), rnd(B, S, C, seed=3)
+    o, prob, score, _ = ops().attention_cross_capture(q, k, v, H, d ** -0.5)
+    ref, s, p = ref_attn(q, k, v, H, d ** -0.5)
+    assert maxerr(o, ref) < 2e-2
+    assert maxerr(score, s) < 2e-3            # bf16 products, fp32 accumulate: exact up to summation order
+    assert maxerr(prob, p) < 1e-3
+    assert abs(prob.sum(-1).mean().item() - 1) < 1e-5
+
+
+def test_cross_capture_normalize_and_subj_cols():
+    B, H, d, Lq, S = 2, 8, 40, 300, 77
+    C = H * d
+    q, k, v = rnd(B, Lq, C, seed=1), rnd(B, S, C, seed=2), rnd(B, S, C, seed=3)
+    ib = torch.arange(B).repeat_interleave(16)
+    in_ = torch.arange(4, 20).repeat(B)
+    flag = torch.zeros(B, S, dtype=torch.uint8)
+    flag[ib, in_] = 1
+    ca = torch.tensor([0.8], device="cuda")
+    cols = in_.view(B, 16).to(torch.int32).cuda()
+    qm = ops().qmean(q)
+    assert maxerr(qm, q.float().mean(dim=1)) < 1e-4
+    o, prob, score, psub = ops().attention_cross_capture(q, k, v, H, d ** -0.5, col_flag=flag.cuda(), qmean=qm,
+                                                        ca_scale=ca, subj_cols=cols)
+    _, s, _ = ref_attn(q, k, v, H, d ** -0.5)
+    sub = s[ib, :, :, in_]
+    sub = (sub - sub.mean(dim=2, keepdim=True)) * 0.8
+    s2 = s.clone()
+    s2[ib, :, :, in_] = sub
+    p2 = s2.softmax(-1)
+    vh = v.float().cpu().view(B, S, H, d).transpose(1, 2)
+    ref = (p2 @ vh).transpose(1, 2).reshape(B, Lq, C)
+    assert maxerr(score, s2) < 3e-3 and maxerr(prob, p2) < 1e-3 and maxerr(o, ref) < 2e-2
+    assert maxerr(psub, p2[:, :, :, 4:20]) < 1e-3
+
+
+def test_cross_capture_mix():
+    B, H, d, Lq, S = 4, 8, 40, 130, 77
+    C = H * d
+    q, k, v = rnd(B, Lq, C, seed=1), rnd(B, S, C, seed=2), rnd(B, S, C, seed=3)
+    o, prob, score, _ = ops().attention_cross_capture(q, k, v, H, d ** -0.5, mix=True)
+    _, s, _ = ref_attn(q, k, v, H, d ** -0.5)
+    sm = ((s[:2] + s[2:]) / 2).repeat(2, 1, 1, 1)
+    p = sm.softmax(-1)
+    vh = v.float().cpu().view(B, S, H, d).transpose(1, 2)
+    ref = (p @ vh).transpose(1, 2).reshape(B, Lq, C)
+    assert maxerr(score, sm) < 3e-3 and maxerr(prob, p) < 1e-3 and maxerr(o, ref) < 2e-2
+
+
+def test_cross_capture_rejects():
+    q, k = rnd(3, 64, 320, seed=1), rnd(3, 77, 320, seed=2)
+    with pytest.raises(RuntimeError):
+        ops().attention_cross_capture(q, k, k, 8, 0.1, mix=True)          # odd batch
+    k2 = rnd(2, 200, 320, seed=3)
+    with pytest.raises(RuntimeError):
+        ops().attention_cross_capture(rnd(2, 64, 320), k2, k2, 8, 0.1)    # > 128 keys
+
+
+# ------------------------------------------------------------------------------------------- K4 & helpers
+@pytest.mark.parametrize("C", [320, 640, 768, 1280])
+@pytest.mark.parametrize("dtype", [BF, torch.float32])
+def test_layernorm(C, dtype):
+    M = 1000
+    x = rnd(M, C, std=2.0, seed=1, dtype=dtype) + 0.5
+    w, b = rnd(C, seed=2, dtype=torch.float32), rnd(C, seed=3, dtype=torch.float32)
+    y = ops().layernorm(x, w, b, 1e-5)
+    ref = F.layer_norm(x.float(), (C,), w, b, 1e-5)
+    assert maxerr(y, ref) < 3e-2
+    y32 = ops().layernorm(x.float(), w, b, 1e-5, out_dtype=torch.float32)
+    assert maxerr(y32, ref) < 1e-4
+
+
+def test_chan_major_and_sbg_head():
+    x = rnd(2, 300, 320, seed=1)
+    y = ops().chan_major(x, 0.25)
+    assert maxerr(y, x.float().permute(0, 2, 1) * 0.25) < 1e-6
+    x32 = rnd(2, 77, 320, seed=2, dtype=torch.float32)
+    assert maxerr(ops().chan_major(x32, 1.0), x32.permute(0, 2, 1)) == 0
+    hs = [rnd(130, 768, seed=s, dtype=torch.float32) for s in (1, 2, 3)]
+    w, b = rnd(768, seed=4, dtype=torch.float32), rnd(768, seed=5, dtype=torch.float32)
+    wl = [1 / 7, 2 / 7, 4 / 7]
+    out = ops().sbg_head(hs, wl, w, b)
+    ref = F.layer_norm(sum(a * h for a, h in zip(wl, hs)), (768,), w, b, 1e-5)
+    assert maxerr(out, ref) < 1e-4
