@@ -20,8 +20,8 @@ SIGNATURES = {
     "adaface_attn_fwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
                          _p, _i32, _f32, _p],
     "adaface_attn_cross_capture_fwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64,
-                                       _i64, _i64, _i64, _f32, _p, _p, _p, _p, _i64, _p, _p, _p, _i32, _p],
-    "adaface_qmean": [_p, _i64, _i64, _i64, _i64, _i64, _p, _p],
+                                       _i64, _i64, _i64, _f32, _p, _p, _p, _p, _i64, _p, _p, _p, _i32, _i32, _p],
+    "adaface_qmean": [_p, _i32, _i64, _i64, _i64, _i64, _i64, _p, _p],
     "adaface_capture_chan_major": [_p, _i32, _i64, _i64, _i64, _i64, _i64, _f32, _p, _p],
     "adaface_layernorm_fwd": [_p, _i32, _i64, _p, _p, _p, _i32, _i64, _i64, _i64, _f32, _p],
     "adaface_sbg_head_fwd": [_p, _p, _p, _p, _c.POINTER(_f32), _i32, _i64, _p, _p, _p, _i64, _i64, _i64, _f32, _p],

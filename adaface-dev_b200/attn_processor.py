@@ -254,18 +254,22 @@ class AttnProcessor_LoRA_Capture(nn.Module):
             ctx = encoder_hidden_states.to(torch.bfloat16).contiguous()
             S = ctx.shape[1]
             c2d = ctx.view(B * S, ctx.shape[2])
-            q = ops.proj(x2d, pk["wq"], bias=pk["bq"]).view(B, N, C)                 # dalc:235
+            # The slow-SDPA path (capture / normalize) keeps q, k, v in fp32 out of the projection GEMMs: the capture
+            # kernel then evaluates q.k with a bf16 hi/lo split, which is what holds probabilities to 1e-3.
+            hp = bool(self.capture_ca_activations or self.normalize_cross_attn)
+            pdt = torch.float32 if hp else torch.bfloat16
+            q = ops.proj(x2d, pk["wq"], bias=pk["bq"], out_dtype=pdt).view(B, N, C)  # dalc:235
             q2 = q
             if lora("q") is not None:                                                # dalc:239-249
-                q2 = _linear(x2d, pk["wq"], pk["bq"], lora("q")).view(B, N, C)
+                q2 = _linear(x2d, pk["wq"], pk["bq"], lora("q"), out_dtype=pdt).view(B, N, C)
                 if self.q_lora_updates_query:
                     q = q2
             if lora("k") is None and lora("v") is None:
-                kv = ops.proj(c2d, pk["wkv"], bias=pk["bkv"]).view(B, S, 2 * C)
+                kv = ops.proj(c2d, pk["wkv"], bias=pk["bkv"], out_dtype=pdt).view(B, S, 2 * C)
                 k, v = kv[:, :, :C], kv[:, :, C:]
             else:
-                k = _linear(c2d, pk["wk"], pk["bk"], lora("k")).view(B, S, C)        # dalc:280-283
-                v = _linear(c2d, pk["wv"], pk["bv"], lora("v")).view(B, S, C)        # dalc:285-288
+                k = _linear(c2d, pk["wk"], pk["bk"], lora("k"), out_dtype=pdt).view(B, S, C)   # dalc:280-283
+                v = _linear(c2d, pk["wv"], pk["bv"], lora("v"), out_dtype=pdt).view(B, S, C)   # dalc:285-288
             if self.capture_ca_activations or self.normalize_cross_attn:            # dalc:309-315
                 col_flag = qm = subj_cols = None
                 mix = bool(self.mix_attn_mats_in_batch)
@@ -284,6 +288,8 @@ class AttnProcessor_LoRA_Capture(nn.Module):
                     subj_cols = torch.full((B, n_sub), -1, device=x.device, dtype=torch.int32)
                     subj_cols[ib.long(), torch.arange(ib.numel(), device=x.device) % n_sub] = in_.to(torch.int32)
                 cap = bool(self.capture_ca_activations)
+                if self.cross_attn_scale_factor.device != x.device:     # processor left on the CPU by the caller
+                    self.cross_attn_scale_factor.data = self.cross_attn_scale_factor.data.to(x.device)
                 o, prob, score, prob_subj = ops.attention_cross_capture(
                     q, k, v, H, sm_scale, want_prob=cap, want_score=cap, col_flag=col_flag, qmean=qm,
                     ca_scale=self.cross_attn_scale_factor.detach().float().reshape(1), mix=mix, subj_cols=subj_cols)

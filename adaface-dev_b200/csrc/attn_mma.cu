@@ -295,7 +295,7 @@ int attn_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k
 constexpr int CAP_BN = 128;   // max context keys
 
 struct CapParams {
-  const bf16 *q, *k, *v;
+  const void *q, *k, *v;   // bf16, or fp32 when the kernel is instantiated with F32IN
   bf16* o;
   long long q_sb, q_sn, k_sb, k_sn, v_sb, v_sn, o_sb, o_sn;
   int B, H, Lq, S;
@@ -311,14 +311,41 @@ struct CapParams {
   int mix;
 };
 
-template <int D, bool MIX>
+// fp32 rows -> bf16 hi (+ lo = bf16(x - hi)) tiles: q.k is then evaluated as hi.hi + lo.hi + hi.lo, i.e. to ~2^-17
+// relative, so that captured probabilities meet the 1e-3 bar (plain bf16 q/k give ~3e-3).
+template <int D>
+__device__ __forceinline__ void load_rows_f32_split(bf16* s_hi, bf16* s_lo, const float* g, long long stride_n, int row0,
+                                                    int L, int rows) {
+  constexpr int LD = AttDims<D>::LD, C4 = D / 4;
+  for (int c = threadIdx.x; c < rows * C4; c += blockDim.x) {
+    const int r = c / C4, c4 = c - r * C4;
+    const int gr = row0 + r;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gr < L) x = *reinterpret_cast<const float4*>(g + (long long)gr * stride_n + c4 * 4);
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
+    uint2 hv;
+    hv.x = *reinterpret_cast<const uint32_t*>(&h01);
+    hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+    *reinterpret_cast<uint2*>(s_hi + r * LD + c4 * 4) = hv;
+    if (s_lo) {
+      uint2 lv;
+      lv.x = pack_bf16(x.x - __bfloat162float(h01.x), x.y - __bfloat162float(h01.y));
+      lv.y = pack_bf16(x.z - __bfloat162float(h23.x), x.w - __bfloat162float(h23.y));
+      *reinterpret_cast<uint2*>(s_lo + r * LD + c4 * 4) = lv;
+    }
+  }
+}
+
+template <int D, bool MIX, bool F32IN>
 __global__ void __launch_bounds__(ATT_THREADS) attn_cross_capture_kernel(const CapParams p) {
   using A = AttDims<D>;
-  constexpr int LD = A::LD, KT = A::KT, NT_O = A::NT_O, NT_S = CAP_BN / 8, NI = MIX ? 2 : 1;
+  constexpr int LD = A::LD, KT = A::KT, NT_O = A::NT_O, NT_S = CAP_BN / 8, NI = MIX ? 2 : 1, NP = F32IN ? 2 : 1;
   extern __shared__ __align__(16) uint8_t smem_cap[];
-  bf16* sQ = reinterpret_cast<bf16*>(smem_cap);          // [NI][BM][LD]
-  bf16* sK = sQ + NI * ATT_BM * LD;                      // [NI][CAP_BN][LD]
-  bf16* sV = sK + NI * CAP_BN * LD;                      // [NI][CAP_BN][LD]
+  bf16* sQ = reinterpret_cast<bf16*>(smem_cap);          // [NP][NI][BM][LD]      (NP: hi / lo parts)
+  bf16* sK = sQ + NP * NI * ATT_BM * LD;                 // [NP][NI][CAP_BN][LD]
+  bf16* sV = sK + NP * NI * CAP_BN * LD;                 // [NI][CAP_BN][LD]
+  bf16* sQlo = sQ + NI * ATT_BM * LD;                    // valid only when F32IN
+  bf16* sKlo = sK + NI * CAP_BN * LD;
   float* sStage = reinterpret_cast<float*>(sV + NI * CAP_BN * LD);   // [4 warps][16][S] (packed rows)
   float* sColMean = sStage + 4 * 16 * CAP_BN;            // [CAP_BN]
   uint8_t* sFlag = reinterpret_cast<uint8_t*>(sColMean + CAP_BN);    // [CAP_BN]
@@ -330,14 +357,23 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_cross_capture_kernel(const C
   const int nts = (S + 7) / 8;               // n8 tiles that hold real keys
   const int half = p.B / 2;
 
-  zero_pad_cols<D>(sQ, NI * ATT_BM);
-  zero_pad_cols<D>(sK, NI * CAP_BN);
+  zero_pad_cols<D>(sQ, NP * NI * ATT_BM);
+  zero_pad_cols<D>(sK, NP * NI * CAP_BN);
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
     const int b = b0 + i * half;
-    load_rows<D>(sQ + i * ATT_BM * LD, p.q + (long long)b * p.q_sb + h * D, p.q_sn, m0, p.Lq, ATT_BM);
-    load_rows<D>(sK + i * CAP_BN * LD, p.k + (long long)b * p.k_sb + h * D, p.k_sn, 0, S, CAP_BN);
-    load_rows<D>(sV + i * CAP_BN * LD, p.v + (long long)b * p.v_sb + h * D, p.v_sn, 0, S, CAP_BN);
+    if constexpr (F32IN) {
+      load_rows_f32_split<D>(sQ + i * ATT_BM * LD, sQlo + i * ATT_BM * LD,
+                             (const float*)p.q + (long long)b * p.q_sb + h * D, p.q_sn, m0, p.Lq, ATT_BM);
+      load_rows_f32_split<D>(sK + i * CAP_BN * LD, sKlo + i * CAP_BN * LD,
+                             (const float*)p.k + (long long)b * p.k_sb + h * D, p.k_sn, 0, S, CAP_BN);
+      load_rows_f32_split<D>(sV + i * CAP_BN * LD, nullptr, (const float*)p.v + (long long)b * p.v_sb + h * D, p.v_sn,
+                             0, S, CAP_BN);
+    } else {
+      load_rows<D>(sQ + i * ATT_BM * LD, (const bf16*)p.q + (long long)b * p.q_sb + h * D, p.q_sn, m0, p.Lq, ATT_BM);
+      load_rows<D>(sK + i * CAP_BN * LD, (const bf16*)p.k + (long long)b * p.k_sb + h * D, p.k_sn, 0, S, CAP_BN);
+      load_rows<D>(sV + i * CAP_BN * LD, (const bf16*)p.v + (long long)b * p.v_sb + h * D, p.v_sn, 0, S, CAP_BN);
+    }
   }
   cp_async_commit();
   cp_async_wait<0>();
@@ -352,8 +388,13 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_cross_capture_kernel(const C
       fl = 1;
       const float* qm = p.qmean + ((long long)b0 * p.H + h) * D;
       const bf16* kr = sK + j * LD;
+      const bf16* kl = sKlo + j * LD;
 #pragma unroll 8
-      for (int dd = 0; dd < D; ++dd) cm += qm[dd] * __bfloat162float(kr[dd]);
+      for (int dd = 0; dd < D; ++dd) {
+        float kv = __bfloat162float(kr[dd]);
+        if constexpr (F32IN) kv += __bfloat162float(kl[dd]);
+        cm += qm[dd] * kv;
+      }
       cm *= p.scale;
     }
     sColMean[j] = cm;
@@ -369,18 +410,25 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_cross_capture_kernel(const C
   for (int i = 0; i < NI; ++i) {
 #pragma unroll
     for (int kk = 0; kk < KT; ++kk) {
-      uint32_t qf[4];
-      ldsm_x4(smem_u32(sQ + i * ATT_BM * LD + (warp * 16 + (lane & 15)) * LD + kk * 16 + (lane >> 4) * 8), qf[0], qf[1],
-              qf[2], qf[3]);
+      const int q_off = i * ATT_BM * LD + (warp * 16 + (lane & 15)) * LD + kk * 16 + (lane >> 4) * 8;
+      uint32_t qf[4], ql[4];
+      ldsm_x4(smem_u32(sQ + q_off), qf[0], qf[1], qf[2], qf[3]);
+      if constexpr (F32IN) ldsm_x4(smem_u32(sQlo + q_off), ql[0], ql[1], ql[2], ql[3]);
 #pragma unroll
       for (int np = 0; np < NT_S / 2; ++np) {
         if (2 * np < nts) {
+          const int k_off = i * CAP_BN * LD + (np * 16 + (lane >> 4) * 8 + (lane & 7)) * LD + kk * 16 + ((lane >> 3) & 1) * 8;
           uint32_t r0, r1, r2, r3;
-          ldsm_x4(smem_u32(sK + i * CAP_BN * LD + (np * 16 + (lane >> 4) * 8 + (lane & 7)) * LD + kk * 16 +
-                           ((lane >> 3) & 1) * 8),
-                  r0, r1, r2, r3);
+          ldsm_x4(smem_u32(sK + k_off), r0, r1, r2, r3);
           mma_bf16_16816(acc_s[2 * np], qf, r0, r1);
           mma_bf16_16816(acc_s[2 * np + 1], qf, r2, r3);
+          if constexpr (F32IN) {
+            mma_bf16_16816(acc_s[2 * np], ql, r0, r1);          // lo . hi
+            mma_bf16_16816(acc_s[2 * np + 1], ql, r2, r3);
+            ldsm_x4(smem_u32(sKlo + k_off), r0, r1, r2, r3);
+            mma_bf16_16816(acc_s[2 * np], qf, r0, r1);          // hi . lo
+            mma_bf16_16816(acc_s[2 * np + 1], qf, r2, r3);
+          }
         }
       }
     }
@@ -514,19 +562,19 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_cross_capture_kernel(const C
   }
 }
 
-template <int D, bool MIX>
+template <int D, bool MIX, bool F32IN>
 static int launch_cap(const CapParams& p, cudaStream_t stream) {
   using A = AttDims<D>;
-  constexpr int NI = MIX ? 2 : 1;
-  constexpr int smem = NI * (ATT_BM + 2 * CAP_BN) * A::LD * 2 + 4 * 16 * CAP_BN * 4 + CAP_BN * 4 + CAP_BN;
+  constexpr int NI = MIX ? 2 : 1, NP = F32IN ? 2 : 1;
+  constexpr int smem = NI * (NP * ATT_BM + NP * CAP_BN + CAP_BN) * A::LD * 2 + 4 * 16 * CAP_BN * 4 + CAP_BN * 4 + CAP_BN;
   static_assert(smem <= 227 * 1024, "capture kernel shared memory exceeds the SM");
   static bool configured = false;
   if (!configured) {
-    AF_CUDA(cudaFuncSetAttribute(attn_cross_capture_kernel<D, MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AF_CUDA(cudaFuncSetAttribute(attn_cross_capture_kernel<D, MIX, F32IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   dim3 grid((p.Lq + ATT_BM - 1) / ATT_BM, p.H, MIX ? p.B / 2 : p.B);
-  attn_cross_capture_kernel<D, MIX><<<grid, ATT_THREADS, smem, stream>>>(p);
+  attn_cross_capture_kernel<D, MIX, F32IN><<<grid, ATT_THREADS, smem, stream>>>(p);
   AF_CUDA(cudaGetLastError());
   ++g_launch_count;
   return 0;
@@ -536,10 +584,11 @@ int attn_cross_capture_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void
                            const void* v, int64_t v_sb, int64_t v_sn, void* o, int64_t o_sb, int64_t o_sn, int64_t B,
                            int64_t H, int64_t Lq, int64_t S, int64_t d, float scale, float* prob, float* score,
                            float* prob_subj, const int32_t* subj_cols, int64_t n_subj, const uint8_t* col_flag,
-                           const float* qmean, const float* ca_scale, int mix, cudaStream_t stream) {
+                           const float* qmean, const float* ca_scale, int mix, int in_dtype, cudaStream_t stream) {
   if (check_view("q", q, q_sb, q_sn, d) || check_view("k", k, k_sb, k_sn, d) || check_view("v", v, v_sb, v_sn, d) ||
       check_view("o", o, o_sb, o_sn, d))
     return 1;
+  AF_CHECK(in_dtype == ADAFACE_BF16 || in_dtype == ADAFACE_F32, "attn_cross_capture_fwd: bad in_dtype %d", in_dtype);
   AF_CHECK(B > 0 && H > 0 && Lq > 0 && S > 0, "attn_cross_capture_fwd: empty problem");
   AF_CHECK(S <= CAP_BN, "attn_cross_capture_fwd: context length %lld exceeds %d keys", (long long)S, CAP_BN);
   AF_CHECK(B <= 65535 && H <= 65535, "attn_cross_capture_fwd: B/H exceed grid limits");
@@ -549,24 +598,25 @@ int attn_cross_capture_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void
   AF_CHECK(!(col_flag && !qmean), "normalize_cross_attn needs qmean (and subj_indices, dalc:120)");
   AF_CHECK(!(prob_subj && (!subj_cols || n_subj <= 0)), "prob_subj needs subj_cols / n_subj");
   CapParams p;
-  p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.o = (bf16*)o;
+  p.q = q; p.k = k; p.v = v; p.o = (bf16*)o;
   p.q_sb = q_sb; p.q_sn = q_sn; p.k_sb = k_sb; p.k_sn = k_sn; p.v_sb = v_sb; p.v_sn = v_sn; p.o_sb = o_sb; p.o_sn = o_sn;
   p.B = (int)B; p.H = (int)H; p.Lq = (int)Lq; p.S = (int)S;
   p.scale = scale;
   p.prob = prob; p.score = score; p.prob_subj = prob_subj; p.subj_cols = subj_cols; p.n_subj = (int)n_subj;
   p.col_flag = col_flag; p.qmean = qmean; p.ca_scale = ca_scale; p.mix = mix;
+  const bool f32 = in_dtype == ADAFACE_F32;
   if (mix) {
     switch (d) {
-      case 40: return launch_cap<40, true>(p, stream);
-      case 80: return launch_cap<80, true>(p, stream);
+      case 40: return f32 ? launch_cap<40, true, true>(p, stream) : launch_cap<40, true, false>(p, stream);
+      case 80: return f32 ? launch_cap<80, true, true>(p, stream) : launch_cap<80, true, false>(p, stream);
     }
     set_error("attn_cross_capture_fwd: mix supports head dims 40 and 80, got %lld", (long long)d);
     return 1;
   }
   switch (d) {
-    case 40: return launch_cap<40, false>(p, stream);
-    case 80: return launch_cap<80, false>(p, stream);
-    case 160: return launch_cap<160, false>(p, stream);
+    case 40: return f32 ? launch_cap<40, false, true>(p, stream) : launch_cap<40, false, false>(p, stream);
+    case 80: return f32 ? launch_cap<80, false, true>(p, stream) : launch_cap<80, false, false>(p, stream);
+    case 160: return f32 ? launch_cap<160, false, true>(p, stream) : launch_cap<160, false, false>(p, stream);
   }
   set_error("attn_cross_capture_fwd: unsupported head dim %lld (supported: 40, 80, 160)", (long long)d);
   return 1;

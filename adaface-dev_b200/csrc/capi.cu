@@ -62,8 +62,8 @@ int attn_fwd(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const
              int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, const uint8_t*, int, float, cudaStream_t);
 int attn_cross_capture_fwd(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t, int64_t,
                            void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, float, float*, float*,
-                           float*, const int32_t*, int64_t, const uint8_t*, const float*, const float*, int, cudaStream_t);
-int qmean(const void*, int64_t, int64_t, int64_t, int64_t, int64_t, float*, cudaStream_t);
+                           float*, const int32_t*, int64_t, const uint8_t*, const float*, const float*, int, int, cudaStream_t);
+int qmean(const void*, int, int64_t, int64_t, int64_t, int64_t, int64_t, float*, cudaStream_t);
 int capture_chan_major(const void*, int, int64_t, int64_t, int64_t, int64_t, int64_t, float, float*, cudaStream_t);
 int layernorm_fwd(const void*, int, int64_t, const float*, const float*, void*, int, int64_t, int64_t, int64_t, float,
                   cudaStream_t);
@@ -101,15 +101,15 @@ int adaface_attn_cross_capture_fwd(const void* q, int64_t q_sb, int64_t q_sn, co
                                    int64_t o_sn, int64_t B, int64_t H, int64_t Lq, int64_t S, int64_t d, float scale,
                                    float* prob, float* score, float* prob_subj, const int32_t* subj_cols,
                                    int64_t n_subj, const uint8_t* col_flag, const float* qmean_,
-                                   const float* ca_scale, int mix, void* stream) {
+                                   const float* ca_scale, int mix, int in_dtype, void* stream) {
   return attn_cross_capture_fwd(q, q_sb, q_sn, k, k_sb, k_sn, v, v_sb, v_sn, o, o_sb, o_sn, B, H, Lq, S, d, scale, prob,
-                                score, prob_subj, subj_cols, n_subj, col_flag, qmean_, ca_scale, mix,
+                                score, prob_subj, subj_cols, n_subj, col_flag, qmean_, ca_scale, mix, in_dtype,
                                 (cudaStream_t)stream);
 }
 
-int adaface_qmean(const void* q, int64_t q_sb, int64_t q_sn, int64_t B, int64_t Lq, int64_t C, float* out,
+int adaface_qmean(const void* q, int q_dtype, int64_t q_sb, int64_t q_sn, int64_t B, int64_t Lq, int64_t C, float* out,
                   void* stream) {
-  return qmean(q, q_sb, q_sn, B, Lq, C, out, (cudaStream_t)stream);
+  return qmean(q, q_dtype, q_sb, q_sn, B, Lq, C, out, (cudaStream_t)stream);
 }
 
 int adaface_capture_chan_major(const void* src, int src_dtype, int64_t s_sb, int64_t s_sn, int64_t B, int64_t L,

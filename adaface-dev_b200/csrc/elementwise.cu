@@ -149,7 +149,8 @@ int sbg_head_fwd(const float* h0, const float* h1, const float* h2, const float*
 
 // ---------------------------------------------------------------------------------------------
 // qmean[b, c] = mean_n q[b, n, c].  grid (C/64, B, splits); 256 threads = 32 channel pairs x 8 row lanes.
-__global__ void __launch_bounds__(256) qmean_kernel(const bf16* __restrict__ q, long long sb, long long sn, int L, int C,
+template <typename T>
+__global__ void __launch_bounds__(256) qmean_kernel(const T* __restrict__ q, long long sb, long long sn, int L, int C,
                                                      float* __restrict__ out, float inv_L) {
   __shared__ float red[8][64];
   const int cp = threadIdx.x & 31, ry = threadIdx.x >> 5;
@@ -159,11 +160,10 @@ __global__ void __launch_bounds__(256) qmean_kernel(const bf16* __restrict__ q, 
   const int r_begin = blockIdx.z * rows_per, r_end = min(L, r_begin + rows_per);
   float a0 = 0.f, a1 = 0.f;
   if (c < C) {
-    const bf16* base = q + (long long)b * sb + c;
+    const T* base = q + (long long)b * sb + c;
     for (int r = r_begin + ry; r < r_end; r += 8) {
-      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(base + (long long)r * sn);
-      a0 += __bfloat162float(v.x);
-      a1 += __bfloat162float(v.y);
+      a0 += ld_as_float(base + (long long)r * sn);
+      a1 += ld_as_float(base + (long long)r * sn + 1);
     }
   }
   red[ry][cp * 2] = a0;
@@ -178,12 +178,16 @@ __global__ void __launch_bounds__(256) qmean_kernel(const bf16* __restrict__ q, 
   }
 }
 
-int qmean(const void* q, int64_t q_sb, int64_t q_sn, int64_t B, int64_t Lq, int64_t C, float* out, cudaStream_t stream) {
+int qmean(const void* q, int q_dtype, int64_t q_sb, int64_t q_sn, int64_t B, int64_t Lq, int64_t C, float* out,
+          cudaStream_t stream) {
   AF_CHECK(q && out && B > 0 && Lq > 0 && C > 0 && C % 2 == 0, "qmean: bad arguments");
   AF_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * B * C, stream));
   const int splits = (int)((Lq + 511) / 512);
   dim3 grid((unsigned)((C + 63) / 64), (unsigned)B, (unsigned)splits);
-  qmean_kernel<<<grid, 256, 0, stream>>>((const bf16*)q, q_sb, q_sn, (int)Lq, (int)C, out, 1.f / (float)Lq);
+  if (q_dtype == ADAFACE_F32)
+    qmean_kernel<float><<<grid, 256, 0, stream>>>((const float*)q, q_sb, q_sn, (int)Lq, (int)C, out, 1.f / (float)Lq);
+  else
+    qmean_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)q, q_sb, q_sn, (int)Lq, (int)C, out, 1.f / (float)Lq);
   AF_CUDA(cudaGetLastError());
   ++g_launch_count;
   return 0;

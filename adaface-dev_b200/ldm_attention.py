@@ -72,13 +72,16 @@ class CrossAttention(nn.Module):
         else:
             ctx = context.to(torch.bfloat16).contiguous()
             S = ctx.shape[1]
-            q = ops.proj(x2d, pk["wq"]).view(B, N, C)
-            kv = ops.proj(ctx.view(B * S, ctx.shape[2]), pk["wkv"]).view(B, S, 2 * C)
+            pdt = torch.float32 if self.save_cross_attn_vars else torch.bfloat16   # fp32 q/k/v feed the capture kernel
+            q = ops.proj(x2d, pk["wq"], out_dtype=pdt).view(B, N, C)
+            kv = ops.proj(ctx.view(B * S, ctx.shape[2]), pk["wkv"], out_dtype=pdt).view(B, S, 2 * C)
             k, v = kv[:, :, :C], kv[:, :, C:]
         key_mask = None
         if mask is not None:                                                      # attention.py:185-194
             key_mask = (mask.reshape(B, -1) != 0).to(torch.uint8).contiguous()
         if self.save_cross_attn_vars:
+            if context is None:
+                raise NotImplementedError("save_cross_attn_vars is only set on cross-attention layers (attn2)")
             if key_mask is not None or k.shape[1] > 128:
                 raise NotImplementedError("capture is only defined for cross-attention contexts (<= 128 keys, no mask)")
             o, prob, score, _ = ops.attention_cross_capture(q, k, v, H, self.scale, want_prob=True, want_score=True)

@@ -81,8 +81,8 @@ def proj(x, w, *, t=None, bs=None, colscale=None, bias=None, residual=None, out=
     return out
 
 
-def _view3(t, name):
-    _need(t, name, torch.bfloat16)
+def _view3(t, name, dtype=torch.bfloat16):
+    _need(t, name, dtype)
     if t.dim() != 3:
         raise ValueError(f"attention: `{name}` must be [B, L, H*d]")
     return t
@@ -115,8 +115,10 @@ def attention(q, k, v, heads, scale, *, key_mask=None, causal_mult=0, out=None):
 def attention_cross_capture(q, k, v, heads, scale, *, want_prob=True, want_score=True, col_flag=None, qmean=None,
                             ca_scale=None, mix=False, subj_cols=None, out=None):
     """The slow SDPA of dalc:79-139 as one kernel (adaface_attn_cross_capture_fwd).
+    q / k / v are all bf16 or all fp32 views (fp32 = high-precision scores for capture).
     Returns (out [B,Lq,C] bf16, prob [B,H,Lq,S] fp32 | None, score | None, prob_subj [B,H,Lq,n_subj] | None)."""
-    _view3(q, "q"), _view3(k, "k"), _view3(v, "v")
+    _view3(q, "q", q.dtype), _view3(k, "k", q.dtype), _view3(v, "v", q.dtype)
+    in_dt = _dt(q)
     B, Lq, C = q.shape
     S = k.shape[1]
     d = C // heads
@@ -142,16 +144,16 @@ def attention_cross_capture(q, k, v, heads, scale, *, want_prob=True, want_score
     _lib.call("adaface_attn_cross_capture_fwd", _ptr(q), q.stride(0), q.stride(1), _ptr(k), k.stride(0), k.stride(1),
               _ptr(v), v.stride(0), v.stride(1), _ptr(out), out.stride(0), out.stride(1), B, heads, Lq, S, d,
               float(scale), _ptr(prob), _ptr(score), _ptr(prob_subj), _ptr(subj_cols), n_subj, _ptr(col_flag),
-              _ptr(qmean), _ptr(ca_scale), int(bool(mix)), _stream())
+              _ptr(qmean), _ptr(ca_scale), int(bool(mix)), in_dt, _stream())
     return out, prob, score, prob_subj
 
 
 def qmean(q):
-    """Mean over the queries: q [B, L, C] bf16 view -> [B, C] fp32 (adaface_qmean)."""
-    _view3(q, "q")
+    """Mean over the queries: q [B, L, C] bf16|fp32 view -> [B, C] fp32 (adaface_qmean)."""
+    _view3(q, "q", q.dtype)
     B, L, C = q.shape
     out = torch.empty((B, C), device=q.device, dtype=torch.float32)
-    _lib.call("adaface_qmean", _ptr(q), q.stride(0), q.stride(1), B, L, C, _ptr(out), _stream())
+    _lib.call("adaface_qmean", _ptr(q), _dt(q), q.stride(0), q.stride(1), B, L, C, _ptr(out), _stream())
     return out
 
 

@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- SD-1.5 attention stack throughput on B200 (BASELINE.json metric) + roofline + CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (config.workload = "sd15_attn_stack_512"): the 32 attention modules of one SD-1.5 U-Net denoising step
+at 512x512 (64x64 latent) -- 16 self- and 16 cross-attention modules incl. their Q/K/V/out projections, levels
+A (4096 tok, 320 ch) x5, B (1024, 640) x5, C (256, 1280) x5, D (64, 1280) x1, 8 heads, 77-token context with the
+16 ada tokens spliced into rows 4:20 -- for a batch of 8 (BASELINE config 3), driven through
+the reference-facing operator ``AttnProcessor_LoRA_Capture.__call__``.  One "step" = one pass over that batch.
+value = algorithmic TFLOP/s (closed forms of SURVEY 8d: self 8NC^2 + 4N^2C, cross 4NC^2 + 4*S*768*C + 4NSC per
+sample and block), whole job over all ranks (weak scaling: every rank processes its own batch of 8).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LEVELS = [("A", 4096, 320, 5), ("B", 1024, 640, 5), ("C", 256, 1280, 5), ("D", 64, 1280, 1)]
+HEADS, S_CTX, CTX_DIM, BATCH = 8, 77, 768, 8
+METRIC, UNIT = "SD1.5 attn-block TFLOP/s", "TFLOP/s"
+
+
+def flops_per_sample(levels=LEVELS):
+    f = 0.0
+    for _, N, C, nblk in levels:
+        self_f = 8 * N * C * C + 4 * N * N * C
+        cross_f = 4 * N * C * C + 4 * S_CTX * CTX_DIM * C + 4 * N * S_CTX * C
+        f += nblk * (self_f + cross_f)
+    return f
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        p.update({k: m[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in m})
+        p["source"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_sample_step(torch, oracle, weights, xs, ctx):
+    """Bounded sample of the workload for the CPU arms: ONE sample (B=1), ONE block per level (4 of the 16
+    blocks): self-attention + cross-attention through the oracle's restatement of the processor."""
+    for (name, N, C, _), w, x in zip(LEVELS, weights, xs):
+        y, _ = oracle.processor_forward(w["self"], x, None, heads=HEADS)
+        oracle.processor_forward(w["cross"], y, ctx, heads=HEADS)
+
+
+def cpu_setup(torch):
+    import oracle
+    g = torch.Generator().manual_seed(0)
+    weights, xs = [], []
+    for _, N, C, _ in LEVELS:
+        mk = lambda o, i: torch.randn(o, i, generator=g) / i ** 0.5
+        weights.append({kind: {"to_q": mk(C, C), "to_k": mk(C, cd), "to_v": mk(C, cd), "to_out_w": mk(C, C),
+                               "to_out_b": torch.zeros(C), "cross_attn_scale_factor": torch.tensor(0.8)}
+                        for kind, cd in (("self", C), ("cross", CTX_DIM))})
+        xs.append(torch.randn(1, N, C, generator=g))
+    ctx = torch.randn(1, S_CTX, CTX_DIM, generator=g)
+    sample_levels = [(n, N, C, 1) for n, N, C, _ in LEVELS]
+    return oracle, weights, xs, ctx, flops_per_sample(sample_levels)
+
+
+def run_cpu(torch, steps, warmup, min_seconds=0.0):
+    """Times `steps` sample steps (or, with min_seconds, as many as fit in about that much CPU time)."""
+    torch.set_num_threads(os.cpu_count())
+    oracle, weights, xs, ctx, fl = cpu_setup(torch)
+    with torch.no_grad():
+        for _ in range(warmup):
+            cpu_sample_step(torch, oracle, weights, xs, ctx)
+        t0 = time.perf_counter()
+        n = 0
+        while n < steps or (time.perf_counter() - t0) < min_seconds:
+            cpu_sample_step(torch, oracle, weights, xs, ctx)
+            n += 1
+        dt = (time.perf_counter() - t0) / n
+    return fl / dt / 1e12, dt, fl, n
+
+
+def main_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (the oracle port -- /root/reference does
+    not exist on the GPU box and has no compiled code on this path), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    val, dt, fl, _ = run_cpu(torch, args.steps, args.warmup)
+    sample = "B=1, one block per level (4 of 16 blocks: self+cross attn at 4096x320, 1024x640, 256x1280, 64x1280), fp32"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "sd15_attn_stack_512", "sample": sample, "flops_per_step": fl},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v == "Active":
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if sm:
+            hi = sorted(sm)[len(sm) // 2:]          # upper half = samples taken under load
+            out = {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def build_stack(torch, a, device):
+    g = torch.Generator().manual_seed(0)
+    mods, xs = [], []
+    for _, N, C, nblk in LEVELS:
+        blocks = []
+        for _ in range(nblk):
+            pair = []
+            for ctx_dim in (None, CTX_DIM):
+                m = a.Attention(C, ctx_dim, HEADS, C // HEADS, processor=a.AttnProcessor_LoRA_Capture(), device=device)
+                with torch.no_grad():
+                    for p in m.parameters():
+                        if p.dim() > 1:
+                            p.copy_((torch.randn(p.shape, generator=g) / p.shape[1] ** 0.5).to(device))
+                        else:
+                            p.zero_()
+                pair.append(m)
+            blocks.append(pair)
+        mods.append(blocks)
+        xs.append(torch.randn(BATCH, N, C, generator=g).to(torch.bfloat16))
+    ctx = torch.randn(BATCH, S_CTX, CTX_DIM, generator=g)
+    ctx[:, 4:20] = torch.randn(BATCH, 16, CTX_DIM, generator=g) * 0.5      # ada tokens spliced into the prompt
+    return mods, xs, ctx.to(torch.bfloat16)
+
+
+def run_stack(mods, xs, ctx):
+    outs = []
+    for blocks, x in zip(mods, xs):
+        y = x
+        for attn1, attn2 in blocks:
+            y1 = attn1(x)
+            y = attn2(y1, encoder_hidden_states=ctx)
+        outs.append(y)
+    return outs
+
+
+def main_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import adaface_dev_b200 as a
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    a._lib.load()
+
+    mods, xs_cpu, ctx_cpu = build_stack(torch, a, dev)
+    xs = [x.to(dev) for x in xs_cpu]
+    ctx = ctx_cpu.to(dev)
+    xs_pin = [x.pin_memory() for x in xs_cpu]
+    ctx_pin = ctx_cpu.pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(3, args.warmup)):
+            run_stack(mods, xs, ctx)
+        barrier()
+        sampler = ClockSampler(local)
+        n0 = a._lib.launch_count()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for s, e in ev:
+            flush.fill_(1)                 # evict L2 between timed iterations (outside the timed interval)
+            s.record()
+            run_stack(mods, xs, ctx)
+            e.record()
+        barrier()
+        launches = a._lib.launch_count() - n0
+        clocks = sampler.stop()
+        t_ms = sum(s.elapsed_time(e) for s, e in ev)
+
+        # ---- end to end: host buffers in, host results out, through the same public operator
+        outs_host = [torch.empty(x.shape, dtype=torch.bfloat16).pin_memory() for x in xs_cpu]
+        h2d = sum(x.numel() * 2 for x in xs_pin) + ctx_pin.numel() * 2
+        d2h = sum(o.numel() * 2 for o in outs_host)
+
+        def e2e_step():
+            xd = [x.to(dev, non_blocking=True) for x in xs_pin]
+            cd = ctx_pin.to(dev, non_blocking=True)
+            outs = run_stack(mods, xd, cd)
+            for oh, o in zip(outs_host, outs):
+                oh.copy_(o, non_blocking=True)
+
+        e2e_step()
+        barrier()
+        e2e_steps = max(3, args.steps // 2)
+        ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(e2e_steps)]
+        for s, e in ee:
+            flush.fill_(1)
+            s.record()
+            e2e_step()
+            e.record()
+        barrier()
+        t_e2e_ms = sum(s.elapsed_time(e) for s, e in ee) / e2e_steps
+
+        # ---- roofline of the dominant kernel: level-A self-attention core (attn_fwd_kernel<40>)
+        _, N, C, _ = LEVELS[0]
+        qkv = torch.randn(BATCH, N, 3 * C, device=dev).to(torch.bfloat16)
+        q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+        for _ in range(3):
+            a.ops.attention(q, k, v, HEADS, (C // HEADS) ** -0.5)
+        torch.cuda.synchronize()
+        kt = []
+        for _ in range(10):
+            flush.fill_(1)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            a.ops.attention(q, k, v, HEADS, (C // HEADS) ** -0.5)
+            e.record()
+            torch.cuda.synchronize()
+            kt.append(s.elapsed_time(e))
+        k_ms = statistics.mean(kt)
+        k_flops = 4.0 * BATCH * N * N * C
+
+    tt = torch.tensor([t_ms, t_e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_ms, t_e2e_ms = tt.tolist()
+    fl_step = flops_per_sample() * BATCH
+    pk = peaks()
+    if rank == 0:
+        ms_per_step = t_ms / args.steps
+        value = world * fl_step / (ms_per_step * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "sd15_attn_stack_512", "batch_per_gpu": BATCH, "global_batch": BATCH * world,
+                       "modules": 32, "ctx_tokens": S_CTX, "heads": HEADS, "flops_per_step_per_gpu": fl_step,
+                       "parallelism": f"dp{world} (batch sharded, no collective)",
+                       "l2": "256 MB flush written between timed iterations; per-step working set > 1 GB"},
+            "frac_of_bf16_peak": value / world / pk["bf16_tflops_sustained"],
+            "e2e": {"value": world * fl_step / (t_e2e_ms * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e_ms},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "attn_fwd_kernel<40> (level-A self-attention core, B=8, 4096 tok, 8x40)",
+                         "bound": "tensor", "achieved": k_flops / (k_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops"],
+                         "unit": "TFLOP/s", "frac": k_flops / (k_ms * 1e-3) / 1e12 / pk["bf16_tflops"],
+                         "traffic": None, "peak_source": pk["source"] + " (burst: kernel timed alone)",
+                         "ms_per_launch": k_ms, "flops_per_launch": k_flops},
+        }
+        if world == 1:
+            val, dt, _, n = run_cpu(torch, 3, 1, min_seconds=12.0)
+            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"B=1, one block per level (4 of 16 blocks), fp32 oracle, {n} runs in ~12 s"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_gpu(args)

@@ -75,18 +75,20 @@ int adaface_attn_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, i
  *          score <- (score - scale * qmean[b,h,:] . k[b,j,h,:]) * (*ca_scale)   (qmean = mean over queries of q;
  *          ca_scale = DEVICE pointer to cross_attn_scale_factor, so the nn.Parameter is never synced to the host)
  * mix (dalc:108-118): B even, instances [sc.., mc..]; score <- (score_b + score_{b +/- B/2}) / 2.
+ * in_dtype: ADAFACE_BF16, or ADAFACE_F32 = q/k/v are fp32 views (the projection GEMM's fp32 output): q.k is then
+ * evaluated with a bf16 hi/lo split (hi.hi + lo.hi + hi.lo) so that captured probabilities are good to 1e-3.
  */
 int adaface_attn_cross_capture_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb,
                                    int64_t k_sn, const void* v, int64_t v_sb, int64_t v_sn, void* o, int64_t o_sb,
                                    int64_t o_sn, int64_t B, int64_t H, int64_t Lq, int64_t S, int64_t d, float scale,
                                    float* prob, float* score, float* prob_subj, const int32_t* subj_cols,
                                    int64_t n_subj, const uint8_t* col_flag, const float* qmean,
-                                   const float* ca_scale, int mix, void* stream);
+                                   const float* ca_scale, int mix, int in_dtype, void* stream);
 
 /* Mean over the Lq queries of q[b, :, c] -> qmean[B, C] fp32 (C = H*d); feeds `normalize` above
  * (mean_i(q_i . k_j) = (mean_i q_i) . k_j, dalc:126). */
-int adaface_qmean(const void* q, int64_t q_sb, int64_t q_sn, int64_t B, int64_t Lq, int64_t C, float* qmean,
-                  void* stream);
+int adaface_qmean(const void* q, int q_dtype, int64_t q_sb, int64_t q_sn, int64_t B, int64_t Lq, int64_t C,
+                  float* qmean, void* stream);
 
 /* Capture re-layout (dalc:349-362): dst[b, c, n] = factor * src[b, n, c], src bf16 or fp32 view with element
  * strides (batch, token), dst fp32 [B, C, L] contiguous  ('b h n d -> b (h d) n' times sqrt(scale)). */

@@ -21,8 +21,14 @@ def rnd(*shape, std=1.0, seed=0, dtype=BF):
     return (torch.randn(*shape, generator=g) * std).to(dtype).cuda()
 
 
-def maxerr(a, b):
-    return (a.float().cpu() - b.float().cpu()).abs().max().item()
+def maxerr(a, b, rtol=0.0):
+    """max over elements of |a - b| - rtol * |b|.  rtol = 2^-8 absorbs the final bf16 rounding of large outputs
+    (bf16 half-ulp = 2^-9 relative), so `atol` bounds the error that is NOT just output quantisation."""
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).abs() - rtol * b.abs()).max().item()
+
+
+R8 = 2.0 ** -8
 
 
 # ------------------------------------------------------------------------------------------- K1 GEMM
@@ -33,7 +39,7 @@ def test_proj_plain(M, N, K):
     y = ops().proj(x, w)
     ref = x.float() @ w.float().T
     assert y.shape == (M, N) and y.dtype == BF
-    assert maxerr(y, ref) < 2e-2 + 1e-2 * ref.abs().max().item() * 0.5
+    assert maxerr(y, ref, R8) < 1e-2
 
 
 @pytest.mark.parametrize("R", [8, 16, 192])
@@ -44,10 +50,10 @@ def test_proj_lora_dora_bias(M, N, K, R):
     A, Bs = rnd(R, K, std=1 / math.sqrt(K), seed=3), rnd(N, R, std=0.05, seed=4)
     cs, bias = rnd(N, seed=5, dtype=torch.float32).abs() + 0.5, rnd(N, seed=6, dtype=torch.float32)
     t = ops().proj(x, A)
-    assert maxerr(t, x.float() @ A.float().T) < 2e-2
+    assert maxerr(t, x.float() @ A.float().T, R8) < 1e-2
     y = ops().proj(x, w, t=t, bs=Bs, colscale=cs, bias=bias)
     ref = cs * (x.float() @ w.float().T + t.float() @ Bs.float().T) + bias
-    assert maxerr(y, ref) < 3e-2
+    assert maxerr(y, ref, R8) < 1e-2
 
 
 def test_proj_epilogues():
@@ -59,14 +65,14 @@ def test_proj_epilogues():
     y = ops().proj(x, w, bias=bias, residual=res32, out_dtype=torch.float32)
     assert y.dtype == torch.float32 and maxerr(y, base + res32) < 5e-3
     y = ops().proj(x, w, bias=bias, residual=res16)
-    assert maxerr(y, base + res16.float()) < 3e-2
+    assert maxerr(y, base + res16.float(), R8) < 1e-2
     y = ops().proj(x, w, bias=bias, act=1)
-    assert maxerr(y, base * torch.sigmoid(1.702 * base)) < 2e-2
+    assert maxerr(y, base * torch.sigmoid(1.702 * base), R8) < 1e-2
     # strided input view (a column slice of a wider buffer) and strided output view
     wide = rnd(M, 3 * K, seed=7)
     outbuf = torch.zeros(M, 2 * N, device="cuda", dtype=BF)
     ops().proj(wide[:, K:2 * K], w, out=outbuf[:, N:])
-    assert maxerr(outbuf[:, N:], wide[:, K:2 * K].float() @ w.float().T) < 2e-2
+    assert maxerr(outbuf[:, N:], wide[:, K:2 * K].float() @ w.float().T, R8) < 1e-2
     assert outbuf[:, :N].abs().max().item() == 0
 
 
@@ -81,7 +87,8 @@ def test_proj_geglu():
     y = ops().proj(x, W[perm].contiguous(), bias=b[perm].contiguous(), act=2)
     h = x.float() @ W.float().T + b
     ref = h[:, :inner] * F.gelu(h[:, inner:])
-    assert y.shape == (M, inner) and maxerr(y, ref) < 3e-2
+    assert y.shape == (M, inner)
+    assert maxerr(y, ref, R8) < 1e-2
 
 
 def test_proj_rejects_bad_input():
@@ -160,6 +167,16 @@ def test_cross_capture_plain(d, Lq, S):
     assert abs(prob.sum(-1).mean().item() - 1) < 1e-5
 
 
+def test_cross_capture_fp32_inputs_split_precision():
+    """fp32 q/k/v (projection GEMM fp32 output): scores via bf16 hi/lo split are accurate to ~1e-5."""
+    B, H, d, Lq, S = 2, 8, 40, 200, 77
+    C = H * d
+    q, k, v = (rnd(B, L, C, seed=s, dtype=torch.float32) for L, s in ((Lq, 1), (S, 2), (S, 3)))
+    o, prob, score, _ = ops().attention_cross_capture(q, k, v, H, d ** -0.5)
+    ref, s_, p_ = ref_attn(q, k, v, H, d ** -0.5)
+    assert maxerr(score, s_) < 2e-4 and maxerr(prob, p_) < 5e-5 and maxerr(o, ref) < 2e-2
+
+
 def test_cross_capture_normalize_and_subj_cols():
     B, H, d, Lq, S = 2, 8, 40, 300, 77
     C = H * d
@@ -217,7 +234,7 @@ def test_layernorm(C, dtype):
     w, b = rnd(C, seed=2, dtype=torch.float32), rnd(C, seed=3, dtype=torch.float32)
     y = ops().layernorm(x, w, b, 1e-5)
     ref = F.layer_norm(x.float(), (C,), w, b, 1e-5)
-    assert maxerr(y, ref) < 3e-2
+    assert maxerr(y, ref, R8) < 1e-2
     y32 = ops().layernorm(x.float(), w, b, 1e-5, out_dtype=torch.float32)
     assert maxerr(y32, ref) < 1e-4
 
