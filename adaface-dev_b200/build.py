@@ -5,7 +5,7 @@ import subprocess
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libadaface_b200.so")
-SOURCES = ["capi.cu", "gemm_tcgen05.cu", "attn_mma.cu", "elementwise.cu"]
+SOURCES = ["capi.cu", "gemm_tcgen05.cu", "attn_tcgen05.cu", "attn_mma.cu", "elementwise.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "128"]
 

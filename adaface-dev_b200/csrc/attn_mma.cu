@@ -10,6 +10,7 @@
 // Head dim 40 is padded to 48 only in shared memory (zero columns); HBM layouts stay those of the
 // reference: [B, L, H*d] with heads interleaved.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "../../include/adaface_b200.h"
@@ -263,6 +264,18 @@ static int check_view(const char* what, const void* ptr, int64_t sb, int64_t sn,
   return 0;
 }
 
+int attn_fwd_tcgen05(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t, int64_t, void*,
+                     int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, float, cudaStream_t);
+
+static bool legacy_attention_forced() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ADAFACE_ATTN_LEGACY");   // debugging aid: route everything to the warp-MMA kernel
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 int attn_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn, const void* v,
              int64_t v_sb, int64_t v_sn, void* o, int64_t o_sb, int64_t o_sn, int64_t B, int64_t H, int64_t Lq,
              int64_t Lk, int64_t d, const uint8_t* key_mask, int causal_mult, float scale, cudaStream_t stream) {
@@ -273,6 +286,11 @@ int attn_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k
            (long long)H, (long long)Lq, (long long)Lk);
   AF_CHECK(B <= 65535 && H <= 65535, "attn_fwd: B/H exceed grid limits");
   AF_CHECK(causal_mult >= 0, "attn_fwd: causal_mult must be >= 0");
+  if (!key_mask && causal_mult == 0 && !legacy_attention_forced()) {
+    // unmasked attention: tcgen05 / TMEM kernel (attn_tcgen05.cu)
+    const int rc = attn_fwd_tcgen05(q, q_sb, q_sn, k, k_sb, k_sn, v, v_sb, v_sn, o, o_sb, o_sn, B, H, Lq, Lk, d, scale, stream);
+    if (rc >= 0) return rc;
+  }
   AttnParams p;
   p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.o = (bf16*)o;
   p.q_sb = q_sb; p.q_sn = q_sn; p.k_sb = k_sb; p.k_sn = k_sn; p.v_sb = v_sb; p.v_sn = v_sn; p.o_sb = o_sb; p.o_sn = o_sn;

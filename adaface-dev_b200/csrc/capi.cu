@@ -56,6 +56,29 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return 0;
 }
 
+int make_tmap_bf16_heads(CUtensorMap* out, const void* base, uint64_t d, uint64_t heads, uint64_t L, uint64_t B,
+                         uint64_t sn, uint64_t sb, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return 1;
+  }
+  cuuint64_t gdim[4] = {d, heads, L, B};
+  cuuint64_t gstride[3] = {d * 2, sn * 2, sb * 2};
+  cuuint32_t box[4] = {64, 1, box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4D) failed (%d): base=%p d=%llu heads=%llu L=%llu B=%llu sn=%llu sb=%llu", (int)r,
+              base, (unsigned long long)d, (unsigned long long)heads, (unsigned long long)L, (unsigned long long)B,
+              (unsigned long long)sn, (unsigned long long)sb);
+    return 1;
+  }
+  return 0;
+}
+
 int proj_lora_fwd(const void*, int64_t, const void*, const void*, int64_t, const void*, const float*, const float*,
                   const void*, int64_t, int, void*, int64_t, int, int64_t, int64_t, int64_t, int64_t, int, cudaStream_t);
 int attn_fwd(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t, int64_t, void*, int64_t,

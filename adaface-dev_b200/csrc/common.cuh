@@ -38,6 +38,11 @@ void set_error(const char* fmt, ...);
 // a {64 cols x box_rows} box and 128-byte swizzle.  Returns 0 on success.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows);
+// 4-D view {d, heads, tokens, batch} of a [B, L, H*d] bf16 tensor (element strides: head = d, token = sn,
+// batch = sb) with a {64, 1, box_rows, 1} box and 128-byte swizzle.  Columns >= d inside the 64-wide box are
+// out of bounds and therefore ZERO-filled by TMA: head dims 40 / 80 / 160 need no padding in HBM.
+int make_tmap_bf16_heads(CUtensorMap* out, const void* base, uint64_t d, uint64_t heads, uint64_t L, uint64_t B,
+                         uint64_t sn, uint64_t sb, uint32_t box_rows);
 
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
@@ -98,6 +103,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
+
 // ---- tcgen05 / TMEM -------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {   // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
@@ -122,11 +136,23 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                            // [61,64) layout: SWIZZLE_128B
   return d;
 }
-// Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major, M x N tile.
-__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {
+// Same 128B-swizzled tile read as an MN-major operand (rows = K index, the 64 contiguous elements = M/N index):
+// 8-row (K) groups 1024 B apart (SBO); `lbo_bytes` = distance between 64-element atoms along M/N.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, A K-major, B K-major (or MN-major), M x N tile.
+__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N, bool b_mn_major = false) {
   return (1u << 4)                    // c_format = F32
          | (1u << 7)                  // a_format = BF16
          | (1u << 10)                 // b_format = BF16
+         | ((b_mn_major ? 1u : 0u) << 16)   // b_major: 0 = K-major, 1 = MN-major
          | ((uint32_t)(N >> 3) << 17) // n_dim
          | ((uint32_t)(M >> 4) << 24);// m_dim
 }
@@ -153,6 +179,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> TMEM, same shape as tmem_ld_32x32b_x16
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+      "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- legacy warp-level pieces ---------------------------------------------------------------
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, bool valid) {
