@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libadaface_b200.so")
+LIB_PATH = os.environ.get("ADAFACE_B200_LIB") or os.path.join(_HERE, "csrc", "libadaface_b200.so")   # env override: A/B builds
 
 _c = ctypes
 _p, _i64, _i32, _f32 = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_float
@@ -19,6 +19,10 @@ SIGNATURES = {
                               _i64, _i32, _p],
     "adaface_attn_fwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
                          _p, _i32, _f32, _p],
+    "adaface_attn_headmajor_fwd": [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _i64, _i64,
+                                   _i64, _i64, _i64, _i64, _i64, _i64, _f32, _p],
+    "adaface_proj_lora_heads_fwd": [_p, _i64, _p, _p, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
+                                    _p],
     "adaface_attn_cross_capture_fwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64,
                                        _i64, _i64, _i64, _f32, _p, _p, _p, _p, _i64, _p, _p, _p, _i32, _i32, _p],
     "adaface_qmean": [_p, _i32, _i64, _i64, _i64, _i64, _i64, _p, _p],

@@ -264,8 +264,9 @@ static int check_view(const char* what, const void* ptr, int64_t sb, int64_t sn,
   return 0;
 }
 
-int attn_fwd_tcgen05(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t, int64_t, void*,
-                     int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, float, cudaStream_t);
+int attn_fwd_tcgen05(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, const void*, int64_t,
+                     int64_t, int64_t, void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
+                     float, cudaStream_t);
 
 static bool legacy_attention_forced() {
   static int v = -1;
@@ -288,7 +289,7 @@ int attn_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k
   AF_CHECK(causal_mult >= 0, "attn_fwd: causal_mult must be >= 0");
   if (!key_mask && causal_mult == 0 && !legacy_attention_forced()) {
     // unmasked attention: tcgen05 / TMEM kernel (attn_tcgen05.cu)
-    const int rc = attn_fwd_tcgen05(q, q_sb, q_sn, k, k_sb, k_sn, v, v_sb, v_sn, o, o_sb, o_sn, B, H, Lq, Lk, d, scale, stream);
+    const int rc = attn_fwd_tcgen05(q, q_sb, d, q_sn, k, k_sb, d, k_sn, v, v_sb, d, v_sn, o, o_sb, o_sn, B, H, Lq, Lk, d, d, d, scale, stream);
     if (rc >= 0) return rc;
   }
   AttnParams p;

@@ -14,6 +14,7 @@
 //              in the swizzled K-major layout, final O / l epilogue.
 // Reference arithmetic: F.scaled_dot_product_attention at dalc:321 / ldm attention.py:181-204 (no mask).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "../../include/adaface_b200.h"
@@ -25,6 +26,10 @@ extern long long g_launch_count;
 constexpr int TA_BM = 128;
 constexpr int TA_BN = 64;
 constexpr int TA_THREADS = 192;
+// Warp roles.  The SM sub-partition scheduler favours HIGHER warp ids, so the two control warps (TMA producer, MMA
+// issuer) sit above the four softmax warps: with the control warps at ids 0/1 the exp-heavy softmax warps starved
+// the MMA issuer and every tile waited for its scores.
+constexpr int kTmaWarp = 4, kMmaWarp = 5;
 
 template <int D>
 struct TaCfg {
@@ -38,7 +43,8 @@ struct TaCfg {
   static constexpr int V_BYTES = NA * KV_ATOM;
   static constexpr int P_BYTES = TA_BM * 128;       // 128 rows x 64 keys bf16
   static constexpr int TMEM_O = 2 * TA_BN;          // O starts after the two S buffers
-  static constexpr int TMEM_COLS = (TMEM_O + DO <= 256) ? 256 : 512;
+  static constexpr int TMEM_P = TMEM_O + DO;        // two bf16 P buffers (32 columns each) when P lives in TMEM
+  static constexpr int TMEM_COLS = (TMEM_P + TA_BN <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = Q_BYTES + ST * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 + 256;
 };
 
@@ -47,9 +53,33 @@ struct TaParams {
   long long o_sb, o_sn;
   int Lq, Lk;
   float scale_log2;
+  int phase_ns;            // experiment: delay of every second CTA per SM (0 = off)
+  unsigned* sm_counter;    // [256] per-SM arrival counters (experiment only)
 };
 
-template <int D>
+// exp2 on the FMA/ALU pipes for a pair of values in [-126, 8]: Cody-Waite split with the 1.5*2^23 magic constant,
+// degree-3 minimax polynomial of 2^f on [-0.5, 0.5] (max rel. error 7.5e-5, far below bf16's 2^-9), exponent
+// re-inserted with one integer shift-add.  Offloads part of the softmax from the 16-op/clk MUFU unit, which is
+// what bounds d = 40 attention (one exp per 160 tensor FLOPs).
+__device__ __forceinline__ float2 exp2_emu2(float2 x) {
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 t = __fadd2_rn(x, make_float2(12582912.f, 12582912.f));
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
+  float2 q = __ffma2_rn(f, make_float2(0.05517164f, 0.05517164f), make_float2(0.24261113f, 0.24261113f));
+  q = __ffma2_rn(q, f, make_float2(0.69326097f, 0.69326097f));
+  q = __ffma2_rn(q, f, make_float2(0.99992806f, 0.99992806f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
+// EMU = how many of every 8 exp2 pairs are evaluated by exp2_emu2 instead of MUFU.EX2 (0..4).
+// PT  = P is handed to the P.V MMA through TMEM (tcgen05.st + A-from-TMEM MMA) instead of shared memory: the P
+//       round trip was 45% of the kernel's shared-memory traffic (ncu: smem data pipe 72% busy with P in smem).
+template <int D, int EMU, bool PT>
 __global__ void __launch_bounds__(TA_THREADS, (D <= 64) ? 2 : 1)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const TaParams p) {
@@ -76,7 +106,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const int m0 = blockIdx.x * TA_BM, h = blockIdx.y, b = blockIdx.z;
   const int n_tiles = (p.Lk + TA_BN - 1) / TA_BN;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -93,7 +123,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
     mbar_init(o_full, 1);
     fence_barrier_init();
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   }
   tc_fence_before();
@@ -101,9 +131,9 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: ptxas then knows one thread is active -> plain R2UR, no waterfall loops
       mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
 #pragma unroll
       for (int a = 0; a < NA; ++a) tma_load_4d(sQ + a * (TA_BM * 128), &tmQ, q_full, a * 64, h, m0, b);
@@ -118,9 +148,9 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: ptxas then knows one thread is active -> plain R2UR, no waterfall loops
       constexpr uint32_t idesc_qk = make_idesc_bf16_f32(TA_BM, TA_BN, false);
       constexpr uint32_t idesc_pv = make_idesc_bf16_f32(TA_BM, DO, true);
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
@@ -146,11 +176,17 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         const int s = j % ST;
 #pragma unroll
         for (int k = 0; k < TA_BN / 16; ++k) {
-          const uint64_t da = make_smem_desc_sw128(aP + (j & 1) * Cfg::P_BYTES + k * 32);
           // V tile as the MN-major B operand: 16 keys = two 8-row groups = 2048 B per K step; atoms along d are
           // KV_ATOM bytes apart (LBO).
           const uint64_t db = make_smem_desc_sw128_mn(aV + s * Cfg::V_BYTES + k * 2048, Cfg::KV_ATOM);
-          umma_bf16(tmem_base + (uint32_t)Cfg::TMEM_O, da, db, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          if constexpr (PT) {
+            // A = P_j from TMEM: 16 keys = 8 packed columns per K step
+            umma_bf16_ts(tmem_base + (uint32_t)Cfg::TMEM_O, tmem_base + (uint32_t)(Cfg::TMEM_P + (j & 1) * (TA_BN / 2) + k * 8),
+                         db, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          } else {
+            const uint64_t da = make_smem_desc_sw128(aP + (j & 1) * Cfg::P_BYTES + k * 32);
+            umma_bf16(tmem_base + (uint32_t)Cfg::TMEM_O, da, db, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&kv_empty[s]);       // K/V stage reusable
         umma_commit(&pv_done[j & 1]);    // O updated, P buffer reusable
@@ -158,78 +194,105 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       umma_commit(o_full);
     }
   } else {
-    // ------------------------------------------------------------------ softmax + epilogue (warps 2..5)
+    // ------------------------------------------------------------------ softmax + epilogue (warps 0..3)
     const int qd = warp & 3;                       // TMEM lane quarter of this warp
     const int row = qd * 32 + lane;                // query row inside the tile
     const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16);
     float m_ref = -INFINITY, l_run = 0.f;
-    for (int j = 0; j < n_tiles; ++j) {
+    if (p.phase_ns > 0) {
+      unsigned smid, par = 0;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      if (lane == 0 && qd == 0) par = atomicAdd(p.sm_counter + smid, 1u);
+      par = __shfl_sync(0xffffffffu, par, 0);
+      __shared__ unsigned s_par;
+      if (qd == 0 && lane == 0) s_par = par;
+      asm volatile("bar.sync 1, 128;");
+      if (s_par & 1) __nanosleep(p.phase_ns);
+    }
+    // (A register prefetch of the next tile's scores was measured 1.5x SLOWER: tcgen05.ld is a ~12-cycle operation,
+    // so there is no latency to hide and the second 64-register buffer only costs spills.)
+    auto tile = [&](const int j, uint32_t (&v)[TA_BN]) {
       const int bsel = j & 1;
       mbar_wait(&s_full[bsel], (j >> 1) & 1);
       tc_fence_after();
-      float x[TA_BN];
-#pragma unroll
-      for (int c = 0; c < TA_BN / 16; ++c) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(t_lane + (uint32_t)(bsel * TA_BN + c * 16), v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x[c * 16 + i] = __uint_as_float(v[i]) * p.scale_log2;
-      }
+      tmem_ld_32x32b_x64_wait(t_lane + (uint32_t)(bsel * TA_BN), v);   // raw q.k dot products of this row
       tc_fence_before();
       mbar_arrive(&s_free[bsel]);                  // S[bsel] may be overwritten by Q K_{j+2}^T
       const int valid = p.Lk - j * TA_BN;          // keys of this tile that exist
       if (valid < TA_BN) {
 #pragma unroll
         for (int i = 0; i < TA_BN; ++i)
-          if (i >= valid) x[i] = -INFINITY;
+          if (i >= valid) v[i] = 0xff800000u;      // -inf
       }
-      float mx = x[0];
+      float mx4[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
 #pragma unroll
-      for (int i = 1; i < TA_BN; ++i) mx = fmaxf(mx, x[i]);
+      for (int i = 4; i < TA_BN; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], __uint_as_float(v[i + u]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;   // scale > 0
 
       if (j == 0) {
         m_ref = (mx == -INFINITY) ? 0.f : mx;
       } else {
-        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);   // O and P[bsel] are quiescent
-        tc_fence_after();
         const bool need = mx > m_ref + 8.f;                     // lazy rescale: tolerate P up to 2^8
         if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1); // rare path: O must be quiescent (P V_{j-1} retired)
+          tc_fence_after();
           const float m_new = need ? mx : m_ref;
           const float f = fast_exp2(m_ref - m_new);
           m_ref = m_new;
           l_run *= f;
 #pragma unroll
           for (int c = 0; c < DO / 16; ++c) {
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(t_lane + (uint32_t)(Cfg::TMEM_O + c * 16), v);
+            uint32_t ov[16];
+            tmem_ld_32x32b_x16(t_lane + (uint32_t)(Cfg::TMEM_O + c * 16), ov);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
-            tmem_st_32x32b_x16(t_lane + (uint32_t)(Cfg::TMEM_O + c * 16), v);
+            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
+            tmem_st_32x32b_x16(t_lane + (uint32_t)(Cfg::TMEM_O + c * 16), ov);
           }
           tmem_st_wait();
         }
       }
-      // P = exp2(x - m_ref), bf16, into the 128B-swizzled K-major tile: 16-byte chunk c of row r lives at
-      // r*128 + ((c ^ (r & 7)) * 16).
+      // P buffer `bsel` was last read by P V_{j-2}: that MMA retired long ago, this wait is (almost) free.  The
+      // softmax warps never wait for P V_{j-1} on the common path.
+      if (j >= 2) mbar_wait(&pv_done[bsel], ((j - 2) >> 1) & 1);
+      // P = exp2(s * scale_log2 - m_ref) (packed fp32x2 FMA), bf16, into the 128B-swizzled K-major tile: the
+      // 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) * 16).
+      // fp32 -> bf16 by TRUNCATION (one PRMT per pair on the ALU pipe instead of F2FP on the 16-lane XU pipe that
+      // the exponentials already saturate); the row sum is taken over the truncated values, so numerator and
+      // denominator stay consistent and the truncation bias cancels in O = sum(p v) / sum(p).
       uint8_t* prow = sP + bsel * Cfg::P_BYTES + row * 128;
-      float lsum = 0.f;
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
+      float2 ls[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      uint32_t pk[TA_BN / 2];
 #pragma unroll
       for (int c = 0; c < TA_BN / 8; ++c) {
-        float e[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          e[i] = fast_exp2(x[c * 8 + i] - m_ref);
-          lsum += e[i];
+        for (int i = 0; i < 4; ++i) {
+          const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[c * 8 + 2 * i]), __uint_as_float(v[c * 8 + 2 * i + 1])), sc2, nm2);
+          const float2 e = (((c * 4 + i) & 7) < EMU) ? exp2_emu2(t) : make_float2(fast_exp2(t.x), fast_exp2(t.y));
+          const uint32_t ex = __float_as_uint(e.x) & 0xffff0000u, ey = __float_as_uint(e.y) & 0xffff0000u;
+          ls[i & 1] = __fadd2_rn(ls[i & 1], make_float2(__uint_as_float(ex), __uint_as_float(ey)));
+          pk[c * 4 + i] = __byte_perm(ex, ey, 0x7632);          // {lo16 = hi half of e.x, hi16 = hi half of e.y}
         }
-        uint4 pk = make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
-        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) * 16)) = pk;
+        if constexpr (!PT)
+          *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) * 16)) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
       }
+      if constexpr (PT) {
+        tmem_st_32x32b_x32(t_lane + (uint32_t)(Cfg::TMEM_P + bsel * (TA_BN / 2)), pk);
+        tmem_st_wait();
+      }
+      const float lsum = (ls[0].x + ls[0].y) + (ls[1].x + ls[1].y);
       l_run += lsum;
-      fence_proxy_async_smem();                    // generic-proxy smem writes -> visible to the tensor core
+      if constexpr (!PT) fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core
       tc_fence_before();
       mbar_arrive(&p_full[bsel]);
+    };
+    {
+      uint32_t va[TA_BN];
+      for (int j = 0; j < n_tiles; ++j) tile(j, va);
     }
     // ---- epilogue: O / l -> bf16 -> [B, Lq, H*d]
     mbar_wait(o_full, 0);
@@ -259,24 +322,252 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <int D>
+
+// =============================================================================================
+// "Many small CTAs" variant.  The ncu profile of the kernel above shows no saturated unit (XU 56%, tensor 40%,
+// issue 50%): with two softmax warps per SM sub-partition the row-per-thread softmax is latency-bound.  This
+// variant trades the intra-CTA double buffering for residency: S and P share ONE 64-column TMEM buffer (P_j is
+// written over the scores it was computed from), O takes 48 more, so a CTA needs 128 TMEM columns and 49 KB of
+// shared memory and FOUR CTAs (16 softmax warps) fit on an SM; the tensor-pipe round trip of one CTA is hidden by
+// the other three.  The scores are read in two 32-column passes (max, then exp) to stay within 80 registers.
+template <int D, int EMU>
+__global__ void __launch_bounds__(TA_THREADS, (D <= 64) ? 4 : 2)
+attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                           const __grid_constant__ CUtensorMap tmV, const TaParams p) {
+  using Cfg = TaCfg<D>;
+  constexpr int NA = Cfg::NA, KT = Cfg::KT, DO = Cfg::DO, ST = 2;
+  constexpr int TMEM_O = TA_BN;                                   // S/P at column 0, O behind it
+  constexpr int TMEM_COLS = (TMEM_O + DO <= 128) ? 128 : 256;
+  extern __shared__ uint8_t smem_raw_mc[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_mc) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + ST * Cfg::K_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * Cfg::V_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + ST;
+  uint64_t* s_full = kv_empty + ST;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* o_full = p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TA_BM, h = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = (p.Lk + TA_BN - 1) / TA_BN;
+
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  } else if (warp == kMmaWarp) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kTmaWarp) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+      for (int a = 0; a < NA; ++a) tma_load_4d(sQ + a * (TA_BM * 128), &tmQ, q_full, a * 64, h, m0, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % ST;
+        mbar_wait(&kv_empty[s], ((j / ST) & 1) ^ 1);
+        const bool skip_v = p.phase_ns == -7;   // EXPERIMENT: halve the L2->SM traffic (results are wrong)
+        mbar_arrive_expect_tx(&kv_full[s], skip_v ? Cfg::K_BYTES : Cfg::K_BYTES + Cfg::V_BYTES);
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+          tma_load_4d(sK + s * Cfg::K_BYTES + a * Cfg::KV_ATOM, &tmK, &kv_full[s], a * 64, h, j * TA_BN, b);
+          if (!skip_v) tma_load_4d(sV + s * Cfg::V_BYTES + a * Cfg::KV_ATOM, &tmV, &kv_full[s], a * 64, h, j * TA_BN, b);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16_f32(TA_BM, TA_BN, false);
+      constexpr uint32_t idesc_pv = make_idesc_bf16_f32(TA_BM, DO, true);
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % ST;
+        mbar_wait(&kv_full[s], (j / ST) & 1);
+        tc_fence_after();
+        // S_j = Q K_j^T.  It overwrites P_{j-1}; tcgen05.mma executes in issue order, so P V_{j-1} has read it.
+#pragma unroll
+        for (int kk = 0; kk < KT; ++kk) {
+          const uint64_t da = make_smem_desc_sw128(aQ + (kk >> 2) * (TA_BM * 128) + (kk & 3) * 32);
+          const uint64_t db = make_smem_desc_sw128(aK + s * Cfg::K_BYTES + (kk >> 2) * Cfg::KV_ATOM + (kk & 3) * 32);
+          umma_bf16(tmem_base, da, db, idesc_qk, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < TA_BN / 16; ++k) {
+          const uint64_t db = make_smem_desc_sw128_mn(aV + s * Cfg::V_BYTES + k * 2048, Cfg::KV_ATOM);
+          umma_bf16_ts(tmem_base + (uint32_t)TMEM_O, tmem_base + (uint32_t)(k * 8), db, idesc_pv, (j | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[s]);
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16);
+    float m_ref = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(s_full, j & 1);          // also implies P V_{j-1} has retired (commit covers all earlier MMAs)
+      tc_fence_after();
+      const int valid = p.Lk - j * TA_BN;
+      // ---- pass 1: row max of the raw scores
+      float mxr = -INFINITY;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32_wait(t_lane + (uint32_t)(hf * 32), v);
+        if (valid < TA_BN) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (hf * 32 + i >= valid) v[i] = 0xff800000u;
+        }
+        float m4[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
+#pragma unroll
+        for (int i = 4; i < 32; i += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) m4[u] = fmaxf(m4[u], __uint_as_float(v[i + u]));
+        }
+        mxr = fmaxf(mxr, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+      }
+      const float mx = mxr * p.scale_log2;
+      if (j == 0) {
+        m_ref = (mx == -INFINITY) ? 0.f : mx;
+      } else {
+        const bool need = mx > m_ref + 8.f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = need ? mx : m_ref;
+          const float f = fast_exp2(m_ref - m_new);
+          m_ref = m_new;
+          l_run *= f;
+#pragma unroll
+          for (int c = 0; c < DO / 16; ++c) {
+            uint32_t ov[16];
+            tmem_ld_32x32b_x16(t_lane + (uint32_t)(TMEM_O + c * 16), ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
+            tmem_st_32x32b_x16(t_lane + (uint32_t)(TMEM_O + c * 16), ov);
+          }
+        }
+      }
+      // ---- pass 2: P = exp2(s * scale - m_ref), truncated to bf16, written over the scores it came from
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
+      float2 ls[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32_wait(t_lane + (uint32_t)(hf * 32), v);
+        if (valid < TA_BN) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (hf * 32 + i >= valid) v[i] = 0xff800000u;
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc2, nm2);
+          const float2 e = ((i & 7) < EMU) ? exp2_emu2(t) : make_float2(fast_exp2(t.x), fast_exp2(t.y));
+          const uint32_t ex = __float_as_uint(e.x) & 0xffff0000u, ey = __float_as_uint(e.y) & 0xffff0000u;
+          ls[i & 1] = __fadd2_rn(ls[i & 1], make_float2(__uint_as_float(ex), __uint_as_float(ey)));
+          pk[i] = __byte_perm(ex, ey, 0x7632);
+        }
+        tmem_st_32x32b_x16(t_lane + (uint32_t)(hf * 16), pk);   // columns [16 hf, 16 hf + 16): already consumed
+      }
+      tmem_st_wait();
+      l_run += (ls[0].x + ls[0].y) + (ls[1].x + ls[1].y);
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    const int grow = m0 + row;
+    bf16* orow = p.o + (long long)b * p.o_sb + (long long)grow * p.o_sn + h * D;
+#pragma unroll
+    for (int c = 0; c < DO / 16; ++c) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(t_lane + (uint32_t)(TMEM_O + c * 16), v);
+      tmem_ld_wait();
+      if (grow < p.Lq) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (c * 16 + half * 8 < D) {
+            uint4 pk;
+            pk.x = pack_bf16(__uint_as_float(v[half * 8 + 0]) * inv, __uint_as_float(v[half * 8 + 1]) * inv);
+            pk.y = pack_bf16(__uint_as_float(v[half * 8 + 2]) * inv, __uint_as_float(v[half * 8 + 3]) * inv);
+            pk.z = pack_bf16(__uint_as_float(v[half * 8 + 4]) * inv, __uint_as_float(v[half * 8 + 5]) * inv);
+            pk.w = pack_bf16(__uint_as_float(v[half * 8 + 6]) * inv, __uint_as_float(v[half * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + c * 16 + half * 8) = pk;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int D, int EMU>
+static int launch_ta_mc(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtensorMap& tV, const TaParams& p, int B, int H,
+                        cudaStream_t stream) {
+  using Cfg = TaCfg<D>;
+  constexpr int smem = Cfg::Q_BYTES + 2 * (Cfg::K_BYTES + Cfg::V_BYTES) + 1024 + 128;
+  static bool configured = false;
+  if (!configured) {
+    AF_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_mc_kernel<D, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid((p.Lq + TA_BM - 1) / TA_BM, H, B);
+  attn_fwd_tcgen05_mc_kernel<D, EMU><<<grid, TA_THREADS, smem, stream>>>(tQ, tK, tV, p);
+  AF_CUDA(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+template <int D, int EMU, bool PT>
 static int launch_ta(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtensorMap& tV, const TaParams& p, int B, int H,
                      cudaStream_t stream) {
   using Cfg = TaCfg<D>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "tcgen05 attention: shared memory exceeds the SM");
   static bool configured = false;
   if (!configured) {
-    AF_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    AF_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<D, EMU, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
   dim3 grid((p.Lq + TA_BM - 1) / TA_BM, H, B);
-  attn_fwd_tcgen05_kernel<D><<<grid, TA_THREADS, Cfg::SMEM_BYTES, stream>>>(tQ, tK, tV, p);
+  attn_fwd_tcgen05_kernel<D, EMU, PT><<<grid, TA_THREADS, Cfg::SMEM_BYTES, stream>>>(tQ, tK, tV, p);
   AF_CUDA(cudaGetLastError());
   ++g_launch_count;
   return 0;
@@ -284,14 +575,19 @@ static int launch_ta(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtenso
 
 // Unmasked attention on the tensor-core path.  Returns -1 when the problem is not eligible (caller falls through to
 // the warp-MMA kernel, which handles masks, causal multi-KV and tiny shapes), 0 on success, > 0 on error.
-int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn, const void* v,
-                     int64_t v_sb, int64_t v_sn, void* o, int64_t o_sb, int64_t o_sn, int64_t B, int64_t H, int64_t Lq,
-                     int64_t Lk, int64_t d, float scale, cudaStream_t stream) {
+// q/k/v element strides: batch (sb), head (sh), token (sn).  Reference layout [B, L, H*d]: sh = d, sn = H*d.
+int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sh,
+                     int64_t k_sn, const void* v, int64_t v_sb, int64_t v_sh, int64_t v_sn, void* o, int64_t o_sb,
+                     int64_t o_sn, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t d, int64_t drow_q, int64_t drow_kv,
+                     float scale, cudaStream_t stream) {
   if (!(d == 40 || d == 80 || d == 160)) return -1;
+  // drow_* = elements that exist in a row: d, or the zero-padded width of a head-major buffer
+  if (drow_q < d) drow_q = d;
+  if (drow_kv < d) drow_kv = d;
   CUtensorMap tQ, tK, tV;
-  if (make_tmap_bf16_heads(&tQ, q, (uint64_t)d, (uint64_t)H, (uint64_t)Lq, (uint64_t)B, (uint64_t)q_sn, (uint64_t)q_sb, TA_BM)) return 3;
-  if (make_tmap_bf16_heads(&tK, k, (uint64_t)d, (uint64_t)H, (uint64_t)Lk, (uint64_t)B, (uint64_t)k_sn, (uint64_t)k_sb, TA_BN)) return 3;
-  if (make_tmap_bf16_heads(&tV, v, (uint64_t)d, (uint64_t)H, (uint64_t)Lk, (uint64_t)B, (uint64_t)v_sn, (uint64_t)v_sb, TA_BN)) return 3;
+  if (make_tmap_bf16_heads(&tQ, q, (uint64_t)drow_q, (uint64_t)H, (uint64_t)Lq, (uint64_t)B, (uint64_t)q_sh, (uint64_t)q_sn, (uint64_t)q_sb, TA_BM)) return 3;
+  if (make_tmap_bf16_heads(&tK, k, (uint64_t)drow_kv, (uint64_t)H, (uint64_t)Lk, (uint64_t)B, (uint64_t)k_sh, (uint64_t)k_sn, (uint64_t)k_sb, TA_BN)) return 3;
+  if (make_tmap_bf16_heads(&tV, v, (uint64_t)drow_kv, (uint64_t)H, (uint64_t)Lk, (uint64_t)B, (uint64_t)v_sh, (uint64_t)v_sn, (uint64_t)v_sb, TA_BN)) return 3;
   TaParams p;
   p.o = (bf16*)o;
   p.o_sb = o_sb;
@@ -299,10 +595,54 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sn, const void* k, i
   p.Lq = (int)Lq;
   p.Lk = (int)Lk;
   p.scale_log2 = scale * 1.4426950408889634f;
+  static unsigned* sm_counter = nullptr;
+  static int phase_ns = -1;
+  if (phase_ns < 0) {
+    const char* e = getenv("ADAFACE_PHASE_NS");
+    phase_ns = e ? atoi(e) : 0;
+    if (phase_ns != 0) {
+      cudaMalloc(&sm_counter, 256 * sizeof(unsigned));
+      cudaMemset(sm_counter, 0, 256 * sizeof(unsigned));
+    }
+  }
+  p.phase_ns = phase_ns;
+  p.sm_counter = sm_counter;
+  static int emu = -1, psmem = 0, mc = 1;
+  if (emu < 0) {
+    const char* m = getenv("ADAFACE_ATTN_MC");      // 1 (default): many-small-CTAs kernel for d = 40 / 80
+    mc = (m && m[0] == '0') ? 0 : 1;
+    const char* e = getenv("ADAFACE_EXP_EMU");      // tuning knob: exp2 pairs of every 8 moved off the MUFU unit
+    emu = (e && e[0] >= '0' && e[0] <= '4') ? (e[0] - '0') : 0;
+    const char* ps = getenv("ADAFACE_P_SMEM");      // debugging aid: hand P to the MMA through shared memory
+    psmem = (ps && ps[0] == '1') ? 1 : 0;
+  }
+  const int ib = (int)B, ih = (int)H;
+  if (mc && !psmem && d == 40) {
+    switch (emu) {
+      case 0: return launch_ta_mc<40, 0>(tQ, tK, tV, p, ib, ih, stream);
+      case 1: return launch_ta_mc<40, 1>(tQ, tK, tV, p, ib, ih, stream);
+      case 2: return launch_ta_mc<40, 2>(tQ, tK, tV, p, ib, ih, stream);
+      case 3: return launch_ta_mc<40, 3>(tQ, tK, tV, p, ib, ih, stream);
+      default: return launch_ta_mc<40, 4>(tQ, tK, tV, p, ib, ih, stream);
+    }
+  }
+  if (mc && !psmem && d == 80) return emu ? launch_ta_mc<80, 2>(tQ, tK, tV, p, ib, ih, stream) : launch_ta_mc<80, 0>(tQ, tK, tV, p, ib, ih, stream);
   switch (d) {
-    case 40: return launch_ta<40>(tQ, tK, tV, p, (int)B, (int)H, stream);
-    case 80: return launch_ta<80>(tQ, tK, tV, p, (int)B, (int)H, stream);
-    case 160: return launch_ta<160>(tQ, tK, tV, p, (int)B, (int)H, stream);
+    case 40:
+      if (psmem) return launch_ta<40, 0, false>(tQ, tK, tV, p, ib, ih, stream);
+      switch (emu) {
+        case 0: return launch_ta<40, 0, true>(tQ, tK, tV, p, ib, ih, stream);
+        case 1: return launch_ta<40, 1, true>(tQ, tK, tV, p, ib, ih, stream);
+        case 2: return launch_ta<40, 2, true>(tQ, tK, tV, p, ib, ih, stream);
+        case 3: return launch_ta<40, 3, true>(tQ, tK, tV, p, ib, ih, stream);
+        default: return launch_ta<40, 4, true>(tQ, tK, tV, p, ib, ih, stream);
+      }
+    case 80:
+      if (psmem) return launch_ta<80, 0, false>(tQ, tK, tV, p, ib, ih, stream);
+      return emu ? launch_ta<80, 2, true>(tQ, tK, tV, p, ib, ih, stream) : launch_ta<80, 0, true>(tQ, tK, tV, p, ib, ih, stream);
+    case 160:
+      if (psmem) return launch_ta<160, 0, false>(tQ, tK, tV, p, ib, ih, stream);
+      return launch_ta<160, 0, true>(tQ, tK, tV, p, ib, ih, stream);
   }
   return -1;
 }

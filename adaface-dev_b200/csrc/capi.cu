@@ -57,14 +57,14 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 }
 
 int make_tmap_bf16_heads(CUtensorMap* out, const void* base, uint64_t d, uint64_t heads, uint64_t L, uint64_t B,
-                         uint64_t sn, uint64_t sb, uint32_t box_rows) {
+                         uint64_t sh, uint64_t sn, uint64_t sb, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
     return 1;
   }
   cuuint64_t gdim[4] = {d, heads, L, B};
-  cuuint64_t gstride[3] = {d * 2, sn * 2, sb * 2};
+  cuuint64_t gstride[3] = {sh * 2, sn * 2, sb * 2};
   cuuint32_t box[4] = {64, 1, box_rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
@@ -80,9 +80,13 @@ int make_tmap_bf16_heads(CUtensorMap* out, const void* base, uint64_t d, uint64_
 }
 
 int proj_lora_fwd(const void*, int64_t, const void*, const void*, int64_t, const void*, const float*, const float*,
-                  const void*, int64_t, int, void*, int64_t, int, int64_t, int64_t, int64_t, int64_t, int, cudaStream_t);
+                  const void*, int64_t, int, void*, int64_t, int, int64_t, int64_t, int64_t, int64_t, int, int64_t, int64_t,
+                  int64_t, int64_t, cudaStream_t);
 int attn_fwd(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t, int64_t, void*, int64_t,
              int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, const uint8_t*, int, float, cudaStream_t);
+int attn_fwd_tcgen05(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, const void*, int64_t,
+                     int64_t, int64_t, void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
+                     float, cudaStream_t);
 int attn_cross_capture_fwd(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t, int64_t,
                            void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, float, float*, float*,
                            float*, const int32_t*, int64_t, const uint8_t*, const float*, const float*, int, int, cudaStream_t);
@@ -108,7 +112,14 @@ int adaface_proj_lora_fwd(const void* x, int64_t ldx, const void* w, const void*
                           int residual_dtype, void* y, int64_t ldy, int y_dtype, int64_t M, int64_t N, int64_t K,
                           int64_t R, int act, void* stream) {
   return proj_lora_fwd(x, ldx, w, t, ldt, bs, colscale, bias, residual, ldr, residual_dtype, y, ldy, y_dtype, M, N, K, R,
-                       act, (cudaStream_t)stream);
+                       act, 0, 0, 0, 0, (cudaStream_t)stream);
+}
+
+int adaface_proj_lora_heads_fwd(const void* x, int64_t ldx, const void* w, const void* t, int64_t ldt, const void* bs,
+                                const float* colscale, const float* bias, void* y, int64_t M, int64_t N, int64_t K,
+                                int64_t R, int64_t heads, int64_t d, int64_t dpad, int64_t rows_per_batch, void* stream) {
+  return proj_lora_fwd(x, ldx, w, t, ldt, bs, colscale, bias, nullptr, 0, ADAFACE_BF16, y, 0, ADAFACE_BF16, M, N, K, R,
+                       ADAFACE_ACT_NONE, heads, d, dpad, rows_per_batch, (cudaStream_t)stream);
 }
 
 int adaface_attn_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn,
@@ -117,6 +128,16 @@ int adaface_attn_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, i
                      float scale, void* stream) {
   return attn_fwd(q, q_sb, q_sn, k, k_sb, k_sn, v, v_sb, v_sn, o, o_sb, o_sn, B, H, Lq, Lk, d, key_mask, causal_mult,
                   scale, (cudaStream_t)stream);
+}
+
+int adaface_attn_headmajor_fwd(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, const void* k, int64_t k_sb,
+                               int64_t k_sh, int64_t k_sn, const void* v, int64_t v_sb, int64_t v_sh, int64_t v_sn, void* o,
+                               int64_t o_sb, int64_t o_sn, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t d,
+                               int64_t drow_q, int64_t drow_kv, float scale, void* stream) {
+  const int rc = attn_fwd_tcgen05(q, q_sb, q_sh, q_sn, k, k_sb, k_sh, k_sn, v, v_sb, v_sh, v_sn, o, o_sb, o_sn, B, H, Lq, Lk,
+                                  d, drow_q, drow_kv, scale, (cudaStream_t)stream);
+  if (rc < 0) set_error("adaface_attn_headmajor_fwd: unsupported head dim %lld (40, 80, 160)", (long long)d);
+  return rc < 0 ? 1 : rc;
 }
 
 int adaface_attn_cross_capture_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb,

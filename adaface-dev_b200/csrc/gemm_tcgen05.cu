@@ -30,6 +30,10 @@ struct GemmEpilogue {
   int M, N;
   int num_kb1, num_kb2;
   int act, y_f32, res_f32;
+  // head-scatter store (hs_d > 0): output column c = which*hs_C + h*hs_d + dd of row b*hs_rows + n goes to
+  // y[which][b][h][n][dd] with rows padded to hs_dpad elements -- the head-major, 128-byte-row layout the
+  // attention kernel's TMA loads want (TMA boxes that run out of bounds inside a row are ~3x slower).
+  int hs_d, hs_dpad, hs_C, hs_H, hs_rows, hs_B;
 };
 
 template <int BN>
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tn_tcgen05_kernel(const __g
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: ptxas then knows one thread is active -> plain R2UR, no waterfall loops
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tn_tcgen05_kernel(const __g
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: ptxas then knows one thread is active -> plain R2UR, no waterfall loops
       constexpr uint32_t idesc = make_idesc_bf16_f32(GEMM_BM, BN);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
@@ -201,6 +205,20 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tn_tcgen05_kernel(const __g
           for (int j = 0; j < 16; ++j)
             if (out_col0 + j < out_n) y[j] = f[j];
         }
+      } else if (ep.hs_d > 0) {
+        const int bb = row / ep.hs_rows, nn = row - bb * ep.hs_rows;
+#pragma unroll
+        for (int g8 = 0; g8 < 2; ++g8) {
+          const int col = out_col0 + g8 * 8;             // 8-column groups never straddle a head (hs_d % 8 == 0)
+          if (col < out_n) {
+            const int which = col / ep.hs_C, rem = col - which * ep.hs_C;
+            const int hh = rem / ep.hs_d, dd = rem - hh * ep.hs_d;
+            bf16* dst = reinterpret_cast<bf16*>(ep.y) +
+                        ((((long long)which * ep.hs_B + bb) * ep.hs_H + hh) * ep.hs_rows + nn) * ep.hs_dpad + dd;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(f[g8 * 8 + 0], f[g8 * 8 + 1]), pack_bf16(f[g8 * 8 + 2], f[g8 * 8 + 3]),
+                                                        pack_bf16(f[g8 * 8 + 4], f[g8 * 8 + 5]), pack_bf16(f[g8 * 8 + 6], f[g8 * 8 + 7]));
+          }
+        }
       } else {
         bf16* y = reinterpret_cast<bf16*>(ep.y) + (long long)row * ep.ldy + out_col0;
         if (out_col0 + 16 <= out_n && ((reinterpret_cast<uintptr_t>(y) & 15) == 0)) {
@@ -248,7 +266,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
 int proj_lora_fwd(const void* x, int64_t ldx, const void* w, const void* t, int64_t ldt, const void* bs,
                   const float* colscale, const float* bias, const void* residual, int64_t ldr, int residual_dtype,
                   void* y, int64_t ldy, int y_dtype, int64_t M, int64_t N, int64_t K, int64_t R, int act,
-                  cudaStream_t stream) {
+                  int64_t hs_heads, int64_t hs_d, int64_t hs_dpad, int64_t hs_rows, cudaStream_t stream) {
   AF_CHECK(x && w && y, "proj_lora_fwd: null x/w/y");
   AF_CHECK(M > 0 && N > 0 && K > 0, "proj_lora_fwd: empty problem M=%lld N=%lld K=%lld", (long long)M, (long long)N,
            (long long)K);
@@ -265,6 +283,13 @@ int proj_lora_fwd(const void* x, int64_t ldx, const void* w, const void* t, int6
              "proj_lora_fwd: t / bs must be 16-byte aligned");
   }
   AF_CHECK(act >= 0 && act <= 2, "proj_lora_fwd: bad act %d", act);
+  if (hs_d > 0) {
+    AF_CHECK(y_dtype == ADAFACE_BF16 && act != ADAFACE_ACT_GEGLU && !residual, "proj_lora_fwd: head-scatter output is plain bf16");
+    AF_CHECK(hs_heads > 0 && hs_d % 8 == 0 && hs_dpad % 8 == 0 && hs_dpad >= hs_d && hs_rows > 0 && M % hs_rows == 0 &&
+                 N % (hs_heads * hs_d) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+             "proj_lora_fwd: bad head-scatter geometry (heads=%lld d=%lld dpad=%lld rows=%lld M=%lld N=%lld)", (long long)hs_heads,
+             (long long)hs_d, (long long)hs_dpad, (long long)hs_rows, (long long)M, (long long)N);
+  }
   AF_CHECK(M < (1ll << 31) && N < (1ll << 31), "proj_lora_fwd: M/N too large");
 
   int BN;
@@ -307,6 +332,12 @@ int proj_lora_fwd(const void* x, int64_t ldx, const void* w, const void* t, int6
   ep.act = act;
   ep.y_f32 = y_dtype == ADAFACE_F32;
   ep.res_f32 = residual_dtype == ADAFACE_F32;
+  ep.hs_d = (int)hs_d;
+  ep.hs_dpad = (int)hs_dpad;
+  ep.hs_H = (int)hs_heads;
+  ep.hs_C = (int)(hs_heads * hs_d);
+  ep.hs_rows = (int)hs_rows;
+  ep.hs_B = hs_rows > 0 ? (int)(M / hs_rows) : 0;
   const int n_tiles = (int)((N + BN - 1) / BN);
   switch (BN) {
     case 64: return launch_gemm<64>(tA, tB, tA2, tB2, ep, n_tiles, stream);

@@ -66,27 +66,29 @@ class CrossAttention(nn.Module):
         C = pk["wq"].shape[0]
         x2d = x16.view(B * N, Cq)
         prob = score = None
-        if context is None:
-            qkv = ops.proj(x2d, pk["wqkv"]).view(B, N, 3 * C)
-            q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
-        else:
-            ctx = context.to(torch.bfloat16).contiguous()
-            S = ctx.shape[1]
-            pdt = torch.float32 if self.save_cross_attn_vars else torch.bfloat16   # fp32 q/k/v feed the capture kernel
-            q = ops.proj(x2d, pk["wq"], out_dtype=pdt).view(B, N, C)
-            kv = ops.proj(ctx.view(B * S, ctx.shape[2]), pk["wkv"], out_dtype=pdt).view(B, S, 2 * C)
-            k, v = kv[:, :, :C], kv[:, :, C:]
         key_mask = None
         if mask is not None:                                                      # attention.py:185-194
             key_mask = (mask.reshape(B, -1) != 0).to(torch.uint8).contiguous()
-        if self.save_cross_attn_vars:
-            if context is None:
+        if context is None:
+            if self.save_cross_attn_vars:
                 raise NotImplementedError("save_cross_attn_vars is only set on cross-attention layers (attn2)")
-            if key_mask is not None or k.shape[1] > 128:
-                raise NotImplementedError("capture is only defined for cross-attention contexts (<= 128 keys, no mask)")
-            o, prob, score, _ = ops.attention_cross_capture(q, k, v, H, self.scale, want_prob=True, want_score=True)
+            o = ops.self_attention_fused_qkv(x2d, pk["wqkv"], None, B, N, H, self.scale, key_mask)
         else:
-            o = ops.attention(q, k, v, H, self.scale, key_mask=key_mask)
+            ctx = context.to(torch.bfloat16).contiguous()
+            S = ctx.shape[1]
+            c2d = ctx.view(B * S, ctx.shape[2])
+            if self.save_cross_attn_vars:
+                if key_mask is not None or S > 128:
+                    raise NotImplementedError("capture is only defined for cross-attention contexts (<= 128 keys, no mask)")
+                q = ops.proj(x2d, pk["wq"], out_dtype=torch.float32).view(B, N, C)      # fp32 q/k/v feed the capture kernel
+                kv = ops.proj(c2d, pk["wkv"], out_dtype=torch.float32).view(B, S, 2 * C)
+                o, prob, score, _ = ops.attention_cross_capture(q, kv[:, :, :C], kv[:, :, C:], H, self.scale)
+            elif key_mask is None:
+                o = ops.cross_attention_fused(x2d, pk["wq"], None, c2d, pk["wkv"], None, B, N, S, H, self.scale)
+            else:
+                q = ops.proj(x2d, pk["wq"]).view(B, N, C)
+                kv = ops.proj(c2d, pk["wkv"]).view(B, S, 2 * C)
+                o = ops.attention(q, kv[:, :, :C], kv[:, :, C:], H, self.scale, key_mask=key_mask)
         res2d = None if residual is None else residual.view(B * N, -1)
         out = ops.proj(o.view(B * N, C), pk["wo"], bias=pk["bo"], residual=res2d, out_dtype=out_dtype).view(B, N, -1)
         if self.save_cross_attn_vars:                                             # attention.py:207-220

@@ -112,6 +112,64 @@ def attention(q, k, v, heads, scale, *, key_mask=None, causal_mult=0, out=None):
     return out
 
 
+def attention_headmajor(q, k, v, scale, *, d=None, out=None):
+    """Unmasked attention for head-major views q [B, H, Lq, drow_q], k / v [B, H, Lk, drow_kv] (any batch / head /
+    token strides, unit stride in the last dim).  `d` = true head dim when rows are zero-padded (drow > d; default:
+    the k/v row width).  Output in the reference layout [B, Lq, H*d] (adaface_attn_headmajor_fwd)."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        _need(t, nm, torch.bfloat16)
+        if t.dim() != 4:
+            raise ValueError(f"attention_headmajor: `{nm}` must be [B, H, L, d]")
+    B, H, Lq, drow_q = q.shape
+    Lk, drow_kv = k.shape[2], k.shape[3]
+    d = drow_kv if d is None else d
+    if v.shape != k.shape or k.shape[:2] != (B, H) or drow_q < d or drow_kv < d:
+        raise ValueError(f"attention_headmajor: inconsistent shapes q{tuple(q.shape)} k{tuple(k.shape)} v{tuple(v.shape)} d={d}")
+    if out is None:
+        out = torch.empty((B, Lq, H * d), device=q.device, dtype=torch.bfloat16)
+    _lib.call("adaface_attn_headmajor_fwd", _ptr(q), q.stride(0), q.stride(1), q.stride(2), _ptr(k), k.stride(0), k.stride(1),
+              k.stride(2), _ptr(v), v.stride(0), v.stride(1), v.stride(2), _ptr(out), out.stride(0), out.stride(1), B, H, Lq,
+              Lk, d, drow_q, drow_kv, float(scale), _stream())
+    return out
+
+
+_HEADS_WS = {}
+
+
+def heads_workspace(n_which, B, H, L, dpad, device):
+    """Zero-initialised [n_which, B, H, L, dpad] bf16 workspace, cached per shape: proj_heads never writes the pad
+    columns, so they stay zero across calls."""
+    key = (n_which, B, H, L, dpad, str(device))
+    ws = _HEADS_WS.get(key)
+    if ws is None:
+        ws = torch.zeros((n_which, B, H, L, dpad), device=device, dtype=torch.bfloat16)
+        _HEADS_WS[key] = ws
+    return ws
+
+
+def proj_heads(x, w, heads, d, rows_per_batch, *, dpad=None, t=None, bs=None, colscale=None, bias=None, out=None):
+    """Projection whose bf16 output is scattered head-major: returns y[which, b, h, n, :dpad] with
+    y[which, b, h, n, dd] = (x W^T ...)[b*rows_per_batch + n, which*heads*d + h*d + dd]  (adaface_proj_lora_heads_fwd)."""
+    _need(x, "x", torch.bfloat16)
+    _need(w, "w", torch.bfloat16)
+    M, K = x.shape
+    N = w.shape[0]
+    if dpad is None:
+        dpad = (d + 63) // 64 * 64
+    n_which = N // (heads * d)
+    B = M // rows_per_batch
+    if out is None:
+        out = heads_workspace(n_which, B, heads, rows_per_batch, dpad, x.device)
+    if tuple(out.shape) != (n_which, B, heads, rows_per_batch, dpad) or not out.is_contiguous():
+        raise ValueError("proj_heads: out must be a contiguous [N/(H*d), B, H, rows_per_batch, dpad] tensor")
+    R, ldt = 0, 0
+    if t is not None:
+        R, ldt = t.shape[1], t.stride(0)
+    _lib.call("adaface_proj_lora_heads_fwd", _ptr(x), x.stride(0), _ptr(w), _ptr(t), ldt, _ptr(bs), _ptr(colscale), _ptr(bias),
+              _ptr(out), M, N, K, R, heads, d, dpad, rows_per_batch, _stream())
+    return out
+
+
 def attention_cross_capture(q, k, v, heads, scale, *, want_prob=True, want_score=True, col_flag=None, qmean=None,
                             ca_scale=None, mix=False, subj_cols=None, out=None):
     """The slow SDPA of dalc:79-139 as one kernel (adaface_attn_cross_capture_fwd).
@@ -197,3 +255,31 @@ def sbg_head(hs, layer_weights, w, b, eps=1e-5):
 
 def softmax_scale(d):
     return 1.0 / math.sqrt(d)
+
+
+def self_attention_fused_qkv(x2d, wqkv, bqkv, B, N, heads, scale, key_mask=None):
+    """Fused QKV projection + unmasked/masked self-attention; returns o [B, N, C] bf16.
+    d = 40 without a mask: the projection scatters q/k/v into the zero-padded head-major workspace (128-byte rows per
+    (batch, head)) that the tcgen05 attention kernel's TMA loads 3x faster than 80-byte head slices; every other
+    case keeps the interleaved [B, N, 3C] buffer."""
+    C = wqkv.shape[0] // 3
+    d = C // heads
+    if key_mask is None and d == 40:
+        ws = proj_heads(x2d, wqkv, heads, d, N, bias=bqkv)
+        return attention_headmajor(ws[0], ws[1], ws[2], scale, d=d)
+    qkv = proj(x2d, wqkv, bias=bqkv).view(B, N, 3 * C)
+    return attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads, scale, key_mask=key_mask)
+
+
+def cross_attention_fused(x2d, wq, bq, ctx2d, wkv, bkv, B, N, S, heads, scale):
+    """q and fused k|v projections + unmasked cross-attention (fast path, dalc:321); returns o [B, N, C] bf16."""
+    C = wq.shape[0]
+    d = C // heads
+    kv = proj(ctx2d, wkv, bias=bkv).view(B, S, 2 * C)
+    if d == 40:
+        q = proj_heads(x2d, wq, heads, d, N, bias=bq)[0]                     # [B, H, N, 64]
+        k = kv[:, :, :C].unflatten(2, (heads, d)).transpose(1, 2)             # views [B, H, S, d] of the interleaved buffer
+        v = kv[:, :, C:].unflatten(2, (heads, d)).transpose(1, 2)
+        return attention_headmajor(q, k, v, scale, d=d)
+    q = proj(x2d, wq, bias=bq).view(B, N, C)
+    return attention(q, kv[:, :, :C], kv[:, :, C:], heads, scale)

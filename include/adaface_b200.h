@@ -50,6 +50,15 @@ int adaface_proj_lora_fwd(const void* x, int64_t ldx, const void* w, const void*
                           int residual_dtype, void* y, int64_t ldy, int y_dtype, int64_t M, int64_t N, int64_t K,
                           int64_t R, int act, void* stream);
 
+/* Same GEMM, bf16 output scattered head-major: output column c = which*H*d + h*d + dd of row b*rows_per_batch + n is
+ * stored at y[which][b][h][n][dd], rows padded to dpad (>= d) elements -- y is a [N/(H*d), M/rows_per_batch, H,
+ * rows_per_batch, dpad] buffer whose pad columns the caller zeroed once.  This is the internal q/k/v layout between
+ * the fused QKV projection and adaface_attn_headmajor_fwd: dense 128-byte rows per (batch, head), which TMA loads
+ * ~3x faster than 80-byte head slices of the interleaved [B, L, H*d] layout (measured, profiles/). */
+int adaface_proj_lora_heads_fwd(const void* x, int64_t ldx, const void* w, const void* t, int64_t ldt, const void* bs,
+                                const float* colscale, const float* bias, void* y, int64_t M, int64_t N, int64_t K,
+                                int64_t R, int64_t heads, int64_t d, int64_t dpad, int64_t rows_per_batch, void* stream);
+
 /* ---- K2: flash attention forward (self-attention, fast cross-attention, CLIP causal multi-KV) ------
  * Replaces F.scaled_dot_product_attention at dalc:321, the einsum attention of
  * ldm/modules/attention.py:181-204 and CLIPAttentionMKV's bmm/softmax/bmm (arc2face_models.py:170-217).
@@ -64,6 +73,16 @@ int adaface_attn_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, i
                      const void* v, int64_t v_sb, int64_t v_sn, void* o, int64_t o_sb, int64_t o_sn, int64_t B,
                      int64_t H, int64_t Lq, int64_t Lk, int64_t d, const uint8_t* key_mask, int causal_mult,
                      float scale, void* stream);
+
+/* Same operator for q/k/v tensors with an explicit HEAD stride (element strides batch / head / token), e.g. the
+ * head-major [which, B, H, L, d] buffer that adaface_proj_lora_fwd can scatter a fused QKV projection into: every
+ * (batch, head) slice is then one dense [L, d] matrix, which is what the TMA loads of the tcgen05 kernel like best.
+ * drow_q / drow_kv = elements that really exist in a q / k,v row (d, or the padded width with zeroed pad columns).
+ * o keeps the reference layout [B, Lq, H*d].  Unmasked only; d in {40, 80, 160}. */
+int adaface_attn_headmajor_fwd(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, const void* k, int64_t k_sb,
+                               int64_t k_sh, int64_t k_sn, const void* v, int64_t v_sb, int64_t v_sh, int64_t v_sn, void* o,
+                               int64_t o_sb, int64_t o_sn, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t d,
+                               int64_t drow_q, int64_t drow_kv, float scale, void* stream);
 
 /* ---- K3: cross-attention with capture / normalize / mix (the slow SDPA of dalc:79-139) -------------
  * S = Lk <= 128 keys staged once in shared memory.  Optional outputs (NULL = not wanted):

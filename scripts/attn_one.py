@@ -1,0 +1,11 @@
+"""Runs the level-A self-attention core a few times (for ncu captures)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import adaface_dev_b200 as a
+N, C, B, H = 4096, 320, 8, 8
+qkv = torch.randn(B, N, 3 * C, device="cuda").to(torch.bfloat16)
+q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
+    a.ops.attention(q, k, v, H, (C // H) ** -0.5)
+torch.cuda.synchronize()

@@ -153,6 +153,25 @@ def test_attention_causal_multi_kv(mult, T):
     assert maxerr(o, ref) < 2e-2
 
 
+@pytest.mark.parametrize("d,N,B", [(40, 320, 2), (80, 200, 1), (160, 64, 2)])
+def test_proj_heads_and_headmajor_attention(d, N, B):
+    """Fused QKV projection scattered into the padded head-major workspace + attention on that layout == the
+    interleaved-layout path (same arithmetic, different addresses)."""
+    H = 8
+    C = H * d
+    x, w = rnd(B * N, C, seed=1), rnd(3 * C, C, std=1 / math.sqrt(C), seed=2)
+    bias = rnd(3 * C, seed=3, dtype=torch.float32)
+    ws = ops().proj_heads(x, w, H, d, N, bias=bias)
+    dpad = ws.shape[-1]
+    ref = (x.float() @ w.float().T + bias).view(B, N, 3, H, d).permute(2, 0, 3, 1, 4)
+    assert maxerr(ws[..., :d], ref, R8) < 1e-2
+    assert ws[..., d:].abs().max().item() == 0 if dpad > d else True
+    qkv = ops().proj(x, w, bias=bias).view(B, N, 3 * C)
+    o_ref = ops().attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H, d ** -0.5)
+    o = ops().attention_headmajor(ws[0], ws[1], ws[2], d ** -0.5, d=d)
+    assert maxerr(o, o_ref) < 1e-2
+
+
 # ------------------------------------------------------------------------------------------- K3 capture
 @pytest.mark.parametrize("d,Lq,S", [(40, 256, 77), (40, 100, 97), (80, 64, 77), (160, 64, 77), (40, 4096, 77), (40, 30, 128)])
 def test_cross_capture_plain(d, Lq, S):
