@@ -17,5 +17,6 @@ from .ldm_attention import CrossAttention, FeedForward, GEGLU, BasicTransformerB
 from .subj_basis_generator import (SubjBasisGenerator, CLIPTextModelWrapper, CLIPAttentionMKV, CLIPTextConfig,  # noqa: F401
                                    template_ids)
 from .build import build  # noqa: F401
+from .graphs import graphed  # noqa: F401
 
 __version__ = "0.1.0"

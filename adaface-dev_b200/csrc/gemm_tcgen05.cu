@@ -2,15 +2,12 @@
 //
 //   Y[M,N] = act( colscale[N] * ( X[M,K] W[N,K]^T + T[M,R] Bs[N,R]^T ) + bias[N] ) + residual[M,N]
 //
-// One CTA computes a 128 x BN output tile.  Warp roles (192 threads):
-//   warp 0    TMA producer: streams 64-wide K slabs of X/W (then of T/Bs -- the rank-R LoRA tail simply
-//             continues the same accumulation) into a STAGES-deep 128B-swizzled smem ring.
-//   warp 1    allocates TMEM, then one elected lane issues tcgen05.mma (M=128, N=BN, K=16) per 32-byte K step;
-//             tcgen05.commit releases smem stages and finally signals the epilogue.
-//   warps 2-5 epilogue: tcgen05.ld the fp32 accumulator (one row per thread, 32 TMEM lanes per warp),
-//             apply DoRA column scale, bias, activation, residual, convert, store.
+// Persistent, warp-specialised kernel: 128 x BN output tiles, STAGES-deep TMA ring, two TMEM accumulators so the
+// epilogue of one tile overlaps the main loop of the next (details at the kernel).
 // Reference arithmetic: nn.Linear / peft lora.Linear(+DoRA) call sites dalc:235-249, 280-288, 328-331
 // (SURVEY.md 8a rows A1, A4); ldm/modules/attention.py:31-58, 156-164; HF CLIP q/k/v/out_proj, fc1, fc2.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/adaface_b200.h"
 
@@ -18,7 +15,7 @@ namespace adaface {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;          // 64 bf16 = 128 B = one swizzle span
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;     // 8 epilogue warps + TMA warp + MMA warp
 constexpr int A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;
 
 struct GemmEpilogue {
@@ -34,42 +31,149 @@ struct GemmEpilogue {
   // y[which][b][h][n][dd] with rows padded to hs_dpad elements -- the head-major, 128-byte-row layout the
   // attention kernel's TMA loads want (TMA boxes that run out of bounds inside a row are ~3x slower).
   int hs_d, hs_dpad, hs_C, hs_H, hs_rows, hs_B;
+  int dbg;   // experiments: 1 = no global stores, 2 = no MMA, 4 = epilogue skipped entirely
 };
 
 template <int BN>
 struct GemmCfg {
   static constexpr int B_STAGE_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN <= 160) ? 3 : 4;   // <=110 KB: two CTAs co-reside per SM (epilogue/mainloop overlap)
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);   // 64:8 128:6 160:5 192:5 256:4
+  static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;   // two accumulator buffers
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
+// Epilogue of one 32-column chunk of one row: scale / bias / activation / residual / convert / store.
+// `c0` = first tile-local column of the chunk, `g` = the matching gate values when ACT == GEGLU.
+// FULL = the whole chunk lies inside N: no per-element bounds predicates (the common case; the epilogue warps run
+// one per scheduler slot with little ILP, so every instruction removed here is ~4 cycles of the critical path).
+template <int BN, bool FULL>
+__device__ __forceinline__ void epilogue_chunk32(const GemmEpilogue& ep, const uint32_t (&v)[32], const uint32_t (&g)[32], int row,
+                                                 bool row_ok, int n_blk, int c0) {
+  const int n0 = n_blk * BN;
+  const bool geglu = ep.act == ADAFACE_ACT_GEGLU;
+  const int col0 = n0 + c0;
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  auto affine = [&](float (&x)[32], int cbase) {
+    if (ep.colscale) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (FULL || cbase + j < ep.N) x[j] *= __ldg(ep.colscale + cbase + j);
+    }
+    if (ep.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (FULL || cbase + j < ep.N) x[j] += __ldg(ep.bias + cbase + j);
+    }
+  };
+  affine(f, col0);
+  int out_col0 = col0;
+  int out_n = ep.N;
+  if (geglu) {
+    float gt[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) gt[j] = __uint_as_float(g[j]);
+    affine(gt, col0 + BN / 2);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] *= gelu_erf(gt[j]);
+    out_col0 = n_blk * (BN / 2) + c0;
+    out_n = ep.N / 2;
+  } else if (ep.act == ADAFACE_ACT_QUICK_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.f + __expf(-1.702f * f[j]));
+  }
+  if (!row_ok || (ep.dbg & 1)) return;
+  if (ep.residual) {
+    if (ep.res_f32) {
+      const float* r = reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + out_col0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (FULL || out_col0 + j < out_n) f[j] += r[j];
+    } else {
+      const bf16* r = reinterpret_cast<const bf16*>(ep.residual) + (long long)row * ep.ldr + out_col0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (FULL || out_col0 + j < out_n) f[j] += __bfloat162float(r[j]);
+    }
+  }
+  if (ep.y_f32) {
+    float* y = reinterpret_cast<float*>(ep.y) + (long long)row * ep.ldy + out_col0;
+    if (FULL && ((reinterpret_cast<uintptr_t>(y) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(y + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (FULL || out_col0 + j < out_n) y[j] = f[j];
+    }
+  } else if (ep.hs_d > 0) {
+    const int bb = row / ep.hs_rows, nn = row - bb * ep.hs_rows;
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      const int col = out_col0 + g8 * 8;             // 8-column groups never straddle a head (hs_d % 8 == 0)
+      if (FULL || col < out_n) {
+        const int which = col / ep.hs_C, rem = col - which * ep.hs_C;
+        const int hh = rem / ep.hs_d, dd = rem - hh * ep.hs_d;
+        bf16* dst = reinterpret_cast<bf16*>(ep.y) +
+                    ((((long long)which * ep.hs_B + bb) * ep.hs_H + hh) * ep.hs_rows + nn) * ep.hs_dpad + dd;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(f[g8 * 8 + 0], f[g8 * 8 + 1]), pack_bf16(f[g8 * 8 + 2], f[g8 * 8 + 3]),
+                                                    pack_bf16(f[g8 * 8 + 4], f[g8 * 8 + 5]), pack_bf16(f[g8 * 8 + 6], f[g8 * 8 + 7]));
+      }
+    }
+  } else {
+    bf16* y = reinterpret_cast<bf16*>(ep.y) + (long long)row * ep.ldy + out_col0;
+    if (FULL && ((reinterpret_cast<uintptr_t>(y) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8)
+        *reinterpret_cast<uint4*>(y + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]), pack_bf16(f[j + 4], f[j + 5]),
+                                                      pack_bf16(f[j + 6], f[j + 7]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (FULL || out_col0 + j < out_n) y[j] = __float2bfloat16(f[j]);
+    }
+  }
+}
+
+// Persistent kernel: grid = min(#tiles, #SMs); CTA c owns tiles c, c + grid, ...  (n fastest, so CTAs running
+// together share their A rows through L2).  Warp roles (320 threads; the control warps take the HIGH warp ids,
+// which the sub-partition scheduler favours):
+//   warps 0-7  epilogue: tcgen05.ld the fp32 accumulator (TMEM lane quarter = warp id & 3; warps w and w+4 take
+//              alternate 32-column chunks), DoRA column scale, bias, activation, residual, convert, store.  Runs one
+//              tile behind the MMA warp (two TMEM accumulators).  Two warps per scheduler because a lone epilogue
+//              warp runs at ~0.25 IPC (measured: the epilogue, not the main loop, bounded the first version).
+//   warp 8     TMA producer: 64-wide K slabs of X/W (then of T/Bs: the rank-R LoRA tail continues the same
+//              accumulation) into a STAGES-deep 128B-swizzled ring that runs across tile boundaries.
+//   warp 9     TMEM allocator + the single thread that issues tcgen05.mma (M=128, N=BN, K=16).
 template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                        const __grid_constant__ CUtensorMap tmB,
-                                                                        const __grid_constant__ CUtensorMap tmA2,
-                                                                        const __grid_constant__ CUtensorMap tmB2,
-                                                                        const GemmEpilogue ep) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                           const __grid_constant__ CUtensorMap tmB,
+                                                                           const __grid_constant__ CUtensorMap tmA2,
+                                                                           const __grid_constant__ CUtensorMap tmB2,
+                                                                           const GemmEpilogue ep) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int kTma = 8, kMma = 9;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* acc_full = empty_bar + STAGES;     // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * GEMM_BM;
   const int num_kb = ep.num_kb1 + ep.num_kb2;
+  const int num_n = (ep.N + BN - 1) / BN;
+  const int num_tiles = ((ep.M + GEMM_BM - 1) / GEMM_BM) * num_n;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kTma && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (ep.num_kb2 > 0) {
@@ -81,9 +185,12 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tn_tcgen05_kernel(const __g
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 256);
+    }
     fence_barrier_init();
-  } else if (warp == 1) {
+  } else if (warp == kMma) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   }
   tc_fence_before();
@@ -91,153 +198,101 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tn_tcgen05_kernel(const __g
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kTma) {
     // ------------------------------------------------------------------ TMA producer
-    if (elect_one()) {   // elect.sync: ptxas then knows one thread is active -> plain R2UR, no waterfall loops
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-        uint8_t* sb = sa + A_STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-        if (kb < ep.num_kb1) {
-          tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0);
-          tma_load_2d(sb, &tmB, &full_bar[s], kb * GEMM_BK, n0);
-        } else {
-          tma_load_2d(sa, &tmA2, &full_bar[s], (kb - ep.num_kb1) * GEMM_BK, m0);
-          tma_load_2d(sb, &tmB2, &full_bar[s], (kb - ep.num_kb1) * GEMM_BK, n0);
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * GEMM_BM, n0 = (tile % num_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          if (kb < ep.num_kb1) {
+            tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0);
+            tma_load_2d(sb, &tmB, &full_bar[s], kb * GEMM_BK, n0);
+          } else {
+            tma_load_2d(sa, &tmA2, &full_bar[s], (kb - ep.num_kb1) * GEMM_BK, m0);
+            tma_load_2d(sb, &tmB2, &full_bar[s], (kb - ep.num_kb1) * GEMM_BK, n0);
+          }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMma) {
     // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {   // elect.sync: ptxas then knows one thread is active -> plain R2UR, no waterfall loops
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16_f32(GEMM_BM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const uint32_t buf = t & 1;
+        mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1);      // epilogue drained this accumulator (2 tiles ago)
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint32_t sb = sa + A_STAGE_BYTES;
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
-        for (int k = 0; k < GEMM_BK / 16; ++k) {
-          // advancing 16 K-elements inside the swizzle span = +32 bytes on the start address
-          const uint64_t da = make_smem_desc_sw128(sa + k * 32);
-          const uint64_t db = make_smem_desc_sw128(sb + k * 32);
-          umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            if (ep.dbg & 2) break;
+            // advancing 16 K-elements inside the swizzle span = +32 bytes on the start address
+            umma_bf16(d_tmem, make_smem_desc_sw128(sa + k * 32), make_smem_desc_sw128(sb + k * 32), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);   // smem stage reusable once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);   // smem stage reusable once these MMAs have read it
+        umma_commit(&acc_full[buf]);    // accumulator complete
       }
-      umma_commit(tmem_full_bar);     // accumulator complete
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;           // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const bool row_ok = row < ep.M;
+    // ------------------------------------------------------------------ epilogue (warps 0..7)
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = warp >> 2;         // which alternate 32-column chunks this warp owns
     const bool geglu = ep.act == ADAFACE_ACT_GEGLU;
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const uint32_t buf = t & 1;
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int row = m_blk * GEMM_BM + q * 32 + lane;
+      const bool row_ok = row < ep.M;
+      mbar_wait(&acc_full[buf], (t >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+      const int cols_here = min(BN, ep.N - n_blk * BN);                       // real columns of this tile
+      const int n_chunks = geglu ? BN / 64 : (cols_here + 31) / 32;
+      bool arrived = false;
+      if ((ep.dbg & 4) || half >= n_chunks) {
+        tc_fence_before();
+        mbar_arrive(&acc_empty[buf]);
+        arrived = true;
+      }
+      if (!(ep.dbg & 4)) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      if (n0 + c0 >= ep.N && !geglu) break;           // warp-uniform
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
-      float f[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int col = n0 + c0 + j;
-        float a = __uint_as_float(v[j]);
-        if (col < ep.N) {
-          if (ep.colscale) a *= __ldg(ep.colscale + col);
-          if (ep.bias) a += __ldg(ep.bias + col);
-        }
-        f[j] = a;
-      }
-      int out_col0 = n0 + c0;          // first output column of this 16-wide group
-      int out_n = ep.N;
-      if (geglu) {
-        // tile columns [0, BN/2) are the "a" half, [BN/2, BN) the gates of the same output columns.
-        if (c0 >= BN / 2) break;
-        uint32_t g[16];
-        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + BN / 2), g);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = n0 + c0 + BN / 2 + j;
-          float gt = __uint_as_float(g[j]);
-          if (col < ep.N) {
-            if (ep.colscale) gt *= __ldg(ep.colscale + col);
-            if (ep.bias) gt += __ldg(ep.bias + col);
+        for (int ci = half; ci < n_chunks; ci += 2) {
+          const int c0 = ci * 32;
+          uint32_t v[32], g[32];
+          tmem_ld_32x32b_x32_wait(t_acc + (uint32_t)c0, v);
+          if (geglu) tmem_ld_32x32b_x32_wait(t_acc + (uint32_t)(c0 + BN / 2), g);
+          if (ci + 2 >= n_chunks && !arrived) {
+            // last TMEM read of this warp for this tile: hand the accumulator back before the global stores
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);
+            arrived = true;
           }
-          f[j] = f[j] * gelu_erf(gt);
-        }
-        out_col0 = blockIdx.x * (BN / 2) + c0;
-        out_n = ep.N / 2;
-      } else if (ep.act == ADAFACE_ACT_QUICK_GELU) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = f[j] / (1.f + __expf(-1.702f * f[j]));
-      }
-      if (!row_ok) continue;
-      if (ep.residual) {
-        if (ep.res_f32) {
-          const float* r = reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + out_col0;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (out_col0 + j < out_n) f[j] += r[j];
-        } else {
-          const bf16* r = reinterpret_cast<const bf16*>(ep.residual) + (long long)row * ep.ldr + out_col0;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (out_col0 + j < out_n) f[j] += __bfloat162float(r[j]);
-        }
-      }
-      if (ep.y_f32) {
-        float* y = reinterpret_cast<float*>(ep.y) + (long long)row * ep.ldy + out_col0;
-        if (out_col0 + 16 <= out_n && ((reinterpret_cast<uintptr_t>(y) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(y + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (out_col0 + j < out_n) y[j] = f[j];
-        }
-      } else if (ep.hs_d > 0) {
-        const int bb = row / ep.hs_rows, nn = row - bb * ep.hs_rows;
-#pragma unroll
-        for (int g8 = 0; g8 < 2; ++g8) {
-          const int col = out_col0 + g8 * 8;             // 8-column groups never straddle a head (hs_d % 8 == 0)
-          if (col < out_n) {
-            const int which = col / ep.hs_C, rem = col - which * ep.hs_C;
-            const int hh = rem / ep.hs_d, dd = rem - hh * ep.hs_d;
-            bf16* dst = reinterpret_cast<bf16*>(ep.y) +
-                        ((((long long)which * ep.hs_B + bb) * ep.hs_H + hh) * ep.hs_rows + nn) * ep.hs_dpad + dd;
-            *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(f[g8 * 8 + 0], f[g8 * 8 + 1]), pack_bf16(f[g8 * 8 + 2], f[g8 * 8 + 3]),
-                                                        pack_bf16(f[g8 * 8 + 4], f[g8 * 8 + 5]), pack_bf16(f[g8 * 8 + 6], f[g8 * 8 + 7]));
-          }
-        }
-      } else {
-        bf16* y = reinterpret_cast<bf16*>(ep.y) + (long long)row * ep.ldy + out_col0;
-        if (out_col0 + 16 <= out_n && ((reinterpret_cast<uintptr_t>(y) & 15) == 0)) {
-          uint4 p0 = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-          uint4 p1 = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]),
-                                pack_bf16(f[14], f[15]));
-          *reinterpret_cast<uint4*>(y) = p0;
-          *reinterpret_cast<uint4*>(y + 8) = p1;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (out_col0 + j < out_n) y[j] = __float2bfloat16(f[j]);
+          const bool full = geglu || (n_blk * BN + c0 + 32 <= ep.N);
+          if (full) epilogue_chunk32<BN, true>(ep, v, g, row, row_ok, n_blk, c0);
+          else epilogue_chunk32<BN, false>(ep, v, g, row, row_ok, n_blk, c0);
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMma) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
@@ -256,7 +311,14 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
                                  Cfg::SMEM_BYTES));
     configured = true;
   }
-  dim3 grid(n_tiles, (ep.M + GEMM_BM - 1) / GEMM_BM);
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    AF_CUDA(cudaGetDevice(&dev));
+    AF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int tiles = n_tiles * ((ep.M + GEMM_BM - 1) / GEMM_BM);
+  dim3 grid(tiles < num_sms ? tiles : num_sms);
   gemm_tn_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tA, tB, tA2, tB2, ep);
   AF_CUDA(cudaGetLastError());
   ++g_launch_count;
@@ -292,22 +354,33 @@ int proj_lora_fwd(const void* x, int64_t ldx, const void* w, const void* t, int6
   }
   AF_CHECK(M < (1ll << 31) && N < (1ll << 31), "proj_lora_fwd: M/N too large");
 
+  // Tile width: the widest of {256, 192, 160, 128, 64} that wastes no column and still gives every SM a tile.
   int BN;
+  const long long m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
   if (act == ADAFACE_ACT_GEGLU) {
     AF_CHECK(N % 128 == 0, "proj_lora_fwd: GEGLU needs N %% 128 == 0 (packed [a|g] tiles), got %lld", (long long)N);
     BN = 128;
-  } else if (N % 160 == 0 && M >= 2048) {
-    BN = 160;
-  } else if (N % 128 == 0 || N > 512) {
-    BN = 128;
-  } else if (N <= 64 || N % 128 <= 64) {
-    BN = 64;
   } else {
-    BN = 128;
+    BN = 0;
+    // cost model: rounds over the 148 SMs x (tile width + fixed per-tile overhead); exact divisors of N only
+    const int cand[5] = {256, 192, 160, 128, 64};
+    long long best = -1;
+    for (int i = 0; i < 5; ++i) {
+      if (N % cand[i]) continue;
+      const long long tiles = m_tiles * (N / cand[i]);
+      const long long cost = ((tiles + 147) / 148) * (cand[i] + 64);
+      if (best < 0 || cost < best) { best = cost; BN = cand[i]; }
+    }
+    if (!BN) BN = (N <= 64 || N % 128 <= 64) && N < 256 ? 64 : 128;   // ragged N: masked last tile
   }
-  // Small problems: prefer more, narrower tiles so that more SMs get work.
-  if (BN == 128 && act != ADAFACE_ACT_GEGLU && ((M + 127) / 128) * ((N + 127) / 128) < 148 && N % 64 == 0) BN = 64;
-
+  {
+    static int force_bn = -1;
+    if (force_bn < 0) {
+      const char* e = getenv("ADAFACE_GEMM_BN");     // tuning knob: force the tile width (64 / 128 / 160)
+      force_bn = e ? atoi(e) : 0;
+    }
+    if (force_bn && act != ADAFACE_ACT_GEGLU) BN = force_bn;
+  }
   CUtensorMap tA, tB, tA2, tB2;
   if (make_tmap_bf16_2d(&tA, x, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, GEMM_BM)) return 3;
   if (make_tmap_bf16_2d(&tB, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)BN)) return 3;
@@ -338,11 +411,18 @@ int proj_lora_fwd(const void* x, int64_t ldx, const void* w, const void* t, int6
   ep.hs_C = (int)(hs_heads * hs_d);
   ep.hs_rows = (int)hs_rows;
   ep.hs_B = hs_rows > 0 ? (int)(M / hs_rows) : 0;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("ADAFACE_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
+    ep.dbg = dbg;
+  }
   const int n_tiles = (int)((N + BN - 1) / BN);
   switch (BN) {
     case 64: return launch_gemm<64>(tA, tB, tA2, tB2, ep, n_tiles, stream);
     case 128: return launch_gemm<128>(tA, tB, tA2, tB2, ep, n_tiles, stream);
     case 160: return launch_gemm<160>(tA, tB, tA2, tB2, ep, n_tiles, stream);
+    case 192: return launch_gemm<192>(tA, tB, tA2, tB2, ep, n_tiles, stream);
+    case 256: return launch_gemm<256>(tA, tB, tA2, tB2, ep, n_tiles, stream);
   }
   set_error("proj_lora_fwd: unreachable tile width %d", BN);
   return 1;

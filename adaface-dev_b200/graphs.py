@@ -1,0 +1,35 @@
+"""CUDA-graph capture of a hot-path callable.
+
+The SD-1.5 attention stack is 112 kernel launches per U-Net step, most of them a few microseconds long: driven
+from Python the step is launch-bound.  ``graphed(fn, *example_inputs)`` warms the callable up (so that every kernel
+variant has been configured and every weight pack / workspace exists), captures one invocation into a CUDA graph
+and returns a function that copies new inputs into the captured input buffers and replays the graph.  Tensor maps
+and all other kernel arguments are baked into the graph; outputs live in the graph's private pool and are
+overwritten by the next replay (clone them if they must survive).
+"""
+import torch
+
+
+def graphed(fn, *example_inputs, warmup=3):
+    static_in = [x.clone() if torch.is_tensor(x) else x for x in example_inputs]
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s), torch.no_grad():
+        for _ in range(warmup):
+            fn(*static_in)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.no_grad(), torch.cuda.graph(g):
+        static_out = fn(*static_in)
+
+    def replay(*inputs):
+        for dst, src in zip(static_in, inputs):
+            if torch.is_tensor(dst) and src is not dst:
+                dst.copy_(src, non_blocking=True)
+        g.replay()
+        return static_out
+
+    replay.graph = g
+    replay.static_inputs = static_in
+    return replay
