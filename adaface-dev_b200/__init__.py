@@ -18,5 +18,6 @@ from .subj_basis_generator import (SubjBasisGenerator, CLIPTextModelWrapper, CLI
                                    template_ids)
 from .build import build  # noqa: F401
 from .graphs import graphed  # noqa: F401
+from . import parallel  # noqa: F401
 
 __version__ = "0.1.0"

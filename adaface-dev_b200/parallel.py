@@ -1,0 +1,90 @@
+"""Multi-GPU plumbing of the hot path: one process per GPU.
+
+Inference shards the denoising batch -- every image x CFG branch is independent through the whole U-Net -- so there
+is NO data-path collective: each rank takes a contiguous range of images and keeps each image's (cond, uncond) pair
+local so that the CFG combine (ldm/models/diffusion/ddim.py:253-255) stays on the rank.  Training is data parallel
+as in the reference (Lightning DDP, main.py:618): one bucketed all-reduce of the trainable gradients
+(SubjBasisGenerator + attention LoRA) per optimizer step, NCCL over NVLink on GPUs, gloo in the CPU tests.
+"""
+from typing import Iterable, List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced [begin, end) range of `n_items` for `rank` (first n_items % world ranks get one extra)."""
+    if not (0 <= rank < world) or n_items < 0:
+        raise ValueError(f"bad shard request n_items={n_items} rank={rank} world={world}")
+    base, extra = divmod(n_items, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def cfg_batch_indices(n_images: int, rank: int, world: int) -> torch.Tensor:
+    """Rows of the CFG-doubled batch this rank owns.  The LDM sampler stacks the batch as [cond_0..cond_{B-1},
+    uncond_0..uncond_{B-1}] (ddim.py:239-248): image i lives at rows i and B+i, and both go to the same rank."""
+    b, e = shard_range(n_images, rank, world)
+    idx = torch.arange(b, e)
+    return torch.cat([idx, idx + n_images])
+
+
+def shard_cfg_batch(tensors: Sequence[torch.Tensor], n_images: int, rank: int, world: int) -> List[torch.Tensor]:
+    """Slice [2*n_images, ...] tensors (latents, contexts, timesteps) down to this rank's images, pairs kept together;
+    the local result is again ordered [cond.., uncond..] so subj_indices need no offset."""
+    idx = cfg_batch_indices(n_images, rank, world)
+    out = []
+    for t in tensors:
+        if t.shape[0] != 2 * n_images:
+            raise ValueError(f"expected leading dim {2 * n_images}, got {tuple(t.shape)}")
+        out.append(t.index_select(0, idx.to(t.device)))
+    return out
+
+
+def cfg_combine(eps: torch.Tensor, scale: float) -> torch.Tensor:
+    """e_t = e_uncond + scale * (e_cond - e_uncond) on a local [cond.., uncond..] batch (ddim.py:253-255)."""
+    e_c, e_u = eps.chunk(2, dim=0)
+    return e_u + scale * (e_c - e_u)
+
+
+def gather_images(local: torch.Tensor, n_images: int, group=None) -> torch.Tensor:
+    """Optional final gather of per-rank results [n_local, ...] into [n_images, ...] on every rank (the only
+    communication of a sampling run: 32 KB per image for 4x64x64 latents)."""
+    world = dist.get_world_size(group)
+    sizes = [shard_range(n_images, r, world) for r in range(world)]
+    n_max = max(e - b for b, e in sizes)                       # ragged shards: pad to the largest, trim after
+    padded = local.new_zeros((n_max,) + tuple(local.shape[1:]))
+    padded[:local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:e - b] for p, (b, e) in zip(parts, sizes)], dim=0)
+
+
+def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, bucket_bytes: int = 64 << 20,
+                        average: bool = True) -> int:
+    """Bucketed gradient all-reduce of the trainable parameters (what DDP does at the accumulation boundary,
+    main.py:618 / yaml:149).  Parameters without a gradient contribute zeros so that every rank issues the same
+    collectives.  NVSwitch makes the cost launch-latency bound, hence few large flat buckets.  Returns #buckets."""
+    params = [p for p in params if p.requires_grad]
+    world = dist.get_world_size(group)
+    n_buckets, i = 0, 0
+    while i < len(params):
+        bucket, size = [], 0
+        while i < len(params) and (not bucket or size + params[i].numel() * 4 <= bucket_bytes):
+            bucket.append(params[i])
+            size += params[i].numel() * 4
+            i += 1
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat /= world
+        off = 0
+        for p in bucket:
+            g = flat[off:off + p.numel()].view_as(p).to(p.dtype)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += p.numel()
+        n_buckets += 1
+    return n_buckets
