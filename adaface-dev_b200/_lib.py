@@ -18,9 +18,9 @@ SIGNATURES = {
     "adaface_proj_lora_fwd": [_p, _i64, _p, _p, _i64, _p, _p, _p, _p, _i64, _i32, _p, _i64, _i32, _i64, _i64, _i64,
                               _i64, _i32, _p],
     "adaface_attn_fwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
-                         _p, _i32, _f32, _p],
+                         _p, _i32, _f32, _p, _p],
     "adaface_attn_headmajor_fwd": [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _i64, _i64,
-                                   _i64, _i64, _i64, _i64, _i64, _i64, _f32, _p],
+                                   _i64, _i64, _i64, _i64, _i64, _i64, _f32, _p, _p],
     "adaface_proj_lora_heads_fwd": [_p, _i64, _p, _p, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
                                     _p],
     "adaface_attn_cross_capture_fwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64,
@@ -29,7 +29,23 @@ SIGNATURES = {
     "adaface_capture_chan_major": [_p, _i32, _i64, _i64, _i64, _i64, _i64, _f32, _p, _p],
     "adaface_layernorm_fwd": [_p, _i32, _i64, _p, _p, _p, _i32, _i64, _i64, _i64, _f32, _p],
     "adaface_sbg_head_fwd": [_p, _p, _p, _p, _c.POINTER(_f32), _i32, _i64, _p, _p, _p, _i64, _i64, _i64, _f32, _p],
+    # ---- backward (ABI v2)
+    "adaface_attn_bwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _p,
+                         _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _i32, _f32, _p],
+    "adaface_attn_cross_capture_bwd_chunks": [_i64, _i64, _i64],
+    "adaface_attn_cross_capture_bwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _i64, _i64,
+                                       _i64, _i64, _i64, _f32, _p, _p, _p, _i32, _i32, _p, _i64, _i64, _p, _i64, _i64, _p, _i64,
+                                       _i64, _i32, _p, _f32, _p, _p, _p, _p],
+    "adaface_transpose": [_p, _i32, _i64, _i64, _p, _i32, _i64, _i64, _i64, _i64, _i64, _f32, _p, _p, _p],
+    "adaface_colsum": [_p, _i32, _i64, _p, _i32, _i64, _p, _p, _p, _i64, _i64, _p],
+    "adaface_layernorm_bwd": [_p, _i32, _i64, _p, _i32, _i64, _p, _p, _i64, _p, _p, _i64, _i64, _f32, _p],
+    "adaface_act_fwd": [_p, _i64, _p, _i64, _i64, _i64, _i32, _p],
+    "adaface_act_bwd": [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i32, _p],
+    "adaface_sbg_head_bwd": [_p, _p, _p, _p, _c.POINTER(_f32), _i32, _i64, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _i64,
+                             _i64, _f32, _p],
 }
+# entry points that return a value instead of a status
+VALUE_RETURNING = ("adaface_version", "adaface_last_error", "adaface_launch_count", "adaface_attn_cross_capture_bwd_chunks")
 
 _lib = None
 
@@ -59,6 +75,10 @@ def call(name, *args):
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed (status {rc}): {lib.adaface_last_error().decode()}")
+
+
+def cross_capture_bwd_chunks(B, H, Lq):
+    return int(load().adaface_attn_cross_capture_bwd_chunks(B, H, Lq))
 
 
 def launch_count():

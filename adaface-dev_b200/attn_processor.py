@@ -219,6 +219,10 @@ class AttnProcessor_LoRA_Capture(nn.Module):
         if not hidden_states.is_cuda:
             raise RuntimeError("adaface_b200 AttnProcessor_LoRA_Capture runs on CUDA only (no CPU fallback)")
 
+        if torch.is_grad_enabled() and (hidden_states.requires_grad or (
+                encoder_hidden_states is not None and encoder_hidden_states.requires_grad) or self._has_trainable()):
+            return self._call_train(attn, hidden_states, encoder_hidden_states, img_mask, subj_indices)
+
         residual = hidden_states
         in_dtype = hidden_states.dtype
         input_ndim = hidden_states.ndim
@@ -326,3 +330,112 @@ class AttnProcessor_LoRA_Capture(nn.Module):
         return hidden_out
 
     forward = __call__
+
+    # -------------------------------------------------------------------------------------------- training path
+    def _has_trainable(self):
+        if self.enable_lora and any(p.requires_grad for n in ("q", "k", "v", "out") if getattr(self, f"to_{n}_lora") is not None
+                                    for p in getattr(self, f"to_{n}_lora").parameters()):
+            return True
+        return bool(self.normalize_cross_attn and self.cross_attn_scale_factor.requires_grad)
+
+    def _subj_aux(self, B, S, subj_indices, device):
+        """col_flag [B,S] uint8 for normalize (dalc:119-133) and subj_cols [B,n] int32 for the subject-columns capture."""
+        col_flag = subj_cols = None
+        if self.normalize_cross_attn and not self.mix_attn_mats_in_batch:
+            if subj_indices is None:
+                raise ValueError("normalize_cross_attn=True requires subj_indices (dalc:120)")
+            ib, in_ = subj_indices
+            col_flag = torch.zeros((B, S), device=device, dtype=torch.uint8)
+            col_flag[ib.long(), in_.long()] = 1
+        if self.capture_subj_cols_only and subj_indices is not None:
+            ib, in_ = subj_indices
+            n_sub = int(ib.numel() // B)
+            subj_cols = torch.full((B, n_sub), -1, device=device, dtype=torch.int32)
+            subj_cols[ib.long(), torch.arange(ib.numel(), device=device) % n_sub] = in_.to(torch.int32)
+        return col_flag, subj_cols
+
+    def _call_train(self, attn, hidden_states, encoder_hidden_states, img_mask, subj_indices):
+        """Same arithmetic as ``__call__`` with every kernel paired with its backward (autograd.py): gradients reach
+        hidden_states, encoder_hidden_states (=> SubjBasisGenerator), the LoRA A / B / DoRA magnitudes and
+        cross_attn_scale_factor (x10 GradientScaler, dalc:129), including through every cached activation.  The
+        frozen base weights get none.  Layout differences from the inference path: q/k/v stay in plain [B, L, C]
+        buffers (they are saved for the recompute-form backward), K and V are projected separately on the capture path."""
+        from . import autograd as ag
+        residual = hidden_states
+        in_dtype = hidden_states.dtype
+        input_ndim = hidden_states.ndim
+        if input_ndim == 4:
+            bsz, channel, height, width = hidden_states.shape
+            hidden_states = hidden_states.view(bsz, channel, height * width).transpose(1, 2)
+        B, N, C_in = hidden_states.shape
+        H = attn.heads
+        x2d = hidden_states.to(torch.bfloat16).contiguous().view(B * N, C_in)
+        pk = _bf16_pack(attn)
+        lora = (lambda n: getattr(self, f"to_{n}_lora")) if self.enable_lora else (lambda n: None)
+        is_cross = encoder_hidden_states is not None
+        C = pk["wq"].shape[0]
+        sm_scale = 1.0 / math.sqrt(C // H)
+        q = q2 = k = v = prob = score = prob_subj = None
+
+        if not is_cross:
+            key_mask = img_mask_to_key_mask(img_mask, N) if img_mask is not None else None
+            if all(lora(n) is None for n in ("q", "k", "v")) and "wqkv" in pk:
+                qkv = ag.linear(x2d, pk, "wqkv", "bqkv").view(B, N, 3 * C)
+                o = ag.attention(qkv, qkv, qkv, (0, C, 2 * C), C, C, H, sm_scale, key_mask)
+            else:
+                q = ag.linear(x2d, pk, "wq", "bq", lora=lora("q") if self.q_lora_updates_query else None).view(B, N, C)
+                k = ag.linear(x2d, pk, "wk", "bk", lora=lora("k")).view(B, N, C)
+                v = ag.linear(x2d, pk, "wv", "bv", lora=lora("v")).view(B, N, C)
+                o = ag.attention(q, k, v, (0, 0, 0), C, C, H, sm_scale, key_mask)
+        else:
+            ctx = encoder_hidden_states.to(torch.bfloat16).contiguous()
+            S = ctx.shape[1]
+            c2d = ctx.view(B * S, ctx.shape[2])
+            hp = bool(self.capture_ca_activations or self.normalize_cross_attn)
+            pdt = torch.float32 if hp else torch.bfloat16
+            if lora("q") is not None:                                                # dalc:239-249
+                q2 = ag.linear(x2d, pk, "wq", "bq", lora=lora("q"), out_dtype=pdt).view(B, N, C)
+                q = q2 if self.q_lora_updates_query else ag.linear(x2d, pk, "wq", "bq", out_dtype=pdt).view(B, N, C)
+            else:
+                q = q2 = ag.linear(x2d, pk, "wq", "bq", out_dtype=pdt).view(B, N, C)
+            if hp or lora("k") is not None or lora("v") is not None:
+                k = ag.linear(c2d, pk, "wk", "bk", lora=lora("k"), out_dtype=pdt).view(B, S, C)   # dalc:280-283
+                v = ag.linear(c2d, pk, "wv", "bv", lora=lora("v"), out_dtype=pdt).view(B, S, C)   # dalc:285-288
+            if hp:                                                                   # dalc:309-315
+                mix = bool(self.mix_attn_mats_in_batch)
+                if mix and B % 2:
+                    raise ValueError("mix_attn_mats_in_batch needs an even batch ordered [sc.., mc..] (dalc:113)")
+                col_flag, subj_cols = self._subj_aux(B, S, subj_indices, x2d.device)
+                if self.cross_attn_scale_factor.device != x2d.device:
+                    self.cross_attn_scale_factor.data = self.cross_attn_scale_factor.data.to(x2d.device)
+                cap = bool(self.capture_ca_activations)
+                o, prob, score, prob_subj = ag.CrossCaptureFn.apply(q, k, v, self.cross_attn_scale_factor, H, sm_scale, cap,
+                                                                    cap, col_flag, subj_cols, mix, 10.0)
+            elif k is None:
+                kv = ag.linear(c2d, pk, "wkv", "bkv").view(B, S, 2 * C)
+                o = ag.attention(q, kv, kv, (0, 0, C), C, C, H, sm_scale)
+            else:
+                o = ag.attention(q, k, v, (0, 0, 0), C, C, H, sm_scale)
+
+        out = ag.linear(o.view(B * N, C), pk, "wo", "bo", lora=lora("out")).view(B, N, -1)   # dalc:328-334
+        hidden_out = out.to(in_dtype)
+        if input_ndim == 4:
+            hidden_out = hidden_out.transpose(-1, -2).reshape(bsz, channel, height, width)
+        if getattr(attn, "residual_connection", False):
+            hidden_out = hidden_out + residual
+        rescale = getattr(attn, "rescale_output_factor", 1.0)
+        if rescale != 1.0:
+            hidden_out = hidden_out / rescale
+        if is_cross and self.capture_ca_activations:                                 # dalc:344-362
+            f = math.sqrt(1.0 / math.sqrt(C))
+            ca = self.cached_activations
+            ca["q"] = ag.ChanMajorFn.apply(q, f)
+            ca["q2"] = ca["q"] if q2 is q else ag.ChanMajorFn.apply(q2, f)
+            ca["k"] = ag.ChanMajorFn.apply(k, f)
+            ca["v"] = ag.ChanMajorFn.apply(v, f)
+            ca["attn"], ca["attnscore"] = prob, score
+            ca["attn_out"] = ag.ChanMajorFn.apply(out, 1.0) if (input_ndim == 3 and rescale == 1.0 and not getattr(
+                attn, "residual_connection", False)) else hidden_out.float().permute(0, 2, 1).contiguous()
+            if prob_subj is not None:
+                ca["attn_subj"] = prob_subj
+        return hidden_out

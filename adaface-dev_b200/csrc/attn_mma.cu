@@ -12,26 +12,12 @@
 #include <math.h>
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "attn_common.cuh"
 #include "../../include/adaface_b200.h"
 
 namespace adaface {
 
 extern long long g_launch_count;
-
-constexpr int ATT_BM = 64;       // queries per CTA (4 warps x 16 rows)
-constexpr int ATT_BN = 64;       // keys per pipeline stage
-constexpr int ATT_THREADS = 128;
-constexpr float LOG2E = 1.4426950408889634f;
-
-template <int D>
-struct AttDims {
-  static constexpr int DP = (D + 15) / 16 * 16;   // MMA-K padded head dim
-  static constexpr int LD = DP + 8;               // smem row pitch (elements): conflict-free ldmatrix
-  static constexpr int KT = DP / 16;              // k16 steps of Q.K^T
-  static constexpr int NT_O = D / 8;              // n8 tiles of the output
-  static constexpr int CH = D / 8;                // 16-byte chunks per row in HBM
-};
 
 struct AttnParams {
   const bf16 *q, *k, *v;
@@ -41,30 +27,8 @@ struct AttnParams {
   const uint8_t* key_mask;
   int causal_mult;
   float scale_log2;
+  float* lse;   // optional [B, H, Lq]: log2(sum_j exp2(s_ij)) for the backward pass (+inf for an empty row)
 };
-
-// rows [row0, row0+rows) of a [L, H*d] head slice -> smem tile (zero fill beyond L)
-// mult > 1: row j is sub-key (j % mult) of token (j / mult), the sub-keys of a token being `sub` elements apart.
-template <int D>
-__device__ __forceinline__ void load_rows(bf16* s, const bf16* g, long long stride_n, int row0, int L, int rows,
-                                          int mult = 1, int sub = 0) {
-  constexpr int CH = AttDims<D>::CH, LD = AttDims<D>::LD;
-  for (int c = threadIdx.x; c < rows * CH; c += blockDim.x) {
-    const int r = c / CH, ch = c - r * CH;
-    const int gr = row0 + r;
-    const bool ok = gr < L;
-    const int j = ok ? gr : 0;
-    const long long off = mult > 1 ? (long long)(j / mult) * stride_n + (long long)(j % mult) * sub : (long long)j * stride_n;
-    cp_async_16(s + r * LD + ch * 8, g + off + ch * 8, ok);
-  }
-}
-template <int D>
-__device__ __forceinline__ void zero_pad_cols(bf16* s, int rows) {
-  constexpr int DP = AttDims<D>::DP, LD = AttDims<D>::LD;
-  if (DP == D) return;
-  for (int r = threadIdx.x; r < rows; r += blockDim.x)
-    *reinterpret_cast<uint4*>(s + r * LD + D) = make_uint4(0, 0, 0, 0);   // DP - D == 8 elements
-}
 
 template <int D>
 __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams p) {
@@ -222,6 +186,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
     l += __shfl_xor_sync(0xffffffffu, l, 1);
     l += __shfl_xor_sync(0xffffffffu, l, 2);
     inv[i] = l > 0.f ? 1.f / l : 0.f;
+    const int r = r_lo + i * 8;
+    if (p.lse && t == 0 && r < p.Lq)
+      p.lse[((long long)b * p.H + h) * p.Lq + r] = l > 0.f ? m_run[i] + log2f(l) : INFINITY;
   }
   bf16* sO = sQ + warp * 16 * LD;
   __syncwarp();
@@ -266,7 +233,7 @@ static int check_view(const char* what, const void* ptr, int64_t sb, int64_t sn,
 
 int attn_fwd_tcgen05(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, const void*, int64_t,
                      int64_t, int64_t, void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
-                     float, cudaStream_t);
+                     float, float*, cudaStream_t);
 
 static bool legacy_attention_forced() {
   static int v = -1;
@@ -279,7 +246,8 @@ static bool legacy_attention_forced() {
 
 int attn_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn, const void* v,
              int64_t v_sb, int64_t v_sn, void* o, int64_t o_sb, int64_t o_sn, int64_t B, int64_t H, int64_t Lq,
-             int64_t Lk, int64_t d, const uint8_t* key_mask, int causal_mult, float scale, cudaStream_t stream) {
+             int64_t Lk, int64_t d, const uint8_t* key_mask, int causal_mult, float scale, float* lse,
+             cudaStream_t stream) {
   if (check_view("q", q, q_sb, q_sn, d) || check_view("k", k, k_sb, k_sn, d) || check_view("v", v, v_sb, v_sn, d) ||
       check_view("o", o, o_sb, o_sn, d))
     return 1;
@@ -289,7 +257,7 @@ int attn_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k
   AF_CHECK(causal_mult >= 0, "attn_fwd: causal_mult must be >= 0");
   if (!key_mask && causal_mult == 0 && !legacy_attention_forced()) {
     // unmasked attention: tcgen05 / TMEM kernel (attn_tcgen05.cu)
-    const int rc = attn_fwd_tcgen05(q, q_sb, d, q_sn, k, k_sb, d, k_sn, v, v_sb, d, v_sn, o, o_sb, o_sn, B, H, Lq, Lk, d, d, d, scale, stream);
+    const int rc = attn_fwd_tcgen05(q, q_sb, d, q_sn, k, k_sb, d, k_sn, v, v_sb, d, v_sn, o, o_sb, o_sn, B, H, Lq, Lk, d, d, d, scale, lse, stream);
     if (rc >= 0) return rc;
   }
   AttnParams p;
@@ -299,6 +267,7 @@ int attn_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k
   p.key_mask = key_mask;
   p.causal_mult = causal_mult;
   p.scale_log2 = scale * LOG2E;
+  p.lse = lse;
   switch (d) {
     case 40: return launch_attn<40>(p, stream);
     case 64: return launch_attn<64>(p, stream);
@@ -329,31 +298,6 @@ struct CapParams {
   const float* ca_scale;   // device scalar (cross_attn_scale_factor) or null = 1
   int mix;
 };
-
-// fp32 rows -> bf16 hi (+ lo = bf16(x - hi)) tiles: q.k is then evaluated as hi.hi + lo.hi + hi.lo, i.e. to ~2^-17
-// relative, so that captured probabilities meet the 1e-3 bar (plain bf16 q/k give ~3e-3).
-template <int D>
-__device__ __forceinline__ void load_rows_f32_split(bf16* s_hi, bf16* s_lo, const float* g, long long stride_n, int row0,
-                                                    int L, int rows) {
-  constexpr int LD = AttDims<D>::LD, C4 = D / 4;
-  for (int c = threadIdx.x; c < rows * C4; c += blockDim.x) {
-    const int r = c / C4, c4 = c - r * C4;
-    const int gr = row0 + r;
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gr < L) x = *reinterpret_cast<const float4*>(g + (long long)gr * stride_n + c4 * 4);
-    const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
-    uint2 hv;
-    hv.x = *reinterpret_cast<const uint32_t*>(&h01);
-    hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-    *reinterpret_cast<uint2*>(s_hi + r * LD + c4 * 4) = hv;
-    if (s_lo) {
-      uint2 lv;
-      lv.x = pack_bf16(x.x - __bfloat162float(h01.x), x.y - __bfloat162float(h01.y));
-      lv.y = pack_bf16(x.z - __bfloat162float(h23.x), x.w - __bfloat162float(h23.y));
-      *reinterpret_cast<uint2*>(s_lo + r * LD + c4 * 4) = lv;
-    }
-  }
-}
 
 template <int D, bool MIX, bool F32IN>
 __global__ void __launch_bounds__(ATT_THREADS) attn_cross_capture_kernel(const CapParams p) {

@@ -55,6 +55,7 @@ struct TaParams {
   float scale_log2;
   int phase_ns;            // experiment: delay of every second CTA per SM (0 = off)
   unsigned* sm_counter;    // [256] per-SM arrival counters (experiment only)
+  float* lse;              // optional [B, H, Lq]: log2-domain log-sum-exp of each row, kept for the backward pass
 };
 
 // exp2 on the FMA/ALU pipes for a pair of values in [-126, 8]: Cody-Waite split with the 1.5*2^23 magic constant,
@@ -299,6 +300,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     tc_fence_after();
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
     const int grow = m0 + row;
+    if (p.lse && grow < p.Lq)
+      p.lse[((long long)b * gridDim.y + h) * p.Lq + grow] = l_run > 0.f ? m_ref + log2f(l_run) : INFINITY;
     bf16* orow = p.o + (long long)b * p.o_sb + (long long)grow * p.o_sn + h * D;
 #pragma unroll
     for (int c = 0; c < DO / 16; ++c) {
@@ -510,6 +513,8 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     tc_fence_after();
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
     const int grow = m0 + row;
+    if (p.lse && grow < p.Lq)
+      p.lse[((long long)b * gridDim.y + h) * p.Lq + grow] = l_run > 0.f ? m_ref + log2f(l_run) : INFINITY;
     bf16* orow = p.o + (long long)b * p.o_sb + (long long)grow * p.o_sn + h * D;
 #pragma unroll
     for (int c = 0; c < DO / 16; ++c) {
@@ -579,7 +584,7 @@ static int launch_ta(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtenso
 int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sh,
                      int64_t k_sn, const void* v, int64_t v_sb, int64_t v_sh, int64_t v_sn, void* o, int64_t o_sb,
                      int64_t o_sn, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t d, int64_t drow_q, int64_t drow_kv,
-                     float scale, cudaStream_t stream) {
+                     float scale, float* lse, cudaStream_t stream) {
   if (!(d == 40 || d == 80 || d == 160)) return -1;
   // drow_* = elements that exist in a row: d, or the zero-padded width of a head-major buffer
   if (drow_q < d) drow_q = d;
@@ -595,6 +600,7 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, co
   p.Lq = (int)Lq;
   p.Lk = (int)Lk;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.lse = lse;
   static unsigned* sm_counter = nullptr;
   static int phase_ns = -1;
   if (phase_ns < 0) {

@@ -83,10 +83,28 @@ int proj_lora_fwd(const void*, int64_t, const void*, const void*, int64_t, const
                   const void*, int64_t, int, void*, int64_t, int, int64_t, int64_t, int64_t, int64_t, int, int64_t, int64_t,
                   int64_t, int64_t, cudaStream_t);
 int attn_fwd(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t, int64_t, void*, int64_t,
-             int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, const uint8_t*, int, float, cudaStream_t);
+             int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, const uint8_t*, int, float, float*, cudaStream_t);
 int attn_fwd_tcgen05(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, const void*, int64_t,
                      int64_t, int64_t, void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
-                     float, cudaStream_t);
+                     float, float*, cudaStream_t);
+int attn_bwd(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t,
+             int64_t, const void*, int64_t, int64_t, const float*, float*, void*, int64_t, int64_t, void*, int64_t, int64_t,
+             void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, const uint8_t*, int, float, cudaStream_t);
+int attn_cross_capture_bwd_chunks(int64_t, int64_t, int64_t);
+int attn_cross_capture_bwd(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t, int64_t,
+                           const void*, int64_t, int64_t, const float*, const float*, int64_t, int64_t, int64_t, int64_t,
+                           int64_t, float, const uint8_t*, const float*, const float*, int, int, void*, int64_t, int64_t, void*,
+                           int64_t, int64_t, void*, int64_t, int64_t, int, float*, float, float*, float*, float*, cudaStream_t);
+int transpose(const void*, int, int64_t, int64_t, void*, int, int64_t, int64_t, int64_t, int64_t, int64_t, float, const float*,
+              const float*, cudaStream_t);
+int colsum(const void*, int, int64_t, const void*, int, int64_t, const float*, const float*, float*, int64_t, int64_t,
+           cudaStream_t);
+int layernorm_bwd(const void*, int, int64_t, const void*, int, int64_t, const float*, void*, int64_t, float*, float*, int64_t,
+                  int64_t, float, cudaStream_t);
+int act_fwd(const void*, int64_t, void*, int64_t, int64_t, int64_t, int, cudaStream_t);
+int act_bwd(const void*, int64_t, const void*, int64_t, void*, int64_t, int64_t, int64_t, int, cudaStream_t);
+int sbg_head_bwd(const float*, const float*, const float*, const float*, const float*, int, int64_t, const float*, const float*,
+                 int64_t, float*, float*, float*, float*, float*, float*, float*, int64_t, int64_t, float, cudaStream_t);
 int attn_cross_capture_fwd(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t, int64_t,
                            void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, float, float*, float*,
                            float*, const int32_t*, int64_t, const uint8_t*, const float*, const float*, int, int, cudaStream_t);
@@ -125,17 +143,17 @@ int adaface_proj_lora_heads_fwd(const void* x, int64_t ldx, const void* w, const
 int adaface_attn_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn,
                      const void* v, int64_t v_sb, int64_t v_sn, void* o, int64_t o_sb, int64_t o_sn, int64_t B,
                      int64_t H, int64_t Lq, int64_t Lk, int64_t d, const uint8_t* key_mask, int causal_mult,
-                     float scale, void* stream) {
+                     float scale, float* lse, void* stream) {
   return attn_fwd(q, q_sb, q_sn, k, k_sb, k_sn, v, v_sb, v_sn, o, o_sb, o_sn, B, H, Lq, Lk, d, key_mask, causal_mult,
-                  scale, (cudaStream_t)stream);
+                  scale, lse, (cudaStream_t)stream);
 }
 
 int adaface_attn_headmajor_fwd(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, const void* k, int64_t k_sb,
                                int64_t k_sh, int64_t k_sn, const void* v, int64_t v_sb, int64_t v_sh, int64_t v_sn, void* o,
                                int64_t o_sb, int64_t o_sn, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t d,
-                               int64_t drow_q, int64_t drow_kv, float scale, void* stream) {
+                               int64_t drow_q, int64_t drow_kv, float scale, float* lse, void* stream) {
   const int rc = attn_fwd_tcgen05(q, q_sb, q_sh, q_sn, k, k_sb, k_sh, k_sn, v, v_sb, v_sh, v_sn, o, o_sb, o_sn, B, H, Lq, Lk,
-                                  d, drow_q, drow_kv, scale, (cudaStream_t)stream);
+                                  d, drow_q, drow_kv, scale, lse, (cudaStream_t)stream);
   if (rc < 0) set_error("adaface_attn_headmajor_fwd: unsupported head dim %lld (40, 80, 160)", (long long)d);
   return rc < 0 ? 1 : rc;
 }
@@ -170,6 +188,67 @@ int adaface_sbg_head_fwd(const float* h0, const float* h1, const float* h2, cons
                          int n_layers, int64_t ldh, const float* w, const float* b, float* out, int64_t ldo,
                          int64_t M, int64_t C, float eps, void* stream) {
   return sbg_head_fwd(h0, h1, h2, h3, wl, n_layers, ldh, w, b, out, ldo, M, C, eps, (cudaStream_t)stream);
+}
+
+int adaface_attn_bwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn, const void* v,
+                     int64_t v_sb, int64_t v_sn, const void* o, int64_t o_sb, int64_t o_sn, const void* dout, int64_t do_sb,
+                     int64_t do_sn, const float* lse, float* delta, void* dq, int64_t dq_sb, int64_t dq_sn, void* dk,
+                     int64_t dk_sb, int64_t dk_sn, void* dv, int64_t dv_sb, int64_t dv_sn, int64_t B, int64_t H, int64_t Lq,
+                     int64_t Lk, int64_t d, const uint8_t* key_mask, int causal_mult, float scale, void* stream) {
+  return attn_bwd(q, q_sb, q_sn, k, k_sb, k_sn, v, v_sb, v_sn, o, o_sb, o_sn, dout, do_sb, do_sn, lse, delta, dq, dq_sb, dq_sn,
+                  dk, dk_sb, dk_sn, dv, dv_sb, dv_sn, B, H, Lq, Lk, d, key_mask, causal_mult, scale, (cudaStream_t)stream);
+}
+
+int adaface_attn_cross_capture_bwd_chunks(int64_t B, int64_t H, int64_t Lq) {
+  return attn_cross_capture_bwd_chunks(B, H, Lq);
+}
+
+int adaface_attn_cross_capture_bwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn,
+                                   const void* v, int64_t v_sb, int64_t v_sn, const void* dout, int64_t do_sb,
+                                   int64_t do_sn, const float* dprob, const float* dscore, int64_t B, int64_t H,
+                                   int64_t Lq, int64_t S, int64_t d, float scale, const uint8_t* col_flag,
+                                   const float* qmean_, const float* ca_scale, int mix, int in_dtype, void* dq, int64_t dq_sb,
+                                   int64_t dq_sn, void* dk, int64_t dk_sb, int64_t dk_sn, void* dv, int64_t dv_sb,
+                                   int64_t dv_sn, int dkv_dtype, float* dca, float dca_mul, float* dk_part,
+                                   float* dv_part, float* dca_part, void* stream) {
+  return attn_cross_capture_bwd(q, q_sb, q_sn, k, k_sb, k_sn, v, v_sb, v_sn, dout, do_sb, do_sn, dprob, dscore, B, H, Lq, S, d,
+                                scale, col_flag, qmean_, ca_scale, mix, in_dtype, dq, dq_sb, dq_sn, dk, dk_sb, dk_sn, dv, dv_sb,
+                                dv_sn, dkv_dtype, dca, dca_mul, dk_part, dv_part, dca_part, (cudaStream_t)stream);
+}
+
+int adaface_transpose(const void* src, int src_dtype, int64_t s_sb, int64_t s_ld, void* dst, int dst_dtype, int64_t d_sb,
+                      int64_t d_ld, int64_t B, int64_t I, int64_t J, float alpha, const float* colscale,
+                      const float* rowscale, void* stream) {
+  return transpose(src, src_dtype, s_sb, s_ld, dst, dst_dtype, d_sb, d_ld, B, I, J, alpha, colscale, rowscale,
+                   (cudaStream_t)stream);
+}
+
+int adaface_colsum(const void* a, int a_dtype, int64_t lda, const void* b, int b_dtype, int64_t ldb, const float* bias,
+                   const float* colmul, float* out, int64_t M, int64_t N, void* stream) {
+  return colsum(a, a_dtype, lda, b, b_dtype, ldb, bias, colmul, out, M, N, (cudaStream_t)stream);
+}
+
+int adaface_layernorm_bwd(const void* x, int x_dtype, int64_t ldx, const void* dy, int dy_dtype, int64_t lddy,
+                          const float* w, void* dx, int64_t lddx, float* dw, float* db, int64_t M, int64_t C, float eps,
+                          void* stream) {
+  return layernorm_bwd(x, x_dtype, ldx, dy, dy_dtype, lddy, w, dx, lddx, dw, db, M, C, eps, (cudaStream_t)stream);
+}
+
+int adaface_act_fwd(const void* u, int64_t ldu, void* h, int64_t ldh, int64_t M, int64_t n_out, int act, void* stream) {
+  return act_fwd(u, ldu, h, ldh, M, n_out, act, (cudaStream_t)stream);
+}
+
+int adaface_act_bwd(const void* u, int64_t ldu, const void* dh, int64_t lddh, void* du, int64_t lddu, int64_t M,
+                    int64_t n_out, int act, void* stream) {
+  return act_bwd(u, ldu, dh, lddh, du, lddu, M, n_out, act, (cudaStream_t)stream);
+}
+
+int adaface_sbg_head_bwd(const float* h0, const float* h1, const float* h2, const float* h3, const float* wl,
+                         int n_layers, int64_t ldh, const float* w, const float* dout, int64_t lddo, float* dh0,
+                         float* dh1, float* dh2, float* dh3, float* dwl, float* dw, float* db, int64_t M, int64_t C,
+                         float eps, void* stream) {
+  return sbg_head_bwd(h0, h1, h2, h3, wl, n_layers, ldh, w, dout, lddo, dh0, dh1, dh2, dh3, dwl, dw, db, M, C, eps,
+                      (cudaStream_t)stream);
 }
 
 }  // extern "C"

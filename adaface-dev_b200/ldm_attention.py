@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from . import autograd as ag
 
 
 def _ver(*ts):
@@ -53,10 +54,52 @@ class CrossAttention(nn.Module):
             with torch.no_grad():
                 pk = {"wq": _bf16(ws[0]), "wo": _bf16(ws[3]), "bo": _f32(ws[4]),
                       "wkv": torch.cat([_bf16(ws[1]), _bf16(ws[2])], dim=0)}
+                inner = pk["wq"].shape[0]
+                pk["wk"], pk["wv"] = pk["wkv"][:inner], pk["wkv"][inner:]      # row-slice views (contiguous)
                 if ws[0].shape[1] == ws[1].shape[1]:
                     pk["wqkv"] = torch.cat([pk["wq"], pk["wkv"]], dim=0)
             self._pack, self._pack_key = pk, key
         return self._pack
+
+    def _attend_train(self, x16, context, mask, residual=None, out_dtype=torch.bfloat16):
+        """``_attend`` with every kernel paired with its backward (autograd.py): gradients reach x and the context;
+        the frozen U-Net weights get none (ddpm.py:637-638)."""
+        B, N, Cq = x16.shape
+        H = self.heads
+        pk = self._weights()
+        C = pk["wq"].shape[0]
+        x2d = x16.reshape(B * N, Cq)
+        q = prob = score = None
+        key_mask = None if mask is None else (mask.reshape(B, -1) != 0).to(torch.uint8).contiguous()
+        if context is None:
+            if self.save_cross_attn_vars:
+                raise NotImplementedError("save_cross_attn_vars is only set on cross-attention layers (attn2)")
+            qkv = ag.linear(x2d, pk, "wqkv").view(B, N, 3 * C)
+            o = ag.attention(qkv, qkv, qkv, (0, C, 2 * C), C, C, H, self.scale, key_mask)
+        else:
+            ctx = context.to(torch.bfloat16).contiguous()
+            S = ctx.shape[1]
+            c2d = ctx.view(B * S, ctx.shape[2])
+            if self.save_cross_attn_vars:
+                if key_mask is not None or S > 128:
+                    raise NotImplementedError("capture is only defined for cross-attention contexts (<= 128 keys, no mask)")
+                q = ag.linear(x2d, pk, "wq", out_dtype=torch.float32).view(B, N, C)
+                k = ag.linear(c2d, pk, "wk", out_dtype=torch.float32).view(B, S, C)
+                v = ag.linear(c2d, pk, "wv", out_dtype=torch.float32).view(B, S, C)
+                one = torch.ones((), device=x16.device)
+                o, prob, score, _ = ag.CrossCaptureFn.apply(q, k, v, one, H, self.scale, True, True, None, None, False, 1.0)
+            else:
+                q = ag.linear(x2d, pk, "wq").view(B, N, C)
+                kv = ag.linear(c2d, pk, "wkv").view(B, S, 2 * C)
+                o = ag.attention(q, kv, kv, (0, 0, C), C, C, H, self.scale, key_mask)
+        res2d = None if residual is None else residual.reshape(B * N, -1)
+        out = ag.linear(o.view(B * N, C), pk, "wo", "bo", residual=res2d, out_dtype=out_dtype).view(B, N, -1)
+        if self.save_cross_attn_vars:
+            if residual is not None:
+                raise RuntimeError("capture with a fused residual would corrupt cached 'attn_out'")
+            self.cached_activations = {"q": ag.ChanMajorFn.apply(q, math.sqrt(self.scale)), "attn": prob, "attnscore": score,
+                                       "attn_out": ag.ChanMajorFn.apply(out, 1.0)}
+        return out
 
     def _attend(self, x16, context, mask, residual=None, out_dtype=torch.bfloat16):
         """x16 [B,N,C] bf16 contiguous -> [B,N,query_dim]; ``residual`` is added in the out-projection epilogue."""
@@ -101,6 +144,8 @@ class CrossAttention(nn.Module):
     def forward(self, x, context=None, mask=None):
         if not x.is_cuda:
             raise RuntimeError("adaface_b200 CrossAttention runs on CUDA only (no CPU fallback)")
+        if torch.is_grad_enabled() and (x.requires_grad or (context is not None and context.requires_grad)):
+            return self._attend_train(x.to(torch.bfloat16).contiguous(), context, mask).to(x.dtype)
         return self._attend(x.to(torch.bfloat16).contiguous(), context, mask).to(x.dtype)
 
 
@@ -141,9 +186,16 @@ class FeedForward(nn.Module):
         g = ops.proj(h16, pk["w1"], bias=pk["b1"], act=ops.ACT_GEGLU)
         return ops.proj(g, pk["w2"], bias=pk["b2"], residual=residual, out_dtype=out_dtype)
 
+    def _ff_train(self, h16, residual=None, out_dtype=torch.bfloat16):
+        """Training form: the packed pre-activation [a | gate] is kept for the GEGLU backward kernel."""
+        pk = self._weights()
+        u = ag.linear(h16, pk, "w1", "b1")
+        return ag.linear(ag.ActFn.apply(u, ops.ACT_GEGLU), pk, "w2", "b2", residual=residual, out_dtype=out_dtype)
+
     def forward(self, x):
         shp = x.shape
-        y = self._ff(x.to(torch.bfloat16).contiguous().view(-1, shp[-1]))
+        ff = self._ff_train if (torch.is_grad_enabled() and x.requires_grad) else self._ff
+        y = ff(x.to(torch.bfloat16).contiguous().view(-1, shp[-1]))
         return y.view(*shp[:-1], -1).to(x.dtype)
 
 
@@ -164,6 +216,8 @@ class BasicTransformerBlock(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("adaface_b200 BasicTransformerBlock runs on CUDA only (no CPU fallback)")
         B, N, C = x.shape
+        if torch.is_grad_enabled() and (x.requires_grad or (context is not None and context.requires_grad)):
+            return self._forward_train(x, context, mask)
         x0 = x.to(torch.bfloat16).contiguous()
         capture = self.attn2.save_cross_attn_vars
         h = self._ln(x0.view(B * N, C), self.norm1).view(B, N, C)
@@ -175,4 +229,22 @@ class BasicTransformerBlock(nn.Module):
             x2 = self.attn2._attend(h, context, None, residual=x1)
         h = self._ln(x2.view(B * N, C), self.norm3)
         x3 = self.ff._ff(h, residual=x2.view(B * N, C)).view(B, N, C)
+        return x3.to(x.dtype)
+
+    def _forward_train(self, x, context, mask):
+        """The same block with every kernel paired with its backward; LayerNorm affine parameters are frozen U-Net
+        weights, so only dx is produced.  With activation checkpointing on in the reference (attention.py:239) the
+        block is recomputed there; here the backward is recompute-form at the kernel level (attention) and keeps only
+        the bf16 activations between kernels."""
+        B, N, C = x.shape
+        ln = lambda t, norm: ag.LayerNormFn.apply(t, norm.weight.detach(), norm.bias.detach(), norm.eps, torch.bfloat16)
+        x0 = x.to(torch.bfloat16).contiguous().view(B * N, C)
+        capture = self.attn2.save_cross_attn_vars
+        x1 = self.attn1._attend_train(ln(x0, self.norm1).view(B, N, C), None, mask, residual=x0).view(B * N, C)
+        h = ln(x1, self.norm2).view(B, N, C)
+        if capture:
+            x2 = (self.attn2._attend_train(h, context, None) + x1.view(B, N, C)).view(B * N, C)
+        else:
+            x2 = self.attn2._attend_train(h, context, None, residual=x1).view(B * N, C)
+        x3 = self.ff._ff_train(ln(x2, self.norm3), residual=x2).view(B, N, C)
         return x3.to(x.dtype)

@@ -88,7 +88,7 @@ def _view3(t, name, dtype=torch.bfloat16):
     return t
 
 
-def attention(q, k, v, heads, scale, *, key_mask=None, causal_mult=0, out=None):
+def attention(q, k, v, heads, scale, *, key_mask=None, causal_mult=0, out=None, lse=None):
     """softmax(scale * q k^T + masks) v for [B, L, H*d] views (adaface_attn_fwd).
     With causal_mult = M > 1 (CLIPAttentionMKV) k / v are [B, T, M*H*d] views: token t carries its M keys back to
     back, Lk = T*M, and key j is visible to query i iff j // M <= i."""
@@ -108,11 +108,19 @@ def attention(q, k, v, heads, scale, *, key_mask=None, causal_mult=0, out=None):
             raise ValueError("attention: key_mask must be a contiguous uint8 [B, Lk] tensor")
     _lib.call("adaface_attn_fwd", _ptr(q), q.stride(0), q.stride(1), _ptr(k), k.stride(0), k.stride(1), _ptr(v),
               v.stride(0), v.stride(1), _ptr(out), out.stride(0), out.stride(1), B, heads, Lq, Lk, d, _ptr(key_mask),
-              int(causal_mult), float(scale), _stream())
+              int(causal_mult), float(scale), _ptr(_lse_buf(lse, B, heads, Lq)), _stream())
     return out
 
 
-def attention_headmajor(q, k, v, scale, *, d=None, out=None):
+def _lse_buf(lse, B, H, Lq):
+    if lse is not None:
+        _need(lse, "lse", torch.float32)
+        if tuple(lse.shape) != (B, H, Lq) or not lse.is_contiguous():
+            raise ValueError(f"attention: lse must be a contiguous fp32 [B, H, Lq] tensor, got {tuple(lse.shape)}")
+    return lse
+
+
+def attention_headmajor(q, k, v, scale, *, d=None, out=None, lse=None):
     """Unmasked attention for head-major views q [B, H, Lq, drow_q], k / v [B, H, Lk, drow_kv] (any batch / head /
     token strides, unit stride in the last dim).  `d` = true head dim when rows are zero-padded (drow > d; default:
     the k/v row width).  Output in the reference layout [B, Lq, H*d] (adaface_attn_headmajor_fwd)."""
@@ -129,7 +137,7 @@ def attention_headmajor(q, k, v, scale, *, d=None, out=None):
         out = torch.empty((B, Lq, H * d), device=q.device, dtype=torch.bfloat16)
     _lib.call("adaface_attn_headmajor_fwd", _ptr(q), q.stride(0), q.stride(1), q.stride(2), _ptr(k), k.stride(0), k.stride(1),
               k.stride(2), _ptr(v), v.stride(0), v.stride(1), v.stride(2), _ptr(out), out.stride(0), out.stride(1), B, H, Lq,
-              Lk, d, drow_q, drow_kv, float(scale), _stream())
+              Lk, d, drow_q, drow_kv, float(scale), _ptr(_lse_buf(lse, B, H, Lq)), _stream())
     return out
 
 
@@ -283,3 +291,134 @@ def cross_attention_fused(x2d, wq, bq, ctx2d, wkv, bkv, B, N, S, heads, scale):
         return attention_headmajor(q, k, v, scale, d=d)
     q = proj(x2d, wq, bias=bq).view(B, N, C)
     return attention(q, kv[:, :, :C], kv[:, :, C:], heads, scale)
+
+
+# ================================================================================================ backward (K5)
+def attention_bwd(q, k, v, o, dout, lse, heads, scale, dq, dk, dv, *, key_mask=None, causal_mult=0):
+    """Flash-attention backward (adaface_attn_bwd): fills the bf16 views dq / dk / dv (shaped like q / k / v)."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v"), (o, "o"), (dout, "dout"), (dq, "dq"), (dk, "dk"), (dv, "dv")):
+        _view3(t, nm)
+    B, Lq, C = q.shape
+    kv_mult = max(1, int(causal_mult))
+    Lk = k.shape[1] * kv_mult
+    d = C // heads
+    _lse_buf(lse, B, heads, Lq)
+    delta = torch.empty_like(lse)
+    _lib.call("adaface_attn_bwd", _ptr(q), q.stride(0), q.stride(1), _ptr(k), k.stride(0), k.stride(1), _ptr(v), v.stride(0),
+              v.stride(1), _ptr(o), o.stride(0), o.stride(1), _ptr(dout), dout.stride(0), dout.stride(1), _ptr(lse),
+              _ptr(delta), _ptr(dq), dq.stride(0), dq.stride(1), _ptr(dk), dk.stride(0), dk.stride(1), _ptr(dv), dv.stride(0),
+              dv.stride(1), B, heads, Lq, Lk, d, _ptr(key_mask), int(causal_mult), float(scale), _stream())
+
+
+def attention_cross_capture_bwd(q, k, v, dout, heads, scale, *, dprob=None, dscore=None, col_flag=None, qmean=None,
+                                ca_scale=None, mix=False, dca_mul=1.0, dkv_dtype=torch.float32):
+    """Backward of attention_cross_capture (adaface_attn_cross_capture_bwd).
+    Returns (dq bf16 [B,Lq,C], dk, dv [B,S,C] of dkv_dtype, dca fp32 [1])."""
+    _view3(q, "q", q.dtype), _view3(k, "k", q.dtype), _view3(v, "v", q.dtype), _view3(dout, "dout")
+    B, Lq, C = q.shape
+    S = k.shape[1]
+    d = C // heads
+    dev = q.device
+    for g, nm in ((dprob, "dprob"), (dscore, "dscore")):
+        if g is not None:
+            _need(g, nm, torch.float32)
+            if tuple(g.shape) != (B, heads, Lq, S) or not g.is_contiguous():
+                raise ValueError(f"attention_cross_capture_bwd: `{nm}` must be a contiguous fp32 [B,H,Lq,S] tensor")
+    chunks = _lib.cross_capture_bwd_chunks(B, heads, Lq)
+    dq = torch.empty((B, Lq, C), device=dev, dtype=torch.bfloat16)
+    dk = torch.empty((B, S, C), device=dev, dtype=dkv_dtype)
+    dv = torch.empty((B, S, C), device=dev, dtype=dkv_dtype)
+    dca = torch.zeros(1, device=dev, dtype=torch.float32)
+    part = torch.empty((2, B * heads * chunks * S * d), device=dev, dtype=torch.float32)
+    dca_part = torch.empty(B * heads * chunks, device=dev, dtype=torch.float32)
+    _lib.call("adaface_attn_cross_capture_bwd", _ptr(q), q.stride(0), q.stride(1), _ptr(k), k.stride(0), k.stride(1), _ptr(v),
+              v.stride(0), v.stride(1), _ptr(dout), dout.stride(0), dout.stride(1), _ptr(dprob), _ptr(dscore), B, heads, Lq, S,
+              d, float(scale), _ptr(col_flag), _ptr(qmean), _ptr(ca_scale), int(bool(mix)), _dt(q), _ptr(dq), dq.stride(0), dq.stride(1),
+              _ptr(dk), dk.stride(0), dk.stride(1), _ptr(dv), dv.stride(0), dv.stride(1), _dt(dk), _ptr(dca), float(dca_mul),
+              _ptr(part[0]), _ptr(part[1]), _ptr(dca_part), _stream())
+    return dq, dk, dv, dca
+
+
+def transpose(src, *, out_dtype=None, alpha=1.0, colscale=None, rowscale=None, pad_to=1):
+    """dst[b, j, i] = alpha * colscale[j] * rowscale[i] * src[b, i, j] (adaface_transpose).  src [I, J] or [B, I, J]
+    with unit stride in J.  `pad_to`: the destination row pitch is rounded up to this multiple and the padding is zero
+    (the GEMM needs reduction lengths / row pitches that are multiples of 8); the returned tensor includes the padding."""
+    _need(src, "src")
+    squeeze = src.dim() == 2
+    s3 = src.unsqueeze(0) if squeeze else src
+    B, I, J = s3.shape
+    out_dtype = out_dtype or src.dtype
+    Ip = (I + pad_to - 1) // pad_to * pad_to
+    dst = (torch.zeros if Ip != I else torch.empty)((B, J, Ip), device=src.device, dtype=out_dtype)
+    _lib.call("adaface_transpose", _ptr(s3), _dt(s3), s3.stride(0), s3.stride(1), _ptr(dst), _dt(dst), dst.stride(0),
+              dst.stride(1), B, I, J, float(alpha), _ptr(colscale), _ptr(rowscale), _stream())
+    return dst[0] if squeeze else dst
+
+
+def colsum(a, *, b=None, bias=None, colmul=None, out=None):
+    """out[j] += colmul[j] * sum_i a[i, j] * (b[i, j] - bias[j]) (adaface_colsum); returns fp32 [N]."""
+    _need(a, "a")
+    M, N = a.shape
+    if out is None:
+        out = torch.zeros(N, device=a.device, dtype=torch.float32)
+    ldb, bdt = 0, BF16
+    if b is not None:
+        _need(b, "b")
+        ldb, bdt = b.stride(0), _dt(b)
+    _lib.call("adaface_colsum", _ptr(a), _dt(a), a.stride(0), _ptr(b), bdt, ldb, _ptr(bias), _ptr(colmul), _ptr(out), M, N,
+              _stream())
+    return out
+
+
+def layernorm_bwd(x, dy, w, eps=1e-5, *, want_wgrad=False):
+    """LayerNorm backward (adaface_layernorm_bwd): returns (dx like x, dw, db) -- dw / db None unless want_wgrad."""
+    _need(x, "x"), _need(dy, "dy"), _need(w, "w", torch.float32)
+    M, C = x.shape
+    dx = torch.empty((M, C), device=x.device, dtype=x.dtype)
+    dw = db = None
+    if want_wgrad:
+        dw = torch.zeros(C, device=x.device, dtype=torch.float32)
+        db = torch.zeros(C, device=x.device, dtype=torch.float32)
+    _lib.call("adaface_layernorm_bwd", _ptr(x), _dt(x), x.stride(0), _ptr(dy), _dt(dy), dy.stride(0), _ptr(w), _ptr(dx),
+              dx.stride(0), _ptr(dw), _ptr(db), M, C, float(eps), _stream())
+    return dx, dw, db
+
+
+def act_fwd(u, act):
+    """h = act(u): quick-GELU [M,N] -> [M,N]; GEGLU packed [M,2N] -> [M,N] (adaface_act_fwd)."""
+    _need(u, "u", torch.bfloat16)
+    M, W = u.shape
+    n_out = W // 2 if act == ACT_GEGLU else W
+    h = torch.empty((M, n_out), device=u.device, dtype=torch.bfloat16)
+    _lib.call("adaface_act_fwd", _ptr(u), u.stride(0), _ptr(h), h.stride(0), M, n_out, int(act), _stream())
+    return h
+
+
+def act_bwd(u, dh, act):
+    """du = dh * act'(u) (adaface_act_bwd)."""
+    _need(u, "u", torch.bfloat16), _need(dh, "dh", torch.bfloat16)
+    M, n_out = dh.shape
+    du = torch.empty_like(u)
+    _lib.call("adaface_act_bwd", _ptr(u), u.stride(0), _ptr(dh), dh.stride(0), _ptr(du), du.stride(0), M, n_out, int(act),
+              _stream())
+    return du
+
+
+def sbg_head_bwd(hs, layer_weights, w, dout, eps=1e-5):
+    """Backward of sbg_head: returns ([dh_l], dwl fp32 [n], dw, db) (adaface_sbg_head_bwd)."""
+    n = len(hs)
+    M, C = hs[0].shape
+    dev = hs[0].device
+    _need(dout, "dout", torch.float32)
+    dhs = [torch.empty((M, C), device=dev, dtype=torch.float32) for _ in hs]
+    for h in hs:
+        if h.stride(0) != C or h.stride(1) != 1:
+            raise ValueError("sbg_head_bwd: hidden states must be contiguous")
+    dwl = torch.zeros(4, device=dev, dtype=torch.float32)
+    dw = torch.zeros(C, device=dev, dtype=torch.float32)
+    db = torch.zeros(C, device=dev, dtype=torch.float32)
+    wl = (ctypes.c_float * n)(*[float(x) for x in layer_weights])
+    pad = [ctypes.c_void_p(0)] * (4 - n)
+    _lib.call("adaface_sbg_head_bwd", *([_ptr(h) for h in hs] + pad), wl, n, C, _ptr(w), _ptr(dout), dout.stride(0),
+              *([_ptr(d) for d in dhs] + pad), _ptr(dwl), _ptr(dw), _ptr(db), M, C, float(eps), _stream())
+    return dhs, dwl[:n], dw, db

@@ -21,6 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from . import autograd as ag
 from .attn_processor import gen_gradient_scaler
 
 # "photo of a" + ", " * (N_ID + 2) tokenised by the CLIP BPE vocab and padded to 77
@@ -132,6 +133,23 @@ class CLIPEncoderLayer(nn.Module):
         return ops.proj(f, pk["w2"], bias=pk["b2"], residual=h, out_dtype=torch.float32)
 
 
+    def run_train(self, h, BS, T):
+        """``run`` with every kernel paired with its backward: gradients to the residual stream and to every
+        parameter of the layer (q/k/v/out projections, fc1, fc2, both LayerNorms)."""
+        pk, a, m = self.pack(), self.self_attn, self.mlp
+        E, M = a.embed_dim, a.multiplier
+        x = ag.LayerNormFn.apply(h, self.layer_norm1.weight, self.layer_norm1.bias, self.layer_norm1.eps, torch.bfloat16)
+        qkv = ag.linear(x, pk, "wqkv", "bqkv", params=(a.q_proj.weight, a.q_proj.bias, a.k_proj.weight, a.k_proj.bias,
+                                                        a.v_proj.weight, a.v_proj.bias)).view(BS, T, E * (1 + 2 * M))
+        o = ag.attention(qkv, qkv, qkv, (0, E, E + E * M), E, E * M, a.num_heads, a.scale, None, M)
+        h = ag.linear(o.view(BS * T, E), pk, "wo", "bo", params=(a.out_proj.weight, a.out_proj.bias), residual=h,
+                      out_dtype=torch.float32)
+        x = ag.LayerNormFn.apply(h, self.layer_norm2.weight, self.layer_norm2.bias, self.layer_norm2.eps, torch.bfloat16)
+        u = ag.linear(x, pk, "w1", "b1", params=(m.fc1.weight, m.fc1.bias))
+        f = ag.ActFn.apply(u, ops.ACT_QUICK_GELU)
+        return ag.linear(f, pk, "w2", "b2", params=(m.fc2.weight, m.fc2.bias), residual=h, out_dtype=torch.float32)
+
+
 class CLIPEncoder(nn.Module):
     def __init__(self, config):
         super().__init__()
@@ -177,10 +195,23 @@ class CLIPTextModelWrapper(nn.Module):
         T_run = T if num_positions is None else min(T, num_positions)           # causal-exact truncation
         h = (input_token_embs[:, :T_run].float() + tm.embeddings.position_embedding.weight[:T_run].float())   # :268
         h = h.reshape(BS * T_run, E).contiguous()
+        train = torch.is_grad_enabled() and (h.requires_grad or any(p.requires_grad for p in tm.encoder.parameters()))
         hs = [h]
         for layer in tm.encoder.layers:                                           # :278-286
-            h = layer.run(h, BS, T_run)
+            h = layer.run_train(h, BS, T_run) if train else layer.run(h, BS, T_run)
             hs.append(h)
+        fl = tm.final_layer_norm
+        if train:
+            if hidden_state_layer_weights is None:
+                tail, wl_t = [h], torch.ones(1, device=h.device)
+            else:
+                if hidden_state_layer_weights.numel() != hidden_state_layer_weights.shape[0]:
+                    raise NotImplementedError("per-channel hidden_state_layer_weights ([3,768]) are not used by the face path")
+                w = hidden_state_layer_weights.float().reshape(-1)
+                wl_t = w / w.sum()                                                # :291-306 (3-element host-side glue)
+                tail = hs[-w.numel():]
+            out = ag.SbgHeadFn.apply(wl_t, fl.weight, fl.bias, fl.eps, *tail)
+            return (out.view(BS, T_run, E),)
         if hidden_state_layer_weights is None:                                    # :291-306
             tail, wl = [h], [1.0]
         else:
@@ -189,7 +220,6 @@ class CLIPTextModelWrapper(nn.Module):
                 raise NotImplementedError("per-channel hidden_state_layer_weights ([3,768]) are not used by the face path")
             wl = (w / w.sum()).tolist()
             tail = hs[-len(wl):]
-        fl = tm.final_layer_norm
         out = ops.sbg_head(tail, wl, fl.weight.detach().float(), fl.bias.detach().float(), fl.eps)
         return (out.view(BS, T_run, E),)
 

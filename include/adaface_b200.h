@@ -16,7 +16,7 @@
 extern "C" {
 #endif
 
-#define ADAFACE_B200_ABI_VERSION 1
+#define ADAFACE_B200_ABI_VERSION 2
 
 /* epilogue activation of adaface_proj_lora_fwd */
 #define ADAFACE_ACT_NONE 0
@@ -68,11 +68,13 @@ int adaface_proj_lora_heads_fwd(const void* x, int64_t ldx, const void* w, const
  * visible to query i iff j / M <= i (arc2face_models.py:192) and, because each token row then holds its M
  * keys back to back (arc2face_models.py:74-79), key j is read at token j / M, column (j % M) * H*d + h*d
  * (k_sn / v_sn are the TOKEN strides; Lk counts keys = tokens * M).  scale multiplies q.k before softmax.
+ * lse (optional, NULL = not wanted): fp32 [B, H, Lq], log2-domain log-sum-exp of every score row -- the only
+ * thing the training forward leaves behind for adaface_attn_bwd.
  */
 int adaface_attn_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn,
                      const void* v, int64_t v_sb, int64_t v_sn, void* o, int64_t o_sb, int64_t o_sn, int64_t B,
                      int64_t H, int64_t Lq, int64_t Lk, int64_t d, const uint8_t* key_mask, int causal_mult,
-                     float scale, void* stream);
+                     float scale, float* lse, void* stream);
 
 /* Same operator for q/k/v tensors with an explicit HEAD stride (element strides batch / head / token), e.g. the
  * head-major [which, B, H, L, d] buffer that adaface_proj_lora_fwd can scatter a fused QKV projection into: every
@@ -82,7 +84,7 @@ int adaface_attn_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, i
 int adaface_attn_headmajor_fwd(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, const void* k, int64_t k_sb,
                                int64_t k_sh, int64_t k_sn, const void* v, int64_t v_sb, int64_t v_sh, int64_t v_sn, void* o,
                                int64_t o_sb, int64_t o_sn, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t d,
-                               int64_t drow_q, int64_t drow_kv, float scale, void* stream);
+                               int64_t drow_q, int64_t drow_kv, float scale, float* lse, void* stream);
 
 /* ---- K3: cross-attention with capture / normalize / mix (the slow SDPA of dalc:79-139) -------------
  * S = Lk <= 128 keys staged once in shared memory.  Optional outputs (NULL = not wanted):
@@ -126,6 +128,69 @@ int adaface_layernorm_fwd(const void* x, int x_dtype, int64_t ldx, const float* 
 int adaface_sbg_head_fwd(const float* h0, const float* h1, const float* h2, const float* h3, const float* wl,
                          int n_layers, int64_t ldh, const float* w, const float* b, float* out, int64_t ldo,
                          int64_t M, int64_t C, float eps, void* stream);
+
+/* ---- K5: backward kernels of the stage-2 training step (ddpm.py:1645-1707 back-propagates through the `sc`
+ * instance of the U-Net into the LoRA / DoRA adapters, cross_attn_scale_factor and, via the context, SubjBasisGenerator).
+ * The reference gets all of this from autograd over eager PyTorch ops; here every gradient is a kernel, recompute
+ * form (nothing of size Lq x Lk is kept between forward and backward).
+ *
+ * Flash-attention backward of adaface_attn_fwd (same views, masks and causal multi-KV addressing):
+ *   delta_i = dO_i . O_i;  P = exp2(scale log2e q.k - lse);  dV = P^T dO;  dS = P o (dO V^T - delta) scale;
+ *   dQ = dS K;  dK = dS^T Q.   lse from the forward call; delta = fp32 [B, H, Lq] scratch.  dq/dk/dv bf16 views shaped
+ * like q/k/v.  Deterministic (no atomics). */
+int adaface_attn_bwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn, const void* v,
+                     int64_t v_sb, int64_t v_sn, const void* o, int64_t o_sb, int64_t o_sn, const void* dout, int64_t do_sb,
+                     int64_t do_sn, const float* lse, float* delta, void* dq, int64_t dq_sb, int64_t dq_sn, void* dk,
+                     int64_t dk_sb, int64_t dk_sn, void* dv, int64_t dv_sb, int64_t dv_sn, int64_t B, int64_t H, int64_t Lq,
+                     int64_t Lk, int64_t d, const uint8_t* key_mask, int causal_mult, float scale, void* stream);
+
+/* Backward of adaface_attn_cross_capture_fwd (dalc:79-139; under mix only the sc half receives dq / dk, dalc:117).  Upstream gradients: dout [B,Lq,H*d]
+ * bf16 and, optionally, dprob / dscore [B,H,Lq,S] fp32 (the losses on cached 'attn' / 'attnscore').  q/k/v, col_flag,
+ * qmean, ca_scale, mix, in_dtype exactly as passed to the forward call.  Outputs: dq bf16 [B,Lq,H*d] view; dk, dv
+ * [B,S,H*d] views of dkv_dtype; dca (optional) = dca_mul * d loss / d cross_attn_scale_factor (dca_mul carries the x10
+ * GradientScaler of dalc:129).  Workspaces (fp32, caller-allocated): dk_part, dv_part of
+ * B*H*chunks*S*d floats and dca_part of B*H*chunks floats, chunks = adaface_attn_cross_capture_bwd_chunks(B, H, Lq). */
+int adaface_attn_cross_capture_bwd_chunks(int64_t B, int64_t H, int64_t Lq);
+int adaface_attn_cross_capture_bwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn,
+                                   const void* v, int64_t v_sb, int64_t v_sn, const void* dout, int64_t do_sb,
+                                   int64_t do_sn, const float* dprob, const float* dscore, int64_t B, int64_t H,
+                                   int64_t Lq, int64_t S, int64_t d, float scale, const uint8_t* col_flag,
+                                   const float* qmean, const float* ca_scale, int mix, int in_dtype, void* dq, int64_t dq_sb,
+                                   int64_t dq_sn, void* dk, int64_t dk_sb, int64_t dk_sn, void* dv, int64_t dv_sb,
+                                   int64_t dv_sn, int dkv_dtype, float* dca, float dca_mul, float* dk_part,
+                                   float* dv_part, float* dca_part, void* stream);
+
+/* dst[b, j, i] = alpha * colscale[j] * rowscale[i] * src[b, i, j]  (src [B, I, J], dst [B, J, I]; element strides
+ * batch / row; colscale fp32 [J], rowscale fp32 [I], either may be NULL).  Operand re-layout of the weight-gradient GEMMs (dW = dY^T X, dA, dB of the LoRA pair,
+ * with the DoRA column scale folded in) and the backward of adaface_capture_chan_major. */
+int adaface_transpose(const void* src, int src_dtype, int64_t s_sb, int64_t s_ld, void* dst, int dst_dtype, int64_t d_sb,
+                      int64_t d_ld, int64_t B, int64_t I, int64_t J, float alpha, const float* colscale,
+                      const float* rowscale, void* stream);
+
+/* out[j] += colmul[j] * sum_i a[i, j] * (b ? b[i, j] - bias[j] : 1)   (out fp32 [N], ACCUMULATED with atomics: zero
+ * it first).  b = NULL: bias gradient.  b = Y, bias, colmul = 1/m: DoRA magnitude gradient. */
+int adaface_colsum(const void* a, int a_dtype, int64_t lda, const void* b, int b_dtype, int64_t ldb, const float* bias,
+                   const float* colmul, float* out, int64_t M, int64_t N, void* stream);
+
+/* LayerNorm backward: dx[M,C] (dtype of x) from x, dy, w; dw / db fp32 [C] ACCUMULATED (zero first) or both NULL when
+ * the affine parameters are frozen (U-Net blocks). */
+int adaface_layernorm_bwd(const void* x, int x_dtype, int64_t ldx, const void* dy, int dy_dtype, int64_t lddy,
+                          const float* w, void* dx, int64_t lddx, float* dw, float* db, int64_t M, int64_t C, float eps,
+                          void* stream);
+
+/* Stand-alone activation (training mode keeps the pre-activation u): h = act(u) and du = dh * act'(u), bf16.
+ * ADAFACE_ACT_QUICK_GELU: u, h, dh, du all [M, n_out].  ADAFACE_ACT_GEGLU: u / du [M, 2 n_out] in packed
+ * [a(64) | gate(64)] tiles, h / dh [M, n_out]. */
+int adaface_act_fwd(const void* u, int64_t ldu, void* h, int64_t ldh, int64_t M, int64_t n_out, int act, void* stream);
+int adaface_act_bwd(const void* u, int64_t ldu, const void* dh, int64_t lddh, void* du, int64_t lddu, int64_t M,
+                    int64_t n_out, int act, void* stream);
+
+/* Backward of adaface_sbg_head_fwd: dh_l = wl[l] * dmix (fp32 [M,C] each, written), dwl[l] += <dmix, h_l>,
+ * dw / db of the final LayerNorm accumulated (zero dwl [4], dw, db first). */
+int adaface_sbg_head_bwd(const float* h0, const float* h1, const float* h2, const float* h3, const float* wl,
+                         int n_layers, int64_t ldh, const float* w, const float* dout, int64_t lddo, float* dh0,
+                         float* dh1, float* dh2, float* dh3, float* dwl, float* dw, float* db, int64_t M, int64_t C,
+                         float eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,8 +21,10 @@ def make_attention(w, C_, ctx_dim, heads=8, processor=None):
     return attn
 
 
-def run_mirror_proc(case, in_dtype=torch.bfloat16):
-    """AttnProcessor_LoRA_Capture mirror on a processor case -> (out, cached_activations)."""
+def run_mirror_proc(case, in_dtype=torch.bfloat16, train=False):
+    """AttnProcessor_LoRA_Capture mirror on a processor case -> (out, cached_activations).
+    train=True: run the autograd-enabled path with leaf inputs -> (out, cache, handles) where handles holds the
+    leaf tensors / modules whose .grad the backward tests read."""
     import adaface_dev_b200 as a
     sp, w = case["spec"], case["w"]
     cross = sp.get("cross", False)
@@ -48,7 +50,15 @@ def run_mirror_proc(case, in_dtype=torch.bfloat16):
         kw["img_mask"] = _T(case["img_mask"])
     if si is not None:
         kw["subj_indices"] = (torch.from_numpy(si[0]).cuda(), torch.from_numpy(si[1]).cuda())
-    out = attn(_T(case["hidden_states"], in_dtype), encoder_hidden_states=_T(case["encoder_hidden_states"], in_dtype), **kw)
+    hs, ehs = _T(case["hidden_states"], in_dtype), _T(case["encoder_hidden_states"], in_dtype)
+    if train:
+        hs.requires_grad_(True)
+        if ehs is not None:
+            ehs.requires_grad_(True)
+        out = attn(hs, encoder_hidden_states=ehs, **kw)
+        return out, proc.cached_activations, dict(hidden_states=hs, encoder_hidden_states=ehs, proc=proc, attn=attn)
+    with torch.no_grad():
+        out = attn(hs, encoder_hidden_states=ehs, **kw)
     return out, proc.cached_activations
 
 
@@ -61,11 +71,21 @@ def load_ldm_attn(m, w):
         m.to_out[0].bias.copy_(_T(w["to_out_b"]))
 
 
-def run_mirror_ldm(case):
+def run_mirror_ldm(case, train=False):
+    with torch.set_grad_enabled(train):
+        return _run_mirror_ldm(case, train)
+
+
+def _run_mirror_ldm(case, train):
     import adaface_dev_b200 as a
     sp, w = case["spec"], case["w"]
     Cc = sp["C"]
     x, ctx, mask = _T(case["x"], torch.bfloat16), _T(case["context"], torch.bfloat16), _T(case["mask"])
+    if train:
+        x.requires_grad_(True)
+        if ctx is not None:
+            ctx.requires_grad_(True)
+        case["_leaves"] = (x, ctx)
     if sp.get("block"):
         blk = a.BasicTransformerBlock(Cc, 8, Cc // 8, context_dim=768).cuda()
         load_ldm_attn(blk.attn1, w["attn1"])
