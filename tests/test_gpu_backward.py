@@ -326,8 +326,9 @@ def test_processor_training_step_vs_oracle(name):
     if sp.get("normalize"):
         g, gr = proc.cross_attn_scale_factor.grad.item(), w["cross_attn_scale_factor"].grad.item()
         assert abs(g - gr) < GRAD_TOL * abs(gr)
-    for p in h["attn"].parameters():        # the frozen base weights never receive a gradient
-        assert p.grad is None
+    at = h["attn"]
+    for mod in (at.to_q, at.to_k, at.to_v, at.to_out[0]):        # the frozen base weights never receive a gradient
+        assert all(p.grad is None for p in mod.parameters())
 
 
 @pytest.mark.parametrize("name", ["ldm_block", "ldm_block_d80", "ldm_cross_save", "ldm_self_mask"])
@@ -369,7 +370,8 @@ def test_sbg_training_step_vs_oracle(name):
     t = C.to_torch({k: v for k, v in case.items() if k != "spec"})
     w = t["w"]
     x = t["faceid2img_prompt_embs"].requires_grad_(True)
-    probe = [(0, "q_w"), (0, "k_b"), (5, "v_w"), (5, "o_w"), (11, "fc1_w"), (11, "fc2_b"), (3, "ln1_w"), (7, "ln2_b")]
+    # (k_proj.bias is not probed: softmax is invariant to it, its true gradient is 0 and only rounding noise remains)
+    probe = [(0, "q_w"), (0, "v_b"), (2, "k_w"), (5, "v_w"), (5, "o_w"), (11, "fc1_w"), (11, "fc2_b"), (3, "ln1_w"), (7, "ln2_b")]
     for li, key in probe:
         w["layers"][li][key].requires_grad_(True)
     w["final_ln_w"].requires_grad_(True)
@@ -388,7 +390,8 @@ def test_sbg_training_step_vs_oracle(name):
     tol = 5e-2                          # 12 layers of bf16 GEMM gradients
     assert rel(xm.grad, x.grad) < tol
     layers = gen.prompt2token_proj.text_model.encoder.layers
-    name_of = {"q_w": lambda l: l.self_attn.q_proj.weight, "k_b": lambda l: l.self_attn.k_proj.bias,
+    name_of = {"q_w": lambda l: l.self_attn.q_proj.weight, "v_b": lambda l: l.self_attn.v_proj.bias,
+               "k_w": lambda l: l.self_attn.k_proj.weight,
                "v_w": lambda l: l.self_attn.v_proj.weight, "o_w": lambda l: l.self_attn.out_proj.weight,
                "fc1_w": lambda l: l.mlp.fc1.weight, "fc2_b": lambda l: l.mlp.fc2.bias,
                "ln1_w": lambda l: l.layer_norm1.weight, "ln2_b": lambda l: l.layer_norm2.bias}
