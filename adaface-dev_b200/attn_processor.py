@@ -41,7 +41,11 @@ class GradientScaler(nn.Module):
         self._debug = torch.tensor(debug, requires_grad=False)
 
     def forward(self, input_):
-        return ScaleGrad.apply(input_, self._alpha.to(input_.device), False)
+        if not (torch.is_grad_enabled() and input_.requires_grad):
+            return input_                      # identity forward: nothing to scale without a backward pass
+        if self._alpha.device != input_.device:
+            self._alpha = self._alpha.to(input_.device)      # moved once, not per call (CUDA-graph friendly)
+        return ScaleGrad.apply(input_, self._alpha, False)
 
 
 def gen_gradient_scaler(alpha, debug=False):

@@ -218,7 +218,12 @@ class CLIPTextModelWrapper(nn.Module):
             w = hidden_state_layer_weights.detach().float().reshape(-1)
             if hidden_state_layer_weights.numel() != hidden_state_layer_weights.shape[0]:
                 raise NotImplementedError("per-channel hidden_state_layer_weights ([3,768]) are not used by the face path")
-            wl = (w / w.sum()).tolist()
+            # host copy of the 3 normalised weights, cached per parameter version (no device sync in steady state,
+            # so the forward can be captured into a CUDA graph)
+            key = (hidden_state_layer_weights.data_ptr(), hidden_state_layer_weights._version)
+            if getattr(self, "_wl_cache", (None, None))[0] != key:
+                self._wl_cache = (key, (w / w.sum()).tolist())
+            wl = self._wl_cache[1]
             tail = hs[-len(wl):]
         out = ops.sbg_head(tail, wl, fl.weight.detach().float(), fl.bias.detach().float(), fl.eps)
         return (out.view(BS, T_run, E),)

@@ -194,6 +194,95 @@ def run_stack(mods, xs, ctx):
     return outs
 
 
+def _time_us(torch, flush, fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.fill_(1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) * 1e3)
+    return statistics.median(ts)
+
+
+def secondary_measurements(torch, a, dev, flush, pk):
+    """Secondary lines (not the headline): the HBM-bound cross-attention / capture kernels against the measured copy
+    bandwidth (SURVEY 8d #1 byte counts), SubjBasisGenerator at BASELINE config 2, and one stage-2-style
+    forward + backward through a captured level-A cross-attention module (config 5, scaled to the hot path)."""
+    ops = a.ops
+    out = {}
+    H, S, N, C = HEADS, S_CTX, 4096, 320
+    d = C // H
+    hbm = pk["hbm_gbs"]
+    with torch.no_grad():
+        # -- cross-attention core, fast path, level A, B = 8: read Q + K,V, write O (bf16)
+        B = BATCH
+        q = torch.zeros(B, H, N, 64, device=dev, dtype=torch.bfloat16)
+        q[..., :d] = torch.randn(B, H, N, d, device=dev).to(torch.bfloat16)
+        kv = torch.randn(B, S, 2 * C, device=dev).to(torch.bfloat16)
+        kh = kv[:, :, :C].unflatten(2, (H, d)).transpose(1, 2)
+        vh = kv[:, :, C:].unflatten(2, (H, d)).transpose(1, 2)
+        us = _time_us(torch, flush, lambda: ops.attention_headmajor(q, kh, vh, d ** -0.5, d=d))
+        by = 2 * B * N * C * 2 + 2 * B * S * C * 2
+        out["cross_attn_fast"] = {"kernel": "attn_fwd_tcgen05_mc_kernel<40>, 77 keys", "shape": f"B={B} N={N} C={C} S={S}", "us": us,
+                                  "algorithmic_bytes": by, "achieved_gbs": by / us / 1e3, "peak_gbs": hbm,
+                                  "frac": by / us / 1e3 / hbm}
+        # -- capture path, config 1 (B = 2, fp32 q/k/v in, bf16 O + fp32 prob [+ score] out)
+        B = 2
+        qf, kf, vf = (torch.randn(B, n_, C, device=dev) for n_ in (N, S, S))
+        core = B * N * C * (4 + 2) + 2 * B * S * C * 4
+        maps = B * H * N * S * 4
+        for nm, kw, by in (("capture_prob", dict(want_score=False), core + maps), ("capture_prob_score", {}, core + 2 * maps)):
+            us = _time_us(torch, flush, lambda: ops.attention_cross_capture(qf, kf, vf, H, d ** -0.5, **kw))
+            out[nm] = {"kernel": "attn_cross_capture_kernel<40,fp32>", "shape": f"B={B} N={N} C={C} S={S}", "us": us,
+                       "algorithmic_bytes": by, "achieved_gbs": by / us / 1e3, "peak_gbs": hbm, "frac": by / us / 1e3 / hbm}
+        # -- SubjBasisGenerator, BASELINE config 2: [64,16,768] -> [64,16,768], random init, 12 layers, K/V multiplier 1
+        gen = a.SubjBasisGenerator().to(dev).eval()
+        x = torch.randn(64, 16, 768, device=dev) * 0.5
+        fn = a.graphed(lambda t: gen(t), x)
+        us = _time_us(torch, flush, lambda: fn(x))
+        T = 20
+        fl = 64 * 12 * (24 * T * 768 * 768 + 4 * T * T * 768)
+        out["subj_basis_generator"] = {"shape": "BS=64, N_ID=16, T_run=20 (causal-exact truncation of 77)", "us": us,
+                                       "flops_executed": fl, "tflops": fl / us / 1e6, "samples_per_s": 64 / us * 1e6}
+    # -- training: forward + backward through one captured cross-attention module (level A, B = 1, S = 97, DoRA r = 192
+    #    on q/k/v/out, normalize_cross_attn, loss on out + captured attn) and through one self-attention module
+    S2 = 97
+    attn = a.Attention(C, CTX_DIM, H, d, device=dev)
+    layers = {"q": attn.to_q, "k": attn.to_k, "v": attn.to_v, "out": attn.to_out[0]}
+    proc = a.AttnProcessor_LoRA_Capture(capture_ca_activations=True, enable_lora=True, lora_proj_layers=layers, lora_rank=192,
+                                        lora_alpha=16).to(dev)
+    proc.reset_attn_cache_and_flags(True, True, False, True)
+    attn.set_processor(proc)
+    hs = torch.randn(1, N, C, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    ehs = torch.randn(1, S2, CTX_DIM, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    si = (torch.zeros(16, dtype=torch.long, device=dev), torch.arange(4, 20, device=dev))
+    gout = torch.randn(1, N, C, device=dev, dtype=torch.bfloat16)
+    gp = torch.randn(1, H, N, S2, device=dev)
+
+    def cross_step():
+        o = attn(hs, encoder_hidden_states=ehs, subj_indices=si)
+        torch.autograd.backward([o, proc.cached_activations["attn"]], [gout, gp])
+    n0 = a._lib.launch_count()
+    cross_step()
+    n_cross = a._lib.launch_count() - n0
+    us_c = _time_us(torch, flush, cross_step, iters=5, warm=2)
+    sattn = a.Attention(C, None, H, d, device=dev)
+
+    def self_step():
+        sattn(hs).backward(gout)
+    us_s = _time_us(torch, flush, self_step, iters=5, warm=2)
+    out["train_fwd_bwd"] = {"cross_capture_lora_r192_levelA_B1_us": us_c, "cross_kernel_launches": int(n_cross),
+                            "self_attn_levelA_B1_us": us_s,
+                            "self_attn_tflops": 3.5 * (4.0 * N * N * C) / us_s / 1e6}
+    return out
+
+
 def main_gpu(args):
     import torch
     import torch.distributed as dist
@@ -244,20 +333,49 @@ def main_gpu(args):
         launches = (a._lib.launch_count() - n0) if not use_graph else LAUNCHES_PER_STEP * args.steps
         t_ms = sum(s.elapsed_time(e) for s, e in ev)
 
-        # ---- end to end: host buffers in, host results out, through the same public operator
-        outs_host = [torch.empty(x.shape, dtype=torch.bfloat16).pin_memory() for x in xs_cpu]
-        h2d = sum(x.numel() * 2 for x in xs_pin) + ctx_pin.numel() * 2
-        d2h = sum(o.numel() * 2 for o in outs_host)
+        # ---- end to end: host buffers in, host results out, through the same public operator.
+        # The step is cut into five independent units (level D, C, B, and the two half-batches of level A -- samples
+        # are independent), each its own CUDA graph.  Three streams: H2D of unit i+1 and D2H of unit i-1
+        # overlap the kernels of unit i; the small levels go first so that level A's 21 MB input is in flight behind them.
+        half = BATCH // 2
+        units = [(3, slice(0, BATCH)), (2, slice(0, BATCH)), (1, slice(0, BATCH)), (0, slice(0, half)), (0, slice(half, BATCH))]
+        unit_fns, unit_in, unit_out = [], [], []
+        for li, sl in units:
+            x_u, c_u = xs[li][sl].contiguous(), ctx[sl].contiguous()
+            if use_graph:
+                fn = a.graphed(lambda x_, c_, li=li: run_stack([mods[li]], [x_], c_)[0], x_u, c_u)
+            else:
+                fn = lambda x_, c_, li=li: run_stack([mods[li]], [x_], c_)[0]
+            unit_fns.append(fn)
+            unit_in.append((xs_pin[li][sl], ctx_pin[sl]))
+            unit_out.append(torch.empty(x_u.shape, dtype=torch.bfloat16).pin_memory())
+        h2d = sum(x.numel() * 2 + c.numel() * 2 for x, c in unit_in)
+        d2h = sum(o.numel() * 2 for o in unit_out)
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        comp = torch.cuda.current_stream()
+        dev_in = [(fn.static_inputs[0], fn.static_inputs[1]) if use_graph else
+                  (torch.empty_like(x, device=dev), torch.empty_like(c, device=dev)) for fn, (x, c) in zip(unit_fns, unit_in)]
 
         def e2e_step():
-            if use_graph:       # H2D straight into the graph's input buffers, replay, D2H of the results
-                outs = step(xs_pin, ctx_pin)
-            else:
-                xd = [x.to(dev, non_blocking=True) for x in xs_pin]
-                cd = ctx_pin.to(dev, non_blocking=True)
-                outs = run_stack(mods, xd, cd)
-            for oh, o in zip(outs_host, outs):
-                oh.copy_(o, non_blocking=True)
+            s_in.wait_stream(comp)          # the previous step has finished reading the input buffers
+            ev_in, ev_out = [], []
+            with torch.cuda.stream(s_in):
+                for (xd, cd), (xh, ch) in zip(dev_in, unit_in):
+                    xd.copy_(xh, non_blocking=True)
+                    cd.copy_(ch, non_blocking=True)
+                    ev_in.append(torch.cuda.Event())
+                    ev_in[-1].record(s_in)
+            outs = []
+            for fn, (xd, cd), ei in zip(unit_fns, dev_in, ev_in):
+                comp.wait_event(ei)
+                outs.append(fn(xd, cd))     # graph replay (inputs already in the graph's buffers) or eager launches
+                ev_out.append(torch.cuda.Event())
+                ev_out[-1].record(comp)
+            with torch.cuda.stream(s_out):
+                for oh, o, eo in zip(unit_out, outs, ev_out):
+                    s_out.wait_event(eo)
+                    oh.copy_(o, non_blocking=True)
+            comp.wait_stream(s_out)         # the closing event on `comp` then covers the last D2H
 
         e2e_step()
         barrier()
@@ -291,6 +409,12 @@ def main_gpu(args):
         k_ms = statistics.mean(kt)
         k_flops = 4.0 * BATCH * N * N * C
         clocks = sampler.stop()
+    extra = None
+    if world == 1 and os.environ.get("ADAFACE_BENCH_EXTRAS", "1") != "0":
+        try:
+            extra = secondary_measurements(torch, a, dev, flush, peaks())
+        except Exception as ex:      # secondary lines never take the headline down with them
+            extra = {"error": f"{type(ex).__name__}: {ex}"}
 
     tt = torch.tensor([t_ms, t_e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -312,7 +436,8 @@ def main_gpu(args):
                        "launch": "CUDA graph replay of the 112-kernel step" if use_graph else "eager Python launches"},
             "frac_of_bf16_peak": value / world / pk["bf16_tflops_sustained"],
             "e2e": {"value": world * fl_step / (t_e2e_ms * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e_ms},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e_ms,
+                    "how": "5 units (levels D, C, B, two half-batches of A), one CUDA graph each; H2D / kernels / D2H on three streams"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "attn_fwd_tcgen05_mc_kernel<40> (level-A self-attention core, B=8, 4096 tok, 8x40)",
@@ -321,6 +446,8 @@ def main_gpu(args):
                          "traffic": None, "peak_source": pk["source"] + " (burst: kernel timed alone)",
                          "ms_per_launch": k_ms, "flops_per_launch": k_flops},
         }
+        if extra is not None:
+            line["secondary"] = extra
         if world == 1:
             val, dt, _, n = run_cpu(torch, 3, 1, min_seconds=12.0)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
