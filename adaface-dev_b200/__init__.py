@@ -5,7 +5,7 @@ Host-side mirrors of the reference's operator surface over the C-
 
     AttnProcessor_LoRA_Capture, Attention, LoraDoraLinear, gen_gradient_scaler   (attn_processor.py)
     CrossAttention, FeedForward, BasicTransformerBlock                          (ldm_attention.py)
-    SubjBasisGenerator, CLIPTextModelWrapper, CLIPAttentionMKV                   (subj_basis_generator.py)
+    SubjBasisGenerator, Arc2FaceID2ImgPrompt, CLIPTextModelWrapper, CLIPAttentionMKV   (subj_basis_generator.py)
 
 The directory is named ``adaface-dev_b200`` (not importable as is); import it as ``adaface_dev_b200``
 (the alias package at the repository root).
@@ -14,8 +14,8 @@ from . import _lib, ops  # noqa: F401
 from .attn_processor import (AttnProcessor_LoRA_Capture, Attention, LoraDoraLinear, ScaleGrad, GradientScaler,  # noqa: F401
                              gen_gradient_scaler, img_mask_to_key_mask)
 from .ldm_attention import CrossAttention, FeedForward, GEGLU, BasicTransformerBlock  # noqa: F401
-from .subj_basis_generator import (SubjBasisGenerator, CLIPTextModelWrapper, CLIPAttentionMKV, CLIPTextConfig,  # noqa: F401
-                                   template_ids)
+from .subj_basis_generator import (SubjBasisGenerator, Arc2FaceID2ImgPrompt, CLIPTextModelWrapper, CLIPAttentionMKV,  # noqa: F401
+                                   CLIPTextConfig, template_ids)
 from .build import build  # noqa: F401
 from .graphs import graphed  # noqa: F401
 from . import parallel  # noqa: F401

@@ -1,11 +1,9 @@
-// K2 / K3: flash-style attention on warp-level tensor-core MMA (mma.sync m16n8k16, bf16 -> fp32).
+// K2: flash-style attention on warp-level tensor-core MMA (mma.sync m16n8k16, bf16 -> fp32).
 //
 //  * attn_fwd_kernel<D>: online-softmax attention for SD-1.5 head dims 40/80/160 (+64 for the CLIP-shaped
-//    encoder): self-attention with the optional img_mask key mask (dalc:254-273), fast cross-attention
-//    (dalc:321) and CLIPAttentionMKV's causal multi-K/V attention (arc2face_models.py:170-217).
-//  * attn_cross_capture_kernel<D>: the slow SDPA of dalc:79-139 -- all S <= 128 context keys staged once in
-//    shared memory (cross-attention is HBM-bound), score edits (normalize / mix), exact softmax, optional
-//    probability / score / subject-column capture written with fully coalesced stores.
+//    encoder): self-attention with the optional img_mask key mask (dalc:254-273), masked cross-attention
+//    and CLIPAttentionMKV's causal multi-K/V attention (arc2face_models.py:170-217).
+//  (K3, the short-context cross-attention / capture kernel, lives in attn_cross_stream.cu.)
 //
 // Head dim 40 is padded to 48 only in shared memory (zero columns); HBM layouts stay those of the
 // reference: [B, L, H*d] with heads interleaved.
@@ -275,313 +273,6 @@ int attn_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k
     case 160: return launch_attn<160>(p, stream);
   }
   set_error("attn_fwd: unsupported head dim %lld (supported: 40, 64, 80, 160)", (long long)d);
-  return 1;
-}
-
-// =============================================================================================
-// K3: cross-attention with capture / normalize / mix.
-constexpr int CAP_BN = 128;   // max context keys
-
-struct CapParams {
-  const void *q, *k, *v;   // bf16, or fp32 when the kernel is instantiated with F32IN
-  bf16* o;
-  long long q_sb, q_sn, k_sb, k_sn, v_sb, v_sn, o_sb, o_sn;
-  int B, H, Lq, S;
-  float scale;
-  float* prob;
-  float* score;
-  float* prob_subj;
-  const int32_t* subj_cols;
-  int n_subj;
-  const uint8_t* col_flag;
-  const float* qmean;   // [B, H*d]
-  const float* ca_scale;   // device scalar (cross_attn_scale_factor) or null = 1
-  int mix;
-};
-
-template <int D, bool MIX, bool F32IN>
-__global__ void __launch_bounds__(ATT_THREADS) attn_cross_capture_kernel(const CapParams p) {
-  using A = AttDims<D>;
-  constexpr int LD = A::LD, KT = A::KT, NT_O = A::NT_O, NT_S = CAP_BN / 8, NI = MIX ? 2 : 1, NP = F32IN ? 2 : 1;
-  extern __shared__ __align__(16) uint8_t smem_cap[];
-  bf16* sQ = reinterpret_cast<bf16*>(smem_cap);          // [NP][NI][BM][LD]      (NP: hi / lo parts)
-  bf16* sK = sQ + NP * NI * ATT_BM * LD;                 // [NP][NI][CAP_BN][LD]
-  bf16* sV = sK + NP * NI * CAP_BN * LD;                 // [NI][CAP_BN][LD]
-  bf16* sQlo = sQ + NI * ATT_BM * LD;                    // valid only when F32IN
-  bf16* sKlo = sK + NI * CAP_BN * LD;
-  float* sStage = reinterpret_cast<float*>(sV + NI * CAP_BN * LD);   // [4 warps][16][S] (packed rows)
-  float* sColMean = sStage + 4 * 16 * CAP_BN;            // [CAP_BN]
-  uint8_t* sFlag = reinterpret_cast<uint8_t*>(sColMean + CAP_BN);    // [CAP_BN]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int m0 = blockIdx.x * ATT_BM, h = blockIdx.y, b0 = blockIdx.z;
-  const int S = p.S;
-  const int nts = (S + 7) / 8;               // n8 tiles that hold real keys
-  const int half = p.B / 2;
-
-  zero_pad_cols<D>(sQ, NP * NI * ATT_BM);
-  zero_pad_cols<D>(sK, NP * NI * CAP_BN);
-#pragma unroll
-  for (int i = 0; i < NI; ++i) {
-    const int b = b0 + i * half;
-    if constexpr (F32IN) {
-      load_rows_f32_split<D>(sQ + i * ATT_BM * LD, sQlo + i * ATT_BM * LD,
-                             (const float*)p.q + (long long)b * p.q_sb + h * D, p.q_sn, m0, p.Lq, ATT_BM);
-      load_rows_f32_split<D>(sK + i * CAP_BN * LD, sKlo + i * CAP_BN * LD,
-                             (const float*)p.k + (long long)b * p.k_sb + h * D, p.k_sn, 0, S, CAP_BN);
-      load_rows_f32_split<D>(sV + i * CAP_BN * LD, nullptr, (const float*)p.v + (long long)b * p.v_sb + h * D, p.v_sn,
-                             0, S, CAP_BN);
-    } else {
-      load_rows<D>(sQ + i * ATT_BM * LD, (const bf16*)p.q + (long long)b * p.q_sb + h * D, p.q_sn, m0, p.Lq, ATT_BM);
-      load_rows<D>(sK + i * CAP_BN * LD, (const bf16*)p.k + (long long)b * p.k_sb + h * D, p.k_sn, 0, S, CAP_BN);
-      load_rows<D>(sV + i * CAP_BN * LD, (const bf16*)p.v + (long long)b * p.v_sb + h * D, p.v_sn, 0, S, CAP_BN);
-    }
-  }
-  cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
-
-  // normalize: per-column mean over the queries = scale * qmean . k_j  (dalc:123-126)
-  if (threadIdx.x < CAP_BN) {
-    const int j = threadIdx.x;
-    float cm = 0.f;
-    uint8_t fl = 0;
-    if (!MIX && p.col_flag && j < S && p.col_flag[(long long)b0 * S + j]) {
-      fl = 1;
-      const float* qm = p.qmean + ((long long)b0 * p.H + h) * D;
-      const bf16* kr = sK + j * LD;
-      const bf16* kl = sKlo + j * LD;
-#pragma unroll 8
-      for (int dd = 0; dd < D; ++dd) {
-        float kv = __bfloat162float(kr[dd]);
-        if constexpr (F32IN) kv += __bfloat162float(kl[dd]);
-        cm += qm[dd] * kv;
-      }
-      cm *= p.scale;
-    }
-    sColMean[j] = cm;
-    sFlag[j] = fl;
-  }
-  __syncthreads();
-
-  // ---- scores
-  float acc_s[NT_S][4];
-#pragma unroll
-  for (int i = 0; i < NT_S; ++i) acc_s[i][0] = acc_s[i][1] = acc_s[i][2] = acc_s[i][3] = 0.f;
-#pragma unroll
-  for (int i = 0; i < NI; ++i) {
-#pragma unroll
-    for (int kk = 0; kk < KT; ++kk) {
-      const int q_off = i * ATT_BM * LD + (warp * 16 + (lane & 15)) * LD + kk * 16 + (lane >> 4) * 8;
-      uint32_t qf[4], ql[4];
-      ldsm_x4(smem_u32(sQ + q_off), qf[0], qf[1], qf[2], qf[3]);
-      if constexpr (F32IN) ldsm_x4(smem_u32(sQlo + q_off), ql[0], ql[1], ql[2], ql[3]);
-#pragma unroll
-      for (int np = 0; np < NT_S / 2; ++np) {
-        if (2 * np < nts) {
-          const int k_off = i * CAP_BN * LD + (np * 16 + (lane >> 4) * 8 + (lane & 7)) * LD + kk * 16 + ((lane >> 3) & 1) * 8;
-          uint32_t r0, r1, r2, r3;
-          ldsm_x4(smem_u32(sK + k_off), r0, r1, r2, r3);
-          mma_bf16_16816(acc_s[2 * np], qf, r0, r1);
-          mma_bf16_16816(acc_s[2 * np + 1], qf, r2, r3);
-          if constexpr (F32IN) {
-            mma_bf16_16816(acc_s[2 * np], ql, r0, r1);          // lo . hi
-            mma_bf16_16816(acc_s[2 * np + 1], ql, r2, r3);
-            ldsm_x4(smem_u32(sKlo + k_off), r0, r1, r2, r3);
-            mma_bf16_16816(acc_s[2 * np], qf, r0, r1);          // hi . lo
-            mma_bf16_16816(acc_s[2 * np + 1], qf, r2, r3);
-          }
-        }
-      }
-    }
-  }
-  const float sc = MIX ? 0.5f * p.scale : p.scale;   // (score_sc + score_mc) / 2, dalc:117
-  const float ca_scale = p.ca_scale ? __ldg(p.ca_scale) : 1.f;
-  float mx[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-  for (int nt = 0; nt < NT_S; ++nt) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int c = nt * 8 + 2 * t + (e & 1);
-      float s = -INFINITY;
-      if (c < S) {
-        s = acc_s[nt][e] * sc;
-        if (sFlag[c]) s = (s - sColMean[c]) * ca_scale;   // dalc:126-130
-      }
-      acc_s[nt][e] = s;
-      mx[e >> 1] = fmaxf(mx[e >> 1], s);
-    }
-  }
-
-  const int row0 = m0 + warp * 16;
-  const int nrows = max(0, min(16, p.Lq - row0));
-  float* st = sStage + warp * 16 * CAP_BN;
-  auto stage_and_store = [&](float* gbase, bool with_subj) {
-    // registers -> smem [16][S] -> one contiguous, fully coalesced global write per instance
-    __syncwarp();
-#pragma unroll
-    for (int nt = 0; nt < NT_S; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int c = nt * 8 + 2 * t + (e & 1);
-        if (c < S) st[(g + (e >> 1) * 8) * S + c] = acc_s[nt][e];
-      }
-    }
-    __syncwarp();
-    for (int i = 0; i < NI; ++i) {
-      const int b = b0 + i * half;
-      if (gbase) {
-        float* dst = gbase + (((long long)b * p.H + h) * p.Lq + row0) * S;
-        for (int x = lane; x < nrows * S; x += 32) dst[x] = st[x];
-      }
-      if (with_subj && p.prob_subj) {
-        float* dst = p.prob_subj + (((long long)b * p.H + h) * p.Lq + row0) * p.n_subj;
-        const int32_t* cols = p.subj_cols + (long long)b * p.n_subj;
-        for (int x = lane; x < nrows * p.n_subj; x += 32) {
-          const int r = x / p.n_subj, jj = x - r * p.n_subj;
-          const int c = cols[jj];
-          dst[x] = (c >= 0 && c < S) ? st[r * S + c] : 0.f;
-        }
-      }
-    }
-  };
-  if (p.score) stage_and_store(p.score, false);   // edited score (dalc:139, quirk 3)
-
-  // ---- exact softmax over the S keys
-  float inv[2];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
-    mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
-  }
-  float sum[2] = {0.f, 0.f};
-#pragma unroll
-  for (int nt = 0; nt < NT_S; ++nt) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float pv = exp2f((acc_s[nt][e] - mx[e >> 1]) * LOG2E);
-      acc_s[nt][e] = pv;
-      sum[e >> 1] += pv;
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 1);
-    sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 2);
-    inv[i] = 1.f / sum[i];
-  }
-#pragma unroll
-  for (int nt = 0; nt < NT_S; ++nt) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) acc_s[nt][e] *= inv[e >> 1];
-  }
-  if (p.prob || p.prob_subj) stage_and_store(p.prob, true);
-
-  // ---- O = P V per instance
-#pragma unroll
-  for (int i = 0; i < NI; ++i) {
-    float acc_o[NT_O][4];
-#pragma unroll
-    for (int x = 0; x < NT_O; ++x) acc_o[x][0] = acc_o[x][1] = acc_o[x][2] = acc_o[x][3] = 0.f;
-#pragma unroll
-    for (int kk = 0; kk < CAP_BN / 16; ++kk) {
-      if (2 * kk < nts) {
-        uint32_t a[4];
-        a[0] = pack_bf16(acc_s[2 * kk][0], acc_s[2 * kk][1]);
-        a[1] = pack_bf16(acc_s[2 * kk][2], acc_s[2 * kk][3]);
-        a[2] = pack_bf16(acc_s[2 * kk + 1][0], acc_s[2 * kk + 1][1]);
-        a[3] = pack_bf16(acc_s[2 * kk + 1][2], acc_s[2 * kk + 1][3]);
-        const bf16* vrow = sV + i * CAP_BN * LD + (kk * 16 + (lane & 15)) * LD;
-#pragma unroll
-        for (int nt = 0; nt + 1 < NT_O; nt += 2) {
-          uint32_t r0, r1, r2, r3;
-          ldsm_x4_trans(smem_u32(vrow + nt * 8 + (lane >> 4) * 8), r0, r1, r2, r3);
-          mma_bf16_16816(acc_o[nt], a, r0, r1);
-          mma_bf16_16816(acc_o[nt + 1], a, r2, r3);
-        }
-        if (NT_O & 1) {
-          uint32_t r0, r1;
-          ldsm_x2_trans(smem_u32(vrow + (NT_O - 1) * 8), r0, r1);
-          mma_bf16_16816(acc_o[NT_O - 1], a, r0, r1);
-        }
-      }
-    }
-    bf16* sO = sQ + i * ATT_BM * LD + warp * 16 * LD;   // this warp's own Q rows: no longer needed
-    __syncwarp();
-#pragma unroll
-    for (int nt = 0; nt < NT_O; ++nt) {
-      *reinterpret_cast<uint32_t*>(sO + g * LD + nt * 8 + 2 * t) = pack_bf16(acc_o[nt][0], acc_o[nt][1]);
-      *reinterpret_cast<uint32_t*>(sO + (g + 8) * LD + nt * 8 + 2 * t) = pack_bf16(acc_o[nt][2], acc_o[nt][3]);
-    }
-    __syncwarp();
-    const int b = b0 + i * half;
-    bf16* go = p.o + (long long)b * p.o_sb + h * D;
-    for (int c = lane; c < nrows * A::CH; c += 32) {
-      const int r = c / A::CH, ch = c - r * A::CH;
-      *reinterpret_cast<uint4*>(go + (long long)(row0 + r) * p.o_sn + ch * 8) =
-          *reinterpret_cast<const uint4*>(sO + r * LD + ch * 8);
-    }
-  }
-}
-
-template <int D, bool MIX, bool F32IN>
-static int launch_cap(const CapParams& p, cudaStream_t stream) {
-  using A = AttDims<D>;
-  constexpr int NI = MIX ? 2 : 1, NP = F32IN ? 2 : 1;
-  constexpr int smem = NI * (NP * ATT_BM + NP * CAP_BN + CAP_BN) * A::LD * 2 + 4 * 16 * CAP_BN * 4 + CAP_BN * 4 + CAP_BN;
-  static_assert(smem <= 227 * 1024, "capture kernel shared memory exceeds the SM");
-  static bool configured = false;
-  if (!configured) {
-    AF_CUDA(cudaFuncSetAttribute(attn_cross_capture_kernel<D, MIX, F32IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
-  dim3 grid((p.Lq + ATT_BM - 1) / ATT_BM, p.H, MIX ? p.B / 2 : p.B);
-  attn_cross_capture_kernel<D, MIX, F32IN><<<grid, ATT_THREADS, smem, stream>>>(p);
-  AF_CUDA(cudaGetLastError());
-  ++g_launch_count;
-  return 0;
-}
-
-int attn_cross_capture_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn,
-                           const void* v, int64_t v_sb, int64_t v_sn, void* o, int64_t o_sb, int64_t o_sn, int64_t B,
-                           int64_t H, int64_t Lq, int64_t S, int64_t d, float scale, float* prob, float* score,
-                           float* prob_subj, const int32_t* subj_cols, int64_t n_subj, const uint8_t* col_flag,
-                           const float* qmean, const float* ca_scale, int mix, int in_dtype, cudaStream_t stream) {
-  if (check_view("q", q, q_sb, q_sn, d) || check_view("k", k, k_sb, k_sn, d) || check_view("v", v, v_sb, v_sn, d) ||
-      check_view("o", o, o_sb, o_sn, d))
-    return 1;
-  AF_CHECK(in_dtype == ADAFACE_BF16 || in_dtype == ADAFACE_F32, "attn_cross_capture_fwd: bad in_dtype %d", in_dtype);
-  AF_CHECK(B > 0 && H > 0 && Lq > 0 && S > 0, "attn_cross_capture_fwd: empty problem");
-  AF_CHECK(S <= CAP_BN, "attn_cross_capture_fwd: context length %lld exceeds %d keys", (long long)S, CAP_BN);
-  AF_CHECK(B <= 65535 && H <= 65535, "attn_cross_capture_fwd: B/H exceed grid limits");
-  AF_CHECK(!(mix && (B % 2)), "mix_attn_mats_in_batch needs an even batch [sc.., mc..] (dalc:113), got B=%lld",
-           (long long)B);
-  AF_CHECK(!(mix && col_flag), "normalize and mix are mutually exclusive (dalc:108-119: mix wins)");
-  AF_CHECK(!(col_flag && !qmean), "normalize_cross_attn needs qmean (and subj_indices, dalc:120)");
-  AF_CHECK(!(prob_subj && (!subj_cols || n_subj <= 0)), "prob_subj needs subj_cols / n_subj");
-  CapParams p;
-  p.q = q; p.k = k; p.v = v; p.o = (bf16*)o;
-  p.q_sb = q_sb; p.q_sn = q_sn; p.k_sb = k_sb; p.k_sn = k_sn; p.v_sb = v_sb; p.v_sn = v_sn; p.o_sb = o_sb; p.o_sn = o_sn;
-  p.B = (int)B; p.H = (int)H; p.Lq = (int)Lq; p.S = (int)S;
-  p.scale = scale;
-  p.prob = prob; p.score = score; p.prob_subj = prob_subj; p.subj_cols = subj_cols; p.n_subj = (int)n_subj;
-  p.col_flag = col_flag; p.qmean = qmean; p.ca_scale = ca_scale; p.mix = mix;
-  const bool f32 = in_dtype == ADAFACE_F32;
-  if (mix) {
-    switch (d) {
-      case 40: return f32 ? launch_cap<40, true, true>(p, stream) : launch_cap<40, true, false>(p, stream);
-      case 80: return f32 ? launch_cap<80, true, true>(p, stream) : launch_cap<80, true, false>(p, stream);
-    }
-    set_error("attn_cross_capture_fwd: mix supports head dims 40 and 80, got %lld", (long long)d);
-    return 1;
-  }
-  switch (d) {
-    case 40: return f32 ? launch_cap<40, false, true>(p, stream) : launch_cap<40, false, false>(p, stream);
-    case 80: return f32 ? launch_cap<80, false, true>(p, stream) : launch_cap<80, false, false>(p, stream);
-    case 160: return f32 ? launch_cap<160, false, true>(p, stream) : launch_cap<160, false, false>(p, stream);
-  }
-  set_error("attn_cross_capture_fwd: unsupported head dim %lld (supported: 40, 80, 160)", (long long)d);
   return 1;
 }
 

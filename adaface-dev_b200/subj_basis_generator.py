@@ -245,6 +245,42 @@ class CLIPTextModelWrapper(nn.Module):
         return n
 
 
+class Arc2FaceID2ImgPrompt(nn.Module):
+    """The stage in front of SubjBasisGenerator: ArcFace 512-d ID embedding -> 16 x 768 image-prompt
+    embeddings, ``Arc2Face_ID2AdaPrompt.map_init_id_to_img_prompt_embs`` (adaface/face_id_to_ada_prompt.py:680-724).
+
+    "photo of a id person" is tokenised and padded to 22 tokens, the 512-d embedding is zero-padded to 768 and written
+    over the token embedding of "id" (position 4), the FROZEN Arc2Face CLIP text encoder (CLIPTextModelWrapper, stock
+    K/V multiplier 1, plain final LayerNorm) runs, and positions 4:20 are returned.  The encoder is causal and nothing
+    past position 19 is returned, so it runs on 20 positions instead of 22 -- exact.  Same kernels as SubjBasisGenerator."""
+
+    PROMPT_IDS = [BOS, 1125, 539, 320, 1014, 2533] + [EOS] * 16          # <bos> photo of a id person <eos> + padding -> 22
+    ARCFACE_POS = 4
+
+    def __init__(self, clip_config=None, dtype=torch.float32):
+        super().__init__()
+        self.dtype = dtype
+        self.id_img_prompt_max_length = 22
+        self.text_to_image_prompt_encoder = CLIPTextModelWrapper(clip_config)
+        for p in self.text_to_image_prompt_encoder.parameters():                 # face_id_to_ada_prompt.py:639-640
+            p.requires_grad = False
+        self.register_buffer("input_ids", torch.tensor(self.PROMPT_IDS), persistent=False)
+
+    def map_init_id_to_img_prompt_embs(self, init_id_embs, clip_features=None, called_for_neg_img_prompt=False):
+        if init_id_embs.dim() != 2 or init_id_embs.shape[1] > 768:
+            raise ValueError(f"init_id_embs must be [N, 512], got {tuple(init_id_embs.shape)}")
+        enc = self.text_to_image_prompt_encoder
+        N, E = init_id_embs.shape[0], enc.config.hidden_size
+        ids = self.input_ids[:20].to(init_id_embs.device)
+        tok = enc(input_ids=ids, return_token_embs=True).float().unsqueeze(0).repeat(N, 1, 1)     # :708
+        tok[:, self.ARCFACE_POS, :init_id_embs.shape[1]] = init_id_embs.float()                   # :705-709 (zero-padded)
+        tok[:, self.ARCFACE_POS, init_id_embs.shape[1]:] = 0
+        prompt_embeds = enc(input_token_embs=tok, num_positions=20)[0]                            # :711-715
+        return prompt_embeds[:, 4:20].to(self.dtype)                                              # :718-723
+
+    forward = map_init_id_to_img_prompt_embs
+
+
 class SubjBasisGenerator(nn.Module):
     """Face-ID image-prompt embeddings [BS,16,768] -> ada prompt embeddings [BS,16(+N_SFX),768]
     (subj_basis_generator.py:564-770, face path; the bg / object branches :733-756 are out of scope)."""

@@ -239,17 +239,25 @@ def secondary_measurements(torch, a, dev, flush, pk):
         maps = B * H * N * S * 4
         for nm, kw, by in (("capture_prob", dict(want_score=False), core + maps), ("capture_prob_score", {}, core + 2 * maps)):
             us = _time_us(torch, flush, lambda: ops.attention_cross_capture(qf, kf, vf, H, d ** -0.5, **kw))
-            out[nm] = {"kernel": "attn_cross_capture_kernel<40,fp32>", "shape": f"B={B} N={N} C={C} S={S}", "us": us,
+            out[nm] = {"kernel": "attn_cross_stream_kernel<40,fp32 hi/lo>", "shape": f"B={B} N={N} C={C} S={S}", "us": us,
                        "algorithmic_bytes": by, "achieved_gbs": by / us / 1e3, "peak_gbs": hbm, "frac": by / us / 1e3 / hbm}
-        # -- SubjBasisGenerator, BASELINE config 2: [64,16,768] -> [64,16,768], random init, 12 layers, K/V multiplier 1
+        # -- BASELINE config 2: ArcFace 512-d ID embedding -> 16 ada prompt tokens, batch 64, random init:
+        #    Arc2Face ID -> image-prompt encoder (12 CLIP layers) + SubjBasisGenerator (12 layers, K/V multiplier 1)
         gen = a.SubjBasisGenerator().to(dev).eval()
+        id2img = a.Arc2FaceID2ImgPrompt().to(dev).eval()
+        ids = torch.nn.functional.normalize(torch.randn(64, 512, device=dev), dim=-1)
         x = torch.randn(64, 16, 768, device=dev) * 0.5
         fn = a.graphed(lambda t: gen(t), x)
         us = _time_us(torch, flush, lambda: fn(x))
+        fn2 = a.graphed(lambda t: gen(id2img(t)), ids)
+        us2 = _time_us(torch, flush, lambda: fn2(ids))
         T = 20
         fl = 64 * 12 * (24 * T * 768 * 768 + 4 * T * T * 768)
         out["subj_basis_generator"] = {"shape": "BS=64, N_ID=16, T_run=20 (causal-exact truncation of 77)", "us": us,
                                        "flops_executed": fl, "tflops": fl / us / 1e6, "samples_per_s": 64 / us * 1e6}
+        out["arcface_to_ada_tokens"] = {"shape": "BS=64: [64,512] -> Arc2Face CLIP encoder -> SubjBasisGenerator -> [64,16,768]",
+                                        "us": us2, "flops_executed": 2 * fl, "tflops": 2 * fl / us2 / 1e6,
+                                        "samples_per_s": 64 / us2 * 1e6}
     # -- training: forward + backward through one captured cross-attention module (level A, B = 1, S = 97, DoRA r = 192
     #    on q/k/v/out, normalize_cross_attn, loss on out + captured attn) and through one self-attention module
     S2 = 97

@@ -33,5 +33,7 @@ from .sbg_oracle import (  # noqa: F401
     clip_encoder_layer,
     clip_text_wrapper_forward,
     sbg_forward,
+    arc2face_id_to_img_prompt,
     SBG_TEMPLATE_IDS,
+    ARC2FACE_PROMPT_IDS,
 )

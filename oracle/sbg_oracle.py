@@ -94,3 +94,20 @@ def sbg_forward(w, faceid2img_prompt_embs, out_id_embs_cfg_scale=1.0, enable_sta
         pad = w["pad_embeddings"][4:4 + N_ID].unsqueeze(0)
         out[:, :N_ID] = core[:, :N_ID] * out_id_embs_cfg_scale + pad * (1 - out_id_embs_cfg_scale)
     return out
+
+
+ARC2FACE_PROMPT_IDS = [49406, 1125, 539, 320, 1014, 2533] + [49407] * 16       # "photo of a id person" padded to 22
+
+
+def arc2face_id_to_img_prompt(w, init_id_embs, prompt_embs=None):
+    """Arc2Face_ID2AdaPrompt.map_init_id_to_img_prompt_embs (adaface/face_id_to_ada_prompt.py:680-724): the 512-d
+    ArcFace embedding, zero-padded to 768 (:703), replaces the token embedding of "id" (position 4, :709) in the
+    22-token prompt; frozen CLIP text encoder (CLIPTextModelWrapper.forward without layer weights, :711-715);
+    positions 4:20 are returned (:723).  ``w``: token_emb [V,E] or precomputed ``prompt_embs`` [22,E], pos_emb, layers,
+    final_ln_*."""
+    N = init_id_embs.shape[0]
+    base = prompt_embs if prompt_embs is not None else w["token_emb"][torch.tensor(ARC2FACE_PROMPT_IDS)]
+    tok = base.unsqueeze(0).repeat(N, 1, 1)
+    E = tok.shape[-1]
+    tok[:, 4] = F.pad(init_id_embs, (0, E - init_id_embs.shape[-1]))
+    return clip_text_wrapper_forward(w, tok, None)[:, 4:20]

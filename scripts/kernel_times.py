@@ -55,6 +55,8 @@ for B in (2, 8):
     vh = kv[:, :, C:].unflatten(2, (H, d)).transpose(1, 2)
     timeit(f"cross fast (head-major q)    B={B} N={N} d={d}", lambda: ops.attention_headmajor(ws, kh, vh, d ** -0.5, d=d),
            bytes_=B * N * H * 64 * 2 + B * N * C * 2)
+    timeit(f"cross stream bf16 (interleaved)  B={B} N={N} d={d}",
+           lambda: ops.attention_cross_capture(q, kv[:, :, :C], kv[:, :, C:], H, d ** -0.5, want_prob=False, want_score=False), bytes_=core)
     qf, kf, vf = rn(B, N, C, dt=torch.float32), rn(B, S, C, dt=torch.float32), rn(B, S, C, dt=torch.float32)
     maps = B * H * N * S * 4
     cap_core = B * N * C * 4 + B * N * C * 2 + 2 * B * S * C * 4

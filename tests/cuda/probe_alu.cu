@@ -4,6 +4,10 @@
 #include <stdint.h>
 __device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+__device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) { uint32_t y; asm volatile("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) { uint32_t y; asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) { uint32_t y; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo)); return y; }
+
 template <int OP>
 __global__ void k(int iters, float* out, long long* cyc) {
   float a[16];
@@ -22,6 +26,15 @@ __global__ void k(int iters, float* out, long long* cyc) {
       if (OP == 4) { float2 t = __ffma2_rn(make_float2(a[i], a[(i + 1) & 15]), make_float2(1.0001f, 1.0001f), make_float2(-0.5f, -0.5f)); a[i] = t.x; a[(i + 1) & 15] = t.y; ++i; }  // FFMA2
       if (OP == 5) { a[i] = ex2(a[i]); a[i] = fmaf(a[i], 0.5f, -1.f); }        // MUFU + FFMA mix
       if (OP == 6) a[i] = __uint_as_float(__byte_perm(__float_as_uint(a[i]), __float_as_uint(a[(i + 1) & 15]), 0x7632)); // PRMT
+      if (OP == 7) a[i] = __uint_as_float(ex2_bf16x2(__float_as_uint(a[i])));   // MUFU.EX2 bf16x2 (2 results per lane-op)
+      if (OP == 8) a[i] = __uint_as_float(ex2_f16x2(__float_as_uint(a[i])));    // MUFU.EX2 f16x2
+      if (OP == 9) a[i] = __uint_as_float(cvt_bf16x2(a[i], a[(i + 1) & 15]));   // F2FP pack
+      if (OP == 10) a[i] = fmaxf(fmaxf(a[i], a[(i + 1) & 15]), a[(i + 2) & 15]); // FMNMX3 ?
+      if (OP == 11) a[i] = __uint_as_float(__float_as_uint(a[i]) + 0x8000u);    // IADD
+      if (OP == 12) {   // candidate softmax inner step for one PAIR: FFMA2, 2 x IADD, PRMT, EX2.bf16x2
+        float2 t = __ffma2_rn(make_float2(a[i], a[(i + 1) & 15]), make_float2(1.0001f, 1.0001f), make_float2(-0.5f, -0.5f));
+        const uint32_t u = __byte_perm(__float_as_uint(t.x) + 0x8000u, __float_as_uint(t.y) + 0x8000u, 0x7632);
+        a[i] = __uint_as_float(ex2_bf16x2(u)); a[(i + 1) & 15] = t.y * 0.f + a[(i + 1) & 15]; ++i; }
     }
   }
   const long long t1 = clock64();
@@ -34,10 +47,10 @@ __global__ void k(int iters, float* out, long long* cyc) {
 
 int main() {
   float* out; long long* cyc; cudaMalloc(&out, 148 * 1024 * 4); cudaMalloc(&cyc, 8);
-  const char* names[] = {"MUFU.EX2", "FFMA", "LOP3", "FMNMX", "FFMA2(pairs)", "EX2+FFMA", "PRMT"};
+  const char* names[] = {"MUFU.EX2", "FFMA", "LOP3", "FMNMX", "FFMA2(pairs)", "EX2+FFMA", "PRMT", "EX2.bf16x2", "EX2.f16x2", "F2FP.bf16x2", "FMNMX x2", "IADD", "pair-step"};
   const int iters = 2000;
-  for (int warps : {4, 8, 16, 32}) {
-    for (int op = 0; op < 7; ++op) {
+  for (int warps : {8, 16, 32}) {
+    for (int op = 0; op < 13; ++op) {
       switch (op) {
         case 0: k<0><<<148, warps * 32>>>(iters, out, cyc); break;
         case 1: k<1><<<148, warps * 32>>>(iters, out, cyc); break;
@@ -46,6 +59,12 @@ int main() {
         case 4: k<4><<<148, warps * 32>>>(iters, out, cyc); break;
         case 5: k<5><<<148, warps * 32>>>(iters, out, cyc); break;
         case 6: k<6><<<148, warps * 32>>>(iters, out, cyc); break;
+        case 7: k<7><<<148, warps * 32>>>(iters, out, cyc); break;
+        case 8: k<8><<<148, warps * 32>>>(iters, out, cyc); break;
+        case 9: k<9><<<148, warps * 32>>>(iters, out, cyc); break;
+        case 10: k<10><<<148, warps * 32>>>(iters, out, cyc); break;
+        case 11: k<11><<<148, warps * 32>>>(iters, out, cyc); break;
+        case 12: k<12><<<148, warps * 32>>>(iters, out, cyc); break;
       }
       cudaDeviceSynchronize();
       long long c = 0; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);

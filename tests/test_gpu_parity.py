@@ -178,3 +178,30 @@ def test_sbg_config2_full_size_properties():
     t = C.to_torch({k: v for k, v in case.items() if k != "spec"})
     ref = oracle.sbg_forward(t["w"], x[:4], multipliers=[1] * 12)          # dense T = 77 restatement
     assert err(out[:4], ref) < 3e-2
+
+
+def test_arc2face_id_to_img_prompt_vs_oracle():
+    """SURVEY 8f row 3 (first half): ArcFace 512-d -> 16 x 768 image-prompt embeddings through the frozen CLIP text
+    encoder (face_id_to_ada_prompt.py:680-724), then on into SubjBasisGenerator -- BASELINE config 2 end to end."""
+    import adaface_dev_b200 as a
+    case = C.build_sbg_case("sbg_m1")
+    gen = make_sbg(case["w"], [1] * 12)
+    m = a.Arc2FaceID2ImgPrompt(clip_config=a.CLIPTextConfig(num_hidden_layers=1)).cuda()
+    m.text_to_image_prompt_encoder = gen.prompt2token_proj            # same seeded 12-layer weights as the SBG case
+    g = torch.Generator().manual_seed(11)
+    rows = {1014: (torch.randn(768, generator=g) * 0.02).bfloat16().float(), 2533: (torch.randn(768, generator=g) * 0.02).bfloat16().float()}
+    with torch.no_grad():
+        for tid, r in rows.items():
+            gen.prompt2token_proj.text_model.embeddings.token_embedding.weight[tid] = r.cuda()
+    ids = torch.nn.functional.normalize(torch.randn(5, 512, generator=g), dim=-1).bfloat16().float()
+    with torch.no_grad():
+        out = m(ids.cuda())
+        ada = gen(out)
+    t = C.to_torch({k: v for k, v in case.items() if k != "spec"})
+    w = t["w"]
+    tok_rows = {int(k): v for k, v in w["token_emb_rows"].items()}
+    tok_rows.update(rows)
+    prompt = torch.stack([tok_rows[i] for i in oracle.ARC2FACE_PROMPT_IDS])
+    ref = oracle.arc2face_id_to_img_prompt(w, ids, prompt_embs=prompt)
+    assert tuple(out.shape) == (5, 16, 768) and err(out, ref) < 3e-2
+    assert err(ada, oracle.sbg_forward(w, ref, multipliers=[1] * 12)) < 4e-2

@@ -113,3 +113,22 @@ def test_dora_identity_at_init():
     m = torch.linalg.norm(W + 0.125 * B @ A, dim=1)          # m == ||W + sBA||  -> plain LoRA
     y = oracle.lora_dora_linear(x, W, None, A, B, m, 0.125)
     assert torch.allclose(y, x @ (W + 0.125 * B @ A).T, atol=1e-5)
+
+
+def test_causal_truncation_is_exact_in_the_oracle():
+    """The product runs the CLIP-shaped encoders on 20 positions instead of 22 / 77: with a causal mask
+    the returned positions 4:20 cannot depend on later ones.  Checked on the oracle itself, small 2-layer stack."""
+    import oracle
+    case = C.build_sbg_case("sbg_m1")
+    t = C.to_torch({k: v for k, v in case.items() if k != "spec"})
+    w = dict(t["w"])
+    w["layers"] = w["layers"][:2]
+    g = torch.Generator().manual_seed(3)
+    prompt = torch.randn(22, 768, generator=g) * 0.02
+    ids = torch.nn.functional.normalize(torch.randn(3, 512, generator=g), dim=-1)
+    full = oracle.arc2face_id_to_img_prompt(w, ids, prompt_embs=prompt)
+    tok = prompt[:20].unsqueeze(0).repeat(3, 1, 1)
+    tok[:, 4] = torch.nn.functional.pad(ids, (0, 256))
+    short = oracle.clip_text_wrapper_forward(w, tok, None)[:, 4:20]
+    assert tuple(full.shape) == (3, 16, 768)
+    assert (full - short).abs().max().item() < 1e-5
