@@ -578,6 +578,272 @@ static int launch_ta(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtenso
   return 0;
 }
 
+// =============================================================================================
+// Short-context variant (cross-attention over the 77 / 97-token prompt, Lk <= 128): HBM-bound, so built to stream.
+// With one CTA per 128-query tile the kernel above spends most of a CTA's life in set-up (TMEM allocation, barrier
+// init, descriptor fetch, first-TMA latency: ~9 us per wave for ~1 us of work).  Here CTAs are PERSISTENT: each owns
+// a contiguous range of (batch, head, query-tile) units, keeps K and V of the current (batch, head) in shared memory
+// (loaded once, all NK = ceil16(Lk) keys as ONE tile), double-buffers the Q tiles through TMA, and runs an EXACT
+// single-pass softmax per tile (every key is present: no online rescaling).  S (NK fp32 columns) and P (bf16, written
+// over S) share one TMEM region, O sits behind it; 128 TMEM columns when NK + DO <= 128 (d = 40, 77 keys: 4 CTAs / SM).
+struct TcParams {
+  bf16* o;
+  long long o_sb, o_sn;
+  int Lq, Lk, H, NK, n_qtiles, n_units, tmem_cols;
+  float scale_log2;
+  float* lse;
+};
+
+// NKT = compile-time number of staged keys (80: the 77-token prompt; 128: anything up to 128, e.g. 97 in training):
+// the score loops unroll completely and only the chunk that straddles Lk pays for masking.
+template <int D, int NKT>
+__global__ void __launch_bounds__(TA_THREADS, (D <= 64) ? 4 : 2)
+attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const TcParams p) {
+  using Cfg = TaCfg<D>;
+  constexpr int NA = Cfg::NA, KT = Cfg::KT, DO = Cfg::DO;
+  constexpr int NK = NKT;                                  // staged keys (multiple of 16, <= 128)
+  constexpr int KV_ATOM = NK * 128;                        // bytes of one 64-column atom of the K / V tile
+  constexpr int TMEM_O = NK;                               // O behind the S / P region
+  extern __shared__ uint8_t smem_raw_tc[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                      // [2][NA][128 rows][128 B]
+  uint8_t* sK = sQ + 2 * Cfg::Q_BYTES;                     // [NA][NK][128 B]
+  uint8_t* sV = sK + NA * KV_ATOM;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NA * KV_ATOM);
+  uint64_t* q_full = bars;                                 // [2]
+  uint64_t* q_empty = bars + 2;                            // [2]
+  uint64_t* kv_full = bars + 4;
+  uint64_t* kv_empty = bars + 5;
+  uint64_t* s_full = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* o_full = bars + 8;
+  uint64_t* o_free = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = (int)((long long)blockIdx.x * p.n_units / gridDim.x);
+  const int u1 = (int)((long long)(blockIdx.x + 1) * p.n_units / gridDim.x);
+
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+    }
+    mbar_init(kv_full, 1);
+    mbar_init(kv_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    mbar_init(o_free, 128);
+    fence_barrier_init();
+  } else if (warp == kMmaWarp) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kTmaWarp) {
+    if (elect_one()) {
+      int prev_bh = -1, kv_loads = 0;
+      for (int u = u0, i = 0; u < u1; ++u, ++i) {
+        const int bh = u / p.n_qtiles, qt = u - bh * p.n_qtiles;
+        const int b = bh / p.H, h = bh - b * p.H;
+        if (bh != prev_bh) {
+          if (kv_loads > 0) mbar_wait(kv_empty, (kv_loads - 1) & 1);   // every MMA that read the old K / V has retired
+          mbar_arrive_expect_tx(kv_full, 2 * NA * KV_ATOM);
+#pragma unroll
+          for (int a = 0; a < NA; ++a) {
+            tma_load_4d(sK + a * KV_ATOM, &tmK, kv_full, a * 64, h, 0, b);
+            tma_load_4d(sV + a * KV_ATOM, &tmV, kv_full, a * 64, h, 0, b);
+          }
+          ++kv_loads;
+          prev_bh = bh;
+        }
+        const int s = i & 1;
+        if (i >= 2) mbar_wait(&q_empty[s], ((i >> 1) - 1) & 1);
+        mbar_arrive_expect_tx(&q_full[s], Cfg::Q_BYTES);
+#pragma unroll
+        for (int a = 0; a < NA; ++a) tma_load_4d(sQ + s * Cfg::Q_BYTES + a * (TA_BM * 128), &tmQ, &q_full[s], a * 64, h, qt * TA_BM, b);
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16_f32(TA_BM, NK, false);
+      constexpr uint32_t idesc_pv = make_idesc_bf16_f32(TA_BM, DO, true);
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
+      int prev_bh = -1, kv_loads = 0;
+      for (int u = u0, i = 0; u < u1; ++u, ++i) {
+        const int bh = u / p.n_qtiles;
+        if (bh != prev_bh) {
+          mbar_wait(kv_full, kv_loads & 1);
+          ++kv_loads;
+          prev_bh = bh;
+        }
+        const int s = i & 1;
+        mbar_wait(&q_full[s], (i >> 1) & 1);
+        if (i >= 1) mbar_wait(o_free, (i - 1) & 1);          // the softmax warps have drained S / P / O of the previous unit
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < KT; ++kk) {
+          const uint64_t da = make_smem_desc_sw128(aQ + s * Cfg::Q_BYTES + (kk >> 2) * (TA_BM * 128) + (kk & 3) * 32);
+          const uint64_t db = make_smem_desc_sw128(aK + (kk >> 2) * KV_ATOM + (kk & 3) * 32);
+          umma_bf16(tmem_base, da, db, idesc_qk, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+        umma_commit(&q_empty[s]);                            // the Q tile is free once S has been produced
+        mbar_wait(p_full, i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < NK / 16; ++k) {
+          const uint64_t db = make_smem_desc_sw128_mn(aV + k * 2048, (uint32_t)KV_ATOM);
+          umma_bf16_ts(tmem_base + (uint32_t)TMEM_O, tmem_base + (uint32_t)(k * 8), db, idesc_pv, k != 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        const int next_bh = (u + 1 < u1) ? (u + 1) / p.n_qtiles : -1;
+        if (next_bh != bh) umma_commit(kv_empty);
+      }
+    }
+  } else {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16);
+    for (int u = u0, i = 0; u < u1; ++u, ++i) {
+      const int bh = u / p.n_qtiles, qt = u - bh * p.n_qtiles;
+      const int b = bh / p.H, h = bh - b * p.H;
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+      // ---- pass 1: row max of the raw scores (keys >= Lk are zero rows of K: masked out)
+      float mxr = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < NK; c += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_lane + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (c + 16 > p.Lk) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c + j >= p.Lk) v[j] = 0xff800000u;
+        }
+        float m4[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
+#pragma unroll
+        for (int j = 4; j < 16; j += 4) {
+#pragma unroll
+          for (int x = 0; x < 4; ++x) m4[x] = fmaxf(m4[x], __uint_as_float(v[j + x]));
+        }
+        mxr = fmaxf(mxr, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+      }
+      const float m_ref = mxr * p.scale_log2;
+      // ---- pass 2: P = exp2(s * scale - max) truncated to bf16, written over the scores it came from
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
+      float2 ls[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+      for (int c = 0; c < NK; c += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_lane + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (c + 16 > p.Lk) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c + j >= p.Lk) v[j] = 0xff800000u;
+        }
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), sc2, nm2);
+          const float2 e = make_float2(fast_exp2(t.x), fast_exp2(t.y));
+          const uint32_t ex = __float_as_uint(e.x) & 0xffff0000u, ey = __float_as_uint(e.y) & 0xffff0000u;
+          ls[j & 1] = __fadd2_rn(ls[j & 1], make_float2(__uint_as_float(ex), __uint_as_float(ey)));
+          pk[j] = __byte_perm(ex, ey, 0x7632);
+        }
+        tmem_st_32x32b_x8(t_lane + (uint32_t)(c >> 1), pk);     // columns [c/2, c/2 + 8): already consumed
+      }
+      tmem_st_wait();
+      const float l_run = (ls[0].x + ls[0].y) + (ls[1].x + ls[1].y);
+      tc_fence_before();
+      mbar_arrive(p_full);
+      // ---- epilogue: O / l -> bf16 -> [B, Lq, H*d]
+      mbar_wait(o_full, i & 1);
+      tc_fence_after();
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      const int grow = qt * TA_BM + row;
+      if (p.lse && grow < p.Lq)
+        p.lse[((long long)b * p.H + h) * p.Lq + grow] = l_run > 0.f ? m_ref + log2f(l_run) : INFINITY;
+      bf16* orow = p.o + (long long)b * p.o_sb + (long long)grow * p.o_sn + h * D;
+#pragma unroll
+      for (int c = 0; c < DO / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_lane + (uint32_t)(TMEM_O + c * 16), v);
+        tmem_ld_wait();
+        if (grow < p.Lq) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            if (c * 16 + half * 8 < D) {
+              uint4 pk;
+              pk.x = pack_bf16(__uint_as_float(v[half * 8 + 0]) * inv, __uint_as_float(v[half * 8 + 1]) * inv);
+              pk.y = pack_bf16(__uint_as_float(v[half * 8 + 2]) * inv, __uint_as_float(v[half * 8 + 3]) * inv);
+              pk.z = pack_bf16(__uint_as_float(v[half * 8 + 4]) * inv, __uint_as_float(v[half * 8 + 5]) * inv);
+              pk.w = pack_bf16(__uint_as_float(v[half * 8 + 6]) * inv, __uint_as_float(v[half * 8 + 7]) * inv);
+              *reinterpret_cast<uint4*>(orow + c * 16 + half * 8) = pk;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(o_free);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+template <int D, int NKT>
+static int launch_tc_cross(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sh,
+                           int64_t k_sn, const void* v, int64_t v_sb, int64_t v_sh, int64_t v_sn, void* o, int64_t o_sb,
+                           int64_t o_sn, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t drow_q, int64_t drow_kv,
+                           float scale, float* lse, cudaStream_t stream) {
+  using Cfg = TaCfg<D>;
+  constexpr int NK = NKT;
+  CUtensorMap tQ, tK, tV;
+  if (make_tmap_bf16_heads(&tQ, q, (uint64_t)drow_q, (uint64_t)H, (uint64_t)Lq, (uint64_t)B, (uint64_t)q_sh, (uint64_t)q_sn, (uint64_t)q_sb, TA_BM)) return 3;
+  if (make_tmap_bf16_heads(&tK, k, (uint64_t)drow_kv, (uint64_t)H, (uint64_t)Lk, (uint64_t)B, (uint64_t)k_sh, (uint64_t)k_sn, (uint64_t)k_sb, (uint32_t)NK)) return 3;
+  if (make_tmap_bf16_heads(&tV, v, (uint64_t)drow_kv, (uint64_t)H, (uint64_t)Lk, (uint64_t)B, (uint64_t)v_sh, (uint64_t)v_sn, (uint64_t)v_sb, (uint32_t)NK)) return 3;
+  TcParams p;
+  p.o = (bf16*)o; p.o_sb = o_sb; p.o_sn = o_sn;
+  p.Lq = (int)Lq; p.Lk = (int)Lk; p.H = (int)H; p.NK = NK;
+  p.n_qtiles = (int)((Lq + TA_BM - 1) / TA_BM);
+  p.n_units = (int)(B * H) * p.n_qtiles;
+  p.tmem_cols = (NK + Cfg::DO <= 128) ? 128 : 256;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.lse = lse;
+  const int smem = 2 * Cfg::Q_BYTES + 2 * Cfg::NA * NK * 128 + 1024 + 128;
+  static int configured = 0;
+  if (smem > configured) {
+    AF_CUDA(cudaFuncSetAttribute((attn_cross_tc_kernel<D, NKT>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  int per_sm = 512 / p.tmem_cols;                           // TMEM columns bound the residency
+  const int by_smem = (227 * 1024) / (smem + 1024);
+  if (per_sm > by_smem) per_sm = by_smem;
+  if (per_sm > ((D <= 64) ? 4 : 2)) per_sm = (D <= 64) ? 4 : 2;
+  if (per_sm < 1) per_sm = 1;
+  int grid = 148 * per_sm;
+  if (grid > p.n_units) grid = p.n_units;
+  attn_cross_tc_kernel<D, NKT><<<grid, TA_THREADS, smem, stream>>>(tQ, tK, tV, p);
+  AF_CUDA(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
 // Unmasked attention on the tensor-core path.  Returns -1 when the problem is not eligible (caller falls through to
 // the warp-MMA kernel, which handles masks, causal multi-KV and tiny shapes), 0 on success, > 0 on error.
 // q/k/v element strides: batch (sb), head (sh), token (sn).  Reference layout [B, L, H*d]: sh = d, sn = H*d.
@@ -589,6 +855,17 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, co
   // drow_* = elements that exist in a row: d, or the zero-padded width of a head-major buffer
   if (drow_q < d) drow_q = d;
   if (drow_kv < d) drow_kv = d;
+  static int tc_cross = -1;
+  if (tc_cross < 0) {
+    const char* e = getenv("ADAFACE_CROSS_TC");       // 1 (default): persistent short-context kernel for Lk <= 128
+    tc_cross = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (tc_cross && Lk <= 128 && Lq >= 512 && (d == 40 || d == 80)) {
+#define AF_TC_ARGS q, q_sb, q_sh, q_sn, k, k_sb, k_sh, k_sn, v, v_sb, v_sh, v_sn, o, o_sb, o_sn, B, H, Lq, Lk, drow_q, drow_kv, scale, lse, stream
+    if (d == 40) return Lk <= 80 ? launch_tc_cross<40, 80>(AF_TC_ARGS) : launch_tc_cross<40, 128>(AF_TC_ARGS);
+    return Lk <= 80 ? launch_tc_cross<80, 80>(AF_TC_ARGS) : launch_tc_cross<80, 128>(AF_TC_ARGS);
+#undef AF_TC_ARGS
+  }
   CUtensorMap tQ, tK, tV;
   if (make_tmap_bf16_heads(&tQ, q, (uint64_t)drow_q, (uint64_t)H, (uint64_t)Lq, (uint64_t)B, (uint64_t)q_sh, (uint64_t)q_sn, (uint64_t)q_sb, TA_BM)) return 3;
   if (make_tmap_bf16_heads(&tK, k, (uint64_t)drow_kv, (uint64_t)H, (uint64_t)Lk, (uint64_t)B, (uint64_t)k_sh, (uint64_t)k_sn, (uint64_t)k_sb, TA_BN)) return 3;
