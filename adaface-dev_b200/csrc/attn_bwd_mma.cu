@@ -337,7 +337,6 @@ static int launch_bwd(const BwdParams& p, cudaStream_t stream) {
     AF_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q));
     configured = true;
   }
-  attn_bwd_delta_kernel<D><<<dim3((p.Lq + 7) / 8, p.H, p.B), 256, 0, stream>>>(p);
   const dim3 gkv((p.Lk + 63) / 64, p.H, p.B), gq((p.Lq + 63) / 64, p.H, p.B);
   if (D <= 80) {
     attn_bwd_dkdv_kernel<D, 0><<<gkv, ATT_THREADS, smem_kv, stream>>>(p);
@@ -349,9 +348,21 @@ static int launch_bwd(const BwdParams& p, cudaStream_t stream) {
   }
   attn_bwd_dq_kernel<D><<<gq, ATT_THREADS, smem_q, stream>>>(p);
   AF_CUDA(cudaGetLastError());
-  g_launch_count += 2;
+  g_launch_count += 1;
   return 0;
 }
+
+template <int D>
+static int launch_delta(const BwdParams& p, cudaStream_t stream) {
+  attn_bwd_delta_kernel<D><<<dim3((p.Lq + 7) / 8, p.H, p.B), 256, 0, stream>>>(p);
+  AF_CUDA(cudaGetLastError());
+  g_launch_count += 1;
+  return 0;
+}
+
+int attn_bwd_tcgen05(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*,
+                     int64_t, int64_t, const float*, const float*, void*, int64_t, int64_t, void*, int64_t, int64_t, void*, int64_t,
+                     int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, float, cudaStream_t);
 
 int attn_bwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn, const void* v, int64_t v_sb,
              int64_t v_sn, const void* o, int64_t o_sb, int64_t o_sn, const void* dout, int64_t do_sb, int64_t do_sn,
@@ -375,14 +386,29 @@ int attn_bwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k
   p.causal_mult = causal_mult;
   p.scale = scale;
   p.scale_log2 = scale * LOG2E;
+  int rc;
+  switch (d) {
+    case 40: rc = launch_delta<40>(p, stream); break;
+    case 64: rc = launch_delta<64>(p, stream); break;
+    case 80: rc = launch_delta<80>(p, stream); break;
+    case 160: rc = launch_delta<160>(p, stream); break;
+    default:
+      set_error("attn_bwd: unsupported head dim %lld (supported: 40, 64, 80, 160)", (long long)d);
+      return 1;
+  }
+  if (rc) return rc;
+  if (!key_mask && causal_mult == 0) {
+    // unmasked attention: tcgen05 / TMEM kernels (attn_bwd_tcgen05.cu)
+    rc = attn_bwd_tcgen05(q, q_sb, q_sn, k, k_sb, k_sn, v, v_sb, v_sn, dout, do_sb, do_sn, lse, delta, dq, dq_sb, dq_sn, dk, dk_sb,
+                          dk_sn, dv, dv_sb, dv_sn, B, H, Lq, Lk, d, scale, stream);
+    if (rc >= 0) return rc;
+  }
   switch (d) {
     case 40: return launch_bwd<40>(p, stream);
     case 64: return launch_bwd<64>(p, stream);
     case 80: return launch_bwd<80>(p, stream);
-    case 160: return launch_bwd<160>(p, stream);
   }
-  set_error("attn_bwd: unsupported head dim %lld (supported: 40, 64, 80, 160)", (long long)d);
-  return 1;
+  return launch_bwd<160>(p, stream);
 }
 
 }  // namespace adaface

@@ -40,7 +40,8 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);   // 64:8 128:6 160:5 192:5 256:4
   static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;   // two accumulator buffers
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STORE_STAGE_BYTES = 8 * 2048;   // one 32-row x 64-byte transposition slab per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
@@ -49,9 +50,25 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + er
 // `c0` = first tile-local column of the chunk, `g` = the matching gate values when ACT == GEGLU.
 // FULL = the whole chunk lies inside N: no per-element bounds predicates (the common case; the epilogue warps run
 // one per scheduler slot with little ILP, so every instruction removed here is ~4 cycles of the critical path).
+// bf16 stores of a FULL chunk go through a warp-private shared-memory slab: a thread owns one ROW of the accumulator
+// (TMEM lane), so storing straight from registers makes every warp-level store touch 32 rows x 16 bytes = 32
+// half-filled sectors (ncu: 32 sectors / request, 2x the output bytes in L1 sector writes, l1tex the busiest unit).
+// After the XOR-swizzled transposition each store instruction writes 8 rows x 64 contiguous bytes = 16 full sectors.
+__device__ __forceinline__ void stage_row64(uint8_t* slab, int lane, const float (&f)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(slab + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+        make_uint4(pack_bf16(f[j * 8 + 0], f[j * 8 + 1]), pack_bf16(f[j * 8 + 2], f[j * 8 + 3]), pack_bf16(f[j * 8 + 4], f[j * 8 + 5]),
+                   pack_bf16(f[j * 8 + 6], f[j * 8 + 7]));
+  __syncwarp();
+}
+__device__ __forceinline__ uint4 unstage_piece(const uint8_t* slab, int r, int pc) {
+  return *reinterpret_cast<const uint4*>(slab + r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
+}
+
 template <int BN, bool FULL>
 __device__ __forceinline__ void epilogue_chunk32(const GemmEpilogue& ep, const uint32_t (&v)[32], const uint32_t (&g)[32], int row,
-                                                 bool row_ok, int n_blk, int c0) {
+                                                 bool row_ok, int n_blk, int c0, uint8_t* slab, int lane) {
   const int n0 = n_blk * BN;
   const bool geglu = ep.act == ADAFACE_ACT_GEGLU;
   const int col0 = n0 + c0;
@@ -86,8 +103,10 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmEpilogue& ep, const u
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.f + __expf(-1.702f * f[j]));
   }
-  if (!row_ok || (ep.dbg & 1)) return;
-  if (ep.residual) {
+  if (ep.dbg & 1) return;
+  const bool staged = FULL && !ep.y_f32 && (ep.hs_d > 0 || ((ep.ldy & 7) == 0 && (out_col0 & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.y) & 15) == 0));   // warp-uniform
+  if (!row_ok && !staged) return;
+  if (ep.residual && row_ok) {
     if (ep.res_f32) {
       const float* r = reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + out_col0;
 #pragma unroll
@@ -110,6 +129,34 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmEpilogue& ep, const u
       for (int j = 0; j < 32; ++j)
         if (FULL || out_col0 + j < out_n) y[j] = f[j];
     }
+  } else if (staged) {
+    stage_row64(slab, lane, f);
+    const int row_base = row - lane;                 // first row of this warp's 32-row slice
+    const int pc = lane & 3;                         // 16-byte piece = 8 output columns
+    const int col = out_col0 + pc * 8;
+    int which = 0, hh = 0, dd = 0;
+    if (ep.hs_d > 0) {                               // 8-column groups never straddle a head (hs_d % 8 == 0)
+      which = col / ep.hs_C;
+      const int rem = col - which * ep.hs_C;
+      hh = rem / ep.hs_d;
+      dd = rem - hh * ep.hs_d;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = i * 8 + (lane >> 2);
+      const int grow = row_base + r;
+      if (grow < ep.M) {
+        bf16* dst;
+        if (ep.hs_d > 0) {
+          const int bb = grow / ep.hs_rows, nn = grow - bb * ep.hs_rows;
+          dst = reinterpret_cast<bf16*>(ep.y) + ((((long long)which * ep.hs_B + bb) * ep.hs_H + hh) * ep.hs_rows + nn) * ep.hs_dpad + dd;
+        } else {
+          dst = reinterpret_cast<bf16*>(ep.y) + (long long)grow * ep.ldy + col;
+        }
+        *reinterpret_cast<uint4*>(dst) = unstage_piece(slab, r, pc);
+      }
+    }
+    __syncwarp();                                    // the slab is rewritten by this warp's next chunk
   } else if (ep.hs_d > 0) {
     const int bb = row / ep.hs_rows, nn = row - bb * ep.hs_rows;
 #pragma unroll
@@ -161,7 +208,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* store_stage = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(store_stage + Cfg::STORE_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full = empty_bar + STAGES;     // [2]
   uint64_t* acc_empty = acc_full + 2;          // [2]
@@ -284,8 +332,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
             arrived = true;
           }
           const bool full = geglu || (n_blk * BN + c0 + 32 <= ep.N);
-          if (full) epilogue_chunk32<BN, true>(ep, v, g, row, row_ok, n_blk, c0);
-          else epilogue_chunk32<BN, false>(ep, v, g, row, row_ok, n_blk, c0);
+          if (full) epilogue_chunk32<BN, true>(ep, v, g, row, row_ok, n_blk, c0, store_stage + warp * 2048, lane);
+          else epilogue_chunk32<BN, false>(ep, v, g, row, row_ok, n_blk, c0, store_stage + warp * 2048, lane);
         }
       }
     }
