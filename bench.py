@@ -89,6 +89,42 @@ def run_cpu(torch, steps, warmup, min_seconds=0.0):
     return fl / dt / 1e12, dt, fl, n
 
 
+def run_reference_ldm(torch, steps, warmup):
+    """The UNMODIFIED reference operator from baseline/_ref (pip-installed copy of /root/reference):
+    ``ldm.modules.attention.CrossAttention`` (ldm/modules/attention.py:146-222), the LDM surface of the same attention
+    operator, on the same bounded sample as the port.  Returns None when baseline/_ref is absent or not importable."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "ldm")):
+        return None
+    sys.path.insert(0, ref)
+    try:
+        from ldm.modules.attention import CrossAttention
+    except Exception:
+        return None
+    finally:
+        sys.path.remove(ref)
+    torch.manual_seed(0)
+    mods, xs = [], []
+    for _, N, C, _ in LEVELS:
+        mods.append((CrossAttention(C, None, HEADS, C // HEADS).eval(), CrossAttention(C, CTX_DIM, HEADS, C // HEADS).eval()))
+        xs.append(torch.randn(1, N, C))
+    ctx = torch.randn(1, S_CTX, CTX_DIM)
+    fl = flops_per_sample([(n, N, C, 1) for n, N, C, _ in LEVELS])
+
+    def step():
+        for (a1, a2), x in zip(mods, xs):
+            a2(a1(x), context=ctx)
+    with torch.no_grad():
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = (time.perf_counter() - t0) / steps
+    return {"value": fl / dt / 1e12, "unit": UNIT, "ms_per_step": dt * 1e3, "kind": "reference",
+            "what": "baseline/_ref ldm.modules.attention.CrossAttention, verbatim, same sample (einsum path: [B*8,N,N] scores)"}
+
+
 def main_reference(args):
     """--impl reference: the reference's CPU implementation of the path (the oracle port -- /root/reference does
     not exist on the GPU box and has no compiled code on this path), all host threads, bounded sample per step."""
@@ -104,6 +140,12 @@ def main_reference(args):
             "config": {"workload": "sd15_attn_stack_512", "sample": sample, "flops_per_step": fl},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    # The headline CPU arm is the oracle's restatement of the diffusers processor (F.scaled_dot_product_attention: the
+    # FASTER of the reference's two attention paths, so the conservative baseline).  When the pip-installed reference
+    # is present its own LDM module is timed verbatim as well and reported next to it.
+    ldm = run_reference_ldm(torch, max(1, min(args.steps, 3)), 1)
+    if ldm is not None:
+        line["reference_verbatim_ldm"] = ldm
     print(json.dumps(line))
 
 
