@@ -29,6 +29,8 @@ SIGNATURES = {
     "adaface_capture_chan_major": [_p, _i32, _i64, _i64, _i64, _i64, _i64, _f32, _p, _p],
     "adaface_layernorm_fwd": [_p, _i32, _i64, _p, _p, _p, _i32, _i64, _i64, _i64, _f32, _p],
     "adaface_sbg_head_fwd": [_p, _p, _p, _p, _c.POINTER(_f32), _i32, _i64, _p, _p, _p, _i64, _i64, _i64, _f32, _p],
+    "adaface_groupnorm_tokens_fwd": [_p, _i32, _p, _p, _i64, _i64, _i64, _i64, _f32, _p, _p, _p, _p],
+    "adaface_tokens_to_nchw_add": [_p, _p, _i32, _p, _i64, _i64, _i64, _p],
     # ---- backward (ABI v2)
     "adaface_attn_bwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _p,
                          _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _i32, _f32, _p],

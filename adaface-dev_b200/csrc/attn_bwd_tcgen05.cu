@@ -53,20 +53,23 @@ struct TbParams {
 };
 
 // ------------------------------------------------------------------------------------------------ dq pass
-template <int D>
-__global__ void __launch_bounds__(TB_THREADS, 2)
+// BN = keys per streamed tile: 32 keeps S (32) + dP (32) + dQ (48) within 128 TMEM columns => 4 CTAs / SM for d = 40
+// (16 softmax warps per SM instead of 8: the pass is bound by exp2 latency, not by the tensor pipe).
+template <int D, int BN>
+__global__ void __launch_bounds__(TB_THREADS, (D <= 64 && BN <= 32) ? 4 : 2)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const TbParams p) {
   using Cfg = TbCfg<D>;
   constexpr int NA = Cfg::NA, KT = Cfg::KT, DO = Cfg::DO, ST = TB_ST;
-  constexpr int TMEM_COLS = (Cfg::TMEM_ACC + DO <= 256) ? 256 : 512;
+  constexpr int SMALL_ATOM = BN * 128, SMALL_BYTES = NA * SMALL_ATOM, TMEM_ACC = 2 * BN;
+  constexpr int TMEM_COLS = (TMEM_ACC + DO <= 128) ? 128 : (TMEM_ACC + DO <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw_bq[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_bq) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                    // [NA][128][128 B]
   uint8_t* sdO = sQ + Cfg::BIG_BYTES;
   uint8_t* sK = sdO + Cfg::BIG_BYTES;                    // [ST][NA][64][128 B]
-  uint8_t* sV = sK + ST * Cfg::SMALL_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * Cfg::SMALL_BYTES);
+  uint8_t* sV = sK + ST * SMALL_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * SMALL_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;                          // [ST]
   uint64_t* kv_empty = kv_full + ST;                     // [ST]
@@ -77,7 +80,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TB_BM, h = blockIdx.y, b = blockIdx.z;
-  const int n_tiles = (p.Lk + TB_BN - 1) / TB_BN;
+  const int n_tiles = (p.Lk + BN - 1) / BN;
 
   if (warp == kTbTma && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -112,17 +115,17 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j % ST;
         mbar_wait(&kv_empty[s], ((j / ST) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * Cfg::SMALL_BYTES);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * SMALL_BYTES);
 #pragma unroll
         for (int a = 0; a < NA; ++a) {
-          tma_load_4d(sK + s * Cfg::SMALL_BYTES + a * Cfg::SMALL_ATOM, &tmK, &kv_full[s], a * 64, h, j * TB_BN, b);
-          tma_load_4d(sV + s * Cfg::SMALL_BYTES + a * Cfg::SMALL_ATOM, &tmV, &kv_full[s], a * 64, h, j * TB_BN, b);
+          tma_load_4d(sK + s * SMALL_BYTES + a * SMALL_ATOM, &tmK, &kv_full[s], a * 64, h, j * BN, b);
+          tma_load_4d(sV + s * SMALL_BYTES + a * SMALL_ATOM, &tmV, &kv_full[s], a * 64, h, j * BN, b);
         }
       }
     }
   } else if (warp == kTbMma) {
     if (elect_one()) {
-      constexpr uint32_t idesc_s = make_idesc_bf16_f32(TB_BM, TB_BN, false);
+      constexpr uint32_t idesc_s = make_idesc_bf16_f32(TB_BM, BN, false);
       constexpr uint32_t idesc_acc = make_idesc_bf16_f32(TB_BM, DO, true);
       const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV);
       mbar_wait(q_full, 0);
@@ -134,23 +137,23 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         // of tile j-1 (which read dS_{j-1}) was issued before them.
 #pragma unroll
         for (int kk = 0; kk < KT; ++kk) {
-          const uint32_t koff = (kk >> 2) * Cfg::SMALL_ATOM + (kk & 3) * 32, qoff = (kk >> 2) * (TB_BM * 128) + (kk & 3) * 32;
-          umma_bf16(tmem_base, make_smem_desc_sw128(aQ + qoff), make_smem_desc_sw128(aK + s * Cfg::SMALL_BYTES + koff), idesc_s,
+          const uint32_t koff = (kk >> 2) * SMALL_ATOM + (kk & 3) * 32, qoff = (kk >> 2) * (TB_BM * 128) + (kk & 3) * 32;
+          umma_bf16(tmem_base, make_smem_desc_sw128(aQ + qoff), make_smem_desc_sw128(aK + s * SMALL_BYTES + koff), idesc_s,
                     kk > 0 ? 1u : 0u);
         }
 #pragma unroll
         for (int kk = 0; kk < KT; ++kk) {
-          const uint32_t koff = (kk >> 2) * Cfg::SMALL_ATOM + (kk & 3) * 32, qoff = (kk >> 2) * (TB_BM * 128) + (kk & 3) * 32;
-          umma_bf16(tmem_base + TB_BN, make_smem_desc_sw128(adO + qoff), make_smem_desc_sw128(aV + s * Cfg::SMALL_BYTES + koff),
+          const uint32_t koff = (kk >> 2) * SMALL_ATOM + (kk & 3) * 32, qoff = (kk >> 2) * (TB_BM * 128) + (kk & 3) * 32;
+          umma_bf16(tmem_base + BN, make_smem_desc_sw128(adO + qoff), make_smem_desc_sw128(aV + s * SMALL_BYTES + koff),
                     idesc_s, kk > 0 ? 1u : 0u);
         }
         umma_commit(s_full);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < TB_BN / 16; ++k) {
-          const uint64_t db = make_smem_desc_sw128_mn(aK + s * Cfg::SMALL_BYTES + k * 2048, Cfg::SMALL_ATOM);
-          umma_bf16_ts(tmem_base + (uint32_t)Cfg::TMEM_ACC, tmem_base + (uint32_t)(k * 8), db, idesc_acc, (j | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < BN / 16; ++k) {
+          const uint64_t db = make_smem_desc_sw128_mn(aK + s * SMALL_BYTES + k * 2048, SMALL_ATOM);
+          umma_bf16_ts(tmem_base + (uint32_t)TMEM_ACC, tmem_base + (uint32_t)(k * 8), db, idesc_acc, (j | k) != 0 ? 1u : 0u);
         }
         umma_commit(&kv_empty[s]);
       }
@@ -169,12 +172,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const int valid = p.Lk - j * TB_BN;
+      const int valid = p.Lk - j * BN;
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
+      for (int hf = 0; hf < BN / 32; ++hf) {
         uint32_t sv[32], dv[32];
         tmem_ld_32x32b_x32_wait(t_lane + (uint32_t)(hf * 32), sv);
-        tmem_ld_32x32b_x32_wait(t_lane + (uint32_t)(TB_BN + hf * 32), dv);
+        tmem_ld_32x32b_x32_wait(t_lane + (uint32_t)(BN + hf * 32), dv);
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -183,7 +186,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           float2 g = __fadd2_rn(make_float2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1])), nd2);
           g = __fmul2_rn(__fmul2_rn(pr, g), ss2);
           uint32_t gx = __float_as_uint(g.x), gy = __float_as_uint(g.y);
-          if (valid < TB_BN) {
+          if (valid < BN) {
             if (hf * 32 + 2 * i >= valid) gx = 0;
             if (hf * 32 + 2 * i + 1 >= valid) gy = 0;
           }
@@ -201,7 +204,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
     for (int c = 0; c < DO / 16; ++c) {
       uint32_t v[16];
-      tmem_ld_32x32b_x16(t_lane + (uint32_t)(Cfg::TMEM_ACC + c * 16), v);
+      tmem_ld_32x32b_x16(t_lane + (uint32_t)(TMEM_ACC + c * 16), v);
       tmem_ld_wait();
       if (grow < p.Lq) {
 #pragma unroll
@@ -418,20 +421,22 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 }
 
 template <int D>
-static int launch_bwd_tc(const CUtensorMap& tQb, const CUtensorMap& tKs, const CUtensorMap& tVs, const CUtensorMap& tdOb,
+static int launch_bwd_tc(const CUtensorMap& tQb, const CUtensorMap& tKs32, const CUtensorMap& tVs32, const CUtensorMap& tdOb,
                          const CUtensorMap& tQs, const CUtensorMap& tKb, const CUtensorMap& tVb, const CUtensorMap& tdOs,
                          const TbParams& p, int B, int H, cudaStream_t stream) {
   using Cfg = TbCfg<D>;
   constexpr int smem = 2 * Cfg::BIG_BYTES + 2 * TB_ST * Cfg::SMALL_BYTES + 2 * 2 * TB_BN * 4 + 1024 + 128;
   static_assert(smem <= 227 * 1024, "tcgen05 attention backward: shared memory exceeds the SM");
+  constexpr int DQ_BN = 64;      // 32 (=> 128 TMEM columns, 4 CTAs / SM at d = 40) measured no faster: 1280 vs 1297 us at B = 8, slower at B = 1
+  constexpr int smem_dq = 2 * Cfg::BIG_BYTES + 2 * TB_ST * Cfg::NA * DQ_BN * 128 + 1024 + 128;
   static bool configured = false;
   if (!configured) {
-    AF_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AF_CUDA(cudaFuncSetAttribute((attn_bwd_dq_tc_kernel<D, DQ_BN>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq));
     AF_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   attn_bwd_dkdv_tc_kernel<D><<<dim3((p.Lk + TB_BM - 1) / TB_BM, H, B), TB_THREADS, smem, stream>>>(tQs, tKb, tVb, tdOs, p);
-  attn_bwd_dq_tc_kernel<D><<<dim3((p.Lq + TB_BM - 1) / TB_BM, H, B), TB_THREADS, smem, stream>>>(tQb, tKs, tVs, tdOb, p);
+  attn_bwd_dq_tc_kernel<D, DQ_BN><<<dim3((p.Lq + TB_BM - 1) / TB_BM, H, B), TB_THREADS, smem_dq, stream>>>(tQb, tKs32, tVs32, tdOb, p);
   AF_CUDA(cudaGetLastError());
   g_launch_count += 2;
   return 0;
@@ -455,8 +460,9 @@ int attn_bwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sn, const void* k, i
   const uint64_t ud = (uint64_t)d, uH = (uint64_t)H, uB = (uint64_t)B;
   if (make_tmap_bf16_heads(&tQb, q, ud, uH, (uint64_t)Lq, uB, ud, (uint64_t)q_sn, (uint64_t)q_sb, TB_BM)) return 3;
   if (make_tmap_bf16_heads(&tdOb, dout, ud, uH, (uint64_t)Lq, uB, ud, (uint64_t)do_sn, (uint64_t)do_sb, TB_BM)) return 3;
-  if (make_tmap_bf16_heads(&tKs, k, ud, uH, (uint64_t)Lk, uB, ud, (uint64_t)k_sn, (uint64_t)k_sb, TB_BN)) return 3;
-  if (make_tmap_bf16_heads(&tVs, v, ud, uH, (uint64_t)Lk, uB, ud, (uint64_t)v_sn, (uint64_t)v_sb, TB_BN)) return 3;
+  const uint32_t dq_bn = 64;                     // streamed key tile of the dq pass (launch_bwd_tc::DQ_BN)
+  if (make_tmap_bf16_heads(&tKs, k, ud, uH, (uint64_t)Lk, uB, ud, (uint64_t)k_sn, (uint64_t)k_sb, dq_bn)) return 3;
+  if (make_tmap_bf16_heads(&tVs, v, ud, uH, (uint64_t)Lk, uB, ud, (uint64_t)v_sn, (uint64_t)v_sb, dq_bn)) return 3;
   if (make_tmap_bf16_heads(&tQs, q, ud, uH, (uint64_t)Lq, uB, ud, (uint64_t)q_sn, (uint64_t)q_sb, TB_BN)) return 3;
   if (make_tmap_bf16_heads(&tdOs, dout, ud, uH, (uint64_t)Lq, uB, ud, (uint64_t)do_sn, (uint64_t)do_sb, TB_BN)) return 3;
   if (make_tmap_bf16_heads(&tKb, k, ud, uH, (uint64_t)Lk, uB, ud, (uint64_t)k_sn, (uint64_t)k_sb, TB_BM)) return 3;

@@ -53,8 +53,6 @@ struct TaParams {
   long long o_sb, o_sn;
   int Lq, Lk;
   float scale_log2;
-  int phase_ns;            // experiment: delay of every second CTA per SM (0 = off)
-  unsigned* sm_counter;    // [256] per-SM arrival counters (experiment only)
   float* lse;              // optional [B, H, Lq]: log2-domain log-sum-exp of each row, kept for the backward pass
 };
 
@@ -200,16 +198,6 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const int row = qd * 32 + lane;                // query row inside the tile
     const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16);
     float m_ref = -INFINITY, l_run = 0.f;
-    if (p.phase_ns > 0) {
-      unsigned smid, par = 0;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      if (lane == 0 && qd == 0) par = atomicAdd(p.sm_counter + smid, 1u);
-      par = __shfl_sync(0xffffffffu, par, 0);
-      __shared__ unsigned s_par;
-      if (qd == 0 && lane == 0) s_par = par;
-      asm volatile("bar.sync 1, 128;");
-      if (s_par & 1) __nanosleep(p.phase_ns);
-    }
     // (A register prefetch of the next tile's scores was measured 1.5x SLOWER: tcgen05.ld is a ~12-cycle operation,
     // so there is no latency to hide and the second 64-register buffer only costs spills.)
     auto tile = [&](const int j, uint32_t (&v)[TA_BN]) {
@@ -394,12 +382,11 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j % ST;
         mbar_wait(&kv_empty[s], ((j / ST) & 1) ^ 1);
-        const bool skip_v = p.phase_ns == -7;   // EXPERIMENT: halve the L2->SM traffic (results are wrong)
-        mbar_arrive_expect_tx(&kv_full[s], skip_v ? Cfg::K_BYTES : Cfg::K_BYTES + Cfg::V_BYTES);
+        mbar_arrive_expect_tx(&kv_full[s], Cfg::K_BYTES + Cfg::V_BYTES);
 #pragma unroll
         for (int a = 0; a < NA; ++a) {
           tma_load_4d(sK + s * Cfg::K_BYTES + a * Cfg::KV_ATOM, &tmK, &kv_full[s], a * 64, h, j * TA_BN, b);
-          if (!skip_v) tma_load_4d(sV + s * Cfg::V_BYTES + a * Cfg::KV_ATOM, &tmV, &kv_full[s], a * 64, h, j * TA_BN, b);
+          tma_load_4d(sV + s * Cfg::V_BYTES + a * Cfg::KV_ATOM, &tmV, &kv_full[s], a * 64, h, j * TA_BN, b);
         }
       }
     }
@@ -878,18 +865,6 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, co
   p.Lk = (int)Lk;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse;
-  static unsigned* sm_counter = nullptr;
-  static int phase_ns = -1;
-  if (phase_ns < 0) {
-    const char* e = getenv("ADAFACE_PHASE_NS");
-    phase_ns = e ? atoi(e) : 0;
-    if (phase_ns != 0) {
-      cudaMalloc(&sm_counter, 256 * sizeof(unsigned));
-      cudaMemset(sm_counter, 0, 256 * sizeof(unsigned));
-    }
-  }
-  p.phase_ns = phase_ns;
-  p.sm_counter = sm_counter;
   static int emu = -1, psmem = 0, mc = 1;
   if (emu < 0) {
     const char* m = getenv("ADAFACE_ATTN_MC");      // 1 (default): many-small-CTAs kernel for d = 40 / 80

@@ -114,6 +114,9 @@ int layernorm_fwd(const void*, int, int64_t, const float*, const float*, void*, 
                   cudaStream_t);
 int sbg_head_fwd(const float*, const float*, const float*, const float*, const float*, int, int64_t, const float*,
                  const float*, float*, int64_t, int64_t, int64_t, float, cudaStream_t);
+int groupnorm_tokens_fwd(const void*, int, const float*, const float*, int64_t, int64_t, int64_t, int64_t, float, float*, float*,
+                         void*, cudaStream_t);
+int tokens_to_nchw_add(const void*, const void*, int, void*, int64_t, int64_t, int64_t, cudaStream_t);
 
 }  // namespace adaface
 
@@ -188,6 +191,16 @@ int adaface_sbg_head_fwd(const float* h0, const float* h1, const float* h2, cons
                          int n_layers, int64_t ldh, const float* w, const float* b, float* out, int64_t ldo,
                          int64_t M, int64_t C, float eps, void* stream) {
   return sbg_head_fwd(h0, h1, h2, h3, wl, n_layers, ldh, w, b, out, ldo, M, C, eps, (cudaStream_t)stream);
+}
+
+int adaface_groupnorm_tokens_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, int64_t B, int64_t C,
+                                 int64_t HW, int64_t groups, float eps, float* a_ws, float* s_ws, void* y, void* stream) {
+  return groupnorm_tokens_fwd(x, x_dtype, gamma, beta, B, C, HW, groups, eps, a_ws, s_ws, y, (cudaStream_t)stream);
+}
+
+int adaface_tokens_to_nchw_add(const void* t, const void* x_in, int x_dtype, void* out, int64_t B, int64_t C, int64_t HW,
+                               void* stream) {
+  return tokens_to_nchw_add(t, x_in, x_dtype, out, B, C, HW, (cudaStream_t)stream);
 }
 
 int adaface_attn_bwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn, const void* v,

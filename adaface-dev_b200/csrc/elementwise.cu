@@ -226,4 +226,120 @@ int capture_chan_major(const void* src, int src_dtype, int64_t s_sb, int64_t s_s
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// SpatialTransformer entry / exit (ldm/modules/attention.py:287-304):
+//   groupnorm_stats      per (batch, group) mean / rstd of x [B, C, HW], folded with the affine parameters into
+//                        a[b, c] = rstd * gamma[c],  s[b, c] = beta[c] - mean * rstd * gamma[c]
+//   groupnorm_tokens     y[b, hw, c] = x[b, c, hw] * a[b, c] + s[b, c]   ('b c h w -> b (h w) c' fused with the norm; bf16)
+//   tokens_to_nchw_add   out[b, c, hw] = t[b, hw, c] + x_in[b, c, hw]    ('b (h w) c -> b c h w' fused with the residual)
+template <typename T>
+__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float* __restrict__ a,
+                                                               float* __restrict__ s, int C, int HW, int groups, float eps) {
+  const int g = blockIdx.x, b = blockIdx.y, cpg = C / groups;
+  const T* xg = x + ((long long)b * C + (long long)g * cpg) * HW;
+  const long long n = (long long)cpg * HW;
+  float sum = 0.f, sq = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = ld_as_float(xg + i);
+    sum += v;
+    sq += v * v;
+  }
+  __shared__ float red[2][8];
+  sum = warp_sum(sum);
+  sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = sum;
+    red[1][threadIdx.x >> 5] = sq;
+  }
+  __syncthreads();
+  float ts = 0.f, tq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    ts += red[0][i];
+    tq += red[1][i];
+  }
+  const float mean = ts / n;
+  const float rstd = rsqrtf(fmaxf(tq / n - mean * mean, 0.f) + eps);
+  for (int c = threadIdx.x; c < cpg; c += blockDim.x) {
+    const int ch = g * cpg + c;
+    const float ga = gamma[ch] * rstd;
+    a[(long long)b * C + ch] = ga;
+    s[(long long)b * C + ch] = beta[ch] - mean * ga;
+  }
+}
+
+// MODE 0: y[b, hw, c] = x[b, c, hw] * a[b, c] + s[b, c] (TIn -> bf16);  MODE 1: out[b, c, hw] = t[b, hw, c] + res[b, c, hw]
+template <typename TIn, typename TOut, int MODE>
+__global__ void __launch_bounds__(256) nchw_tokens_kernel(const TIn* __restrict__ src, TOut* __restrict__ dst, const float* __restrict__ a,
+                                                           const float* __restrict__ s, const TOut* __restrict__ res, int I, int J) {
+  // src [B, I, J] -> dst [B, J, I]; MODE 0: I = C, J = HW; MODE 1: I = HW, J = C
+  __shared__ float tile[64][65];
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64, b = blockIdx.z;
+  const TIn* sb = src + (long long)b * I * J;
+  TOut* db = dst + (long long)b * I * J;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+#pragma unroll 4
+  for (int r = ty; r < 64; r += 4) {
+    const int i = i0 + r, j = j0 + tx;
+    float v = 0.f;
+    if (i < I && j < J) {
+      v = ld_as_float(sb + (long long)i * J + j);
+      if (MODE == 0) v = v * a[(long long)b * I + i] + s[(long long)b * I + i];
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int r = ty; r < 64; r += 4) {
+    const int j = j0 + r, i = i0 + tx;
+    if (j < J && i < I) {
+      float v = tile[tx][r];
+      const long long o = (long long)j * I + i;
+      if (MODE == 1) v += ld_as_float(res + (long long)b * I * J + o);
+      if constexpr (sizeof(TOut) == 2) db[o] = __float2bfloat16(v);
+      else db[o] = v;
+    }
+  }
+}
+
+int groupnorm_tokens_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, int64_t B, int64_t C, int64_t HW,
+                         int64_t groups, float eps, float* a_ws, float* s_ws, void* y, cudaStream_t stream) {
+  AF_CHECK(x && gamma && beta && a_ws && s_ws && y, "groupnorm_tokens_fwd: null pointer");
+  AF_CHECK(B > 0 && C > 0 && HW > 0 && groups > 0 && C % groups == 0 && B <= 65535, "groupnorm_tokens_fwd: bad shape");
+  const dim3 gs((unsigned)groups, (unsigned)B), gt((unsigned)((HW + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
+  if (x_dtype == ADAFACE_F32) {
+    groupnorm_stats_kernel<float><<<gs, 256, 0, stream>>>((const float*)x, gamma, beta, a_ws, s_ws, (int)C, (int)HW, (int)groups, eps);
+    nchw_tokens_kernel<float, bf16, 0><<<gt, 256, 0, stream>>>((const float*)x, (bf16*)y, a_ws, s_ws, nullptr, (int)C, (int)HW);
+  } else if (x_dtype == ADAFACE_BF16) {
+    groupnorm_stats_kernel<bf16><<<gs, 256, 0, stream>>>((const bf16*)x, gamma, beta, a_ws, s_ws, (int)C, (int)HW, (int)groups, eps);
+    nchw_tokens_kernel<bf16, bf16, 0><<<gt, 256, 0, stream>>>((const bf16*)x, (bf16*)y, a_ws, s_ws, nullptr, (int)C, (int)HW);
+  } else {
+    set_error("groupnorm_tokens_fwd: bad dtype %d", x_dtype);
+    return 1;
+  }
+  AF_CUDA(cudaGetLastError());
+  g_launch_count += 2;
+  return 0;
+}
+
+int tokens_to_nchw_add(const void* t, const void* x_in, int x_dtype, void* out, int64_t B, int64_t C, int64_t HW,
+                       cudaStream_t stream) {
+  AF_CHECK(t && x_in && out, "tokens_to_nchw_add: null pointer");
+  AF_CHECK(B > 0 && C > 0 && HW > 0 && B <= 65535, "tokens_to_nchw_add: bad shape");
+  const dim3 grid((unsigned)((C + 63) / 64), (unsigned)((HW + 63) / 64), (unsigned)B);
+  if (x_dtype == ADAFACE_F32)
+    nchw_tokens_kernel<bf16, float, 1><<<grid, 256, 0, stream>>>((const bf16*)t, (float*)out, nullptr, nullptr, (const float*)x_in, (int)HW, (int)C);
+  else if (x_dtype == ADAFACE_BF16)
+    nchw_tokens_kernel<bf16, bf16, 1><<<grid, 256, 0, stream>>>((const bf16*)t, (bf16*)out, nullptr, nullptr, (const bf16*)x_in, (int)HW, (int)C);
+  else {
+    set_error("tokens_to_nchw_add: bad dtype %d", x_dtype);
+    return 1;
+  }
+  AF_CUDA(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
 }  // namespace adaface

@@ -13,6 +13,7 @@ import math
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import ops
 from . import autograd as ag
@@ -248,3 +249,52 @@ class BasicTransformerBlock(nn.Module):
             x2 = self.attn2._attend_train(h, context, None, residual=x1).view(B * N, C)
         x3 = self.ff._ff_train(ln(x2, self.norm3), residual=x2).view(B, N, C)
         return x3.to(x.dtype)
+
+
+class SpatialTransformer(nn.Module):
+    """ldm/modules/attention.py:254-304: GroupNorm(32, eps 1e-6) -> 1x1 proj_in -> tokens ->
+    BasicTransformerBlock x depth -> 1x1 proj_out (zero-initialised) -> + input.  Same module / parameter names as the
+    reference (norm, proj_in, transformer_blocks.N, proj_out), so SD-1.5 LDM checkpoints load as they are.
+    The norm is fused with the NCHW -> tokens re-layout, the 1x1 convolutions are projection GEMMs, and the way back to
+    NCHW is fused with the residual.  Forward only this round (the frozen U-Net's GroupNorm backward is not built)."""
+
+    def __init__(self, in_channels, n_heads, d_head, depth=1, dropout=0., context_dim=None):
+        super().__init__()
+        self.in_channels = in_channels
+        inner_dim = n_heads * d_head
+        self.norm = nn.GroupNorm(num_groups=32, num_channels=in_channels, eps=1e-6, affine=True)
+        self.proj_in = nn.Conv2d(in_channels, inner_dim, kernel_size=1, stride=1, padding=0)
+        self.transformer_blocks = nn.ModuleList(
+            [BasicTransformerBlock(inner_dim, n_heads, d_head, dropout=dropout, context_dim=context_dim) for _ in range(depth)])
+        self.proj_out = nn.Conv2d(inner_dim, in_channels, kernel_size=1, stride=1, padding=0)
+        for p in self.proj_out.parameters():          # zero_module (attention.py:280)
+            nn.init.zeros_(p)
+        self._pack_key, self._pack = None, None
+
+    def _weights(self):
+        ps = (self.norm.weight, self.norm.bias, self.proj_in.weight, self.proj_in.bias, self.proj_out.weight, self.proj_out.bias)
+        key = _ver(*ps)
+        if key != self._pack_key:
+            with torch.no_grad():
+                self._pack = {"gn_w": _f32(ps[0]), "gn_b": _f32(ps[1]), "w_in": _bf16(ps[2].flatten(1)), "b_in": _f32(ps[3]),
+                              "w_out": _bf16(ps[4].flatten(1)), "b_out": _f32(ps[5])}
+            self._pack_key = key
+        return self._pack
+
+    def forward(self, x, context=None, mask=None):
+        if not x.is_cuda:
+            raise RuntimeError("adaface_b200 SpatialTransformer runs on CUDA only (no CPU fallback)")
+        if torch.is_grad_enabled() and (x.requires_grad or (context is not None and context.requires_grad)):
+            raise NotImplementedError("SpatialTransformer backward (GroupNorm / 1x1 convolutions of the frozen U-Net) is not built "
+                                      "yet; use BasicTransformerBlock directly for the training path")
+        b, c, h, w = x.shape
+        pk = self._weights()
+        x_in = x.contiguous()
+        t = ops.groupnorm_tokens(x_in, pk["gn_w"], pk["gn_b"], self.norm.num_groups, self.norm.eps)      # :291, 293
+        t = ops.proj(t.view(b * h * w, c), pk["w_in"], bias=pk["b_in"]).view(b, h * w, -1)                # :292
+        for block in self.transformer_blocks:
+            block.attn2.infeat_size = (h, w)                                                             # :296
+            mask2 = F.interpolate(mask, size=(h, w), mode="nearest") if mask is not None else None       # :298
+            t = block(t, context=context, mask=mask2)
+        t = ops.proj(t.reshape(b * h * w, -1), pk["w_out"], bias=pk["b_out"]).view(b, h * w, c)           # :303
+        return ops.tokens_to_nchw_add(t, x_in)                                                            # :301, 304

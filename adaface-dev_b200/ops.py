@@ -261,6 +261,31 @@ def sbg_head(hs, layer_weights, w, b, eps=1e-5):
     return out
 
 
+def groupnorm_tokens(x, gamma, beta, groups=32, eps=1e-6):
+    """GroupNorm over [B, C, h, w] fused with 'b c h w -> b (h w) c': returns bf16 [B, h*w, C] (adaface_groupnorm_tokens_fwd)."""
+    _need(x, "x")
+    if x.dim() != 4 or not x.is_contiguous():
+        raise ValueError("groupnorm_tokens: x must be a contiguous [B, C, h, w] tensor")
+    B, C, h, w = x.shape
+    _need(gamma, "gamma", torch.float32), _need(beta, "beta", torch.float32)
+    ws = torch.empty((2, B, C), device=x.device, dtype=torch.float32)
+    y = torch.empty((B, h * w, C), device=x.device, dtype=torch.bfloat16)
+    _lib.call("adaface_groupnorm_tokens_fwd", _ptr(x), _dt(x), _ptr(gamma), _ptr(beta), B, C, h * w, int(groups), float(eps),
+              _ptr(ws[0]), _ptr(ws[1]), _ptr(y), _stream())
+    return y
+
+
+def tokens_to_nchw_add(t, x_in):
+    """out[b, c, h, w] = t[b, (h w), c] + x_in[b, c, h, w] (adaface_tokens_to_nchw_add); t bf16, out like x_in."""
+    _need(t, "t", torch.bfloat16), _need(x_in, "x_in")
+    B, C, h, w = x_in.shape
+    if tuple(t.shape) != (B, h * w, C) or not t.is_contiguous() or not x_in.is_contiguous():
+        raise ValueError("tokens_to_nchw_add: t must be a contiguous [B, h*w, C] tensor matching x_in [B, C, h, w]")
+    out = torch.empty_like(x_in)
+    _lib.call("adaface_tokens_to_nchw_add", _ptr(t), _ptr(x_in), _dt(x_in), _ptr(out), B, C, h * w, _stream())
+    return out
+
+
 def softmax_scale(d):
     return 1.0 / math.sqrt(d)
 

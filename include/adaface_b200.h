@@ -129,6 +129,17 @@ int adaface_sbg_head_fwd(const float* h0, const float* h1, const float* h2, cons
                          int n_layers, int64_t ldh, const float* w, const float* b, float* out, int64_t ldo,
                          int64_t M, int64_t C, float eps, void* stream);
 
+/* ---- SpatialTransformer entry / exit (ldm/modules/attention.py:287-304) -------------
+ * y[b, hw, c] = GroupNorm(groups, eps)(x)[b, c, hw] * gamma[c] + beta[c]: the norm (attention.py:70-71, 291) fused with
+ * 'b c h w -> b (h w) c' (:293).  x [B, C, HW] contiguous bf16 | fp32, y [B, HW, C] bf16 for the proj_in GEMM (the 1x1
+ * convolution :268-272 is a Linear over channels).  a_ws, s_ws: fp32 [B, C] scratch (folded scale / shift). */
+int adaface_groupnorm_tokens_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, int64_t B, int64_t C,
+                                 int64_t HW, int64_t groups, float eps, float* a_ws, float* s_ws, void* y, void* stream);
+/* out[b, c, hw] = t[b, hw, c] + x_in[b, c, hw]: 'b (h w) c -> b c h w' (:301) fused with the residual (:304);
+ * t bf16 [B, HW, C] (output of the proj_out GEMM), x_in / out [B, C, HW] of x_dtype. */
+int adaface_tokens_to_nchw_add(const void* t, const void* x_in, int x_dtype, void* out, int64_t B, int64_t C, int64_t HW,
+                               void* stream);
+
 /* ---- K5: backward kernels of the stage-2 training step (ddpm.py:1645-1707 back-propagates through the `sc`
  * instance of the U-Net into the LoRA / DoRA adapters, cross_attn_scale_factor and, via the context, SubjBasisGenerator).
  * The reference gets all of this from autograd over eager PyTorch ops; here every gradient is a kernel, recompute

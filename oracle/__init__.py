@@ -27,6 +27,7 @@ from .attn_oracle import (  # noqa: F401
     ldm_cross_attention,
     basic_transformer_block,
     geglu_feed_forward,
+    spatial_transformer,
 )
 from .sbg_oracle import (  # noqa: F401
     clip_mkv_attention,

@@ -202,3 +202,17 @@ def basic_transformer_block(w, x, context=None, mask=None, heads=8):
     x1 = ldm_cross_attention(w["attn1"], ln(x, 1), mask=mask, heads=heads)[0] + x
     x2 = x1 + ldm_cross_attention(w["attn2"], ln(x1, 2), context=context, heads=heads)[0]
     return geglu_feed_forward(w, ln(x2, 3)) + x2
+
+
+def spatial_transformer(w, x, context=None, mask=None, heads=8):
+    """ldm/modules/attention.py:287-304 with depth 1: GroupNorm(32, eps 1e-6) (:70-71) -> 1x1 proj_in -> 'b c h w -> b (h w) c'
+    -> BasicTransformerBlock (mask nearest-resized to the map, :298) -> back to NCHW -> 1x1 proj_out -> + input.
+    ``w``: the block's dict plus gn_w, gn_b, proj_in_w/b [C,C], proj_out_w/b."""
+    B, C, h, wd = x.shape
+    t = F.group_norm(x, 32, w["gn_w"], w["gn_b"], 1e-6)
+    t = F.conv2d(t, w["proj_in_w"][:, :, None, None], w["proj_in_b"])
+    t = t.permute(0, 2, 3, 1).reshape(B, h * wd, -1)
+    m2 = F.interpolate(mask, size=(h, wd), mode="nearest") if mask is not None else None
+    t = basic_transformer_block(w, t, context=context, mask=m2, heads=heads)
+    t = t.reshape(B, h, wd, -1).permute(0, 3, 1, 2)
+    return F.conv2d(t, w["proj_out_w"][:, :, None, None], w["proj_out_b"]) + x

@@ -127,6 +127,39 @@ def build_ldm_case(name):
     return case
 
 
+# SpatialTransformer (ldm/modules/attention.py:254-304): GroupNorm + 1x1 proj_in + block + 1x1 proj_out + residual
+SPATIAL_CASES = {
+    "ldm_spatial": dict(seed=35, B=2, side=16, C=320, S=77, mask=True),
+    "ldm_spatial_d80": dict(seed=36, B=1, side=8, C=640, S=77),
+}
+
+
+def build_spatial_case(name):
+    sp = SPATIAL_CASES[name]
+    rng = np.random.default_rng(sp["seed"])
+    B, side, C = sp["B"], sp["side"], sp["C"]
+    case = dict(spec=sp)
+    case["x"] = normal(rng, (B, C, side, side))
+    case["mask"] = img_mask(rng, B, 64) if sp.get("mask") else None          # full-resolution mask: resized per level (:298)
+    w = {"attn1": attn_weights(rng, C, C), "attn2": attn_weights(rng, C, 768)}
+    for i in (1, 2, 3):
+        w[f"norm{i}_w"] = bf16r(1 + 0.1 * rng.standard_normal(C))
+        w[f"norm{i}_b"] = normal(rng, (C,), 0.05)
+    w["ff_proj_w"] = normal(rng, (8 * C, C), 1 / math.sqrt(C))
+    w["ff_proj_b"] = normal(rng, (8 * C,), 0.02)
+    w["ff_out_w"] = normal(rng, (C, 4 * C), 1 / math.sqrt(4 * C))
+    w["ff_out_b"] = normal(rng, (C,), 0.02)
+    w["gn_w"] = bf16r(1 + 0.1 * rng.standard_normal(C))
+    w["gn_b"] = normal(rng, (C,), 0.05)
+    w["proj_in_w"] = normal(rng, (C, C), 1 / math.sqrt(C))
+    w["proj_in_b"] = normal(rng, (C,), 0.02)
+    w["proj_out_w"] = normal(rng, (C, C), 1 / math.sqrt(C))                  # not zero, so the branch is exercised
+    w["proj_out_b"] = normal(rng, (C,), 0.02)
+    case["w"] = w
+    case["context"] = normal(rng, (B, sp["S"], 768))
+    return case
+
+
 # SubjBasisGenerator / CLIP-shaped encoder (surface 3).  E=768, 12 heads x 64, MLP 3072, 77 positions.
 SBG_CASES = {
     "mkv_m1":   dict(seed=41, BS=2, T=77, mult=1, layers=0),

@@ -194,6 +194,32 @@ def run_ldm_cases():
             save(name, case, outs)
 
 
+def run_spatial_cases():
+    from ldm.modules.attention import SpatialTransformer
+
+    for name in C.SPATIAL_CASES:
+        case = C.build_spatial_case(name)
+        sp, w = case["spec"], case["w"]
+        Cc = sp["C"]
+        m = SpatialTransformer(Cc, 8, Cc // 8, depth=1, context_dim=768).eval()
+        blk = m.transformer_blocks[0]
+        blk.checkpoint = False
+        for at, key in ((blk.attn1, "attn1"), (blk.attn2, "attn2")):
+            aw = w[key]
+            at.to_q.weight.data, at.to_k.weight.data, at.to_v.weight.data = T(aw["to_q"]), T(aw["to_k"]), T(aw["to_v"])
+            at.to_out[0].weight.data, at.to_out[0].bias.data = T(aw["to_out_w"]), T(aw["to_out_b"])
+        for i, ln in enumerate((blk.norm1, blk.norm2, blk.norm3), 1):
+            ln.weight.data, ln.bias.data = T(w[f"norm{i}_w"]), T(w[f"norm{i}_b"])
+        blk.ff.net[0].proj.weight.data, blk.ff.net[0].proj.bias.data = T(w["ff_proj_w"]), T(w["ff_proj_b"])
+        blk.ff.net[2].weight.data, blk.ff.net[2].bias.data = T(w["ff_out_w"]), T(w["ff_out_b"])
+        m.norm.weight.data, m.norm.bias.data = T(w["gn_w"]), T(w["gn_b"])
+        m.proj_in.weight.data, m.proj_in.bias.data = T(w["proj_in_w"])[:, :, None, None].clone(), T(w["proj_in_b"])
+        m.proj_out.weight.data, m.proj_out.bias.data = T(w["proj_out_w"])[:, :, None, None].clone(), T(w["proj_out_b"])
+        with torch.no_grad():
+            out = m(T(case["x"]), context=T(case["context"]), mask=T(case["mask"]))
+        save(name, case, {"out": out})
+
+
 # --------------------------------------------------------------------------------- SBG cases
 class _EncOut:
     """Minimal stand-in for HF BaseModelOutput: tuple-indexable and attribute-addressable."""
@@ -301,6 +327,12 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_grad_enabled(True)
     dalc = install_stubs()
-    run_proc_cases(dalc)
-    run_ldm_cases()
-    run_sbg_cases()
+    only = sys.argv[1] if len(sys.argv) > 1 else ""        # e.g. `make_golden.py spatial`: regenerate one family only
+    if only in ("", "proc"):
+        run_proc_cases(dalc)
+    if only in ("", "ldm"):
+        run_ldm_cases()
+    if only in ("", "spatial"):
+        run_spatial_cases()
+    if only in ("", "sbg"):
+        run_sbg_cases()

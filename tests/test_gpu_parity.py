@@ -205,3 +205,49 @@ def test_arc2face_id_to_img_prompt_vs_oracle():
     ref = oracle.arc2face_id_to_img_prompt(w, ids, prompt_embs=prompt)
     assert tuple(out.shape) == (5, 16, 768) and err(out, ref) < 3e-2
     assert err(ada, oracle.sbg_forward(w, ref, multipliers=[1] * 12)) < 4e-2
+
+
+@pytest.mark.parametrize("name", list(C.SPATIAL_CASES))
+def test_spatial_transformer_vs_reference_golden(name):
+    """SpatialTransformer (GroupNorm fused with the NCHW -> tokens re-layout, 1x1 convolutions as
+    projection GEMMs, tokens -> NCHW fused with the residual) against the reference's own module output."""
+    import adaface_dev_b200 as a
+    from mirror_utils import load_ldm_attn
+    case = C.build_spatial_case(name)
+    sp, w = case["spec"], case["w"]
+    g = gold(name)
+    Cc = sp["C"]
+    m = a.SpatialTransformer(Cc, 8, Cc // 8, depth=1, context_dim=768).cuda()
+    blk = m.transformer_blocks[0]
+    load_ldm_attn(blk.attn1, w["attn1"])
+    load_ldm_attn(blk.attn2, w["attn2"])
+    with torch.no_grad():
+        for i, ln in enumerate((blk.norm1, blk.norm2, blk.norm3), 1):
+            ln.weight.copy_(_T(w[f"norm{i}_w"]))
+            ln.bias.copy_(_T(w[f"norm{i}_b"]))
+        blk.ff.net[0].proj.weight.copy_(_T(w["ff_proj_w"])); blk.ff.net[0].proj.bias.copy_(_T(w["ff_proj_b"]))
+        blk.ff.net[2].weight.copy_(_T(w["ff_out_w"])); blk.ff.net[2].bias.copy_(_T(w["ff_out_b"]))
+        m.norm.weight.copy_(_T(w["gn_w"])); m.norm.bias.copy_(_T(w["gn_b"]))
+        m.proj_in.weight.copy_(_T(w["proj_in_w"])[:, :, None, None]); m.proj_in.bias.copy_(_T(w["proj_in_b"]))
+        m.proj_out.weight.copy_(_T(w["proj_out_w"])[:, :, None, None]); m.proj_out.bias.copy_(_T(w["proj_out_b"]))
+        out = m(_T(case["x"]), context=_T(case["context"], torch.bfloat16), mask=_T(case["mask"]))
+    assert out.dtype == torch.float32 and tuple(out.shape) == g["out"].shape
+    assert err(out, g["out"]) < 3e-2          # one more bf16 GEMM pair around the block than ldm_block (2e-2)
+    # state-dict compatibility with the reference module (same keys)
+    keys = set(m.state_dict())
+    assert {"norm.weight", "proj_in.weight", "proj_out.bias", "transformer_blocks.0.attn1.to_q.weight",
+            "transformer_blocks.0.ff.net.0.proj.weight", "transformer_blocks.0.norm3.bias"} <= keys
+
+
+def test_groupnorm_tokens_kernel():
+    x = torch.randn(3, 640, 24, 24, generator=torch.Generator().manual_seed(2)).cuda()
+    gam = (1 + 0.1 * torch.randn(640, generator=torch.Generator().manual_seed(3))).cuda()
+    bet = (0.1 * torch.randn(640, generator=torch.Generator().manual_seed(4))).cuda()
+    import adaface_dev_b200 as a
+    y = a.ops.groupnorm_tokens(x, gam, bet, 32, 1e-6)
+    ref = torch.nn.functional.group_norm(x, 32, gam, bet, 1e-6).permute(0, 2, 3, 1).reshape(3, 576, 640)
+    assert err(y, ref.cpu()) < 2e-2
+    t = torch.randn(3, 576, 640, generator=torch.Generator().manual_seed(5)).bfloat16().cuda()
+    out = a.ops.tokens_to_nchw_add(t, x)
+    ref2 = t.float().reshape(3, 24, 24, 640).permute(0, 3, 1, 2) + x
+    assert err(out, ref2.cpu()) < 1e-5

@@ -132,3 +132,13 @@ def test_causal_truncation_is_exact_in_the_oracle():
     short = oracle.clip_text_wrapper_forward(w, tok, None)[:, 4:20]
     assert tuple(full.shape) == (3, 16, 768)
     assert (full - short).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("name", list(C.SPATIAL_CASES))
+def test_spatial_transformer_oracle_vs_reference(name):
+    """SpatialTransformer (ldm/modules/attention.py:287-304): GroupNorm + 1x1 proj_in + block + 1x1 proj_out + residual."""
+    case = C.build_spatial_case(name)
+    g = load(name, case)
+    t = C.to_torch({k: v for k, v in case.items() if k != "spec"})
+    out = oracle.spatial_transformer(t["w"], t["x"], context=t["context"], mask=t["mask"])
+    close(out, g["out"], atol=5e-5, what=name)
