@@ -14,8 +14,8 @@ from . import _lib, ops  # noqa: F401
 from .attn_processor import (AttnProcessor_LoRA_Capture, Attention, LoraDoraLinear, ScaleGrad, GradientScaler,  # noqa: F401
                              gen_gradient_scaler, img_mask_to_key_mask)
 from .ldm_attention import CrossAttention, FeedForward, GEGLU, BasicTransformerBlock, SpatialTransformer  # noqa: F401
-from .subj_basis_generator import (SubjBasisGenerator, Arc2FaceID2ImgPrompt, CLIPTextModelWrapper, CLIPAttentionMKV,  # noqa: F401
-                                   CLIPTextConfig, template_ids)
+from .subj_basis_generator import (SubjBasisGenerator, Arc2FaceID2ImgPrompt, FrozenCLIPTextEncoder, CLIPTextModelWrapper,  # noqa: F401
+                                   CLIPAttentionMKV, CLIPTextConfig, template_ids)
 from .build import build  # noqa: F401
 from .graphs import graphed  # noqa: F401
 from . import parallel  # noqa: F401

@@ -281,6 +281,37 @@ class Arc2FaceID2ImgPrompt(nn.Module):
     forward = map_init_id_to_img_prompt_embs
 
 
+class FrozenCLIPTextEncoder(nn.Module):
+    """The SD-1.5 prompt encoder around the path (second half): the patched HF CLIP text model of
+    ``FrozenCLIPEmbedder`` (ldm/modules/encoders/modules.py:180-338) -- token embeddings, optional EmbeddingManager
+    splice of the ada tokens (``embedding_manager(input_ids, inputs_embeds)``, :196-197), position embeddings, 12
+    causal pre-LN layers, weighted sum of the last hidden states (``last_layers_skip_weights`` = [0.5, 0.5], the
+    NovelAI trick, :318-327) and the final LayerNorm.  Frozen; same kernels as SubjBasisGenerator; HF parameter names
+    under ``transformer.text_model.*`` so SD-1.5 text-encoder checkpoints load as they are."""
+
+    def __init__(self, clip_config=None, last_layers_skip_weights=(0.5, 0.5), max_length=77):
+        super().__init__()
+        self.transformer = CLIPTextModelWrapper(clip_config)
+        self.max_length = max_length
+        self.last_layers_skip_weights = None if last_layers_skip_weights is None else list(last_layers_skip_weights)
+        for p in self.parameters():
+            p.requires_grad = False
+
+    def forward(self, input_ids, embedding_manager=None):
+        if input_ids.dim() != 2:
+            raise ValueError("input_ids must be [B, T]")
+        tok = self.transformer(input_ids=input_ids, return_token_embs=True)
+        if embedding_manager is not None:                                            # modules.py:196-197
+            tok = embedding_manager(input_ids, tok)
+        w = None
+        if self.last_layers_skip_weights is not None:
+            sw = self.last_layers_skip_weights
+            if abs(sum(sw) - 1.0) > 1e-6:
+                raise NotImplementedError("last_layers_skip_weights must sum to 1 (the reference uses [0.5, 0.5])")
+            w = torch.tensor(sw, device=tok.device, dtype=torch.float32).view(-1, 1)
+        return self.transformer(input_token_embs=tok, hidden_state_layer_weights=w)[0]    # modules.py:300-330
+
+
 class SubjBasisGenerator(nn.Module):
     """Face-ID image-prompt embeddings [BS,16,768] -> ada prompt embeddings [BS,16(+N_SFX),768]
     (subj_basis_generator.py:564-770, face path; the bg / object branches :733-756 are out of scope)."""

@@ -387,8 +387,10 @@ def main_gpu(args):
         # The step is cut into five independent units (level D, C, B, and the two half-batches of level A -- samples
         # are independent), each its own CUDA graph.  Three streams: H2D of unit i+1 and D2H of unit i-1
         # overlap the kernels of unit i; the small levels go first so that level A's 21 MB input is in flight behind them.
-        half = BATCH // 2
-        units = [(3, slice(0, BATCH)), (2, slice(0, BATCH)), (1, slice(0, BATCH)), (0, slice(0, half)), (0, slice(half, BATCH))]
+        a_split = int(os.environ.get("ADAFACE_BENCH_A_SPLIT", "2"))     # level A in this many batch slices (2: measured best)
+        step_b = BATCH // a_split
+        units = [(3, slice(0, BATCH)), (2, slice(0, BATCH)), (1, slice(0, BATCH))] + \
+                [(0, slice(i * step_b, (i + 1) * step_b)) for i in range(a_split)]
         unit_fns, unit_in, unit_out = [], [], []
         for li, sl in units:
             x_u, c_u = xs[li][sl].contiguous(), ctx[sl].contiguous()
@@ -487,7 +489,7 @@ def main_gpu(args):
             "frac_of_bf16_peak": value / world / pk["bf16_tflops_sustained"],
             "e2e": {"value": world * fl_step / (t_e2e_ms * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e_ms,
-                    "how": "5 units (levels D, C, B, two half-batches of A), one CUDA graph each; H2D / kernels / D2H on three streams"},
+                    "how": f"{3 + a_split} units (levels D, C, B, {a_split} batch slices of A), one CUDA graph each; H2D / kernels / D2H on three streams"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "attn_fwd_tcgen05_mc_kernel<40> (level-A self-attention core, B=8, 4096 tok, 8x40)",

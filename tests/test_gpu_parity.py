@@ -251,3 +251,30 @@ def test_groupnorm_tokens_kernel():
     out = a.ops.tokens_to_nchw_add(t, x)
     ref2 = t.float().reshape(3, 24, 24, 640).permute(0, 3, 1, 2) + x
     assert err(out, ref2.cpu()) < 1e-5
+
+
+def test_sd_text_encoder_with_ada_token_splice_vs_oracle():
+    """SURVEY 8f row 3 (second half): the SD prompt encoder (ldm/modules/encoders/modules.py:180-338) at the full 77
+    positions with an EmbeddingManager-style splice of 16 ada tokens into rows 4:20 and the [0.5, 0.5] last-layers
+    weighting -- the tensor that the cross-attention layers then consume as `encoder_hidden_states`."""
+    import adaface_dev_b200 as a
+    case = C.build_sbg_case("sbg_m1")
+    gen = make_sbg(case["w"], [1] * 12)
+    enc = a.FrozenCLIPTextEncoder(clip_config=a.CLIPTextConfig(num_hidden_layers=1)).cuda()
+    enc.transformer = gen.prompt2token_proj                    # the seeded 12-layer weights of the SBG case
+    ids = torch.tensor([C.TEMPLATE_IDS, C.TEMPLATE_IDS], device="cuda")
+    g = torch.Generator().manual_seed(5)
+    ada = (torch.randn(2, 16, 768, generator=g) * 0.5).bfloat16().float()
+
+    def splice(input_ids, embs):                               # what EmbeddingManager.forward does for the subject tokens
+        embs = embs.clone()
+        embs[:, 4:20] = ada.to(embs.device)
+        return embs
+    with torch.no_grad():
+        out = enc(ids, embedding_manager=splice)
+    t = C.to_torch({k: v for k, v in case.items() if k != "spec"})
+    w = t["w"]
+    tok = w["template_embs"].unsqueeze(0).repeat(2, 1, 1)
+    tok[:, 4:20] = ada
+    ref = oracle.clip_text_wrapper_forward(w, tok, torch.tensor([[0.5], [0.5]]))
+    assert tuple(out.shape) == (2, 77, 768) and err(out, ref) < 3e-2
