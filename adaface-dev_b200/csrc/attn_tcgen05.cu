@@ -531,6 +531,284 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
   }
 }
 
+// =============================================================================================
+// "Quad" variant for d = 40 (level A, half of the whole attention stack's time).  ncu on the many-small-CTAs kernel
+// shows XU (exp2) 63 % + tensor phases that do not overlap: the four co-resident CTAs phase-lock -- they share the XU
+// pipe, so they finish their softmax together, then queue their P.V / Q.K MMAs on the tensor pipe together while the
+// XU idles (measured 830 clk per CTA tile against 512 clk of exp2 work).  This kernel puts the four 128-query tiles
+// into ONE CTA (512 consecutive queries of one (batch, head), 16 softmax warps + TMA + MMA warp, all 512 TMEM columns:
+// S/P 64 + O 48 per tile) so that ONE thread issues every tcgen05.mma in a fixed round-robin:
+//     P.V(g, j), Q.K(g, j+1)  for g = 0..3,  each gated by that tile's own p_full barrier.
+// A tile's next scores are produced right after its P.V while the other three tiles are still in their softmax, so
+// the tensor work of one tile always runs under the exp2 work of the others, and every K/V tile is fetched once per
+// 512 queries instead of once per 128 (4x less TMA / L2 traffic).
+// Wave quantisation: a CTA now lasts 4x longer, so 512 units on 148 SMs would leave 80 SMs idle for a whole CTA
+// lifetime in the 4th round (measured: 387 us, no better than the small-CTA kernel).  The launcher therefore runs
+// floor(units / 148) * 148 four-tile CTAs and covers the remainder with TWO-tile CTAs (G = 2, 256 TMEM columns)
+// in a second launch, which finish in less than half the time of a four-tile CTA.
+constexpr int TQ_G = 4;                       // query tiles per CTA (bulk launch)
+constexpr int TQ_ST = 3;                      // K/V ring: tiles j and j+1 are live at once, j+2 in flight
+
+// EMU = how many of every 8 exp2 pairs go to the FMA-pipe polynomial (exp2_emu2) instead of MUFU.EX2.
+template <int D, int G, int EMU>
+__global__ void __launch_bounds__((4 * G + 2) * 32, 1)
+attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                             const __grid_constant__ CUtensorMap tmV, const TaParams p, const int unit0, const int H) {
+  using Cfg = TaCfg<D>;
+  constexpr int NA = Cfg::NA, KT = Cfg::KT, DO = Cfg::DO, ST = TQ_ST;
+  constexpr int TMEM_G = 128, TMEM_O = TA_BN;                     // per tile: S/P at +0, O at +64
+  static_assert(TMEM_O + DO <= TMEM_G && NA == 1, "quad kernel: head dim must fit 128 TMEM columns per tile");
+  constexpr int kTma = 4 * G, kMma = 4 * G + 1;
+  extern __shared__ uint8_t smem_raw_tq[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tq) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                             // [G][128][128 B]
+  uint8_t* sK = sQ + G * Cfg::Q_BYTES;                            // [ST][64][128 B]
+  uint8_t* sV = sK + ST * Cfg::K_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * Cfg::V_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;                                   // [ST]
+  uint64_t* kv_empty = kv_full + ST;                              // [ST]
+  uint64_t* s_full = kv_empty + ST;                               // [G]
+  uint64_t* p_full = s_full + G;                                  // [G]
+  uint64_t* o_full = p_full + G;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // unit = (batch, head, block of G query tiles), linearised with the query block fastest
+  const int n_qb = (p.Lq + G * TA_BM - 1) / (G * TA_BM);
+  const int unit = unit0 + blockIdx.x;
+  const int qb = unit % n_qb, bh = unit / n_qb;
+  const int h = bh % H, b = bh / H;
+  const int m0 = qb * (G * TA_BM);
+  const int n_tiles = (p.Lk + TA_BN - 1) / TA_BN;
+
+  if (warp == kTma && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int g = 0; g < G; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_full[g], 128);
+    }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  } else if (warp == kMma) {
+    tmem_alloc(tmem_slot, G * TMEM_G);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kTma) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, G * Cfg::Q_BYTES);
+#pragma unroll
+      for (int g = 0; g < G; ++g) tma_load_4d(sQ + g * Cfg::Q_BYTES, &tmQ, q_full, 0, h, m0 + g * TA_BM, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % ST;
+        mbar_wait(&kv_empty[s], ((j / ST) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], Cfg::K_BYTES + Cfg::V_BYTES);
+        tma_load_4d(sK + s * Cfg::K_BYTES, &tmK, &kv_full[s], 0, h, j * TA_BN, b);
+        tma_load_4d(sV + s * Cfg::V_BYTES, &tmV, &kv_full[s], 0, h, j * TA_BN, b);
+      }
+    }
+  } else if (warp == kMma) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16_f32(TA_BM, TA_BN, false);
+      constexpr uint32_t idesc_pv = make_idesc_bf16_f32(TA_BM, DO, true);
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
+      auto issue_qk = [&](int g, int j) {
+        const int s = j % ST;
+#pragma unroll
+        for (int kk = 0; kk < KT; ++kk) {
+          const uint64_t da = make_smem_desc_sw128(aQ + g * Cfg::Q_BYTES + (kk & 3) * 32);
+          const uint64_t db = make_smem_desc_sw128(aK + s * Cfg::K_BYTES + (kk & 3) * 32);
+          umma_bf16(tmem_base + (uint32_t)(g * TMEM_G), da, db, idesc_qk, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[g]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      // PING-PONG: the tiles form two halves; the second half's first scores are only produced once the first half
+      // has finished its first softmax.  From then on the blocking round-robin below keeps the halves half a period
+      // apart: while one half exponentiates (XU), the other half's P.V / Q.K run on the tensor pipe.
+#pragma unroll
+      for (int g = 0; g < G / 2; ++g) issue_qk(g, 0);
+#pragma unroll
+      for (int g = 0; g < G / 2; ++g) mbar_wait(&p_full[g], 0);
+#pragma unroll
+      for (int g = G / 2; g < G; ++g) issue_qk(g, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % ST;
+        const bool more = j + 1 < n_tiles;
+        if (more) {
+          mbar_wait(&kv_full[(j + 1) % ST], ((j + 1) / ST) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          mbar_wait(&p_full[g], j & 1);                           // tile g's P_j is in TMEM
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < TA_BN / 16; ++k) {
+            const uint64_t db = make_smem_desc_sw128_mn(aV + s * Cfg::V_BYTES + k * 2048, Cfg::KV_ATOM);
+            umma_bf16_ts(tmem_base + (uint32_t)(g * TMEM_G + TMEM_O), tmem_base + (uint32_t)(g * TMEM_G + k * 8), db, idesc_pv,
+                         (j | k) != 0 ? 1u : 0u);
+          }
+          if (more) issue_qk(g, j + 1);                           // overwrites P_j: executes after the P.V above (in order)
+        }
+        umma_commit(&kv_empty[s]);                                // every tile's P.V_j has been issued
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    const int g = warp >> 2, qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(g * TMEM_G);
+    float m_ref = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&s_full[g], j & 1);          // also implies P V_{j-1} of this tile has retired
+      tc_fence_after();
+      const int valid = p.Lk - j * TA_BN;
+      float mxr = -INFINITY;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32_wait(t_lane + (uint32_t)(hf * 32), v);
+        if (valid < TA_BN) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (hf * 32 + i >= valid) v[i] = 0xff800000u;
+        }
+        float m4[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
+#pragma unroll
+        for (int i = 4; i < 32; i += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) m4[u] = fmaxf(m4[u], __uint_as_float(v[i + u]));
+        }
+        mxr = fmaxf(mxr, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+      }
+      const float mx = mxr * p.scale_log2;
+      if (j == 0) {
+        m_ref = (mx == -INFINITY) ? 0.f : mx;
+      } else {
+        const bool need = mx > m_ref + 8.f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = need ? mx : m_ref;
+          const float f = fast_exp2(m_ref - m_new);
+          m_ref = m_new;
+          l_run *= f;
+#pragma unroll
+          for (int c = 0; c < DO / 16; ++c) {
+            uint32_t ov[16];
+            tmem_ld_32x32b_x16(t_lane + (uint32_t)(TMEM_O + c * 16), ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
+            tmem_st_32x32b_x16(t_lane + (uint32_t)(TMEM_O + c * 16), ov);
+          }
+        }
+      }
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
+      float2 ls[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32_wait(t_lane + (uint32_t)(hf * 32), v);
+        if (valid < TA_BN) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (hf * 32 + i >= valid) v[i] = 0xff800000u;
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc2, nm2);
+          const float2 e = ((i & 7) < EMU) ? exp2_emu2(t) : make_float2(fast_exp2(t.x), fast_exp2(t.y));
+          const uint32_t ex = __float_as_uint(e.x) & 0xffff0000u, ey = __float_as_uint(e.y) & 0xffff0000u;
+          ls[i & 1] = __fadd2_rn(ls[i & 1], make_float2(__uint_as_float(ex), __uint_as_float(ey)));
+          pk[i] = __byte_perm(ex, ey, 0x7632);
+        }
+        tmem_st_32x32b_x16(t_lane + (uint32_t)(hf * 16), pk);
+      }
+      tmem_st_wait();
+      l_run += (ls[0].x + ls[0].y) + (ls[1].x + ls[1].y);
+      tc_fence_before();
+      mbar_arrive(&p_full[g]);
+    }
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    const int grow = m0 + g * TA_BM + row;
+    if (p.lse && grow < p.Lq)
+      p.lse[((long long)b * H + h) * p.Lq + grow] = l_run > 0.f ? m_ref + log2f(l_run) : INFINITY;
+    bf16* orow = p.o + (long long)b * p.o_sb + (long long)grow * p.o_sn + h * D;
+#pragma unroll
+    for (int c = 0; c < DO / 16; ++c) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(t_lane + (uint32_t)(TMEM_O + c * 16), v);
+      tmem_ld_wait();
+      if (grow < p.Lq) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (c * 16 + half * 8 < D) {
+            uint4 pk;
+            pk.x = pack_bf16(__uint_as_float(v[half * 8 + 0]) * inv, __uint_as_float(v[half * 8 + 1]) * inv);
+            pk.y = pack_bf16(__uint_as_float(v[half * 8 + 2]) * inv, __uint_as_float(v[half * 8 + 3]) * inv);
+            pk.z = pack_bf16(__uint_as_float(v[half * 8 + 4]) * inv, __uint_as_float(v[half * 8 + 5]) * inv);
+            pk.w = pack_bf16(__uint_as_float(v[half * 8 + 6]) * inv, __uint_as_float(v[half * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + c * 16 + half * 8) = pk;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMma) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, G * TMEM_G);
+  }
+}
+
+// tQ4 / tQ2: Q maps are identical (128-row boxes); the tail launch only changes the unit size.
+template <int D, int EMU>
+static int launch_ta_quad(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtensorMap& tV, const TaParams& p, int B, int H,
+                          cudaStream_t stream) {
+  using Cfg = TaCfg<D>;
+  constexpr int smem4 = 4 * Cfg::Q_BYTES + TQ_ST * (Cfg::K_BYTES + Cfg::V_BYTES) + 1024 + 256;
+  constexpr int smem2 = 2 * Cfg::Q_BYTES + TQ_ST * (Cfg::K_BYTES + Cfg::V_BYTES) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 4, EMU>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+    AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 2, EMU>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    configured = true;
+  }
+  const int n_sm = 148;
+  const int n_qb4 = (p.Lq + 4 * TA_BM - 1) / (4 * TA_BM);
+  const int units4 = B * H * n_qb4;
+  // bulk: whole rounds of four-tile CTAs; tail: the rest as two-tile CTAs (only when Lq splits evenly into them)
+  int bulk = (units4 / n_sm) * n_sm;
+  if (p.Lq % (4 * TA_BM) != 0 || bulk == 0) bulk = units4;
+  if (bulk > 0) {
+    attn_fwd_tcgen05_quad_kernel<D, 4, EMU><<<bulk, 18 * 32, smem4, stream>>>(tQ, tK, tV, p, 0, H);
+    ++g_launch_count;
+  }
+  if (units4 > bulk) {
+    attn_fwd_tcgen05_quad_kernel<D, 2, EMU><<<2 * (units4 - bulk), 10 * 32, smem2, stream>>>(tQ, tK, tV, p, 2 * bulk, H);
+    ++g_launch_count;
+  }
+  AF_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int D, int EMU>
 static int launch_ta_mc(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtensorMap& tV, const TaParams& p, int B, int H,
                         cudaStream_t stream) {
@@ -866,15 +1144,31 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, co
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse;
   static int emu = -1, psmem = 0, mc = 1;
+  static bool emu_set = false;
   if (emu < 0) {
     const char* m = getenv("ADAFACE_ATTN_MC");      // 1 (default): many-small-CTAs kernel for d = 40 / 80
     mc = (m && m[0] == '0') ? 0 : 1;
     const char* e = getenv("ADAFACE_EXP_EMU");      // tuning knob: exp2 pairs of every 8 moved off the MUFU unit
     emu = (e && e[0] >= '0' && e[0] <= '4') ? (e[0] - '0') : 0;
+    emu_set = e != nullptr;
     const char* ps = getenv("ADAFACE_P_SMEM");      // debugging aid: hand P to the MMA through shared memory
     psmem = (ps && ps[0] == '1') ? 1 : 0;
   }
   const int ib = (int)B, ih = (int)H;
+  static int quad = -1;
+  if (quad < 0) {
+    const char* e = getenv("ADAFACE_ATTN_QUAD");    // 1 (default): four query tiles per CTA, one in-order MMA issuer (d = 40)
+    quad = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (quad && mc && !psmem && d == 40 && Lq >= 2 * TQ_G * TA_BM && Lk > 128) {
+    switch (emu_set ? emu : 1) {      // default: 1 of every 8 exp2 pairs on the FMA pipe (measured best: 359 vs 370 us)
+      case 0: return launch_ta_quad<40, 0>(tQ, tK, tV, p, ib, ih, stream);
+      case 1: return launch_ta_quad<40, 1>(tQ, tK, tV, p, ib, ih, stream);
+      case 2: return launch_ta_quad<40, 2>(tQ, tK, tV, p, ib, ih, stream);
+      case 3: return launch_ta_quad<40, 3>(tQ, tK, tV, p, ib, ih, stream);
+      default: return launch_ta_quad<40, 4>(tQ, tK, tV, p, ib, ih, stream);
+    }
+  }
   if (mc && !psmem && d == 40) {
     switch (emu) {
       case 0: return launch_ta_mc<40, 0>(tQ, tK, tV, p, ib, ih, stream);

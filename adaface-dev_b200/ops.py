@@ -142,6 +142,10 @@ def attention_headmajor(q, k, v, scale, *, d=None, out=None, lse=None):
 
 
 _HEADS_WS = {}
+# A/B switch.  The four-tile attention kernel fetches every K/V tile once per 512 queries, so the slow in-row-OOB TMA
+# path of the interleaved layout no longer matters and the padded head-major detour (60 % more QKV store bytes) is
+# off by default: measured 470 vs 459 TFLOP/s on the whole stack.
+_SELF_HEADMAJOR = __import__("os").environ.get("ADAFACE_SELF_HEADMAJOR", "0") == "1"
 
 
 def heads_workspace(n_which, B, H, L, dpad, device):
@@ -291,13 +295,12 @@ def softmax_scale(d):
 
 
 def self_attention_fused_qkv(x2d, wqkv, bqkv, B, N, heads, scale, key_mask=None):
-    """Fused QKV projection + unmasked/masked self-attention; returns o [B, N, C] bf16.
-    d = 40 without a mask: the projection scatters q/k/v into the zero-padded head-major workspace (128-byte rows per
-    (batch, head)) that the tcgen05 attention kernel's TMA loads 3x faster than 80-byte head slices; every other
-    case keeps the interleaved [B, N, 3C] buffer."""
+    """Fused QKV projection + unmasked/masked self-attention; returns o [B, N, C] bf16 from the interleaved [B, N, 3C]
+    buffer.  (ADAFACE_SELF_HEADMAJOR=1 restores the d = 40 detour through the zero-padded head-major workspace, which
+    the single-tile kernels' TMA loads 3x faster than 80-byte head slices.)"""
     C = wqkv.shape[0] // 3
     d = C // heads
-    if key_mask is None and d == 40:
+    if key_mask is None and d == 40 and _SELF_HEADMAJOR:
         ws = proj_heads(x2d, wqkv, heads, d, N, bias=bqkv)
         return attention_headmajor(ws[0], ws[1], ws[2], scale, d=d)
     qkv = proj(x2d, wqkv, bias=bqkv).view(B, N, 3 * C)

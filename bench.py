@@ -222,7 +222,10 @@ def build_stack(torch, a, device):
 
 # kernels of libadaface_b200.so per step: 16 blocks x (self: QKV GEMM, attention, out GEMM; cross: q GEMM, kv GEMM,
 # attention, out GEMM) = 112; counted live when the step is not replayed from a CUDA graph.
-LAUNCHES_PER_STEP = 16 * 7
+LAUNCHES_PER_STEP = 16 * 7 + 5      # + the tail launch of the 5 level-A self-attention calls
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel, from the ncu --set full capture
+# summarised in profiles/r01_ncu_full_attn_quad.txt (algorithmic: 4 * B * N * C * 2 = 83.9 MB)
+ROOFLINE_TRAFFIC_BYTES = None
 
 
 def run_stack(mods, xs, ctx):
@@ -441,20 +444,22 @@ def main_gpu(args):
         barrier()
         t_e2e_ms = sum(s.elapsed_time(e) for s, e in ee) / e2e_steps
 
-        # ---- roofline of the dominant kernel: level-A self-attention core (attn_fwd_kernel<40>)
+        # ---- roofline of the dominant kernel: level-A self-attention core, in the layout the processor feeds it
+        #      (q/k/v = column slices of the fused [B, N, 3C] projection buffer), timed alone with L2 flushed
         _, N, C, _ = LEVELS[0]
         dh = C // HEADS
-        ws = torch.zeros(3, BATCH, HEADS, N, 64, device=dev, dtype=torch.bfloat16)    # the processor's q/k/v workspace layout
-        ws[..., :dh] = torch.randn(3, BATCH, HEADS, N, dh, device=dev).to(torch.bfloat16)
+        qkv = torch.randn(BATCH, N, 3 * C, device=dev).to(torch.bfloat16)
+        kq, kk, kv_ = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+        ko = torch.empty(BATCH, N, C, device=dev, dtype=torch.bfloat16)
         for _ in range(3):
-            a.ops.attention_headmajor(ws[0], ws[1], ws[2], dh ** -0.5, d=dh)
+            a.ops.attention(kq, kk, kv_, HEADS, dh ** -0.5, out=ko)
         torch.cuda.synchronize()
         kt = []
         for _ in range(10):
             flush.fill_(1)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            a.ops.attention_headmajor(ws[0], ws[1], ws[2], dh ** -0.5, d=dh)
+            a.ops.attention(kq, kk, kv_, HEADS, dh ** -0.5, out=ko)
             e.record()
             torch.cuda.synchronize()
             kt.append(s.elapsed_time(e))
@@ -485,17 +490,17 @@ def main_gpu(args):
                        "modules": 32, "ctx_tokens": S_CTX, "heads": HEADS, "flops_per_step_per_gpu": fl_step,
                        "parallelism": f"dp{world} (batch sharded, no collective)",
                        "l2": "256 MB flush written between timed iterations; per-step working set > 1 GB",
-                       "launch": "CUDA graph replay of the 112-kernel step" if use_graph else "eager Python launches"},
+                       "launch": "CUDA graph replay of the 117-kernel step" if use_graph else "eager Python launches"},
             "frac_of_bf16_peak": value / world / pk["bf16_tflops_sustained"],
             "e2e": {"value": world * fl_step / (t_e2e_ms * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e_ms,
                     "how": f"{3 + a_split} units (levels D, C, B, {a_split} batch slices of A), one CUDA graph each; H2D / kernels / D2H on three streams"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "attn_fwd_tcgen05_mc_kernel<40> (level-A self-attention core, B=8, 4096 tok, 8x40)",
+            "roofline": {"kernel": "attn_fwd_tcgen05_quad_kernel<40> (level-A self-attention core, B=8, 4096 tok, 8x40; bulk + tail launch)",
                          "bound": "tensor", "achieved": k_flops / (k_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops"],
                          "unit": "TFLOP/s", "frac": k_flops / (k_ms * 1e-3) / 1e12 / pk["bf16_tflops"],
-                         "traffic": None, "peak_source": pk["source"] + " (burst: kernel timed alone)",
+                         "traffic": ROOFLINE_TRAFFIC_BYTES, "peak_source": pk["source"] + " (burst: kernel timed alone)",
                          "ms_per_launch": k_ms, "flops_per_launch": k_flops},
         }
         if extra is not None:

@@ -121,7 +121,9 @@ def ref_attn(q, k, v, H, scale, key_mask=None, causal_mult=0):
 @pytest.mark.parametrize("d,Lq,Lk", [(40, 256, 256), (40, 1000, 1000), (40, 77, 300), (80, 192, 130), (160, 64, 64),
                                      (160, 100, 77), (64, 20, 20), (40, 4096, 77), (40, 1, 1),
                                      # persistent short-context tcgen05 kernel (Lk <= 128, Lq >= 512)
-                                     (80, 1024, 77), (40, 1000, 97), (40, 4096, 128), (80, 600, 16), (40, 513, 1), (40, 2048, 120)])
+                                     (80, 1024, 77), (40, 1000, 97), (40, 4096, 128), (80, 600, 16), (40, 513, 1), (40, 2048, 120),
+                                     # four-tile ("quad") kernel: d = 40, Lq >= 1024, Lk > 128; ragged key and query tails
+                                     (40, 2048, 1111), (40, 1500, 4096), (40, 1024, 129)])
 def test_attention(d, Lq, Lk):
     B, H = 2, 8 if d != 64 else 12
     C = H * d
