@@ -15,6 +15,7 @@ SIGNATURES = {
     "adaface_version": [],
     "adaface_last_error": [],
     "adaface_launch_count": [],
+    "adaface_set_pdl": [_i32],
     "adaface_proj_lora_fwd": [_p, _i64, _p, _p, _i64, _p, _p, _p, _p, _i64, _i32, _p, _i64, _i32, _i64, _i64, _i64,
                               _i64, _i32, _p],
     "adaface_attn_fwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
@@ -47,7 +48,8 @@ SIGNATURES = {
                              _i64, _f32, _p],
 }
 # entry points that return a value instead of a status
-VALUE_RETURNING = ("adaface_version", "adaface_last_error", "adaface_launch_count", "adaface_attn_cross_capture_bwd_chunks")
+VALUE_RETURNING = ("adaface_version", "adaface_last_error", "adaface_launch_count", "adaface_set_pdl",
+                   "adaface_attn_cross_capture_bwd_chunks")
 
 _lib = None
 
@@ -81,6 +83,11 @@ def call(name, *args):
 
 def cross_capture_bwd_chunks(B, H, Lq):
     return int(load().adaface_attn_cross_capture_bwd_chunks(B, H, Lq))
+
+
+def set_pdl(enabled):
+    """Programmatic dependent launch on / off (adaface_set_pdl); returns the previous setting."""
+    return bool(load().adaface_set_pdl(int(bool(enabled))))
 
 
 def launch_count():

@@ -129,6 +129,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // global memory is touched only after the predecessor kernel has completed
 
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
@@ -311,6 +312,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
     }
   }
+  pdl_launch_dependents();     // late trigger: the successor's CTAs are scheduled while this one tears down
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
@@ -373,6 +375,7 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // global memory is touched only after the predecessor kernel has completed
 
   if (warp == kTmaWarp) {
     if (elect_one()) {
@@ -523,6 +526,7 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       }
     }
   }
+  pdl_launch_dependents();     // late trigger: the successor's CTAs are scheduled while this one tears down
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
@@ -604,6 +608,7 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // global memory is touched only after the predecessor kernel has completed
 
   if (warp == kTma) {
     if (elect_one()) {
@@ -770,6 +775,7 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
       }
     }
   }
+  pdl_launch_dependents();     // late trigger: the successor's CTAs are scheduled while this one tears down
   tc_fence_before();
   __syncthreads();
   if (warp == kMma) {
@@ -798,11 +804,11 @@ static int launch_ta_quad(const CUtensorMap& tQ, const CUtensorMap& tK, const CU
   int bulk = (units4 / n_sm) * n_sm;
   if (p.Lq % (4 * TA_BM) != 0 || bulk == 0) bulk = units4;
   if (bulk > 0) {
-    attn_fwd_tcgen05_quad_kernel<D, 4, EMU><<<bulk, 18 * 32, smem4, stream>>>(tQ, tK, tV, p, 0, H);
+    AF_CUDA(launch_pdl(attn_fwd_tcgen05_quad_kernel<D, 4, EMU>, dim3(bulk), dim3(18 * 32), smem4, stream, tQ, tK, tV, p, 0, H));
     ++g_launch_count;
   }
   if (units4 > bulk) {
-    attn_fwd_tcgen05_quad_kernel<D, 2, EMU><<<2 * (units4 - bulk), 10 * 32, smem2, stream>>>(tQ, tK, tV, p, 2 * bulk, H);
+    AF_CUDA(launch_pdl(attn_fwd_tcgen05_quad_kernel<D, 2, EMU>, dim3(2 * (units4 - bulk)), dim3(10 * 32), smem2, stream, tQ, tK, tV, p, 2 * bulk, H));
     ++g_launch_count;
   }
   AF_CUDA(cudaGetLastError());
@@ -820,7 +826,7 @@ static int launch_ta_mc(const CUtensorMap& tQ, const CUtensorMap& tK, const CUte
     configured = true;
   }
   dim3 grid((p.Lq + TA_BM - 1) / TA_BM, H, B);
-  attn_fwd_tcgen05_mc_kernel<D, EMU><<<grid, TA_THREADS, smem, stream>>>(tQ, tK, tV, p);
+  AF_CUDA(launch_pdl(attn_fwd_tcgen05_mc_kernel<D, EMU>, grid, dim3(TA_THREADS), smem, stream, tQ, tK, tV, p));
   AF_CUDA(cudaGetLastError());
   ++g_launch_count;
   return 0;
@@ -837,7 +843,7 @@ static int launch_ta(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtenso
     configured = true;
   }
   dim3 grid((p.Lq + TA_BM - 1) / TA_BM, H, B);
-  attn_fwd_tcgen05_kernel<D, EMU, PT><<<grid, TA_THREADS, Cfg::SMEM_BYTES, stream>>>(tQ, tK, tV, p);
+  AF_CUDA(launch_pdl(attn_fwd_tcgen05_kernel<D, EMU, PT>, grid, dim3(TA_THREADS), Cfg::SMEM_BYTES, stream, tQ, tK, tV, p));
   AF_CUDA(cudaGetLastError());
   ++g_launch_count;
   return 0;
@@ -912,6 +918,7 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // global memory is touched only after the predecessor kernel has completed
 
   if (warp == kTmaWarp) {
     if (elect_one()) {
@@ -1063,6 +1070,7 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_arrive(o_free);
     }
   }
+  pdl_launch_dependents();     // late trigger: the successor's CTAs are scheduled while this one tears down
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
@@ -1103,7 +1111,7 @@ static int launch_tc_cross(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_
   if (per_sm < 1) per_sm = 1;
   int grid = 148 * per_sm;
   if (grid > p.n_units) grid = p.n_units;
-  attn_cross_tc_kernel<D, NKT><<<grid, TA_THREADS, smem, stream>>>(tQ, tK, tV, p);
+  AF_CUDA(launch_pdl(attn_cross_tc_kernel<D, NKT>, dim3(grid), dim3(TA_THREADS), smem, stream, tQ, tK, tV, p));
   AF_CUDA(cudaGetLastError());
   ++g_launch_count;
   return 0;

@@ -56,6 +56,15 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------
+// The step is ~117 short kernels (avg 30 us): launch latency, CTA ramp-up and each kernel's prologue (barrier init,
+// TMEM allocation, descriptor prefetch) are a measurable share of it.  Kernels launched with launch_pdl() may start
+// while the previous kernel of the stream is still draining; pdl_wait() (griddepcontrol.wait) blocks until that kernel
+// has completed and its memory is visible, so it must precede the first access to global memory the predecessor may
+// touch; pdl_launch_dependents() lets the successor's CTAs be scheduled as soon as resources free up.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- mbarrier -------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -295,5 +304,23 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 #endif  // __CUDACC__
+
+// Host: launch with the programmatic-stream-serialization attribute (ADAFACE_PDL=0 disables it).  Captured into CUDA
+// graphs as a programmatic dependency edge.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 }  // namespace adaface

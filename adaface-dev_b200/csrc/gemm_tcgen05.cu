@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // this kernel touches global memory only after its predecessor has completed
 
   if (warp == kTma) {
     // ------------------------------------------------------------------ TMA producer
@@ -338,6 +339,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
       }
     }
   }
+  pdl_launch_dependents();     // late trigger: the successor's CTAs are scheduled while this one tears down
   tc_fence_before();
   __syncthreads();
   if (warp == kMma) {
@@ -367,7 +369,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   }
   const int tiles = n_tiles * ((ep.M + GEMM_BM - 1) / GEMM_BM);
   dim3 grid(tiles < num_sms ? tiles : num_sms);
-  gemm_tn_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tA, tB, tA2, tB2, ep);
+  AF_CUDA(launch_pdl(gemm_tn_tcgen05_kernel<BN>, grid, dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tA, tB, tA2, tB2, ep));
   AF_CUDA(cudaGetLastError());
   ++g_launch_count;
   return 0;

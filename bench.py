@@ -395,6 +395,7 @@ def main_gpu(args):
         units = [(3, slice(0, BATCH)), (2, slice(0, BATCH)), (1, slice(0, BATCH))] + \
                 [(0, slice(i * step_b, (i + 1) * step_b)) for i in range(a_split)]
         unit_fns, unit_in, unit_out = [], [], []
+        prev_pdl = a._lib.set_pdl(os.environ.get("ADAFACE_BENCH_E2E_PDL", "1") != "0")   # programmatic dependent launch inside the unit graphs
         for li, sl in units:
             x_u, c_u = xs[li][sl].contiguous(), ctx[sl].contiguous()
             if use_graph:
@@ -404,6 +405,7 @@ def main_gpu(args):
             unit_fns.append(fn)
             unit_in.append((xs_pin[li][sl], ctx_pin[sl]))
             unit_out.append(torch.empty(x_u.shape, dtype=torch.bfloat16).pin_memory())
+        a._lib.set_pdl(prev_pdl)
         h2d = sum(x.numel() * 2 + c.numel() * 2 for x, c in unit_in)
         d2h = sum(o.numel() * 2 for o in unit_out)
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()

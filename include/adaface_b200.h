@@ -32,6 +32,10 @@ int adaface_version(void);
 const char* adaface_last_error(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches evidence). */
 int64_t adaface_launch_count(void);
+/* Programmatic dependent launch for the tcgen05 kernels (launch attribute programmaticStreamSerialization; the kernels
+ * run griddepcontrol.wait before their first global access).  Returns the previous setting.  Default: env ADAFACE_PDL
+ * (off).  Helps launch-gap-bound sequences (small CUDA graphs between copies), costs ~3 % on one long graph. */
+int adaface_set_pdl(int enabled);
 
 /* ---- K1: projection GEMM with the LoRA/DoRA update folded in --------------------------------------
  * Replaces attn.to_q / to_k / to_v / to_out[0] (dalc:235, 283, 288, 331), their peft lora.Linear
