@@ -387,10 +387,11 @@ def main_gpu(args):
         t_ms = sum(s.elapsed_time(e) for s, e in ev)
 
         # ---- end to end: host buffers in, host results out, through the same public operator.
-        # The step is cut into five independent units (level D, C, B, and the two half-batches of level A -- samples
-        # are independent), each its own CUDA graph.  Three streams: H2D of unit i+1 and D2H of unit i-1
-        # overlap the kernels of unit i; the small levels go first so that level A's 21 MB input is in flight behind them.
-        a_split = int(os.environ.get("ADAFACE_BENCH_A_SPLIT", "2"))     # level A in this many batch slices (2: measured best)
+        # The step is cut into independent units (levels D, C, B, A -- the four levels of the stack do not depend on each
+        # other; level A can further be cut into batch slices, samples being independent), each its own CUDA
+        # graph.  Three streams: H2D of unit i+1 and D2H of unit i-1 overlap the kernels of unit i; the small levels go
+        # first so that level A's 21 MB input is in flight behind them.  Exposed: the first unit's H2D and the last D2H.
+        a_split = int(os.environ.get("ADAFACE_BENCH_A_SPLIT", "1"))     # level A in this many batch slices (1 / 2 measured equal: 4.14 / 4.18 ms)
         step_b = BATCH // a_split
         units = [(3, slice(0, BATCH)), (2, slice(0, BATCH)), (1, slice(0, BATCH))] + \
                 [(0, slice(i * step_b, (i + 1) * step_b)) for i in range(a_split)]
@@ -413,7 +414,13 @@ def main_gpu(args):
         dev_in = [(fn.static_inputs[0], fn.static_inputs[1]) if use_graph else
                   (torch.empty_like(x, device=dev), torch.empty_like(c, device=dev)) for fn, (x, c) in zip(unit_fns, unit_in)]
 
+        diag_nocopy = os.environ.get("ADAFACE_BENCH_E2E_NOCOPY") == "1"     # diagnosis only: unit graphs without the copies
+
         def e2e_step():
+            if diag_nocopy:
+                for fn, (xd, cd) in zip(unit_fns, dev_in):
+                    fn(xd, cd)
+                return
             s_in.wait_stream(comp)          # the previous step has finished reading the input buffers
             ev_in, ev_out = [], []
             with torch.cuda.stream(s_in):
