@@ -546,6 +546,9 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
 // A tile's next scores are produced right after its P.V while the other three tiles are still in their softmax, so
 // the tensor work of one tile always runs under the exp2 work of the others, and every K/V tile is fetched once per
 // 512 queries instead of once per 128 (4x less TMA / L2 traffic).
+// (Tried on top of this and dropped: THREE tiles per CTA with TWO threads per query row -- 24 softmax warps, scores read
+// from TMEM once, half-row maxima exchanged through shared memory + 64-thread named barriers: correct, but 418 us vs
+// 372 us; the extra hand-off per tile costs more than the shorter per-warp chain saves.)
 // Wave quantisation: a CTA now lasts 4x longer, so 512 units on 148 SMs would leave 80 SMs idle for a whole CTA
 // lifetime in the 4th round (measured: 387 us, no better than the small-CTA kernel).  The launcher therefore runs
 // floor(units / 148) * 148 four-tile CTAs and covers the remainder with TWO-tile CTAs (G = 2, 256 TMEM columns)
