@@ -564,7 +564,7 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
   using Cfg = TaCfg<D>;
   constexpr int NA = Cfg::NA, KT = Cfg::KT, DO = Cfg::DO, ST = TQ_ST;
   constexpr int TMEM_G = 128, TMEM_O = TA_BN;                     // per tile: S/P at +0, O at +64
-  static_assert(TMEM_O + DO <= TMEM_G && NA == 1, "quad kernel: head dim must fit 128 TMEM columns per tile");
+  static_assert(TMEM_O + DO <= TMEM_G && NA == 1 && D < DO, "quad kernel: head dim must fit 128 TMEM columns per tile and leave a pad column for the row sums");
   constexpr int kTma = 4 * G, kMma = 4 * G + 1;
   extern __shared__ uint8_t smem_raw_tq[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tq) + 1023) & ~uintptr_t(1023));
@@ -578,7 +578,8 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
   uint64_t* s_full = kv_empty + ST;                               // [G]
   uint64_t* p_full = s_full + G;                                  // [G]
   uint64_t* o_full = p_full + G;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* v_ready = o_full + 1;                                 // [ST]: the ones column has been written into V stage s
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_ready + ST);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // unit = (batch, head, block of G query tiles), linearised with the query block fastest
@@ -597,6 +598,7 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
     for (int s = 0; s < ST; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
+      mbar_init(&v_ready[s], 1);
     }
     for (int g = 0; g < G; ++g) {
       mbar_init(&s_full[g], 1);
@@ -614,17 +616,37 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
   pdl_wait();                  // global memory is touched only after the predecessor kernel has completed
 
   if (warp == kTma) {
-    if (elect_one()) {
+    // The whole warp runs this loop: one elected lane issues the TMA loads (two tiles ahead), then all 32 lanes write
+    // the ONES COLUMN into the V tile that has just landed: column D of every V row := 1.0, so that column D of the
+    // P.V accumulator is the row sum of P -- the softmax warps then neither mask-truncate nor add up their probabilities.
+    const bool leader = elect_one();
+    auto issue_kv = [&](int j) {
+      const int s = j % ST;
+      mbar_wait(&kv_empty[s], ((j / ST) & 1) ^ 1);
+      mbar_arrive_expect_tx(&kv_full[s], Cfg::K_BYTES + Cfg::V_BYTES);
+      tma_load_4d(sK + s * Cfg::K_BYTES, &tmK, &kv_full[s], 0, h, j * TA_BN, b);
+      tma_load_4d(sV + s * Cfg::V_BYTES, &tmV, &kv_full[s], 0, h, j * TA_BN, b);
+    };
+    if (leader) {
       mbar_arrive_expect_tx(q_full, G * Cfg::Q_BYTES);
 #pragma unroll
       for (int g = 0; g < G; ++g) tma_load_4d(sQ + g * Cfg::Q_BYTES, &tmQ, q_full, 0, h, m0 + g * TA_BM, b);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % ST;
-        mbar_wait(&kv_empty[s], ((j / ST) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], Cfg::K_BYTES + Cfg::V_BYTES);
-        tma_load_4d(sK + s * Cfg::K_BYTES, &tmK, &kv_full[s], 0, h, j * TA_BN, b);
-        tma_load_4d(sV + s * Cfg::V_BYTES, &tmV, &kv_full[s], 0, h, j * TA_BN, b);
+      issue_kv(0);
+      if (n_tiles > 1) issue_kv(1);
+    }
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j % ST;
+      mbar_wait(&kv_full[s], (j / ST) & 1);
+#pragma unroll
+      for (int r = lane; r < TA_BN; r += 32)       // 128B-swizzled tile: element D of row r sits in chunk (D/8) ^ (r & 7)
+        *reinterpret_cast<uint16_t*>(sV + s * Cfg::V_BYTES + r * 128 + ((((D >> 3) ^ (r & 7)) << 4) | ((D & 7) << 1))) = 0x3F80;
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (leader) {
+        mbar_arrive(&v_ready[s]);
+        if (j + 2 < n_tiles) issue_kv(j + 2);
       }
+      __syncwarp();
     }
   } else if (warp == kMma) {
     if (elect_one()) {
@@ -656,10 +678,9 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j % ST;
         const bool more = j + 1 < n_tiles;
-        if (more) {
-          mbar_wait(&kv_full[(j + 1) % ST], ((j + 1) / ST) & 1);
-          tc_fence_after();
-        }
+        mbar_wait(&v_ready[s], (j / ST) & 1);                     // V_j carries its ones column
+        if (more) mbar_wait(&kv_full[(j + 1) % ST], ((j + 1) / ST) & 1);
+        tc_fence_after();
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           mbar_wait(&p_full[g], j & 1);                           // tile g's P_j is in TMEM
@@ -680,30 +701,27 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
     const int g = warp >> 2, qd = warp & 3;
     const int row = qd * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(g * TMEM_G);
-    float m_ref = -INFINITY, l_run = 0.f;
+    float m_ref = -INFINITY;
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(&s_full[g], j & 1);          // also implies P V_{j-1} of this tile has retired
       tc_fence_after();
       const int valid = p.Lk - j * TA_BN;
-      float mxr = -INFINITY;
+      // the 64 scores of this row are read from TMEM ONCE and stay in registers for both the max and the exp pass
+      // (one CTA per SM: 112 registers per thread are available)
+      uint32_t v[TA_BN];
+      tmem_ld_32x32b_x64_wait(t_lane, v);
+      if (valid < TA_BN) {
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32_wait(t_lane + (uint32_t)(hf * 32), v);
-        if (valid < TA_BN) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (hf * 32 + i >= valid) v[i] = 0xff800000u;
-        }
-        float m4[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
-#pragma unroll
-        for (int i = 4; i < 32; i += 4) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) m4[u] = fmaxf(m4[u], __uint_as_float(v[i + u]));
-        }
-        mxr = fmaxf(mxr, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+        for (int i = 0; i < TA_BN; ++i)
+          if (i >= valid) v[i] = 0xff800000u;
       }
-      const float mx = mxr * p.scale_log2;
+      float m4[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
+#pragma unroll
+      for (int i = 4; i < TA_BN; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) m4[u] = fmaxf(m4[u], __uint_as_float(v[i + u]));
+      }
+      const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
       if (j == 0) {
         m_ref = (mx == -INFINITY) ? 0.f : mx;
       } else {
@@ -712,7 +730,6 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
           const float m_new = need ? mx : m_ref;
           const float f = fast_exp2(m_ref - m_new);
           m_ref = m_new;
-          l_run *= f;
 #pragma unroll
           for (int c = 0; c < DO / 16; ++c) {
             uint32_t ov[16];
@@ -725,34 +742,30 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
         }
       }
       const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
-      float2 ls[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32_wait(t_lane + (uint32_t)(hf * 32), v);
-        if (valid < TA_BN) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (hf * 32 + i >= valid) v[i] = 0xff800000u;
-        }
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc2, nm2);
+          const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[hf * 32 + 2 * i]), __uint_as_float(v[hf * 32 + 2 * i + 1])), sc2, nm2);
           const float2 e = ((i & 7) < EMU) ? exp2_emu2(t) : make_float2(fast_exp2(t.x), fast_exp2(t.y));
-          const uint32_t ex = __float_as_uint(e.x) & 0xffff0000u, ey = __float_as_uint(e.y) & 0xffff0000u;
-          ls[i & 1] = __fadd2_rn(ls[i & 1], make_float2(__uint_as_float(ex), __uint_as_float(ey)));
-          pk[i] = __byte_perm(ex, ey, 0x7632);
+          pk[i] = __byte_perm(__float_as_uint(e.x), __float_as_uint(e.y), 0x7632);   // truncate to bf16; the row sum comes from the MMA
         }
         tmem_st_32x32b_x16(t_lane + (uint32_t)(hf * 16), pk);
       }
       tmem_st_wait();
-      l_run += (ls[0].x + ls[0].y) + (ls[1].x + ls[1].y);
       tc_fence_before();
       mbar_arrive(&p_full[g]);
     }
     mbar_wait(o_full, 0);
     tc_fence_after();
+    float l_run;                                                   // row sum of P = column D of the accumulator
+    {
+      uint32_t v8[8];
+      tmem_ld_32x32b_x8(t_lane + (uint32_t)(TMEM_O + (D & ~7)), v8);
+      tmem_ld_wait();
+      l_run = __uint_as_float(v8[D & 7]);
+    }
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
     const int grow = m0 + g * TA_BM + row;
     if (p.lse && grow < p.Lq)
@@ -1172,7 +1185,7 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, co
     quad = (e && e[0] == '0') ? 0 : 1;
   }
   if (quad && mc && !psmem && d == 40 && Lq >= 2 * TQ_G * TA_BM && Lk > 128) {
-    switch (emu_set ? emu : 1) {      // default: 1 of every 8 exp2 pairs on the FMA pipe (measured best: 359 vs 370 us)
+    switch (emu_set ? emu : 2) {      // default: 2 of every 8 exp2 pairs on the FMA pipe (measured: 366 / 349 / 333 / 334 / 342 us for 0..4)
       case 0: return launch_ta_quad<40, 0>(tQ, tK, tV, p, ib, ih, stream);
       case 1: return launch_ta_quad<40, 1>(tQ, tK, tV, p, ib, ih, stream);
       case 2: return launch_ta_quad<40, 2>(tQ, tK, tV, p, ib, ih, stream);
