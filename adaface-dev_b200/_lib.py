@@ -85,9 +85,10 @@ def cross_capture_bwd_chunks(B, H, Lq):
     return int(load().adaface_attn_cross_capture_bwd_chunks(B, H, Lq))
 
 
-def set_pdl(enabled):
-    """Programmatic dependent launch on / off (adaface_set_pdl); returns the previous setting."""
-    return bool(load().adaface_set_pdl(int(bool(enabled))))
+def set_pdl(mask):
+    """Programmatic dependent launch (adaface_set_pdl): bit 0 = projection GEMMs, bit 1 = attention kernels; True = both.
+    Returns the previous mask."""
+    return int(load().adaface_set_pdl(3 if mask is True else int(mask)))
 
 
 def launch_count():

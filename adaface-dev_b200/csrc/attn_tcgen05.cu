@@ -820,11 +820,11 @@ static int launch_ta_quad(const CUtensorMap& tQ, const CUtensorMap& tK, const CU
   int bulk = (units4 / n_sm) * n_sm;
   if (p.Lq % (4 * TA_BM) != 0 || bulk == 0) bulk = units4;
   if (bulk > 0) {
-    AF_CUDA(launch_pdl(attn_fwd_tcgen05_quad_kernel<D, 4, EMU>, dim3(bulk), dim3(18 * 32), smem4, stream, tQ, tK, tV, p, 0, H));
+    AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_quad_kernel<D, 4, EMU>, dim3(bulk), dim3(18 * 32), smem4, stream, tQ, tK, tV, p, 0, H));
     ++g_launch_count;
   }
   if (units4 > bulk) {
-    AF_CUDA(launch_pdl(attn_fwd_tcgen05_quad_kernel<D, 2, EMU>, dim3(2 * (units4 - bulk)), dim3(10 * 32), smem2, stream, tQ, tK, tV, p, 2 * bulk, H));
+    AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_quad_kernel<D, 2, EMU>, dim3(2 * (units4 - bulk)), dim3(10 * 32), smem2, stream, tQ, tK, tV, p, 2 * bulk, H));
     ++g_launch_count;
   }
   AF_CUDA(cudaGetLastError());
@@ -842,7 +842,7 @@ static int launch_ta_mc(const CUtensorMap& tQ, const CUtensorMap& tK, const CUte
     configured = true;
   }
   dim3 grid((p.Lq + TA_BM - 1) / TA_BM, H, B);
-  AF_CUDA(launch_pdl(attn_fwd_tcgen05_mc_kernel<D, EMU>, grid, dim3(TA_THREADS), smem, stream, tQ, tK, tV, p));
+  AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_mc_kernel<D, EMU>, grid, dim3(TA_THREADS), smem, stream, tQ, tK, tV, p));
   AF_CUDA(cudaGetLastError());
   ++g_launch_count;
   return 0;
@@ -859,7 +859,7 @@ static int launch_ta(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtenso
     configured = true;
   }
   dim3 grid((p.Lq + TA_BM - 1) / TA_BM, H, B);
-  AF_CUDA(launch_pdl(attn_fwd_tcgen05_kernel<D, EMU, PT>, grid, dim3(TA_THREADS), Cfg::SMEM_BYTES, stream, tQ, tK, tV, p));
+  AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_kernel<D, EMU, PT>, grid, dim3(TA_THREADS), Cfg::SMEM_BYTES, stream, tQ, tK, tV, p));
   AF_CUDA(cudaGetLastError());
   ++g_launch_count;
   return 0;
@@ -1127,7 +1127,7 @@ static int launch_tc_cross(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_
   if (per_sm < 1) per_sm = 1;
   int grid = 148 * per_sm;
   if (grid > p.n_units) grid = p.n_units;
-  AF_CUDA(launch_pdl(attn_cross_tc_kernel<D, NKT>, dim3(grid), dim3(TA_THREADS), smem, stream, tQ, tK, tV, p));
+  AF_CUDA(launch_pdl(2, attn_cross_tc_kernel<D, NKT>, dim3(grid), dim3(TA_THREADS), smem, stream, tQ, tK, tV, p));
   AF_CUDA(cudaGetLastError());
   ++g_launch_count;
   return 0;

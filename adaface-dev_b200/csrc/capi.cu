@@ -11,13 +11,13 @@ namespace adaface {
 long long g_launch_count = 0;
 static thread_local char g_err[1024] = "";
 
-static int g_pdl = -1;
-bool pdl_enabled() {
+static int g_pdl = -1;           // bit mask: 1 = projection GEMMs, 2 = attention kernels
+bool pdl_enabled(int kind) {
   if (g_pdl < 0) {
-    const char* e = getenv("ADAFACE_PDL");       // default off: measured -3 % on the 117-kernel graph, +3 % on the
-    g_pdl = (e && e[0] == '1') ? 1 : 0;          // end-to-end path (small per-level graphs between copies)
+    const char* e = getenv("ADAFACE_PDL");       // default 1 (GEMMs only): measured on the 117-kernel step graph
+    g_pdl = e ? atoi(e) : 1;                     // 0: 3.221 ms, 1: 3.141 ms, 2: 3.192 ms, 3: 3.151 ms
   }
-  return g_pdl == 1;
+  return (g_pdl & kind) != 0;
 }
 
 void set_error(const char* fmt, ...) {
@@ -137,9 +137,10 @@ extern "C" {
 int adaface_version(void) { return ADAFACE_B200_ABI_VERSION; }
 const char* adaface_last_error(void) { return g_err; }
 int64_t adaface_launch_count(void) { return g_launch_count; }
-int adaface_set_pdl(int enabled) {
-  const int prev = pdl_enabled() ? 1 : 0;
-  g_pdl = enabled ? 1 : 0;
+int adaface_set_pdl(int mask) {
+  pdl_enabled(1);
+  const int prev = g_pdl;
+  g_pdl = mask;
   return prev;
 }
 

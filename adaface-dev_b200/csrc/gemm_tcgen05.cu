@@ -369,7 +369,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   }
   const int tiles = n_tiles * ((ep.M + GEMM_BM - 1) / GEMM_BM);
   dim3 grid(tiles < num_sms ? tiles : num_sms);
-  AF_CUDA(launch_pdl(gemm_tn_tcgen05_kernel<BN>, grid, dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tA, tB, tA2, tB2, ep));
+  AF_CUDA(launch_pdl(1, gemm_tn_tcgen05_kernel<BN>, grid, dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tA, tB, tA2, tB2, ep));
   AF_CUDA(cudaGetLastError());
   ++g_launch_count;
   return 0;

@@ -396,7 +396,7 @@ def main_gpu(args):
         units = [(3, slice(0, BATCH)), (2, slice(0, BATCH)), (1, slice(0, BATCH))] + \
                 [(0, slice(i * step_b, (i + 1) * step_b)) for i in range(a_split)]
         unit_fns, unit_in, unit_out = [], [], []
-        prev_pdl = a._lib.set_pdl(os.environ.get("ADAFACE_BENCH_E2E_PDL", "1") != "0")   # programmatic dependent launch inside the unit graphs
+        prev_pdl = a._lib.set_pdl(int(os.environ.get("ADAFACE_BENCH_E2E_PDL", "3")))   # programmatic dependent launch mask inside the unit graphs
         for li, sl in units:
             x_u, c_u = xs[li][sl].contiguous(), ctx[sl].contiguous()
             if use_graph:

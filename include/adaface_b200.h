@@ -33,9 +33,10 @@ const char* adaface_last_error(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches evidence). */
 int64_t adaface_launch_count(void);
 /* Programmatic dependent launch for the tcgen05 kernels (launch attribute programmaticStreamSerialization; the kernels
- * run griddepcontrol.wait before their first global access).  Returns the previous setting.  Default: env ADAFACE_PDL
- * (off).  Helps launch-gap-bound sequences (small CUDA graphs between copies), costs ~3 % on one long graph. */
-int adaface_set_pdl(int enabled);
+ * run griddepcontrol.wait before their first global access).  Returns the previous mask.  Default: env ADAFACE_PDL,
+ * else 1 (GEMMs only: the short projection kernels gain most from overlapping their launch ramp with the
+ * predecessor's tail; +2.5 % on the whole step). */
+int adaface_set_pdl(int mask);   /* bit 0: projection GEMMs, bit 1: attention kernels */
 
 /* ---- K1: projection GEMM with the LoRA/DoRA update folded in --------------------------------------
  * Replaces attn.to_q / to_k / to_v / to_out[0] (dalc:235, 283, 288, 331), their peft lora.Linear
