@@ -888,7 +888,8 @@ __global__ void __launch_bounds__(TA_THREADS, (D <= 64) ? 4 : 2)
 attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const TcParams p) {
   using Cfg = TaCfg<D>;
-  constexpr int NA = Cfg::NA, KT = Cfg::KT, DO = Cfg::DO;
+  constexpr int NA = Cfg::NA, KT = Cfg::KT;
+  constexpr int DO = (D % 16 == 0) ? D + 16 : Cfg::DO;      // accumulator width incl. a pad column D that receives the row sums
   constexpr int NK = NKT;                                  // staged keys (multiple of 16, <= 128)
   constexpr int KV_ATOM = NK * 128;                        // bytes of one 64-column atom of the K / V tile
   constexpr int TMEM_O = NK;                               // O behind the S / P region
@@ -906,7 +907,8 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* p_full = bars + 7;
   uint64_t* o_full = bars + 8;
   uint64_t* o_free = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* v_ready = bars + 10;                           // K / V of the current (batch, head) landed AND V carries its ones column
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u0 = (int)((long long)blockIdx.x * p.n_units / gridDim.x);
@@ -922,6 +924,7 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     mbar_init(kv_full, 1);
     mbar_init(kv_empty, 1);
+    mbar_init(v_ready, 1);
     mbar_init(s_full, 1);
     mbar_init(p_full, 128);
     mbar_init(o_full, 1);
@@ -937,12 +940,16 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   pdl_wait();                  // global memory is touched only after the predecessor kernel has completed
 
   if (warp == kTmaWarp) {
-    if (elect_one()) {
-      int prev_bh = -1, kv_loads = 0;
-      for (int u = u0, i = 0; u < u1; ++u, ++i) {
-        const int bh = u / p.n_qtiles, qt = u - bh * p.n_qtiles;
-        const int b = bh / p.H, h = bh - b * p.H;
-        if (bh != prev_bh) {
+    // whole warp: one elected lane issues the TMA loads; when a new (batch, head) arrives all lanes write the ONES
+    // COLUMN (column D of every V row := 1.0) so that column D of the P.V accumulator is the row sum of P
+    const bool leader = elect_one();
+    int prev_bh = -1, kv_loads = 0;
+    for (int u = u0, i = 0; u < u1; ++u, ++i) {
+      const int bh = u / p.n_qtiles, qt = u - bh * p.n_qtiles;
+      const int b = bh / p.H, h = bh - b * p.H;
+      const bool new_kv = bh != prev_bh;
+      if (leader) {
+        if (new_kv) {
           if (kv_loads > 0) mbar_wait(kv_empty, (kv_loads - 1) & 1);   // every MMA that read the old K / V has retired
           mbar_arrive_expect_tx(kv_full, 2 * NA * KV_ATOM);
 #pragma unroll
@@ -950,8 +957,6 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             tma_load_4d(sK + a * KV_ATOM, &tmK, kv_full, a * 64, h, 0, b);
             tma_load_4d(sV + a * KV_ATOM, &tmV, kv_full, a * 64, h, 0, b);
           }
-          ++kv_loads;
-          prev_bh = bh;
         }
         const int s = i & 1;
         if (i >= 2) mbar_wait(&q_empty[s], ((i >> 1) - 1) & 1);
@@ -959,6 +964,18 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
         for (int a = 0; a < NA; ++a) tma_load_4d(sQ + s * Cfg::Q_BYTES + a * (TA_BM * 128), &tmQ, &q_full[s], a * 64, h, qt * TA_BM, b);
       }
+      if (new_kv) {
+        mbar_wait(kv_full, kv_loads & 1);
+        uint8_t* atom = sV + (D >> 6) * KV_ATOM;             // the 64-column atom that holds column D
+        for (int r = lane; r < NK; r += 32)
+          *reinterpret_cast<uint16_t*>(atom + r * 128 + (((((D & 63) >> 3) ^ (r & 7)) << 4) | ((D & 7) << 1))) = 0x3F80;
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (leader) mbar_arrive(v_ready);
+        ++kv_loads;
+        prev_bh = bh;
+      }
+      __syncwarp();
     }
   } else if (warp == kMmaWarp) {
     if (elect_one()) {
@@ -969,7 +986,7 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int u = u0, i = 0; u < u1; ++u, ++i) {
         const int bh = u / p.n_qtiles;
         if (bh != prev_bh) {
-          mbar_wait(kv_full, kv_loads & 1);
+          mbar_wait(v_ready, kv_loads & 1);
           ++kv_loads;
           prev_bh = bh;
         }
@@ -1029,7 +1046,6 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float m_ref = mxr * p.scale_log2;
       // ---- pass 2: P = exp2(s * scale - max) truncated to bf16, written over the scores it came from
       const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
-      float2 ls[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
       for (int c = 0; c < NK; c += 16) {
         uint32_t v[16];
@@ -1045,26 +1061,30 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int j = 0; j < 8; ++j) {
           const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), sc2, nm2);
           const float2 e = make_float2(fast_exp2(t.x), fast_exp2(t.y));
-          const uint32_t ex = __float_as_uint(e.x) & 0xffff0000u, ey = __float_as_uint(e.y) & 0xffff0000u;
-          ls[j & 1] = __fadd2_rn(ls[j & 1], make_float2(__uint_as_float(ex), __uint_as_float(ey)));
-          pk[j] = __byte_perm(ex, ey, 0x7632);
+          pk[j] = __byte_perm(__float_as_uint(e.x), __float_as_uint(e.y), 0x7632);   // truncate; the row sum comes from the MMA
         }
         tmem_st_32x32b_x8(t_lane + (uint32_t)(c >> 1), pk);     // columns [c/2, c/2 + 8): already consumed
       }
       tmem_st_wait();
-      const float l_run = (ls[0].x + ls[0].y) + (ls[1].x + ls[1].y);
       tc_fence_before();
       mbar_arrive(p_full);
       // ---- epilogue: O / l -> bf16 -> [B, Lq, H*d]
       mbar_wait(o_full, i & 1);
       tc_fence_after();
+      float l_run;                                             // row sum of P = column D of the accumulator
+      {
+        uint32_t v8[8];
+        tmem_ld_32x32b_x8(t_lane + (uint32_t)(TMEM_O + (D & ~7)), v8);
+        tmem_ld_wait();
+        l_run = __uint_as_float(v8[D & 7]);
+      }
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
       const int grow = qt * TA_BM + row;
       if (p.lse && grow < p.Lq)
         p.lse[((long long)b * p.H + h) * p.Lq + grow] = l_run > 0.f ? m_ref + log2f(l_run) : INFINITY;
       bf16* orow = p.o + (long long)b * p.o_sb + (long long)grow * p.o_sn + h * D;
 #pragma unroll
-      for (int c = 0; c < DO / 16; ++c) {
+      for (int c = 0; c < (D + 15) / 16; ++c) {
         uint32_t v[16];
         tmem_ld_32x32b_x16(t_lane + (uint32_t)(TMEM_O + c * 16), v);
         tmem_ld_wait();
@@ -1111,7 +1131,8 @@ static int launch_tc_cross(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_
   p.Lq = (int)Lq; p.Lk = (int)Lk; p.H = (int)H; p.NK = NK;
   p.n_qtiles = (int)((Lq + TA_BM - 1) / TA_BM);
   p.n_units = (int)(B * H) * p.n_qtiles;
-  p.tmem_cols = (NK + Cfg::DO <= 128) ? 128 : 256;
+  constexpr int DO_S = (D % 16 == 0) ? D + 16 : Cfg::DO;
+  p.tmem_cols = (NK + DO_S <= 128) ? 128 : 256;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse;
   const int smem = 2 * Cfg::Q_BYTES + 2 * Cfg::NA * NK * 128 + 1024 + 128;
