@@ -31,7 +31,6 @@ struct GemmEpilogue {
   // y[which][b][h][n][dd] with rows padded to hs_dpad elements -- the head-major, 128-byte-row layout the
   // attention kernel's TMA loads want (TMA boxes that run out of bounds inside a row are ~3x slower).
   int hs_d, hs_dpad, hs_C, hs_H, hs_rows, hs_B;
-  int dbg;   // experiments: 1 = no global stores, 2 = no MMA, 4 = epilogue skipped entirely
 };
 
 template <int BN>
@@ -103,7 +102,6 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmEpilogue& ep, const u
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.f + __expf(-1.702f * f[j]));
   }
-  if (ep.dbg & 1) return;
   const bool staged = FULL && !ep.y_f32 && (ep.hs_d > 0 || ((ep.ldy & 7) == 0 && (out_col0 & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.y) & 15) == 0));   // warp-uniform
   if (!row_ok && !staged) return;
   if (ep.residual && row_ok) {
@@ -287,7 +285,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
           const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
-            if (ep.dbg & 2) break;
             // advancing 16 K-elements inside the swizzle span = +32 bytes on the start address
             umma_bf16(d_tmem, make_smem_desc_sw128(sa + k * 32), make_smem_desc_sw128(sb + k * 32), idesc,
                       (kb | k) != 0 ? 1u : 0u);
@@ -314,12 +311,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
       const int cols_here = min(BN, ep.N - n_blk * BN);                       // real columns of this tile
       const int n_chunks = geglu ? BN / 64 : (cols_here + 31) / 32;
       bool arrived = false;
-      if ((ep.dbg & 4) || half >= n_chunks) {
+      if (half >= n_chunks) {
         tc_fence_before();
         mbar_arrive(&acc_empty[buf]);
         arrived = true;
       }
-      if (!(ep.dbg & 4)) {
+      {
 #pragma unroll 1
         for (int ci = half; ci < n_chunks; ci += 2) {
           const int c0 = ci * 32;
@@ -461,11 +458,6 @@ int proj_lora_fwd(const void* x, int64_t ldx, const void* w, const void* t, int6
   ep.hs_C = (int)(hs_heads * hs_d);
   ep.hs_rows = (int)hs_rows;
   ep.hs_B = hs_rows > 0 ? (int)(M / hs_rows) : 0;
-  {
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("ADAFACE_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
-    ep.dbg = dbg;
-  }
   const int n_tiles = (int)((N + BN - 1) / BN);
   switch (BN) {
     case 64: return launch_gemm<64>(tA, tB, tA2, tB2, ep, n_tiles, stream);
