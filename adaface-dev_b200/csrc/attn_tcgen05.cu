@@ -557,7 +557,11 @@ constexpr int TQ_G = 4;                       // query tiles per CTA (bulk launc
 constexpr int TQ_ST = 3;                      // K/V ring: tiles j and j+1 are live at once, j+2 in flight
 
 // EMU = how many of every 8 exp2 pairs go to the FMA-pipe polynomial (exp2_emu2) instead of MUFU.EX2.
-template <int D, int G, int EMU>
+// SPLIT (wave tail, G = 4): the four TMEM slots hold TWO query tiles x TWO halves of the keys (slot g = tile g / 2, key
+// half g % 2); each slot runs the same online softmax over its half and the two partial results of a tile are merged
+// in the epilogue through shared memory (O = 2^(m0-m) O0 + 2^(m1-m) O1 -- the row sum rides along as column D).  A
+// tail CTA then has the full 16 softmax warps for half as long, instead of 8 warps for the whole key range.
+template <int D, int G, int EMU, bool SPLIT>
 __global__ void __launch_bounds__((4 * G + 2) * 32, 1)
 attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                              const __grid_constant__ CUtensorMap tmV, const TaParams p, const int unit0, const int H) {
@@ -566,12 +570,15 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
   constexpr int TMEM_G = 128, TMEM_O = TA_BN;                     // per tile: S/P at +0, O at +64
   static_assert(TMEM_O + DO <= TMEM_G && NA == 1 && D < DO, "quad kernel: head dim must fit 128 TMEM columns per tile and leave a pad column for the row sums");
   constexpr int kTma = 4 * G, kMma = 4 * G + 1;
+  constexpr int NQ = SPLIT ? G / 2 : G;                           // query tiles per CTA
+  constexpr int KH = SPLIT ? 2 : 1;                               // key halves (sub-tiles per ring stage)
+  static_assert(!SPLIT || G == 4, "SPLIT mode is built for four TMEM slots");
   extern __shared__ uint8_t smem_raw_tq[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_tq) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                             // [G][128][128 B]
-  uint8_t* sK = sQ + G * Cfg::Q_BYTES;                            // [ST][64][128 B]
-  uint8_t* sV = sK + ST * Cfg::K_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * Cfg::V_BYTES);
+  uint8_t* sQ = smem;                                             // [NQ][128][128 B]
+  uint8_t* sK = sQ + NQ * Cfg::Q_BYTES;                           // [ST][KH][64][128 B]
+  uint8_t* sV = sK + ST * KH * Cfg::K_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * KH * Cfg::V_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;                                   // [ST]
   uint64_t* kv_empty = kv_full + ST;                              // [ST]
@@ -583,12 +590,12 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // unit = (batch, head, block of G query tiles), linearised with the query block fastest
-  const int n_qb = (p.Lq + G * TA_BM - 1) / (G * TA_BM);
+  const int n_qb = (p.Lq + NQ * TA_BM - 1) / (NQ * TA_BM);
   const int unit = unit0 + blockIdx.x;
   const int qb = unit % n_qb, bh = unit / n_qb;
   const int h = bh % H, b = bh / H;
-  const int m0 = qb * (G * TA_BM);
-  const int n_tiles = (p.Lk + TA_BN - 1) / TA_BN;
+  const int m0 = qb * (NQ * TA_BM);
+  const int n_tiles = ((p.Lk + TA_BN - 1) / TA_BN) / KH;         // iterations; SPLIT: slot half kh covers key tiles [kh * n_tiles, ...)
 
   if (warp == kTma && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -623,14 +630,17 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
     auto issue_kv = [&](int j) {
       const int s = j % ST;
       mbar_wait(&kv_empty[s], ((j / ST) & 1) ^ 1);
-      mbar_arrive_expect_tx(&kv_full[s], Cfg::K_BYTES + Cfg::V_BYTES);
-      tma_load_4d(sK + s * Cfg::K_BYTES, &tmK, &kv_full[s], 0, h, j * TA_BN, b);
-      tma_load_4d(sV + s * Cfg::V_BYTES, &tmV, &kv_full[s], 0, h, j * TA_BN, b);
+      mbar_arrive_expect_tx(&kv_full[s], KH * (Cfg::K_BYTES + Cfg::V_BYTES));
+#pragma unroll
+      for (int kh = 0; kh < KH; ++kh) {
+        tma_load_4d(sK + (s * KH + kh) * Cfg::K_BYTES, &tmK, &kv_full[s], 0, h, (j + kh * n_tiles) * TA_BN, b);
+        tma_load_4d(sV + (s * KH + kh) * Cfg::V_BYTES, &tmV, &kv_full[s], 0, h, (j + kh * n_tiles) * TA_BN, b);
+      }
     };
     if (leader) {
-      mbar_arrive_expect_tx(q_full, G * Cfg::Q_BYTES);
+      mbar_arrive_expect_tx(q_full, NQ * Cfg::Q_BYTES);
 #pragma unroll
-      for (int g = 0; g < G; ++g) tma_load_4d(sQ + g * Cfg::Q_BYTES, &tmQ, q_full, 0, h, m0 + g * TA_BM, b);
+      for (int g = 0; g < NQ; ++g) tma_load_4d(sQ + g * Cfg::Q_BYTES, &tmQ, q_full, 0, h, m0 + g * TA_BM, b);
       issue_kv(0);
       if (n_tiles > 1) issue_kv(1);
     }
@@ -638,8 +648,8 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
       const int s = j % ST;
       mbar_wait(&kv_full[s], (j / ST) & 1);
 #pragma unroll
-      for (int r = lane; r < TA_BN; r += 32)       // 128B-swizzled tile: element D of row r sits in chunk (D/8) ^ (r & 7)
-        *reinterpret_cast<uint16_t*>(sV + s * Cfg::V_BYTES + r * 128 + ((((D >> 3) ^ (r & 7)) << 4) | ((D & 7) << 1))) = 0x3F80;
+      for (int r = lane; r < KH * TA_BN; r += 32)  // 128B-swizzled tile: element D of row r sits in chunk (D/8) ^ (r & 7)
+        *reinterpret_cast<uint16_t*>(sV + s * KH * Cfg::V_BYTES + r * 128 + ((((D >> 3) ^ (r & 7)) << 4) | ((D & 7) << 1))) = 0x3F80;
       fence_proxy_async_smem();
       __syncwarp();
       if (leader) {
@@ -657,8 +667,8 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
         const int s = j % ST;
 #pragma unroll
         for (int kk = 0; kk < KT; ++kk) {
-          const uint64_t da = make_smem_desc_sw128(aQ + g * Cfg::Q_BYTES + (kk & 3) * 32);
-          const uint64_t db = make_smem_desc_sw128(aK + s * Cfg::K_BYTES + (kk & 3) * 32);
+          const uint64_t da = make_smem_desc_sw128(aQ + (SPLIT ? g >> 1 : g) * Cfg::Q_BYTES + (kk & 3) * 32);
+          const uint64_t db = make_smem_desc_sw128(aK + (s * KH + (SPLIT ? g & 1 : 0)) * Cfg::K_BYTES + (kk & 3) * 32);
           umma_bf16(tmem_base + (uint32_t)(g * TMEM_G), da, db, idesc_qk, kk > 0 ? 1u : 0u);
         }
         umma_commit(&s_full[g]);
@@ -687,7 +697,7 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < TA_BN / 16; ++k) {
-            const uint64_t db = make_smem_desc_sw128_mn(aV + s * Cfg::V_BYTES + k * 2048, Cfg::KV_ATOM);
+            const uint64_t db = make_smem_desc_sw128_mn(aV + (s * KH + (SPLIT ? g & 1 : 0)) * Cfg::V_BYTES + k * 2048, Cfg::KV_ATOM);
             umma_bf16_ts(tmem_base + (uint32_t)(g * TMEM_G + TMEM_O), tmem_base + (uint32_t)(g * TMEM_G + k * 8), db, idesc_pv,
                          (j | k) != 0 ? 1u : 0u);
           }
@@ -705,7 +715,7 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(&s_full[g], j & 1);          // also implies P V_{j-1} of this tile has retired
       tc_fence_after();
-      const int valid = p.Lk - j * TA_BN;
+      const int valid = p.Lk - (j + (SPLIT ? (g & 1) * n_tiles : 0)) * TA_BN;
       // the 64 scores of this row are read from TMEM ONCE and stay in registers for both the max and the exp pass
       // (one CTA per SM: 112 registers per thread are available)
       uint32_t v[TA_BN];
@@ -759,33 +769,76 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
     }
     mbar_wait(o_full, 0);
     tc_fence_after();
-    float l_run;                                                   // row sum of P = column D of the accumulator
-    {
-      uint32_t v8[8];
-      tmem_ld_32x32b_x8(t_lane + (uint32_t)(TMEM_O + (D & ~7)), v8);
-      tmem_ld_wait();
-      l_run = __uint_as_float(v8[D & 7]);
-    }
-    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    const int grow = m0 + g * TA_BM + row;
-    if (p.lse && grow < p.Lq)
-      p.lse[((long long)b * H + h) * p.Lq + grow] = l_run > 0.f ? m_ref + log2f(l_run) : INFINITY;
+    const int qi = SPLIT ? g >> 1 : g;                              // query tile of this TMEM slot
+    const int grow = m0 + qi * TA_BM + row;
     bf16* orow = p.o + (long long)b * p.o_sb + (long long)grow * p.o_sn + h * D;
+    if constexpr (SPLIT) {
+      // merge the two key halves of a tile: the odd slot hands (m, O[0..DO)) to the even slot through shared memory
+      // (the K / V ring is free: every MMA has completed)
+      float* xch = reinterpret_cast<float*>(sK) + (size_t)qi * TA_BM * (DO + 1);
+      float acc[DO];
 #pragma unroll
-    for (int c = 0; c < DO / 16; ++c) {
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(t_lane + (uint32_t)(TMEM_O + c * 16), v);
-      tmem_ld_wait();
-      if (grow < p.Lq) {
+      for (int c = 0; c < DO / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_lane + (uint32_t)(TMEM_O + c * 16), v);
+        tmem_ld_wait();
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          if (c * 16 + half * 8 < D) {
+        for (int x = 0; x < 16; ++x) acc[c * 16 + x] = __uint_as_float(v[x]);
+      }
+      if (g & 1) {
+#pragma unroll
+        for (int x = 0; x < DO; ++x) xch[x * TA_BM + row] = acc[x];     // column-major: conflict-free
+        xch[DO * TA_BM + row] = m_ref;
+      }
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + qi) : "memory");
+      if (!(g & 1)) {
+        const float m1 = xch[DO * TA_BM + row];
+        const float m = fmaxf(m_ref, m1);
+        const float f0 = fast_exp2(m_ref - m), f1 = fast_exp2(m1 - m);
+#pragma unroll
+        for (int x = 0; x < DO; ++x) acc[x] = acc[x] * f0 + xch[x * TA_BM + row] * f1;
+        const float l_run = acc[D];
+        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+        if (p.lse && grow < p.Lq) p.lse[((long long)b * H + h) * p.Lq + grow] = l_run > 0.f ? m + log2f(l_run) : INFINITY;
+        if (grow < p.Lq) {
+#pragma unroll
+          for (int c8 = 0; c8 < D / 8; ++c8) {
             uint4 pk;
-            pk.x = pack_bf16(__uint_as_float(v[half * 8 + 0]) * inv, __uint_as_float(v[half * 8 + 1]) * inv);
-            pk.y = pack_bf16(__uint_as_float(v[half * 8 + 2]) * inv, __uint_as_float(v[half * 8 + 3]) * inv);
-            pk.z = pack_bf16(__uint_as_float(v[half * 8 + 4]) * inv, __uint_as_float(v[half * 8 + 5]) * inv);
-            pk.w = pack_bf16(__uint_as_float(v[half * 8 + 6]) * inv, __uint_as_float(v[half * 8 + 7]) * inv);
-            *reinterpret_cast<uint4*>(orow + c * 16 + half * 8) = pk;
+            pk.x = pack_bf16(acc[c8 * 8 + 0] * inv, acc[c8 * 8 + 1] * inv);
+            pk.y = pack_bf16(acc[c8 * 8 + 2] * inv, acc[c8 * 8 + 3] * inv);
+            pk.z = pack_bf16(acc[c8 * 8 + 4] * inv, acc[c8 * 8 + 5] * inv);
+            pk.w = pack_bf16(acc[c8 * 8 + 6] * inv, acc[c8 * 8 + 7] * inv);
+            *reinterpret_cast<uint4*>(orow + c8 * 8) = pk;
+          }
+        }
+      }
+    } else {
+      float l_run;                                                 // row sum of P = column D of the accumulator
+      {
+        uint32_t v8[8];
+        tmem_ld_32x32b_x8(t_lane + (uint32_t)(TMEM_O + (D & ~7)), v8);
+        tmem_ld_wait();
+        l_run = __uint_as_float(v8[D & 7]);
+      }
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      if (p.lse && grow < p.Lq)
+        p.lse[((long long)b * H + h) * p.Lq + grow] = l_run > 0.f ? m_ref + log2f(l_run) : INFINITY;
+#pragma unroll
+      for (int c = 0; c < DO / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_lane + (uint32_t)(TMEM_O + c * 16), v);
+        tmem_ld_wait();
+        if (grow < p.Lq) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            if (c * 16 + half * 8 < D) {
+              uint4 pk;
+              pk.x = pack_bf16(__uint_as_float(v[half * 8 + 0]) * inv, __uint_as_float(v[half * 8 + 1]) * inv);
+              pk.y = pack_bf16(__uint_as_float(v[half * 8 + 2]) * inv, __uint_as_float(v[half * 8 + 3]) * inv);
+              pk.z = pack_bf16(__uint_as_float(v[half * 8 + 4]) * inv, __uint_as_float(v[half * 8 + 5]) * inv);
+              pk.w = pack_bf16(__uint_as_float(v[half * 8 + 6]) * inv, __uint_as_float(v[half * 8 + 7]) * inv);
+              *reinterpret_cast<uint4*>(orow + c * 16 + half * 8) = pk;
+            }
           }
         }
       }
@@ -807,24 +860,36 @@ static int launch_ta_quad(const CUtensorMap& tQ, const CUtensorMap& tK, const CU
   using Cfg = TaCfg<D>;
   constexpr int smem4 = 4 * Cfg::Q_BYTES + TQ_ST * (Cfg::K_BYTES + Cfg::V_BYTES) + 1024 + 256;
   constexpr int smem2 = 2 * Cfg::Q_BYTES + TQ_ST * (Cfg::K_BYTES + Cfg::V_BYTES) + 1024 + 256;
+  constexpr int smemS = 2 * Cfg::Q_BYTES + TQ_ST * 2 * (Cfg::K_BYTES + Cfg::V_BYTES) + 1024 + 256;
+  static_assert(2 * TA_BM * (Cfg::DO + 1) * 4 <= TQ_ST * 2 * (Cfg::K_BYTES + Cfg::V_BYTES), "SPLIT merge scratch must fit the K/V ring");
   static bool configured = false;
   if (!configured) {
-    AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 4, EMU>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
-    AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 2, EMU>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 4, EMU, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+    AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 2, EMU, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 4, EMU, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smemS));
     configured = true;
+  }
+  static int tail_mode = -1;
+  if (tail_mode < 0) {
+    const char* e = getenv("ADAFACE_QUAD_TAIL");     // 1 (default): two tiles x two key halves per tail CTA; 2: two-tile CTAs
+    tail_mode = (e && e[0] == '2') ? 2 : 1;
   }
   const int n_sm = 148;
   const int n_qb4 = (p.Lq + 4 * TA_BM - 1) / (4 * TA_BM);
   const int units4 = B * H * n_qb4;
+  const int n_ktiles = (p.Lk + TA_BN - 1) / TA_BN;
   // bulk: whole rounds of four-tile CTAs; tail: the rest as two-tile CTAs (only when Lq splits evenly into them)
   int bulk = (units4 / n_sm) * n_sm;
   if (p.Lq % (4 * TA_BM) != 0 || bulk == 0) bulk = units4;
   if (bulk > 0) {
-    AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_quad_kernel<D, 4, EMU>, dim3(bulk), dim3(18 * 32), smem4, stream, tQ, tK, tV, p, 0, H));
+    AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_quad_kernel<D, 4, EMU, false>, dim3(bulk), dim3(18 * 32), smem4, stream, tQ, tK, tV, p, 0, H));
     ++g_launch_count;
   }
   if (units4 > bulk) {
-    AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_quad_kernel<D, 2, EMU>, dim3(2 * (units4 - bulk)), dim3(10 * 32), smem2, stream, tQ, tK, tV, p, 2 * bulk, H));
+    if (tail_mode == 1 && n_ktiles % 2 == 0 && p.Lk % TA_BN == 0)
+      AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_quad_kernel<D, 4, EMU, true>, dim3(2 * (units4 - bulk)), dim3(18 * 32), smemS, stream, tQ, tK, tV, p, 2 * bulk, H));
+    else
+      AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_quad_kernel<D, 2, EMU, false>, dim3(2 * (units4 - bulk)), dim3(10 * 32), smem2, stream, tQ, tK, tV, p, 2 * bulk, H));
     ++g_launch_count;
   }
   AF_CUDA(cudaGetLastError());

@@ -133,6 +133,25 @@ def test_attention(d, Lq, Lk):
     assert maxerr(o, ref) < 2e-2
 
 
+@pytest.mark.parametrize("B,Lq,Lk", [(5, 2048, 2048), (5, 2048, 1111), (3, 4096, 4096)])
+def test_attention_quad_wave_tail(B, Lq, Lk):
+    """More (batch, head, 512-query) units than SMs: the four-tile kernel runs whole waves and hands the remainder to its
+    tail launch -- two tiles x two key halves merged in the epilogue (even number of full key tiles) or two-tile CTAs
+    (ragged keys).  Also checks the log-sum-exp the training path keeps."""
+    import math
+    H, d = 8, 40
+    C = H * d
+    qkv = rnd(B, max(Lq, Lk), 3 * C, seed=7)
+    q, k, v = qkv[:, :Lq, :C], qkv[:, :Lk, C:2 * C], qkv[:, :Lk, 2 * C:]
+    lse = torch.empty(B, H, Lq, device="cuda")
+    o = ops().attention(q, k, v, H, d ** -0.5, lse=lse)
+    hd = lambda t: t.float().reshape(B, -1, H, d).transpose(1, 2)
+    ref = torch.nn.functional.scaled_dot_product_attention(hd(q), hd(k), hd(v)).transpose(1, 2).reshape(B, Lq, C)
+    assert (o.float() - ref).abs().max().item() < 2e-2
+    rlse = torch.logsumexp(hd(q) @ hd(k).transpose(-1, -2) * d ** -0.5, dim=-1) * math.log2(math.e)
+    assert (lse - rlse).abs().max().item() < 2e-2
+
+
 def test_attention_fused_qkv_views_and_key_mask():
     B, N, H, d = 2, 320, 8, 40
     C = H * d
