@@ -388,57 +388,73 @@ def main_gpu(args):
 
         # ---- end to end: host buffers in, host results out, through the same public operator.
         # The step is cut into independent units (levels D, C, B, A -- the four levels of the stack do not depend on each
-        # other; level A can further be cut into batch slices, samples being independent), each its own CUDA
-        # graph.  Three streams: H2D of unit i+1 and D2H of unit i-1 overlap the kernels of unit i; the small levels go
+        # other), each its own CUDA graph.  Three streams: H2D of unit i+1 and D2H of unit i-1 overlap the kernels of unit i; the small levels go
         # first so that level A's 21 MB input is in flight behind them.  Exposed: the first unit's H2D and the last D2H.
-        a_split = int(os.environ.get("ADAFACE_BENCH_A_SPLIT", "1"))     # level A in this many batch slices (1 / 2 measured equal: 4.14 / 4.18 ms)
-        step_b = BATCH // a_split
-        units = [(3, slice(0, BATCH)), (2, slice(0, BATCH)), (1, slice(0, BATCH))] + \
-                [(0, slice(i * step_b, (i + 1) * step_b)) for i in range(a_split)]
-        unit_fns, unit_in, unit_out = [], [], []
+        # Level A's 21 MB output would otherwise only start its D2H after the whole level: its LAST block is run per batch
+        # slice (samples are independent), so each slice's D2H overlaps the next slice's kernels.
+        tail_split = int(os.environ.get("ADAFACE_BENCH_A_TAIL_SPLIT", "4"))     # measured: off 3.51 ms, 2: 3.43 ms, 4: 3.41 ms
+        specs = [dict(blocks=mods[li], li=li, sl=slice(0, BATCH), up=None, out=True) for li in (3, 2, 1)]
+        if tail_split > 1 and len(mods[0]) > 1:
+            specs.append(dict(blocks=mods[0][:-1], li=0, sl=slice(0, BATCH), up=None, out=False))
+            sb = BATCH // tail_split
+            specs += [dict(blocks=mods[0][-1:], li=0, sl=slice(i * sb, (i + 1) * sb), up=3, out=True) for i in range(tail_split)]
+        else:
+            specs.append(dict(blocks=mods[0], li=0, sl=slice(0, BATCH), up=None, out=True))
         prev_pdl = a._lib.set_pdl(int(os.environ.get("ADAFACE_BENCH_E2E_PDL", "3")))   # programmatic dependent launch mask inside the unit graphs
-        for li, sl in units:
-            x_u, c_u = xs[li][sl].contiguous(), ctx[sl].contiguous()
-            if use_graph:
-                fn = a.graphed(lambda x_, c_, li=li: run_stack([mods[li]], [x_], c_)[0], x_u, c_u)
-            else:
-                fn = lambda x_, c_, li=li: run_stack([mods[li]], [x_], c_)[0]
-            unit_fns.append(fn)
-            unit_in.append((xs_pin[li][sl], ctx_pin[sl]))
-            unit_out.append(torch.empty(x_u.shape, dtype=torch.bfloat16).pin_memory())
+        units = []
+        for sp in specs:
+            u = dict(sp)
+            if sp["up"] is None:
+                x_u, c_u = xs[sp["li"]][sp["sl"]].contiguous(), ctx[sp["sl"]].contiguous()
+                u["host_in"] = (xs_pin[sp["li"]][sp["sl"]], ctx_pin[sp["sl"]])
+            else:                                   # chained unit: its input is (a batch slice of) an earlier unit's output
+                up = units[sp["up"]]
+                x_u, c_u = up["dev_out"][sp["sl"]].contiguous(), up["dev_in"][1][sp["sl"]].contiguous()
+                u["host_in"] = None
+            body = (lambda x_, c_, blocks=sp["blocks"]: run_stack([blocks], [x_], c_)[0])
+            u["fn"] = a.graphed(body, x_u, c_u) if use_graph else body
+            u["dev_in"] = tuple(u["fn"].static_inputs[:2]) if use_graph else (torch.empty_like(x_u), torch.empty_like(c_u))
+            u["dev_out"] = u["fn"](*u["dev_in"]) if use_graph else torch.empty_like(x_u)      # graphs return their static output
+            u["host_out"] = torch.empty(x_u.shape, dtype=torch.bfloat16).pin_memory() if sp["out"] else None
+            units.append(u)
         a._lib.set_pdl(prev_pdl)
-        h2d = sum(x.numel() * 2 + c.numel() * 2 for x, c in unit_in)
-        d2h = sum(o.numel() * 2 for o in unit_out)
+        h2d = sum(x.numel() * 2 + c.numel() * 2 for x, c in (u["host_in"] for u in units if u["host_in"] is not None))
+        d2h = sum(u["host_out"].numel() * 2 for u in units if u["host_out"] is not None)
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
         comp = torch.cuda.current_stream()
-        dev_in = [(fn.static_inputs[0], fn.static_inputs[1]) if use_graph else
-                  (torch.empty_like(x, device=dev), torch.empty_like(c, device=dev)) for fn, (x, c) in zip(unit_fns, unit_in)]
+        torch.cuda.synchronize()
 
         diag_nocopy = os.environ.get("ADAFACE_BENCH_E2E_NOCOPY") == "1"     # diagnosis only: unit graphs without the copies
 
         def e2e_step():
-            if diag_nocopy:
-                for fn, (xd, cd) in zip(unit_fns, dev_in):
-                    fn(xd, cd)
-                return
             s_in.wait_stream(comp)          # the previous step has finished reading the input buffers
-            ev_in, ev_out = [], []
-            with torch.cuda.stream(s_in):
-                for (xd, cd), (xh, ch) in zip(dev_in, unit_in):
-                    xd.copy_(xh, non_blocking=True)
-                    cd.copy_(ch, non_blocking=True)
-                    ev_in.append(torch.cuda.Event())
-                    ev_in[-1].record(s_in)
-            outs = []
-            for fn, (xd, cd), ei in zip(unit_fns, dev_in, ev_in):
-                comp.wait_event(ei)
-                outs.append(fn(xd, cd))     # graph replay (inputs already in the graph's buffers) or eager launches
-                ev_out.append(torch.cuda.Event())
-                ev_out[-1].record(comp)
+            ev_in = {}
+            if not diag_nocopy:
+                with torch.cuda.stream(s_in):
+                    for ui, u in enumerate(units):
+                        if u["host_in"] is not None:
+                            u["dev_in"][0].copy_(u["host_in"][0], non_blocking=True)
+                            u["dev_in"][1].copy_(u["host_in"][1], non_blocking=True)
+                            ev_in[ui] = torch.cuda.Event()
+                            ev_in[ui].record(s_in)
+            done = []
+            for ui, u in enumerate(units):
+                if ui in ev_in:
+                    comp.wait_event(ev_in[ui])
+                if u["up"] is None:
+                    out = u["fn"](*u["dev_in"])          # graph replay (inputs already in the graph's buffers) or eager launches
+                else:                                    # device-to-device hand-over of the upstream unit's output slice
+                    up = units[u["up"]]
+                    out = u["fn"](up["cur_out"][u["sl"]], up["dev_in"][1][u["sl"]])
+                u["cur_out"] = out
+                if u["host_out"] is not None and not diag_nocopy:
+                    ev = torch.cuda.Event()
+                    ev.record(comp)
+                    done.append((u, out, ev))
             with torch.cuda.stream(s_out):
-                for oh, o, eo in zip(unit_out, outs, ev_out):
-                    s_out.wait_event(eo)
-                    oh.copy_(o, non_blocking=True)
+                for u, out, ev in done:
+                    s_out.wait_event(ev)
+                    u["host_out"].copy_(out, non_blocking=True)
             comp.wait_stream(s_out)         # the closing event on `comp` then covers the last D2H
 
         e2e_step()
@@ -503,7 +519,7 @@ def main_gpu(args):
             "frac_of_bf16_peak": value / world / pk["bf16_tflops_sustained"],
             "e2e": {"value": world * fl_step / (t_e2e_ms * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e_ms,
-                    "how": f"{3 + a_split} units (levels D, C, B, {a_split} batch slices of A), one CUDA graph each; H2D / kernels / D2H on three streams"},
+                    "how": f"{len(units)} CUDA-graph units (levels D, C, B, A; the last level-A block per batch slice so that its D2H overlaps); H2D / kernels / D2H on three streams"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "attn_fwd_tcgen05_quad_kernel<40> (level-A self-attention core, B=8, 4096 tok, 8x40; bulk + tail launch)",
