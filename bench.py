@@ -225,7 +225,7 @@ def build_stack(torch, a, device):
 LAUNCHES_PER_STEP = 16 * 7 + 5      # + the tail launch of the 5 level-A self-attention calls
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel, from the ncu --set full capture
 # summarised in profiles/r01_ncu_full_attn_quad.txt (algorithmic: 4 * B * N * C * 2 = 83.9 MB; the 21 MB of output leave L2 after the kernel)
-ROOFLINE_TRAFFIC_BYTES = 65696768   # 64.4 MB read + 1.3 MB written inside the two launches (outputs are still in L2)
+ROOFLINE_TRAFFIC_BYTES = 66132224   # 64.4 MB read + 1.7 MB written inside the two launches (outputs are still in L2)
 
 
 def run_stack(mods, xs, ctx):
