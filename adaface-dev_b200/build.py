@@ -34,6 +34,12 @@ def _compile(nvcc, src, verbose):
 
 def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a.  Returns the path of the shared library."""
+    if not force and os.path.exists(LIB):
+        # fast path (e.g. on the GPU box, where the library arrives prebuilt and the object directory does not travel):
+        # nothing to do when the library is newer than every source and header
+        deps = [os.path.join(CSRC, f) for f in SOURCES] + _headers()
+        if all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
+            return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ, exist_ok=True)
     if force:
