@@ -32,6 +32,12 @@ SIGNATURES = {
     "adaface_sbg_head_fwd": [_p, _p, _p, _p, _c.POINTER(_f32), _i32, _i64, _p, _p, _p, _i64, _i64, _i64, _f32, _p],
     "adaface_groupnorm_tokens_fwd": [_p, _i32, _p, _p, _i64, _i64, _i64, _i64, _f32, _p, _p, _p, _p],
     "adaface_tokens_to_nchw_add": [_p, _p, _i32, _p, _i64, _i64, _i64, _p],
+    "adaface_conv3x3_fwd": [_p, _i64, _i64, _i64, _i64, _p, _p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _i32, _p, _i64, _i32, _i64,
+                            _i32, _i32, _p],
+    "adaface_groupnorm_act_tokens_fwd": [_p, _p, _p, _i64, _i64, _i64, _i64, _f32, _i32, _p, _p, _p, _p, _p],
+    "adaface_groupnorm_act_tokens_ws_floats": [_i64, _i64, _i64],
+    "adaface_silu_fwd": [_p, _i32, _p, _i64, _p],
+    "adaface_upsample2x_tokens": [_p, _p, _i64, _i64, _i64, _i64, _p],
     # ---- backward (ABI v2)
     "adaface_attn_bwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _p,
                          _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _i32, _f32, _p],
@@ -49,7 +55,7 @@ SIGNATURES = {
 }
 # entry points that return a value instead of a status
 VALUE_RETURNING = ("adaface_version", "adaface_last_error", "adaface_launch_count", "adaface_set_pdl",
-                   "adaface_attn_cross_capture_bwd_chunks")
+                   "adaface_attn_cross_capture_bwd_chunks", "adaface_groupnorm_act_tokens_ws_floats")
 
 _lib = None
 
@@ -70,6 +76,7 @@ def load():
         fn.restype = _c.c_int
     lib.adaface_last_error.restype = _c.c_char_p
     lib.adaface_launch_count.restype = _c.c_int64
+    lib.adaface_groupnorm_act_tokens_ws_floats.restype = _c.c_int64
     _lib = lib
     return lib
 

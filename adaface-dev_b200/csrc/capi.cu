@@ -89,6 +89,28 @@ int make_tmap_bf16_heads(CUtensorMap* out, const void* base, uint64_t d, uint64_
   return 0;
 }
 
+int make_tmap_bf16_nhwc(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint64_t sw,
+                        uint64_t sh, uint64_t sb, uint32_t box_w, uint32_t box_h, uint32_t box_b) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return 1;
+  }
+  cuuint64_t gdim[4] = {C, W, H, B};
+  cuuint64_t gstride[3] = {sw * 2, sh * 2, sb * 2};
+  cuuint32_t box[4] = {64, box_w, box_h, box_b};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(NHWC) failed (%d): base=%p C=%llu W=%llu H=%llu B=%llu box=%ux%ux%u", (int)r, base,
+              (unsigned long long)C, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B, box_w, box_h, box_b);
+    return 1;
+  }
+  return 0;
+}
+
 int proj_lora_fwd(const void*, int64_t, const void*, const void*, int64_t, const void*, const float*, const float*,
                   const void*, int64_t, int, void*, int64_t, int, int64_t, int64_t, int64_t, int64_t, int, int64_t, int64_t,
                   int64_t, int64_t, cudaStream_t);
@@ -127,6 +149,13 @@ int sbg_head_fwd(const float*, const float*, const float*, const float*, const f
 int groupnorm_tokens_fwd(const void*, int, const float*, const float*, int64_t, int64_t, int64_t, int64_t, float, float*, float*,
                          void*, cudaStream_t);
 int tokens_to_nchw_add(const void*, const void*, int, void*, int64_t, int64_t, int64_t, cudaStream_t);
+int conv3x3_fwd(const void*, int64_t, int64_t, int64_t, int64_t, const void*, const void*, int64_t, const void*, int64_t, const float*,
+                const float*, const float*, const void*, int64_t, int, void*, int64_t, int, int64_t, int, int, cudaStream_t);
+int groupnorm_act_tokens_fwd(const void*, const float*, const float*, int64_t, int64_t, int64_t, int64_t, float, int, float*, float*,
+                             float*, void*, cudaStream_t);
+int64_t groupnorm_act_tokens_ws_floats(int64_t, int64_t, int64_t);
+int silu_fwd(const void*, int, void*, int64_t, cudaStream_t);
+int upsample2x_tokens(const void*, void*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
 
 }  // namespace adaface
 
@@ -212,6 +241,27 @@ int adaface_sbg_head_fwd(const float* h0, const float* h1, const float* h2, cons
 int adaface_groupnorm_tokens_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, int64_t B, int64_t C,
                                  int64_t HW, int64_t groups, float eps, float* a_ws, float* s_ws, void* y, void* stream) {
   return groupnorm_tokens_fwd(x, x_dtype, gamma, beta, B, C, HW, groups, eps, a_ws, s_ws, y, (cudaStream_t)stream);
+}
+
+int adaface_conv3x3_fwd(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, const void* w, const void* t, int64_t ldt,
+                        const void* bs, int64_t R, const float* colscale, const float* bias, const float* rowbias,
+                        const void* residual, int64_t ldr, int residual_dtype, void* y, int64_t ldy, int y_dtype, int64_t Cout,
+                        int stride, int act, void* stream) {
+  return conv3x3_fwd(x, B, H, W, Cin, w, t, ldt, bs, R, colscale, bias, rowbias, residual, ldr, residual_dtype, y, ldy, y_dtype, Cout,
+                     stride, act, (cudaStream_t)stream);
+}
+
+int adaface_groupnorm_act_tokens_fwd(const void* x, const float* gamma, const float* beta, int64_t B, int64_t HW, int64_t C,
+                                     int64_t groups, float eps, int act, float* part_ws, float* a_ws, float* s_ws, void* y,
+                                     void* stream) {
+  return groupnorm_act_tokens_fwd(x, gamma, beta, B, HW, C, groups, eps, act, part_ws, a_ws, s_ws, y, (cudaStream_t)stream);
+}
+int64_t adaface_groupnorm_act_tokens_ws_floats(int64_t B, int64_t HW, int64_t groups) {
+  return groupnorm_act_tokens_ws_floats(B, HW, groups);
+}
+int adaface_silu_fwd(const void* x, int x_dtype, void* y, int64_t n, void* stream) { return silu_fwd(x, x_dtype, y, n, (cudaStream_t)stream); }
+int adaface_upsample2x_tokens(const void* x, void* y, int64_t B, int64_t H, int64_t W, int64_t C, void* stream) {
+  return upsample2x_tokens(x, y, B, H, W, C, (cudaStream_t)stream);
 }
 
 int adaface_tokens_to_nchw_add(const void* t, const void* x_in, int x_dtype, void* out, int64_t B, int64_t C, int64_t HW,

@@ -44,6 +44,12 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int make_tmap_bf16_heads(CUtensorMap* out, const void* base, uint64_t d, uint64_t heads, uint64_t L, uint64_t B,
                          uint64_t sh, uint64_t sn, uint64_t sb, uint32_t box_rows);
 
+// 4-D view {C, W, H, B} of an NHWC bf16 activation (element strides sw / sh / sb, so that a stride-2 parity view is the
+// same call) with a {64, box_w, box_h, box_b} box and 128-byte swizzle: the A operand of the implicit-GEMM convolution.
+// Coordinates may be negative / run past W, H: those pixels are zero-filled, which is the convolution's padding.
+int make_tmap_bf16_nhwc(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint64_t sw,
+                        uint64_t sh, uint64_t sb, uint32_t box_w, uint32_t box_h, uint32_t box_b);
+
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

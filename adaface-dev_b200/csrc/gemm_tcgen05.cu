@@ -31,6 +31,31 @@ struct GemmEpilogue {
   // y[which][b][h][n][dd] with rows padded to hs_dpad elements -- the head-major, 128-byte-row layout the
   // attention kernel's TMA loads want (TMA boxes that run out of bounds inside a row are ~3x slower).
   int hs_d, hs_dpad, hs_C, hs_H, hs_rows, hs_B;
+  // implicit-GEMM 3x3 convolution (CONV instantiation only): the A operand is the NHWC activation itself, one TMA box
+  // of `cv_tile_rows` output pixels (whole image rows) per (tap, 64-channel chunk), shifted by the tap offset; the zero
+  // padding of the convolution is TMA's out-of-bounds fill.
+  int cv_kc;          // 64-channel chunks per tap (K loop = 9 taps x cv_kc)
+  int cv_W, cv_HW;    // OUTPUT width, pixels per output image
+  int cv_img_rows;    // output pixels of one image covered by a tile (W * image rows per tile)
+  int cv_tpi;         // tiles per image (cv_imgs == 1)
+  int cv_imgs;        // images per tile (> 1 only when a whole image is smaller than 128 pixels)
+  int cv_stride;      // 1 | 2
+  int num_m;          // number of M tiles (GEMM: ceil(M / 128))
+  const float* rowbias;   // fp32 [images, N] added per output image (the ResBlock's time-embedding term), or NULL
+};
+
+// Tensor maps of the CONV A operand: one for stride 1; one per input parity (py, px) for stride 2.
+struct ConvMaps {
+  CUtensorMap m[4];
+};
+struct NoConvMaps {};
+template <bool CONV>
+struct ConvArg {
+  using type = NoConvMaps;
+};
+template <>
+struct ConvArg<true> {
+  using type = ConvMaps;
 };
 
 template <int BN>
@@ -67,7 +92,8 @@ __device__ __forceinline__ uint4 unstage_piece(const uint8_t* slab, int r, int p
 
 template <int BN, bool FULL>
 __device__ __forceinline__ void epilogue_chunk32(const GemmEpilogue& ep, const uint32_t (&v)[32], const uint32_t (&g)[32], int row,
-                                                 bool row_ok, int n_blk, int c0, uint8_t* slab, int lane) {
+                                                 bool row_ok, int row_end, const float* rowbias, int n_blk, int c0, uint8_t* slab,
+                                                 int lane) {
   const int n0 = n_blk * BN;
   const bool geglu = ep.act == ADAFACE_ACT_GEGLU;
   const int col0 = n0 + c0;
@@ -87,6 +113,11 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmEpilogue& ep, const u
     }
   };
   affine(f, col0);
+  if (rowbias) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (FULL || col0 + j < ep.N) f[j] += __ldg(rowbias + col0 + j);
+  }
   int out_col0 = col0;
   int out_n = ep.N;
   if (geglu) {
@@ -143,7 +174,7 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmEpilogue& ep, const u
     for (int i = 0; i < 4; ++i) {
       const int r = i * 8 + (lane >> 2);
       const int grow = row_base + r;
-      if (grow < ep.M) {
+      if (grow < row_end) {
         bf16* dst;
         if (ep.hs_d > 0) {
           const int bb = grow / ep.hs_rows, nn = grow - bb * ep.hs_rows;
@@ -194,11 +225,19 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmEpilogue& ep, const u
 //   warp 8     TMA producer: 64-wide K slabs of X/W (then of T/Bs: the rank-R LoRA tail continues the same
 //              accumulation) into a STAGES-deep 128B-swizzled ring that runs across tile boundaries.
 //   warp 9     TMEM allocator + the single thread that issues tcgen05.mma (M=128, N=BN, K=16).
-template <int BN>
+//
+// CONV = implicit-GEMM 3x3 convolution over an NHWC activation (openaimodel.py:164-277 ResBlock / Downsample / Upsample
+// convolutions): M = output pixels, N = output channels, K = 9 taps x input channels.  Only the
+// producer differs: the A stage of (tap, chunk) is a 4-D TMA box {64 channels, W, image rows, images} of the activation
+// displaced by the tap offset -- rows / columns outside the image arrive as zeros (the padding) -- and lands in shared
+// memory exactly like a [128, 64] K-major tile, so the MMA and epilogue code is the GEMM's.  A stride-2 convolution
+// reads through four tensor maps, one per input parity (y & 1, x & 1), each a stride-2 view of the activation.
+template <int BN, bool CONV>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                            const __grid_constant__ CUtensorMap tmB,
                                                                            const __grid_constant__ CUtensorMap tmA2,
                                                                            const __grid_constant__ CUtensorMap tmB2,
+                                                                           const __grid_constant__ typename ConvArg<CONV>::type cmaps,
                                                                            const GemmEpilogue ep) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -217,7 +256,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
   const int lane = threadIdx.x & 31;
   const int num_kb = ep.num_kb1 + ep.num_kb2;
   const int num_n = (ep.N + BN - 1) / BN;
-  const int num_tiles = ((ep.M + GEMM_BM - 1) / GEMM_BM) * num_n;
+  const int num_tiles = ep.num_m * num_n;
 
   if (warp == kTma && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -250,12 +289,42 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
     if (elect_one()) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * GEMM_BM, n0 = (tile % num_n) * BN;
+        const int m_blk = tile / num_n, n0 = (tile % num_n) * BN;
+        int m0 = m_blk * GEMM_BM, img0 = 0, y0 = 0;
+        if constexpr (CONV) {
+          if (ep.cv_imgs > 1) {
+            img0 = m_blk * ep.cv_imgs;
+            m0 = img0 * ep.cv_HW;
+          } else {
+            img0 = m_blk / ep.cv_tpi;
+            const int yc = m_blk - img0 * ep.cv_tpi;
+            y0 = yc * (ep.cv_img_rows / ep.cv_W);
+            m0 = img0 * ep.cv_HW + yc * ep.cv_img_rows;
+          }
+        }
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
           uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
+          if (CONV && kb < ep.num_kb1) {
+            if constexpr (CONV) {
+              // the A box holds cv_img_rows * cv_imgs pixels x 128 bytes (zero-filled parts included)
+              mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(ep.cv_img_rows * ep.cv_imgs * 128 + Cfg::B_STAGE_BYTES));
+              const int tap = kb / ep.cv_kc, ch = kb - tap * ep.cv_kc;
+              const int ky = tap / 3, kx = tap - ky * 3;
+              if (ep.cv_stride == 1) {
+                tma_load_4d(sa, &cmaps.m[0], &full_bar[s], ch * GEMM_BK, kx - 1, y0 + ky - 1, img0);
+              } else {
+                // input (2 y + ky - 1, 2 x + kx - 1): parity 1 / index -1 for k = 0, parity 0 / index 0 for k = 1,
+                // parity 1 / index 0 for k = 2
+                const int py = ky != 1, px = kx != 1;
+                tma_load_4d(sa, &cmaps.m[py * 2 + px], &full_bar[s], ch * GEMM_BK, kx == 0 ? -1 : 0, y0 + (ky == 0 ? -1 : 0), img0);
+              }
+              tma_load_2d(sb, &tmB, &full_bar[s], kb * GEMM_BK, n0);
+            }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           if (kb < ep.num_kb1) {
             tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0);
@@ -303,8 +372,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const uint32_t buf = t & 1;
       const int m_blk = tile / num_n, n_blk = tile % num_n;
-      const int row = m_blk * GEMM_BM + q * 32 + lane;
-      const bool row_ok = row < ep.M;
+      int row = m_blk * GEMM_BM + q * 32 + lane;
+      int row_end = ep.M;
+      const float* rowbias = nullptr;
+      if constexpr (CONV) {
+        int base;
+        if (ep.cv_imgs > 1) {
+          base = m_blk * ep.cv_imgs * ep.cv_HW;
+          row_end = min(ep.M, base + ep.cv_imgs * ep.cv_HW);
+        } else {
+          const int img = m_blk / ep.cv_tpi, yc = m_blk - img * ep.cv_tpi;
+          base = img * ep.cv_HW + yc * ep.cv_img_rows;
+          row_end = min((img + 1) * ep.cv_HW, base + ep.cv_img_rows);
+        }
+        row = base + q * 32 + lane;
+        if (ep.rowbias) rowbias = ep.rowbias + (long long)(min(row, ep.M - 1) / ep.cv_HW) * ep.N;
+      }
+      const bool row_ok = row < row_end;
       mbar_wait(&acc_full[buf], (t >> 1) & 1);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
@@ -330,8 +414,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
             arrived = true;
           }
           const bool full = geglu || (n_blk * BN + c0 + 32 <= ep.N);
-          if (full) epilogue_chunk32<BN, true>(ep, v, g, row, row_ok, n_blk, c0, store_stage + warp * 2048, lane);
-          else epilogue_chunk32<BN, false>(ep, v, g, row, row_ok, n_blk, c0, store_stage + warp * 2048, lane);
+          if (full) epilogue_chunk32<BN, true>(ep, v, g, row, row_ok, row_end, rowbias, n_blk, c0, store_stage + warp * 2048, lane);
+          else epilogue_chunk32<BN, false>(ep, v, g, row, row_ok, row_end, rowbias, n_blk, c0, store_stage + warp * 2048, lane);
         }
       }
     }
@@ -348,13 +432,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
 // ---------------------------------------------------------------------------------------------
 extern long long g_launch_count;
 
-template <int BN>
+template <int BN, bool CONV = false>
 static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tA2, const CUtensorMap& tB2,
-                       const GemmEpilogue& ep, int n_tiles, cudaStream_t stream) {
+                       const GemmEpilogue& ep, int n_tiles, cudaStream_t stream,
+                       const typename ConvArg<CONV>::type& cmaps = typename ConvArg<CONV>::type()) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    AF_CUDA(cudaFuncSetAttribute(gemm_tn_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    AF_CUDA(cudaFuncSetAttribute(gemm_tn_tcgen05_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg::SMEM_BYTES));
     configured = true;
   }
@@ -364,12 +449,41 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     AF_CUDA(cudaGetDevice(&dev));
     AF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int tiles = n_tiles * ((ep.M + GEMM_BM - 1) / GEMM_BM);
+  const int tiles = n_tiles * ep.num_m;
   dim3 grid(tiles < num_sms ? tiles : num_sms);
-  AF_CUDA(launch_pdl(1, gemm_tn_tcgen05_kernel<BN>, grid, dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tA, tB, tA2, tB2, ep));
+  AF_CUDA(launch_pdl(1, gemm_tn_tcgen05_kernel<BN, CONV>, grid, dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tA, tB, tA2, tB2, cmaps, ep));
   AF_CUDA(cudaGetLastError());
   ++g_launch_count;
   return 0;
+}
+
+// Tile width: the widest of {256, 192, 160, 128, 64} that wastes no column and still gives every SM a tile.
+static int pick_tile_width(long long N, long long m_tiles, int act) {
+  int BN;
+  if (act == ADAFACE_ACT_GEGLU) {
+    BN = 128;
+  } else {
+    BN = 0;
+    // cost model: rounds over the 148 SMs x (tile width + fixed per-tile overhead); exact divisors of N only
+    const int cand[5] = {256, 192, 160, 128, 64};
+    long long best = -1;
+    for (int i = 0; i < 5; ++i) {
+      if (N % cand[i]) continue;
+      const long long tiles = m_tiles * (N / cand[i]);
+      const long long cost = ((tiles + 147) / 148) * (cand[i] + 64);
+      if (best < 0 || cost < best) { best = cost; BN = cand[i]; }
+    }
+    if (!BN) BN = (N <= 64 || N % 128 <= 64) && N < 256 ? 64 : 128;   // ragged N: masked last tile
+  }
+  {
+    static int force_bn = -1;
+    if (force_bn < 0) {
+      const char* e = getenv("ADAFACE_GEMM_BN");     // tuning knob: force the tile width (64 / 128 / 160)
+      force_bn = e ? atoi(e) : 0;
+    }
+    if (force_bn && act != ADAFACE_ACT_GEGLU) BN = force_bn;
+  }
+  return BN;
 }
 
 int proj_lora_fwd(const void* x, int64_t ldx, const void* w, const void* t, int64_t ldt, const void* bs,
@@ -401,33 +515,10 @@ int proj_lora_fwd(const void* x, int64_t ldx, const void* w, const void* t, int6
   }
   AF_CHECK(M < (1ll << 31) && N < (1ll << 31), "proj_lora_fwd: M/N too large");
 
-  // Tile width: the widest of {256, 192, 160, 128, 64} that wastes no column and still gives every SM a tile.
-  int BN;
   const long long m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
-  if (act == ADAFACE_ACT_GEGLU) {
+  if (act == ADAFACE_ACT_GEGLU)
     AF_CHECK(N % 128 == 0, "proj_lora_fwd: GEGLU needs N %% 128 == 0 (packed [a|g] tiles), got %lld", (long long)N);
-    BN = 128;
-  } else {
-    BN = 0;
-    // cost model: rounds over the 148 SMs x (tile width + fixed per-tile overhead); exact divisors of N only
-    const int cand[5] = {256, 192, 160, 128, 64};
-    long long best = -1;
-    for (int i = 0; i < 5; ++i) {
-      if (N % cand[i]) continue;
-      const long long tiles = m_tiles * (N / cand[i]);
-      const long long cost = ((tiles + 147) / 148) * (cand[i] + 64);
-      if (best < 0 || cost < best) { best = cost; BN = cand[i]; }
-    }
-    if (!BN) BN = (N <= 64 || N % 128 <= 64) && N < 256 ? 64 : 128;   // ragged N: masked last tile
-  }
-  {
-    static int force_bn = -1;
-    if (force_bn < 0) {
-      const char* e = getenv("ADAFACE_GEMM_BN");     // tuning knob: force the tile width (64 / 128 / 160)
-      force_bn = e ? atoi(e) : 0;
-    }
-    if (force_bn && act != ADAFACE_ACT_GEGLU) BN = force_bn;
-  }
+  const int BN = pick_tile_width(N, m_tiles, act);
   CUtensorMap tA, tB, tA2, tB2;
   if (make_tmap_bf16_2d(&tA, x, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, GEMM_BM)) return 3;
   if (make_tmap_bf16_2d(&tB, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)BN)) return 3;
@@ -458,6 +549,9 @@ int proj_lora_fwd(const void* x, int64_t ldx, const void* w, const void* t, int6
   ep.hs_C = (int)(hs_heads * hs_d);
   ep.hs_rows = (int)hs_rows;
   ep.hs_B = hs_rows > 0 ? (int)(M / hs_rows) : 0;
+  ep.cv_kc = ep.cv_W = ep.cv_HW = ep.cv_img_rows = ep.cv_tpi = ep.cv_imgs = ep.cv_stride = 0;
+  ep.num_m = (int)m_tiles;
+  ep.rowbias = nullptr;
   const int n_tiles = (int)((N + BN - 1) / BN);
   switch (BN) {
     case 64: return launch_gemm<64>(tA, tB, tA2, tB2, ep, n_tiles, stream);
@@ -467,6 +561,102 @@ int proj_lora_fwd(const void* x, int64_t ldx, const void* w, const void* t, int6
     case 256: return launch_gemm<256>(tA, tB, tA2, tB2, ep, n_tiles, stream);
   }
   set_error("proj_lora_fwd: unreachable tile width %d", BN);
+  return 1;
+}
+
+// 3x3 convolution (padding 1, stride 1 | 2) over an NHWC activation: see the CONV notes at the kernel.
+int conv3x3_fwd(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, const void* w, const void* t, int64_t ldt,
+                const void* bs, int64_t R, const float* colscale, const float* bias, const float* rowbias, const void* residual,
+                int64_t ldr, int residual_dtype, void* y, int64_t ldy, int y_dtype, int64_t Cout, int stride, int act,
+                cudaStream_t stream) {
+  AF_CHECK(x && w && y, "conv3x3_fwd: null x/w/y");
+  AF_CHECK(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3x3_fwd: empty problem");
+  AF_CHECK(stride == 1 || stride == 2, "conv3x3_fwd: stride %d (1 | 2)", stride);
+  AF_CHECK(stride == 1 || (H % 2 == 0 && W % 2 == 0), "conv3x3_fwd: stride 2 needs even H, W (got %lld x %lld)", (long long)H, (long long)W);
+  AF_CHECK(Cin % 8 == 0, "conv3x3_fwd: Cin (%lld) must be a multiple of 8 (16-byte TMA strides)", (long long)Cin);
+  AF_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0, "conv3x3_fwd: x / w must be 16-byte aligned");
+  AF_CHECK(act == ADAFACE_ACT_NONE || act == ADAFACE_ACT_QUICK_GELU, "conv3x3_fwd: bad act %d", act);
+  const bool lora = (t != nullptr) || (bs != nullptr) || R > 0;
+  if (lora) {
+    AF_CHECK(t && bs && R > 0 && R % 8 == 0 && ldt % 8 == 0, "conv3x3_fwd: t, bs, R (multiple of 8) must be given together");
+    AF_CHECK((reinterpret_cast<uintptr_t>(t) & 15) == 0 && (reinterpret_cast<uintptr_t>(bs) & 15) == 0, "conv3x3_fwd: t / bs must be 16-byte aligned");
+  }
+  const int64_t Ho = H / stride, Wo = W / stride;
+  AF_CHECK(Wo <= 128, "conv3x3_fwd: output width %lld > 128 is not tiled yet", (long long)Wo);
+  const int64_t M = B * Ho * Wo;
+  AF_CHECK(M < (1ll << 31) && Cout < (1ll << 31), "conv3x3_fwd: problem too large");
+  int64_t rh = 128 / Wo;                       // image rows per tile
+  if (rh > Ho) rh = Ho;
+  int64_t imgs = 1, tpi;
+  if (rh == Ho) {
+    imgs = 128 / (Wo * Ho);
+    if (imgs < 1) imgs = 1;
+    if (imgs > B) imgs = B;
+    tpi = 1;
+  } else {
+    tpi = (Ho + rh - 1) / rh;
+  }
+  const int64_t kc = (Cin + GEMM_BK - 1) / GEMM_BK;
+
+  GemmEpilogue ep;
+  ep.colscale = colscale;
+  ep.bias = bias;
+  ep.residual = residual;
+  ep.y = y;
+  ep.ldr = ldr;
+  ep.ldy = ldy;
+  ep.M = (int)M;
+  ep.N = (int)Cout;
+  ep.num_kb1 = (int)(9 * kc);
+  ep.num_kb2 = lora ? (int)((R + GEMM_BK - 1) / GEMM_BK) : 0;
+  ep.act = act;
+  ep.y_f32 = y_dtype == ADAFACE_F32;
+  ep.res_f32 = residual_dtype == ADAFACE_F32;
+  ep.hs_d = ep.hs_dpad = ep.hs_H = ep.hs_C = ep.hs_rows = ep.hs_B = 0;
+  ep.cv_kc = (int)kc;
+  ep.cv_W = (int)Wo;
+  ep.cv_HW = (int)(Ho * Wo);
+  ep.cv_img_rows = (int)(Wo * rh);
+  ep.cv_tpi = (int)tpi;
+  ep.cv_imgs = (int)imgs;
+  ep.cv_stride = stride;
+  ep.num_m = (int)(imgs > 1 ? (B + imgs - 1) / imgs : B * tpi);
+  ep.rowbias = rowbias;
+
+  const int BN = pick_tile_width(Cout, ep.num_m, act);
+  ConvMaps cm;
+  const bf16* xb = reinterpret_cast<const bf16*>(x);
+  if (stride == 1) {
+    if (make_tmap_bf16_nhwc(&cm.m[0], xb, (uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B, (uint64_t)Cin, (uint64_t)(W * Cin),
+                            (uint64_t)(H * W * Cin), (uint32_t)Wo, (uint32_t)rh, (uint32_t)imgs))
+      return 3;
+    cm.m[1] = cm.m[2] = cm.m[3] = cm.m[0];
+  } else {
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px)
+        if (make_tmap_bf16_nhwc(&cm.m[py * 2 + px], xb + (py * W + px) * Cin, (uint64_t)Cin, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B,
+                                (uint64_t)(2 * Cin), (uint64_t)(2 * W * Cin), (uint64_t)(H * W * Cin), (uint32_t)Wo, (uint32_t)rh,
+                                (uint32_t)imgs))
+          return 3;
+  }
+  CUtensorMap tB, tA2, tB2;
+  if (make_tmap_bf16_2d(&tB, w, (uint64_t)Cout, (uint64_t)(9 * kc * GEMM_BK), (uint64_t)(9 * kc * GEMM_BK), (uint32_t)BN)) return 3;
+  if (lora) {
+    if (make_tmap_bf16_2d(&tA2, t, (uint64_t)M, (uint64_t)R, (uint64_t)ldt, GEMM_BM)) return 3;
+    if (make_tmap_bf16_2d(&tB2, bs, (uint64_t)Cout, (uint64_t)R, (uint64_t)R, (uint32_t)BN)) return 3;
+  } else {
+    tA2 = tB;
+    tB2 = tB;
+  }
+  const int n_tiles = (int)((Cout + BN - 1) / BN);
+  switch (BN) {
+    case 64: return launch_gemm<64, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm);
+    case 128: return launch_gemm<128, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm);
+    case 160: return launch_gemm<160, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm);
+    case 192: return launch_gemm<192, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm);
+    case 256: return launch_gemm<256, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm);
+  }
+  set_error("conv3x3_fwd: unreachable tile width %d", BN);
   return 1;
 }
 

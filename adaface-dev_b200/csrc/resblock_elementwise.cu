@@ -1,0 +1,205 @@
+// HBM-bound helpers of the U-Net ResBlock / Upsample path on NHWC ("tokens", [B, H*W, C] bf16) activations
+// (ldm/modules/diffusionmodules/openaimodel.py:92-277).  The convolutions themselves are the CONV
+// instantiation of the tcgen05 GEMM (gemm_tcgen05.cu); here:
+//   gn_tokens_partial / gn_tokens_finalize / gn_tokens_apply
+//                     GroupNorm32 (fp32 statistics, util.py normalization() = GroupNorm(32, C)) + SiLU in front of each
+//                     3x3 convolution (openaimodel.py:203-207, 229-236), tokens in -> tokens out
+//   silu              SiLU of the time embedding in front of emb_layers' Linear (openaimodel.py:222-228)
+//   upsample2x        nearest-neighbour 2x of Upsample.forward (openaimodel.py:109-119) in NHWC
+#include "common.cuh"
+#include "../../include/adaface_b200.h"
+
+namespace adaface {
+
+extern long long g_launch_count;
+
+constexpr int GN_ROWS = 64;        // rows of one image summed by one CTA of the partial kernel
+constexpr int GN_MAX_PAIRS = 1280; // C <= 2560
+
+// part[((b * chunks) + chunk) * groups + g] = (sum, sum of squares) over rows [chunk * GN_ROWS, +GN_ROWS) of group g.
+// Threads walk channel PAIRS (a pair never straddles a group: C / groups is even), so every load instruction of a warp
+// reads 128 contiguous bytes of one row.
+__global__ void __launch_bounds__(256) gn_tokens_partial_kernel(const bf16* __restrict__ x, float2* __restrict__ part, int C, int HW,
+                                                                 int groups) {
+  __shared__ float ps[GN_MAX_PAIRS], pq[GN_MAX_PAIRS];
+  const int chunk = blockIdx.x, b = blockIdx.y, chunks = gridDim.x;
+  const int r0 = chunk * GN_ROWS, r1 = min(HW, r0 + GN_ROWS);
+  const int pairs = C >> 1;
+  const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(x + ((long long)b * HW + r0) * C);
+  for (int p = threadIdx.x; p < pairs; p += blockDim.x) {
+    float s = 0.f, q = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < r1 - r0; ++r) {
+      const float2 v = __bfloat1622float2(xb[(long long)r * pairs + p]);
+      s += v.x + v.y;
+      q += v.x * v.x + v.y * v.y;
+    }
+    ps[p] = s;
+    pq[p] = q;
+  }
+  __syncthreads();
+  const int ppg = pairs / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int i = 0; i < ppg; ++i) {
+      s += ps[g * ppg + i];
+      q += pq[g * ppg + i];
+    }
+    part[((long long)b * chunks + chunk) * groups + g] = make_float2(s, q);
+  }
+}
+
+// One CTA per image: group statistics from the partials (fixed summation order: deterministic), folded with the affine
+// parameters into a[b, c] = rstd * gamma[c], s[b, c] = beta[c] - mean * rstd * gamma[c].
+__global__ void __launch_bounds__(256) gn_tokens_finalize_kernel(const float2* __restrict__ part, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, float* __restrict__ a,
+                                                                  float* __restrict__ s, int C, int HW, int groups, int chunks, float eps) {
+  __shared__ float mean_s[256], rstd_s[256];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cpg = C / groups;
+  for (int g = warp; g < groups; g += 8) {
+    float sum = 0.f, sq = 0.f;
+    for (int c = lane; c < chunks; c += 32) {
+      const float2 v = part[((long long)b * chunks + c) * groups + g];
+      sum += v.x;
+      sq += v.y;
+    }
+    sum = warp_sum(sum);
+    sq = warp_sum(sq);
+    if (lane == 0) {
+      const float n = (float)cpg * (float)HW;
+      const float mean = sum / n;
+      mean_s[g] = mean;
+      rstd_s[g] = rsqrtf(fmaxf(sq / n - mean * mean, 0.f) + eps);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float ga = gamma[c] * rstd_s[g];
+    a[(long long)b * C + c] = ga;
+    s[(long long)b * C + c] = beta[c] - mean_s[g] * ga;
+  }
+}
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
+
+// y[b, r, c] = act(x[b, r, c] * a[b, c] + s[b, c]); 8 channels (16 bytes) per thread, a / s of the image in shared memory.
+template <int ACT>
+__global__ void __launch_bounds__(256) gn_tokens_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ a,
+                                                               const float* __restrict__ s, bf16* __restrict__ y, int C, int HW,
+                                                               int rows_per_cta) {
+  extern __shared__ float as_s[];    // [2][C]
+  const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    as_s[c] = a[(long long)b * C + c];
+    as_s[C + c] = s[(long long)b * C + c];
+  }
+  __syncthreads();
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
+  const int vec = C >> 3;
+  const long long base = ((long long)b * HW + r0) * vec;
+  const uint4* xv = reinterpret_cast<const uint4*>(x) + base;
+  uint4* yv = reinterpret_cast<uint4*>(y) + base;
+  const int n = (r1 - r0) * vec;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c0 = (i % vec) << 3;
+    const uint4 u = xv[i];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xffff0000u);
+      lo = lo * as_s[c0 + 2 * j] + as_s[C + c0 + 2 * j];
+      hi = hi * as_s[c0 + 2 * j + 1] + as_s[C + c0 + 2 * j + 1];
+      if (ACT == 1) {
+        lo = silu_f(lo);
+        hi = silu_f(hi);
+      }
+      o[j] = pack_bf16(lo, hi);
+    }
+    yv[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+int groupnorm_act_tokens_fwd(const void* x, const float* gamma, const float* beta, int64_t B, int64_t HW, int64_t C, int64_t groups,
+                             float eps, int act, float* part_ws, float* a_ws, float* s_ws, void* y, cudaStream_t stream) {
+  AF_CHECK(x && gamma && beta && part_ws && a_ws && s_ws && y, "groupnorm_act_tokens_fwd: null pointer");
+  AF_CHECK(B > 0 && HW > 0 && C > 0 && groups > 0 && groups <= 256 && C % groups == 0 && (C / groups) % 2 == 0 && C % 8 == 0 &&
+               C <= 2 * GN_MAX_PAIRS && B <= 65535,
+           "groupnorm_act_tokens_fwd: bad shape B=%lld HW=%lld C=%lld groups=%lld", (long long)B, (long long)HW, (long long)C,
+           (long long)groups);
+  AF_CHECK(act == 0 || act == 1, "groupnorm_act_tokens_fwd: act %d (0 none | 1 SiLU)", act);
+  AF_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "groupnorm_act_tokens_fwd: x / y must be 16-byte aligned");
+  const int chunks = (int)((HW + GN_ROWS - 1) / GN_ROWS);
+  gn_tokens_partial_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, 0, stream>>>((const bf16*)x, (float2*)part_ws, (int)C, (int)HW, (int)groups);
+  gn_tokens_finalize_kernel<<<(unsigned)B, 256, 0, stream>>>((const float2*)part_ws, gamma, beta, a_ws, s_ws, (int)C, (int)HW, (int)groups, chunks, eps);
+  long long rows = (B * HW + 295) / 296;            // ~2 CTAs per SM
+  if (rows < 4) rows = 4;
+  if (rows > 64) rows = 64;
+  const dim3 grid((unsigned)((HW + rows - 1) / rows), (unsigned)B);
+  const size_t smem = (size_t)(2 * C * sizeof(float));
+  if (act == 1) gn_tokens_apply_kernel<1><<<grid, 256, smem, stream>>>((const bf16*)x, a_ws, s_ws, (bf16*)y, (int)C, (int)HW, (int)rows);
+  else gn_tokens_apply_kernel<0><<<grid, 256, smem, stream>>>((const bf16*)x, a_ws, s_ws, (bf16*)y, (int)C, (int)HW, (int)rows);
+  AF_CUDA(cudaGetLastError());
+  g_launch_count += 3;
+  return 0;
+}
+
+int64_t groupnorm_act_tokens_ws_floats(int64_t B, int64_t HW, int64_t groups) {
+  return 2 * B * ((HW + GN_ROWS - 1) / GN_ROWS) * groups;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void __launch_bounds__(256) silu_kernel(const TIn* __restrict__ x, bf16* __restrict__ y, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float v;
+    if constexpr (sizeof(TIn) == 2) v = __bfloat162float(x[i]);
+    else v = x[i];
+    y[i] = __float2bfloat16(silu_f(v));
+  }
+}
+
+int silu_fwd(const void* x, int x_dtype, void* y, int64_t n, cudaStream_t stream) {
+  AF_CHECK(x && y && n > 0, "silu_fwd: null pointer / empty");
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (x_dtype == ADAFACE_F32) silu_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, (bf16*)y, (long long)n);
+  else if (x_dtype == ADAFACE_BF16) silu_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)x, (bf16*)y, (long long)n);
+  else {
+    set_error("silu_fwd: bad dtype %d", x_dtype);
+    return 1;
+  }
+  AF_CUDA(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// y[b, 2h + i, 2w + j, :] = x[b, h, w, :]  (i, j in {0, 1}); one thread per 16 bytes of OUTPUT
+__global__ void __launch_bounds__(256) upsample2x_tokens_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int vec,
+                                                                 long long n_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const int v = (int)(i % vec);
+  long long p = i / vec;
+  const int ox = (int)(p % (2 * W));
+  p /= 2 * W;
+  const int oy = (int)(p % (2 * H));
+  const long long b = p / (2 * H);
+  y[i] = x[((b * H + (oy >> 1)) * W + (ox >> 1)) * vec + v];
+}
+
+int upsample2x_tokens(const void* x, void* y, int64_t B, int64_t H, int64_t W, int64_t C, cudaStream_t stream) {
+  AF_CHECK(x && y, "upsample2x_tokens: null pointer");
+  AF_CHECK(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "upsample2x_tokens: bad shape");
+  AF_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "upsample2x_tokens: x / y must be 16-byte aligned");
+  const long long n_out = B * 4 * H * W * (C / 8);
+  upsample2x_tokens_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, stream>>>((const uint4*)x, (uint4*)y, (int)H, (int)W, (int)(C / 8), n_out);
+  AF_CUDA(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+}  // namespace adaface

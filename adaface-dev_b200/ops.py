@@ -290,6 +290,98 @@ def tokens_to_nchw_add(t, x_in):
     return out
 
 
+def pack_conv3x3_weight(weight):
+    """[Cout, Cin, 3, 3] (nn.Conv2d) -> bf16 [Cout, 9 * Kc], Kc = Cin rounded up to 64, K index = (ky*3 + kx) * Kc + ci:
+    the K-major operand adaface_conv3x3_fwd reads (one 64-channel slab per tap and chunk).  Load-time re-layout."""
+    Cout, Cin, kh, kw = weight.shape
+    if (kh, kw) != (3, 3):
+        raise ValueError(f"pack_conv3x3_weight: expected a 3x3 kernel, got {kh}x{kw}")
+    kc = (Cin + 63) // 64 * 64
+    w = torch.zeros((Cout, 9, kc), device=weight.device, dtype=torch.bfloat16)
+    w[:, :, :Cin] = weight.detach().permute(0, 2, 3, 1).reshape(Cout, 9, Cin).to(torch.bfloat16)
+    return w.reshape(Cout, 9 * kc).contiguous()
+
+
+def conv3x3(x, w_packed, hw, *, stride=1, bias=None, rowbias=None, residual=None, t=None, bs=None, colscale=None, out=None,
+            out_dtype=torch.bfloat16):
+    """3x3 convolution, padding 1, over NHWC tokens (adaface_conv3x3_fwd): x bf16 [B, h*w, Cin] contiguous with hw = (h, w),
+    w_packed from pack_conv3x3_weight, bias fp32 [Cout], rowbias fp32 [B, Cout] (added per image), residual / out
+    [B, ho*wo, Cout]; t [B*ho*wo, R] / bs [Cout, R] / colscale [Cout] = conv-LoRA / DoRA tail.  Returns [B, ho*wo, Cout]."""
+    _need(x, "x", torch.bfloat16), _need(w_packed, "w_packed", torch.bfloat16)
+    h, w = hw
+    if x.dim() != 3 or not x.is_contiguous() or x.shape[1] != h * w or not w_packed.is_contiguous():
+        raise ValueError(f"conv3x3: x must be a contiguous [B, h*w, Cin] tensor (got {tuple(x.shape)}, hw={hw})")
+    B, _, Cin = x.shape
+    Cout = w_packed.shape[0]
+    if w_packed.shape[1] != 9 * ((Cin + 63) // 64 * 64):
+        raise ValueError(f"conv3x3: w_packed{tuple(w_packed.shape)} does not match Cin={Cin}")
+    if stride not in (1, 2):
+        raise ValueError("conv3x3: stride must be 1 or 2")
+    ho, wo = h // stride, w // stride
+    M = B * ho * wo
+    for v, nm, shape in ((bias, "bias", (Cout,)), (colscale, "colscale", (Cout,)), (rowbias, "rowbias", (B, Cout))):
+        if v is not None:
+            _need(v, nm, torch.float32)
+            if tuple(v.shape) != shape or not v.is_contiguous():
+                raise ValueError(f"conv3x3: `{nm}` must be a contiguous fp32 {shape} tensor")
+    R, ldt = 0, 0
+    if t is not None or bs is not None:
+        _need(t, "t", torch.bfloat16), _need(bs, "bs", torch.bfloat16)
+        if t.shape[0] != M or bs.shape[0] != Cout or t.shape[1] != bs.shape[1] or not bs.is_contiguous():
+            raise ValueError(f"conv3x3: bad LoRA shapes t{tuple(t.shape)} bs{tuple(bs.shape)}")
+        R, ldt = t.shape[1], t.stride(0)
+    if out is None:
+        out = torch.empty((B, ho * wo, Cout), device=x.device, dtype=out_dtype)
+    _need(out, "out")
+    if tuple(out.shape) != (B, ho * wo, Cout) or not out.is_contiguous():
+        raise ValueError(f"conv3x3: out has shape {tuple(out.shape)}, expected contiguous {(B, ho * wo, Cout)}")
+    ldr, rdt = 0, BF16
+    if residual is not None:
+        _need(residual, "residual")
+        if tuple(residual.shape) != (B, ho * wo, Cout) or not residual.is_contiguous():
+            raise ValueError("conv3x3: residual shape mismatch")
+        ldr, rdt = Cout, _dt(residual)
+    _lib.call("adaface_conv3x3_fwd", _ptr(x), B, h, w, Cin, _ptr(w_packed), _ptr(t), ldt, _ptr(bs), R, _ptr(colscale), _ptr(bias),
+              _ptr(rowbias), _ptr(residual), ldr, rdt, _ptr(out), Cout, _dt(out), Cout, int(stride), ACT_NONE, _stream())
+    return out
+
+
+def groupnorm_act_tokens(x, gamma, beta, groups=32, eps=1e-5, silu=True):
+    """act(GroupNorm(x)) over tokens: x bf16 [B, HW, C] -> bf16 [B, HW, C] (adaface_groupnorm_act_tokens_fwd)."""
+    _need(x, "x", torch.bfloat16), _need(gamma, "gamma", torch.float32), _need(beta, "beta", torch.float32)
+    if x.dim() != 3 or not x.is_contiguous():
+        raise ValueError("groupnorm_act_tokens: x must be a contiguous [B, HW, C] tensor")
+    B, HW, C = x.shape
+    n_ws = int(_lib.load().adaface_groupnorm_act_tokens_ws_floats(B, HW, int(groups)))
+    ws = torch.empty(n_ws + 2 * B * C, device=x.device, dtype=torch.float32)
+    y = torch.empty_like(x)
+    _lib.call("adaface_groupnorm_act_tokens_fwd", _ptr(x), _ptr(gamma), _ptr(beta), B, HW, C, int(groups), float(eps), 1 if silu else 0,
+              _ptr(ws), _ptr(ws[n_ws:]), _ptr(ws[n_ws + B * C:]), _ptr(y), _stream())
+    return y
+
+
+def silu(x):
+    """SiLU(x) -> bf16 (adaface_silu_fwd); x bf16 | fp32 contiguous."""
+    _need(x, "x")
+    if not x.is_contiguous():
+        raise ValueError("silu: x must be contiguous")
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _lib.call("adaface_silu_fwd", _ptr(x), _dt(x), _ptr(y), x.numel(), _stream())
+    return y
+
+
+def upsample2x_tokens(x, hw):
+    """Nearest 2x of NHWC tokens: bf16 [B, h*w, C] -> [B, 4*h*w, C] (adaface_upsample2x_tokens)."""
+    _need(x, "x", torch.bfloat16)
+    h, w = hw
+    if x.dim() != 3 or not x.is_contiguous() or x.shape[1] != h * w:
+        raise ValueError("upsample2x_tokens: x must be a contiguous [B, h*w, C] tensor")
+    B, _, C = x.shape
+    y = torch.empty((B, 4 * h * w, C), device=x.device, dtype=torch.bfloat16)
+    _lib.call("adaface_upsample2x_tokens", _ptr(x), _ptr(y), B, h, w, C, _stream())
+    return y
+
+
 def softmax_scale(d):
     return 1.0 / math.sqrt(d)
 

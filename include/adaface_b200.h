@@ -145,6 +145,35 @@ int adaface_groupnorm_tokens_fwd(const void* x, int x_dtype, const float* gamma,
 int adaface_tokens_to_nchw_add(const void* t, const void* x_in, int x_dtype, void* out, int64_t B, int64_t C, int64_t HW,
                                void* stream);
 
+/* ---- ResBlock / Downsample / Upsample of the U-Net (ldm/modules/diffusionmodules/openaimodel.py:92-277; SURVEY 8f
+ * row 2) on NHWC activations: x [B, H, W, Cin] bf16 contiguous == the "tokens" layout [B, H*W, C] of the attention path,
+ * so a ResBlock -> SpatialTransformer chain never leaves it.
+ *
+ * 3x3 convolution, padding 1, stride 1 | 2 (conv_nd(2, cin, cout, 3, padding=1 [, stride=2]) :110, :151, :206, :236) as an
+ * implicit GEMM on tcgen05: M = B*Ho*Wo output pixels, N = Cout, K = 9 taps x Cin; the activation tile of every tap is a
+ * shifted TMA box whose out-of-image part is zero-filled (= the padding), so no im2col buffer exists.
+ *   w        bf16 [Cout, 9 * Kc] with Kc = Cin rounded up to 64: w[co][(ky*3 + kx) * Kc + ci] = weight[co][ci][ky][kx]
+ *   bias     fp32 [Cout] or NULL;   rowbias fp32 [B, Cout] or NULL: added to every pixel of image b (h + emb_out :257)
+ *   residual [B*Ho*Wo, ldr] bf16 | fp32 or NULL (skip_connection(x) + h :260);   y [B*Ho*Wo, ldy] bf16 | fp32
+ *   t, bs, R, colscale: optional conv-LoRA / DoRA tail exactly as in adaface_proj_lora_fwd (t = lora_A conv output [M, R],
+ *   bs = scaled lora_B 1x1 weight [Cout, R]; dalc:541-591).   Cin % 8 == 0, Wo <= 128, even H, W for stride 2. */
+int adaface_conv3x3_fwd(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, const void* w, const void* t, int64_t ldt,
+                        const void* bs, int64_t R, const float* colscale, const float* bias, const float* rowbias,
+                        const void* residual, int64_t ldr, int residual_dtype, void* y, int64_t ldy, int y_dtype, int64_t Cout,
+                        int stride, int act, void* stream);
+/* y = act(GroupNorm(groups, eps)(x) * gamma + beta) over tokens: x, y bf16 [B, HW, C]; act 0 = none, 1 = SiLU
+ * (normalization() + nn.SiLU() in front of each convolution, openaimodel.py:203-205, 229-231; fp32 statistics like
+ * GroupNorm32, util.py).  part_ws: adaface_groupnorm_act_tokens_ws_floats(B, HW, groups) floats; a_ws, s_ws: fp32 [B, C]. */
+int adaface_groupnorm_act_tokens_fwd(const void* x, const float* gamma, const float* beta, int64_t B, int64_t HW, int64_t C,
+                                     int64_t groups, float eps, int act, float* part_ws, float* a_ws, float* s_ws, void* y,
+                                     void* stream);
+int64_t adaface_groupnorm_act_tokens_ws_floats(int64_t B, int64_t HW, int64_t groups);
+/* y = SiLU(x) as bf16, n elements (the nn.SiLU() in front of emb_layers' Linear, openaimodel.py:222-228). */
+int adaface_silu_fwd(const void* x, int x_dtype, void* y, int64_t n, void* stream);
+/* Nearest-neighbour 2x (F.interpolate(scale_factor=2, mode="nearest"), openaimodel.py:116): x bf16 [B, H, W, C] ->
+ * y [B, 2H, 2W, C]. */
+int adaface_upsample2x_tokens(const void* x, void* y, int64_t B, int64_t H, int64_t W, int64_t C, void* stream);
+
 /* ---- K5: backward kernels of the stage-2 training step (ddpm.py:1645-1707 back-propagates through the `sc`
  * instance of the U-Net into the LoRA / DoRA adapters, cross_attn_scale_factor and, via the context, SubjBasisGenerator).
  * The reference gets all of this from autograd over eager PyTorch ops; here every gradient is a kernel, recompute

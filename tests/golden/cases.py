@@ -160,6 +160,40 @@ def build_spatial_case(name):
     return case
 
 
+# ResBlock / Upsample / Downsample (ldm/modules/diffusionmodules/openaimodel.py:92-277).  `kind`: res | up | down
+UNET_BLOCK_CASES = {
+    "unet_res_a":      dict(seed=51, kind="res", B=2, h=16, w=16, cin=320, cout=320, emb=1280),             # identity skip
+    "unet_res_skip":   dict(seed=52, kind="res", B=3, h=8, w=8, cin=640, cout=320, emb=1280),               # 1x1 skip, 2 images / tile
+    "unet_res_rect":   dict(seed=53, kind="res", B=1, h=12, w=32, cin=64, cout=128, emb=256, skip3=True),    # 3x3 skip, ragged image rows
+    "unet_up":         dict(seed=54, kind="up", B=2, h=8, w=8, cin=320),
+    "unet_down":       dict(seed=55, kind="down", B=2, h=16, w=16, cin=320),
+}
+
+
+def build_unet_block_case(name):
+    sp = UNET_BLOCK_CASES[name]
+    rng = np.random.default_rng(sp["seed"])
+    B, h, w, cin = sp["B"], sp["h"], sp["w"], sp["cin"]
+    case = dict(spec=sp)
+    case["x"] = normal(rng, (B, cin, h, w))
+    ws = {}
+    if sp["kind"] == "res":
+        cout, emb = sp["cout"], sp["emb"]
+        case["emb"] = normal(rng, (B, emb))
+        ws["gn1_w"], ws["gn1_b"] = bf16r(1 + 0.1 * rng.standard_normal(cin)), normal(rng, (cin,), 0.05)
+        ws["conv1_w"], ws["conv1_b"] = normal(rng, (cout, cin, 3, 3), 1 / math.sqrt(9 * cin)), normal(rng, (cout,), 0.02)
+        ws["emb_w"], ws["emb_b"] = normal(rng, (cout, emb), 1 / math.sqrt(emb)), normal(rng, (cout,), 0.02)
+        ws["gn2_w"], ws["gn2_b"] = bf16r(1 + 0.1 * rng.standard_normal(cout)), normal(rng, (cout,), 0.05)
+        ws["conv2_w"], ws["conv2_b"] = normal(rng, (cout, cout, 3, 3), 1 / math.sqrt(9 * cout)), normal(rng, (cout,), 0.02)   # not zero
+        if cin != cout:
+            k = 3 if sp.get("skip3") else 1
+            ws["skip_w"], ws["skip_b"] = normal(rng, (cout, cin, k, k), 1 / math.sqrt(k * k * cin)), normal(rng, (cout,), 0.02)
+    else:
+        ws["conv_w"], ws["conv_b"] = normal(rng, (cin, cin, 3, 3), 1 / math.sqrt(9 * cin)), normal(rng, (cin,), 0.02)
+    case["w"] = ws
+    return case
+
+
 # SubjBasisGenerator / CLIP-shaped encoder (surface 3).  E=768, 12 heads x 64, MLP 3072, 77 positions.
 SBG_CASES = {
     "mkv_m1":   dict(seed=41, BS=2, T=77, mult=1, layers=0),

@@ -220,6 +220,32 @@ def run_spatial_cases():
         save(name, case, {"out": out})
 
 
+def run_unet_block_cases():
+    from ldm.modules.diffusionmodules.openaimodel import ResBlock, Upsample, Downsample
+
+    for name in C.UNET_BLOCK_CASES:
+        case = C.build_unet_block_case(name)
+        sp, w = case["spec"], case["w"]
+        if sp["kind"] == "res":
+            m = ResBlock(sp["cin"], sp["emb"], 0.0, out_channels=sp["cout"], use_conv=bool(sp.get("skip3")), dims=2,
+                         use_checkpoint=False, use_scale_shift_norm=False).eval()
+            pairs = [(m.in_layers[0], "gn1"), (m.in_layers[2], "conv1"), (m.emb_layers[1], "emb"), (m.out_layers[0], "gn2"),
+                     (m.out_layers[3], "conv2")]
+            if "skip_w" in w:
+                pairs.append((m.skip_connection, "skip"))
+            for mod, key in pairs:
+                mod.weight.data, mod.bias.data = T(w[key + "_w"]).clone(), T(w[key + "_b"]).clone()
+            with torch.no_grad():
+                out = m(T(case["x"]), T(case["emb"]))
+        else:
+            m = (Upsample if sp["kind"] == "up" else Downsample)(sp["cin"], True, dims=2).eval()
+            conv = m.conv if sp["kind"] == "up" else m.op
+            conv.weight.data, conv.bias.data = T(w["conv_w"]).clone(), T(w["conv_b"]).clone()
+            with torch.no_grad():
+                out = m(T(case["x"]))
+        save(name, case, {"out": out})
+
+
 # --------------------------------------------------------------------------------- SBG cases
 class _EncOut:
     """Minimal stand-in for HF BaseModelOutput: tuple-indexable and attribute-addressable."""
@@ -334,5 +360,7 @@ if __name__ == "__main__":
         run_ldm_cases()
     if only in ("", "spatial"):
         run_spatial_cases()
+    if only in ("", "unet_blocks"):
+        run_unet_block_cases()
     if only in ("", "sbg"):
         run_sbg_cases()

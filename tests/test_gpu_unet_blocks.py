@@ -1,0 +1,170 @@
+"""GPU parity of the U-Net's convolutional blocks: the implicit-GEMM 3x3 convolution on tcgen05, GroupNorm +
+SiLU over NHWC tokens, nearest 2x, and the ResBlock / Upsample / Downsample mirrors against
+  (1) the committed golden fixtures = outputs of the reference's own modules (tests/golden/unet_*.npz),
+  (2) the CPU oracle (oracle/unet_blocks_oracle.py) on seeded inputs, up to the level-A size of BASELINE.json.
+Tolerance: max-abs 2e-2 on bf16 outputs of O(1) magnitude (north_star), tighter where the output is fp32."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases as C
+from oracle import unet_blocks_oracle as ub
+from mirror_utils import _T
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def err(a, ref):
+    ref = torch.from_numpy(ref) if isinstance(ref, np.ndarray) else ref
+    return (a.detach().float().cpu() - ref.float()).abs().max().item()
+
+
+def rnd(shape, seed, scale=1.0):
+    return (scale * torch.randn(*shape, generator=torch.Generator().manual_seed(seed))).bfloat16().float()
+
+
+def nhwc(x):                      # [B, C, h, w] fp32 -> bf16 tokens [B, h*w, C] on the GPU
+    b, c, h, w = x.shape
+    return x.permute(0, 2, 3, 1).reshape(b, h * w, c).contiguous().bfloat16().cuda()
+
+
+def nchw(t, hw):                  # tokens [B, h*w, C] -> fp32 [B, C, h, w] on the CPU
+    b, _, c = t.shape
+    return t.float().cpu().reshape(b, hw[0], hw[1], c).permute(0, 3, 1, 2)
+
+
+# (B, h, w, cin, cout, stride): levels A-D of SD-1.5, odd batches with several images per tile, ragged image rows
+# (w = 40 -> 120-pixel tiles; h = 12 with 8-row tiles), channel counts that are not multiples of 64, stride 2
+CONV_SHAPES = [
+    (2, 64, 64, 320, 320, 1), (2, 32, 32, 640, 320, 1), (3, 16, 16, 1280, 640, 1), (3, 8, 8, 1280, 1280, 1),
+    (1, 12, 32, 64, 128, 1), (2, 24, 40, 72, 100, 1), (5, 4, 4, 64, 64, 1), (1, 8, 128, 64, 64, 1),
+    (2, 64, 64, 320, 320, 2), (3, 16, 16, 1280, 1280, 2), (1, 8, 8, 64, 64, 2), (2, 24, 80, 72, 100, 2),
+]
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv3x3_vs_oracle(shape):
+    import adaface_dev_b200 as a
+    B, h, w, cin, cout, stride = shape
+    x, wt, bias = rnd((B, cin, h, w), 1), rnd((cout, cin, 3, 3), 2, (9 * cin) ** -0.5), rnd((cout,), 3, 0.1).float()
+    ref = ub.conv3x3(x, wt, bias, stride=stride)
+    wp = a.ops.pack_conv3x3_weight(wt.cuda())
+    y = a.ops.conv3x3(nhwc(x), wp, (h, w), stride=stride, bias=bias.cuda(), out_dtype=torch.float32)
+    ho, wo = h // stride, w // stride
+    assert tuple(y.shape) == (B, ho * wo, cout)
+    assert err(nchw(y, (ho, wo)), ref) < 2e-3          # fp32 accumulation of exact bf16 products; fp32 output
+    yb = a.ops.conv3x3(nhwc(x), wp, (h, w), stride=stride, bias=bias.cuda())
+    assert yb.dtype == torch.bfloat16 and err(nchw(yb, (ho, wo)), ref) < 2e-2
+
+
+def test_conv3x3_epilogue_terms():
+    """Per-image bias (the ResBlock's time-embedding term), residual (its skip connection) and a conv-LoRA tail."""
+    import adaface_dev_b200 as a
+    B, h, w, cin, cout, R = 3, 8, 8, 128, 192, 16
+    x, wt = rnd((B, cin, h, w), 11), rnd((cout, cin, 3, 3), 12, (9 * cin) ** -0.5)
+    bias, rowb, res = rnd((cout,), 13, 0.1), rnd((B, cout), 14, 0.5), rnd((B, cout, h, w), 15)
+    wa, wb = rnd((R, cin, 3, 3), 16, (9 * cin) ** -0.5), rnd((cout, R), 17, R ** -0.5)
+    wp = a.ops.pack_conv3x3_weight(wt.cuda())
+    base = ub.conv3x3(x, wt, bias) + rowb[:, :, None, None] + res
+    y = a.ops.conv3x3(nhwc(x), wp, (h, w), bias=bias.cuda(), rowbias=rowb.cuda(), residual=nhwc(res), out_dtype=torch.float32)
+    assert err(nchw(y, (h, w)), base) < 2e-3
+    # conv-LoRA: lora_A is a 3x3 convolution to R channels, lora_B a 1x1 back to cout (dalc:541-591)
+    t = a.ops.conv3x3(nhwc(x), a.ops.pack_conv3x3_weight(wa.cuda()), (h, w))                 # [B, hw, R] bf16
+    t_ref = t.float().cpu()
+    lora = torch.einsum("bnr,or->bno", t_ref, wb)
+    assert err(nchw(t, (h, w)), ub.conv3x3(x, wa, None)) < 2e-2
+    y2 = a.ops.conv3x3(nhwc(x), wp, (h, w), bias=bias.cuda(), t=t.view(B * h * w, R), bs=wb.bfloat16().cuda(), out_dtype=torch.float32)
+    ref2 = ub.conv3x3(x, wt, bias) + lora.reshape(B, h, w, cout).permute(0, 3, 1, 2)
+    assert err(nchw(y2, (h, w)), ref2) < 2e-3
+
+
+def test_conv3x3_rejects_bad_input():
+    import adaface_dev_b200 as a
+    wp = a.ops.pack_conv3x3_weight(torch.zeros(64, 64, 3, 3).cuda())
+    x = torch.zeros(1, 64, 64, dtype=torch.bfloat16).cuda()
+    with pytest.raises(ValueError):
+        a.ops.conv3x3(x, wp, (4, 8))                       # hw does not match the token count
+    with pytest.raises(RuntimeError):
+        a.ops.conv3x3(torch.zeros(1, 9, 64, dtype=torch.bfloat16).cuda(), wp, (3, 3), stride=2)    # odd size under stride 2
+    with pytest.raises(RuntimeError):
+        a.ops.conv3x3(torch.zeros(1, 256, 64, dtype=torch.bfloat16), wp, (16, 16))                 # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("shape", [(2, 4096, 320), (3, 64, 1280), (1, 100, 64), (2, 1024, 960)], ids=lambda s: "x".join(map(str, s)))
+def test_groupnorm_act_tokens_vs_oracle(shape):
+    import adaface_dev_b200 as a
+    B, HW, Cc = shape
+    x = rnd((B, HW, Cc), 21) * 2 + 0.5
+    gam, bet = 1 + 0.1 * torch.randn(Cc, generator=torch.Generator().manual_seed(22)), 0.1 * torch.randn(Cc, generator=torch.Generator().manual_seed(23))
+    xc = x.bfloat16().float().permute(0, 2, 1).reshape(B, Cc, HW, 1)
+    n = ub.group_norm32(xc, gam, bet)
+    for silu in (True, False):
+        y = a.ops.groupnorm_act_tokens(x.bfloat16().cuda(), gam.cuda(), bet.cuda(), 32, 1e-5, silu=silu)
+        ref = (ub.silu(n) if silu else n).reshape(B, Cc, HW).permute(0, 2, 1)
+        assert y.dtype == torch.bfloat16 and err(y, ref) < 2e-2
+
+
+def test_silu_and_upsample_kernels():
+    import adaface_dev_b200 as a
+    e = rnd((3, 1280), 31, 2.0)
+    assert err(a.ops.silu(e.cuda()), ub.silu(e)) < 2e-2          # bf16 output, |y| < 8: half an ulp = 1.6e-2
+    assert err(a.ops.silu(e.bfloat16().cuda()), ub.silu(e)) < 2e-2
+    x = rnd((2, 64, 6, 10), 32)
+    up = a.ops.upsample2x_tokens(nhwc(x), (6, 10))
+    ref = x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+    assert err(nchw(up, (12, 20)), ref) == 0.0             # a copy: bit-exact
+
+
+def _load_res(m, w):
+    pairs = [(m.in_layers[0], "gn1"), (m.in_layers[2], "conv1"), (m.emb_layers[1], "emb"), (m.out_layers[0], "gn2"), (m.out_layers[3], "conv2")]
+    if "skip_w" in w:
+        pairs.append((m.skip_connection, "skip"))
+    with torch.no_grad():
+        for mod, key in pairs:
+            mod.weight.copy_(_T(w[key + "_w"]))
+            mod.bias.copy_(_T(w[key + "_b"]))
+
+
+@pytest.mark.parametrize("name", list(C.UNET_BLOCK_CASES))
+def test_unet_block_vs_reference_golden(name):
+    """The NCHW drop-in mirrors against the outputs of the reference's own ResBlock / Upsample / Downsample modules."""
+    import adaface_dev_b200 as a
+    case = C.build_unet_block_case(name)
+    sp, w = case["spec"], case["w"]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    if sp["kind"] == "res":
+        m = a.ResBlock(sp["cin"], sp["emb"], 0.0, out_channels=sp["cout"], use_conv=bool(sp.get("skip3"))).cuda().eval()
+        _load_res(m, w)
+        with torch.no_grad():
+            out = m(_T(case["x"]), _T(case["emb"]))
+        assert {"in_layers.0.weight", "in_layers.2.bias", "emb_layers.1.weight", "out_layers.0.bias", "out_layers.3.weight"} <= set(m.state_dict())
+    else:
+        m = (a.Upsample if sp["kind"] == "up" else a.Downsample)(sp["cin"], True).cuda().eval()
+        conv = m.conv if sp["kind"] == "up" else m.op
+        with torch.no_grad():
+            conv.weight.copy_(_T(w["conv_w"]))
+            conv.bias.copy_(_T(w["conv_b"]))
+            out = m(_T(case["x"]))
+    assert out.dtype == torch.float32 and tuple(out.shape) == g["out"].shape
+    assert err(out, g["out"]) < 3e-2          # bf16 activations between the two convolutions, output magnitude ~2
+
+
+def test_resblock_tokens_entry_and_full_size():
+    """NHWC-resident entry at the level-A size of BASELINE.json (B = 2, 64 x 64, 320 channels) against the oracle."""
+    import adaface_dev_b200 as a
+    B, h, wd, Cc, E = 2, 64, 64, 320, 1280
+    rng = np.random.default_rng(7)
+    f = lambda shape, s=1.0: torch.from_numpy((s * rng.standard_normal(shape)).astype(np.float32)).bfloat16().float()
+    w = {"gn1_w": 1 + f((Cc,), 0.1), "gn1_b": f((Cc,), 0.05), "conv1_w": f((Cc, Cc, 3, 3), (9 * Cc) ** -0.5), "conv1_b": f((Cc,), 0.02),
+         "emb_w": f((Cc, E), E ** -0.5), "emb_b": f((Cc,), 0.02), "gn2_w": 1 + f((Cc,), 0.1), "gn2_b": f((Cc,), 0.05),
+         "conv2_w": f((Cc, Cc, 3, 3), (9 * Cc) ** -0.5), "conv2_b": f((Cc,), 0.02)}
+    x, emb = f((B, Cc, h, wd)), f((B, E))
+    ref = ub.res_block(w, x, emb)
+    m = a.ResBlock(Cc, E, 0.0).cuda().eval()
+    _load_res(m, {k: v.numpy() for k, v in w.items()})
+    with torch.no_grad():
+        out = m.forward_tokens(nhwc(x), emb.cuda(), (h, wd))
+    assert out.dtype == torch.bfloat16 and err(nchw(out, (h, wd)), ref) < 3e-2

@@ -142,3 +142,20 @@ def test_spatial_transformer_oracle_vs_reference(name):
     t = C.to_torch({k: v for k, v in case.items() if k != "spec"})
     out = oracle.spatial_transformer(t["w"], t["x"], context=t["context"], mask=t["mask"])
     close(out, g["out"], atol=5e-5, what=name)
+
+
+@pytest.mark.parametrize("name", list(C.UNET_BLOCK_CASES))
+def test_unet_blocks_oracle_vs_reference(name):
+    """ResBlock / Upsample / Downsample (ldm/modules/diffusionmodules/openaimodel.py:92-277) against the reference modules."""
+    from oracle import unet_blocks_oracle as ub
+    case = C.build_unet_block_case(name)
+    g = load(name, case)
+    t = C.to_torch({k: v for k, v in case.items() if k != "spec"})
+    kind = case["spec"]["kind"]
+    if kind == "res":
+        out = ub.res_block(t["w"], t["x"], t["emb"])
+    elif kind == "up":
+        out = ub.upsample(t["w"], t["x"])
+    else:
+        out = ub.downsample(t["w"], t["x"])
+    close(out, g["out"], atol=5e-5, what=name)
