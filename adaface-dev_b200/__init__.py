@@ -6,6 +6,7 @@ Host-side mirrors of the reference's operator surface over the C-
     AttnProcessor_LoRA_Capture, Attention, LoraDoraLinear, gen_gradient_scaler   (attn_processor.py)
     CrossAttention, FeedForward, BasicTransformerBlock, SpatialTransformer       (ldm_attention.py)
     ResBlock, Upsample, Downsample                                               (ldm_unet_blocks.py)
+    UNetModel, TimestepEmbedSequential                                           (ldm_unet.py)
     SubjBasisGenerator, Arc2FaceID2ImgPrompt, CLIPTextModelWrapper, CLIPAttentionMKV   (subj_basis_generator.py)
 
 The directory is named ``adaface-dev_b200`` (not importable as is); import it as ``adaface_dev_b200``
@@ -16,6 +17,7 @@ from .attn_processor import (AttnProcessor_LoRA_Capture, Attention, LoraDoraLine
                              gen_gradient_scaler, img_mask_to_key_mask)
 from .ldm_attention import CrossAttention, FeedForward, GEGLU, BasicTransformerBlock, SpatialTransformer  # noqa: F401
 from .ldm_unet_blocks import ResBlock, Upsample, Downsample  # noqa: F401
+from .ldm_unet import UNetModel, TimestepEmbedSequential  # noqa: F401
 from .subj_basis_generator import (SubjBasisGenerator, Arc2FaceID2ImgPrompt, FrozenCLIPTextEncoder, CLIPTextModelWrapper,  # noqa: F401
                                    CLIPAttentionMKV, CLIPTextConfig, template_ids)
 from .build import build  # noqa: F401

@@ -38,6 +38,7 @@ SIGNATURES = {
     "adaface_groupnorm_act_tokens_ws_floats": [_i64, _i64, _i64],
     "adaface_silu_fwd": [_p, _i32, _p, _i64, _p],
     "adaface_upsample2x_tokens": [_p, _p, _i64, _i64, _i64, _i64, _p],
+    "adaface_timestep_embedding": [_p, _i64, _i64, _f32, _p, _p],
     # ---- backward (ABI v2)
     "adaface_attn_bwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _p,
                          _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _i32, _f32, _p],

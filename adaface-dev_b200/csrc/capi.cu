@@ -156,6 +156,7 @@ int groupnorm_act_tokens_fwd(const void*, const float*, const float*, int64_t, i
 int64_t groupnorm_act_tokens_ws_floats(int64_t, int64_t, int64_t);
 int silu_fwd(const void*, int, void*, int64_t, cudaStream_t);
 int upsample2x_tokens(const void*, void*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
+int timestep_embedding(const float*, int64_t, int64_t, float, void*, cudaStream_t);
 
 }  // namespace adaface
 
@@ -262,6 +263,10 @@ int64_t adaface_groupnorm_act_tokens_ws_floats(int64_t B, int64_t HW, int64_t gr
 int adaface_silu_fwd(const void* x, int x_dtype, void* y, int64_t n, void* stream) { return silu_fwd(x, x_dtype, y, n, (cudaStream_t)stream); }
 int adaface_upsample2x_tokens(const void* x, void* y, int64_t B, int64_t H, int64_t W, int64_t C, void* stream) {
   return upsample2x_tokens(x, y, B, H, W, C, (cudaStream_t)stream);
+}
+
+int adaface_timestep_embedding(const float* t, int64_t B, int64_t dim, float max_period, void* out, void* stream) {
+  return timestep_embedding(t, B, dim, max_period, out, (cudaStream_t)stream);
 }
 
 int adaface_tokens_to_nchw_add(const void* t, const void* x_in, int x_dtype, void* out, int64_t B, int64_t C, int64_t HW,

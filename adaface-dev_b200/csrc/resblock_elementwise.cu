@@ -13,17 +13,17 @@ namespace adaface {
 
 extern long long g_launch_count;
 
-constexpr int GN_ROWS = 64;        // rows of one image summed by one CTA of the partial kernel
+constexpr int GN_ROWS = 64;        // most rows of one image summed by one CTA of the partial kernel (fewer for small maps)
 constexpr int GN_MAX_PAIRS = 1280; // C <= 2560
 
 // part[((b * chunks) + chunk) * groups + g] = (sum, sum of squares) over rows [chunk * GN_ROWS, +GN_ROWS) of group g.
 // Threads walk channel PAIRS (a pair never straddles a group: C / groups is even), so every load instruction of a warp
 // reads 128 contiguous bytes of one row.
 __global__ void __launch_bounds__(256) gn_tokens_partial_kernel(const bf16* __restrict__ x, float2* __restrict__ part, int C, int HW,
-                                                                 int groups) {
+                                                                 int groups, int rows) {
   __shared__ float ps[GN_MAX_PAIRS], pq[GN_MAX_PAIRS];
   const int chunk = blockIdx.x, b = blockIdx.y, chunks = gridDim.x;
-  const int r0 = chunk * GN_ROWS, r1 = min(HW, r0 + GN_ROWS);
+  const int r0 = chunk * rows, r1 = min(HW, r0 + rows);
   const int pairs = C >> 1;
   const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(x + ((long long)b * HW + r0) * C);
   for (int p = threadIdx.x; p < pairs; p += blockDim.x) {
@@ -122,6 +122,14 @@ __global__ void __launch_bounds__(256) gn_tokens_apply_kernel(const bf16* __rest
   }
 }
 
+// rows per CTA of the partial kernel: ~2 CTAs per SM when the map is small, never more than GN_ROWS
+static int gn_partial_rows(int64_t B, int64_t HW) {
+  long long rows = (B * HW + 295) / 296;
+  if (rows < 4) rows = 4;
+  if (rows > GN_ROWS) rows = GN_ROWS;
+  return (int)rows;
+}
+
 int groupnorm_act_tokens_fwd(const void* x, const float* gamma, const float* beta, int64_t B, int64_t HW, int64_t C, int64_t groups,
                              float eps, int act, float* part_ws, float* a_ws, float* s_ws, void* y, cudaStream_t stream) {
   AF_CHECK(x && gamma && beta && part_ws && a_ws && s_ws && y, "groupnorm_act_tokens_fwd: null pointer");
@@ -131,8 +139,9 @@ int groupnorm_act_tokens_fwd(const void* x, const float* gamma, const float* bet
            (long long)groups);
   AF_CHECK(act == 0 || act == 1, "groupnorm_act_tokens_fwd: act %d (0 none | 1 SiLU)", act);
   AF_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "groupnorm_act_tokens_fwd: x / y must be 16-byte aligned");
-  const int chunks = (int)((HW + GN_ROWS - 1) / GN_ROWS);
-  gn_tokens_partial_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, 0, stream>>>((const bf16*)x, (float2*)part_ws, (int)C, (int)HW, (int)groups);
+  const int prow = gn_partial_rows(B, HW);
+  const int chunks = (int)((HW + prow - 1) / prow);
+  gn_tokens_partial_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, 0, stream>>>((const bf16*)x, (float2*)part_ws, (int)C, (int)HW, (int)groups, prow);
   gn_tokens_finalize_kernel<<<(unsigned)B, 256, 0, stream>>>((const float2*)part_ws, gamma, beta, a_ws, s_ws, (int)C, (int)HW, (int)groups, chunks, eps);
   long long rows = (B * HW + 295) / 296;            // ~2 CTAs per SM
   if (rows < 4) rows = 4;
@@ -147,7 +156,8 @@ int groupnorm_act_tokens_fwd(const void* x, const float* gamma, const float* bet
 }
 
 int64_t groupnorm_act_tokens_ws_floats(int64_t B, int64_t HW, int64_t groups) {
-  return 2 * B * ((HW + GN_ROWS - 1) / GN_ROWS) * groups;
+  const int prow = gn_partial_rows(B, HW);
+  return 2 * B * ((HW + prow - 1) / prow) * groups;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -197,6 +207,32 @@ int upsample2x_tokens(const void* x, void* y, int64_t B, int64_t H, int64_t W, i
   AF_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "upsample2x_tokens: x / y must be 16-byte aligned");
   const long long n_out = B * 4 * H * W * (C / 8);
   upsample2x_tokens_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, stream>>>((const uint4*)x, (uint4*)y, (int)H, (int)W, (int)(C / 8), n_out);
+  AF_CUDA(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sinusoidal timestep embedding (ldm/modules/diffusionmodules/util.py:154-174): out[b] = [cos(t_b f_i) | sin(t_b f_i)],
+// f_i = exp(-ln(max_period) i / half).  B x dim values: evaluated in double so that --use_fast_math cannot touch them.
+__global__ void __launch_bounds__(256) timestep_embedding_kernel(const float* __restrict__ t, bf16* __restrict__ out, int B, int dim,
+                                                                  float max_period) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * dim) return;
+  const int b = idx / dim, j = idx - b * dim, half = dim / 2;
+  float v = 0.f;
+  if (j < 2 * half) {
+    const int i = j < half ? j : j - half;
+    const float freq = (float)exp(-log((double)max_period) * (double)i / (double)half);
+    const float arg = t[b] * freq;
+    v = (float)(j < half ? cos((double)arg) : sin((double)arg));
+  }
+  out[idx] = __float2bfloat16(v);
+}
+
+int timestep_embedding(const float* t, int64_t B, int64_t dim, float max_period, void* out, cudaStream_t stream) {
+  AF_CHECK(t && out && B > 0 && dim > 1 && B * dim < (1ll << 31), "timestep_embedding: bad arguments");
+  timestep_embedding_kernel<<<(unsigned)((B * dim + 255) / 256), 256, 0, stream>>>(t, (bf16*)out, (int)B, (int)dim, max_period);
   AF_CUDA(cudaGetLastError());
   ++g_launch_count;
   return 0;

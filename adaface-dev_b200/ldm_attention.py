@@ -281,6 +281,22 @@ class SpatialTransformer(nn.Module):
             self._pack_key = key
         return self._pack
 
+    def forward_tokens(self, t_in, hw, context=None, mask=None):
+        """NHWC-resident entry (the U-Net mirror keeps activations as tokens): t_in bf16 [B, h*w, C] -> bf16 [B, h*w, C].
+        Same arithmetic as forward(); the norm runs tokens -> tokens and the residual rides in proj_out's epilogue."""
+        if torch.is_grad_enabled() and (t_in.requires_grad or (context is not None and context.requires_grad)):
+            raise NotImplementedError("SpatialTransformer backward is not built yet")
+        b, n, c = t_in.shape
+        h, w = hw
+        pk = self._weights()
+        t = ops.groupnorm_act_tokens(t_in, pk["gn_w"], pk["gn_b"], self.norm.num_groups, self.norm.eps, silu=False)   # :291
+        t = ops.proj(t.view(b * n, c), pk["w_in"], bias=pk["b_in"]).view(b, n, -1)                                   # :292
+        for block in self.transformer_blocks:
+            block.attn2.infeat_size = (h, w)
+            mask2 = F.interpolate(mask, size=(h, w), mode="nearest") if mask is not None else None
+            t = block(t, context=context, mask=mask2)
+        return ops.proj(t.reshape(b * n, -1), pk["w_out"], bias=pk["b_out"], residual=t_in.view(b * n, c)).view(b, n, c)   # :303-304
+
     def forward(self, x, context=None, mask=None):
         if not x.is_cuda:
             raise RuntimeError("adaface_b200 SpatialTransformer runs on CUDA only (no CPU fallback)")

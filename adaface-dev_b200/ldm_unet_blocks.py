@@ -23,11 +23,15 @@ from .ldm_attention import _bf16, _f32, _ver
 
 def _to_tokens(x):
     b, c, h, w = x.shape
+    if x.dtype not in (torch.bfloat16, torch.float32):
+        x = x.float()
     return ops.transpose(x.contiguous().view(b, c, h * w), out_dtype=torch.bfloat16)          # [B, h*w, C]
 
 
 def _to_nchw(t, hw, dtype):
     b, _, c = t.shape
+    if dtype not in (torch.bfloat16, torch.float32):            # fp16 callers (the reference's autocast): through fp32
+        return ops.transpose(t, out_dtype=torch.float32).view(b, c, *hw).to(dtype)
     return ops.transpose(t, out_dtype=dtype).view(b, c, *hw)
 
 
@@ -77,8 +81,9 @@ class ResBlock(nn.Module):
             self._pack, self._pack_key = pk, key
         return self._pack
 
-    def forward_tokens(self, t, emb, hw):
-        """t bf16 [B, h*w, C] (NHWC), emb [B, emb_channels] -> bf16 [B, h*w, out_channels]."""
+    def forward_tokens(self, t, emb, hw, emb_act=None):
+        """t bf16 [B, h*w, C] (NHWC), emb [B, emb_channels] -> bf16 [B, h*w, out_channels].  ``emb_act`` = SiLU(emb) as
+        bf16 when the caller has already evaluated it (the U-Net shares it between its ResBlocks)."""
         _no_grad_only("ResBlock", t, emb)
         if self.training and self.dropout > 0:
             raise NotImplementedError("ResBlock: dropout > 0 in training mode is not built (the reference trains with dropout 0)")
@@ -86,7 +91,9 @@ class ResBlock(nn.Module):
         b = t.shape[0]
         gn1, gn2 = self.in_layers[0], self.out_layers[0]
         h = ops.groupnorm_act_tokens(t, pk["gn1_w"], pk["gn1_b"], gn1.num_groups, gn1.eps, silu=True)                 # :240 in_layers[:-1]
-        emb_out = ops.proj(ops.silu(emb.contiguous()), pk["w_emb"], bias=pk["b_emb"], out_dtype=torch.float32)       # :248
+        if emb_act is None:
+            emb_act = ops.silu(emb.contiguous())
+        emb_out = ops.proj(emb_act, pk["w_emb"], bias=pk["b_emb"], out_dtype=torch.float32)                           # :248
         h = ops.conv3x3(h, pk["w1"], hw, bias=pk["b1"], rowbias=emb_out)                                              # :247 + :257
         h = ops.groupnorm_act_tokens(h, pk["gn2_w"], pk["gn2_b"], gn2.num_groups, gn2.eps, silu=True)                 # :258
         if "w_skip" not in pk:

@@ -370,6 +370,16 @@ def silu(x):
     return y
 
 
+def timestep_embedding(timesteps, dim, max_period=10000):
+    """Sinusoidal embedding of a 1-D batch of timesteps -> bf16 [B, dim] (adaface_timestep_embedding)."""
+    if not timesteps.is_cuda or timesteps.dim() != 1:
+        raise RuntimeError("timestep_embedding: `timesteps` must be a 1-D CUDA tensor (no CPU fallback exists)")
+    t = timesteps.float().contiguous()
+    out = torch.empty((t.shape[0], dim), device=t.device, dtype=torch.bfloat16)
+    _lib.call("adaface_timestep_embedding", _ptr(t), t.shape[0], int(dim), float(max_period), _ptr(out), _stream())
+    return out
+
+
 def upsample2x_tokens(x, hw):
     """Nearest 2x of NHWC tokens: bf16 [B, h*w, C] -> [B, 4*h*w, C] (adaface_upsample2x_tokens)."""
     _need(x, "x", torch.bfloat16)

@@ -173,6 +173,9 @@ int adaface_silu_fwd(const void* x, int x_dtype, void* y, int64_t n, void* strea
 /* Nearest-neighbour 2x (F.interpolate(scale_factor=2, mode="nearest"), openaimodel.py:116): x bf16 [B, H, W, C] ->
  * y [B, 2H, 2W, C]. */
 int adaface_upsample2x_tokens(const void* x, void* y, int64_t B, int64_t H, int64_t W, int64_t C, void* stream);
+/* Sinusoidal timestep embedding (ldm/modules/diffusionmodules/util.py:154-174): t fp32 [B] -> out bf16 [B, dim] =
+ * [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(max_period) i / (dim / 2)); an odd last column is zero. */
+int adaface_timestep_embedding(const float* t, int64_t B, int64_t dim, float max_period, void* out, void* stream);
 
 /* ---- K5: backward kernels of the stage-2 training step (ddpm.py:1645-1707 back-propagates through the `sc`
  * instance of the U-Net into the LoRA / DoRA adapters, cross_attn_scale_factor and, via the context, SubjBasisGenerator).

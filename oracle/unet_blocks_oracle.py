@@ -69,3 +69,97 @@ def upsample(w, x):
 def downsample(w, x):
     """Downsample.forward (openaimodel.py:159-161), use_conv: 3x3, stride 2, padding 1."""
     return conv3x3(x, w["conv_w"], w["conv_b"], stride=2)
+
+
+# ----------------------------------------------------------------------------------------------
+# The whole U-Net (openaimodel.py:414-960), driven by a reference-format state dict.
+def timestep_embedding(timesteps, dim, max_period=10000):
+    """ldm/modules/diffusionmodules/util.py:154-174 (repeat_only=False)."""
+    import math
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    args = timesteps[:, None].float() * freqs[None]
+    emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    if dim % 2:
+        emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)
+    return emb
+
+
+def unet_layout(cfg):
+    """Layer kinds of input_blocks / middle_block / output_blocks as UNetModel.__init__ builds them (:520-684) for
+    use_spatial_transformer=True, conv_resample=True, resblock_updown=False: lists of 'conv_in' | 'res' | 'attn' | 'down' | 'up'."""
+    nrb, mults, ares = cfg["num_res_blocks"], list(cfg["channel_mult"]), set(cfg["attention_resolutions"])
+    inp, ds = [["conv_in"]], 1
+    for level in range(len(mults)):
+        for _ in range(nrb):
+            inp.append(["res", "attn"] if ds in ares else ["res"])
+        if level != len(mults) - 1:
+            inp.append(["down"])
+            ds *= 2
+    out = []
+    for level in reversed(range(len(mults))):
+        for i in range(nrb + 1):
+            layers = ["res", "attn"] if ds in ares else ["res"]
+            if level and i == nrb:
+                layers.append("up")
+                ds //= 2
+            out.append(layers)
+    return inp, ["res", "attn", "res"], out
+
+
+def _res_weights(sd, p):
+    w = {"gn1_w": sd[p + "in_layers.0.weight"], "gn1_b": sd[p + "in_layers.0.bias"], "conv1_w": sd[p + "in_layers.2.weight"],
+         "conv1_b": sd[p + "in_layers.2.bias"], "emb_w": sd[p + "emb_layers.1.weight"], "emb_b": sd[p + "emb_layers.1.bias"],
+         "gn2_w": sd[p + "out_layers.0.weight"], "gn2_b": sd[p + "out_layers.0.bias"], "conv2_w": sd[p + "out_layers.3.weight"],
+         "conv2_b": sd[p + "out_layers.3.bias"]}
+    if p + "skip_connection.weight" in sd:
+        w["skip_w"], w["skip_b"] = sd[p + "skip_connection.weight"], sd[p + "skip_connection.bias"]
+    return w
+
+
+def _spatial_weights(sd, p):
+    b = p + "transformer_blocks.0."
+    w = {"gn_w": sd[p + "norm.weight"], "gn_b": sd[p + "norm.bias"], "proj_in_w": sd[p + "proj_in.weight"][:, :, 0, 0],
+         "proj_in_b": sd[p + "proj_in.bias"], "proj_out_w": sd[p + "proj_out.weight"][:, :, 0, 0], "proj_out_b": sd[p + "proj_out.bias"],
+         "ff_proj_w": sd[b + "ff.net.0.proj.weight"], "ff_proj_b": sd[b + "ff.net.0.proj.bias"], "ff_out_w": sd[b + "ff.net.2.weight"],
+         "ff_out_b": sd[b + "ff.net.2.bias"]}
+    for i in (1, 2, 3):
+        w[f"norm{i}_w"], w[f"norm{i}_b"] = sd[b + f"norm{i}.weight"], sd[b + f"norm{i}.bias"]
+    for a in ("attn1", "attn2"):
+        w[a] = {"to_q": sd[b + a + ".to_q.weight"], "to_k": sd[b + a + ".to_k.weight"], "to_v": sd[b + a + ".to_v.weight"],
+                "to_out_w": sd[b + a + ".to_out.0.weight"], "to_out_b": sd[b + a + ".to_out.0.bias"]}
+    return w
+
+
+def unet_forward(sd, cfg, x, timesteps, context, mask=None):
+    """UNetModel.forward (openaimodel.py:820-960) without capture: time embedding -> input blocks (skips pushed) -> middle
+    block -> output blocks (skip popped and concatenated on the channel axis, :925) -> out (norm, SiLU, conv)."""
+    from .attn_oracle import spatial_transformer
+    heads = cfg["num_heads"]
+
+    def run(layers, prefix, h, emb):
+        for j, kind in enumerate(layers):
+            p = f"{prefix}{j}."
+            if kind == "conv_in":
+                h = conv3x3(h, sd[p + "weight"], sd[p + "bias"])
+            elif kind == "res":
+                h = res_block(_res_weights(sd, p), h, emb)
+            elif kind == "attn":
+                h = spatial_transformer(_spatial_weights(sd, p), h, context=context, mask=mask, heads=heads)
+            elif kind == "down":
+                h = downsample({"conv_w": sd[p + "op.weight"], "conv_b": sd[p + "op.bias"]}, h)
+            else:
+                h = upsample({"conv_w": sd[p + "conv.weight"], "conv_b": sd[p + "conv.bias"]}, h)
+        return h
+
+    inp, mid, out = unet_layout(cfg)
+    t_emb = timestep_embedding(timesteps, cfg["model_channels"])
+    emb = F.linear(silu(F.linear(t_emb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])), sd["time_embed.2.weight"], sd["time_embed.2.bias"])
+    h, hs = x, []
+    for i, layers in enumerate(inp):
+        h = run(layers, f"input_blocks.{i}.", h, emb)
+        hs.append(h)
+    h = run(mid, "middle_block.", h, emb)
+    for i, layers in enumerate(out):
+        h = run(layers, f"output_blocks.{i}.", torch.cat([h, hs.pop()], dim=1), emb)
+    return conv3x3(silu(group_norm32(h, sd["out.0.weight"], sd["out.0.bias"])), sd["out.2.weight"], sd["out.2.bias"])

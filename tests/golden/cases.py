@@ -194,6 +194,43 @@ def build_unet_block_case(name):
     return case
 
 
+# The whole U-Net (ldm/modules/diffusionmodules/openaimodel.py:414-960) on a two-level SD-1.5-shaped configuration (320 / 640
+# channels, head dims 40 / 80, attention at both levels).  Weights: every entry of the state dict, in sorted key order, from one
+# seeded stream (so that the reference module, the oracle and the mirror are filled identically from their own key sets).
+UNET_CFG_SMALL = dict(in_channels=4, model_channels=320, out_channels=4, num_res_blocks=1, attention_resolutions=[1, 2],
+                      channel_mult=(1, 2), num_heads=8, use_spatial_transformer=True, context_dim=768, transformer_depth=1, legacy=False)
+UNET_CASES = {
+    "unet_small": dict(seed=61, cfg=UNET_CFG_SMALL, B=2, h=16, w=16, S=77, mask=True),
+}
+
+
+def unet_state_dict(shapes, seed):
+    """shapes: {state-dict key: shape}.  >= 2-D weights ~ N(0, 1/fan_in) (bf16-exact), norm weights 1 + 0.1 N, biases 0.02 N."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for k in sorted(shapes):
+        shp = tuple(shapes[k])
+        if len(shp) >= 2:
+            sd[k] = normal(rng, shp, 1 / math.sqrt(int(np.prod(shp[1:]))))
+        elif k.endswith("weight"):
+            sd[k] = bf16r(1 + 0.1 * rng.standard_normal(shp))
+        else:
+            sd[k] = normal(rng, shp, 0.02)
+    return sd
+
+
+def build_unet_case(name):
+    sp = UNET_CASES[name]
+    rng = np.random.default_rng(sp["seed"])
+    B, h, w = sp["B"], sp["h"], sp["w"]
+    case = dict(spec=sp)
+    case["x"] = normal(rng, (B, sp["cfg"]["in_channels"], h, w))
+    case["timesteps"] = rng.integers(0, 1000, size=(B,)).astype(np.int64)
+    case["context"] = normal(rng, (B, sp["S"], sp["cfg"]["context_dim"]))
+    case["mask"] = img_mask(rng, B, 64) if sp.get("mask") else None
+    return case
+
+
 # SubjBasisGenerator / CLIP-shaped encoder (surface 3).  E=768, 12 heads x 64, MLP 3072, 77 positions.
 SBG_CASES = {
     "mkv_m1":   dict(seed=41, BS=2, T=77, mult=1, layers=0),

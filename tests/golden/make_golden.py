@@ -85,6 +85,8 @@ def install_stubs():
     _mod("peft.tuners", lora=lora)
     _mod("peft.tuners.lora.dora", DoraLinearLayer=_Dummy)
     _mod("peft.tuners.tuners_utils", BaseTunerLayer=_Dummy)
+    _mod("omegaconf")                                   # UNetModel.__init__ only compares type(context_dim) with ListConfig
+    _mod("omegaconf.listconfig", ListConfig=_Dummy)
     sys.path.insert(0, REF)
     # adaface/util.py drags in diffusers pipelines + the un-vendored ConsistentID package; the two
     # helpers the hot path needs from it are identical copies of dalc:23-67.
@@ -246,6 +248,25 @@ def run_unet_block_cases():
         save(name, case, {"out": out})
 
 
+def run_unet_cases():
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    from ldm.modules.attention import BasicTransformerBlock
+
+    for name in C.UNET_CASES:
+        case = C.build_unet_case(name)
+        sp = case["spec"]
+        m = UNetModel(**sp["cfg"]).eval()
+        for mod in m.modules():
+            if isinstance(mod, BasicTransformerBlock):
+                mod.checkpoint = False
+        sd = C.unet_state_dict({k: v.shape for k, v in m.state_dict().items()}, sp["seed"] + 1000)
+        m.load_state_dict({k: T(v) for k, v in sd.items()})
+        with torch.no_grad():
+            out = m(T(case["x"]), T(case["timesteps"]), context=T(case["context"]),
+                    extra_info={"img_mask": T(case["mask"]), "capture_ca_activations": False})
+        save(name, case, {"out": out})
+
+
 # --------------------------------------------------------------------------------- SBG cases
 class _EncOut:
     """Minimal stand-in for HF BaseModelOutput: tuple-indexable and attribute-addressable."""
@@ -362,5 +383,7 @@ if __name__ == "__main__":
         run_spatial_cases()
     if only in ("", "unet_blocks"):
         run_unet_block_cases()
+    if only in ("", "unet"):
+        run_unet_cases()
     if only in ("", "sbg"):
         run_sbg_cases()

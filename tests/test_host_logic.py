@@ -146,3 +146,56 @@ def test_cfg_pair_sharding_indices():
         assert idx.tolist() == list(range(b, e)) + [n + i for i in range(b, e)]
         seen += list(range(b, e))
     assert seen == list(range(n))
+
+
+def test_conv3x3_weight_pack_layout():
+    """ops.pack_conv3x3_weight: K index = (ky*3 + kx) * Kc + ci with Kc = Cin rounded up to 64 and zero padding, i.e. a
+    pixel's 3x3 neighbourhood in NHWC order times the packed row reproduces the convolution (oracle conv3x3)."""
+    from oracle import unet_blocks_oracle as ub
+    torch.manual_seed(1)
+    for cin, cout in ((8, 16), (72, 24), (128, 8)):
+        w = torch.randn(cout, cin, 3, 3).bfloat16().float()
+        wp = a.ops.pack_conv3x3_weight(w)
+        kc = (cin + 63) // 64 * 64
+        assert wp.dtype == torch.bfloat16 and tuple(wp.shape) == (cout, 9 * kc)
+        x = torch.randn(1, cin, 5, 6)
+        xp = F.pad(x, (1, 1, 1, 1)).permute(0, 2, 3, 1)                          # NHWC, padded
+        rows = []
+        for y in range(5):
+            for xx in range(6):
+                patch = torch.zeros(9, kc)
+                patch[:, :cin] = xp[0, y:y + 3, xx:xx + 3].reshape(9, cin)
+                rows.append(patch.reshape(-1))
+        got = (torch.stack(rows) @ wp.float().T).reshape(5, 6, cout).permute(2, 0, 1)
+        assert (got - ub.conv3x3(x, w, None)[0]).abs().max().item() < 1e-4
+    with pytest.raises(ValueError):
+        a.ops.pack_conv3x3_weight(torch.zeros(4, 4, 1, 1))
+
+
+def test_unet_mirror_structure_matches_reference_layout():
+    """The mirror's module tree (built on the meta device) follows UNetModel.__init__ (openaimodel.py:520-684) as restated by
+    the oracle's unet_layout: layer kinds per block, channel counts of the skip concatenations, state-dict key names."""
+    from oracle import unet_blocks_oracle as ub
+    kinds = {a.ResBlock: "res", a.SpatialTransformer: "attn", a.Downsample: "down", a.Upsample: "up", torch.nn.Conv2d: "conv_in"}
+    sd15 = dict(in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2, attention_resolutions=[4, 2, 1],
+                channel_mult=(1, 2, 4, 4), num_heads=8, use_spatial_transformer=True, context_dim=768, transformer_depth=1, legacy=False)
+    for cfg in (sd15, C.UNET_CFG_SMALL):
+        with torch.device("meta"):
+            m = a.UNetModel(**cfg)
+        inp, mid, out = ub.unet_layout(cfg)
+        assert [[kinds[type(l)] for l in b] for b in m.input_blocks] == inp
+        assert [kinds[type(l)] for l in m.middle_block] == mid
+        assert [[kinds[type(l)] for l in b] for b in m.output_blocks] == out
+    with torch.device("meta"):
+        m = a.UNetModel(**sd15)
+    assert sum(p.numel() for p in m.parameters()) == 859520964            # the SD-1.5 U-Net
+    assert [b[0].channels for b in m.output_blocks] == [2560, 2560, 2560, 2560, 2560, 1920, 1920, 1280, 960, 960, 640, 640]
+    assert m._cross_attn(24) is m.output_blocks[11][1].transformer_blocks[0].attn2 and m._cross_attn(12) is m.middle_block[1].transformer_blocks[0].attn2
+    keys = set(m.state_dict())
+    assert {"time_embed.0.weight", "input_blocks.0.0.weight", "input_blocks.3.0.op.weight", "middle_block.1.proj_in.weight",
+            "output_blocks.2.1.conv.weight", "output_blocks.11.1.transformer_blocks.0.attn2.to_k.weight", "out.2.bias"} <= keys
+    with pytest.raises(NotImplementedError):
+        a.UNetModel(4, 320, 4, 2, [4], num_heads=8)                       # no spatial transformer: not the SD-1.5 form
+    x = torch.zeros(1, 4, 8, 8)
+    with pytest.raises(RuntimeError):
+        m(x, torch.zeros(1), context=torch.zeros(1, 77, 768))            # CPU tensors: there is no fallback

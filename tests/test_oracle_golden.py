@@ -159,3 +159,20 @@ def test_unet_blocks_oracle_vs_reference(name):
     else:
         out = ub.downsample(t["w"], t["x"])
     close(out, g["out"], atol=5e-5, what=name)
+
+
+@pytest.mark.parametrize("name", list(C.UNET_CASES))
+def test_unet_oracle_vs_reference(name):
+    """UNetModel.forward (ldm/modules/diffusionmodules/openaimodel.py:820-960) against the reference module on a two-level
+    SD-1.5-shaped configuration: time embedding, ResBlocks, SpatialTransformers, Down / Upsample, skip concatenations."""
+    from oracle import unet_blocks_oracle as ub
+    case = C.build_unet_case(name)
+    sp = case["spec"]
+    g = load(name, case)
+    import adaface_dev_b200 as a      # module structure only (CPU construction on the meta device; no kernels are called)
+    with torch.device("meta"):
+        shapes = {k: v.shape for k, v in a.UNetModel(**sp["cfg"]).state_dict().items()}
+    sd = {k: torch.from_numpy(v) for k, v in C.unet_state_dict(shapes, sp["seed"] + 1000).items()}
+    t = C.to_torch({k: v for k, v in case.items() if k != "spec"})
+    out = ub.unet_forward(sd, sp["cfg"], t["x"], t["timesteps"], t["context"], mask=t["mask"])
+    close(out, g["out"], atol=2e-4, what=name)
