@@ -35,7 +35,7 @@ SIGNATURES = {
     "adaface_conv3x3_fwd": [_p, _i64, _i64, _i64, _i64, _p, _p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _i32, _p, _i64, _i32, _i64,
                             _i32, _i32, _p],
     "adaface_groupnorm_act_tokens_fwd": [_p, _p, _p, _i64, _i64, _i64, _i64, _f32, _i32, _p, _p, _p, _p, _p],
-    "adaface_groupnorm_act_tokens_ws_floats": [_i64, _i64, _i64],
+    "adaface_groupnorm_act_tokens_ws_floats": [_i64, _i64, _i64, _i64],
     "adaface_silu_fwd": [_p, _i32, _p, _i64, _p],
     "adaface_upsample2x_tokens": [_p, _p, _i64, _i64, _i64, _i64, _p],
     "adaface_timestep_embedding": [_p, _i64, _i64, _f32, _p, _p],

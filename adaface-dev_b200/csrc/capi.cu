@@ -153,7 +153,7 @@ int conv3x3_fwd(const void*, int64_t, int64_t, int64_t, int64_t, const void*, co
                 const float*, const float*, const void*, int64_t, int, void*, int64_t, int, int64_t, int, int, cudaStream_t);
 int groupnorm_act_tokens_fwd(const void*, const float*, const float*, int64_t, int64_t, int64_t, int64_t, float, int, float*, float*,
                              float*, void*, cudaStream_t);
-int64_t groupnorm_act_tokens_ws_floats(int64_t, int64_t, int64_t);
+int64_t groupnorm_act_tokens_ws_floats(int64_t, int64_t, int64_t, int64_t);
 int silu_fwd(const void*, int, void*, int64_t, cudaStream_t);
 int upsample2x_tokens(const void*, void*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
 int timestep_embedding(const float*, int64_t, int64_t, float, void*, cudaStream_t);
@@ -257,8 +257,8 @@ int adaface_groupnorm_act_tokens_fwd(const void* x, const float* gamma, const fl
                                      void* stream) {
   return groupnorm_act_tokens_fwd(x, gamma, beta, B, HW, C, groups, eps, act, part_ws, a_ws, s_ws, y, (cudaStream_t)stream);
 }
-int64_t adaface_groupnorm_act_tokens_ws_floats(int64_t B, int64_t HW, int64_t groups) {
-  return groupnorm_act_tokens_ws_floats(B, HW, groups);
+int64_t adaface_groupnorm_act_tokens_ws_floats(int64_t B, int64_t HW, int64_t C, int64_t groups) {
+  return groupnorm_act_tokens_ws_floats(B, HW, C, groups);
 }
 int adaface_silu_fwd(const void* x, int x_dtype, void* y, int64_t n, void* stream) { return silu_fwd(x, x_dtype, y, n, (cudaStream_t)stream); }
 int adaface_upsample2x_tokens(const void* x, void* y, int64_t B, int64_t H, int64_t W, int64_t C, void* stream) {

@@ -42,6 +42,12 @@ struct GemmEpilogue {
   int cv_stride;      // 1 | 2
   int num_m;          // number of M tiles (GEMM: ceil(M / 128))
   const float* rowbias;   // fp32 [images, N] added per output image (the ResBlock's time-embedding term), or NULL
+  // split-K (CONV only): a small-M convolution (levels C / D: 4-16 M tiles, K up to 23040) would leave most SMs idle and
+  // stream its K range through a handful of CTAs; `splits` CTAs share one output tile instead, each accumulating
+  // `kb_per_split` K blocks and storing its raw fp32 partial tile to splitk_ws[split][M][N]; conv_splitk_reduce_kernel
+  // then sums the partials in fixed order and applies the epilogue terms.
+  int splits, kb_per_split;
+  float* splitk_ws;
 };
 
 // Tensor maps of the CONV A operand: one for stride 1; one per input parity (py, px) for stride 2.
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
   const int lane = threadIdx.x & 31;
   const int num_kb = ep.num_kb1 + ep.num_kb2;
   const int num_n = (ep.N + BN - 1) / BN;
-  const int num_tiles = ep.num_m * num_n;
+  const int num_tiles = ep.num_m * num_n * (CONV ? ep.splits : 1);
 
   if (warp == kTma && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -289,7 +295,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
     if (elect_one()) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n, n0 = (tile % num_n) * BN;
+        int tile_mn = tile, kb_lo = 0, kb_hi = num_kb;
+        if constexpr (CONV) {
+          if (ep.splits > 1) {
+            const int sp = tile / (ep.num_m * num_n);
+            tile_mn = tile - sp * (ep.num_m * num_n);
+            kb_lo = sp * ep.kb_per_split;
+            kb_hi = min(num_kb, kb_lo + ep.kb_per_split);
+          }
+        }
+        const int m_blk = tile_mn / num_n, n0 = (tile_mn % num_n) * BN;
         int m0 = m_blk * GEMM_BM, img0 = 0, y0 = 0;
         if constexpr (CONV) {
           if (ep.cv_imgs > 1) {
@@ -302,7 +317,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
             m0 = img0 * ep.cv_HW + yc * ep.cv_img_rows;
           }
         }
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
           uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
@@ -346,7 +361,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
         mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1);      // epilogue drained this accumulator (2 tiles ago)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        int kb_lo = 0, kb_hi = num_kb;
+        if constexpr (CONV) {
+          if (ep.splits > 1) {
+            kb_lo = (tile / (ep.num_m * num_n)) * ep.kb_per_split;
+            kb_hi = min(num_kb, kb_lo + ep.kb_per_split);
+          }
+        }
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(&full_bar[s], (it / STAGES) & 1);
           tc_fence_after();
@@ -356,7 +378,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // advancing 16 K-elements inside the swizzle span = +32 bytes on the start address
             umma_bf16(d_tmem, make_smem_desc_sw128(sa + k * 32), make_smem_desc_sw128(sb + k * 32), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+                      (kb > kb_lo || k != 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);   // smem stage reusable once these MMAs have read it
         }
@@ -371,7 +393,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
     uint32_t t = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const uint32_t buf = t & 1;
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      int tile_mn = tile, split = 0;
+      if constexpr (CONV) {
+        if (ep.splits > 1) {
+          split = tile / (ep.num_m * num_n);
+          tile_mn = tile - split * (ep.num_m * num_n);
+        }
+      }
+      const int m_blk = tile_mn / num_n, n_blk = tile_mn % num_n;
       int row = m_blk * GEMM_BM + q * 32 + lane;
       int row_end = ep.M;
       const float* rowbias = nullptr;
@@ -413,6 +442,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
             mbar_arrive(&acc_empty[buf]);
             arrived = true;
           }
+          if constexpr (CONV) {
+            if (ep.splits > 1) {      // raw fp32 partial tile: the epilogue terms are applied by the reduce kernel
+              if (row_ok) {
+                float* dst = ep.splitk_ws + ((long long)split * ep.M + row) * ep.N + n_blk * BN + c0;
+                const int nv = min(32, ep.N - (n_blk * BN + c0));
+                if (nv == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+                  for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (j < nv) dst[j] = __uint_as_float(v[j]);
+                }
+              }
+              continue;
+            }
+          }
           const bool full = geglu || (n_blk * BN + c0 + 32 <= ep.N);
           if (full) epilogue_chunk32<BN, true>(ep, v, g, row, row_ok, row_end, rowbias, n_blk, c0, store_stage + warp * 2048, lane);
           else epilogue_chunk32<BN, false>(ep, v, g, row, row_ok, row_end, rowbias, n_blk, c0, store_stage + warp * 2048, lane);
@@ -449,7 +496,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     AF_CUDA(cudaGetDevice(&dev));
     AF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int tiles = n_tiles * ep.num_m;
+  const int tiles = n_tiles * ep.num_m * (CONV ? ep.splits : 1);
   dim3 grid(tiles < num_sms ? tiles : num_sms);
   AF_CUDA(launch_pdl(1, gemm_tn_tcgen05_kernel<BN, CONV>, grid, dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tA, tB, tA2, tB2, cmaps, ep));
   AF_CUDA(cudaGetLastError());
@@ -552,6 +599,9 @@ int proj_lora_fwd(const void* x, int64_t ldx, const void* w, const void* t, int6
   ep.cv_kc = ep.cv_W = ep.cv_HW = ep.cv_img_rows = ep.cv_tpi = ep.cv_imgs = ep.cv_stride = 0;
   ep.num_m = (int)m_tiles;
   ep.rowbias = nullptr;
+  ep.splits = 1;
+  ep.kb_per_split = 0;
+  ep.splitk_ws = nullptr;
   const int n_tiles = (int)((N + BN - 1) / BN);
   switch (BN) {
     case 64: return launch_gemm<64>(tA, tB, tA2, tB2, ep, n_tiles, stream);
@@ -562,6 +612,62 @@ int proj_lora_fwd(const void* x, int64_t ldx, const void* w, const void* t, int6
   }
   set_error("proj_lora_fwd: unreachable tile width %d", BN);
   return 1;
+}
+
+// y[row, c] = act(colscale[c] * sum_s ws[s][row][c] + bias[c] + rowbias[row / HW][c]) + residual[row, c]: the epilogue of a
+// split-K convolution.  One thread per 4 columns (N % 4 == 0), partials summed in split order (deterministic).
+__global__ void __launch_bounds__(256) conv_splitk_reduce_kernel(const GemmEpilogue ep) {
+  const int n4 = ep.N >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)ep.M * n4) return;
+  const int row = (int)(idx / n4), c = (int)(idx - (long long)row * n4) << 2;
+  const long long plane = (long long)ep.M * ep.N;
+  const float* p = ep.splitk_ws + (long long)row * ep.N + c;
+  float4 acc = *reinterpret_cast<const float4*>(p);
+  for (int s = 1; s < ep.splits; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(p + s * plane);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  float f[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (ep.colscale) f[j] *= ep.colscale[c + j];
+    if (ep.bias) f[j] += ep.bias[c + j];
+    if (ep.rowbias) f[j] += ep.rowbias[(long long)(row / ep.cv_HW) * ep.N + c + j];
+    if (ep.act == ADAFACE_ACT_QUICK_GELU) f[j] = f[j] / (1.f + __expf(-1.702f * f[j]));
+    if (ep.residual) {
+      f[j] += ep.res_f32 ? reinterpret_cast<const float*>(ep.residual)[(long long)row * ep.ldr + c + j]
+                         : __bfloat162float(reinterpret_cast<const bf16*>(ep.residual)[(long long)row * ep.ldr + c + j]);
+    }
+  }
+  if (ep.y_f32) {
+    float* y = reinterpret_cast<float*>(ep.y) + (long long)row * ep.ldy + c;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = f[j];
+  } else {
+    bf16* y = reinterpret_cast<bf16*>(ep.y) + (long long)row * ep.ldy + c;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = __float2bfloat16(f[j]);
+  }
+}
+
+// Split-K workspace: one buffer per device, grown on demand (stream-ordered allocation is not needed: the buffer is only
+// ever touched by kernels of the calling stream, and a larger request replaces it after a device synchronisation).
+static float* splitk_workspace(size_t floats) {
+  static float* ws = nullptr;
+  static size_t cap = 0;
+  if (floats > cap) {
+    if (ws) {
+      if (cudaDeviceSynchronize() != cudaSuccess) return nullptr;
+      cudaFree(ws);
+      ws = nullptr;
+      cap = 0;
+    }
+    const size_t want = floats < (size_t(8) << 20) ? (size_t(8) << 20) : floats;      // >= 32 MB: covers every SD-1.5 shape
+    if (cudaMalloc(&ws, want * sizeof(float)) != cudaSuccess) return nullptr;
+    cap = want;
+  }
+  return ws;
 }
 
 // 3x3 convolution (padding 1, stride 1 | 2) over an NHWC activation: see the CONV notes at the kernel.
@@ -622,8 +728,40 @@ int conv3x3_fwd(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, con
   ep.cv_stride = stride;
   ep.num_m = (int)(imgs > 1 ? (B + imgs - 1) / imgs : B * tpi);
   ep.rowbias = rowbias;
+  ep.splits = 1;
+  ep.kb_per_split = 0;
+  ep.splitk_ws = nullptr;
 
-  const int BN = pick_tile_width(Cout, ep.num_m, act);
+  int BN = pick_tile_width(Cout, ep.num_m, act);
+  {
+    // split-K when the output tiles cannot fill half the SMs and the K loop is long (levels C / D of the U-Net)
+    static int splitk = -1;
+    if (splitk < 0) {
+      const char* e = getenv("ADAFACE_CONV_SPLITK");       // A/B switch: 0 = never split
+      splitk = e ? atoi(e) : 1;
+    }
+    const int num_kb = ep.num_kb1 + ep.num_kb2;
+    if (splitk && Cout % 4 == 0 && num_kb >= 48) {
+      int bn = BN;
+      if (Cout % 128 == 0 && (long long)ep.num_m * (Cout / 128) <= 74) bn = 128;      // wider tiles: each A tile is re-read by fewer CTAs
+      const long long tiles = (long long)ep.num_m * ((Cout + bn - 1) / bn);
+      if (tiles <= 74) {
+        int sp = (int)(148 / tiles);
+        if (sp > 8) sp = 8;
+        if (sp > num_kb / 16) sp = num_kb / 16;
+        if (sp >= 2) {
+          const int per = (num_kb + sp - 1) / sp;
+          sp = (num_kb + per - 1) / per;                   // no empty split
+          float* ws = splitk_workspace((size_t)sp * (size_t)M * (size_t)Cout);
+          AF_CHECK(ws != nullptr, "conv3x3_fwd: cannot allocate the split-K workspace");
+          ep.splits = sp;
+          ep.kb_per_split = per;
+          ep.splitk_ws = ws;
+          BN = bn;
+        }
+      }
+    }
+  }
   ConvMaps cm;
   const bf16* xb = reinterpret_cast<const bf16*>(x);
   if (stride == 1) {
@@ -649,15 +787,23 @@ int conv3x3_fwd(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, con
     tB2 = tB;
   }
   const int n_tiles = (int)((Cout + BN - 1) / BN);
+  int rc;
   switch (BN) {
-    case 64: return launch_gemm<64, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm);
-    case 128: return launch_gemm<128, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm);
-    case 160: return launch_gemm<160, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm);
-    case 192: return launch_gemm<192, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm);
-    case 256: return launch_gemm<256, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm);
+    case 64: rc = launch_gemm<64, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm); break;
+    case 128: rc = launch_gemm<128, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm); break;
+    case 160: rc = launch_gemm<160, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm); break;
+    case 192: rc = launch_gemm<192, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm); break;
+    case 256: rc = launch_gemm<256, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm); break;
+    default:
+      set_error("conv3x3_fwd: unreachable tile width %d", BN);
+      return 1;
   }
-  set_error("conv3x3_fwd: unreachable tile width %d", BN);
-  return 1;
+  if (rc || ep.splits == 1) return rc;
+  const long long n_thr = (long long)M * (Cout / 4);
+  conv_splitk_reduce_kernel<<<(unsigned)((n_thr + 255) / 256), 256, 0, stream>>>(ep);
+  AF_CUDA(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
 }
 
 }  // namespace adaface

@@ -1,7 +1,7 @@
 // HBM-bound helpers of the U-Net ResBlock / Upsample path on NHWC ("tokens", [B, H*W, C] bf16) activations
 // (ldm/modules/diffusionmodules/openaimodel.py:92-277).  The convolutions themselves are the CONV
 // instantiation of the tcgen05 GEMM (gemm_tcgen05.cu); here:
-//   gn_tokens_partial / gn_tokens_finalize / gn_tokens_apply
+//   gn_tokens_stats | gn_tokens_partial + gn_tokens_finalize, then gn_tokens_apply
 //                     GroupNorm32 (fp32 statistics, util.py normalization() = GroupNorm(32, C)) + SiLU in front of each
 //                     3x3 convolution (openaimodel.py:203-207, 229-236), tokens in -> tokens out
 //   silu              SiLU of the time embedding in front of emb_layers' Linear (openaimodel.py:222-228)
@@ -82,6 +82,55 @@ __global__ void __launch_bounds__(256) gn_tokens_finalize_kernel(const float2* _
   }
 }
 
+constexpr int GN_STATS_THREADS = 1024;
+
+// One CTA per (group, image): mean / rstd of the group's [HW, C / groups] slab of the tokens, folded with the affine
+// parameters into a[b, c] = rstd * gamma[c], s[b, c] = beta[c] - mean * rstd * gamma[c].  Threads form a TR x TP grid
+// (TP = pairs per group rounded up to a power of two): a row of the slab is ppg adjacent bf16 pairs, rows are C apart.
+// 1024 threads so that each walks only HW / TR rows (the loop is latency-bound: one 4-byte load per row).
+// Fixed summation order: deterministic.
+template <int TP>
+__global__ void __launch_bounds__(GN_STATS_THREADS) gn_tokens_stats_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                                            const float* __restrict__ beta, float* __restrict__ a,
+                                                                            float* __restrict__ s, int C, int HW, int groups, float eps) {
+  constexpr int TR = GN_STATS_THREADS / TP;
+  __shared__ float red[2][32];
+  const int g = blockIdx.x, b = blockIdx.y, cpg = C / groups, ppg = cpg >> 1, pairs = C >> 1;
+  const int p = threadIdx.x % TP, r0 = threadIdx.x / TP;
+  const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(x + (long long)b * HW * C + g * cpg);
+  float sum = 0.f, sq = 0.f;
+  if (p < ppg) {
+#pragma unroll 4
+    for (int r = r0; r < HW; r += TR) {
+      const float2 v = __bfloat1622float2(xb[(long long)r * pairs + p]);
+      sum += v.x + v.y;
+      sq += v.x * v.x + v.y * v.y;
+    }
+  }
+  sum = warp_sum(sum);
+  sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = sum;
+    red[1][threadIdx.x >> 5] = sq;
+  }
+  __syncthreads();
+  float ts = 0.f, tq = 0.f;
+#pragma unroll
+  for (int i = 0; i < GN_STATS_THREADS / 32; ++i) {
+    ts += red[0][i];
+    tq += red[1][i];
+  }
+  const float n = (float)cpg * (float)HW;
+  const float mean = ts / n;
+  const float rstd = rsqrtf(fmaxf(tq / n - mean * mean, 0.f) + eps);
+  for (int c = threadIdx.x; c < cpg; c += blockDim.x) {
+    const int ch = g * cpg + c;
+    const float ga = gamma[ch] * rstd;
+    a[(long long)b * C + ch] = ga;
+    s[(long long)b * C + ch] = beta[ch] - mean * ga;
+  }
+}
+
 __device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
 
 // y[b, r, c] = act(x[b, r, c] * a[b, c] + s[b, c]); 8 channels (16 bytes) per thread, a / s of the image in shared memory.
@@ -122,6 +171,9 @@ __global__ void __launch_bounds__(256) gn_tokens_apply_kernel(const bf16* __rest
   }
 }
 
+// narrow groups take the row-split statistics path (see groupnorm_act_tokens_fwd)
+static bool gn_row_split(int64_t C, int64_t groups) { return C / groups <= 16 && groups <= 256 && C <= 2 * GN_MAX_PAIRS; }
+
 // rows per CTA of the partial kernel: ~2 CTAs per SM when the map is small, never more than GN_ROWS
 static int gn_partial_rows(int64_t B, int64_t HW) {
   long long rows = (B * HW + 295) / 296;
@@ -132,17 +184,34 @@ static int gn_partial_rows(int64_t B, int64_t HW) {
 
 int groupnorm_act_tokens_fwd(const void* x, const float* gamma, const float* beta, int64_t B, int64_t HW, int64_t C, int64_t groups,
                              float eps, int act, float* part_ws, float* a_ws, float* s_ws, void* y, cudaStream_t stream) {
-  AF_CHECK(x && gamma && beta && part_ws && a_ws && s_ws && y, "groupnorm_act_tokens_fwd: null pointer");
-  AF_CHECK(B > 0 && HW > 0 && C > 0 && groups > 0 && groups <= 256 && C % groups == 0 && (C / groups) % 2 == 0 && C % 8 == 0 &&
-               C <= 2 * GN_MAX_PAIRS && B <= 65535,
+  AF_CHECK(x && gamma && beta && a_ws && s_ws && y, "groupnorm_act_tokens_fwd: null pointer");
+  AF_CHECK(B > 0 && HW > 0 && C > 0 && groups > 0 && groups <= 65535 && C % groups == 0 && (C / groups) % 2 == 0 && C % 8 == 0 &&
+               C / groups <= 256 && C <= 6144 && B <= 65535,
            "groupnorm_act_tokens_fwd: bad shape B=%lld HW=%lld C=%lld groups=%lld", (long long)B, (long long)HW, (long long)C,
            (long long)groups);
   AF_CHECK(act == 0 || act == 1, "groupnorm_act_tokens_fwd: act %d (0 none | 1 SiLU)", act);
   AF_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "groupnorm_act_tokens_fwd: x / y must be 16-byte aligned");
-  const int prow = gn_partial_rows(B, HW);
-  const int chunks = (int)((HW + prow - 1) / prow);
-  gn_tokens_partial_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, 0, stream>>>((const bf16*)x, (float2*)part_ws, (int)C, (int)HW, (int)groups, prow);
-  gn_tokens_finalize_kernel<<<(unsigned)B, 256, 0, stream>>>((const float2*)part_ws, gamma, beta, a_ws, s_ws, (int)C, (int)HW, (int)groups, chunks, eps);
+  const int ppg = (int)(C / groups / 2);
+  int n_launch = 2;
+  if (gn_row_split(C, groups)) {
+    // narrow groups (level A: 10 channels = 20 bytes per row): a CTA per group would gather 20-byte pieces; sum whole
+    // rows per CTA instead and reduce the per-chunk partials in a second small kernel
+    AF_CHECK(part_ws != nullptr && groups <= 256 && C <= 2 * GN_MAX_PAIRS, "groupnorm_act_tokens_fwd: row-split path needs part_ws, groups <= 256, C <= 2560");
+    const int prow = gn_partial_rows(B, HW);
+    const int chunks = (int)((HW + prow - 1) / prow);
+    gn_tokens_partial_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, 0, stream>>>((const bf16*)x, (float2*)part_ws, (int)C, (int)HW, (int)groups, prow);
+    gn_tokens_finalize_kernel<<<(unsigned)B, 256, 0, stream>>>((const float2*)part_ws, gamma, beta, a_ws, s_ws, (int)C, (int)HW, (int)groups, chunks, eps);
+    n_launch = 3;
+  } else {
+    const dim3 gs((unsigned)groups, (unsigned)B);
+#define AF_GN_STATS(TP) \
+  gn_tokens_stats_kernel<TP><<<gs, GN_STATS_THREADS, 0, stream>>>((const bf16*)x, gamma, beta, a_ws, s_ws, (int)C, (int)HW, (int)groups, eps)
+    if (ppg <= 16) AF_GN_STATS(16);
+    else if (ppg <= 32) AF_GN_STATS(32);
+    else if (ppg <= 64) AF_GN_STATS(64);
+    else AF_GN_STATS(128);
+#undef AF_GN_STATS
+  }
   long long rows = (B * HW + 295) / 296;            // ~2 CTAs per SM
   if (rows < 4) rows = 4;
   if (rows > 64) rows = 64;
@@ -151,11 +220,12 @@ int groupnorm_act_tokens_fwd(const void* x, const float* gamma, const float* bet
   if (act == 1) gn_tokens_apply_kernel<1><<<grid, 256, smem, stream>>>((const bf16*)x, a_ws, s_ws, (bf16*)y, (int)C, (int)HW, (int)rows);
   else gn_tokens_apply_kernel<0><<<grid, 256, smem, stream>>>((const bf16*)x, a_ws, s_ws, (bf16*)y, (int)C, (int)HW, (int)rows);
   AF_CUDA(cudaGetLastError());
-  g_launch_count += 3;
+  g_launch_count += n_launch;
   return 0;
 }
 
-int64_t groupnorm_act_tokens_ws_floats(int64_t B, int64_t HW, int64_t groups) {
+int64_t groupnorm_act_tokens_ws_floats(int64_t B, int64_t HW, int64_t C, int64_t groups) {
+  if (!gn_row_split(C, groups)) return 0;
   const int prow = gn_partial_rows(B, HW);
   return 2 * B * ((HW + prow - 1) / prow) * groups;
 }

@@ -352,11 +352,11 @@ def groupnorm_act_tokens(x, gamma, beta, groups=32, eps=1e-5, silu=True):
     if x.dim() != 3 or not x.is_contiguous():
         raise ValueError("groupnorm_act_tokens: x must be a contiguous [B, HW, C] tensor")
     B, HW, C = x.shape
-    n_ws = int(_lib.load().adaface_groupnorm_act_tokens_ws_floats(B, HW, int(groups)))
-    ws = torch.empty(n_ws + 2 * B * C, device=x.device, dtype=torch.float32)
+    n_ws = int(_lib.load().adaface_groupnorm_act_tokens_ws_floats(B, HW, C, int(groups)))
+    ws = torch.empty(2 * B * C + n_ws, device=x.device, dtype=torch.float32)
     y = torch.empty_like(x)
     _lib.call("adaface_groupnorm_act_tokens_fwd", _ptr(x), _ptr(gamma), _ptr(beta), B, HW, C, int(groups), float(eps), 1 if silu else 0,
-              _ptr(ws), _ptr(ws[n_ws:]), _ptr(ws[n_ws + B * C:]), _ptr(y), _stream())
+              _ptr(ws[2 * B * C:]) if n_ws else ctypes.c_void_p(0), _ptr(ws), _ptr(ws[B * C:]), _ptr(y), _stream())
     return y
 
 

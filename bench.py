@@ -125,6 +125,38 @@ def run_reference_ldm(torch, steps, warmup):
             "what": "baseline/_ref ldm.modules.attention.CrossAttention, verbatim, same sample (einsum path: [B*8,N,N] scores)"}
 
 
+def run_reference_unet(torch):
+    """The UNMODIFIED reference U-Net from baseline/_ref (``ldm.modules.diffusionmodules.openaimodel.UNetModel``, SD-1.5
+    configuration, random init, fp32, all host threads): ONE forward of ONE sample -- the CPU comparator of the GPU arm's
+    secondary ``unet_forward`` line.  ``omegaconf`` (absent here; only its ListConfig type is compared in the constructor)
+    is stubbed.  Returns None when baseline/_ref is absent or not importable."""
+    import types
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "ldm")):
+        return None
+    sys.path.insert(0, ref)
+    try:
+        if "omegaconf" not in sys.modules:
+            lc = types.ModuleType("omegaconf.listconfig")
+            lc.ListConfig = type("ListConfig", (), {})
+            sys.modules["omegaconf"], sys.modules["omegaconf.listconfig"] = types.ModuleType("omegaconf"), lc
+        from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    except Exception:
+        return None
+    finally:
+        sys.path.remove(ref)
+    torch.manual_seed(0)
+    unet = UNetModel(in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2, attention_resolutions=[4, 2, 1],
+                     channel_mult=(1, 2, 4, 4), num_heads=8, use_spatial_transformer=True, context_dim=CTX_DIM, legacy=False).eval()
+    x, ts, ctx = torch.randn(1, 4, 64, 64), torch.tensor([500]), torch.randn(1, S_CTX, CTX_DIM)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        unet(x, ts, context=ctx, extra_info={})
+        dt = time.perf_counter() - t0
+    return {"ms_per_sample": dt * 1e3, "samples_per_s": 1 / dt, "kind": "reference", "cores": torch.get_num_threads(),
+            "what": "baseline/_ref UNetModel.forward, verbatim, SD-1.5 config, B=1, 64x64 latents, fp32, one un-warmed forward"}
+
+
 def main_reference(args):
     """--impl reference: the reference's CPU implementation of the path (the oracle port -- /root/reference does
     not exist on the GPU box and has no compiled code on this path), all host threads, bounded sample per step."""
@@ -146,6 +178,10 @@ def main_reference(args):
     ldm = run_reference_ldm(torch, max(1, min(args.steps, 3)), 1)
     if ldm is not None:
         line["reference_verbatim_ldm"] = ldm
+    if os.environ.get("ADAFACE_BENCH_EXTRAS", "1") != "0":
+        un = run_reference_unet(torch)
+        if un is not None:
+            line["reference_verbatim_unet"] = un
     print(json.dumps(line))
 
 
@@ -303,6 +339,43 @@ def secondary_measurements(torch, a, dev, flush, pk):
         out["arcface_to_ada_tokens"] = {"shape": "BS=64: [64,512] -> Arc2Face CLIP encoder -> SubjBasisGenerator -> [64,16,768]",
                                         "us": us2, "flops_executed": 2 * fl, "tflops": 2 * fl / us2 / 1e6,
                                         "samples_per_s": 64 / us2 * 1e6}
+        # -- the implicit-GEMM 3x3 convolution (tensor-bound: K = 9 Cin) at the U-Net's sizes, B = 8
+        tf_peak = pk["bf16_tflops"]
+        conv = {}
+        for side, cin, cout in ((64, 320, 320), (32, 640, 640), (16, 1280, 1280)):
+            xt = torch.randn(BATCH, side * side, cin, device=dev).to(torch.bfloat16)
+            wp = ops.pack_conv3x3_weight(torch.randn(cout, cin, 3, 3, device=dev) * (9 * cin) ** -0.5)
+            bias = torch.zeros(cout, device=dev)
+            yt = torch.empty(BATCH, side * side, cout, device=dev, dtype=torch.bfloat16)
+            us = _time_us(torch, flush, lambda: ops.conv3x3(xt, wp, (side, side), bias=bias, out=yt))
+            fl = 2.0 * BATCH * side * side * cout * 9 * cin
+            conv[f"{side}x{side}_{cin}to{cout}"] = {"us": us, "tflops": fl / us / 1e6, "peak_tflops": tf_peak, "frac": fl / us / 1e6 / tf_peak}
+        out["conv3x3_implicit_gemm"] = {"kernel": "gemm_tn_tcgen05_kernel<BN, CONV>", "batch": BATCH, "bound": "tensor", **conv}
+        # -- the caller of the whole path: one SD-1.5 U-Net forward (random weights), one CUDA graph per batch size
+        with torch.device("meta"):
+            unet = a.UNetModel(in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2, attention_resolutions=[4, 2, 1],
+                               channel_mult=(1, 2, 4, 4), num_heads=8, use_spatial_transformer=True, context_dim=CTX_DIM)
+        unet = unet.to_empty(device=dev).eval()
+        for k_, p_ in unet.named_parameters():
+            if p_.dim() >= 2:
+                p_.normal_(std=p_[0].numel() ** -0.5)
+            elif k_.endswith("weight"):
+                p_.fill_(1.0)
+            else:
+                p_.zero_()
+        un = {"what": "UNetModel.forward (openaimodel.py:820-960), 64x64 latents, 77-token context, bf16 NHWC-resident, CUDA graph",
+              "params": sum(p_.numel() for p_ in unet.parameters())}
+        for B in (2, BATCH):
+            xl, ts_, cx = torch.randn(B, 4, 64, 64, device=dev), torch.randint(0, 1000, (B,), device=dev), torch.randn(B, S, CTX_DIM, device=dev).to(torch.bfloat16)
+            n0 = a._lib.launch_count()
+            unet(xl, ts_, context=cx)
+            nk = a._lib.launch_count() - n0
+            gfn = a.graphed(lambda x_, t_, c_: unet(x_, t_, context=c_), xl, ts_, cx)
+            us = _time_us(torch, flush, lambda: gfn(xl, ts_, cx), iters=5)
+            un[f"B{B}"] = {"ms": us / 1e3, "samples_per_s": B / us * 1e6, "kernels": int(nk)}
+            del gfn
+        out["unet_forward"] = un
+        del unet
     # -- training: forward + backward through one captured cross-attention module (level A, B = 1, S = 97, DoRA r = 192
     #    on q/k/v/out, normalize_cross_attn, loss on out + captured attn) and through one self-attention module
     S2 = 97

@@ -163,11 +163,12 @@ int adaface_conv3x3_fwd(const void* x, int64_t B, int64_t H, int64_t W, int64_t 
                         int stride, int act, void* stream);
 /* y = act(GroupNorm(groups, eps)(x) * gamma + beta) over tokens: x, y bf16 [B, HW, C]; act 0 = none, 1 = SiLU
  * (normalization() + nn.SiLU() in front of each convolution, openaimodel.py:203-205, 229-231; fp32 statistics like
- * GroupNorm32, util.py).  part_ws: adaface_groupnorm_act_tokens_ws_floats(B, HW, groups) floats; a_ws, s_ws: fp32 [B, C]. */
+ * GroupNorm32, util.py).  a_ws, s_ws: fp32 [B, C] scratch (folded scale / shift per image and channel); part_ws:
+ * adaface_groupnorm_act_tokens_ws_floats(B, HW, C, groups) floats of scratch (may be 0 -> NULL allowed).  C / groups even. */
 int adaface_groupnorm_act_tokens_fwd(const void* x, const float* gamma, const float* beta, int64_t B, int64_t HW, int64_t C,
                                      int64_t groups, float eps, int act, float* part_ws, float* a_ws, float* s_ws, void* y,
                                      void* stream);
-int64_t adaface_groupnorm_act_tokens_ws_floats(int64_t B, int64_t HW, int64_t groups);
+int64_t adaface_groupnorm_act_tokens_ws_floats(int64_t B, int64_t HW, int64_t C, int64_t groups);
 /* y = SiLU(x) as bf16, n elements (the nn.SiLU() in front of emb_layers' Linear, openaimodel.py:222-228). */
 int adaface_silu_fwd(const void* x, int x_dtype, void* y, int64_t n, void* stream);
 /* Nearest-neighbour 2x (F.interpolate(scale_factor=2, mode="nearest"), openaimodel.py:116): x bf16 [B, H, W, C] ->

@@ -81,6 +81,23 @@ def test_conv3x3_epilogue_terms():
     assert err(nchw(y2, (h, w)), ref2) < 2e-3
 
 
+def test_conv3x3_split_k_epilogue_terms():
+    """A small-M, long-K convolution (level D of the U-Net: 2 x 8 x 8 pixels, K = 9 x 1280) runs split-K: partial fp32 tiles +
+    the reduce kernel, which applies bias, per-image bias and residual."""
+    import adaface_dev_b200 as a
+    B, h, w, cin, cout = 2, 8, 8, 1280, 1280
+    x, wt = rnd((B, cin, h, w), 41), rnd((cout, cin, 3, 3), 42, (9 * cin) ** -0.5)
+    bias, rowb, res = rnd((cout,), 43, 0.1), rnd((B, cout), 44, 0.5), rnd((B, cout, h, w), 45)
+    ref = ub.conv3x3(x, wt, bias) + rowb[:, :, None, None] + res
+    wp = a.ops.pack_conv3x3_weight(wt.cuda())
+    y = a.ops.conv3x3(nhwc(x), wp, (h, w), bias=bias.cuda(), rowbias=rowb.cuda(), residual=nhwc(res), out_dtype=torch.float32)
+    assert err(nchw(y, (h, w)), ref) < 2e-3
+    yb = a.ops.conv3x3(nhwc(x), wp, (h, w), bias=bias.cuda(), rowbias=rowb.cuda(), residual=nhwc(res))
+    assert yb.dtype == torch.bfloat16 and err(nchw(yb, (h, w)), ref) < 4e-2          # |y| up to ~6: bf16 half-ulp 1.6e-2
+    y1 = a.ops.conv3x3(nhwc(x), wp, (h, w), bias=bias.cuda(), rowbias=rowb.cuda(), residual=nhwc(res), out_dtype=torch.float32)
+    assert torch.equal(y, y1)                                                        # fixed summation order: deterministic
+
+
 def test_conv3x3_rejects_bad_input():
     import adaface_dev_b200 as a
     wp = a.ops.pack_conv3x3_weight(torch.zeros(64, 64, 3, 3).cuda())
