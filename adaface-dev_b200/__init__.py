@@ -5,7 +5,7 @@ Host-side mirrors of the reference's operator surface over the C-
 
     AttnProcessor_LoRA_Capture, Attention, LoraDoraLinear, gen_gradient_scaler   (attn_processor.py)
     CrossAttention, FeedForward, BasicTransformerBlock, SpatialTransformer       (ldm_attention.py)
-    ResBlock, Upsample, Downsample                                               (ldm_unet_blocks.py)
+    ResBlock, Upsample, Downsample, LoraDoraConv2d                               (ldm_unet_blocks.py)
     UNetModel, TimestepEmbedSequential                                           (ldm_unet.py)
     SubjBasisGenerator, Arc2FaceID2ImgPrompt, CLIPTextModelWrapper, CLIPAttentionMKV   (subj_basis_generator.py)
 
@@ -16,7 +16,7 @@ from . import _lib, ops  # noqa: F401
 from .attn_processor import (AttnProcessor_LoRA_Capture, Attention, LoraDoraLinear, ScaleGrad, GradientScaler,  # noqa: F401
                              gen_gradient_scaler, img_mask_to_key_mask)
 from .ldm_attention import CrossAttention, FeedForward, GEGLU, BasicTransformerBlock, SpatialTransformer  # noqa: F401
-from .ldm_unet_blocks import ResBlock, Upsample, Downsample  # noqa: F401
+from .ldm_unet_blocks import ResBlock, Upsample, Downsample, LoraDoraConv2d  # noqa: F401
 from .ldm_unet import UNetModel, TimestepEmbedSequential  # noqa: F401
 from .subj_basis_generator import (SubjBasisGenerator, Arc2FaceID2ImgPrompt, FrozenCLIPTextEncoder, CLIPTextModelWrapper,  # noqa: F401
                                    CLIPAttentionMKV, CLIPTextConfig, template_ids)

@@ -159,3 +159,88 @@ class Downsample(nn.Module):
             raise RuntimeError("adaface_b200 Downsample runs on CUDA only (no CPU fallback)")
         hw = tuple(x.shape[2:])
         return _to_nchw(self.forward_tokens(_to_tokens(x), hw), (hw[0] // 2, hw[1] // 2), x.dtype)
+
+
+# ------------------------------------------------------------------------------------------------ conv-LoRA (dalc:541-591)
+class _ConvMagnitude(nn.Module):
+    def __init__(self, mag):
+        super().__init__()
+        self.weight = nn.Parameter(mag)
+
+
+class LoraDoraConv2d(nn.Module):
+    """Parameter container with peft's ``lora.Conv2d(use_dora=True)`` layout for a 3x3 (or 1x1) base convolution -- the
+    ``up_blocks.3.resnets.[12].conv1 / conv2 / conv_shortcut`` adapters the reference installs with
+    ``set_up_ffn_loras`` (adaface/diffusers_attn_lora_capture.py:541-591; r = 192, alpha = 16, DoRA):
+    ``base_layer``, ``lora_A[adapter]`` = Conv2d(cin, r, k, padding, bias=False), ``lora_B[adapter]`` = Conv2d(r, cout, 1,
+    bias=False), ``lora_magnitude_vector[adapter].weight`` [cout].  Init as peft: A Kaiming-uniform(a = sqrt 5), B zero,
+    magnitude = ||W|| per output channel (identity adapter).  Eval-mode arithmetic (convolution form):
+        y = bias + m / ||W + s B.A||_(cin,kh,kw) * (conv(x, W) + s conv1x1(conv(x, A), B))
+    runs as two launches of the implicit-GEMM kernel: T = conv(x, A) (Cout = r), then the base convolution with the rank-r
+    tail T (sB)^T accumulated into the same TMEM tile and the DoRA column scale + bias in its epilogue.  Forward only."""
+
+    def __init__(self, base_layer, adapter_name="default", r=192, lora_alpha=16, use_dora=True, lora_dropout=0.1):
+        super().__init__()
+        if not use_dora:
+            raise NotImplementedError("the reference always uses DoRA (lora_uses_dora=True)")
+        k = base_layer.kernel_size
+        if k not in ((3, 3), (1, 1)) or base_layer.stride != (1, 1) or base_layer.padding != (k[0] // 2, k[0] // 2):
+            raise NotImplementedError("LoraDoraConv2d: 3x3 (padding 1) or 1x1 base convolutions with stride 1 only")
+        self.base_layer = base_layer
+        self.r, self.lora_alpha, self.scaling, self.adapter = r, lora_alpha, lora_alpha / r, adapter_name
+        dev = base_layer.weight.device
+        cin, cout = base_layer.in_channels, base_layer.out_channels
+        self.lora_A = nn.ModuleDict({adapter_name: nn.Conv2d(cin, r, k, padding=base_layer.padding, bias=False, device=dev)})
+        self.lora_B = nn.ModuleDict({adapter_name: nn.Conv2d(r, cout, 1, bias=False, device=dev)})
+        nn.init.kaiming_uniform_(self.lora_A[adapter_name].weight, a=5 ** 0.5)
+        nn.init.zeros_(self.lora_B[adapter_name].weight)
+        self.lora_magnitude_vector = nn.ModuleDict({adapter_name: _ConvMagnitude(torch.linalg.norm(base_layer.weight.detach().float().flatten(1), dim=1))})
+        self._pack_key, self._pack = None, None
+        self.enable_adapters = lambda *a, **k_: None
+        self.set_adapter = lambda *a, **k_: None
+
+    @property
+    def is_3x3(self):
+        return self.base_layer.kernel_size == (3, 3)
+
+    def pack(self):
+        """(W, A, s*B [cout, r], colscale = m / ||W + s B.A||, bias): W / A in the kernel's K-major tap layout for 3x3, plain
+        [cout, cin] / [r, cin] for 1x1.  Rebuilt only when a parameter changed."""
+        A, B = self.lora_A[self.adapter].weight, self.lora_B[self.adapter].weight
+        m, W, b = self.lora_magnitude_vector[self.adapter].weight, self.base_layer.weight, self.base_layer.bias
+        key = _ver(A, B, m, W, b)
+        if key != self._pack_key:
+            with torch.no_grad():
+                Bf = B.float().flatten(1)                                                    # [cout, r]
+                comp = (Bf @ A.float().flatten(1)).view_as(W)                                # B . A as one [cout, cin, kh, kw] kernel
+                wn = torch.linalg.norm((W.float() + self.scaling * comp).flatten(1), dim=1)
+                if self.is_3x3:
+                    wp, ap = ops.pack_conv3x3_weight(W), ops.pack_conv3x3_weight(A)
+                else:
+                    wp, ap = _bf16(W.flatten(1)), _bf16(A.flatten(1))
+                self._pack = (wp, ap, (Bf * self.scaling).to(torch.bfloat16).contiguous(), (m.float() / wn).contiguous(), _f32(b))
+            self._pack_key = key
+        return self._pack
+
+    def forward_tokens(self, t, hw, rowbias=None, residual=None):
+        """t bf16 [B, h*w, cin] -> bf16 [B, h*w, cout]; ``rowbias`` / ``residual`` as in ops.conv3x3 (3x3 only / both)."""
+        _no_grad_only("LoraDoraConv2d", t)
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("LoraDoraConv2d: the training path (dropout on the adapter branch, backward) is not built")
+        wp, ap, bs, cs, bias = self.pack()
+        b, n, _ = t.shape
+        if self.is_3x3:
+            ta = ops.conv3x3(t, ap, hw)
+            return ops.conv3x3(t, wp, hw, bias=bias, rowbias=rowbias, residual=residual, t=ta.view(b * n, -1), bs=bs, colscale=cs)
+        if rowbias is not None:
+            raise NotImplementedError("LoraDoraConv2d: rowbias is only defined for the 3x3 form")
+        x2d = t.view(b * n, -1)
+        ta = ops.proj(x2d, ap)
+        res2d = None if residual is None else residual.view(b * n, -1)
+        return ops.proj(x2d, wp, t=ta, bs=bs, colscale=cs, bias=bias, residual=res2d).view(b, n, -1)
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("adaface_b200 LoraDoraConv2d runs on CUDA only (no CPU fallback)")
+        hw = tuple(x.shape[2:])
+        return _to_nchw(self.forward_tokens(_to_tokens(x), hw), hw, x.dtype)

@@ -163,3 +163,17 @@ def unet_forward(sd, cfg, x, timesteps, context, mask=None):
     for i, layers in enumerate(out):
         h = run(layers, f"output_blocks.{i}.", torch.cat([h, hs.pop()], dim=1), emb)
     return conv3x3(silu(group_norm32(h, sd["out.0.weight"], sd["out.0.bias"])), sd["out.2.weight"], sd["out.2.bias"])
+
+
+def lora_dora_conv(x, W, b, A, B, m, scaling):
+    """peft ``lora.Conv2d(use_dora=True)`` in eval mode (PARITY UNPINNED: peft is un-vendored; restated from its published
+    algorithm, anchored on the reference's call site adaface/diffusers_attn_lora_capture.py:541-591):
+        y = bias + m / ||W + s B.A|| * (conv(x, W) + s conv1x1(conv(x, A), B)),  norm over (cin, kh, kw), detached.
+    W [cout, cin, k, k], A [r, cin, k, k], B [cout, r, 1, 1], m [cout]; k = 3 (padding 1) or 1."""
+    k = W.shape[-1]
+    conv = (lambda t, w_: conv3x3(t, w_, None)) if k == 3 else (lambda t, w_: torch.einsum("bchw,oc->bohw", t, w_[:, :, 0, 0]))
+    lora = torch.einsum("bchw,oc->bohw", conv(x, A), B[:, :, 0, 0]) * scaling
+    comp = (B.flatten(1) @ A.flatten(1)).view_as(W)
+    wn = torch.linalg.norm((W + scaling * comp).flatten(1), dim=1).detach()
+    y = (m / wn)[None, :, None, None] * (conv(x, W) + lora)
+    return y if b is None else y + b[None, :, None, None]

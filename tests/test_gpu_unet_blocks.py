@@ -230,3 +230,37 @@ def test_unet_vs_reference_golden(name):
     assert tuple(acts["attn"][8].shape) == (2, 8, 256, 77) and tuple(acts["outfeat"][8].shape) == (2, 320, 16, 16)
     assert (acts["attn"][8].sum(-1) - 1).abs().max().item() < 1e-3
     assert all(not m._cross_attn(li).save_cross_attn_vars for li in (7, 8))
+
+
+@pytest.mark.parametrize("k", [3, 1])
+def test_lora_dora_conv_vs_oracle(k):
+    """Conv-LoRA / DoRA adapter (dalc:541-591: r = 192, alpha = 16 on up_blocks.3.resnets.[12].conv1 / conv2 / conv_shortcut):
+    640 -> 320 at 16 x 16, adapter moved off its identity initialisation."""
+    import adaface_dev_b200 as a
+    torch.manual_seed(5)
+    B, h, w, cin, cout = 2, 16, 16, 640, 320
+    base = torch.nn.Conv2d(cin, cout, k, padding=k // 2)
+    with torch.no_grad():
+        base.weight.copy_(rnd((cout, cin, k, k), 51, (k * k * cin) ** -0.5))
+        base.bias.copy_(rnd((cout,), 52, 0.05))
+    m = a.LoraDoraConv2d(base, r=192, lora_alpha=16)
+    with torch.no_grad():
+        m.lora_A["default"].weight.copy_(rnd((192, cin, k, k), 53, (k * k * cin) ** -0.5))
+        m.lora_B["default"].weight.copy_(rnd((cout, 192, 1, 1), 54, 0.3))
+        m.lora_magnitude_vector["default"].weight.mul_(1.1)
+    x = rnd((B, cin, h, w), 55)
+    ref = ub.lora_dora_conv(x, base.weight.detach(), base.bias.detach(), m.lora_A["default"].weight.detach(),
+                            m.lora_B["default"].weight.detach(), m.lora_magnitude_vector["default"].weight.detach(), m.scaling)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        out = m(x.cuda())
+    assert out.dtype == torch.float32 and tuple(out.shape) == (B, cout, h, w)
+    assert err(out, ref) < 3e-2                      # bf16 adapter branch T = conv(x, A) feeding the rank-192 tail
+    assert {"base_layer.weight", "lora_A.default.weight", "lora_B.default.weight", "lora_magnitude_vector.default.weight"} <= set(m.state_dict())
+    # identity at init (peft: B = 0, magnitude = ||W||): the adapter reproduces the base convolution
+    fresh = a.LoraDoraConv2d(base, r=192, lora_alpha=16).cuda().eval()
+    with torch.no_grad():
+        out0 = fresh(x.cuda())
+    ref0 = ub.conv3x3(x, base.weight.detach(), base.bias.detach()) if k == 3 else \
+        torch.einsum("bchw,oc->bohw", x, base.weight.detach()[:, :, 0, 0]) + base.bias.detach()[None, :, None, None]
+    assert err(out0, ref0) < 2e-2
