@@ -733,6 +733,10 @@ int conv3x3_fwd(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, con
   ep.splitk_ws = nullptr;
 
   int BN = pick_tile_width(Cout, ep.num_m, act);
+  // The tile-width cost model is the projection GEMM's (short K, per-tile overhead matters).  With K = 9 Cin the main loop
+  // dominates and the widest tile that divides Cout wins on arithmetic intensity: measured (profiles/r01_conv_bn_sweep.txt)
+  // 160 beats 64 / 128 / 256 at every SD-1.5 shape, also where it leaves SMs idle (B = 2, 32 x 32, 1280 -> 640: 44 vs 60 us).
+  if (Cout % 160 == 0 && getenv("ADAFACE_GEMM_BN") == nullptr) BN = 160;
   {
     // split-K when the output tiles cannot fill half the SMs and the K loop is long (levels C / D of the U-Net)
     static int splitk = -1;

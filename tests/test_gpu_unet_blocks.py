@@ -243,13 +243,14 @@ def test_lora_dora_conv_vs_oracle(k):
     with torch.no_grad():
         base.weight.copy_(rnd((cout, cin, k, k), 51, (k * k * cin) ** -0.5))
         base.bias.copy_(rnd((cout,), 52, 0.05))
+    W0, b0 = base.weight.detach().clone(), base.bias.detach().clone()        # CPU copies: .cuda() below moves `base` in place
     m = a.LoraDoraConv2d(base, r=192, lora_alpha=16)
     with torch.no_grad():
         m.lora_A["default"].weight.copy_(rnd((192, cin, k, k), 53, (k * k * cin) ** -0.5))
         m.lora_B["default"].weight.copy_(rnd((cout, 192, 1, 1), 54, 0.3))
         m.lora_magnitude_vector["default"].weight.mul_(1.1)
     x = rnd((B, cin, h, w), 55)
-    ref = ub.lora_dora_conv(x, base.weight.detach(), base.bias.detach(), m.lora_A["default"].weight.detach(),
+    ref = ub.lora_dora_conv(x, W0, b0, m.lora_A["default"].weight.detach(),
                             m.lora_B["default"].weight.detach(), m.lora_magnitude_vector["default"].weight.detach(), m.scaling)
     m = m.cuda().eval()
     with torch.no_grad():
@@ -261,6 +262,5 @@ def test_lora_dora_conv_vs_oracle(k):
     fresh = a.LoraDoraConv2d(base, r=192, lora_alpha=16).cuda().eval()
     with torch.no_grad():
         out0 = fresh(x.cuda())
-    ref0 = ub.conv3x3(x, base.weight.detach(), base.bias.detach()) if k == 3 else \
-        torch.einsum("bchw,oc->bohw", x, base.weight.detach()[:, :, 0, 0]) + base.bias.detach()[None, :, None, None]
+    ref0 = ub.conv3x3(x, W0, b0) if k == 3 else torch.einsum("bchw,oc->bohw", x, W0[:, :, 0, 0]) + b0[None, :, None, None]
     assert err(out0, ref0) < 2e-2
