@@ -39,6 +39,8 @@ SIGNATURES = {
     "adaface_silu_fwd": [_p, _i32, _p, _i64, _p],
     "adaface_upsample2x_tokens": [_p, _p, _i64, _i64, _i64, _i64, _p],
     "adaface_timestep_embedding": [_p, _i64, _i64, _f32, _p, _p],
+    "adaface_groupnorm_act_tokens_bwd": [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _f32, _i32, _p, _p, _p],
+    "adaface_resample2x_bwd": [_p, _p, _i64, _i64, _i64, _i64, _i32, _p],
     # ---- backward (ABI v2)
     "adaface_attn_bwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _p,
                          _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _i32, _f32, _p],

@@ -258,6 +258,89 @@ class SbgHeadFn(Function):
 
 
 # ------------------------------------------------------------------------------------------------ helpers
+# ------------------------------------------------------------------------------------------------ U-Net convolutional blocks
+def _b16c(t):
+    t = t if t.dtype == BF16 else t.to(BF16)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def needs_grad(*ts):
+    return torch.is_grad_enabled() and any(t is not None and torch.is_tensor(t) and t.requires_grad for t in ts)
+
+
+class GroupNormActFn(Function):
+    """act(GroupNorm(x)) over NHWC tokens with frozen affine parameters: backward = adaface_groupnorm_act_tokens_bwd."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps, silu):
+        ctx.cfg = (groups, eps, silu)
+        ctx.save_for_backward(x, gamma, beta)
+        return ops.groupnorm_act_tokens(x, gamma, beta, groups, eps, silu=silu)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta = ctx.saved_tensors
+        groups, eps, silu = ctx.cfg
+        return ops.groupnorm_act_tokens_bwd(x, _b16c(dy), gamma, beta, groups, eps, silu=silu), None, None, None, None, None
+
+
+class Conv3x3Fn(Function):
+    """3x3 convolution with a FROZEN weight (+ bias, per-image bias, residual).  dX is the same implicit-GEMM kernel over the
+    flipped / transposed weight pack (stride 2: after zero-insertion of dY); the residual's gradient is dY itself."""
+
+    @staticmethod
+    def forward(ctx, x, pack, wkey, weight, hw, stride, bias, rowbias, residual, out_dtype):
+        ctx.pack, ctx.wkey, ctx.weight, ctx.hw, ctx.stride = pack, wkey, weight, hw, stride
+        ctx.res_dtype = None if residual is None else residual.dtype
+        return ops.conv3x3(x, pack[wkey], hw, stride=stride, bias=bias, rowbias=rowbias, residual=residual, out_dtype=out_dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dx = dres = None
+        if ctx.needs_input_grad[0]:
+            key = ctx.wkey + "_dx"
+            wdx = ctx.pack.get(key)
+            if wdx is None:
+                wdx = ctx.pack[key] = ops.pack_conv3x3_weight_dx(ctx.weight)
+            g = _b16c(dy)
+            if ctx.stride == 2:
+                g = ops.resample2x_bwd(g, (ctx.hw[0] // 2, ctx.hw[1] // 2), 1)
+            dx = ops.conv3x3(g, wdx, ctx.hw)
+        if ctx.res_dtype is not None and ctx.needs_input_grad[8]:
+            dres = dy if dy.dtype == ctx.res_dtype else dy.to(ctx.res_dtype)
+        return dx, None, None, None, None, None, None, None, dres, None
+
+
+class Upsample2xFn(Function):
+    @staticmethod
+    def forward(ctx, x, hw):
+        ctx.hw = hw
+        return ops.upsample2x_tokens(x, hw)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.resample2x_bwd(_b16c(dy), ctx.hw, 0), None
+
+
+def groupnorm_act(x, gamma, beta, groups, eps, silu):
+    if needs_grad(x):
+        return GroupNormActFn.apply(x, gamma, beta, groups, eps, silu)
+    return ops.groupnorm_act_tokens(x, gamma, beta, groups, eps, silu=silu)
+
+
+def conv3x3(x, pack, wkey, weight, hw, *, stride=1, bias=None, rowbias=None, residual=None, out_dtype=BF16):
+    """``weight`` = the module's [Cout, Cin, 3, 3] parameter (only read to build the dX pack on the first backward)."""
+    if needs_grad(x, residual):
+        return Conv3x3Fn.apply(x, pack, wkey, weight, hw, stride, bias, rowbias, residual, out_dtype)
+    return ops.conv3x3(x, pack[wkey], hw, stride=stride, bias=bias, rowbias=rowbias, residual=residual, out_dtype=out_dtype)
+
+
+def upsample2x(x, hw):
+    if needs_grad(x):
+        return Upsample2xFn.apply(x, hw)
+    return ops.upsample2x_tokens(x, hw)
+
+
 def linear(x, pack, wkey, bkey=None, *, lora=None, params=None, residual=None, out_dtype=BF16):
     """One projection of the training path: frozen weight (default), frozen weight + DoRA adapter (``lora``), or
     trainable nn.Linear parameters (``params`` = (w0, b0, w1, b1, ...))."""

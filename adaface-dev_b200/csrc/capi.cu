@@ -157,6 +157,9 @@ int64_t groupnorm_act_tokens_ws_floats(int64_t, int64_t, int64_t, int64_t);
 int silu_fwd(const void*, int, void*, int64_t, cudaStream_t);
 int upsample2x_tokens(const void*, void*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
 int timestep_embedding(const float*, int64_t, int64_t, float, void*, cudaStream_t);
+int groupnorm_act_tokens_bwd(const void*, const void*, const float*, const float*, int64_t, int64_t, int64_t, int64_t, float, int, float*,
+                             void*, cudaStream_t);
+int resample2x_bwd(const void*, void*, int64_t, int64_t, int64_t, int64_t, int, cudaStream_t);
 
 }  // namespace adaface
 
@@ -263,6 +266,14 @@ int64_t adaface_groupnorm_act_tokens_ws_floats(int64_t B, int64_t HW, int64_t C,
 int adaface_silu_fwd(const void* x, int x_dtype, void* y, int64_t n, void* stream) { return silu_fwd(x, x_dtype, y, n, (cudaStream_t)stream); }
 int adaface_upsample2x_tokens(const void* x, void* y, int64_t B, int64_t H, int64_t W, int64_t C, void* stream) {
   return upsample2x_tokens(x, y, B, H, W, C, (cudaStream_t)stream);
+}
+
+int adaface_groupnorm_act_tokens_bwd(const void* x, const void* dy, const float* gamma, const float* beta, int64_t B, int64_t HW,
+                                     int64_t C, int64_t groups, float eps, int act, float* coef_ws, void* dx, void* stream) {
+  return groupnorm_act_tokens_bwd(x, dy, gamma, beta, B, HW, C, groups, eps, act, coef_ws, dx, (cudaStream_t)stream);
+}
+int adaface_resample2x_bwd(const void* x, void* y, int64_t B, int64_t H, int64_t W, int64_t C, int mode, void* stream) {
+  return resample2x_bwd(x, y, B, H, W, C, mode, (cudaStream_t)stream);
 }
 
 int adaface_timestep_embedding(const float* t, int64_t B, int64_t dim, float max_period, void* out, void* stream) {

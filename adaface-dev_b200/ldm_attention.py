@@ -283,18 +283,24 @@ class SpatialTransformer(nn.Module):
 
     def forward_tokens(self, t_in, hw, context=None, mask=None):
         """NHWC-resident entry (the U-Net mirror keeps activations as tokens): t_in bf16 [B, h*w, C] -> bf16 [B, h*w, C].
-        Same arithmetic as forward(); the norm runs tokens -> tokens and the residual rides in proj_out's epilogue."""
-        if torch.is_grad_enabled() and (t_in.requires_grad or (context is not None and context.requires_grad)):
-            raise NotImplementedError("SpatialTransformer backward is not built yet")
+        Same arithmetic as forward(); the norm runs tokens -> tokens and the residual rides in proj_out's epilogue.
+        Differentiable w.r.t. the tokens and the context (frozen weights: GroupNormActFn, FrozenLinearFn, the block's
+        training path)."""
         b, n, c = t_in.shape
         h, w = hw
         pk = self._weights()
-        t = ops.groupnorm_act_tokens(t_in, pk["gn_w"], pk["gn_b"], self.norm.num_groups, self.norm.eps, silu=False)   # :291
-        t = ops.proj(t.view(b * n, c), pk["w_in"], bias=pk["b_in"]).view(b, n, -1)                                   # :292
+        train = ag.needs_grad(t_in, context)
+        t = ag.groupnorm_act(t_in, pk["gn_w"], pk["gn_b"], self.norm.num_groups, self.norm.eps, False)                # :291
+        if train:
+            t = ag.linear(t.view(b * n, c), pk, "w_in", "b_in").view(b, n, -1)
+        else:
+            t = ops.proj(t.view(b * n, c), pk["w_in"], bias=pk["b_in"]).view(b, n, -1)                               # :292
         for block in self.transformer_blocks:
             block.attn2.infeat_size = (h, w)
             mask2 = F.interpolate(mask, size=(h, w), mode="nearest") if mask is not None else None
             t = block(t, context=context, mask=mask2)
+        if train:
+            return ag.linear(t.reshape(b * n, -1), pk, "w_out", "b_out", residual=t_in.view(b * n, c)).view(b, n, c)
         return ops.proj(t.reshape(b * n, -1), pk["w_out"], bias=pk["b_out"], residual=t_in.view(b * n, c)).view(b, n, c)   # :303-304
 
     def forward(self, x, context=None, mask=None):

@@ -12,12 +12,14 @@ B200 design: the whole forward runs on NHWC bf16 tokens [B, h*w, C].  The 4-chan
 implicit-GEMM tcgen05 kernel, every 1x1 convolution / Linear the projection GEMM, GroupNorm(+SiLU) one pass over tokens, and
 the transformer blocks consume / produce the same layout.  SiLU(emb) is evaluated once per forward instead of once per
 ResBlock.  The skip concatenations are the only torch data movement left (torch.cat along the channel axis).
-Forward only; CUDA only, no fallback.
+Training: the forward is differentiable w.r.t. the prompt context (every block pairs its kernels with backward kernels through
+autograd.py; the U-Net's own weights are frozen and get no gradient).  CUDA only, no fallback.
 """
 import torch
 import torch.nn as nn
 
 from . import ops
+from . import autograd as ag
 from .ldm_attention import SpatialTransformer, _bf16, _f32, _ver
 from .ldm_unet_blocks import ResBlock, Upsample, Downsample, _to_nchw
 
@@ -131,8 +133,9 @@ class UNetModel(nn.Module):
             raise RuntimeError("adaface_b200 UNetModel runs on CUDA only (no CPU fallback)")
         if y is not None:
             raise NotImplementedError("UNetModel: class-conditional models are not built")
-        if torch.is_grad_enabled() and (x.requires_grad or (context is not None and context.requires_grad)):
-            raise NotImplementedError("UNetModel: the backward pass through the frozen U-Net is not built yet")
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise NotImplementedError("UNetModel: gradients w.r.t. the latent input are not built (stage 2 back-propagates into "
+                                      "the prompt context only, ddpm.py:1645-1707); pass x.detach()")
         pk = self._weights()
         B, cin, H, W = x.shape
         hw = (H, W)
@@ -183,6 +186,6 @@ class UNetModel(nn.Module):
             extra_info["ca_layers_activations"] = {key: {li: acts[li][key] for li in acts}
                                                    for key in ("outfeat", "attn", "attnscore", "q", "attn_out")}
         gn = self.out[0]
-        h = ops.groupnorm_act_tokens(h, pk["gn_w"], pk["gn_b"], gn.num_groups, gn.eps, silu=True)                   # :960
-        o = ops.conv3x3(h, pk["w_out"], hw, bias=pk["b_out"], out_dtype=torch.float32)
+        h = ag.groupnorm_act(h, pk["gn_w"], pk["gn_b"], gn.num_groups, gn.eps, True)                                 # :960
+        o = ag.conv3x3(h, pk, "w_out", self.out[2].weight, hw, bias=pk["b_out"], out_dtype=torch.float32)
         return _to_nchw(o, hw, x.dtype)

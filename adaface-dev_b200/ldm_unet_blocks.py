@@ -12,12 +12,15 @@ ResBlock -> SpatialTransformer chain needs no re-layout -- and a 3x3 convolution
 activation tiles are shifted TMA boxes (zero padding = TMA out-of-bounds fill; adaface_conv3x3_fwd).  GroupNorm + SiLU is
 one pass over the tokens, the time-embedding term rides in the first convolution's epilogue as a per-image bias and the
 skip connection in the second one's as the residual.  ``forward`` keeps the reference's NCHW signature (one transpose
-in, one out); ``forward_tokens`` is the NHWC-resident entry.  Forward only; CUDA only, no fallback.
+in, one out); ``forward_tokens`` is the NHWC-resident entry.  Training: ``forward_tokens`` is differentiable w.r.t. its token
+input (autograd.py: GroupNormActFn / Conv3x3Fn / Upsample2xFn; the weights are the frozen U-Net's and get no gradient); the
+conv-LoRA adapter's own training path is not built.  CUDA only, no fallback.
 """
 import torch
 import torch.nn as nn
 
 from . import ops
+from . import autograd as ag
 from .ldm_attention import _bf16, _f32, _ver
 
 
@@ -30,6 +33,8 @@ def _to_tokens(x):
 
 def _to_nchw(t, hw, dtype):
     b, _, c = t.shape
+    if ag.needs_grad(t):                                        # training: the transposition has a backward (fp32 out)
+        return ag.ChanMajorFn.apply(t, 1.0).view(b, c, *hw).to(dtype)
     if dtype not in (torch.bfloat16, torch.float32):            # fp16 callers (the reference's autocast): through fp32
         return ops.transpose(t, out_dtype=torch.float32).view(b, c, *hw).to(dtype)
     return ops.transpose(t, out_dtype=dtype).view(b, c, *hw)
@@ -37,7 +42,7 @@ def _to_nchw(t, hw, dtype):
 
 def _no_grad_only(name, *ts):
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts):
-        raise NotImplementedError(f"{name}: backward of the frozen U-Net's convolutional blocks is not built yet")
+        raise NotImplementedError(f"{name}: the training path of this module is not built yet")
 
 
 class ResBlock(nn.Module):
@@ -84,25 +89,27 @@ class ResBlock(nn.Module):
     def forward_tokens(self, t, emb, hw, emb_act=None):
         """t bf16 [B, h*w, C] (NHWC), emb [B, emb_channels] -> bf16 [B, h*w, out_channels].  ``emb_act`` = SiLU(emb) as
         bf16 when the caller has already evaluated it (the U-Net shares it between its ResBlocks)."""
-        _no_grad_only("ResBlock", t, emb)
+        _no_grad_only("ResBlock (time embedding)", emb, emb_act)      # the time embedding is frozen: gradients flow through t only
         if self.training and self.dropout > 0:
             raise NotImplementedError("ResBlock: dropout > 0 in training mode is not built (the reference trains with dropout 0)")
         pk = self._weights()
         b = t.shape[0]
-        gn1, gn2 = self.in_layers[0], self.out_layers[0]
-        h = ops.groupnorm_act_tokens(t, pk["gn1_w"], pk["gn1_b"], gn1.num_groups, gn1.eps, silu=True)                 # :240 in_layers[:-1]
+        gn1, gn2, conv1, conv2 = self.in_layers[0], self.out_layers[0], self.in_layers[2], self.out_layers[3]
+        h = ag.groupnorm_act(t, pk["gn1_w"], pk["gn1_b"], gn1.num_groups, gn1.eps, True)                              # :240 in_layers[:-1]
         if emb_act is None:
             emb_act = ops.silu(emb.contiguous())
         emb_out = ops.proj(emb_act, pk["w_emb"], bias=pk["b_emb"], out_dtype=torch.float32)                           # :248
-        h = ops.conv3x3(h, pk["w1"], hw, bias=pk["b1"], rowbias=emb_out)                                              # :247 + :257
-        h = ops.groupnorm_act_tokens(h, pk["gn2_w"], pk["gn2_b"], gn2.num_groups, gn2.eps, silu=True)                 # :258
+        h = ag.conv3x3(h, pk, "w1", conv1.weight, hw, bias=pk["b1"], rowbias=emb_out)                                 # :247 + :257
+        h = ag.groupnorm_act(h, pk["gn2_w"], pk["gn2_b"], gn2.num_groups, gn2.eps, True)                              # :258
         if "w_skip" not in pk:
             skip = t
         elif self.use_conv:
-            skip = ops.conv3x3(t, pk["w_skip"], hw, bias=pk["b_skip"])
+            skip = ag.conv3x3(t, pk, "w_skip", self.skip_connection.weight, hw, bias=pk["b_skip"])
+        elif ag.needs_grad(t):
+            skip = ag.linear(t.view(b * hw[0] * hw[1], -1), pk, "w_skip", "b_skip").view(b, hw[0] * hw[1], -1)
         else:
             skip = ops.proj(t.view(b * hw[0] * hw[1], -1), pk["w_skip"], bias=pk["b_skip"]).view(b, hw[0] * hw[1], -1)
-        return ops.conv3x3(h, pk["w2"], hw, bias=pk["b2"], residual=skip)                                             # :258-260
+        return ag.conv3x3(h, pk, "w2", conv2.weight, hw, bias=pk["b2"], residual=skip)                                # :258-260
 
     def forward(self, x, emb):
         if not x.is_cuda:
@@ -122,14 +129,13 @@ class Upsample(nn.Module):
         self._pack_key, self._pack = None, None
 
     def forward_tokens(self, t, hw):
-        _no_grad_only("Upsample", t)
-        up = ops.upsample2x_tokens(t, hw)                                       # :116
+        up = ag.upsample2x(t, hw)                                               # :116
         if not self.use_conv:
             return up
         key = _ver(self.conv.weight, self.conv.bias)
         if key != self._pack_key:
-            self._pack, self._pack_key = (ops.pack_conv3x3_weight(self.conv.weight), _f32(self.conv.bias)), key
-        return ops.conv3x3(up, self._pack[0], (2 * hw[0], 2 * hw[1]), bias=self._pack[1])      # :118
+            self._pack, self._pack_key = {"w": ops.pack_conv3x3_weight(self.conv.weight), "b": _f32(self.conv.bias)}, key
+        return ag.conv3x3(up, self._pack, "w", self.conv.weight, (2 * hw[0], 2 * hw[1]), bias=self._pack["b"])      # :118
 
     def forward(self, x):
         if not x.is_cuda:
@@ -148,11 +154,10 @@ class Downsample(nn.Module):
         self._pack_key, self._pack = None, None
 
     def forward_tokens(self, t, hw):
-        _no_grad_only("Downsample", t)
         key = _ver(self.op.weight, self.op.bias)
         if key != self._pack_key:
-            self._pack, self._pack_key = (ops.pack_conv3x3_weight(self.op.weight), _f32(self.op.bias)), key
-        return ops.conv3x3(t, self._pack[0], hw, stride=2, bias=self._pack[1])   # :160
+            self._pack, self._pack_key = {"w": ops.pack_conv3x3_weight(self.op.weight), "b": _f32(self.op.bias)}, key
+        return ag.conv3x3(t, self._pack, "w", self.op.weight, hw, stride=2, bias=self._pack["b"])   # :160
 
     def forward(self, x):
         if not x.is_cuda:

@@ -360,6 +360,39 @@ def groupnorm_act_tokens(x, gamma, beta, groups=32, eps=1e-5, silu=True):
     return y
 
 
+def groupnorm_act_tokens_bwd(x, dy, gamma, beta, groups=32, eps=1e-5, silu=True):
+    """dX of groupnorm_act_tokens (frozen gamma / beta): x, dy bf16 [B, HW, C] -> bf16 (adaface_groupnorm_act_tokens_bwd)."""
+    _need(x, "x", torch.bfloat16), _need(dy, "dy", torch.bfloat16), _need(gamma, "gamma", torch.float32), _need(beta, "beta", torch.float32)
+    if x.dim() != 3 or not x.is_contiguous() or dy.shape != x.shape or not dy.is_contiguous():
+        raise ValueError("groupnorm_act_tokens_bwd: x and dy must be contiguous [B, HW, C] tensors of one shape")
+    B, HW, C = x.shape
+    ws = torch.empty((4, B, C), device=x.device, dtype=torch.float32)
+    dx = torch.empty_like(x)
+    _lib.call("adaface_groupnorm_act_tokens_bwd", _ptr(x), _ptr(dy), _ptr(gamma), _ptr(beta), B, HW, C, int(groups), float(eps),
+              1 if silu else 0, _ptr(ws), _ptr(dx), _stream())
+    return dx
+
+
+def resample2x_bwd(x, hw_low, mode):
+    """mode 0: 2x2 sum-pool [B, 4*h*w, C] -> [B, h*w, C] (backward of upsample2x_tokens); mode 1: zero-insert [B, h*w, C] ->
+    [B, 4*h*w, C] (first step of the backward of a stride-2 conv3x3).  hw_low = (h, w) of the LOW resolution."""
+    _need(x, "x", torch.bfloat16)
+    h, w = hw_low
+    n_in = 4 * h * w if mode == 0 else h * w
+    if x.dim() != 3 or not x.is_contiguous() or x.shape[1] != n_in:
+        raise ValueError(f"resample2x_bwd: x must be a contiguous [B, {n_in}, C] tensor")
+    B, _, C = x.shape
+    y = torch.empty((B, h * w if mode == 0 else 4 * h * w, C), device=x.device, dtype=torch.bfloat16)
+    _lib.call("adaface_resample2x_bwd", _ptr(x), _ptr(y), B, h, w, C, int(mode), _stream())
+    return y
+
+
+def pack_conv3x3_weight_dx(weight):
+    """Packed operand of the convolution's input gradient: dX = conv3x3(dY, W') with W'[ci, co, ky, kx] = W[co, ci, 2-ky, 2-kx]
+    (flipped taps, transposed channels) -- the same implicit-GEMM kernel computes it."""
+    return pack_conv3x3_weight(weight.detach().flip(2, 3).transpose(0, 1).contiguous())
+
+
 def silu(x):
     """SiLU(x) -> bf16 (adaface_silu_fwd); x bf16 | fp32 contiguous."""
     _need(x, "x")

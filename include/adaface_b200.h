@@ -178,6 +178,16 @@ int adaface_upsample2x_tokens(const void* x, void* y, int64_t B, int64_t H, int6
  * [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(max_period) i / (dim / 2)); an odd last column is zero. */
 int adaface_timestep_embedding(const float* t, int64_t B, int64_t dim, float max_period, void* out, void* stream);
 
+/* Backward of adaface_groupnorm_act_tokens_fwd w.r.t. x (gamma / beta are frozen U-Net weights, ddpm.py:637-638): x, dy, dx
+ * bf16 [B, HW, C]; statistics are recomputed from x; coef_ws: fp32 [4, B, C] scratch.  Deterministic. */
+int adaface_groupnorm_act_tokens_bwd(const void* x, const void* dy, const float* gamma, const float* beta, int64_t B, int64_t HW,
+                                     int64_t C, int64_t groups, float eps, int act, float* coef_ws, void* dx, void* stream);
+/* Re-sampling steps of the backward pass on NHWC bf16 (H, W = the LOW resolution):
+ *   mode 0: y [B, H, W, C] = 2x2 sum-pool of x [B, 2H, 2W, C]          (backward of adaface_upsample2x_tokens)
+ *   mode 1: y [B, 2H, 2W, C] = x [B, H, W, C] at even positions, else 0 (the backward of a stride-2 adaface_conv3x3_fwd is the
+ *           stride-1 convolution of this tensor with the flipped, transposed weights) */
+int adaface_resample2x_bwd(const void* x, void* y, int64_t B, int64_t H, int64_t W, int64_t C, int mode, void* stream);
+
 /* ---- K5: backward kernels of the stage-2 training step (ddpm.py:1645-1707 back-propagates through the `sc`
  * instance of the U-Net into the LoRA / DoRA adapters, cross_attn_scale_factor and, via the context, SubjBasisGenerator).
  * The reference gets all of this from autograd over eager PyTorch ops; here every gradient is a kernel, recompute

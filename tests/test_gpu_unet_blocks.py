@@ -264,3 +264,96 @@ def test_lora_dora_conv_vs_oracle(k):
         out0 = fresh(x.cuda())
     ref0 = ub.conv3x3(x, W0, b0) if k == 3 else torch.einsum("bchw,oc->bohw", x, W0[:, :, 0, 0]) + b0[None, :, None, None]
     assert err(out0, ref0) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------ backward (training path)
+def gerr(got, ref):
+    """bf16-grade gradient bar of tests/test_gpu_backward.py: max-abs error relative to the max-abs of the reference gradient."""
+    ref = ref.float()
+    return (got.detach().float().cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-12)
+
+
+@pytest.mark.parametrize("shape", [(2, 256, 320), (1, 64, 1280), (2, 100, 64), (1, 1024, 960)], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("silu", [True, False])
+def test_groupnorm_act_tokens_bwd_vs_oracle(shape, silu):
+    import adaface_dev_b200 as a
+    B, HW, Cc = shape
+    x = (rnd((B, HW, Cc), 61) * 1.5 + 0.3).bfloat16().float().requires_grad_(True)
+    dy = rnd((B, HW, Cc), 62)
+    gam, bet = 1 + 0.1 * torch.randn(Cc, generator=torch.Generator().manual_seed(63)), 0.1 * torch.randn(Cc, generator=torch.Generator().manual_seed(64))
+    n = ub.group_norm32(x.permute(0, 2, 1).reshape(B, Cc, HW, 1), gam, bet)
+    y = (ub.silu(n) if silu else n).reshape(B, Cc, HW).permute(0, 2, 1)
+    (ref,) = torch.autograd.grad(y, x, dy)
+    got = a.ops.groupnorm_act_tokens_bwd(x.detach().bfloat16().cuda(), dy.bfloat16().cuda(), gam.cuda(), bet.cuda(), 32, 1e-5, silu=silu)
+    assert got.dtype == torch.bfloat16 and gerr(got, ref) < 2e-2
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 128, 64, 1), (2, 16, 16, 64, 128, 2), (1, 8, 8, 1280, 1280, 1), (3, 12, 32, 64, 64, 1)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_conv3x3_input_gradient_vs_oracle(shape):
+    """dX of the frozen-weight convolution = the same kernel over flipped / transposed weights (stride 2: after zero-insertion)."""
+    import adaface_dev_b200 as a
+    from adaface_dev_b200 import autograd as ag
+    B, h, w, cin, cout, stride = shape
+    x = rnd((B, cin, h, w), 71).requires_grad_(True)
+    wt, bias = rnd((cout, cin, 3, 3), 72, (9 * cin) ** -0.5), rnd((cout,), 73, 0.1)
+    dy = rnd((B, cout, h // stride, w // stride), 74)
+    (ref,) = torch.autograd.grad(ub.conv3x3(x, wt, bias, stride=stride), x, dy)
+    xt = nhwc(x.detach()).requires_grad_(True)
+    pack = {"w": a.ops.pack_conv3x3_weight(wt.cuda())}
+    y = ag.conv3x3(xt, pack, "w", wt.cuda(), (h, w), stride=stride, bias=bias.cuda())
+    y.backward(nhwc(dy))
+    assert xt.grad.dtype == torch.bfloat16 and gerr(nchw(xt.grad, (h, w)), ref) < 2e-2
+    assert "w_dx" in pack                                   # the dX operand is packed once and cached next to the forward pack
+
+
+def test_upsample_and_resblock_backward_vs_oracle():
+    import adaface_dev_b200 as a
+    from adaface_dev_b200 import autograd as ag
+    x = rnd((2, 64, 6, 10), 81)
+    t = nhwc(x).requires_grad_(True)
+    g = rnd((2, 64, 12, 20), 82)
+    ag.upsample2x(t, (6, 10)).backward(nhwc(g))
+    ref = g.reshape(2, 64, 6, 2, 10, 2).sum(dim=(3, 5))
+    assert gerr(nchw(t.grad, (6, 10)), ref) < 1e-2
+    for name in ("unet_res_a", "unet_res_skip", "unet_res_rect"):
+        case = C.build_unet_block_case(name)
+        sp, w = case["spec"], case["w"]
+        wt = {k: torch.from_numpy(v) for k, v in w.items()}
+        xr = torch.from_numpy(case["x"]).requires_grad_(True)
+        emb = torch.from_numpy(case["emb"])
+        out_ref = ub.res_block(wt, xr, emb)
+        G = rnd(tuple(out_ref.shape), 83)
+        (ref,) = torch.autograd.grad(out_ref, xr, G)
+        m = a.ResBlock(sp["cin"], sp["emb"], 0.0, out_channels=sp["cout"], use_conv=bool(sp.get("skip3"))).cuda().eval()
+        _load_res(m, w)
+        hw = (sp["h"], sp["w"])
+        tt = nhwc(xr.detach()).requires_grad_(True)
+        out = m.forward_tokens(tt, emb.cuda(), hw)
+        assert err(nchw(out, hw), out_ref.detach()) < 3e-2
+        out.backward(nhwc(G))
+        assert gerr(nchw(tt.grad, hw), ref) < 3e-2, name
+        assert all(p.grad is None for p in m.parameters())          # frozen U-Net weights receive no gradient
+
+
+def test_unet_context_gradient_vs_oracle():
+    """Stage-2 direction of the whole U-Net mirror (ddpm.py:1645-1707): d loss / d prompt context through every ResBlock,
+    SpatialTransformer, Down / Upsample and skip concatenation, against autograd through the CPU oracle."""
+    case = C.build_unet_case("unet_small")
+    sp = case["spec"]
+    m = _unet_from_case(case)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    x, ts = torch.from_numpy(case["x"]), torch.from_numpy(case["timesteps"])
+    ctx_ref = torch.from_numpy(case["context"]).requires_grad_(True)
+    mask = torch.from_numpy(case["mask"])
+    out_ref = ub.unet_forward(sd, sp["cfg"], x, ts, ctx_ref, mask=mask)
+    G = rnd(tuple(out_ref.shape), 91)
+    (ref,) = torch.autograd.grad(out_ref, ctx_ref, G)
+    ctx = torch.from_numpy(case["context"]).cuda().requires_grad_(True)
+    out = m(x.cuda(), ts.cuda(), context=ctx, extra_info={"img_mask": mask.cuda()})
+    assert out.requires_grad and err(out, out_ref.detach()) < 6e-2
+    out.backward(G.cuda())
+    assert tuple(ctx.grad.shape) == tuple(ref.shape) and gerr(ctx.grad, ref) < 6e-2
+    assert all(p.grad is None for p in m.parameters())
+    with pytest.raises(NotImplementedError):
+        m(x.cuda().requires_grad_(True), ts.cuda(), context=ctx)
