@@ -303,6 +303,8 @@ class Conv3x3Fn(Function):
             if wdx is None:
                 wdx = ctx.pack[key] = ops.pack_conv3x3_weight_dx(ctx.weight)
             g = _b16c(dy)
+            if g.shape[2] % 8:                       # the U-Net's 4-channel output convolution: TMA needs 16-byte pixel strides
+                g = torch.nn.functional.pad(g, (0, 8 - g.shape[2] % 8))
             if ctx.stride == 2:
                 g = ops.resample2x_bwd(g, (ctx.hw[0] // 2, ctx.hw[1] // 2), 1)
             dx = ops.conv3x3(g, wdx, ctx.hw)
