@@ -256,7 +256,7 @@ class SpatialTransformer(nn.Module):
     BasicTransformerBlock x depth -> 1x1 proj_out (zero-initialised) -> + input.  Same module / parameter names as the
     reference (norm, proj_in, transformer_blocks.N, proj_out), so SD-1.5 LDM checkpoints load as they are.
     The norm is fused with the NCHW -> tokens re-layout, the 1x1 convolutions are projection GEMMs, and the way back to
-    NCHW is fused with the residual.  Forward only this round (the frozen U-Net's GroupNorm backward is not built)."""
+    NCHW is fused with the residual.  ``forward_tokens`` is the NHWC-resident, differentiable entry (frozen weights)."""
 
     def __init__(self, in_channels, n_heads, d_head, depth=1, dropout=0., context_dim=None):
         super().__init__()
@@ -306,10 +306,13 @@ class SpatialTransformer(nn.Module):
     def forward(self, x, context=None, mask=None):
         if not x.is_cuda:
             raise RuntimeError("adaface_b200 SpatialTransformer runs on CUDA only (no CPU fallback)")
-        if torch.is_grad_enabled() and (x.requires_grad or (context is not None and context.requires_grad)):
-            raise NotImplementedError("SpatialTransformer backward (GroupNorm / 1x1 convolutions of the frozen U-Net) is not built "
-                                      "yet; use BasicTransformerBlock directly for the training path")
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise NotImplementedError("SpatialTransformer.forward: gradients w.r.t. an NCHW input are not built; use forward_tokens "
+                                      "(differentiable w.r.t. tokens and context) or the UNetModel mirror")
         b, c, h, w = x.shape
+        if ag.needs_grad(context):                     # training through the context: the tokens path carries the backward
+            from .ldm_unet_blocks import _to_nchw, _to_tokens
+            return _to_nchw(self.forward_tokens(_to_tokens(x), (h, w), context=context, mask=mask), (h, w), x.dtype)
         pk = self._weights()
         x_in = x.contiguous()
         t = ops.groupnorm_tokens(x_in, pk["gn_w"], pk["gn_b"], self.norm.num_groups, self.norm.eps)      # :291, 293

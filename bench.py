@@ -375,7 +375,21 @@ def secondary_measurements(torch, a, dev, flush, pk):
             un[f"B{B}"] = {"ms": us / 1e3, "samples_per_s": B / us * 1e6, "kernels": int(nk)}
             del gfn
         out["unet_forward"] = un
-        del unet
+    # -- stage-2 direction through the same mirror: forward + backward w.r.t. the prompt context (frozen U-Net), B = 2, eager
+    xl, ts_ = torch.randn(2, 4, 64, 64, device=dev), torch.randint(0, 1000, (2,), device=dev)
+    cx = torch.randn(2, 97, CTX_DIM, device=dev, requires_grad=True)
+    gy = torch.randn(2, 4, 64, 64, device=dev)
+
+    def unet_step():
+        cx.grad = None
+        unet(xl, ts_, context=cx).backward(gy)
+    n0 = a._lib.launch_count()
+    unet_step()
+    nk = a._lib.launch_count() - n0
+    us = _time_us(torch, flush, unet_step, iters=3, warm=1)
+    out["unet_forward"]["train_fwd_bwd_context_B2"] = {"ms": us / 1e3, "kernels": int(nk), "what": "forward + backward w.r.t. a 97-token "
+                                                      "context through every block (frozen weights), launches issued from Python"}
+    del unet
     # -- training: forward + backward through one captured cross-attention module (level A, B = 1, S = 97, DoRA r = 192
     #    on q/k/v/out, normalize_cross_attn, loss on out + captured attn) and through one self-attention module
     S2 = 97

@@ -357,3 +357,38 @@ def test_unet_context_gradient_vs_oracle():
     assert all(p.grad is None for p in m.parameters())
     with pytest.raises(NotImplementedError):
         m(x.cuda().requires_grad_(True), ts.cuda(), context=ctx)
+
+
+def test_spatial_transformer_context_gradient_vs_oracle():
+    """SpatialTransformer.forward (NCHW surface) with a context that requires grad runs the differentiable tokens path:
+    output against the reference fixture, d context against autograd through the oracle."""
+    import adaface_dev_b200 as a
+    import oracle
+    from mirror_utils import load_ldm_attn
+    name = "ldm_spatial_d80"
+    case = C.build_spatial_case(name)
+    sp, w = case["spec"], case["w"]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    Cc = sp["C"]
+    m = a.SpatialTransformer(Cc, 8, Cc // 8, depth=1, context_dim=768).cuda()
+    blk = m.transformer_blocks[0]
+    load_ldm_attn(blk.attn1, w["attn1"])
+    load_ldm_attn(blk.attn2, w["attn2"])
+    with torch.no_grad():
+        for i, ln in enumerate((blk.norm1, blk.norm2, blk.norm3), 1):
+            ln.weight.copy_(_T(w[f"norm{i}_w"])); ln.bias.copy_(_T(w[f"norm{i}_b"]))
+        blk.ff.net[0].proj.weight.copy_(_T(w["ff_proj_w"])); blk.ff.net[0].proj.bias.copy_(_T(w["ff_proj_b"]))
+        blk.ff.net[2].weight.copy_(_T(w["ff_out_w"])); blk.ff.net[2].bias.copy_(_T(w["ff_out_b"]))
+        m.norm.weight.copy_(_T(w["gn_w"])); m.norm.bias.copy_(_T(w["gn_b"]))
+        m.proj_in.weight.copy_(_T(w["proj_in_w"])[:, :, None, None]); m.proj_in.bias.copy_(_T(w["proj_in_b"]))
+        m.proj_out.weight.copy_(_T(w["proj_out_w"])[:, :, None, None]); m.proj_out.bias.copy_(_T(w["proj_out_b"]))
+    t = C.to_torch({k: v for k, v in case.items() if k != "spec"})
+    ctx_ref = t["context"].clone().requires_grad_(True)
+    out_ref = oracle.spatial_transformer(t["w"], t["x"], context=ctx_ref, mask=t["mask"])
+    G = rnd(tuple(out_ref.shape), 95)
+    (ref,) = torch.autograd.grad(out_ref, ctx_ref, G)
+    ctx = _T(case["context"]).requires_grad_(True)
+    out = m(_T(case["x"]), context=ctx, mask=_T(case["mask"]))
+    assert out.requires_grad and err(out, g["out"]) < 3e-2
+    out.backward(G.cuda())
+    assert gerr(ctx.grad, ref) < 3e-2
