@@ -653,21 +653,25 @@ __global__ void __launch_bounds__(256) conv_splitk_reduce_kernel(const GemmEpilo
 
 // Split-K workspace: one buffer per device, grown on demand (stream-ordered allocation is not needed: the buffer is only
 // ever touched by kernels of the calling stream, and a larger request replaces it after a device synchronisation).
+// Single-stream use per device: two streams running split-K convolutions concurrently would share it.
 static float* splitk_workspace(size_t floats) {
-  static float* ws = nullptr;
-  static size_t cap = 0;
-  if (floats > cap) {
-    if (ws) {
+  constexpr int MAX_DEV = 64;
+  static float* ws[MAX_DEV] = {nullptr};
+  static size_t cap[MAX_DEV] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
+  if (floats > cap[dev]) {
+    if (ws[dev]) {
       if (cudaDeviceSynchronize() != cudaSuccess) return nullptr;
-      cudaFree(ws);
-      ws = nullptr;
-      cap = 0;
+      cudaFree(ws[dev]);
+      ws[dev] = nullptr;
+      cap[dev] = 0;
     }
     const size_t want = floats < (size_t(8) << 20) ? (size_t(8) << 20) : floats;      // >= 32 MB: covers every SD-1.5 shape
-    if (cudaMalloc(&ws, want * sizeof(float)) != cudaSuccess) return nullptr;
-    cap = want;
+    if (cudaMalloc(&ws[dev], want * sizeof(float)) != cudaSuccess) return nullptr;
+    cap[dev] = want;
   }
-  return ws;
+  return ws[dev];
 }
 
 // 3x3 convolution (padding 1, stride 1 | 2) over an NHWC activation: see the CONV notes at the kernel.
