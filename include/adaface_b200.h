@@ -1,8 +1,10 @@
 /* adaface_b200.h -- C-ABI of the B200-native AdaFace hot path (libadaface_b200.so).
  *
- * Drop-in boundary for the reference's attention operator and SubjBasisGenerator transformer
- * (SURVEY.md section 8b).  Every entry point takes raw DEVICE pointers + int64 shapes/strides + a
- * cudaStream_t (passed as void*), never allocates or frees, and returns 0 on success; on failure it
+ * Drop-in boundary for the reference's attention operator, SubjBasisGenerator transformer and -- since ABI v3 -- the
+ * convolutional blocks of the U-Net around them (SURVEY.md sections 8b, 8f).  Every entry point takes raw DEVICE pointers + int64 shapes/strides + a
+ * cudaStream_t (passed as void*), never allocates or frees (one exception: adaface_conv3x3_fwd keeps a per-device fp32
+ * split-K workspace, >= 32 MB, allocated on first use -- so warm a shape up before capturing it into a CUDA graph), and
+ * returns 0 on success; on failure it
  * returns non-zero and adaface_last_error() holds the message (the Python side raises RuntimeError --
  * never breakpoint()/abort as the reference does).
  * All activations are bf16 (uint16 storage) unless a flag says fp32; parameters of epilogues are fp32.
@@ -16,7 +18,7 @@
 extern "C" {
 #endif
 
-#define ADAFACE_B200_ABI_VERSION 2
+#define ADAFACE_B200_ABI_VERSION 3 /* v3 = v2 + the U-Net convolution set (additive) */
 
 /* epilogue activation of adaface_proj_lora_fwd */
 #define ADAFACE_ACT_NONE 0
