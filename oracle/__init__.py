@@ -14,6 +14,8 @@ Pinning (see DESIGN.md "Oracle"):
     /root/reference behind sys.modules stubs (tests/golden/make_golden.py),
     committed as fixtures under tests/golden/*.npz.
   * ResBlock / Upsample / Downsample (unet_blocks_oracle.py): pinned the same way (fixture unet_blocks.npz).
+  * capture-consumer losses (capture_losses_oracle.py): pinned the same way (fixtures closs_*.npz); no
+    kernel consumes them yet.
   * LoRA/DoRA linear (peft, un-vendored, unpinned in requirements.txt:30) and the
     HF-4.44 CLIP encoder loop (transformers>=4.44.2, installed here: 5.5.0 whose
     CLIPEncoder no longer accepts causal_attention_mask): PARITY UNPINNED -- the
@@ -30,7 +32,7 @@ from .attn_oracle import (  # noqa: F401
     geglu_feed_forward,
     spatial_transformer,
 )
-from . import unet_blocks_oracle  # noqa: F401
+from . import unet_blocks_oracle, capture_losses_oracle  # noqa: F401
 from .sbg_oracle import (  # noqa: F401
     clip_mkv_attention,
     clip_encoder_layer,

@@ -231,6 +231,52 @@ def build_unet_case(name):
     return case
 
 
+# Consumers of the captured activations (ldm/util.py:1822-1918, 2047-2121): layers 23 / 24 at a 16 x 16 map.
+CLOSS_CASES = {
+    "closs_bg_suppress":       dict(seed=71, kind="bg", B=2, block=2, N=256, S=77, first=4, n_subj=16),
+    "closs_bg_suppress_1inst": dict(seed=72, kind="bg", B=4, block=1, N=256, S=97, first=6, n_subj=20),
+    "closs_sc_rep_distill":    dict(seed=73, kind="distill", N=256, S=77, C=320, first=4, n_subj=16, fg_percent=0.3),
+    "closs_sc_rep_small_face": dict(seed=74, kind="distill", N=256, S=77, C=320, first=4, n_subj=16, fg_percent=0.05),
+}
+
+
+def build_closs_case(name):
+    sp = CLOSS_CASES[name]
+    rng = np.random.default_rng(sp["seed"])
+    N, S, H = sp["N"], sp["S"], 8
+    case = dict(spec=sp)
+
+    def probs(B):
+        z = rng.standard_normal((B, H, N, S)).astype(np.float32) * 2
+        z[..., sp["first"]:sp["first"] + sp["n_subj"]] += 1.0            # some mass on the subject columns
+        e = np.exp(z - z.max(-1, keepdims=True))
+        return (e / e.sum(-1, keepdims=True)).astype(np.float32)
+
+    if sp["kind"] == "bg":
+        B = sp["B"]
+        case["attn23"], case["attn24"] = probs(B), probs(B)
+        ib, it = subj_indices(B, sp["first"], sp["n_subj"])
+        case["subj_ib"], case["subj_it"] = ib, it
+        m = np.zeros((sp["block"], 1, 64, 64), np.float32)        # the caller hands over the masks of the first block only (:1872)
+        for b in range(sp["block"]):
+            y0, x0 = rng.integers(4, 24, size=2)
+            m[b, 0, y0:y0 + 28, x0:x0 + 24] = 1
+        case["fg_mask"] = m
+    else:
+        C = sp["C"]
+        case["attn23"], case["attn24"] = probs(4), probs(4)
+        for key in ("k23", "k24", "v23", "v24"):
+            case[key] = normal(rng, (4, C, S))
+        case["subj_ib"] = np.zeros(sp["n_subj"], np.int64)
+        case["subj_it"] = np.arange(sp["first"], sp["first"] + sp["n_subj"]).astype(np.int64)
+        emb = np.zeros((4, S, 1), np.float32)
+        emb[:, 1:40] = 1                                                  # prompt tokens (BOS excluded), padding beyond
+        pad = np.zeros((4, S, 1), np.float32)
+        pad[:, 40:] = 1
+        case["emb_mask"], case["pad_mask"] = emb, pad
+    return case
+
+
 # SubjBasisGenerator / CLIP-shaped encoder (surface 3).  E=768, 12 heads x 64, MLP 3072, 77 positions.
 SBG_CASES = {
     "mkv_m1":   dict(seed=41, BS=2, T=77, mult=1, layers=0),

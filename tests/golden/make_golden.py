@@ -267,6 +267,24 @@ def run_unet_cases():
         save(name, case, {"out": out})
 
 
+def run_closs_cases():
+    import ldm.util as U
+
+    for name in C.CLOSS_CASES:
+        case = C.build_closs_case(name)
+        sp = case["spec"]
+        subj = (T(case["subj_ib"]), T(case["subj_it"]))
+        if sp["kind"] == "bg":
+            ca = {22: T(case["attn23"]) * 0 + 1.0 / sp["S"], 23: T(case["attn23"]), 24: T(case["attn24"])}      # layer 22 is ignored
+            loss = U.calc_subj_masked_bg_suppress_loss(ca, subj, sp["block"], T(case["fg_mask"]))
+            save(name, case, {"loss": loss})
+        else:
+            acts = {"attn": {23: T(case["attn23"]), 24: T(case["attn24"])}, "k": {23: T(case["k23"]), 24: T(case["k24"])},
+                    "v": {23: T(case["v23"]), 24: T(case["v24"])}}
+            out = U.calc_sc_rep_attn_distill_loss(acts, subj, T(case["emb_mask"]), T(case["pad_mask"]), sp["fg_percent"])
+            save(name, case, {"losses": torch.stack([torch.as_tensor(o, dtype=torch.float32) for o in out])})
+
+
 # --------------------------------------------------------------------------------- SBG cases
 class _EncOut:
     """Minimal stand-in for HF BaseModelOutput: tuple-indexable and attribute-addressable."""
@@ -385,5 +403,7 @@ if __name__ == "__main__":
         run_unet_block_cases()
     if only in ("", "unet"):
         run_unet_cases()
+    if only in ("", "closs"):
+        run_closs_cases()
     if only in ("", "sbg"):
         run_sbg_cases()

@@ -176,3 +176,24 @@ def test_unet_oracle_vs_reference(name):
     t = C.to_torch({k: v for k, v in case.items() if k != "spec"})
     out = ub.unet_forward(sd, sp["cfg"], t["x"], t["timesteps"], t["context"], mask=t["mask"])
     close(out, g["out"], atol=2e-4, what=name)
+
+
+@pytest.mark.parametrize("name", list(C.CLOSS_CASES))
+def test_capture_consumer_losses_oracle_vs_reference(name):
+    """calc_subj_masked_bg_suppress_loss / calc_sc_rep_attn_distill_loss (ldm/util.py:1822-1918, 2047-2121)
+    against the reference's own functions -- the oracle the fused capture-consumer kernels will be held to."""
+    from oracle import capture_losses_oracle as cl
+    case = C.build_closs_case(name)
+    sp = case["spec"]
+    g = load(name, case)
+    t = C.to_torch({k: v for k, v in case.items() if k != "spec"})
+    subj = (t["subj_ib"], t["subj_it"])
+    if sp["kind"] == "bg":
+        loss = cl.subj_masked_bg_suppress_loss({23: t["attn23"], 24: t["attn24"]}, subj, sp["block"], t["fg_mask"])
+        assert g["loss"] > 0                       # the hinge is active in the fixture
+        close(loss, g["loss"], atol=1e-6, what=name)
+    else:
+        acts = {"attn": {23: t["attn23"], 24: t["attn24"]}, "k": {23: t["k23"], 24: t["k24"]}, "v": {23: t["v23"], 24: t["v24"]}}
+        out = cl.sc_rep_attn_distill_loss(acts, subj, t["emb_mask"], t["pad_mask"], sp["fg_percent"])
+        close(torch.stack([torch.as_tensor(o, dtype=torch.float32) for o in out]), g["losses"], atol=1e-5, what=name)
+        assert (g["losses"] > 0).all() == (sp["fg_percent"] >= 0.1)      # below FG_THRES every term is zero (:2075)
