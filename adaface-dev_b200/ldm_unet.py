@@ -91,6 +91,14 @@ class UNetModel(nn.Module):
             nn.init.zeros_(p)
         self._pack_key, self._pack = None, None
 
+    def load_ldm_state_dict(self, state_dict, prefix="model.diffusion_model.", strict=True):
+        """Load the U-Net part of a full LDM / SD-1.5 checkpoint state dict (``LatentDiffusion`` keeps the U-Net under
+        ``model.diffusion_model.``, ldm/models/diffusion/ddpm.py): keys outside ``prefix`` are ignored."""
+        sd = {k[len(prefix):]: v for k, v in state_dict.items() if k.startswith(prefix)}
+        if not sd:
+            raise KeyError(f"UNetModel.load_ldm_state_dict: no key starts with {prefix!r}")
+        return self.load_state_dict(sd, strict=strict)
+
     def _weights(self):
         conv_in, l0, l2, gn, conv_out = self.input_blocks[0][0], self.time_embed[0], self.time_embed[2], self.out[0], self.out[2]
         ps = (conv_in.weight, conv_in.bias, l0.weight, l0.bias, l2.weight, l2.bias, gn.weight, gn.bias, conv_out.weight, conv_out.bias)

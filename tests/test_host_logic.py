@@ -225,3 +225,20 @@ def test_conv_dora_pack_matches_peft_formula():
         assert (y - ref).abs().max().item() < 2e-2          # bf16 rounding of s*B only
     with pytest.raises(NotImplementedError):
         a.LoraDoraConv2d(torch.nn.Conv2d(8, 8, 3, stride=2, padding=1))
+
+
+def test_unet_loads_the_unet_part_of_an_ldm_checkpoint():
+    """LatentDiffusion checkpoints keep the U-Net under 'model.diffusion_model.'; other entries (VAE, text encoder) are ignored."""
+    m = a.UNetModel(**C.UNET_CFG_SMALL)
+    src = a.UNetModel(**C.UNET_CFG_SMALL)
+    with torch.no_grad():
+        for p in src.parameters():
+            p.normal_()
+    ckpt = {"model.diffusion_model." + k: v for k, v in src.state_dict().items()}
+    ckpt["first_stage_model.encoder.conv_in.weight"] = torch.zeros(1)
+    ckpt["cond_stage_model.transformer.text_model.embeddings.position_ids"] = torch.zeros(1)
+    res = m.load_ldm_state_dict(ckpt)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert all(torch.equal(p, q) for p, q in zip(m.state_dict().values(), src.state_dict().values()))
+    with pytest.raises(KeyError):
+        m.load_ldm_state_dict({"foo.bar": torch.zeros(1)})
