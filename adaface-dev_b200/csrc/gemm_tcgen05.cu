@@ -654,6 +654,9 @@ __global__ void __launch_bounds__(256) conv_splitk_reduce_kernel(const GemmEpilo
 // Split-K workspace: one buffer per device, grown on demand (stream-ordered allocation is not needed: the buffer is only
 // ever touched by kernels of the calling stream, and a larger request replaces it after a device synchronisation).
 // Single-stream use per device: two streams running split-K convolutions concurrently would share it.
+// The 32 MB floor is never outgrown by conv3x3_fwd: it splits only when tiles <= 74 and takes splits <= 148 / tiles, so
+// splits * M * Cout <= 148 tiles * 128 rows * 256 columns = 4.85 M floats < 8 M.  The regrow branch therefore never runs after
+// the first call, and pointers baked into captured CUDA graphs stay valid.
 static float* splitk_workspace(size_t floats) {
   constexpr int MAX_DEV = 64;
   static float* ws[MAX_DEV] = {nullptr};
