@@ -39,3 +39,27 @@ def test_cpu_tensors_are_rejected_loudly():
     proc, attn = a.AttnProcessor_LoRA_Capture(), a.Attention(320, None, 8, 40)
     with pytest.raises(RuntimeError):
         proc(attn, torch.zeros(1, 4, 320))
+
+
+def test_header_is_plain_c_and_links_from_a_c_program(tmp_path):
+    """The boundary is a C ABI: a C99 translation unit that includes include/adaface_b200.h compiles with -pedantic, links
+    against libadaface_b200.so and calls an entry point (no compute: there is no GPU here)."""
+    import shutil
+    import subprocess
+    import __graft_entry__ as g
+    g.build()
+    import adaface_dev_b200 as a
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("no gcc")
+    src = tmp_path / "abi_demo.c"
+    src.write_text('#include "adaface_b200.h"\n'
+                   "int main(void) { return adaface_version() == ADAFACE_B200_ABI_VERSION ? 0 : 1; }\n")
+    libdir = os.path.dirname(a._lib.LIB_PATH)
+    exe = tmp_path / "abi_demo"
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           "-L", libdir, "-ladaface_b200", f"-Wl,-rpath,{libdir}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert subprocess.run([str(exe)]).returncode == 0
