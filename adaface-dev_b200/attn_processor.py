@@ -283,22 +283,11 @@ class AttnProcessor_LoRA_Capture(nn.Module):
             if fast:
                 pass
             elif hp:                                                                 # dalc:309-315
-                col_flag = qm = subj_cols = None
                 mix = bool(self.mix_attn_mats_in_batch)
                 if mix and B % 2:
                     raise ValueError("mix_attn_mats_in_batch needs an even batch ordered [sc.., mc..] (dalc:113)")
-                if self.normalize_cross_attn and not mix:
-                    if subj_indices is None:
-                        raise ValueError("normalize_cross_attn=True requires subj_indices (dalc:120)")
-                    ib, in_ = subj_indices
-                    col_flag = torch.zeros((B, S), device=x.device, dtype=torch.uint8)
-                    col_flag[ib.long(), in_.long()] = 1
-                    qm = ops.qmean(q)
-                if self.capture_subj_cols_only and subj_indices is not None:
-                    ib, in_ = subj_indices
-                    n_sub = int(ib.numel() // B)
-                    subj_cols = torch.full((B, n_sub), -1, device=x.device, dtype=torch.int32)
-                    subj_cols[ib.long(), torch.arange(ib.numel(), device=x.device) % n_sub] = in_.to(torch.int32)
+                col_flag, subj_cols = self._subj_aux(B, S, subj_indices, x.device)
+                qm = ops.qmean(q) if col_flag is not None else None
                 cap = bool(self.capture_ca_activations)
                 if self.cross_attn_scale_factor.device != x.device:     # processor left on the CPU by the caller
                     self.cross_attn_scale_factor.data = self.cross_attn_scale_factor.data.to(x.device)
@@ -353,10 +342,32 @@ class AttnProcessor_LoRA_Capture(nn.Module):
             col_flag[ib.long(), in_.long()] = 1
         if self.capture_subj_cols_only and subj_indices is not None:
             ib, in_ = subj_indices
-            n_sub = int(ib.numel() // B)
+            slot, n_sub = self._subj_slots(ib.to(device), B)
             subj_cols = torch.full((B, n_sub), -1, device=device, dtype=torch.int32)
-            subj_cols[ib.long(), torch.arange(ib.numel(), device=device) % n_sub] = in_.to(torch.int32)
+            subj_cols[ib.long(), slot] = in_.to(device=device, dtype=torch.int32)
         return col_flag, subj_cols
+
+    def _subj_slots(self, ib, B):
+        """Slot of every subject token inside its own instance's row of ``subj_cols`` = how many tokens of the same instance
+        precede it, and n_sub = the largest per-instance count.  The reference's ``subj_indices`` routinely cover only part of the
+        batch (the conditional half of a CFG batch, ddim.py:239-243; sliced batches), so the counts are NOT assumed equal.
+        n_sub sizes an allocation, hence one host read per distinct index tensor (cached on its storage + version); inside a CUDA
+        graph capture an uncached index tensor is an error rather than a silent wrong shape."""
+        key = (ib.data_ptr(), ib._version, ib.numel(), B, ib.device)
+        hit = getattr(self, "_slot_cache", None)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        if ib.numel() == 0:
+            return ib.long(), 1
+        if ib.is_cuda and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("capture_subj_cols_only: call once outside CUDA-graph capture with these subj_indices first")
+        onehot = ib.long()[:, None] == torch.arange(B, device=ib.device)[None, :]
+        if not bool(onehot.any(dim=1).all()):
+            raise IndexError(f"subj_indices: batch index outside [0, {B})")
+        slot = (onehot.cumsum(dim=0) - 1)[torch.arange(ib.numel(), device=ib.device), ib.long()]
+        n_sub = int(onehot.sum(dim=0).max().item())
+        self._slot_cache = (key, slot, n_sub)
+        return slot, n_sub
 
     def _call_train(self, attn, hidden_states, encoder_hidden_states, img_mask, subj_indices):
         """Same arithmetic as ``__call__`` with every kernel paired with its backward (autograd.py): gradients reach

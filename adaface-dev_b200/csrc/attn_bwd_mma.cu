@@ -329,13 +329,14 @@ static int launch_bwd(const BwdParams& p, cudaStream_t stream) {
   using A = AttDims<D>;
   constexpr int smem_kv = 6 * 64 * A::LD * 2 + 4 * 64 * 4;
   constexpr int smem_q = 6 * 64 * A::LD * 2 + 2 * 64;
-  static bool configured = false;
-  if (!configured) {
+  static DevOnce configured;
+  const int cfg_dev = af_device();
+  if (!configured.done(cfg_dev)) {
     AF_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv));
     AF_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv));
     AF_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel<D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv));
     AF_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q));
-    configured = true;
+    configured.set(cfg_dev);
   }
   const dim3 gkv((p.Lk + 63) / 64, p.H, p.B), gq((p.Lq + 63) / 64, p.H, p.B);
   if (D <= 80) {

@@ -429,11 +429,12 @@ static int launch_bwd_tc(const CUtensorMap& tQb, const CUtensorMap& tKs32, const
   static_assert(smem <= 227 * 1024, "tcgen05 attention backward: shared memory exceeds the SM");
   constexpr int DQ_BN = 64;      // 32 (=> 128 TMEM columns, 4 CTAs / SM at d = 40) measured no faster: 1280 vs 1297 us at B = 8, slower at B = 1
   constexpr int smem_dq = 2 * Cfg::BIG_BYTES + 2 * TB_ST * Cfg::NA * DQ_BN * 128 + 1024 + 128;
-  static bool configured = false;
-  if (!configured) {
+  static DevOnce configured;
+  const int cfg_dev = af_device();
+  if (!configured.done(cfg_dev)) {
     AF_CUDA(cudaFuncSetAttribute((attn_bwd_dq_tc_kernel<D, DQ_BN>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq));
     AF_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured.set(cfg_dev);
   }
   attn_bwd_dkdv_tc_kernel<D><<<dim3((p.Lk + TB_BM - 1) / TB_BM, H, B), TB_THREADS, smem, stream>>>(tQs, tKb, tVb, tdOs, p);
   attn_bwd_dq_tc_kernel<D, DQ_BN><<<dim3((p.Lq + TB_BM - 1) / TB_BM, H, B), TB_THREADS, smem_dq, stream>>>(tQb, tKs32, tVs32, tdOb, p);

@@ -475,10 +475,11 @@ static int launch_cap_bwd(const CapBwdParams& p, int chunks, cudaStream_t stream
   constexpr int smem = NI * ((NP + 1) * CB_BN + (NP + 1) * ATT_BM) * A::LD * 2 + 2 * ATT_BM * CB_LDP * 2 +
                        (1 + NI) * CB_BN * D * 4 + CB_BN * 4 + 16 + CB_BN;
   static_assert(smem <= 227 * 1024, "capture backward kernel shared memory exceeds the SM");
-  static bool configured = false;
-  if (!configured) {
+  static DevOnce configured;
+  const int cfg_dev = af_device();
+  if (!configured.done(cfg_dev)) {
     AF_CUDA(cudaFuncSetAttribute(attn_cross_capture_bwd_kernel<D, MIX, F32IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured.set(cfg_dev);
   }
   attn_cross_capture_bwd_kernel<D, MIX, F32IN><<<dim3(chunks, p.H, MIX ? p.B / 2 : p.B), ATT_THREADS, smem, stream>>>(p);
   AF_CUDA(cudaGetLastError());

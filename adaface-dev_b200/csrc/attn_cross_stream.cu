@@ -382,13 +382,14 @@ static int launch_cs(CapParams& p, cudaStream_t stream) {
   const bool maps = p.prob || p.score || p.prob_subj;
   const int smem = ((NP + 1) * NI * KROWS + 4 * NP * NI * 16) * A::LD * 2 + KROWS * 4 + KROWS + (maps ? 4 * 16 * p.S * 4 : 0) + 16;
   AF_CHECK(smem <= 227 * 1024, "attn_cross_stream: %d bytes of shared memory exceed the SM", smem);
-  static int configured_smem = 0, ctas_per_sm[2] = {0, 0};
+  static int configured_smem[AF_MAX_DEV] = {0}, ctas_per_sm[AF_MAX_DEV][2] = {{0, 0}};      // per device
+  const int cfg_dev = af_device();
   auto kern = attn_cross_stream_kernel<D, NTS, MIX, F32IN>;
-  if (smem > configured_smem) {
+  if (smem > configured_smem[cfg_dev]) {
     AF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured_smem = smem;
+    configured_smem[cfg_dev] = smem;
   }
-  int& occ = ctas_per_sm[maps ? 1 : 0];
+  int& occ = ctas_per_sm[cfg_dev][maps ? 1 : 0];
   if (occ == 0) {
     AF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, ATT_THREADS, smem));
     if (occ < 1) occ = 1;
@@ -396,7 +397,7 @@ static int launch_cs(CapParams& p, cudaStream_t stream) {
   // one wave of resident CTAs: chunks per (batch, head) so that the grid just fills the machine
   const int nb = MIX ? p.B / 2 : p.B;
   const int tiles = (p.Lq + ATT_BM - 1) / ATT_BM;
-  int chunks = (148 * occ + nb * p.H - 1) / (nb * p.H);
+  int chunks = (af_num_sms() * occ + nb * p.H - 1) / (nb * p.H);
   if (chunks > tiles) chunks = tiles;
   if (chunks < 1) chunks = 1;
   p.tiles_per_cta = (tiles + chunks - 1) / chunks;

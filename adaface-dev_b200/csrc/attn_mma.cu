@@ -209,10 +209,11 @@ template <int D>
 static int launch_attn(const AttnParams& p, cudaStream_t stream) {
   using A = AttDims<D>;
   constexpr int smem = (ATT_BM + 4 * ATT_BN) * A::LD * 2 + 2 * ATT_BN;
-  static bool configured = false;
-  if (!configured) {
+  static DevOnce configured;
+  const int cfg_dev = af_device();
+  if (!configured.done(cfg_dev)) {
     AF_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured.set(cfg_dev);
   }
   dim3 grid((p.Lq + ATT_BM - 1) / ATT_BM, p.H, p.B);
   attn_fwd_kernel<D><<<grid, ATT_THREADS, smem, stream>>>(p);

@@ -862,19 +862,20 @@ static int launch_ta_quad(const CUtensorMap& tQ, const CUtensorMap& tK, const CU
   constexpr int smem2 = 2 * Cfg::Q_BYTES + TQ_ST * (Cfg::K_BYTES + Cfg::V_BYTES) + 1024 + 256;
   constexpr int smemS = 2 * Cfg::Q_BYTES + TQ_ST * 2 * (Cfg::K_BYTES + Cfg::V_BYTES) + 1024 + 256;
   static_assert(2 * TA_BM * (Cfg::DO + 1) * 4 <= TQ_ST * 2 * (Cfg::K_BYTES + Cfg::V_BYTES), "SPLIT merge scratch must fit the K/V ring");
-  static bool configured = false;
-  if (!configured) {
+  static DevOnce configured;
+  const int cfg_dev = af_device();
+  if (!configured.done(cfg_dev)) {
     AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 4, EMU, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
     AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 2, EMU, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
     AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 4, EMU, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smemS));
-    configured = true;
+    configured.set(cfg_dev);
   }
   static int tail_mode = -1;
   if (tail_mode < 0) {
     const char* e = getenv("ADAFACE_QUAD_TAIL");     // 1 (default): two tiles x two key halves per tail CTA; 2: two-tile CTAs
     tail_mode = (e && e[0] == '2') ? 2 : 1;
   }
-  const int n_sm = 148;
+  const int n_sm = af_num_sms();
   const int n_qb4 = (p.Lq + 4 * TA_BM - 1) / (4 * TA_BM);
   const int units4 = B * H * n_qb4;
   const int n_ktiles = (p.Lk + TA_BN - 1) / TA_BN;
@@ -901,10 +902,11 @@ static int launch_ta_mc(const CUtensorMap& tQ, const CUtensorMap& tK, const CUte
                         cudaStream_t stream) {
   using Cfg = TaCfg<D>;
   constexpr int smem = Cfg::Q_BYTES + 2 * (Cfg::K_BYTES + Cfg::V_BYTES) + 1024 + 128;
-  static bool configured = false;
-  if (!configured) {
+  static DevOnce configured;
+  const int cfg_dev = af_device();
+  if (!configured.done(cfg_dev)) {
     AF_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_mc_kernel<D, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured.set(cfg_dev);
   }
   dim3 grid((p.Lq + TA_BM - 1) / TA_BM, H, B);
   AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_mc_kernel<D, EMU>, grid, dim3(TA_THREADS), smem, stream, tQ, tK, tV, p));
@@ -918,10 +920,11 @@ static int launch_ta(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtenso
                      cudaStream_t stream) {
   using Cfg = TaCfg<D>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "tcgen05 attention: shared memory exceeds the SM");
-  static bool configured = false;
-  if (!configured) {
+  static DevOnce configured;
+  const int cfg_dev = af_device();
+  if (!configured.done(cfg_dev)) {
     AF_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<D, EMU, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
+    configured.set(cfg_dev);
   }
   dim3 grid((p.Lq + TA_BM - 1) / TA_BM, H, B);
   AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_kernel<D, EMU, PT>, grid, dim3(TA_THREADS), Cfg::SMEM_BYTES, stream, tQ, tK, tV, p));
@@ -1201,17 +1204,18 @@ static int launch_tc_cross(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse;
   const int smem = 2 * Cfg::Q_BYTES + 2 * Cfg::NA * NK * 128 + 1024 + 128;
-  static int configured = 0;
-  if (smem > configured) {
+  static int configured[AF_MAX_DEV] = {0};                 // per device
+  const int cfg_dev = af_device();
+  if (smem > configured[cfg_dev]) {
     AF_CUDA(cudaFuncSetAttribute((attn_cross_tc_kernel<D, NKT>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
+    configured[cfg_dev] = smem;
   }
   int per_sm = 512 / p.tmem_cols;                           // TMEM columns bound the residency
   const int by_smem = (227 * 1024) / (smem + 1024);
   if (per_sm > by_smem) per_sm = by_smem;
   if (per_sm > ((D <= 64) ? 4 : 2)) per_sm = (D <= 64) ? 4 : 2;
   if (per_sm < 1) per_sm = 1;
-  int grid = 148 * per_sm;
+  int grid = af_num_sms() * per_sm;
   if (grid > p.n_units) grid = p.n_units;
   AF_CUDA(launch_pdl(2, attn_cross_tc_kernel<D, NKT>, dim3(grid), dim3(TA_THREADS), smem, stream, tQ, tK, tV, p));
   AF_CUDA(cudaGetLastError());

@@ -20,6 +20,17 @@ bool pdl_enabled(int kind) {
   return (g_pdl & kind) != 0;
 }
 
+int af_num_sms() {
+  static std::atomic<int> sms[AF_MAX_DEV];
+  const int dev = af_device();
+  int n = sms[dev].load(std::memory_order_relaxed);
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    sms[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
 #error "adaface_b200 kernels are written for sm_100a only"
 #endif
@@ -33,6 +35,31 @@ void set_error(const char* fmt, ...);
       return 2;                                                                             \
     }                                                                                       \
   } while (0)
+
+// Per-DEVICE one-time configuration (cudaFuncSetAttribute and the SM count are per device, not per process; the library is
+// built for several devices in one process).  One instance per call site; a race on the first call only repeats an idempotent,
+// thread-safe runtime call.
+constexpr int AF_MAX_DEV = 64;
+inline int af_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < AF_MAX_DEV) ? d : 0;
+}
+struct DevOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool done(int dev) const { return (mask.load(std::memory_order_acquire) >> dev) & 1ull; }
+  void set(int dev) { mask.fetch_or(1ull << dev, std::memory_order_release); }
+};
+#define AF_CONFIG_SMEM(kernel, bytes)                                                                        \
+  do {                                                                                                       \
+    static ::adaface::DevOnce _once;                                                                         \
+    const int _dev = ::adaface::af_device();                                                                 \
+    if (!_once.done(_dev)) {                                                                                 \
+      AF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));       \
+      _once.set(_dev);                                                                                       \
+    }                                                                                                        \
+  } while (0)
+int af_num_sms();     // SM count of the CURRENT device (cached per device); 148 on B200
 
 // Encodes a 2-D bf16 row-major [rows, cols] tensor (row stride `ld` elements) as a TMA descriptor with
 // a {64 cols x box_rows} box and 128-byte swizzle.  Returns 0 on success.

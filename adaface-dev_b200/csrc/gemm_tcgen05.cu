@@ -484,18 +484,14 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
                        const GemmEpilogue& ep, int n_tiles, cudaStream_t stream,
                        const typename ConvArg<CONV>::type& cmaps = typename ConvArg<CONV>::type()) {
   using Cfg = GemmCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
+  static DevOnce configured;
+  const int cfg_dev = af_device();
+  if (!configured.done(cfg_dev)) {
     AF_CUDA(cudaFuncSetAttribute(gemm_tn_tcgen05_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg::SMEM_BYTES));
-    configured = true;
+    configured.set(cfg_dev);
   }
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    AF_CUDA(cudaGetDevice(&dev));
-    AF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int num_sms = af_num_sms();
   const int tiles = n_tiles * ep.num_m * (CONV ? ep.splits : 1);
   dim3 grid(tiles < num_sms ? tiles : num_sms);
   AF_CUDA(launch_pdl(1, gemm_tn_tcgen05_kernel<BN, CONV>, grid, dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tA, tB, tA2, tB2, cmaps, ep));

@@ -31,6 +31,22 @@ def _f32(t):
     return None if t is None else t.detach().float().contiguous()
 
 
+def _ldm_key_mask(mask, B):
+    """attention.py:185-194 fills masked scores with ``-finfo.max`` (not -inf): every key of an instance whose mask is ALL zero
+    gets the same score, so that instance attends uniformly to all keys (out = mean of V) -- realistic when the nearest resize of
+    ``SpatialTransformer`` (:298) makes a small face mask vanish at 8 x 8 / 16 x 16.  Returns the uint8 key mask with such
+    instances unmasked (so the kernels never see an empty row) and the per-instance empty flags; evaluated on the device."""
+    m = mask.reshape(B, -1) != 0
+    empty = m.sum(dim=1) == 0
+    return (m | empty[:, None]).to(torch.uint8).contiguous(), empty
+
+
+def _uniform_where_empty(o, v, empty):
+    """Replace the output rows of empty-mask instances by the uniform-attention result mean_j V[j] (per channel = per head)."""
+    vmean = v.float().mean(dim=1, keepdim=True).to(o.dtype)
+    return torch.where(empty[:, None, None], vmean.expand_as(o), o)
+
+
 class CrossAttention(nn.Module):
     def __init__(self, query_dim, context_dim=None, heads=8, dim_head=64, dropout=0.):
         super().__init__()
@@ -71,12 +87,14 @@ class CrossAttention(nn.Module):
         C = pk["wq"].shape[0]
         x2d = x16.reshape(B * N, Cq)
         q = prob = score = None
-        key_mask = None if mask is None else (mask.reshape(B, -1) != 0).to(torch.uint8).contiguous()
+        key_mask, empty = (None, None) if mask is None else _ldm_key_mask(mask, B)
         if context is None:
             if self.save_cross_attn_vars:
                 raise NotImplementedError("save_cross_attn_vars is only set on cross-attention layers (attn2)")
             qkv = ag.linear(x2d, pk, "wqkv").view(B, N, 3 * C)
             o = ag.attention(qkv, qkv, qkv, (0, C, 2 * C), C, C, H, self.scale, key_mask)
+            if empty is not None:
+                o = _uniform_where_empty(o, qkv[:, :, 2 * C:], empty)
         else:
             ctx = context.to(torch.bfloat16).contiguous()
             S = ctx.shape[1]
@@ -93,6 +111,8 @@ class CrossAttention(nn.Module):
                 q = ag.linear(x2d, pk, "wq").view(B, N, C)
                 kv = ag.linear(c2d, pk, "wkv").view(B, S, 2 * C)
                 o = ag.attention(q, kv, kv, (0, 0, C), C, C, H, self.scale, key_mask)
+                if empty is not None:
+                    o = _uniform_where_empty(o, kv[:, :, C:], empty)
         res2d = None if residual is None else residual.reshape(B * N, -1)
         out = ag.linear(o.view(B * N, C), pk, "wo", "bo", residual=res2d, out_dtype=out_dtype).view(B, N, -1)
         if self.save_cross_attn_vars:
@@ -110,13 +130,16 @@ class CrossAttention(nn.Module):
         C = pk["wq"].shape[0]
         x2d = x16.view(B * N, Cq)
         prob = score = None
-        key_mask = None
-        if mask is not None:                                                      # attention.py:185-194
-            key_mask = (mask.reshape(B, -1) != 0).to(torch.uint8).contiguous()
+        key_mask, empty = (None, None) if mask is None else _ldm_key_mask(mask, B)       # attention.py:185-194
         if context is None:
             if self.save_cross_attn_vars:
                 raise NotImplementedError("save_cross_attn_vars is only set on cross-attention layers (attn2)")
-            o = ops.self_attention_fused_qkv(x2d, pk["wqkv"], None, B, N, H, self.scale, key_mask)
+            if key_mask is None:
+                o = ops.self_attention_fused_qkv(x2d, pk["wqkv"], None, B, N, H, self.scale)
+            else:
+                qkv = ops.proj(x2d, pk["wqkv"]).view(B, N, 3 * C)
+                o = ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H, self.scale, key_mask=key_mask)
+                o = _uniform_where_empty(o, qkv[:, :, 2 * C:], empty)
         else:
             ctx = context.to(torch.bfloat16).contiguous()
             S = ctx.shape[1]
@@ -133,6 +156,7 @@ class CrossAttention(nn.Module):
                 q = ops.proj(x2d, pk["wq"]).view(B, N, C)
                 kv = ops.proj(c2d, pk["wkv"]).view(B, S, 2 * C)
                 o = ops.attention(q, kv[:, :, :C], kv[:, :, C:], H, self.scale, key_mask=key_mask)
+                o = _uniform_where_empty(o, kv[:, :, C:], empty)
         res2d = None if residual is None else residual.view(B * N, -1)
         out = ops.proj(o.view(B * N, C), pk["wo"], bias=pk["bo"], residual=res2d, out_dtype=out_dtype).view(B, N, -1)
         if self.save_cross_attn_vars:                                             # attention.py:207-220

@@ -63,10 +63,21 @@ def gather_images(local: torch.Tensor, n_images: int, group=None) -> torch.Tenso
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, bucket_bytes: int = 64 << 20,
                         average: bool = True) -> int:
     """Bucketed gradient all-reduce of the trainable parameters (what DDP does at the accumulation boundary,
-    main.py:618 / yaml:149).  Parameters without a gradient contribute zeros so that every rank issues the same
-    collectives.  NVSwitch makes the cost launch-latency bound, hence few large flat buckets.  Returns #buckets."""
+    main.py:618 / yaml:149).  NVSwitch makes the cost launch-latency bound, hence few large flat buckets.
+
+    Every rank must issue the same collectives, so a has-gradient flag per parameter is all-reduced (MAX) first: a parameter
+    whose gradient is None on EVERY rank (e.g. LoRA modules switched off for this iteration by reset_attn_cache_and_flags
+    while requires_grad stays True) is left out and keeps ``.grad = None`` -- exactly what the reference's DDP step leaves
+    behind, so Adam / AdamW neither update its moments nor decay it.  A parameter with a gradient on at least one rank
+    contributes zeros from the ranks that have none.  Returns the number of data buckets."""
     params = [p for p in params if p.requires_grad]
+    if not params:
+        return 0
     world = dist.get_world_size(group)
+    dev = params[0].device
+    has = torch.tensor([0 if p.grad is None else 1 for p in params], device=dev, dtype=torch.int32)
+    dist.all_reduce(has, op=dist.ReduceOp.MAX, group=group)
+    params = [p for p, h in zip(params, has.tolist()) if h]
     n_buckets, i = 0, 0
     while i < len(params):
         bucket, size = [], 0
@@ -74,15 +85,23 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, bucket
             bucket.append(params[i])
             size += params[i].numel() * 4
             i += 1
-        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in bucket])
+        flat = torch.empty(size // 4, device=dev, dtype=torch.float32)
+        off = 0
+        for p in bucket:
+            dst = flat[off:off + p.numel()]
+            if p.grad is None:
+                dst.zero_()
+            else:
+                dst.copy_(p.grad.reshape(-1))
+            off += p.numel()
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         if average:
             flat /= world
         off = 0
         for p in bucket:
-            g = flat[off:off + p.numel()].view_as(p).to(p.dtype)
+            g = flat[off:off + p.numel()].view_as(p)
             if p.grad is None:
-                p.grad = g.clone()
+                p.grad = g.to(p.dtype, copy=True)
             else:
                 p.grad.copy_(g)
             off += p.numel()

@@ -202,6 +202,8 @@ class CLIPTextModelWrapper(nn.Module):
             hs.append(h)
         fl = tm.final_layer_norm
         if train:
+            if isinstance(hidden_state_layer_weights, (list, tuple)):
+                hidden_state_layer_weights = torch.tensor(hidden_state_layer_weights, device=h.device, dtype=torch.float32).view(-1, 1)
             if hidden_state_layer_weights is None:
                 tail, wl_t = [h], torch.ones(1, device=h.device)
             else:
@@ -214,16 +216,25 @@ class CLIPTextModelWrapper(nn.Module):
             return (out.view(BS, T_run, E),)
         if hidden_state_layer_weights is None:                                    # :291-306
             tail, wl = [h], [1.0]
+        elif isinstance(hidden_state_layer_weights, (list, tuple)):               # host weights: no device read at all
+            tot = float(sum(hidden_state_layer_weights))
+            wl = [float(v) / tot for v in hidden_state_layer_weights]
+            tail = hs[-len(wl):]
         else:
             w = hidden_state_layer_weights.detach().float().reshape(-1)
             if hidden_state_layer_weights.numel() != hidden_state_layer_weights.shape[0]:
                 raise NotImplementedError("per-channel hidden_state_layer_weights ([3,768]) are not used by the face path")
-            # host copy of the 3 normalised weights, cached per parameter version (no device sync in steady state,
-            # so the forward can be captured into a CUDA graph)
-            key = (hidden_state_layer_weights.data_ptr(), hidden_state_layer_weights._version)
-            if getattr(self, "_wl_cache", (None, None))[0] != key:
-                self._wl_cache = (key, (w / w.sum()).tolist())
-            wl = self._wl_cache[1]
+            # host copy of the 3 normalised weights, cached per tensor OBJECT and version: the cache keeps the tensor alive, so
+            # its identity cannot be recycled by another tensor (a data_ptr can).  A parameter that is stepped in place bumps
+            # _version and is re-read; steady-state inference does no device sync and can be captured into a CUDA graph.
+            cache = getattr(self, "_wl_cache", None)
+            if cache is None or cache[0] is not hidden_state_layer_weights or cache[1] != hidden_state_layer_weights._version:
+                if w.is_cuda and torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("hidden_state_layer_weights: pass a list of floats (or run once outside the capture) -- a "
+                                       "device tensor cannot be read during CUDA-graph capture")
+                cache = (hidden_state_layer_weights, hidden_state_layer_weights._version, (w / w.sum()).tolist())
+                self._wl_cache = cache
+            wl = cache[2]
             tail = hs[-len(wl):]
         out = ops.sbg_head(tail, wl, fl.weight.detach().float(), fl.bias.detach().float(), fl.eps)
         return (out.view(BS, T_run, E),)
@@ -308,7 +319,7 @@ class FrozenCLIPTextEncoder(nn.Module):
             sw = self.last_layers_skip_weights
             if abs(sum(sw) - 1.0) > 1e-6:
                 raise NotImplementedError("last_layers_skip_weights must sum to 1 (the reference uses [0.5, 0.5])")
-            w = torch.tensor(sw, device=tok.device, dtype=torch.float32).view(-1, 1)
+            w = [float(v) for v in sw]        # host list: no per-call device tensor, no sync, graph-capturable
         return self.transformer(input_token_embs=tok, hidden_state_layer_weights=w)[0]    # modules.py:300-330
 
 

@@ -95,6 +95,8 @@ def build_proc_case(name):
 
 LDM_CASES = {
     "ldm_self_mask":  dict(seed=31, B=2, N=256, C=320, mask=True),
+    # one instance's mask is ALL zero: the reference fills with -finfo.max, so that instance attends uniformly (attention.py:188-194)
+    "ldm_self_mask_empty": dict(seed=37, B=3, N=64, C=320, mask=True, zero_instance=1),
     "ldm_cross_save": dict(seed=32, B=2, N=64, C=320, S=77, cross=True, save=True),
     "ldm_block":      dict(seed=33, B=2, N=256, C=320, S=77, block=True, mask=True),
     "ldm_block_d80":  dict(seed=34, B=1, N=64, C=640, S=77, block=True),
@@ -108,7 +110,7 @@ def build_ldm_case(name):
     case = dict(spec=sp)
     case["x"] = normal(rng, (B, N, C))
     side = int(math.sqrt(N))
-    case["mask"] = img_mask(rng, B, side) if sp.get("mask") else None
+    case["mask"] = img_mask(rng, B, side, sp.get("zero_instance")) if sp.get("mask") else None
     if sp.get("block"):
         w = {"attn1": attn_weights(rng, C, C), "attn2": attn_weights(rng, C, 768)}
         for i in (1, 2, 3):

@@ -331,7 +331,7 @@ def test_processor_training_step_vs_oracle(name):
         assert all(p.grad is None for p in mod.parameters())
 
 
-@pytest.mark.parametrize("name", ["ldm_block", "ldm_block_d80", "ldm_cross_save", "ldm_self_mask"])
+@pytest.mark.parametrize("name", ["ldm_block", "ldm_block_d80", "ldm_cross_save", "ldm_self_mask", "ldm_self_mask_empty"])
 def test_ldm_training_step_vs_oracle(name):
     case = C.build_ldm_case(name)
     sp = case["spec"]

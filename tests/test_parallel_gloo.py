@@ -96,3 +96,22 @@ def test_shard_range_covers_everything_once():
             assert seen == list(range(n))
             sizes = [a.parallel.shard_range(n, r, world) for r in range(world)]
             assert max(e - b for b, e in sizes) - min(e - b for b, e in sizes) <= 1
+
+
+def _none_grad_job(rank, world):
+    import adaface_dev_b200 as a
+    torch.manual_seed(0)
+    used, one_sided, unused = (torch.nn.Parameter(torch.ones(4)) for _ in range(3))
+    loss = (used * (rank + 1)).sum()
+    if rank == 0:
+        loss = loss + (one_sided * 3).sum()                   # gradient on rank 0 only
+    loss.backward()
+    a.parallel.allreduce_gradients([used, one_sided, unused])
+    return (used.grad.tolist(), one_sided.grad.tolist(), unused.grad is None)
+
+
+def test_gradient_allreduce_keeps_globally_unused_params_gradless():
+    """A parameter without a gradient on every rank keeps .grad = None (DDP semantics: Adam must not touch it); one with a
+    gradient on some rank only gets the mean with zeros from the others."""
+    for used, one_sided, unused_is_none in _run(_none_grad_job):
+        assert used == [1.5] * 4 and one_sided == [1.5] * 4 and unused_is_none
