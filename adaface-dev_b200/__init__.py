@@ -7,6 +7,7 @@ Host-side mirrors of the reference's operator surface over the C-
     CrossAttention, FeedForward, BasicTransformerBlock, SpatialTransformer       (ldm_attention.py)
     ResBlock, Upsample, Downsample, LoraDoraConv2d                               (ldm_unet_blocks.py)
     UNetModel, TimestepEmbedSequential                                           (ldm_unet.py)
+    DDIMSampler, UNetDenoiser                                                    (ddim.py)
     SubjBasisGenerator, Arc2FaceID2ImgPrompt, CLIPTextModelWrapper, CLIPAttentionMKV   (subj_basis_generator.py)
 
 The directory is named ``adaface-dev_b200`` (not importable as is); import it as ``adaface_dev_b200``
@@ -20,6 +21,7 @@ from .ldm_unet_blocks import ResBlock, Upsample, Downsample, LoraDoraConv2d  # n
 from .ldm_unet import UNetModel, TimestepEmbedSequential  # noqa: F401
 from .subj_basis_generator import (SubjBasisGenerator, Arc2FaceID2ImgPrompt, FrozenCLIPTextEncoder, CLIPTextModelWrapper,  # noqa: F401
                                    CLIPAttentionMKV, CLIPTextConfig, template_ids)
+from .ddim import DDIMSampler, UNetDenoiser, ddim_cfg_step, make_linear_alphas_cumprod  # noqa: F401
 from .build import build  # noqa: F401
 from .graphs import graphed  # noqa: F401
 from . import parallel  # noqa: F401

@@ -1,0 +1,64 @@
+// Sampler-side elementwise kernels around the U-Net (BASELINE config 4: 50-step DDIM with classifier-free guidance).
+//   ddim_cfg_step_kernel   ldm/models/diffusion/ddim.py:253-255 (CFG combine) + :280-301 (x0 prediction, x_{t-1}) in ONE pass.
+// HBM-bound and tiny (32 KB per image); what matters is that the whole step stays on the device and inside the step's CUDA
+// graph: the per-step scalars come from a DEVICE coefficient row, so one captured graph serves all 50 steps.
+// Every operation is a separately rounded IEEE fp32 op in the reference's order (no FMA contraction, no fast-math division),
+// so for identical eps the result is bit-identical to the reference's torch fp32 arithmetic.
+#include "common.cuh"
+#include "../../include/adaface_b200.h"
+
+namespace adaface {
+
+extern long long g_launch_count;
+
+// coef (device, fp32[8]): 0 guidance scale, 1 sqrt(1 - a_t), 2 sqrt(a_t), 3 sqrt(a_prev), 4 sqrt(1 - a_prev - sigma^2), 5 sigma_t,
+// 6 temperature, 7 unused
+__device__ __forceinline__ float ddim_one(float ec, float eu, float x, float nz, bool cfg, const float (&c)[8], float& pred) {
+  const float e = cfg ? __fadd_rn(eu, __fmul_rn(c[0], __fsub_rn(ec, eu))) : ec;            // ddim.py:255
+  pred = __fdiv_rn(__fsub_rn(x, __fmul_rn(c[1], e)), c[2]);                                // :281
+  const float dir = __fmul_rn(c[4], e);                                                    // :285
+  const float noise = __fmul_rn(__fmul_rn(c[5], nz), c[6]);                                // :289
+  return __fadd_rn(__fadd_rn(__fmul_rn(c[3], pred), dir), noise);                          // :301
+}
+
+__global__ void __launch_bounds__(256) ddim_cfg_step_kernel(const float4* __restrict__ eps, const float4* x, const float4* __restrict__ noise,
+                                                            const float* __restrict__ coef, float4* x_prev, float4* x_dup,
+                                                            float4* __restrict__ pred_x0, long long n4, int cfg) {
+  float c[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i] = __ldg(coef + i);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 ec = eps[i];
+    const float4 eu = cfg ? eps[n4 + i] : ec;
+    const float4 xv = x[i];
+    const float4 nz = noise ? noise[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 p, o;
+    o.x = ddim_one(ec.x, eu.x, xv.x, nz.x, cfg, c, p.x);
+    o.y = ddim_one(ec.y, eu.y, xv.y, nz.y, cfg, c, p.y);
+    o.z = ddim_one(ec.z, eu.z, xv.z, nz.z, cfg, c, p.z);
+    o.w = ddim_one(ec.w, eu.w, xv.w, nz.w, cfg, c, p.w);
+    x_prev[i] = o;
+    if (x_dup) x_dup[i] = o;
+    if (pred_x0) pred_x0[i] = p;
+  }
+}
+
+int ddim_cfg_step(const float* eps, int64_t n_images, int64_t n_per_image, int has_uncond, const float* x, const float* coef,
+                  const float* noise, float* x_prev, float* x_dup, float* pred_x0, cudaStream_t stream) {
+  AF_CHECK(eps && x && coef && x_prev, "ddim_cfg_step: null pointer");
+  AF_CHECK(n_images > 0 && n_per_image > 0 && n_per_image % 4 == 0, "ddim_cfg_step: n_per_image must be a positive multiple of 4 (got %lld)",
+           (long long)n_per_image);
+  for (const void* p : {(const void*)eps, (const void*)x, (const void*)noise, (const void*)x_prev, (const void*)x_dup, (const void*)pred_x0})
+    AF_CHECK(((uintptr_t)p & 15) == 0, "ddim_cfg_step: pointers must be 16-byte aligned");
+  const long long n4 = n_images * n_per_image / 4;
+  long long grid = (n4 + 255) / 256;
+  const long long cap = (long long)af_num_sms() * 8;
+  if (grid > cap) grid = cap;
+  ddim_cfg_step_kernel<<<(unsigned)grid, 256, 0, stream>>>((const float4*)eps, (const float4*)x, (const float4*)noise, coef, (float4*)x_prev,
+                                                          (float4*)x_dup, (float4*)pred_x0, n4, has_uncond ? 1 : 0);
+  AF_CUDA(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+}  // namespace adaface

@@ -257,11 +257,11 @@ def build_stack(torch, a, device):
 
 
 # kernels of libadaface_b200.so per step: 16 blocks x (self: QKV GEMM, attention, out GEMM; cross: q GEMM, kv GEMM,
-# attention, out GEMM) = 112; counted live when the step is not replayed from a CUDA graph.
-LAUNCHES_PER_STEP = 16 * 7 + 5      # + the tail launch of the 5 level-A self-attention calls
+# attention, out GEMM) = 112 + the tail launch of the 5 level-A self-attention calls; COUNTED LIVE in main_gpu on one eager step.
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel, from the ncu --set full capture
 # summarised in profiles/r01_ncu_full_attn_quad.txt (algorithmic: 4 * B * N * C * 2 = 83.9 MB; the 21 MB of output leave L2 after the kernel)
 ROOFLINE_TRAFFIC_BYTES = 66132224   # 64.4 MB read + 1.7 MB written inside the two launches (outputs are still in L2)
+ROOFLINE_TRAFFIC_SOURCE = "ncu --set full capture, profiles/r01_ncu_full_attn_quad.txt (dram__bytes_read.sum + dram__bytes_write.sum; not measurable inside bench.py)"
 
 
 def run_stack(mods, xs, ctx):
@@ -273,6 +273,26 @@ def run_stack(mods, xs, ctx):
             y = attn2(y1, encoder_hidden_states=ctx)
         outs.append(y)
     return outs
+
+
+def check_step_output(torch, mods, xs_cpu, ctx_cpu, outs):
+    """Ties the timed step to correctness inside the run: the outputs the timed CUDA graph left behind for levels D and C
+    (last block: self-attention then cross-attention module) against the CPU oracle on sample 0 (bf16-rounded weights,
+    fp32 arithmetic).  Bar = north_star's max-abs 2e-2 on bf16 block outputs."""
+    import oracle
+    errs = {}
+    for li in (3, 2):
+        attn1, attn2 = mods[li][-1]
+        r = lambda p: p.detach().float().cpu().bfloat16().float()
+        wd = lambda m: {"to_q": r(m.to_q.weight), "to_k": r(m.to_k.weight), "to_v": r(m.to_v.weight), "to_out_w": r(m.to_out[0].weight),
+                        "to_out_b": r(m.to_out[0].bias), "cross_attn_scale_factor": torch.tensor(0.8)}
+        x, c = xs_cpu[li][:1].float(), ctx_cpu[:1].float()
+        with torch.no_grad():
+            y1, _ = oracle.processor_forward(wd(attn1), x, None, heads=HEADS)
+            y, _ = oracle.processor_forward(wd(attn2), y1.bfloat16().float(), c, heads=HEADS)
+        errs[LEVELS[li][0]] = (outs[li][:1].float().cpu() - y).abs().max().item()
+    return {"what": "output of the timed graph, levels D and C (last block, sample 0) vs the CPU oracle", "max_abs_err": errs,
+            "tol": 2e-2, "ok": all(v < 2e-2 for v in errs.values())}
 
 
 def _time_us(torch, flush, fn, iters=10, warm=3):
@@ -291,7 +311,7 @@ def _time_us(torch, flush, fn, iters=10, warm=3):
     return statistics.median(ts)
 
 
-def secondary_measurements(torch, a, dev, flush, pk):
+def secondary_measurements(torch, a, dev, flush, pk, unet):
     """Secondary lines (not the headline): the HBM-bound cross-attention / capture kernels against the measured copy
     bandwidth (SURVEY 8d #1 byte counts), SubjBasisGenerator at BASELINE config 2, and one stage-2-style
     forward + backward through a captured level-A cross-attention module (config 5, scaled to the hot path)."""
@@ -352,17 +372,6 @@ def secondary_measurements(torch, a, dev, flush, pk):
             conv[f"{side}x{side}_{cin}to{cout}"] = {"us": us, "tflops": fl / us / 1e6, "peak_tflops": tf_peak, "frac": fl / us / 1e6 / tf_peak}
         out["conv3x3_implicit_gemm"] = {"kernel": "gemm_tn_tcgen05_kernel<BN, CONV>", "batch": BATCH, "bound": "tensor", **conv}
         # -- the caller of the whole path: one SD-1.5 U-Net forward (random weights), one CUDA graph per batch size
-        with torch.device("meta"):
-            unet = a.UNetModel(in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2, attention_resolutions=[4, 2, 1],
-                               channel_mult=(1, 2, 4, 4), num_heads=8, use_spatial_transformer=True, context_dim=CTX_DIM)
-        unet = unet.to_empty(device=dev).eval()
-        for k_, p_ in unet.named_parameters():
-            if p_.dim() >= 2:
-                p_.normal_(std=p_[0].numel() ** -0.5)
-            elif k_.endswith("weight"):
-                p_.fill_(1.0)
-            else:
-                p_.zero_()
         un = {"what": "UNetModel.forward (openaimodel.py:820-960), 64x64 latents, 77-token context, bf16 NHWC-resident, CUDA graph",
               "params": sum(p_.numel() for p_ in unet.parameters())}
         for B in (2, BATCH):
@@ -389,7 +398,6 @@ def secondary_measurements(torch, a, dev, flush, pk):
     us = _time_us(torch, flush, unet_step, iters=3, warm=1)
     out["unet_forward"]["train_fwd_bwd_context_B2"] = {"ms": us / 1e3, "kernels": int(nk), "what": "forward + backward w.r.t. a 97-token "
                                                       "context through every block (frozen weights), launches issued from Python"}
-    del unet
     # -- training: forward + backward through one captured cross-attention module (level A, B = 1, S = 97, DoRA r = 192
     #    on q/k/v/out, normalize_cross_attn, loss on out + captured attn) and through one self-attention module
     S2 = 97
@@ -423,6 +431,97 @@ def secondary_measurements(torch, a, dev, flush, pk):
     return out
 
 
+def build_unet(torch, a, dev):
+    """SD-1.5 U-Net mirror, random init (no checkpoints offline): weights ~ N(0, 1/fan_in), norms 1 / 0."""
+    with torch.device("meta"):
+        unet = a.UNetModel(in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2, attention_resolutions=[4, 2, 1],
+                           channel_mult=(1, 2, 4, 4), num_heads=8, use_spatial_transformer=True, context_dim=CTX_DIM)
+    unet = unet.to_empty(device=dev).eval()
+    g = torch.Generator(device=dev).manual_seed(0)
+    with torch.no_grad():
+        for k_, p_ in unet.named_parameters():
+            if p_.dim() >= 2:
+                p_.normal_(std=p_[0].numel() ** -0.5, generator=g)
+            elif k_.endswith("weight"):
+                p_.fill_(1.0)
+            else:
+                p_.zero_()
+    return unet
+
+
+DDIM_IMAGES, DDIM_STEPS, DDIM_GUIDANCE = 64, 50, 4.0
+
+
+def ddim_measurement(torch, a, dev, rank, world, barrier, unet=None):
+    """BASELINE config 4: 50-step DDIM at 512^2, 64 images x CFG = U-Net batch 128 in total, the images sharded
+    across the ranks (STRONG scaling, no collective: every image's (cond, uncond) pair stays on one GPU).  Metric: denoise
+    image-steps / s = 50 * 64 / time.  `value`: latents and prompts already resident in HBM; `e2e`: pinned host buffers in
+    (x_T fp32, cond / uncond prompt embeddings bf16), host latents out, copies inside the timed region."""
+    import torch.distributed as dist
+    unet = unet if unet is not None else build_unet(torch, a, dev)
+    model = a.UNetDenoiser(unet)
+    b, e = a.parallel.shard_range(DDIM_IMAGES, rank, world)
+    n_loc = e - b
+    mb = int(os.environ.get("ADAFACE_BENCH_DDIM_MB", "16"))
+    mb = max(1, min(mb, n_loc))
+    g = torch.Generator().manual_seed(1234)
+    xT_all = torch.randn(DDIM_IMAGES, 4, 64, 64, generator=g)
+    cond_all = torch.randn(DDIM_IMAGES, S_CTX, CTX_DIM, generator=g)
+    cond_all[:, 4:20] = torch.randn(DDIM_IMAGES, 16, CTX_DIM, generator=g) * 0.5          # ada tokens spliced into the prompt
+    unc_all = torch.randn(1, S_CTX, CTX_DIM, generator=g).expand(DDIM_IMAGES, -1, -1)
+    xT_h = xT_all[b:e].contiguous().pin_memory()
+    cond_h = cond_all[b:e].to(torch.bfloat16).contiguous().pin_memory()
+    unc_h = unc_all[b:e].to(torch.bfloat16).contiguous().pin_memory()
+    out_h = torch.empty(n_loc, 4, 64, 64).pin_memory()
+    xT_d, cond_d, unc_d = xT_h.to(dev), cond_h.to(dev), unc_h.to(dev)
+    smp = a.DDIMSampler(model, micro_batch=mb)
+    kw = dict(eta=0., verbose=False, guidance_scale=DDIM_GUIDANCE)
+    n0 = a._lib.launch_count()
+    smp.sample(2, n_loc, (4, 64, 64), conditioning=cond_d, x_T=xT_d, unconditional_conditioning=unc_d, **kw)     # captures the step graph(s)
+    launches_warm = a._lib.launch_count() - n0
+    torch.cuda.synchronize()
+
+    def timed(fn):
+        barrier()
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = fn()
+        t.record()
+        barrier()
+        return s.elapsed_time(t), r
+
+    t_dev, x0 = timed(lambda: smp.sample(DDIM_STEPS, n_loc, (4, 64, 64), conditioning=cond_d, x_T=xT_d,
+                                         unconditional_conditioning=unc_d, **kw)[0])
+
+    def e2e():
+        xd, cd, ud = xT_h.to(dev, non_blocking=True), cond_h.to(dev, non_blocking=True), unc_h.to(dev, non_blocking=True)
+        x0_ = smp.sample(DDIM_STEPS, n_loc, (4, 64, 64), conditioning=cd, x_T=xd, unconditional_conditioning=ud, **kw)[0]
+        out_h.copy_(x0_, non_blocking=True)
+        return x0_
+    t_e2e, x0e = timed(e2e)
+    torch.cuda.synchronize()
+    same = bool(torch.equal(x0e, x0)) and bool(torch.equal(out_h, x0.cpu()))
+    finite = bool(torch.isfinite(x0).all())
+    tt = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = tt.tolist()
+    work = DDIM_STEPS * DDIM_IMAGES
+    n_mb = (n_loc + mb - 1) // mb
+    return {"metric": "UNet denoise steps/s @512^2 (50-step DDIM, 64 images x CFG, batch sharded)", "unit": "image-steps/s",
+            "value": work / (t_dev * 1e-3), "ms_total": t_dev, "scaling": "strong", "n_gpus": world,
+            "e2e": {"value": work / (t_e2e * 1e-3), "unit": "image-steps/s", "ms_total": t_e2e,
+                    "h2d_bytes_per_run": int(xT_h.numel() * 4 + cond_h.numel() * 2 + unc_h.numel() * 2), "d2h_bytes_per_run": int(out_h.numel() * 4)},
+            "unet_samples_per_s_per_gpu": 2 * n_loc * DDIM_STEPS / (t_dev * 1e-3),
+            "unet_tflops_per_gpu": 2 * n_loc * DDIM_STEPS * 8.0327e11 / (t_dev * 1e-3) / 1e12,
+            "config": {"global_images": DDIM_IMAGES, "unet_batch_global": 2 * DDIM_IMAGES, "images_per_gpu": n_loc,
+                       "micro_batch_images": mb, "unet_batch_per_call": 2 * mb, "ddim_steps": DDIM_STEPS, "guidance_scale": DDIM_GUIDANCE,
+                       "eta": 0.0, "timesteps": "1, 21, ..., 981 (ddim.py:29-35)", "latent": "4x64x64", "ctx": "77x768, ada tokens in rows 4:20",
+                       "launch": f"one CUDA graph (U-Net + fused CFG/DDIM update) replayed {DDIM_STEPS * n_mb} times per rank; no collective"},
+            "graph_replays_per_rank": DDIM_STEPS * n_mb, "kernels_in_two_warmup_steps_eager": int(launches_warm),
+            "checks": {"finite": finite, "e2e_equals_device_run_bitwise": same}}
+
+
 def main_gpu(args):
     import torch
     import torch.distributed as dist
@@ -453,6 +552,9 @@ def main_gpu(args):
     with torch.no_grad():
         for _ in range(max(3, args.warmup)):
             run_stack(mods, xs, ctx)
+        n0 = a._lib.launch_count()
+        run_stack(mods, xs, ctx)
+        launches_per_step = a._lib.launch_count() - n0          # counted live on one eager step (the graph replays the same kernels)
         if use_graph:
             # one U-Net step of the attention stack = 112 short launches: replay them as one CUDA graph
             step_fn = a.graphed(lambda *t: run_stack(mods, list(t[:-1]), t[-1]), *xs, ctx)
@@ -470,8 +572,9 @@ def main_gpu(args):
             step(xs, ctx)
             e.record()
         barrier()
-        launches = (a._lib.launch_count() - n0) if not use_graph else LAUNCHES_PER_STEP * args.steps
+        launches = (a._lib.launch_count() - n0) if not use_graph else launches_per_step * args.steps
         t_ms = sum(s.elapsed_time(e) for s, e in ev)
+        check = check_step_output(torch, mods, xs_cpu, ctx_cpu, step(xs, ctx)) if rank == 0 else None
 
         # ---- end to end: host buffers in, host results out, through the same public operator.
         # The step is cut into independent units (levels D, C, B, A -- the four levels of the stack do not depend on each
@@ -578,12 +681,25 @@ def main_gpu(args):
         k_ms = statistics.mean(kt)
         k_flops = 4.0 * BATCH * N * N * C
         clocks = sampler.stop()
-    extra = None
-    if world == 1 and os.environ.get("ADAFACE_BENCH_EXTRAS", "1") != "0":
+    extra = ddim = unet = None
+    want_ddim = os.environ.get("ADAFACE_BENCH_DDIM", "1") != "0"
+    want_extra = world == 1 and os.environ.get("ADAFACE_BENCH_EXTRAS", "1") != "0"
+    if want_ddim or want_extra:
+        unet = build_unet(torch, a, dev)
+    if want_ddim:
+        # BASELINE config 4 on every N: strong scaling of the 50-step DDIM run (global batch 128 sharded, no collective)
         try:
-            extra = secondary_measurements(torch, a, dev, flush, peaks())
+            ddim = ddim_measurement(torch, a, dev, rank, world, barrier, unet)
+        except Exception as ex:
+            if world > 1:
+                raise                  # a rank that drops out would dead-lock the others in the next collective
+            ddim = {"error": f"{type(ex).__name__}: {ex}"}
+    if want_extra:
+        try:
+            extra = secondary_measurements(torch, a, dev, flush, peaks(), unet)
         except Exception as ex:      # secondary lines never take the headline down with them
             extra = {"error": f"{type(ex).__name__}: {ex}"}
+    del unet
 
     tt = torch.tensor([t_ms, t_e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -602,19 +718,24 @@ def main_gpu(args):
                        "modules": 32, "ctx_tokens": S_CTX, "heads": HEADS, "flops_per_step_per_gpu": fl_step,
                        "parallelism": f"dp{world} (batch sharded, no collective)",
                        "l2": "256 MB flush written between timed iterations; per-step working set > 1 GB",
-                       "launch": "CUDA graph replay of the 117-kernel step" if use_graph else "eager Python launches"},
+                       "launch": f"CUDA graph replay of the {launches_per_step}-kernel step" if use_graph else "eager Python launches",
+                       "chaining": "within a level every block reads the level's input x (blocks are independent: same FLOPs, same shapes "
+                                   "as the U-Net's, no data dependence between blocks of a level); attn2 consumes attn1's output"},
             "frac_of_bf16_peak": value / world / pk["bf16_tflops_sustained"],
             "e2e": {"value": world * fl_step / (t_e2e_ms * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e_ms,
                     "how": f"{len(units)} CUDA-graph units (levels D, C, B, A; the last level-A block per batch slice so that its D2H overlaps); H2D / kernels / D2H on three streams"},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "gpu_launches_per_step": int(launches_per_step),
+            "check": check,
             "clocks": clocks,
             "roofline": {"kernel": "attn_fwd_tcgen05_quad_kernel<40> (level-A self-attention core, B=8, 4096 tok, 8x40; bulk + tail launch)",
                          "bound": "tensor", "achieved": k_flops / (k_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops"],
                          "unit": "TFLOP/s", "frac": k_flops / (k_ms * 1e-3) / 1e12 / pk["bf16_tflops"],
-                         "traffic": ROOFLINE_TRAFFIC_BYTES, "peak_source": pk["source"] + " (burst: kernel timed alone)",
+                         "traffic": ROOFLINE_TRAFFIC_BYTES, "traffic_source": ROOFLINE_TRAFFIC_SOURCE, "peak_source": pk["source"] + " (burst: kernel timed alone)",
                          "ms_per_launch": k_ms, "flops_per_launch": k_flops},
         }
+        if ddim is not None:
+            line["unet_steps_per_s"] = ddim
         if extra is not None:
             line["secondary"] = extra
         if world == 1:

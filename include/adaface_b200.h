@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define ADAFACE_B200_ABI_VERSION 3 /* v3 = v2 + the U-Net convolution set (additive) */
+#define ADAFACE_B200_ABI_VERSION 4 /* v3 = v2 + the U-Net convolution set; v4 = v3 + sampler step, capture consumers (additive) */
 
 /* epilogue activation of adaface_proj_lora_fwd */
 #define ADAFACE_ACT_NONE 0
@@ -252,6 +252,18 @@ int adaface_sbg_head_bwd(const float* h0, const float* h1, const float* h2, cons
                          int n_layers, int64_t ldh, const float* w, const float* dout, int64_t lddo, float* dh0,
                          float* dh1, float* dh2, float* dh3, float* dwl, float* dw, float* db, int64_t M, int64_t C,
                          float eps, void* stream);
+
+/* ---- K6 (ABI v4): sampler step around the U-Net ---------------------------------------------------------------------
+ * One DDIM step for n_images latents of n_per_image fp32 elements each (ldm/models/diffusion/ddim.py:223-302, the
+ * arithmetic after apply_model): classifier-free-guidance combine e = e_u + g (e_c - e_u) (:253-255) when has_uncond
+ * (eps = [cond images.., uncond images..], the reference's CFG batch order :239-248), pred_x0 = (x - sqrt(1-a_t) e) / sqrt(a_t)
+ * (:281), x_prev = sqrt(a_prev) pred_x0 + sqrt(1 - a_prev - sigma^2) e + sigma * noise * temperature (:285-301).
+ * coef: DEVICE fp32[8] = {g, sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma, temperature, -} so that one
+ * captured CUDA graph serves every step.  noise (fp32, same shape as x) may be NULL (eta = 0).  x_prev may alias x;
+ * x_dup (nullable) receives a second copy of x_prev (the uncond half of the next step's CFG batch); pred_x0 nullable.
+ * Separately rounded fp32 ops in the reference's order: bit-identical to torch fp32 for identical eps. */
+int adaface_ddim_cfg_step(const float* eps, int64_t n_images, int64_t n_per_image, int has_uncond, const float* x,
+                          const float* coef, const float* noise, float* x_prev, float* x_dup, float* pred_x0, void* stream);
 
 #ifdef __cplusplus
 }

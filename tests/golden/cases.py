@@ -201,8 +201,13 @@ def build_unet_block_case(name):
 # seeded stream (so that the reference module, the oracle and the mirror are filled identically from their own key sets).
 UNET_CFG_SMALL = dict(in_channels=4, model_channels=320, out_channels=4, num_res_blocks=1, attention_resolutions=[1, 2],
                       channel_mult=(1, 2), num_heads=8, use_spatial_transformer=True, context_dim=768, transformer_depth=1, legacy=False)
+# The SD-1.5 configuration itself (not in the repo's YAMLs, standard SD-v1 values; 859.5 M parameters): the size
+# BASELINE config 3 is quoted on.  Its weights are regenerated from the seed on both sides (3.4 GB fp32: not a fixture).
+UNET_CFG_SD15 = dict(in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2, attention_resolutions=[4, 2, 1],
+                     channel_mult=(1, 2, 4, 4), num_heads=8, use_spatial_transformer=True, context_dim=768, transformer_depth=1, legacy=False)
 UNET_CASES = {
     "unet_small": dict(seed=61, cfg=UNET_CFG_SMALL, B=2, h=16, w=16, S=77, mask=True),
+    "unet_sd15_full": dict(seed=62, cfg=UNET_CFG_SD15, B=2, h=64, w=64, S=77, big=True),
 }
 
 
@@ -230,6 +235,34 @@ def build_unet_case(name):
     case["timesteps"] = rng.integers(0, 1000, size=(B,)).astype(np.int64)
     case["context"] = normal(rng, (B, sp["S"], sp["cfg"]["context_dim"]))
     case["mask"] = img_mask(rng, B, 64) if sp.get("mask") else None
+    return case
+
+
+# DDIM sampling loop around the U-Net (ldm/models/diffusion/ddim.py:70-302; BASELINE config 4).  `model`: "standin" = an analytic
+# noise predictor (pins the schedule / CFG / update arithmetic on the CPU), "unet_small" = the reference U-Net of UNET_CFG_SMALL.
+DDIM_CASES = {
+    "ddim_standin_50":     dict(seed=81, model="standin", B=2, h=8, w=8, S=77, steps=50, guidance=4.0),
+    "ddim_standin_anneal": dict(seed=82, model="standin", B=3, h=8, w=8, S=77, steps=20, guidance=(6.0, 2.0)),
+    "ddim_standin_nocfg":  dict(seed=83, model="standin", B=2, h=8, w=8, S=77, steps=10, guidance=1.0, no_uncond=True),
+    "ddim_unet_small":     dict(seed=84, model="unet_small", B=2, h=16, w=16, S=77, steps=4, guidance=3.0),
+}
+
+
+def standin_eps(x, t, c):
+    """Analytic stand-in for model.apply_model(x, t, c): smooth in x, depends on the timestep and on the prompt."""
+    tt = t.to(x.dtype).view(-1, 1, 1, 1) / 1000.0
+    cc = c.mean(dim=(1, 2)).view(-1, 1, 1, 1)
+    return torch.tanh(0.7 * x + 0.5 * tt + 3.0 * cc)
+
+
+def build_ddim_case(name):
+    sp = DDIM_CASES[name]
+    rng = np.random.default_rng(sp["seed"])
+    B, h, w = sp["B"], sp["h"], sp["w"]
+    case = dict(spec=sp)
+    case["x_T"] = normal(rng, (B, 4, h, w))
+    case["cond"] = normal(rng, (B, sp["S"], 768))
+    case["uncond"] = None if sp.get("no_uncond") else normal(rng, (B, sp["S"], 768))
     return case
 
 

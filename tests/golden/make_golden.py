@@ -253,8 +253,11 @@ def run_unet_cases():
     from ldm.modules.attention import BasicTransformerBlock
 
     for name in C.UNET_CASES:
+        if len(sys.argv) > 2 and sys.argv[2] != name:      # `make_golden.py unet unet_small`: one case only
+            continue
         case = C.build_unet_case(name)
         sp = case["spec"]
+        torch.manual_seed(0)
         m = UNetModel(**sp["cfg"]).eval()
         for mod in m.modules():
             if isinstance(mod, BasicTransformerBlock):
@@ -265,6 +268,57 @@ def run_unet_cases():
             out = m(T(case["x"]), T(case["timesteps"]), context=T(case["context"]),
                     extra_info={"img_mask": T(case["mask"]), "capture_ca_activations": False})
         save(name, case, {"out": out})
+
+
+class _StandInLDM:
+    """The 10-line stand-in for LatentDiffusion that DDIMSampler needs: schedule buffers + apply_model."""
+
+    def __init__(self, apply_model):
+        from ldm.modules.diffusionmodules.util import make_beta_schedule
+        betas = make_beta_schedule("linear", 1000, linear_start=0.00085, linear_end=0.012)
+        ac = np.cumprod(1. - betas, axis=0)                                          # ddpm.py:301-303
+        self.num_timesteps = 1000
+        self.betas = torch.tensor(betas, dtype=torch.float32)
+        self.alphas_cumprod = torch.tensor(ac, dtype=torch.float32)
+        self.alphas_cumprod_prev = torch.tensor(np.append(1., ac[:-1]), dtype=torch.float32)
+        self.device = torch.device("cpu")
+        self.apply_model = apply_model
+
+
+def run_ddim_cases():
+    from ldm.models.diffusion.ddim import DDIMSampler
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    from ldm.modules.attention import BasicTransformerBlock
+
+    class CpuDDIMSampler(DDIMSampler):
+        def register_buffer(self, name, attr):       # the reference's hard-codes .to("cuda") (ddim.py:21-25): keep tensors where they are
+            setattr(self, name, attr)
+
+    for name in C.DDIM_CASES:
+        case = C.build_ddim_case(name)
+        sp = case["spec"]
+        if sp["model"] == "standin":
+            apply_model = C.standin_eps
+        else:
+            m = UNetModel(**C.UNET_CFG_SMALL).eval()
+            for mod in m.modules():
+                if isinstance(mod, BasicTransformerBlock):
+                    mod.checkpoint = False
+            sd = C.unet_state_dict({k: v.shape for k, v in m.state_dict().items()}, sp["seed"] + 1000)
+            m.load_state_dict({k: T(v) for k, v in sd.items()})
+            apply_model = lambda x, t, c, m=m: m(x, t, context=c, extra_info={})
+        ldm_model = _StandInLDM(apply_model)
+        sampler = CpuDDIMSampler(ldm_model)
+        g = sp["guidance"]
+        with torch.no_grad():
+            img, inter = sampler.sample(sp["steps"], sp["B"], (4, sp["h"], sp["w"]), conditioning=T(case["cond"]), eta=0.,
+                                        verbose=False, x_T=T(case["x_T"]), guidance_scale=list(g) if isinstance(g, tuple) else g,
+                                        unconditional_conditioning=T(case["uncond"]), log_every_t=1)
+        save(name, case, {"x0": img, "pred_x0_last": inter["pred_x0"][-1], "x_after_first": inter["x_inter"][1],
+                          "alphas_cumprod": ldm_model.alphas_cumprod, "ddim_timesteps": sampler.ddim_timesteps, "ddim_alphas": sampler.ddim_alphas,
+                          "ddim_alphas_prev": np.asarray(sampler.ddim_alphas_prev, dtype=np.float64),
+                          "ddim_sigmas": np.asarray(sampler.ddim_sigmas, dtype=np.float64),
+                          "ddim_sqrt_one_minus_alphas": sampler.ddim_sqrt_one_minus_alphas})
 
 
 def run_closs_cases():
@@ -403,6 +457,8 @@ if __name__ == "__main__":
         run_unet_block_cases()
     if only in ("", "unet"):
         run_unet_cases()
+    if only in ("", "ddim"):
+        run_ddim_cases()
     if only in ("", "closs"):
         run_closs_cases()
     if only in ("", "sbg"):

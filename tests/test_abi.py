@@ -17,7 +17,7 @@ def test_library_builds_and_exports_header_symbols():
     assert declared == set(a._lib.SIGNATURES), "ctypes table and header disagree"
     for name in declared:
         assert getattr(lib, name) is not None
-    assert a._lib.load().adaface_version() == 3
+    assert a._lib.load().adaface_version() == 4
 
 
 def test_product_never_imports_oracle():

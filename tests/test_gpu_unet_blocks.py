@@ -12,6 +12,7 @@ import torch
 import cases as C
 from oracle import unet_blocks_oracle as ub
 from mirror_utils import _T
+from parity_log import record
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -210,6 +211,7 @@ def test_unet_vs_reference_golden(name):
     """The whole U-Net mirror (NHWC-resident forward) against the output of the reference's UNetModel on the same state dict."""
     case = C.build_unet_case(name)
     g = np.load(os.path.join(GOLD, name + ".npz"))
+    sp_big = case["spec"].get("big", False)
     m = _unet_from_case(case)
     x, ts, ctx, mask = _T(case["x"]), torch.from_numpy(case["timesteps"]).cuda(), _T(case["context"]), _T(case["mask"])
     with torch.no_grad():
@@ -217,8 +219,20 @@ def test_unet_vs_reference_golden(name):
     assert out.dtype == torch.float32 and tuple(out.shape) == g["out"].shape
     ref = torch.from_numpy(g["out"])
     rel = ((out.cpu() - ref).norm() / ref.norm()).item()
-    # eight bf16 blocks deep (the reference runs fp16 under autocast): output std 0.56, max 2.4
+    record("unet", name, "eps [B,4,h,w]", err(out, ref), 6e-2, f"rel-L2 {rel:.2e}; ref max-abs {ref.abs().max().item():.2f}")
+    # eight (small) / 25 (SD-1.5) bf16 blocks deep (the reference runs fp16 under autocast): output std 0.56, max 2.4
     assert err(out, ref) < 6e-2 and rel < 2e-2, (err(out, ref), rel)
+    if sp_big:
+        # SD-1.5 itself (BASELINE config 3's size): captured layers are the reference's own 22, 23, 24 (openaimodel.py:853)
+        info = {"capture_ca_activations": True}
+        with torch.no_grad():
+            out2 = m(x, ts, context=ctx, extra_info=info)
+        assert err(out2, out.cpu()) < 3e-2
+        acts = info["ca_layers_activations"]
+        assert set(acts["attn"]) == {22, 23, 24} and tuple(acts["attn"][24].shape) == (2, 8, 4096, 77)
+        assert tuple(acts["outfeat"][22].shape) == (2, 320, 64, 64)
+        assert (acts["attn"][23].sum(-1) - 1).abs().max().item() < 1e-3
+        return
     # capture plumbing (openaimodel.py:849-941): same prediction, maps of the captured cross-attention layers handed back
     m.captured_layer_indices = (7, 8)              # the two full-resolution output blocks of this small configuration
     info = {"img_mask": mask, "capture_ca_activations": True}
