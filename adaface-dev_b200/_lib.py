@@ -53,6 +53,12 @@ SIGNATURES = {
     "adaface_layernorm_bwd": [_p, _i32, _i64, _p, _i32, _i64, _p, _p, _i64, _p, _p, _i64, _i64, _f32, _p],
     "adaface_act_fwd": [_p, _i64, _p, _i64, _i64, _i64, _i32, _p],
     "adaface_act_bwd": [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i32, _p],
+    # ---- capture with fused consumers (ABI v4)
+    "adaface_attn_cross_consume_fwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
+                                       _f32, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _i64, _p],
+    "adaface_attn_cross_consume_bwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64,
+                                       _i64, _f32, _p, _p, _p, _i32, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i32, _p, _f32,
+                                       _p, _p, _p, _p, _p, _p, _p, _p],
     # ---- sampler step (ABI v4)
     "adaface_ddim_cfg_step": [_p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _p],
     "adaface_sbg_head_bwd": [_p, _p, _p, _p, _c.POINTER(_f32), _i32, _i64, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _i64,

@@ -192,6 +192,7 @@ class AttnProcessor_LoRA_Capture(nn.Module):
         self.q_lora_updates_query = q_lora_updates_query
         # subject-columns-only capture (optional mode): also emit cached_activations['attn_subj']
         self.capture_subj_cols_only = False
+        self.capture_consumers = None          # set_capture_consumers(): fused reductions of the captured map
         self.to_q_lora = self.to_k_lora = self.to_v_lora = self.to_out_lora = None
         # Reference quirk 2 (fixed): always defined, so capture works with LoRA globally off (dalc:164-168, 314).
         self.cross_attn_scale_factor = nn.Parameter(torch.tensor(0.8), requires_grad=True)
@@ -201,6 +202,50 @@ class AttnProcessor_LoRA_Capture(nn.Module):
                     raise ValueError(f"unknown LoRA projection '{name}'")
                 setattr(self, f"to_{name}_lora", LoraDoraLinear(layer, "default", r=lora_rank, lora_alpha=lora_alpha,
                                                                 use_dora=lora_uses_dora, lora_dropout=0.1))
+
+    def set_capture_consumers(self, subj_sum=False, ref_attn=None, keep_attn=False):
+        """B200 extension: while capturing, REDUCE the probability map inside the attention kernel instead of
+        writing [B,8,N,S] fp32 -- ``cached_activations['attn_subj_sum']`` [B,H,N] = mass on each instance's subject columns (what
+        calc_subj_masked_bg_suppress_loss reads, ldm/util.py:1862-1868) when ``subj_sum``; ``['attn_sqdiff']`` [B] = sum over
+        (h, i, j) of (attn - ref_attn)^2 against the detached sc_rep map ``ref_attn`` [B,H,N,S] (calc_sc_rep_attn_distill_loss,
+        :2084-2089).  Both are differentiable.  'attn' / 'attnscore' are then only produced when ``keep_attn``.  Call with no
+        arguments to switch the consumers off."""
+        self.capture_consumers = {"subj_sum": bool(subj_sum), "ref_attn": ref_attn, "keep_attn": bool(keep_attn)} \
+            if (subj_sum or ref_attn is not None) else None
+
+    def _consume(self, q, k, v, H, sm_scale, B, S, subj_indices, train):
+        """The capture call with fused consumers (both the autograd and the no-grad form)."""
+        from . import autograd as ag
+        cons = self.capture_consumers
+        if self.mix_attn_mats_in_batch:
+            raise NotImplementedError("capture consumers are not defined together with mix_attn_mats_in_batch")
+        col_flag, _ = self._subj_aux(B, S, subj_indices, q.device)
+        sum_flag = None
+        if cons["subj_sum"]:
+            if subj_indices is None:
+                raise ValueError("capture consumer 'subj_sum' requires subj_indices")
+            ib, in_ = subj_indices
+            sum_flag = torch.zeros((B, S), device=q.device, dtype=torch.uint8)
+            sum_flag[ib.long(), in_.long()] = 1
+        ref = cons["ref_attn"]
+        if ref is not None:
+            ref = ref.detach().float().contiguous()
+        if self.cross_attn_scale_factor.device != q.device:
+            self.cross_attn_scale_factor.data = self.cross_attn_scale_factor.data.to(q.device)
+        prob = None
+        if train:
+            o, subj_sum, sqdiff = ag.CrossConsumeFn.apply(q, k, v, self.cross_attn_scale_factor, H, sm_scale, col_flag, sum_flag, ref, 10.0)
+        else:
+            qm = ops.qmean(q) if col_flag is not None else None
+            o, subj_sum, sqdiff, prob = ops.attention_cross_consume(
+                q, k, v, H, sm_scale, sum_flag=sum_flag, ref_prob=ref, want_prob=cons["keep_attn"], col_flag=col_flag, qmean=qm,
+                ca_scale=self.cross_attn_scale_factor.detach().float().reshape(1))
+        extra = {}
+        if sum_flag is not None:
+            extra["attn_subj_sum"] = subj_sum
+        if ref is not None:
+            extra["attn_sqdiff"] = sqdiff
+        return o, prob, extra
 
     def reset_attn_cache_and_flags(self, capture_ca_activations, normalize_cross_attn, mix_attn_mats_in_batch, enable_lora):
         """dalc:184-190."""
@@ -265,7 +310,7 @@ class AttnProcessor_LoRA_Capture(nn.Module):
             hp = bool(self.capture_ca_activations or self.normalize_cross_attn)
             pdt = torch.float32 if hp else torch.bfloat16
             fast = (not hp) and all(lora(n) is None for n in ("q", "k", "v"))
-            q = q2 = k = v = prob = score = prob_subj = None
+            q = q2 = k = v = prob = score = prob_subj = consumed = None
             if fast:                                                                 # dalc:320-322: 3 launches in all
                 o = ops.cross_attention_fused(x2d, pk["wq"], pk["bq"], c2d, pk["wkv"], pk["bkv"], B, N, S, H, sm_scale)
             else:
@@ -291,9 +336,13 @@ class AttnProcessor_LoRA_Capture(nn.Module):
                 cap = bool(self.capture_ca_activations)
                 if self.cross_attn_scale_factor.device != x.device:     # processor left on the CPU by the caller
                     self.cross_attn_scale_factor.data = self.cross_attn_scale_factor.data.to(x.device)
-                o, prob, score, prob_subj = ops.attention_cross_capture(
-                    q, k, v, H, sm_scale, want_prob=cap, want_score=cap, col_flag=col_flag, qmean=qm,
-                    ca_scale=self.cross_attn_scale_factor.detach().float().reshape(1), mix=mix, subj_cols=subj_cols)
+                if cap and self.capture_consumers is not None:
+                    o, prob, consumed = self._consume(q, k, v, H, sm_scale, B, S, subj_indices, train=False)
+                    score = prob_subj = None
+                else:
+                    o, prob, score, prob_subj = ops.attention_cross_capture(
+                        q, k, v, H, sm_scale, want_prob=cap, want_score=cap, col_flag=col_flag, qmean=qm,
+                        ca_scale=self.cross_attn_scale_factor.detach().float().reshape(1), mix=mix, subj_cols=subj_cols)
             else:                                                                    # dalc:320-322
                 o = ops.attention(q, k, v, H, sm_scale)
                 prob = score = prob_subj = None
@@ -320,6 +369,8 @@ class AttnProcessor_LoRA_Capture(nn.Module):
                 attn, "residual_connection", False)) else hidden_out.float().permute(0, 2, 1).contiguous()
             if prob_subj is not None:
                 ca["attn_subj"] = prob_subj
+            if consumed:
+                ca.update(consumed)
         return hidden_out
 
     forward = __call__
@@ -390,7 +441,7 @@ class AttnProcessor_LoRA_Capture(nn.Module):
         is_cross = encoder_hidden_states is not None
         C = pk["wq"].shape[0]
         sm_scale = 1.0 / math.sqrt(C // H)
-        q = q2 = k = v = prob = score = prob_subj = None
+        q = q2 = k = v = prob = score = prob_subj = consumed = None
 
         if not is_cross:
             key_mask = img_mask_to_key_mask(img_mask, N) if img_mask is not None else None
@@ -424,8 +475,11 @@ class AttnProcessor_LoRA_Capture(nn.Module):
                 if self.cross_attn_scale_factor.device != x2d.device:
                     self.cross_attn_scale_factor.data = self.cross_attn_scale_factor.data.to(x2d.device)
                 cap = bool(self.capture_ca_activations)
-                o, prob, score, prob_subj = ag.CrossCaptureFn.apply(q, k, v, self.cross_attn_scale_factor, H, sm_scale, cap,
-                                                                    cap, col_flag, subj_cols, mix, 10.0)
+                if cap and self.capture_consumers is not None:
+                    o, prob, consumed = self._consume(q, k, v, H, sm_scale, B, S, subj_indices, train=True)
+                else:
+                    o, prob, score, prob_subj = ag.CrossCaptureFn.apply(q, k, v, self.cross_attn_scale_factor, H, sm_scale, cap,
+                                                                        cap, col_flag, subj_cols, mix, 10.0)
             elif k is None:
                 kv = ag.linear(c2d, pk, "wkv", "bkv").view(B, S, 2 * C)
                 o = ag.attention(q, kv, kv, (0, 0, C), C, C, H, sm_scale)
@@ -453,4 +507,6 @@ class AttnProcessor_LoRA_Capture(nn.Module):
                 attn, "residual_connection", False)) else hidden_out.float().permute(0, 2, 1).contiguous()
             if prob_subj is not None:
                 ca["attn_subj"] = prob_subj
+            if consumed:
+                ca.update(consumed)
         return hidden_out

@@ -194,6 +194,45 @@ class CrossCaptureFn(Function):
         return dq.to(q.dtype), dk, dv, dcap, None, None, None, None, None, None, None, None
 
 
+class CrossConsumeFn(Function):
+    """Capture with fused consumers: out, subj_sum [B,H,Lq] and sqdiff [B] = sum (prob - ref_prob)^2, all
+    differentiable w.r.t. q, k, v (and cross_attn_scale_factor under normalize) -- no [B,H,Lq,S] map in either direction."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, ca_param, heads, scale, col_flag, sum_flag, ref_prob, dca_mul):
+        qm = ops.qmean(q) if col_flag is not None else None
+        ca = ca_param.detach().float().reshape(1)
+        out, subj_sum, sqdiff, _ = ops.attention_cross_consume(q, k, v, heads, scale, sum_flag=sum_flag, ref_prob=ref_prob,
+                                                               col_flag=col_flag, qmean=qm, ca_scale=ca)
+        ctx.cfg = (heads, scale, dca_mul)
+        ctx.save_for_backward(q, k, v, ca, col_flag, qm, ca_param, sum_flag, ref_prob)
+        dev = q.device
+        if subj_sum is None:
+            subj_sum = torch.zeros((), device=dev)
+            ctx.mark_non_differentiable(subj_sum)
+        if sqdiff is None:
+            sqdiff = torch.zeros((), device=dev)
+            ctx.mark_non_differentiable(sqdiff)
+        return out, subj_sum, sqdiff
+
+    @staticmethod
+    def backward(ctx, dout, dsum, dsq):
+        q, k, v, ca, col_flag, qm, ca_param, sum_flag, ref_prob = ctx.saved_tensors
+        heads, scale, dca_mul = ctx.cfg
+        B, Lq, C = q.shape
+        if dout is None:
+            dout = torch.zeros((B, Lq, C), device=q.device, dtype=BF16)
+        g_subj = dsum.float().contiguous() if (dsum is not None and sum_flag is not None) else None
+        coef = None
+        if ref_prob is not None and dsq is not None:
+            coef = (2.0 * dsq.float().reshape(-1).expand(B)).contiguous()    # d/dP sum (P - R)^2 = 2 (P - R), times upstream, per instance
+        dq, dk, dv, dca = ops.attention_cross_consume_bwd(q, k, v, _b16(dout), heads, scale, sum_flag=sum_flag if g_subj is not None else None,
+                                                          g_subj=g_subj, ref_prob=ref_prob if coef is not None else None, mse_coef=coef,
+                                                          col_flag=col_flag, qmean=qm, ca_scale=ca, dca_mul=dca_mul, dkv_dtype=k.dtype)
+        dcap = dca.reshape(ca_param.shape).to(ca_param.dtype) if ctx.needs_input_grad[3] else None
+        return dq.to(q.dtype), dk, dv, dcap, None, None, None, None, None, None
+
+
 class ChanMajorFn(Function):
     """cached q / q2 / k / v / attn_out: 'b n c -> b c n' times a factor, fp32 (dalc:349-362)."""
 

@@ -44,6 +44,11 @@ struct CapBwdParams {
   float* dca_part;                  // [B * H * chunks]
   int B, H, Lq, S, tiles_per_cta;
   float scale;
+  // ---- implicit dprob terms of the fused capture consumers (the dense [B,H,Lq,S] gradient map is never materialised)
+  const uint8_t* sum_flag;          // [B, S]
+  const float* g_subj;              // [B, H, Lq]: dprob[b,h,r,c] += g_subj[b,h,r] * sum_flag[b,c]      (d subj_sum)
+  const float* ref_prob;            // [B, H, Lq, S]
+  const float* mse_coef;            // device [B]: dprob[b] += mse_coef[b] * (P - ref_prob)              (d sum (P - ref)^2 = 2 (P - ref))
 };
 
 // out[16 keys x D] = sum over the 64 queries of A^T B: A = [64 queries][CB_LDP] tile (P or dS, columns = keys),
@@ -142,6 +147,18 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_cross_capture_bwd_kernel(con
   const float ca_scale = p.ca_scale ? __ldg(p.ca_scale) : 1.f;
   const float sc = MIX ? 0.5f * p.scale : p.scale;       // (score_sc + score_mc) / 2, dalc:117
   float dc_local = 0.f;
+  static_assert(NT_S <= 16, "sum_bits holds two columns for each of at most 16 key tiles");
+  uint32_t sum_bits = 0;       // this thread's score columns that belong to the subject-column sum (fused consumers)
+  if (!MIX && p.g_subj) {
+#pragma unroll
+    for (int nt = 0; nt < NT_S; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = nt * 8 + 2 * t + e;
+        if (c < S && p.sum_flag[(long long)b0 * S + c]) sum_bits |= 1u << (2 * nt + e);
+      }
+    }
+  }
 
   for (int tile = tile_begin; tile < tile_end; ++tile) {
     const int m0 = tile * ATT_BM;
@@ -256,6 +273,30 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_cross_capture_bwd_kernel(con
       }
     }
     const int row_lo = m0 + warp * 16 + g;
+    if constexpr (!MIX) {
+      if (p.g_subj) {
+        const float* gs = p.g_subj + ((long long)b0 * p.H + h) * p.Lq;
+        const float g0 = row_lo < p.Lq ? __ldg(gs + row_lo) : 0.f, g1 = row_lo + 8 < p.Lq ? __ldg(gs + row_lo + 8) : 0.f;
+#pragma unroll
+        for (int nt = 0; nt < NT_S; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (sum_bits & (1u << (2 * nt + (e & 1)))) acc_dp[nt][e] += (e >> 1) ? g1 : g0;
+        }
+      }
+      if (p.ref_prob) {
+        const float coef = __ldg(p.mse_coef + b0);
+        const float* ref = p.ref_prob + (((long long)b0 * p.H + h) * p.Lq) * S;
+#pragma unroll
+        for (int nt = 0; nt < NT_S; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = nt * 8 + 2 * t + (e & 1), r = row_lo + (e >> 1) * 8;
+            if (c < S && r < p.Lq) acc_dp[nt][e] += coef * (acc_s[nt][e] - __ldg(ref + (long long)r * S + c));
+          }
+        }
+      }
+    }
     if (p.dprob) {
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
@@ -504,8 +545,12 @@ int attn_cross_capture_bwd(const void* q, int64_t q_sb, int64_t q_sn, const void
                            float scale, const uint8_t* col_flag, const float* qmean, const float* ca_scale, int mix, int in_dtype,
                            void* dq, int64_t dq_sb, int64_t dq_sn, void* dk, int64_t dk_sb, int64_t dk_sn, void* dv,
                            int64_t dv_sb, int64_t dv_sn, int dkv_dtype, float* dca, float dca_mul, float* dk_part,
-                           float* dv_part, float* dca_part, cudaStream_t stream) {
+                           float* dv_part, float* dca_part, cudaStream_t stream, const uint8_t* sum_flag, const float* g_subj,
+                           const float* ref_prob, const float* mse_coef) {
   AF_CHECK(q && k && v && dout && dq && dk && dv && dk_part && dv_part && dca_part, "attn_cross_capture_bwd: null pointer");
+  AF_CHECK(!(mix && (g_subj || ref_prob)), "attn_cross_capture_bwd: the fused consumers are not defined for mix_attn_mats_in_batch");
+  AF_CHECK(!g_subj == !sum_flag || !g_subj, "attn_cross_capture_bwd: g_subj needs sum_flag");
+  AF_CHECK(!ref_prob == !mse_coef, "attn_cross_capture_bwd: ref_prob and mse_coef go together");
   AF_CHECK(in_dtype == ADAFACE_BF16 || in_dtype == ADAFACE_F32, "attn_cross_capture_bwd: bad in_dtype %d", in_dtype);
   AF_CHECK(dkv_dtype == ADAFACE_BF16 || dkv_dtype == ADAFACE_F32, "attn_cross_capture_bwd: bad dkv_dtype %d", dkv_dtype);
   AF_CHECK(B > 0 && H > 0 && Lq > 0 && S > 0 && B <= 65535 && H <= 65535, "attn_cross_capture_bwd: bad problem size");
@@ -525,6 +570,7 @@ int attn_cross_capture_bwd(const void* q, int64_t q_sb, int64_t q_sn, const void
   p.dk_part = dk_part; p.dv_part = dv_part; p.dca_part = dca_part;
   p.B = (int)B; p.H = (int)H; p.Lq = (int)Lq; p.S = (int)S;
   p.scale = scale;
+  p.sum_flag = sum_flag; p.g_subj = g_subj; p.ref_prob = ref_prob; p.mse_coef = mse_coef;
   const int chunks = attn_cross_capture_bwd_chunks(B, H, Lq);
   const int tiles = (int)((Lq + ATT_BM - 1) / ATT_BM);
   p.tiles_per_cta = (tiles + chunks - 1) / chunks;

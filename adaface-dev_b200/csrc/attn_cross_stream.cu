@@ -42,6 +42,13 @@ struct CapParams {
   const float* ca_scale;   // device scalar (cross_attn_scale_factor) or null = 1
   int mix;
   int tiles_per_cta;
+  // ---- fused capture consumers: reductions of the probability map computed where the map is in registers,
+  //      so that the [B,H,Lq,S] fp32 map itself need not be written (prob / score may be NULL)
+  const uint8_t* sum_flag;   // [B, S]: columns summed into subj_sum (the instance's subject tokens)
+  float* subj_sum;           // [B, H, Lq] = sum over flagged columns of prob      (ldm/util.py:1862-1868, do_sum=True)
+  const float* ref_prob;     // [B, H, Lq, S]: probabilities of the reference instance (sc_rep, detached; ldm/util.py:2084-2089)
+  float* sq_part;            // [B, H, sq_slots, 4]: per-(CTA, warp) partial sums of (prob - ref_prob)^2; zero-initialised by the caller
+  int sq_slots;
 };
 
 // NTS = n8 key tiles held in registers (10 -> up to 80 keys, 16 -> up to 128); KROWS = NTS * 8 staged key rows.
@@ -60,7 +67,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_cross_stream_kernel(const Ca
   bf16* sQ = sV + NI * KROWS * LD;                               // [4 warps][NP][NI][16][LD]
   float* sColMean = reinterpret_cast<float*>(sQ + 4 * QSLAB);    // [KROWS]
   uint8_t* sFlag = reinterpret_cast<uint8_t*>(sColMean + KROWS); // [KROWS]
-  float* sStage = reinterpret_cast<float*>(sFlag + KROWS);       // [4 warps][16][S] fp32, only when maps are captured
+  uint8_t* sSumFlag = sFlag + KROWS;                             // [KROWS]
+  float* sStage = reinterpret_cast<float*>(sSumFlag + KROWS);    // [4 warps][16][S] fp32, only when maps are captured
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -111,6 +119,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_cross_stream_kernel(const Ca
     }
     sColMean[j] = cm;
     sFlag[j] = fl;
+    sSumFlag[j] = (!MIX && p.sum_flag && j < S && p.sum_flag[(long long)b0 * S + j]) ? 1 : 0;
   }
   __syncthreads();        // the last block-wide barrier: from here on every warp runs its own pipeline
 
@@ -128,6 +137,15 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_cross_stream_kernel(const Ca
     for (int e = 0; e < 2; ++e)
       if (sFlag[nt * 8 + 2 * t + e]) flag_bits |= 1u << (2 * nt + e);
   }
+
+  uint32_t sum_bits = 0;      // columns of this thread that belong to the subject-column sum
+#pragma unroll
+  for (int nt = 0; nt < NTS; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      if (sSumFlag[nt * 8 + 2 * t + e]) sum_bits |= 1u << (2 * nt + e);
+  }
+  float sq_acc = 0.f;         // running sum of (prob - ref_prob)^2 over this warp's rows of every tile of the CTA
 
   // ---- Q rows of one tile: global -> registers (prefetch) -> bf16 hi/lo slab
   uint4 qreg[NI][PER];
@@ -327,6 +345,42 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_cross_stream_kernel(const Ca
       for (int e = 0; e < 4; ++e) acc_s[nt][e] *= inv[e >> 1];
     }
     if (p.prob || p.prob_subj) stage_and_store(p.prob, true);
+    if constexpr (!MIX) {
+      // ---- fused consumers: the probabilities are in registers -- reduce them here instead of writing the map
+      if (p.subj_sum) {
+        float ss[2] = {0.f, 0.f};
+#pragma unroll
+        for (int nt = 0; nt < NTS; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (sum_bits & (1u << (2 * nt + (e & 1)))) ss[e >> 1] += acc_s[nt][e];
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], 1);
+          ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], 2);
+        }
+        if (t == 0) {
+          float* dst = p.subj_sum + ((long long)b0 * p.H + h) * p.Lq + row0;
+          if (g < nrows) dst[g] = ss[0];
+          if (g + 8 < nrows) dst[g + 8] = ss[1];
+        }
+      }
+      if (p.ref_prob) {
+        const float* ref = p.ref_prob + (((long long)b0 * p.H + h) * p.Lq + row0) * S;
+#pragma unroll
+        for (int nt = 0; nt < NTS; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = nt * 8 + 2 * t + (e & 1), r = g + (e >> 1) * 8;
+            if (c < S && r < nrows) {
+              const float df = acc_s[nt][e] - __ldg(ref + r * S + c);
+              sq_acc += df * df;
+            }
+          }
+        }
+      }
+    }
 
     // ---- O = P V per instance
 #pragma unroll
@@ -373,6 +427,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_cross_stream_kernel(const Ca
       }
     }
   }
+  if constexpr (!MIX) {
+    if (p.sq_part) {          // deterministic: one slot per (batch, head, chunk, warp), summed by the caller in a fixed order
+      sq_acc = warp_sum(sq_acc);
+      if (lane == 0 && chunk < p.sq_slots) p.sq_part[((((long long)b0 * p.H + h) * p.sq_slots) + chunk) * 4 + warp] = sq_acc;
+    }
+  }
 }
 
 template <int D, int NTS, bool MIX, bool F32IN>
@@ -380,7 +440,7 @@ static int launch_cs(CapParams& p, cudaStream_t stream) {
   using A = AttDims<D>;
   constexpr int NI = MIX ? 2 : 1, NP = F32IN ? 2 : 1, KROWS = NTS * 8;
   const bool maps = p.prob || p.score || p.prob_subj;
-  const int smem = ((NP + 1) * NI * KROWS + 4 * NP * NI * 16) * A::LD * 2 + KROWS * 4 + KROWS + (maps ? 4 * 16 * p.S * 4 : 0) + 16;
+  const int smem = ((NP + 1) * NI * KROWS + 4 * NP * NI * 16) * A::LD * 2 + KROWS * 4 + 2 * KROWS + (maps ? 4 * 16 * p.S * 4 : 0) + 16;
   AF_CHECK(smem <= 227 * 1024, "attn_cross_stream: %d bytes of shared memory exceed the SM", smem);
   static int configured_smem[AF_MAX_DEV] = {0}, ctas_per_sm[AF_MAX_DEV][2] = {{0, 0}};      // per device
   const int cfg_dev = af_device();
@@ -402,6 +462,7 @@ static int launch_cs(CapParams& p, cudaStream_t stream) {
   if (chunks < 1) chunks = 1;
   p.tiles_per_cta = (tiles + chunks - 1) / chunks;
   chunks = (tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  AF_CHECK(!p.sq_part || chunks <= p.sq_slots, "attn_cross_stream: sq_part has %d slots per (batch, head), %d needed", p.sq_slots, chunks);
   kern<<<dim3(chunks, p.H, nb), ATT_THREADS, smem, stream>>>(p);
   AF_CUDA(cudaGetLastError());
   ++g_launch_count;
@@ -425,8 +486,12 @@ int attn_cross_capture_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void
                            const void* v, int64_t v_sb, int64_t v_sn, void* o, int64_t o_sb, int64_t o_sn, int64_t B,
                            int64_t H, int64_t Lq, int64_t S, int64_t d, float scale, float* prob, float* score,
                            float* prob_subj, const int32_t* subj_cols, int64_t n_subj, const uint8_t* col_flag,
-                           const float* qmean, const float* ca_scale, int mix, int in_dtype, cudaStream_t stream) {
+                           const float* qmean, const float* ca_scale, int mix, int in_dtype, cudaStream_t stream,
+                           const uint8_t* sum_flag, float* subj_sum, const float* ref_prob, float* sq_part, int64_t sq_slots) {
   AF_CHECK(in_dtype == ADAFACE_BF16 || in_dtype == ADAFACE_F32, "attn_cross_capture_fwd: bad in_dtype %d", in_dtype);
+  AF_CHECK(!(mix && (subj_sum || ref_prob)), "attn_cross_capture_fwd: the fused consumers are not defined for mix_attn_mats_in_batch");
+  AF_CHECK(!subj_sum == !sum_flag, "attn_cross_capture_fwd: subj_sum and sum_flag go together");
+  AF_CHECK(!ref_prob == !sq_part && (!sq_part || sq_slots > 0), "attn_cross_capture_fwd: ref_prob, sq_part and sq_slots go together");
   const int64_t al = in_dtype == ADAFACE_F32 ? 4 : 8;
   if (check_view_cs("q", q, q_sb, q_sn, d, al) || check_view_cs("k", k, k_sb, k_sn, d, al) ||
       check_view_cs("v", v, v_sb, v_sn, d, al) || check_view_cs("o", o, o_sb, o_sn, d, 8))
@@ -447,6 +512,7 @@ int attn_cross_capture_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void
   p.prob = prob; p.score = score; p.prob_subj = prob_subj; p.subj_cols = subj_cols; p.n_subj = (int)n_subj;
   p.col_flag = col_flag; p.qmean = qmean; p.ca_scale = ca_scale; p.mix = mix;
   p.tiles_per_cta = 1;
+  p.sum_flag = sum_flag; p.subj_sum = subj_sum; p.ref_prob = ref_prob; p.sq_part = sq_part; p.sq_slots = (int)sq_slots;
   const bool f32 = in_dtype == ADAFACE_F32;
   if (mix) {
     switch (d) {

@@ -137,7 +137,8 @@ int attn_cross_capture_bwd_chunks(int64_t, int64_t, int64_t);
 int attn_cross_capture_bwd(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t, int64_t,
                            const void*, int64_t, int64_t, const float*, const float*, int64_t, int64_t, int64_t, int64_t,
                            int64_t, float, const uint8_t*, const float*, const float*, int, int, void*, int64_t, int64_t, void*,
-                           int64_t, int64_t, void*, int64_t, int64_t, int, float*, float, float*, float*, float*, cudaStream_t);
+                           int64_t, int64_t, void*, int64_t, int64_t, int, float*, float, float*, float*, float*, cudaStream_t,
+                           const uint8_t*, const float*, const float*, const float*);
 int transpose(const void*, int, int64_t, int64_t, void*, int, int64_t, int64_t, int64_t, int64_t, int64_t, float, const float*,
               const float*, cudaStream_t);
 int colsum(const void*, int, int64_t, const void*, int, int64_t, const float*, const float*, float*, int64_t, int64_t,
@@ -150,7 +151,8 @@ int sbg_head_bwd(const float*, const float*, const float*, const float*, const f
                  int64_t, float*, float*, float*, float*, float*, float*, float*, int64_t, int64_t, float, cudaStream_t);
 int attn_cross_capture_fwd(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t, int64_t,
                            void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, float, float*, float*,
-                           float*, const int32_t*, int64_t, const uint8_t*, const float*, const float*, int, int, cudaStream_t);
+                           float*, const int32_t*, int64_t, const uint8_t*, const float*, const float*, int, int, cudaStream_t,
+                           const uint8_t*, float*, const float*, float*, int64_t);
 int qmean(const void*, int, int64_t, int64_t, int64_t, int64_t, int64_t, float*, cudaStream_t);
 int capture_chan_major(const void*, int, int64_t, int64_t, int64_t, int64_t, int64_t, float, float*, cudaStream_t);
 int layernorm_fwd(const void*, int, int64_t, const float*, const float*, void*, int, int64_t, int64_t, int64_t, float,
@@ -230,7 +232,18 @@ int adaface_attn_cross_capture_fwd(const void* q, int64_t q_sb, int64_t q_sn, co
                                    const float* ca_scale, int mix, int in_dtype, void* stream) {
   return attn_cross_capture_fwd(q, q_sb, q_sn, k, k_sb, k_sn, v, v_sb, v_sn, o, o_sb, o_sn, B, H, Lq, S, d, scale, prob,
                                 score, prob_subj, subj_cols, n_subj, col_flag, qmean_, ca_scale, mix, in_dtype,
-                                (cudaStream_t)stream);
+                                (cudaStream_t)stream, nullptr, nullptr, nullptr, nullptr, 0);
+}
+
+int adaface_attn_cross_consume_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn,
+                                   const void* v, int64_t v_sb, int64_t v_sn, void* o, int64_t o_sb, int64_t o_sn, int64_t B,
+                                   int64_t H, int64_t Lq, int64_t S, int64_t d, float scale, float* prob,
+                                   const uint8_t* col_flag, const float* qmean_, const float* ca_scale, int in_dtype,
+                                   const uint8_t* sum_flag, float* subj_sum, const float* ref_prob, float* sq_part,
+                                   int64_t sq_slots, void* stream) {
+  return attn_cross_capture_fwd(q, q_sb, q_sn, k, k_sb, k_sn, v, v_sb, v_sn, o, o_sb, o_sn, B, H, Lq, S, d, scale, prob, nullptr,
+                                nullptr, nullptr, 0, col_flag, qmean_, ca_scale, 0, in_dtype, (cudaStream_t)stream, sum_flag,
+                                subj_sum, ref_prob, sq_part, sq_slots);
 }
 
 int adaface_qmean(const void* q, int q_dtype, int64_t q_sb, int64_t q_sn, int64_t B, int64_t Lq, int64_t C, float* out,
@@ -324,7 +337,22 @@ int adaface_attn_cross_capture_bwd(const void* q, int64_t q_sb, int64_t q_sn, co
                                    float* dv_part, float* dca_part, void* stream) {
   return attn_cross_capture_bwd(q, q_sb, q_sn, k, k_sb, k_sn, v, v_sb, v_sn, dout, do_sb, do_sn, dprob, dscore, B, H, Lq, S, d,
                                 scale, col_flag, qmean_, ca_scale, mix, in_dtype, dq, dq_sb, dq_sn, dk, dk_sb, dk_sn, dv, dv_sb,
-                                dv_sn, dkv_dtype, dca, dca_mul, dk_part, dv_part, dca_part, (cudaStream_t)stream);
+                                dv_sn, dkv_dtype, dca, dca_mul, dk_part, dv_part, dca_part, (cudaStream_t)stream, nullptr, nullptr,
+                                nullptr, nullptr);
+}
+
+int adaface_attn_cross_consume_bwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn,
+                                   const void* v, int64_t v_sb, int64_t v_sn, const void* dout, int64_t do_sb, int64_t do_sn,
+                                   const float* dprob, int64_t B, int64_t H, int64_t Lq, int64_t S, int64_t d, float scale,
+                                   const uint8_t* col_flag, const float* qmean_, const float* ca_scale, int in_dtype, void* dq,
+                                   int64_t dq_sb, int64_t dq_sn, void* dk, int64_t dk_sb, int64_t dk_sn, void* dv, int64_t dv_sb,
+                                   int64_t dv_sn, int dkv_dtype, float* dca, float dca_mul, float* dk_part, float* dv_part,
+                                   float* dca_part, const uint8_t* sum_flag, const float* g_subj, const float* ref_prob,
+                                   const float* mse_coef, void* stream) {
+  return attn_cross_capture_bwd(q, q_sb, q_sn, k, k_sb, k_sn, v, v_sb, v_sn, dout, do_sb, do_sn, dprob, nullptr, B, H, Lq, S, d,
+                                scale, col_flag, qmean_, ca_scale, 0, in_dtype, dq, dq_sb, dq_sn, dk, dk_sb, dk_sn, dv, dv_sb,
+                                dv_sn, dkv_dtype, dca, dca_mul, dk_part, dv_part, dca_part, (cudaStream_t)stream, sum_flag, g_subj,
+                                ref_prob, mse_coef);
 }
 
 int adaface_transpose(const void* src, int src_dtype, int64_t s_sb, int64_t s_ld, void* dst, int dst_dtype, int64_t d_sb,

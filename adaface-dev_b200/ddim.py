@@ -108,6 +108,11 @@ class DDIMSampler:
         T = self.ddpm_num_timesteps
         c = T // ddim_num_steps
         self.ddim_timesteps = np.asarray(list(range(0, T, c))) + 1                                 # util.py:48-57
+        if self.ddim_timesteps[-1] >= T:
+            # e.g. 3 steps of 1000: range(0, 1000, 333) + 1 ends at 1000.  The reference indexes alphas_cumprod[1000] there and dies
+            # with an IndexError (util.py:66); same condition, a message that says why
+            raise ValueError(f"ddim_num_steps={ddim_num_steps} does not divide the {T} training steps evenly enough: the last DDIM "
+                             f"timestep would be {int(self.ddim_timesteps[-1])} >= {T} (the reference fails at util.py:66)")
         ac = self.model.alphas_cumprod.detach().float().cpu()
         if ac.shape[0] != T:
             raise ValueError("alphas_cumprod have to be defined for each timestep")

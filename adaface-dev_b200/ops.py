@@ -218,6 +218,88 @@ def attention_cross_capture(q, k, v, heads, scale, *, want_prob=True, want_score
     return out, prob, score, prob_subj
 
 
+def _consume_checks(q, k, heads, col_flag, qmean_, sum_flag, ref_prob):
+    B, Lq, C = q.shape
+    S = k.shape[1]
+    if col_flag is not None:
+        _need(col_flag, "col_flag", torch.uint8)
+        _need(qmean_, "qmean", torch.float32)
+        if tuple(col_flag.shape) != (B, S) or tuple(qmean_.shape) != (B, C):
+            raise ValueError("attention_cross_consume: col_flag must be [B,S] and qmean [B,C]")
+    if sum_flag is not None:
+        _need(sum_flag, "sum_flag", torch.uint8)
+        if tuple(sum_flag.shape) != (B, S) or not sum_flag.is_contiguous():
+            raise ValueError("attention_cross_consume: sum_flag must be a contiguous uint8 [B,S] tensor")
+    if ref_prob is not None:
+        _need(ref_prob, "ref_prob", torch.float32)
+        if tuple(ref_prob.shape) != (B, heads, Lq, S) or not ref_prob.is_contiguous():
+            raise ValueError("attention_cross_consume: ref_prob must be a contiguous fp32 [B,H,Lq,S] tensor")
+
+
+def attention_cross_consume(q, k, v, heads, scale, *, sum_flag=None, ref_prob=None, want_prob=False, col_flag=None, qmean=None,
+                            ca_scale=None, out=None):
+    """Capture with fused consumers (adaface_attn_cross_consume_fwd): the slow SDPA of dalc:79-139 whose
+    probability map is reduced in registers instead of being written.  Returns (out [B,Lq,C] bf16, subj_sum [B,H,Lq] fp32 | None
+    = mass on the columns flagged in sum_flag [B,S], sqdiff [B] fp32 | None = sum_{h,i,j} (prob - ref_prob)^2, prob | None)."""
+    _view3(q, "q", q.dtype), _view3(k, "k", q.dtype), _view3(v, "v", q.dtype)
+    _consume_checks(q, k, heads, col_flag, qmean, sum_flag, ref_prob)
+    B, Lq, C = q.shape
+    S = k.shape[1]
+    dev = q.device
+    if out is None:
+        out = torch.empty((B, Lq, C), device=dev, dtype=torch.bfloat16)
+    prob = torch.empty((B, heads, Lq, S), device=dev, dtype=torch.float32) if want_prob else None
+    subj_sum = torch.empty((B, heads, Lq), device=dev, dtype=torch.float32) if sum_flag is not None else None
+    slots = (Lq + 63) // 64
+    sq_part = torch.zeros((B, heads * slots * 4), device=dev, dtype=torch.float32) if ref_prob is not None else None
+    _lib.call("adaface_attn_cross_consume_fwd", _ptr(q), q.stride(0), q.stride(1), _ptr(k), k.stride(0), k.stride(1), _ptr(v),
+              v.stride(0), v.stride(1), _ptr(out), out.stride(0), out.stride(1), B, heads, Lq, S, C // heads, float(scale), _ptr(prob),
+              _ptr(col_flag), _ptr(qmean), _ptr(ca_scale), _dt(q), _ptr(sum_flag), _ptr(subj_sum), _ptr(ref_prob), _ptr(sq_part),
+              slots, _stream())
+    sqdiff = sq_part.sum(dim=1) if sq_part is not None else None          # fixed-order reduction of the per-CTA partials
+    return out, subj_sum, sqdiff, prob
+
+
+def attention_cross_consume_bwd(q, k, v, dout, heads, scale, *, sum_flag=None, g_subj=None, ref_prob=None, mse_coef=None, dprob=None,
+                                col_flag=None, qmean=None, ca_scale=None, dca_mul=1.0, dkv_dtype=torch.float32):
+    """Backward of attention_cross_consume (adaface_attn_cross_consume_bwd): the map's gradient is implicit --
+    g_subj [B,H,Lq] on the flagged columns + mse_coef (device scalar) * (P - ref_prob) (+ an optional dense dprob).
+    Returns (dq bf16 [B,Lq,C], dk, dv [B,S,C] of dkv_dtype, dca fp32 [1])."""
+    _view3(q, "q", q.dtype), _view3(k, "k", q.dtype), _view3(v, "v", q.dtype), _view3(dout, "dout")
+    _consume_checks(q, k, heads, col_flag, qmean, sum_flag, ref_prob)
+    B, Lq, C = q.shape
+    S = k.shape[1]
+    d = C // heads
+    dev = q.device
+    if g_subj is not None:
+        _need(g_subj, "g_subj", torch.float32)
+        if tuple(g_subj.shape) != (B, heads, Lq) or not g_subj.is_contiguous() or sum_flag is None:
+            raise ValueError("attention_cross_consume_bwd: g_subj must be a contiguous fp32 [B,H,Lq] tensor and needs sum_flag")
+    if (ref_prob is None) != (mse_coef is None):
+        raise ValueError("attention_cross_consume_bwd: ref_prob and mse_coef go together")
+    if mse_coef is not None:
+        _need(mse_coef, "mse_coef", torch.float32)
+        if mse_coef.numel() != B or not mse_coef.is_contiguous():
+            raise ValueError("attention_cross_consume_bwd: mse_coef must be a contiguous fp32 [B] tensor")
+    if dprob is not None:
+        _need(dprob, "dprob", torch.float32)
+        if tuple(dprob.shape) != (B, heads, Lq, S) or not dprob.is_contiguous():
+            raise ValueError("attention_cross_consume_bwd: dprob must be a contiguous fp32 [B,H,Lq,S] tensor")
+    chunks = _lib.cross_capture_bwd_chunks(B, heads, Lq)
+    dq = torch.empty((B, Lq, C), device=dev, dtype=torch.bfloat16)
+    dk = torch.empty((B, S, C), device=dev, dtype=dkv_dtype)
+    dv = torch.empty((B, S, C), device=dev, dtype=dkv_dtype)
+    dca = torch.zeros(1, device=dev, dtype=torch.float32)
+    part = torch.empty((2, B * heads * chunks * S * d), device=dev, dtype=torch.float32)
+    dca_part = torch.empty(B * heads * chunks, device=dev, dtype=torch.float32)
+    _lib.call("adaface_attn_cross_consume_bwd", _ptr(q), q.stride(0), q.stride(1), _ptr(k), k.stride(0), k.stride(1), _ptr(v),
+              v.stride(0), v.stride(1), _ptr(dout), dout.stride(0), dout.stride(1), _ptr(dprob), B, heads, Lq, S, d, float(scale),
+              _ptr(col_flag), _ptr(qmean), _ptr(ca_scale), _dt(q), _ptr(dq), dq.stride(0), dq.stride(1), _ptr(dk), dk.stride(0),
+              dk.stride(1), _ptr(dv), dv.stride(0), dv.stride(1), _dt(dk), _ptr(dca), float(dca_mul), _ptr(part[0]), _ptr(part[1]),
+              _ptr(dca_part), _ptr(sum_flag), _ptr(g_subj), _ptr(ref_prob), _ptr(mse_coef), _stream())
+    return dq, dk, dv, dca
+
+
 def qmean(q):
     """Mean over the queries: q [B, L, C] bf16|fp32 view -> [B, C] fp32 (adaface_qmean)."""
     _view3(q, "q", q.dtype)

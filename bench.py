@@ -342,6 +342,21 @@ def secondary_measurements(torch, a, dev, flush, pk, unet):
             us = _time_us(torch, flush, lambda: ops.attention_cross_capture(qf, kf, vf, H, d ** -0.5, **kw))
             out[nm] = {"kernel": "attn_cross_stream_kernel<40,fp32 hi/lo>", "shape": f"B={B} N={N} C={C} S={S}", "us": us,
                        "algorithmic_bytes": by, "achieved_gbs": by / us / 1e3, "peak_gbs": hbm, "frac": by / us / 1e3 / hbm}
+        # -- the same capture with FUSED CONSUMERS -- the [B,H,N,S] map is reduced in registers, not written.
+        #    "subj_sum": mass on the 16 subject columns -> [B,H,N] fp32; "sqdiff": sum (prob - ref)^2 against a resident reference map
+        sflag = torch.zeros(B, S, device=dev, dtype=torch.uint8)
+        sflag[:, 4:20] = 1
+        refp = torch.softmax(torch.randn(B, H, N, S, device=dev), dim=-1)
+        for nm, kw, by in (("capture_fused_subj_sum", dict(sum_flag=sflag), core + B * H * N * 4),
+                           ("capture_fused_sqdiff", dict(ref_prob=refp), core + maps),
+                           ("capture_fused_both", dict(sum_flag=sflag, ref_prob=refp), core + maps + B * H * N * 4)):
+            us = _time_us(torch, flush, lambda: ops.attention_cross_consume(qf, kf, vf, H, d ** -0.5, **kw))
+            out[nm] = {"kernel": "attn_cross_stream_kernel<40,fp32 hi/lo> + fused consumers", "shape": f"B={B} N={N} C={C} S={S}", "us": us,
+                       "algorithmic_bytes": by, "achieved_gbs": by / us / 1e3, "peak_gbs": hbm, "frac": by / us / 1e3 / hbm,
+                       "bytes_not_written_vs_capture_prob": maps if "ref_prob" not in kw else 0,
+                       "note": "same job as capture_prob + a separate reduction pass over the 20 MB map; compare `us`, the fraction falls "
+                               "because the bytes do"}
+        del refp
         # -- BASELINE config 2: ArcFace 512-d ID embedding -> 16 ada prompt tokens, batch 64, random init:
         #    Arc2Face ID -> image-prompt encoder (12 CLIP layers) + SubjBasisGenerator (12 layers, K/V multiplier 1)
         gen = a.SubjBasisGenerator().to(dev).eval()

