@@ -352,6 +352,58 @@ class Conv3x3Fn(Function):
         return dx, None, None, None, None, None, None, None, dres, None
 
 
+class ConvLoraFn(Function):
+    """peft lora.Conv2d with DoRA in eval form on a frozen 3x3 / 1x1 base convolution (dalc:541-591; SURVEY 8a A4, conv form):
+        y = colscale o (conv(x, W) + s conv1x1(conv(x, A), B)) + bias,   colscale = m / ||W + s B.A|| (detached, as in peft)
+    with A / B / magnitude trainable.  Forward = the implicit-GEMM kernel twice (T = conv(x, A), then the base convolution with
+    the rank-r tail in the same TMEM tile).  Backward: dZ = dY o colscale; dT = dZ (sB); dX = conv(dZ, W') + conv(dT, A') on the
+    same kernel over flipped / transposed weights; dB = s dZ^T T and dA = dT^T im2col(x) on the K-major projection GEMM;
+    d magnitude as for the linear adapter."""
+
+    @staticmethod
+    def forward(ctx, x, lora, A, B, m, hw):
+        wp, ap, bs, cs, bias = lora.pack()
+        b, n, _ = x.shape
+        if lora.is_3x3:
+            t = ops.conv3x3(x, ap, hw).view(b * n, -1)
+            y = ops.conv3x3(x, wp, hw, bias=bias, t=t, bs=bs, colscale=cs)
+        else:
+            t = ops.proj(x.view(b * n, -1), ap)
+            y = ops.proj(x.view(b * n, -1), wp, t=t, bs=bs, colscale=cs, bias=bias).view(b, n, -1)
+        ctx.lora, ctx.hw, ctx.bias = lora, hw, bias
+        ctx.save_for_backward(x, t, y, bs, cs, m)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, t, y, bs, cs, m = ctx.saved_tensors
+        lora, hw = ctx.lora, ctx.hw
+        b, n, cin = x.shape
+        dy16 = _b16c(dy)
+        dy2d = dy16.view(b * n, -1)
+        dt = ops.proj(dy2d, ops.transpose(bs, rowscale=cs))                                        # [P, r] = dZ (sB)
+        W, A = lora.base_layer.weight, lora.lora_A[lora.adapter].weight
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if lora.is_3x3:
+                # conv(dZ, W') with dZ = dY o colscale: the column scale is folded into W's output-channel axis before packing
+                dx = ops.conv3x3(dy16, ops.pack_conv3x3_weight_dx(W.detach().float() * cs.view(-1, 1, 1, 1)), hw)
+                dx = ops.conv3x3(dt.view(b, n, -1), ops.pack_conv3x3_weight_dx(A), hw, residual=dx)
+            else:
+                w16 = W.detach().flatten(1).to(BF16)
+                dx = ops.proj(dy2d, ops.transpose(w16, rowscale=cs), t=dt, bs=ops.transpose(A.detach().flatten(1).to(BF16))).view(b, n, cin)
+        dzt = ops.transpose(dy2d, colscale=cs, alpha=float(lora.scaling), pad_to=8)               # [cout, Pp] = s dZ^T
+        dB = ops.proj(dzt, ops.transpose(t, pad_to=8), out_dtype=torch.float32)                   # [cout, r]
+        dtt = ops.transpose(dt, pad_to=8)                                                          # [r, Pp]
+        if lora.is_3x3:
+            col = ops.im2col3x3_tokens(x, hw)                                                      # [P, 9 Kc]
+            dA = ops.unpack_conv3x3_weight(ops.proj(dtt, ops.transpose(col, pad_to=8), out_dtype=torch.float32), cin)
+        else:
+            dA = ops.proj(dtt, ops.transpose(x.view(b * n, cin), pad_to=8), out_dtype=torch.float32).view_as(A)
+        dm = ops.colsum(dy2d, b=y.view(b * n, -1), bias=ctx.bias, colmul=m.detach().float().reciprocal().contiguous())
+        return dx, None, dA.view_as(A).to(A.dtype), dB.view(lora.lora_B[lora.adapter].weight.shape).to(A.dtype), dm.to(m.dtype), None
+
+
 class Upsample2xFn(Function):
     @staticmethod
     def forward(ctx, x, hw):

@@ -168,6 +168,7 @@ int groupnorm_act_tokens_fwd(const void*, const float*, const float*, int64_t, i
                              float*, void*, cudaStream_t);
 int64_t groupnorm_act_tokens_ws_floats(int64_t, int64_t, int64_t, int64_t);
 int silu_fwd(const void*, int, void*, int64_t, cudaStream_t);
+int im2col3x3_tokens(const void*, void*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
 int ddim_cfg_step(const float*, int64_t, int64_t, int, const float*, const float*, const float*, float*, float*, float*, cudaStream_t);
 int upsample2x_tokens(const void*, void*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
 int timestep_embedding(const float*, int64_t, int64_t, float, void*, cudaStream_t);
@@ -291,6 +292,9 @@ int64_t adaface_groupnorm_act_tokens_ws_floats(int64_t B, int64_t HW, int64_t C,
 int adaface_ddim_cfg_step(const float* eps, int64_t n_images, int64_t n_per_image, int has_uncond, const float* x, const float* coef,
                           const float* noise, float* x_prev, float* x_dup, float* pred_x0, void* stream) {
   return ddim_cfg_step(eps, n_images, n_per_image, has_uncond, x, coef, noise, x_prev, x_dup, pred_x0, (cudaStream_t)stream);
+}
+int adaface_im2col3x3_tokens(const void* x, void* col, int64_t B, int64_t H, int64_t W, int64_t C, void* stream) {
+  return im2col3x3_tokens(x, col, B, H, W, C, (cudaStream_t)stream);
 }
 int adaface_silu_fwd(const void* x, int x_dtype, void* y, int64_t n, void* stream) { return silu_fwd(x, x_dtype, y, n, (cudaStream_t)stream); }
 int adaface_upsample2x_tokens(const void* x, void* y, int64_t B, int64_t H, int64_t W, int64_t C, void* stream) {

@@ -61,4 +61,38 @@ int ddim_cfg_step(const float* eps, int64_t n_images, int64_t n_per_image, int h
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// im2col of an NHWC activation for the WEIGHT gradient of a 3x3 convolution adapter (conv-LoRA A matrix, dalc:541-591):
+//   col[(b, y, x), tap * Kc + c] = X[b, y + ky - 1, x + kx - 1, c]   (zero outside the image / for c >= C),  tap = ky * 3 + kx
+// -- the K index of ops.pack_conv3x3_weight, so dA_packed [r, 9 Kc] = dT^T col is one K-major GEMM on the projection kernel.
+// Training only, three adapters per U-Net pass at B = 1 (47 MB of col at level A): a plain 16-byte-vector copy kernel.
+__global__ void __launch_bounds__(256) im2col3x3_tokens_kernel(const uint4* __restrict__ x, uint4* __restrict__ col, int H, int W, int vecC,
+                                                               int vecK, long long n_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const int v = (int)(i % vecK);
+  long long r = i / vecK;
+  const int tap = (int)(r % 9);
+  r /= 9;
+  const int px = (int)(r % W);
+  r /= W;
+  const int py = (int)(r % H);
+  const long long b = r / H;
+  const int sy = py + tap / 3 - 1, sx = px + tap % 3 - 1;
+  uint4 val = make_uint4(0, 0, 0, 0);
+  if (v < vecC && sy >= 0 && sy < H && sx >= 0 && sx < W) val = x[((b * H + sy) * W + sx) * vecC + v];
+  col[i] = val;
+}
+
+int im2col3x3_tokens(const void* x, void* col, int64_t B, int64_t H, int64_t W, int64_t C, cudaStream_t stream) {
+  AF_CHECK(x && col && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "im2col3x3_tokens: null pointer / empty / C not a multiple of 8");
+  const int64_t kc = (C + 63) / 64 * 64;
+  const long long n_out = (long long)B * H * W * 9 * (kc / 8);
+  im2col3x3_tokens_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, stream>>>((const uint4*)x, (uint4*)col, (int)H, (int)W, (int)(C / 8),
+                                                                              (int)(kc / 8), n_out);
+  AF_CUDA(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
 }  // namespace adaface

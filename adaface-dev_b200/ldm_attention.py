@@ -31,6 +31,14 @@ def _f32(t):
     return None if t is None else t.detach().float().contiguous()
 
 
+def _processor_key_mask(mask, B):
+    """The diffusers-processor rule for the same mask (dalc:254-273, ``CrossAttention.mask_mode = 'processor'``): if ANY instance's
+    mask is all zero the mask is dropped for the whole batch; no uniform-attention instances."""
+    m = mask.reshape(B, -1) != 0
+    drop = (m.sum(dim=1) == 0).any()
+    return (m | drop).to(torch.uint8).contiguous(), None
+
+
 def _ldm_key_mask(mask, B):
     """attention.py:185-194 fills masked scores with ``-finfo.max`` (not -inf): every key of an instance whose mask is ALL zero
     gets the same score, so that instance attends uniformly to all keys (out = mean of V) -- realistic when the nearest resize of
@@ -63,6 +71,19 @@ class CrossAttention(nn.Module):
         self.save_cross_attn_vars = False
         self.cached_activations = None
         self._pack_key, self._pack = None, None
+        # Optional AttnProcessor_LoRA_Capture (the diffusers surface of the same operator) installed by
+        # unet_wrapper.set_up_attn_processors on the captured layers: the block then routes this module through it
+        # (LoRA / normalize / capture with the processor's keys and C^-1/4 factor).  ``processor_kwargs`` = the per-call
+        # cross_attention_kwargs ({'img_mask', 'subj_indices'}, ddpm.py:4227-4229).
+        self.processor = None
+        self.processor_kwargs = None
+        self.mask_mode = "ldm"            # 'ldm': attention.py:185-194 (-finfo.max fill); 'processor': dalc:254-273 (drop if any empty)
+
+    def run_processor(self, x16, context):
+        kw = {k: v for k, v in (self.processor_kwargs or {}).items() if k in ("img_mask", "subj_indices")}
+        if context is not None:
+            kw.pop("img_mask", None)                 # the mask only reaches self-attention (dalc:254: `if img_mask is not None and not is_cross`)
+        return self.processor(self, x16, encoder_hidden_states=context, **kw)
 
     def _weights(self):
         ws = (self.to_q.weight, self.to_k.weight, self.to_v.weight, self.to_out[0].weight, self.to_out[0].bias)
@@ -87,7 +108,7 @@ class CrossAttention(nn.Module):
         C = pk["wq"].shape[0]
         x2d = x16.reshape(B * N, Cq)
         q = prob = score = None
-        key_mask, empty = (None, None) if mask is None else _ldm_key_mask(mask, B)
+        key_mask, empty = (None, None) if mask is None else (_processor_key_mask if self.mask_mode == "processor" else _ldm_key_mask)(mask, B)
         if context is None:
             if self.save_cross_attn_vars:
                 raise NotImplementedError("save_cross_attn_vars is only set on cross-attention layers (attn2)")
@@ -130,7 +151,7 @@ class CrossAttention(nn.Module):
         C = pk["wq"].shape[0]
         x2d = x16.view(B * N, Cq)
         prob = score = None
-        key_mask, empty = (None, None) if mask is None else _ldm_key_mask(mask, B)       # attention.py:185-194
+        key_mask, empty = (None, None) if mask is None else (_processor_key_mask if self.mask_mode == "processor" else _ldm_key_mask)(mask, B)       # attention.py:185-194
         if context is None:
             if self.save_cross_attn_vars:
                 raise NotImplementedError("save_cross_attn_vars is only set on cross-attention layers (attn2)")
@@ -241,14 +262,18 @@ class BasicTransformerBlock(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("adaface_b200 BasicTransformerBlock runs on CUDA only (no CPU fallback)")
         B, N, C = x.shape
-        if torch.is_grad_enabled() and (x.requires_grad or (context is not None and context.requires_grad)):
+        proc = self.attn2.processor
+        if torch.is_grad_enabled() and (x.requires_grad or (context is not None and context.requires_grad)
+                                        or (proc is not None and proc._has_trainable())):
             return self._forward_train(x, context, mask)
         x0 = x.to(torch.bfloat16).contiguous()
         capture = self.attn2.save_cross_attn_vars
         h = self._ln(x0.view(B * N, C), self.norm1).view(B, N, C)
         x1 = self.attn1._attend(h, None, mask, residual=x0)
         h = self._ln(x1.view(B * N, C), self.norm2).view(B, N, C)
-        if capture:      # cached attn_out must be the bare attention output (attention.py:220)
+        if self.attn2.processor is not None:
+            x2 = self.attn2.run_processor(h, context) + x1
+        elif capture:      # cached attn_out must be the bare attention output (attention.py:220)
             x2 = self.attn2._attend(h, context, None) + x1
         else:
             x2 = self.attn2._attend(h, context, None, residual=x1)
@@ -267,7 +292,9 @@ class BasicTransformerBlock(nn.Module):
         capture = self.attn2.save_cross_attn_vars
         x1 = self.attn1._attend_train(ln(x0, self.norm1).view(B, N, C), None, mask, residual=x0).view(B * N, C)
         h = ln(x1, self.norm2).view(B, N, C)
-        if capture:
+        if self.attn2.processor is not None:
+            x2 = (self.attn2.run_processor(h, context) + x1.view(B, N, C)).view(B * N, C)
+        elif capture:
             x2 = (self.attn2._attend_train(h, context, None) + x1.view(B, N, C)).view(B * N, C)
         else:
             x2 = self.attn2._attend_train(h, context, None, residual=x1).view(B * N, C)
@@ -323,7 +350,7 @@ class SpatialTransformer(nn.Module):
             block.attn2.infeat_size = (h, w)
             mask2 = F.interpolate(mask, size=(h, w), mode="nearest") if mask is not None else None
             t = block(t, context=context, mask=mask2)
-        if train:
+        if train or ag.needs_grad(t):                  # (a trainable adapter inside a block also starts the autograd graph)
             return ag.linear(t.reshape(b * n, -1), pk, "w_out", "b_out", residual=t_in.view(b * n, c)).view(b, n, c)
         return ops.proj(t.reshape(b * n, -1), pk["w_out"], bias=pk["b_out"], residual=t_in.view(b * n, c)).view(b, n, c)   # :303-304
 

@@ -20,6 +20,7 @@ import torch.nn as nn
 
 from . import ops
 from . import autograd as ag
+from .attn_processor import gen_gradient_scaler
 from .ldm_attention import SpatialTransformer, _bf16, _f32, _ver
 from .ldm_unet_blocks import ResBlock, Upsample, Downsample, _to_nchw
 
@@ -117,6 +118,14 @@ class UNetModel(nn.Module):
                  else self.output_blocks[layer_idx - n_in - 1])
         return block[1].transformer_blocks[0].attn2
 
+    def _processor_modules(self):
+        out = []
+        for m in self.modules():
+            if isinstance(m, SpatialTransformer):
+                for blk in m.transformer_blocks:
+                    out += [ca for ca in (blk.attn1, blk.attn2) if ca.processor is not None]
+        return out
+
     def _run(self, block, h, hw, emb, emb_act, context, mask):
         for layer in block:
             if isinstance(layer, ResBlock):
@@ -151,15 +160,27 @@ class UNetModel(nn.Module):
         mask = extra_info.get("img_mask", None) if extra_info is not None else None
         captured = self.captured_layer_indices if capture else ()
         for li in captured:
-            self._cross_attn(li).save_cross_attn_vars = True
+            if self._cross_attn(li).processor is None:
+                self._cross_attn(li).save_cross_attn_vars = True
+        # modules routed through an installed AttnProcessor_LoRA_Capture (unet_wrapper.set_up_attn_processors) get this call's
+        # cross_attention_kwargs (ddpm.py:4227-4229)
+        subj_indices = extra_info.get("subj_indices", None) if extra_info is not None else None
+        for ca in self._processor_modules():
+            ca.processor_kwargs = {"img_mask": mask, "subj_indices": subj_indices}
+        # A7 (dalc:382-394): gradient scale on the skip tensors entering diffusers up_blocks[1:] = output_blocks[num_res_blocks + 1:]
+        gradscale = float(extra_info.get("res_hidden_states_gradscale", 1)) if extra_info is not None else 1.0
+        res_grad_scaler = gen_gradient_scaler(gradscale)
         acts = {}
 
         def grab(li, h, hw_):
             if li in captured:
                 ca = self._cross_attn(li)
-                acts[li] = ca.cached_activations
-                acts[li]["outfeat"] = _to_nchw(h, hw_, x.dtype)
-                ca.cached_activations = None
+                if ca.processor is not None:               # diffusers surface: the processor's cache (q, q2, k, v, attn, ...; dalc:344-362)
+                    acts[li] = dict(ca.processor.cached_activations)
+                else:
+                    acts[li] = ca.cached_activations
+                    ca.cached_activations = None
+                acts[li]["outfeat"] = _to_nchw(h, hw_, x.dtype)                   # dalc:438-440 / openaimodel.py:933
 
         try:
             t_emb = ops.timestep_embedding(timesteps, self.model_channels)                                          # :839
@@ -178,9 +199,12 @@ class UNetModel(nn.Module):
             h, hw = self._run(self.middle_block, h, hw, emb, emb_act, context, mask)
             grab(layer_idx, h, hw)
             layer_idx += 1
-            for block in self.output_blocks:
+            for bi, block in enumerate(self.output_blocks):
                 hw_in = hw
-                h = torch.cat([h, hs.pop()], dim=2)                                                                # :925
+                skip = hs.pop()
+                if bi >= self.num_res_blocks + 1 and gradscale != 1.0:      # diffusers up_blocks[1:]
+                    skip = res_grad_scaler(skip)
+                h = torch.cat([h, skip], dim=2)                                                                    # :925
                 h, hw = self._run(block, h, hw_in, emb, emb_act, context, mask)
                 if layer_idx in captured:
                     # the captured feature map is the block's output before any trailing Upsample only when there is none:
@@ -191,8 +215,11 @@ class UNetModel(nn.Module):
             for li in captured:
                 self._cross_attn(li).save_cross_attn_vars = False
         if capture:                                                                                                 # :937-941
-            extra_info["ca_layers_activations"] = {key: {li: acts[li][key] for li in acts}
-                                                   for key in ("outfeat", "attn", "attnscore", "q", "attn_out")}
+            keys = ("outfeat", "attn", "attnscore", "q", "attn_out")
+            if any(self._cross_attn(li).processor is not None for li in captured):
+                keys = ("outfeat", "attn", "attnscore", "q", "q2", "k", "v", "attn_out", "attn_subj", "attn_subj_sum", "attn_sqdiff")
+            extra_info["ca_layers_activations"] = {key: {li: acts[li][key] for li in acts if acts[li].get(key) is not None}
+                                                   for key in keys}
         gn = self.out[0]
         h = ag.groupnorm_act(h, pk["gn_w"], pk["gn_b"], gn.num_groups, gn.eps, True)                                 # :960
         o = ag.conv3x3(h, pk, "w_out", self.out[2].weight, hw, bias=pk["b_out"], out_dtype=torch.float32)

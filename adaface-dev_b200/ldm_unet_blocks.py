@@ -13,8 +13,8 @@ activation tiles are shifted TMA boxes (zero padding = TMA out-of-bounds fill; a
 one pass over the tokens, the time-embedding term rides in the first convolution's epilogue as a per-image bias and the
 skip connection in the second one's as the residual.  ``forward`` keeps the reference's NCHW signature (one transpose
 in, one out); ``forward_tokens`` is the NHWC-resident entry.  Training: ``forward_tokens`` is differentiable w.r.t. its token
-input (autograd.py: GroupNormActFn / Conv3x3Fn / Upsample2xFn; the weights are the frozen U-Net's and get no gradient); the
-conv-LoRA adapter's own training path is not built.  CUDA only, no fallback.
+input (autograd.py: GroupNormActFn / Conv3x3Fn / Upsample2xFn; the weights are the frozen U-Net's and get no gradient; the conv-LoRA
+adapters -- ResBlock.conv_loras, LoraDoraConv2d -- train through ConvLoraFn).  CUDA only, no fallback.
 """
 import torch
 import torch.nn as nn
@@ -67,6 +67,10 @@ class ResBlock(nn.Module):
         else:
             self.skip_connection = nn.Conv2d(channels, self.out_channels, 1)
         self._pack_key, self._pack = None, None
+        # conv-LoRA adapters by diffusers name ('conv1', 'conv2', 'conv_shortcut'), installed by set_up_ffn_loras
+        # (dalc:541-591: up_blocks.3.resnets.[12].conv*); consulted only while ``ffn_lora_on`` (set_lora_and_capture_flags)
+        self.conv_loras = nn.ModuleDict()
+        self.ffn_lora_on = False
 
     def _weights(self):
         gn1, conv1, lin, gn2, conv2 = self.in_layers[0], self.in_layers[2], self.emb_layers[1], self.out_layers[0], self.out_layers[3]
@@ -99,16 +103,24 @@ class ResBlock(nn.Module):
         if emb_act is None:
             emb_act = ops.silu(emb.contiguous())
         emb_out = ops.proj(emb_act, pk["w_emb"], bias=pk["b_emb"], out_dtype=torch.float32)                           # :248
-        h = ag.conv3x3(h, pk, "w1", conv1.weight, hw, bias=pk["b1"], rowbias=emb_out)                                 # :247 + :257
+        lo = self.conv_loras if (self.ffn_lora_on and len(self.conv_loras)) else {}
+        if "conv1" in lo:
+            h = lo["conv1"].forward_tokens(h, hw, rowbias=emb_out)
+        else:
+            h = ag.conv3x3(h, pk, "w1", conv1.weight, hw, bias=pk["b1"], rowbias=emb_out)                             # :247 + :257
         h = ag.groupnorm_act(h, pk["gn2_w"], pk["gn2_b"], gn2.num_groups, gn2.eps, True)                              # :258
         if "w_skip" not in pk:
             skip = t
+        elif "conv_shortcut" in lo:
+            skip = lo["conv_shortcut"].forward_tokens(t, hw)
         elif self.use_conv:
             skip = ag.conv3x3(t, pk, "w_skip", self.skip_connection.weight, hw, bias=pk["b_skip"])
         elif ag.needs_grad(t):
             skip = ag.linear(t.view(b * hw[0] * hw[1], -1), pk, "w_skip", "b_skip").view(b, hw[0] * hw[1], -1)
         else:
             skip = ops.proj(t.view(b * hw[0] * hw[1], -1), pk["w_skip"], bias=pk["b_skip"]).view(b, hw[0] * hw[1], -1)
+        if "conv2" in lo:
+            return lo["conv2"].forward_tokens(h, hw, residual=skip)
         return ag.conv3x3(h, pk, "w2", conv2.weight, hw, bias=pk["b2"], residual=skip)                                # :258-260
 
     def forward(self, x, emb):
@@ -182,7 +194,8 @@ class LoraDoraConv2d(nn.Module):
     magnitude = ||W|| per output channel (identity adapter).  Eval-mode arithmetic (convolution form):
         y = bias + m / ||W + s B.A||_(cin,kh,kw) * (conv(x, W) + s conv1x1(conv(x, A), B))
     runs as two launches of the implicit-GEMM kernel: T = conv(x, A) (Cout = r), then the base convolution with the rank-r
-    tail T (sB)^T accumulated into the same TMEM tile and the DoRA column scale + bias in its epilogue.  Forward only."""
+    tail T (sB)^T accumulated into the same TMEM tile and the DoRA column scale + bias in its epilogue.  Training: ConvLoraFn
+    (autograd.py) pairs it with dX, dA (through an im2col of x), dB and d magnitude."""
 
     def __init__(self, base_layer, adapter_name="default", r=192, lora_alpha=16, use_dora=True, lora_dropout=0.1):
         super().__init__()
@@ -203,6 +216,26 @@ class LoraDoraConv2d(nn.Module):
         self._pack_key, self._pack = None, None
         self.enable_adapters = lambda *a, **k_: None
         self.set_adapter = lambda *a, **k_: None
+
+    def add_adapter(self, adapter_name):
+        """A further adapter on the same base convolution (the reference keeps 'recon_loss', 'unet_distill' and 'comp_distill'
+        sets side by side, dalc:553-556); same init as the first."""
+        if adapter_name in self.lora_A:
+            return
+        first = self.adapter
+        a0, b0 = self.lora_A[first], self.lora_B[first]
+        dev = a0.weight.device
+        self.lora_A[adapter_name] = nn.Conv2d(a0.in_channels, a0.out_channels, a0.kernel_size, padding=a0.padding, bias=False, device=dev)
+        self.lora_B[adapter_name] = nn.Conv2d(b0.in_channels, b0.out_channels, 1, bias=False, device=dev)
+        nn.init.kaiming_uniform_(self.lora_A[adapter_name].weight, a=5 ** 0.5)
+        nn.init.zeros_(self.lora_B[adapter_name].weight)
+        self.lora_magnitude_vector[adapter_name] = _ConvMagnitude(torch.linalg.norm(self.base_layer.weight.detach().float().flatten(1), dim=1))
+
+    def set_active_adapter(self, adapter_name):
+        if adapter_name not in self.lora_A:
+            raise KeyError(f"LoraDoraConv2d: unknown adapter {adapter_name!r} (have {list(self.lora_A)})")
+        if adapter_name != self.adapter:
+            self.adapter, self._pack_key = adapter_name, None
 
     @property
     def is_3x3(self):
@@ -229,11 +262,19 @@ class LoraDoraConv2d(nn.Module):
 
     def forward_tokens(self, t, hw, rowbias=None, residual=None):
         """t bf16 [B, h*w, cin] -> bf16 [B, h*w, cout]; ``rowbias`` / ``residual`` as in ops.conv3x3 (3x3 only / both)."""
-        _no_grad_only("LoraDoraConv2d", t)
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("LoraDoraConv2d: the training path (dropout on the adapter branch, backward) is not built")
-        wp, ap, bs, cs, bias = self.pack()
         b, n, _ = t.shape
+        ad = self.adapter
+        A, B, m = self.lora_A[ad].weight, self.lora_B[ad].weight, self.lora_magnitude_vector[ad].weight
+        if torch.is_grad_enabled() and (t.requires_grad or A.requires_grad or B.requires_grad or m.requires_grad):
+            # training (eval-mode arithmetic: the U-Net and its adapters stay in .eval(), ddpm.py:637-638, so lora_dropout is
+            # inactive): the adapter-fused convolution with its backward; the per-image bias / skip are added by autograd ops
+            y = ag.ConvLoraFn.apply(t if t.dtype == torch.bfloat16 else t.to(torch.bfloat16), self, A, B, m, hw)
+            if rowbias is not None:
+                y = y + rowbias.to(y.dtype)[:, None, :]
+            if residual is not None:
+                y = y + residual
+            return y
+        wp, ap, bs, cs, bias = self.pack()
         if self.is_3x3:
             ta = ops.conv3x3(t, ap, hw)
             return ops.conv3x3(t, wp, hw, bias=bias, rowbias=rowbias, residual=residual, t=ta.view(b * n, -1), bs=bs, colscale=cs)

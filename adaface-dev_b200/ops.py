@@ -469,6 +469,27 @@ def resample2x_bwd(x, hw_low, mode):
     return y
 
 
+def im2col3x3_tokens(x, hw):
+    """bf16 NHWC tokens [B, h*w, C] -> bf16 [B*h*w, 9*Kc] in the K order of pack_conv3x3_weight (adaface_im2col3x3_tokens): the
+    X operand of a 3x3 adapter's weight gradient dA = dT^T im2col(X)."""
+    _need(x, "x", torch.bfloat16)
+    h, w = hw
+    if x.dim() != 3 or not x.is_contiguous() or x.shape[1] != h * w or x.shape[2] % 8:
+        raise ValueError("im2col3x3_tokens: x must be a contiguous [B, h*w, C] tensor with C a multiple of 8")
+    B, _, C = x.shape
+    kc = (C + 63) // 64 * 64
+    col = torch.empty((B * h * w, 9 * kc), device=x.device, dtype=torch.bfloat16)
+    _lib.call("adaface_im2col3x3_tokens", _ptr(x), _ptr(col), B, h, w, C, _stream())
+    return col
+
+
+def unpack_conv3x3_weight(w_packed, cin):
+    """Inverse of pack_conv3x3_weight for a gradient: [Cout, 9*Kc] -> [Cout, cin, 3, 3] (same dtype)."""
+    cout = w_packed.shape[0]
+    kc = w_packed.shape[1] // 9
+    return w_packed.view(cout, 3, 3, kc)[..., :cin].permute(0, 3, 1, 2).contiguous()
+
+
 def pack_conv3x3_weight_dx(weight):
     """Packed operand of the convolution's input gradient: dX = conv3x3(dY, W') with W'[ci, co, ky, kx] = W[co, ci, 2-ky, 2-kx]
     (flipped taps, transposed channels) -- the same implicit-GEMM kernel computes it."""

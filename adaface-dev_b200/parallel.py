@@ -107,3 +107,112 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, bucket
             off += p.numel()
         n_buckets += 1
     return n_buckets
+
+
+class GradBucketer:
+    """Overlapped data-parallel gradient all-reduce for the stage-2 trainable set (LoRA / DoRA adapters + SubjBasisGenerator,
+    ~1e8 fp32 values; the reference relies on Lightning DDP for this, main.py:618).
+
+    Parameters are packed, in the order their gradients become ready (reverse registration order), into flat fp32 buckets and
+    every ``p.grad`` is made a VIEW of its bucket, so autograd accumulates straight into the communication buffer (no copy in,
+    no copy out).  A post-accumulate hook counts ready parameters; when a bucket is complete its all-reduce is launched at once
+    on a side stream (NCCL over NVLink / NVSwitch), overlapping the rest of the backward pass.  ``finish()`` launches whatever
+    is left, waits, averages, and -- DDP semantics -- leaves ``.grad = None`` on parameters that received no gradient on ANY
+    rank this iteration so that Adam / AdamW skip them.  ``zero()`` re-arms the buckets for the next iteration."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group=None, bucket_bytes: int = 64 << 20, average: bool = True,
+                 expected_uses: int = 1):
+        self.group, self.average, self.expected = group, average, max(1, int(expected_uses))
+        self.params = [p for p in params if p.requires_grad]
+        if any(p.dtype != torch.float32 for p in self.params):
+            raise ValueError("GradBucketer: trainable parameters are kept in fp32 (ddpm.py:4175-4177)")
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.buckets, self._where = [], {}
+        cur, size = [], 0
+        for p in reversed(self.params):
+            if cur and size + p.numel() * 4 > bucket_bytes:
+                self._add_bucket(cur)
+                cur, size = [], 0
+            cur.append(p)
+            size += p.numel() * 4
+        if cur:
+            self._add_bucket(cur)
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self._touched = torch.zeros(len(self.params), dtype=torch.int32)
+        self._index = {id(p): i for i, p in enumerate(self.params)}
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self.zero()
+
+    def _add_bucket(self, plist):
+        n = sum(p.numel() for p in plist)
+        flat = torch.zeros(n, device=plist[0].device, dtype=torch.float32)
+        b = {"flat": flat, "params": plist, "views": [], "pending": 0, "work": None, "launched": False}
+        off = 0
+        for p in plist:
+            b["views"].append(flat[off:off + p.numel()].view_as(p))
+            self._where[id(p)] = b
+            off += p.numel()
+        self.buckets.append(b)
+
+    def zero(self):
+        """Zero the buckets and point every .grad back at its view (call instead of optimizer.zero_grad())."""
+        self._touched.zero_()
+        self._count = {}
+        for b in self.buckets:
+            b["flat"].zero_()
+            b["pending"], b["work"], b["launched"] = len(b["params"]), None, False
+            for p, v in zip(b["params"], b["views"]):
+                p.grad = v
+
+    def _on_grad(self, p):
+        self._touched[self._index[id(p)]] = 1
+        c = self._count.get(id(p), 0) + 1
+        self._count[id(p)] = c
+        if c != self.expected:                   # a parameter used several times per iteration (e.g. 4 denoising steps) is ready
+            return                               # only after its last accumulation
+        b = self._where[id(p)]
+        b["pending"] -= 1
+        if b["pending"] == 0 and not b["launched"]:
+            self._launch(b)
+
+    def _launch(self, b):
+        b["launched"] = True
+        if self.world == 1:
+            return
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
+            dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group)
+
+    def finish(self) -> int:
+        """Complete the iteration's reduction.  Returns the number of buckets."""
+        for b in self.buckets:                   # buckets holding parameters without a gradient on this rank: same collectives everywhere
+            if not b["launched"]:
+                self._launch(b)
+        for b in self.buckets:
+            if b["work"] is not None:
+                b["work"].wait()
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        if self.world > 1:
+            if self.average:
+                for b in self.buckets:
+                    b["flat"] /= self.world
+            dev = self.params[0].device
+            t = self._touched.to(dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            touched = t.cpu()
+        else:
+            touched = self._touched
+        for p, used in zip(self.params, touched.tolist()):
+            if not used:
+                p.grad = None                    # no rank produced a gradient: the optimiser must skip it (DDP semantics)
+        return len(self.buckets)
+
+    def close(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

@@ -537,6 +537,109 @@ def ddim_measurement(torch, a, dev, rank, world, barrier, unet=None):
             "checks": {"finite": finite, "e2e_equals_device_run_bitwise": same}}
 
 
+def stage2_measurement(torch, a, dev, rank, world, barrier, unet, steps=4, warm=2):
+    """BASELINE config 5, scaled to what the hot path sees: one stage-2 (compositional distillation) iteration =
+    4 denoising steps x [ss, sc_rep no-grad; sc WITH grad; mc no-grad -- four sliced B = 1 U-Net calls with capture on layers
+    22-24, S = 97, attention LoRA r = 192 (DoRA) on q/k/v/out + conv-LoRA on up_blocks.3.resnets.[12], normalize_cross_attn on
+    sc / sc_rep -- plus one no-grad B = 4 unconditional call], loss = subject-mass background suppression + sc-vs-sc_rep
+    distillation (the consumers of the captured maps, fused into the capture kernel), backward through the sc instance into
+    the adapters and -- through rows 4:20 of the prompt -- the SubjBasisGenerator, then the data-parallel all-reduce of the
+    trainable gradients (GradBucketer over NCCL, overlapped with the SubjBasisGenerator's backward).  WEAK scaling: every rank
+    runs its own subject (as the reference seeds per rank, ldm/util.py:524-530).  No optimiser step (out of scope)."""
+    import torch.distributed as dist
+    from adaface_dev_b200.unet_wrapper import DiffusersUNetWrapper
+    from adaface_dev_b200.stage2 import CompDistillStep
+    S2 = 97
+    w = DiffusersUNetWrapper(unet, use_attn_lora=True, use_ffn_lora=True, lora_rank=192)
+    gen = torch.Generator().manual_seed(7)
+    with torch.no_grad():                              # adapters off their identity init so that every gradient path is live
+        for n_, p_ in w.unet_lora_modules.named_parameters():
+            if "lora_B" in n_:
+                p_.copy_((torch.randn(p_.shape, generator=gen) * 0.02).to(dev))
+    sbg = a.SubjBasisGenerator().to(dev)
+    sbg.train()
+    lora_params = w.trainable_parameters()
+    sbg_params = [p_ for p_ in sbg.parameters() if p_.requires_grad]
+    gb_lora = a.parallel.GradBucketer(lora_params, expected_uses=steps)
+    gb_sbg = a.parallel.GradBucketer(sbg_params, expected_uses=1)
+    step = CompDistillStep(w, fused_consumers=os.environ.get("ADAFACE_BENCH_STAGE2_FUSED", "1") != "0", use_ffn_lora=True)
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.randn(4, 4, 64, 64, generator=g).to(dev)
+    ts = [torch.full((4,), v, dtype=torch.long, device=dev) for v in (800, 600, 400, 200)][:steps]
+    base_prompt = torch.randn(4, S2, CTX_DIM, generator=g).to(dev)
+    uncond = torch.randn(1, S2, CTX_DIM, generator=g).expand(4, -1, -1).contiguous().to(dev)
+    id_embs = (torch.randn(1, 16, CTX_DIM, generator=g) * 0.5).to(dev)
+    si = (torch.zeros(16, dtype=torch.long, device=dev), torch.arange(4, 20, device=dev))
+    fg = torch.zeros(1, 1, 64, 64, device=dev)
+    fg[0, 0, 12:44, 16:40] = 1
+    emb_mask = torch.zeros(4, S2, 1, device=dev)
+    emb_mask[:, 1:40] = 1
+    pad_mask = torch.zeros(4, S2, 1, device=dev)
+    pad_mask[:, 40:] = 1
+
+    def iteration(comm=True):
+        gb_lora.zero()
+        gb_sbg.zero()
+        if not comm:
+            gb_lora.world = gb_sbg.world = 1
+        ada = sbg(id_embs)                                           # [1, 16, 768], differentiable
+        ada_leaf = ada.detach().requires_grad_(True)
+
+        def prompt():
+            pe = base_prompt.clone()
+            pe[0:3, 4:20] = ada_leaf.to(pe.dtype)                    # ss, sc, sc_rep carry the subject tokens; mc is the class prompt
+            return pe
+        totals = step.step(x, ts, prompt, uncond, si, fg, emb_mask, pad_mask, sc_fg_mask_percent=0.3)
+        ada.backward(ada_leaf.grad)                                  # SubjBasisGenerator backward: its buckets go out as they fill
+        gb_lora.finish()
+        gb_sbg.finish()
+        gb_lora.world = gb_sbg.world = world
+        return totals
+
+    def timed(fn, n):
+        barrier()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record()
+        for _ in range(n):
+            r_ = fn()
+        e_.record()
+        barrier()
+        return s_.elapsed_time(e_) / n, r_
+
+    for _ in range(warm):
+        iteration()
+    n0 = a._lib.launch_count()
+    iteration()
+    launches = a._lib.launch_count() - n0
+    n_it = 3
+    t_full, totals = timed(iteration, n_it)
+    t_nocomm, _ = timed(lambda: iteration(comm=False), n_it) if world > 1 else (t_full, None)
+
+    def allreduce_only():
+        for gb in (gb_lora, gb_sbg):
+            for b_ in gb.buckets:
+                dist.all_reduce(b_["flat"])
+    t_ar = timed(allreduce_only, 3)[0] if world > 1 else 0.0
+    n_par = sum(p_.numel() for p_ in lora_params + sbg_params)
+    tt = torch.tensor([t_full, t_nocomm, t_ar], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_full, t_nocomm, t_ar = tt.tolist()
+    finite = all(bool(torch.isfinite(torch.as_tensor(v)).all()) for v in totals.values())
+    gb_lora.close()
+    gb_sbg.close()
+    return {"metric": "stage-2 compositional-distillation iterations/s (4 denoising steps, capture + backward, DDP all-reduce)",
+            "unit": "iterations/s", "value": world * 1e3 / t_full, "ms_per_iteration": t_full, "scaling": "weak", "n_gpus": world,
+            "ms_per_iteration_without_collectives": t_nocomm, "allreduce_alone_ms": t_ar,
+            "allreduce_exposed_share": max(0.0, (t_full - t_nocomm) / t_full) if world > 1 else 0.0,
+            "allreduce_bytes": int(n_par * 4), "trainable_params": {"lora": int(sum(p_.numel() for p_ in lora_params)),
+                                                                      "subj_basis_generator": int(sum(p_.numel() for p_ in sbg_params))},
+            "buckets": len(gb_lora.buckets) + len(gb_sbg.buckets), "kernels_per_iteration": int(launches),
+            "config": {"denoising_steps": steps, "instances": "ss, sc, sc_rep, mc (B=1 slices) + uncond B=4", "ctx_tokens": S2, "lora_rank": 192,
+                       "captured_layers": [22, 23, 24], "fused_capture_consumers": step.fused, "launch": "eager (Python launches)"},
+            "losses": {k_: float(v_) for k_, v_ in totals.items()}, "checks": {"finite": finite}}
+
+
 def main_gpu(args):
     import torch
     import torch.distributed as dist
@@ -714,6 +817,16 @@ def main_gpu(args):
             extra = secondary_measurements(torch, a, dev, flush, peaks(), unet)
         except Exception as ex:      # secondary lines never take the headline down with them
             extra = {"error": f"{type(ex).__name__}: {ex}"}
+    stage2 = None
+    if os.environ.get("ADAFACE_BENCH_STAGE2", "1") != "0":
+        if unet is None:
+            unet = build_unet(torch, a, dev)
+        try:                           # last: the wrapper installs processors / adapters on the U-Net and freezes it
+            stage2 = stage2_measurement(torch, a, dev, rank, world, barrier, unet)
+        except Exception as ex:
+            if world > 1:
+                raise
+            stage2 = {"error": f"{type(ex).__name__}: {ex}"}
     del unet
 
     tt = torch.tensor([t_ms, t_e2e_ms], device=dev, dtype=torch.float64)
@@ -751,6 +864,8 @@ def main_gpu(args):
         }
         if ddim is not None:
             line["unet_steps_per_s"] = ddim
+        if stage2 is not None:
+            line["stage2_step"] = stage2
         if extra is not None:
             line["secondary"] = extra
         if world == 1:

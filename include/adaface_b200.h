@@ -295,6 +295,12 @@ int adaface_attn_cross_consume_bwd(const void* q, int64_t q_sb, int64_t q_sn, co
 int adaface_ddim_cfg_step(const float* eps, int64_t n_images, int64_t n_per_image, int has_uncond, const float* x,
                           const float* coef, const float* noise, float* x_prev, float* x_dup, float* pred_x0, void* stream);
 
+/* im2col for the weight gradient of a 3x3 convolution adapter (conv-LoRA A matrix; adaface/diffusers_attn_lora_capture.py:541-591,
+ * peft lora.Conv2d): x bf16 NHWC [B, H, W, C] -> col bf16 [B*H*W, 9*Kc], Kc = C rounded up to 64,
+ * col[p, (ky*3+kx)*Kc + c] = x[b, y+ky-1, x+kx-1, c] (zero outside the image and for c >= C) -- the K order of the packed
+ * weights of adaface_conv3x3_fwd, so that dA_packed = dT^T col is one call of adaface_proj_lora_fwd.  C multiple of 8. */
+int adaface_im2col3x3_tokens(const void* x, void* col, int64_t B, int64_t H, int64_t W, int64_t C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

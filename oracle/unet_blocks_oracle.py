@@ -131,10 +131,13 @@ def _spatial_weights(sd, p):
     return w
 
 
-def unet_forward(sd, cfg, x, timesteps, context, mask=None):
+def unet_forward(sd, cfg, x, timesteps, context, mask=None, res_hidden_states_gradscale=1.0):
     """UNetModel.forward (openaimodel.py:820-960) without capture: time embedding -> input blocks (skips pushed) -> middle
-    block -> output blocks (skip popped and concatenated on the channel axis, :925) -> out (norm, SiLU, conv)."""
-    from .attn_oracle import spatial_transformer
+    block -> output blocks (skip popped and concatenated on the channel axis, :925) -> out (norm, SiLU, conv).
+    res_hidden_states_gradscale: the ScaleGrad the training wrapper puts on the skip tensors entering diffusers up_blocks[1:]
+    (CrossAttnUpBlock2D_forward_capture, adaface/diffusers_attn_lora_capture.py:382-394; = output blocks from index
+    num_res_blocks + 1 on): identity forward, gradient times the factor."""
+    from .attn_oracle import spatial_transformer, scale_grad
     heads = cfg["num_heads"]
 
     def run(layers, prefix, h, emb):
@@ -160,8 +163,12 @@ def unet_forward(sd, cfg, x, timesteps, context, mask=None):
         h = run(layers, f"input_blocks.{i}.", h, emb)
         hs.append(h)
     h = run(mid, "middle_block.", h, emb)
+    first_scaled = cfg["num_res_blocks"] + 1
     for i, layers in enumerate(out):
-        h = run(layers, f"output_blocks.{i}.", torch.cat([h, hs.pop()], dim=1), emb)
+        skip = hs.pop()
+        if i >= first_scaled and res_hidden_states_gradscale != 1.0:
+            skip = scale_grad(skip, res_hidden_states_gradscale)
+        h = run(layers, f"output_blocks.{i}.", torch.cat([h, skip], dim=1), emb)
     return conv3x3(silu(group_norm32(h, sd["out.0.weight"], sd["out.0.bias"])), sd["out.2.weight"], sd["out.2.bias"])
 
 

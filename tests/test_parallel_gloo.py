@@ -115,3 +115,38 @@ def test_gradient_allreduce_keeps_globally_unused_params_gradless():
     gradient on some rank only gets the mean with zeros from the others."""
     for used, one_sided, unused_is_none in _run(_none_grad_job):
         assert used == [1.5] * 4 and one_sided == [1.5] * 4 and unused_is_none
+
+
+def _bucketer_job(rank, world):
+    import adaface_dev_b200 as a
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Linear(32, 4))     # same init on both ranks
+    unused = torch.nn.Parameter(torch.ones(3))
+    gb = a.parallel.GradBucketer(list(model.parameters()) + [unused], bucket_bytes=1024, expected_uses=2)
+    out = []
+    for it in range(2):                                                              # two iterations: zero() re-arms the buckets
+        gb.zero()
+        for micro in range(2):                                                       # two accumulations per iteration
+            x = torch.randn(8, 16, generator=torch.Generator().manual_seed(100 * it + 10 * micro + rank))
+            model(x).square().mean().backward()
+        nb = gb.finish()
+        out.append((nb, [p.grad.clone() for p in model.parameters()], unused.grad is None))
+    gb.close()
+    return out
+
+
+def test_grad_bucketer_matches_mean_of_accumulated_gradients():
+    r0, r1 = _run(_bucketer_job)
+    for it in range(2):
+        (nb0, g0, none0), (nb1, g1, none1) = r0[it], r1[it]
+        assert nb0 == nb1 and nb0 >= 2 and none0 and none1
+        for a_, b_ in zip(g0, g1):
+            assert torch.equal(a_, b_)
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Linear(32, 4))
+        for r in range(2):
+            for micro in range(2):
+                x = torch.randn(8, 16, generator=torch.Generator().manual_seed(100 * it + 10 * micro + r))
+                model(x).square().mean().backward()
+        for got, p in zip(g0, model.parameters()):
+            assert torch.allclose(got, p.grad / 2, atol=1e-6)
