@@ -15,8 +15,11 @@ import torch.nn.functional as F
 ALIGN_LAYERS = (23, 24)          # attn_align_layer_weights = subj_comp_rep_distill_layer_weights = {23: 1, 24: 1}, normalised (:1839, :2058)
 
 
-def _layer_weights():
-    return {li: 1.0 / len(ALIGN_LAYERS) for li in ALIGN_LAYERS}
+def _layer_weights(layer_weights=None):
+    """normalize_dict_values (ldm/util.py:1088-1095) of the per-layer weights; default: the reference's {23: 1, 24: 1}."""
+    lw = {li: 1.0 for li in ALIGN_LAYERS} if layer_weights is None else dict(layer_weights)
+    tot = float(sum(lw.values()))
+    return {li: v / tot for li, v in lw.items()}
 
 
 def resize_mask_to_target_size(mask, area):
@@ -27,14 +30,14 @@ def resize_mask_to_target_size(mask, area):
     return torch.maximum(near, bil)
 
 
-def calc_subj_masked_bg_suppress_loss(attn_subj_sum, subj_indices, BLOCK_SIZE, fg_mask, bg_attn_tolerance=0.02):
+def calc_subj_masked_bg_suppress_loss(attn_subj_sum, subj_indices, BLOCK_SIZE, fg_mask, bg_attn_tolerance=0.02, layer_weights=None):
     """ldm/util.py:1822-1918 on the kernel-reduced maps.  attn_subj_sum: {layer: [>= BLOCK_SIZE, H, N]} = probability mass on each
     instance's subject columns (the reference computes it as sel_emb_attns_by_indices(..., do_sum=True) from the full map)."""
     if subj_indices is None or len(subj_indices) == 0 or fg_mask is None:
         return 0
     if fg_mask.chunk(4)[0].float().mean() >= 0.998:                                     # :1845: no foreground / background split
         return 0
-    loss, lws = 0, _layer_weights()
+    loss, lws = 0, _layer_weights(layer_weights)
     for li, lw in lws.items():
         if li not in attn_subj_sum:
             continue
@@ -59,7 +62,7 @@ def masked_l2_loss(pred, target, mask):
 
 
 def calc_sc_rep_attn_distill_loss(attn_sqdiff, attn_shape, ca_k, ca_v, subj_indices_1b, prompt_emb_mask_4b, prompt_pad_mask_4b,
-                                  sc_fg_mask_percent, FG_THRES=0.1):
+                                  sc_fg_mask_percent, FG_THRES=0.1, layer_weights=None):
     """ldm/util.py:2047-2121.  attn_sqdiff: {layer: [1] = sum over (h, i, j) of (sc_attn - sc_rep_attn)^2} from the fused kernel,
     attn_shape: {layer: (H, N, S)} of the map it was reduced over; ca_k / ca_v: {layer: [4, C, S]} for (ss, sc, sc_rep, mc).
     Returns (attn, subj_k, nonsubj_k, subj_v, nonsubj_v) losses."""
@@ -72,7 +75,7 @@ def calc_sc_rep_attn_distill_loss(attn_sqdiff, attn_shape, ca_k, ca_v, subj_indi
     nonsubj[subj_indices_1b] = 0                                                        # :2068
     nonsubj = torch.logical_or(nonsubj, sc_pad).unsqueeze(1)                            # [1, 1, S]
     l_attn = l_sk = l_nk = l_sv = l_nv = 0
-    for li, lw in _layer_weights().items():
+    for li, lw in _layer_weights(layer_weights).items():
         if li not in attn_sqdiff:
             continue
         H, N, S = attn_shape[li]

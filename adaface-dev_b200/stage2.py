@@ -93,9 +93,11 @@ class CompDistillStep:
                 sums[li] = (p_sc * flag[:, None, None, :]).sum(-1)
                 sq[li] = ((p_sc - p_sr.detach()) ** 2).sum().reshape(1)
                 shp[li] = tuple(p_sc.shape[1:])
-        l_bg = closs.calc_subj_masked_bg_suppress_loss(sums, subj_indices_1b, 1, sc_fg_mask)
+        lws = {li: 1.0 for li in L}
+        l_bg = closs.calc_subj_masked_bg_suppress_loss(sums, subj_indices_1b, 1, sc_fg_mask, layer_weights=lws)
         l_attn, l_sk, l_nk, l_sv, l_nv = closs.calc_sc_rep_attn_distill_loss(sq, shp, cat4("k"), cat4("v"), subj_indices_1b,
-                                                                            prompt_emb_mask_4b, prompt_pad_mask_4b, sc_fg_mask_percent)
+                                                                            prompt_emb_mask_4b, prompt_pad_mask_4b, sc_fg_mask_percent,
+                                                                            layer_weights=lws)
         return {"subj_mb_suppress": l_bg, "rep_distill_attn": l_attn, "rep_distill_subj_k": l_sk, "rep_distill_nonsubj_k": l_nk,
                 "rep_distill_subj_v": l_sv, "rep_distill_nonsubj_v": l_nv}
 

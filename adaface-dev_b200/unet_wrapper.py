@@ -186,7 +186,9 @@ class DiffusersUNetWrapper(nn.Module):
             p.requires_grad = False
         self.ffn_lora_layers, self.unet_lora_modules = [], None
         if self.use_attn_lora or self.use_ffn_lora:
-            pat = 'up_blocks.3.resnets.[12].conv[a-z0-9_]+' if self.use_ffn_lora else None
+            # reference: 'up_blocks.3.resnets.[12].conv[a-z0-9_]+' (ddpm.py:4146); "3" = the last up block of SD-1.5
+            last = max(int(n.split(".")[1]) for n in diffusers_module_names(self.diffusion_model) if n.startswith("up_blocks."))
+            pat = f'up_blocks.{last}.resnets.[12].conv[a-z0-9_]+' if self.use_ffn_lora else None
             ffn_layers, ffn_opt = set_up_ffn_loras(self.diffusion_model, pat, True, self.lora_rank, self.lora_rank // self.ffn_lora_scale_down)
             self.ffn_lora_layers = list(ffn_layers.values())
             mods = {}
