@@ -1,0 +1,15 @@
+// Parameters shared by the tcgen05 attention kernels (attn_tcgen05.cu, attn_tcgen05_q48.cu).
+#pragma once
+#include "common.cuh"
+
+namespace adaface {
+
+struct TaParams {
+  bf16* o;
+  long long o_sb, o_sn;
+  int Lq, Lk;
+  float scale_log2;
+  float* lse;              // optional [B, H, Lq]: log2-domain log-sum-exp of each row, kept for the backward pass
+};
+
+}  // namespace adaface

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "attn_tc_params.cuh"
 #include "../../include/adaface_b200.h"
 
 namespace adaface {
@@ -48,27 +49,27 @@ struct TaCfg {
   static constexpr int SMEM_BYTES = Q_BYTES + ST * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 + 256;
 };
 
-struct TaParams {
-  bf16* o;
-  long long o_sb, o_sn;
-  int Lq, Lk;
-  float scale_log2;
-  float* lse;              // optional [B, H, Lq]: log2-domain log-sum-exp of each row, kept for the backward pass
-};
 
 // exp2 on the FMA/ALU pipes for a pair of values in [-126, 8]: Cody-Waite split with the 1.5*2^23 magic constant,
 // degree-3 minimax polynomial of 2^f on [-0.5, 0.5] (max rel. error 7.5e-5, far below bf16's 2^-9), exponent
 // re-inserted with one integer shift-add.  Offloads part of the softmax from the 16-op/clk MUFU unit, which is
 // what bounds d = 40 attention (one exp per 160 tensor FLOPs).
+template <int DEG = 3>
 __device__ __forceinline__ float2 exp2_emu2(float2 x) {
   x.x = fmaxf(x.x, -126.f);
   x.y = fmaxf(x.y, -126.f);
   const float2 t = __fadd2_rn(x, make_float2(12582912.f, 12582912.f));
   const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
   const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
-  float2 q = __ffma2_rn(f, make_float2(0.05517164f, 0.05517164f), make_float2(0.24261113f, 0.24261113f));
-  q = __ffma2_rn(q, f, make_float2(0.69326097f, 0.69326097f));
-  q = __ffma2_rn(q, f, make_float2(0.99992806f, 0.99992806f));
+  float2 q;
+  if constexpr (DEG == 3) {
+    q = __ffma2_rn(f, make_float2(0.05517164f, 0.05517164f), make_float2(0.24261113f, 0.24261113f));
+    q = __ffma2_rn(q, f, make_float2(0.69326097f, 0.69326097f));
+    q = __ffma2_rn(q, f, make_float2(0.99992806f, 0.99992806f));
+  } else {      // degree-2 minimax: max rel. error 1.7e-3, below the 3.9e-3 of the truncating bf16 pack that follows
+    q = __ffma2_rn(f, make_float2(0.23842894f, 0.23842894f), make_float2(0.7034480f, 0.7034480f));
+    q = __ffma2_rn(q, f, make_float2(1.0004431f, 1.0004431f));
+  }
   float2 r;
   r.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
   r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
@@ -758,7 +759,9 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[hf * 32 + 2 * i]), __uint_as_float(v[hf * 32 + 2 * i + 1])), sc2, nm2);
-          const float2 e = ((i & 7) < EMU) ? exp2_emu2(t) : make_float2(fast_exp2(t.x), fast_exp2(t.y));
+          // EMU 0..4: that many of every 8 pairs on the degree-3 polynomial; EMU 5..7: 2..4 pairs on the degree-2 one
+          constexpr int EMU_N = EMU <= 4 ? EMU : EMU - 3, EMU_DEG = EMU <= 4 ? 3 : 2;
+          const float2 e = ((i & 7) < EMU_N) ? exp2_emu2<EMU_DEG>(t) : make_float2(fast_exp2(t.x), fast_exp2(t.y));
           pk[i] = __byte_perm(__float_as_uint(e.x), __float_as_uint(e.y), 0x7632);   // truncate to bf16; the row sum comes from the MMA
         }
         tmem_st_32x32b_x16(t_lane + (uint32_t)(hf * 16), pk);
@@ -1263,7 +1266,7 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, co
     const char* m = getenv("ADAFACE_ATTN_MC");      // 1 (default): many-small-CTAs kernel for d = 40 / 80
     mc = (m && m[0] == '0') ? 0 : 1;
     const char* e = getenv("ADAFACE_EXP_EMU");      // tuning knob: exp2 pairs of every 8 moved off the MUFU unit
-    emu = (e && e[0] >= '0' && e[0] <= '4') ? (e[0] - '0') : 0;
+    emu = (e && e[0] >= '0' && e[0] <= '7') ? (e[0] - '0') : 0;
     emu_set = e != nullptr;
     const char* ps = getenv("ADAFACE_P_SMEM");      // debugging aid: hand P to the MMA through shared memory
     psmem = (ps && ps[0] == '1') ? 1 : 0;
@@ -1275,12 +1278,16 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, co
     quad = (e && e[0] == '0') ? 0 : 1;
   }
   if (quad && mc && !psmem && d == 40 && Lq >= 2 * TQ_G * TA_BM && Lk > 128) {
-    switch (emu_set ? emu : 2) {      // default: 2 of every 8 exp2 pairs on the FMA pipe (measured: 366 / 349 / 333 / 334 / 342 us for 0..4)
+    switch (emu_set ? emu : 5) {      // default: 2 of every 8 exp2 pairs on the FMA pipe, degree-2 polynomial (round 2, us: EMU 2: 298.0, 3: 311.3,
+                                      // 5 (= 2 pairs, degree 2): 294.9, 6: 306.2, 7: 310.3; round 1: 366 / 349 / 333 / 334 / 342 for 0..4)
       case 0: return launch_ta_quad<40, 0>(tQ, tK, tV, p, ib, ih, stream);
       case 1: return launch_ta_quad<40, 1>(tQ, tK, tV, p, ib, ih, stream);
       case 2: return launch_ta_quad<40, 2>(tQ, tK, tV, p, ib, ih, stream);
       case 3: return launch_ta_quad<40, 3>(tQ, tK, tV, p, ib, ih, stream);
-      default: return launch_ta_quad<40, 4>(tQ, tK, tV, p, ib, ih, stream);
+      case 4: return launch_ta_quad<40, 4>(tQ, tK, tV, p, ib, ih, stream);
+      case 5: return launch_ta_quad<40, 5>(tQ, tK, tV, p, ib, ih, stream);
+      case 6: return launch_ta_quad<40, 6>(tQ, tK, tV, p, ib, ih, stream);
+      default: return launch_ta_quad<40, 7>(tQ, tK, tV, p, ib, ih, stream);
     }
   }
   if (mc && !psmem && d == 40) {
