@@ -23,7 +23,7 @@ from .subj_basis_generator import (SubjBasisGenerator, Arc2FaceID2ImgPrompt, Fro
                                    CLIPAttentionMKV, CLIPTextConfig, template_ids)
 from .ddim import DDIMSampler, UNetDenoiser, ddim_cfg_step, make_linear_alphas_cumprod  # noqa: F401
 from .build import build  # noqa: F401
-from .graphs import graphed  # noqa: F401
+from .graphs import graphed, graphed_step, invalidate_trainable_packs  # noqa: F401
 from . import parallel  # noqa: F401
 
 __version__ = "0.1.0"

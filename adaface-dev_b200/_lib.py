@@ -59,6 +59,9 @@ SIGNATURES = {
     "adaface_attn_cross_consume_bwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64,
                                        _i64, _f32, _p, _p, _p, _i32, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i32, _p, _f32,
                                        _p, _p, _p, _p, _p, _p, _p, _p],
+    "adaface_sbg_head_fwd_dev": [_p, _p, _p, _p, _p, _i32, _i64, _p, _p, _p, _i64, _i64, _i64, _f32, _p],
+    "adaface_sbg_head_bwd_dev": [_p, _p, _p, _p, _p, _i32, _i64, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _f32, _p],
+    "adaface_dora_colscale": [_p, _i32, _p, _i64, _f32, _p, _p, _i64, _i64, _p],
     "adaface_im2col3x3_tokens": [_p, _p, _i64, _i64, _i64, _i64, _p],
     # ---- sampler step (ABI v4)
     "adaface_ddim_cfg_step": [_p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _p],

@@ -99,12 +99,18 @@ class LoraDoraLinear(nn.Module):
         key = tuple((t.data_ptr(), t._version) for t in (A, B, m, W))
         if key != self._pack_key:
             with torch.no_grad():
-                Af, Bf = A.float(), B.float()
-                wn = torch.linalg.norm(W.float() + self.scaling * (Bf @ Af), dim=1)
-                self._pack = (A.to(torch.bfloat16).contiguous(), (Bf * self.scaling).to(torch.bfloat16).contiguous(),
-                              (m.float() / wn).contiguous())
+                A16 = A.detach().to(torch.bfloat16).contiguous()
+                B16 = B.detach().to(torch.bfloat16).contiguous()
+                Wd = W.detach()
+                cs = ops.dora_colscale(Wd if Wd.dtype in (torch.float32, torch.bfloat16) else Wd.float(), A16, B16, self.scaling, m)
+                self._pack = (A16, (B.detach().float() * self.scaling).to(torch.bfloat16).contiguous(), cs)
             self._pack_key = key
         return self._pack
+
+    def invalidate(self):
+        """Force the next pack() to rebuild the operands from the live parameters (call before capturing a training step into a
+        CUDA graph, so that the rebuild is part of the graph and every replay sees the optimiser's latest update)."""
+        self._pack_key = None
 
 
 class Attention(nn.Module):
@@ -167,6 +173,14 @@ def _linear(x2d, w16, bias, lora: Optional[LoraDoraLinear], **kw):
     return ops.proj(x2d, w16, t=t, bs=Bs16, colscale=colscale, bias=bias, **kw)
 
 
+def _token_flags(B, S, ib, in_, device):
+    """uint8 [B, S] with ones at (ib[k], in_[k]).  The value operand is a DEVICE tensor: ``flag[ib, in_] = 1`` would stage the
+    Python scalar through a host tensor, which CUDA-graph capture forbids."""
+    flag = torch.zeros((B, S), device=device, dtype=torch.uint8)
+    ib, in_ = ib.to(device).long(), in_.to(device).long()
+    return flag.index_put_((ib, in_), torch.ones(ib.numel(), device=device, dtype=torch.uint8))
+
+
 def img_mask_to_key_mask(img_mask, n_tokens):
     """dalc:254-273: nearest-resize the [B,1,H,W] mask to sqrt(N) x sqrt(N), use it as a KEY mask, and drop it for
     the whole batch if any instance's resized mask is all zero -- evaluated on the device (no host sync)."""
@@ -225,8 +239,7 @@ class AttnProcessor_LoRA_Capture(nn.Module):
             if subj_indices is None:
                 raise ValueError("capture consumer 'subj_sum' requires subj_indices")
             ib, in_ = subj_indices
-            sum_flag = torch.zeros((B, S), device=q.device, dtype=torch.uint8)
-            sum_flag[ib.long(), in_.long()] = 1
+            sum_flag = _token_flags(B, S, ib, in_, q.device)
         ref = cons["ref_attn"]
         if ref is not None:
             ref = ref.detach().float().contiguous()
@@ -389,8 +402,7 @@ class AttnProcessor_LoRA_Capture(nn.Module):
             if subj_indices is None:
                 raise ValueError("normalize_cross_attn=True requires subj_indices (dalc:120)")
             ib, in_ = subj_indices
-            col_flag = torch.zeros((B, S), device=device, dtype=torch.uint8)
-            col_flag[ib.long(), in_.long()] = 1
+            col_flag = _token_flags(B, S, ib, in_, device)
         if self.capture_subj_cols_only and subj_indices is not None:
             ib, in_ = subj_indices
             slot, n_sub = self._subj_slots(ib.to(device), B)

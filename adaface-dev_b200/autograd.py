@@ -283,16 +283,17 @@ class SbgHeadFn(Function):
 
     @staticmethod
     def forward(ctx, wl_t, ln_w, ln_b, eps, *hs):
-        wl = [float(x) for x in wl_t.detach().reshape(-1).tolist()]
+        # the (normalised) layer weights stay on the DEVICE: no host read per step, the whole step is graph-capturable
+        wl = wl_t.detach().float().reshape(-1).contiguous()
         wf = ln_w.detach().float().contiguous()
-        ctx.wl, ctx.eps, ctx.wl_shape, ctx.wl_dtype = wl, eps, wl_t.shape, wl_t.dtype
-        ctx.save_for_backward(wf, *hs)
+        ctx.eps, ctx.wl_shape, ctx.wl_dtype = eps, wl_t.shape, wl_t.dtype
+        ctx.save_for_backward(wf, wl, *hs)
         return ops.sbg_head(list(hs), wl, wf, ln_b.detach().float().contiguous(), eps)
 
     @staticmethod
     def backward(ctx, dout):
-        wf, *hs = ctx.saved_tensors
-        dhs, dwl, dw, db = ops.sbg_head_bwd(hs, ctx.wl, wf, dout.float().contiguous(), ctx.eps)
+        wf, wl, *hs = ctx.saved_tensors
+        dhs, dwl, dw, db = ops.sbg_head_bwd(hs, wl, wf, dout.float().contiguous(), ctx.eps)
         return (dwl.reshape(ctx.wl_shape).to(ctx.wl_dtype), dw, db, None) + tuple(dhs)
 
 

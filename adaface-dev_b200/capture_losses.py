@@ -35,8 +35,9 @@ def calc_subj_masked_bg_suppress_loss(attn_subj_sum, subj_indices, BLOCK_SIZE, f
     instance's subject columns (the reference computes it as sel_emb_attns_by_indices(..., do_sum=True) from the full map)."""
     if subj_indices is None or len(subj_indices) == 0 or fg_mask is None:
         return 0
-    if fg_mask.chunk(4)[0].float().mean() >= 0.998:                                     # :1845: no foreground / background split
-        return 0
+    # The reference's early exits (:1845 no fg / bg split; :1881-1888 an instance without foreground or background pixels skips
+    # the layer) are evaluated ON THE DEVICE as 0 / 1 factors, so the function never synchronises (CUDA-graph-capturable).
+    run = (fg_mask.chunk(4)[0].float().mean() < 0.998).float()
     loss, lws = 0, _layer_weights(layer_weights)
     for li, lw in lws.items():
         if li not in attn_subj_sum:
@@ -45,12 +46,11 @@ def calc_subj_masked_bg_suppress_loss(attn_subj_sum, subj_indices, BLOCK_SIZE, f
         fg = resize_mask_to_target_size(fg_mask, subj_attn.shape[-1]).reshape(BLOCK_SIZE, 1, -1).to(subj_attn.device)
         fg3 = (fg.expand(-1, subj_attn.shape[1], -1) > 1e-6).float()                    # :1875-1877
         bg3 = 1 - fg3
-        if bool((fg3.sum(dim=(1, 2)) == 0).any()) or bool((bg3.sum(dim=(1, 2)) == 0).any()):      # :1881-1888
-            continue
+        keep = ((fg3.sum(dim=(1, 2)) > 0).all() & (bg3.sum(dim=(1, 2)) > 0).all()).float()
         excess = subj_attn * bg3 - bg_attn_tolerance                                    # :1907
         pos = (excess > 0).float()
-        loss = loss + (excess * pos).sum() / torch.clamp(pos.sum(), min=1e-6) * lw      # masked_mean (:1910)
-    return loss
+        loss = loss + keep * (excess * pos).sum() / torch.clamp(pos.sum(), min=1e-6) * lw      # masked_mean (:1910)
+    return run.to(loss.device) * loss if torch.is_tensor(loss) else loss
 
 
 def masked_l2_loss(pred, target, mask):
@@ -72,7 +72,8 @@ def calc_sc_rep_attn_distill_loss(attn_sqdiff, attn_shape, ca_k, ca_v, subj_indi
     _, sc_emb, _, _ = prompt_emb_mask_4b.squeeze(2).chunk(4)
     _, sc_pad, _, _ = prompt_pad_mask_4b.squeeze(2).chunk(4)
     nonsubj = sc_emb.clone()
-    nonsubj[subj_indices_1b] = 0                                                        # :2068
+    ib, it = subj_indices_1b                                                            # :2068 (value as a device tensor: no host staging)
+    nonsubj.index_put_((ib.to(nonsubj.device).long(), it.to(nonsubj.device).long()), torch.zeros(ib.numel(), device=nonsubj.device, dtype=nonsubj.dtype))
     nonsubj = torch.logical_or(nonsubj, sc_pad).unsqueeze(1)                            # [1, 1, S]
     l_attn = l_sk = l_nk = l_sv = l_nv = 0
     for li, lw in _layer_weights(layer_weights).items():

@@ -148,7 +148,7 @@ int layernorm_bwd(const void*, int, int64_t, const void*, int, int64_t, const fl
 int act_fwd(const void*, int64_t, void*, int64_t, int64_t, int64_t, int, cudaStream_t);
 int act_bwd(const void*, int64_t, const void*, int64_t, void*, int64_t, int64_t, int64_t, int, cudaStream_t);
 int sbg_head_bwd(const float*, const float*, const float*, const float*, const float*, int, int64_t, const float*, const float*,
-                 int64_t, float*, float*, float*, float*, float*, float*, float*, int64_t, int64_t, float, cudaStream_t);
+                 int64_t, float*, float*, float*, float*, float*, float*, float*, int64_t, int64_t, float, cudaStream_t, const float*);
 int attn_cross_capture_fwd(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t, int64_t,
                            void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, float, float*, float*,
                            float*, const int32_t*, int64_t, const uint8_t*, const float*, const float*, int, int, cudaStream_t,
@@ -158,7 +158,7 @@ int capture_chan_major(const void*, int, int64_t, int64_t, int64_t, int64_t, int
 int layernorm_fwd(const void*, int, int64_t, const float*, const float*, void*, int, int64_t, int64_t, int64_t, float,
                   cudaStream_t);
 int sbg_head_fwd(const float*, const float*, const float*, const float*, const float*, int, int64_t, const float*,
-                 const float*, float*, int64_t, int64_t, int64_t, float, cudaStream_t);
+                 const float*, float*, int64_t, int64_t, int64_t, float, cudaStream_t, const float*);
 int groupnorm_tokens_fwd(const void*, int, const float*, const float*, int64_t, int64_t, int64_t, int64_t, float, float*, float*,
                          void*, cudaStream_t);
 int tokens_to_nchw_add(const void*, const void*, int, void*, int64_t, int64_t, int64_t, cudaStream_t);
@@ -169,6 +169,7 @@ int groupnorm_act_tokens_fwd(const void*, const float*, const float*, int64_t, i
 int64_t groupnorm_act_tokens_ws_floats(int64_t, int64_t, int64_t, int64_t);
 int silu_fwd(const void*, int, void*, int64_t, cudaStream_t);
 int im2col3x3_tokens(const void*, void*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
+int dora_colscale(const void*, int, const float*, int64_t, float, const float*, float*, int64_t, int64_t, cudaStream_t);
 int ddim_cfg_step(const float*, int64_t, int64_t, int, const float*, const float*, const float*, float*, float*, float*, cudaStream_t);
 int upsample2x_tokens(const void*, void*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
 int timestep_embedding(const float*, int64_t, int64_t, float, void*, cudaStream_t);
@@ -265,7 +266,12 @@ int adaface_layernorm_fwd(const void* x, int x_dtype, int64_t ldx, const float* 
 int adaface_sbg_head_fwd(const float* h0, const float* h1, const float* h2, const float* h3, const float* wl,
                          int n_layers, int64_t ldh, const float* w, const float* b, float* out, int64_t ldo,
                          int64_t M, int64_t C, float eps, void* stream) {
-  return sbg_head_fwd(h0, h1, h2, h3, wl, n_layers, ldh, w, b, out, ldo, M, C, eps, (cudaStream_t)stream);
+  return sbg_head_fwd(h0, h1, h2, h3, wl, n_layers, ldh, w, b, out, ldo, M, C, eps, (cudaStream_t)stream, nullptr);
+}
+int adaface_sbg_head_fwd_dev(const float* h0, const float* h1, const float* h2, const float* h3, const float* wl_dev, int n_layers,
+                             int64_t ldh, const float* w, const float* b, float* out, int64_t ldo, int64_t M, int64_t C, float eps,
+                             void* stream) {
+  return sbg_head_fwd(h0, h1, h2, h3, nullptr, n_layers, ldh, w, b, out, ldo, M, C, eps, (cudaStream_t)stream, wl_dev);
 }
 
 int adaface_groupnorm_tokens_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, int64_t B, int64_t C,
@@ -292,6 +298,10 @@ int64_t adaface_groupnorm_act_tokens_ws_floats(int64_t B, int64_t HW, int64_t C,
 int adaface_ddim_cfg_step(const float* eps, int64_t n_images, int64_t n_per_image, int has_uncond, const float* x, const float* coef,
                           const float* noise, float* x_prev, float* x_dup, float* pred_x0, void* stream) {
   return ddim_cfg_step(eps, n_images, n_per_image, has_uncond, x, coef, noise, x_prev, x_dup, pred_x0, (cudaStream_t)stream);
+}
+int adaface_dora_colscale(const void* W, int w_dtype, const float* BA, int64_t ldba, float s, const float* m, float* out, int64_t N,
+                          int64_t K, void* stream) {
+  return dora_colscale(W, w_dtype, BA, ldba, s, m, out, N, K, (cudaStream_t)stream);
 }
 int adaface_im2col3x3_tokens(const void* x, void* col, int64_t B, int64_t H, int64_t W, int64_t C, void* stream) {
   return im2col3x3_tokens(x, col, B, H, W, C, (cudaStream_t)stream);
@@ -391,7 +401,13 @@ int adaface_sbg_head_bwd(const float* h0, const float* h1, const float* h2, cons
                          float* dh1, float* dh2, float* dh3, float* dwl, float* dw, float* db, int64_t M, int64_t C,
                          float eps, void* stream) {
   return sbg_head_bwd(h0, h1, h2, h3, wl, n_layers, ldh, w, dout, lddo, dh0, dh1, dh2, dh3, dwl, dw, db, M, C, eps,
-                      (cudaStream_t)stream);
+                      (cudaStream_t)stream, nullptr);
+}
+int adaface_sbg_head_bwd_dev(const float* h0, const float* h1, const float* h2, const float* h3, const float* wl_dev, int n_layers,
+                             int64_t ldh, const float* w, const float* dout, int64_t lddo, float* dh0, float* dh1, float* dh2,
+                             float* dh3, float* dwl, float* dw, float* db, int64_t M, int64_t C, float eps, void* stream) {
+  return sbg_head_bwd(h0, h1, h2, h3, nullptr, n_layers, ldh, w, dout, lddo, dh0, dh1, dh2, dh3, dwl, dw, db, M, C, eps,
+                      (cudaStream_t)stream, wl_dev);
 }
 
 }  // extern "C"

@@ -89,6 +89,7 @@ int layernorm_fwd(const void* x, int x_dtype, int64_t ldx, const float* w, const
 struct HeadPtrs {
   const float* h[4];
   float wl[4];
+  const float* wl_dev;     // when set, the layer weights are read from DEVICE memory (CUDA-graph-capturable training step)
   int n;
 };
 
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(256) sbg_head_kernel(const HeadPtrs hp, long l
     const int c = i * 32 + lane;
     float a = 0.f;
     if (c < C)
-      for (int l = 0; l < hp.n; ++l) a += hp.wl[l] * hp.h[l][(long long)row * ldh + c];
+      for (int l = 0; l < hp.n; ++l) a += (hp.wl_dev ? __ldg(hp.wl_dev + l) : hp.wl[l]) * hp.h[l][(long long)row * ldh + c];
     v[i] = a;
     s += a;
   }
@@ -129,17 +130,18 @@ __global__ void __launch_bounds__(256) sbg_head_kernel(const HeadPtrs hp, long l
 
 int sbg_head_fwd(const float* h0, const float* h1, const float* h2, const float* h3, const float* wl, int n_layers,
                  int64_t ldh, const float* w, const float* b, float* out, int64_t ldo, int64_t M, int64_t C, float eps,
-                 cudaStream_t stream) {
-  AF_CHECK(n_layers >= 1 && n_layers <= 4 && wl, "sbg_head_fwd: n_layers must be 1..4 (got %d)", n_layers);
+                 cudaStream_t stream, const float* wl_dev) {
+  AF_CHECK(n_layers >= 1 && n_layers <= 4 && (wl || wl_dev), "sbg_head_fwd: n_layers must be 1..4 (got %d)", n_layers);
   AF_CHECK(M > 0 && C > 0 && C <= 768, "sbg_head_fwd: unsupported shape M=%lld C=%lld", (long long)M, (long long)C);
   HeadPtrs hp;
   const float* hs[4] = {h0, h1, h2, h3};
   for (int i = 0; i < 4; ++i) {
     hp.h[i] = hs[i];
-    hp.wl[i] = i < n_layers ? wl[i] : 0.f;   // wl is a HOST array of n_layers floats
+    hp.wl[i] = (i < n_layers && wl) ? wl[i] : 0.f;   // wl is a HOST array of n_layers floats
     AF_CHECK(i >= n_layers || hs[i], "sbg_head_fwd: hidden state %d is null", i);
   }
   hp.n = n_layers;
+  hp.wl_dev = wl_dev;
   dim3 grid(((int)M + 7) / 8);
   sbg_head_kernel<768><<<grid, 256, 0, stream>>>(hp, ldh, w, b, out, ldo, (int)M, (int)C, eps);
   AF_CUDA(cudaGetLastError());

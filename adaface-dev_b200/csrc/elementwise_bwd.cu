@@ -332,6 +332,7 @@ struct HeadBwdPtrs {
   const float* h[4];
   float* dh[4];
   float wl[4];
+  const float* wl_dev;     // device copy of the layer weights (used when set)
   int n;
 };
 
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(256) sbg_head_bwd_kernel(const HeadBwdPtrs hp,
       if (c < C) {
 #pragma unroll
         for (int l = 0; l < 4; ++l)
-          if (l < hp.n) m += hp.wl[l] * hp.h[l][(long long)row * ldh + c];
+          if (l < hp.n) m += (hp.wl_dev ? __ldg(hp.wl_dev + l) : hp.wl[l]) * hp.h[l][(long long)row * ldh + c];
       }
       v[i] = m;
       gy[i] = c < C ? dout[(long long)row * lddo + c] : 0.f;
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(256) sbg_head_bwd_kernel(const HeadBwdPtrs hp,
           if (l < hp.n) {
             const long long o = (long long)row * ldh + c;
             dl[l] += dm * hp.h[l][o];
-            hp.dh[l][o] = hp.wl[l] * dm;
+            hp.dh[l][o] = (hp.wl_dev ? __ldg(hp.wl_dev + l) : hp.wl[l]) * dm;
           }
         }
       }
@@ -425,8 +426,8 @@ __global__ void __launch_bounds__(256) sbg_head_bwd_kernel(const HeadBwdPtrs hp,
 
 int sbg_head_bwd(const float* h0, const float* h1, const float* h2, const float* h3, const float* wl, int n_layers, int64_t ldh,
                  const float* w, const float* dout, int64_t lddo, float* dh0, float* dh1, float* dh2, float* dh3, float* dwl,
-                 float* dw, float* db, int64_t M, int64_t C, float eps, cudaStream_t stream) {
-  AF_CHECK(n_layers >= 1 && n_layers <= 4 && wl && w && dout && dwl && dw && db, "sbg_head_bwd: bad arguments");
+                 float* dw, float* db, int64_t M, int64_t C, float eps, cudaStream_t stream, const float* wl_dev) {
+  AF_CHECK(n_layers >= 1 && n_layers <= 4 && (wl || wl_dev) && w && dout && dwl && dw && db, "sbg_head_bwd: bad arguments");
   AF_CHECK(M > 0 && C > 0 && C <= 768, "sbg_head_bwd: unsupported shape M=%lld C=%lld (C <= 768)", (long long)M, (long long)C);
   HeadBwdPtrs hp;
   const float* hs[4] = {h0, h1, h2, h3};
@@ -434,10 +435,11 @@ int sbg_head_bwd(const float* h0, const float* h1, const float* h2, const float*
   for (int i = 0; i < 4; ++i) {
     hp.h[i] = i < n_layers ? hs[i] : nullptr;
     hp.dh[i] = i < n_layers ? dhs[i] : nullptr;
-    hp.wl[i] = i < n_layers ? wl[i] : 0.f;
+    hp.wl[i] = (i < n_layers && wl) ? wl[i] : 0.f;
     AF_CHECK(i >= n_layers || (hs[i] != nullptr && dhs[i] != nullptr), "sbg_head_bwd: null hidden state / gradient %d", i);
   }
   hp.n = n_layers;
+  hp.wl_dev = wl_dev;
   int grid = (int)((M + 7) / 8);
   if (grid > 148 * 2) grid = 148 * 2;
   sbg_head_bwd_kernel<768><<<grid, 256, 0, stream>>>(hp, ldh, w, dout, lddo, dwl, dw, db, (int)M, (int)C, eps);

@@ -62,6 +62,43 @@ int ddim_cfg_step(const float* eps, int64_t n_images, int64_t n_per_image, int h
 }
 
 // ---------------------------------------------------------------------------------------------
+// DoRA column scale (peft DoraLinearLayer / DoraConv2dLayer in eval form): colscale[n] = m[n] / ||W[n,:] + s BA[n,:]||_2,
+// the norm detached as in peft.  One warp per output row; W fp32 | bf16 [N, K] (a convolution weight flattened over cin, kh, kw),
+// BA fp32 [N, K] = B.A from the projection GEMM (NULL: plain ||W||).  Runs once per parameter update -- with the B.A product on
+// the tcgen05 GEMM this removes the last library arithmetic (cuBLAS sgemm + torch reduce) from the training step.
+template <typename TW>
+__global__ void __launch_bounds__(256) dora_colscale_kernel(const TW* __restrict__ W, const float* __restrict__ BA, long long ldba, float s,
+                                                            const float* __restrict__ m, float* __restrict__ out, int N, int K) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= N) return;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float w;
+    if constexpr (sizeof(TW) == 2) w = __bfloat162float(W[(long long)row * K + k]);
+    else w = W[(long long)row * K + k];
+    if (BA) w += s * BA[(long long)row * ldba + k];
+    acc += w * w;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = m[row] / sqrtf(acc);
+}
+
+int dora_colscale(const void* W, int w_dtype, const float* BA, int64_t ldba, float s, const float* m, float* out, int64_t N, int64_t K,
+                  cudaStream_t stream) {
+  AF_CHECK(W && m && out && N > 0 && K > 0, "dora_colscale: null pointer / empty");
+  const unsigned grid = (unsigned)((N + 7) / 8);
+  if (w_dtype == ADAFACE_F32) dora_colscale_kernel<float><<<grid, 256, 0, stream>>>((const float*)W, BA, ldba, s, m, out, (int)N, (int)K);
+  else if (w_dtype == ADAFACE_BF16) dora_colscale_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)W, BA, ldba, s, m, out, (int)N, (int)K);
+  else {
+    set_error("dora_colscale: bad dtype %d", w_dtype);
+    return 1;
+  }
+  AF_CUDA(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // im2col of an NHWC activation for the WEIGHT gradient of a 3x3 convolution adapter (conv-LoRA A matrix, dalc:541-591):
 //   col[(b, y, x), tap * Kc + c] = X[b, y + ky - 1, x + kx - 1, c]   (zero outside the image / for c >= C),  tap = ky * 3 + kx
 // -- the K index of ops.pack_conv3x3_weight, so dA_packed [r, 9 Kc] = dT^T col is one K-major GEMM on the projection kernel.

@@ -33,3 +33,46 @@ def graphed(fn, *example_inputs, warmup=3):
     replay.graph = g
     replay.static_inputs = static_in
     return replay
+
+
+def invalidate_trainable_packs(*modules):
+    """Every module that caches bf16 operand packs of TRAINABLE parameters (LoRA / DoRA adapters, SubjBasisGenerator layers)
+    exposes ``invalidate()``; calling it makes the next forward rebuild the pack from the live parameters."""
+    n = 0
+    for root in modules:
+        for m in root.modules():
+            inv = getattr(m, "invalidate", None)
+            if callable(inv):
+                inv()
+                n += 1
+    return n
+
+
+def graphed_step(fn, *trainable_modules, warmup=2):
+    """CUDA-graph capture of a whole TRAINING step: ``fn()`` runs forward + backward and accumulates into pre-existing ``.grad``
+    buffers (parallel.GradBucketer keeps them at fixed addresses).  The stage-2 iteration is ~14 000 kernel launches issued from
+    Python (35 us each on average); replayed as one graph it is bound by the kernels instead.
+
+    Requirements on ``fn``: no host synchronisation (no .item() / bool(tensor) / .tolist()), no collective (run the gradient
+    all-reduce after the replay), the same control flow every iteration.  The operand packs of trainable parameters are
+    invalidated right before the capture so that their rebuild is PART of the graph: a replay after an optimiser step computes
+    with the updated weights.  Returns ``replay() -> fn's captured return value`` (tensors in the graph's private pool)."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(warmup):
+            invalidate_trainable_packs(*trainable_modules)
+            fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    invalidate_trainable_packs(*trainable_modules)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = fn()
+
+    def replay():
+        g.replay()
+        return out
+
+    replay.graph = g
+    return replay

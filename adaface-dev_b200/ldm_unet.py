@@ -169,7 +169,10 @@ class UNetModel(nn.Module):
             ca.processor_kwargs = {"img_mask": mask, "subj_indices": subj_indices}
         # A7 (dalc:382-394): gradient scale on the skip tensors entering diffusers up_blocks[1:] = output_blocks[num_res_blocks + 1:]
         gradscale = float(extra_info.get("res_hidden_states_gradscale", 1)) if extra_info is not None else 1.0
-        res_grad_scaler = gen_gradient_scaler(gradscale)
+        cache = self.__dict__.setdefault("_grad_scalers", {})      # one scaler per factor, its alpha moved to the device once
+        res_grad_scaler = cache.get(gradscale)                     # (a fresh one per call would stage alpha through the host every time)
+        if res_grad_scaler is None:
+            res_grad_scaler = cache[gradscale] = gen_gradient_scaler(gradscale)
         acts = {}
 
         def grab(li, h, hw_):

@@ -231,6 +231,10 @@ class LoraDoraConv2d(nn.Module):
         nn.init.zeros_(self.lora_B[adapter_name].weight)
         self.lora_magnitude_vector[adapter_name] = _ConvMagnitude(torch.linalg.norm(self.base_layer.weight.detach().float().flatten(1), dim=1))
 
+    def invalidate(self):
+        """Force the next pack() to rebuild from the live parameters (see LoraDoraLinear.invalidate)."""
+        self._pack_key = None
+
     def set_active_adapter(self, adapter_name):
         if adapter_name not in self.lora_A:
             raise KeyError(f"LoraDoraConv2d: unknown adapter {adapter_name!r} (have {list(self.lora_A)})")
@@ -249,14 +253,16 @@ class LoraDoraConv2d(nn.Module):
         key = _ver(A, B, m, W, b)
         if key != self._pack_key:
             with torch.no_grad():
-                Bf = B.float().flatten(1)                                                    # [cout, r]
-                comp = (Bf @ A.float().flatten(1)).view_as(W)                                # B . A as one [cout, cin, kh, kw] kernel
-                wn = torch.linalg.norm((W.float() + self.scaling * comp).flatten(1), dim=1)
+                Bf = B.detach().float().flatten(1)                                           # [cout, r]
+                # ||W + s B.A|| over (cin, kh, kw) with B.A on the projection GEMM (no library arithmetic, graph-capturable)
+                Wf = W.detach().flatten(1)
+                cs = ops.dora_colscale((Wf if Wf.dtype in (torch.float32, torch.bfloat16) else Wf.float()).contiguous(),
+                                       _bf16(A.flatten(1)), _bf16(Bf), self.scaling, m)
                 if self.is_3x3:
                     wp, ap = ops.pack_conv3x3_weight(W), ops.pack_conv3x3_weight(A)
                 else:
                     wp, ap = _bf16(W.flatten(1)), _bf16(A.flatten(1))
-                self._pack = (wp, ap, (Bf * self.scaling).to(torch.bfloat16).contiguous(), (m.float() / wn).contiguous(), _f32(b))
+                self._pack = (wp, ap, (Bf * self.scaling).to(torch.bfloat16).contiguous(), cs, _f32(b))
             self._pack_key = key
         return self._pack
 

@@ -332,7 +332,7 @@ def layernorm(x, w, b, eps=1e-5, out_dtype=torch.bfloat16):
 
 def sbg_head(hs, layer_weights, w, b, eps=1e-5):
     """LayerNorm(sum_l wl[l] * h_l) for up to 4 fp32 [M, C] hidden states (adaface_sbg_head_fwd)."""
-    if not 1 <= len(hs) <= 4 or len(layer_weights) != len(hs):
+    if not 1 <= len(hs) <= 4 or (layer_weights.numel() if torch.is_tensor(layer_weights) else len(layer_weights)) != len(hs):
         raise ValueError("sbg_head: 1..4 hidden states with one weight each")
     M, C = hs[0].shape
     for h in hs:
@@ -340,8 +340,13 @@ def sbg_head(hs, layer_weights, w, b, eps=1e-5):
         if tuple(h.shape) != (M, C) or h.stride(0) != hs[0].stride(0):
             raise ValueError("sbg_head: hidden states must share shape and row stride")
     out = torch.empty((M, C), device=hs[0].device, dtype=torch.float32)
-    wl = (ctypes.c_float * len(hs))(*[float(x) for x in layer_weights])
     ptrs = [_ptr(h) for h in hs] + [ctypes.c_void_p(0)] * (4 - len(hs))
+    if torch.is_tensor(layer_weights):        # device weights (fp32 [n], already normalised): no host read, graph-capturable
+        _need(layer_weights, "layer_weights", torch.float32)
+        _lib.call("adaface_sbg_head_fwd_dev", *ptrs, _ptr(layer_weights), len(hs), hs[0].stride(0), _ptr(w), _ptr(b), _ptr(out),
+                  out.stride(0), M, C, float(eps), _stream())
+        return out
+    wl = (ctypes.c_float * len(hs))(*[float(x) for x in layer_weights])
     _lib.call("adaface_sbg_head_fwd", *ptrs, wl, len(hs), hs[0].stride(0), _ptr(w), _ptr(b), _ptr(out), out.stride(0), M,
               C, float(eps), _stream())
     return out
@@ -467,6 +472,25 @@ def resample2x_bwd(x, hw_low, mode):
     y = torch.empty((B, h * w if mode == 0 else 4 * h * w, C), device=x.device, dtype=torch.bfloat16)
     _lib.call("adaface_resample2x_bwd", _ptr(x), _ptr(y), B, h, w, C, int(mode), _stream())
     return y
+
+
+def dora_colscale(W, A16, B16, scaling, m):
+    """colscale = m / ||W + s B A||_row (adaface_dora_colscale) with the product B A on the projection GEMM: W [N, K] fp32 | bf16
+    contiguous, A16 bf16 [r, K], B16 bf16 [N, r] (UNscaled), m fp32 [N].  Returns fp32 [N].  No library arithmetic."""
+    _need(W, "W")
+    N, K = W.shape
+    if not W.is_contiguous():
+        raise ValueError("dora_colscale: W must be contiguous")
+    rp = (A16.shape[0] + 7) // 8 * 8
+    At = transpose(A16, pad_to=1)                                  # [K, r]
+    if rp != A16.shape[0]:                                         # reduction length must be a multiple of 8 for the GEMM
+        At = torch.nn.functional.pad(At, (0, rp - A16.shape[0]))
+        B16 = torch.nn.functional.pad(B16, (0, rp - B16.shape[1]))
+    BA = proj(B16.contiguous(), At.contiguous(), out_dtype=torch.float32)      # [N, K] = B A
+    out = torch.empty(N, device=W.device, dtype=torch.float32)
+    mf = m.detach().float().contiguous()
+    _lib.call("adaface_dora_colscale", _ptr(W), _dt(W), _ptr(BA), BA.stride(0), float(scaling), _ptr(mf), _ptr(out), N, K, _stream())
+    return out
 
 
 def im2col3x3_tokens(x, hw):
@@ -683,8 +707,13 @@ def sbg_head_bwd(hs, layer_weights, w, dout, eps=1e-5):
     dwl = torch.zeros(4, device=dev, dtype=torch.float32)
     dw = torch.zeros(C, device=dev, dtype=torch.float32)
     db = torch.zeros(C, device=dev, dtype=torch.float32)
-    wl = (ctypes.c_float * n)(*[float(x) for x in layer_weights])
     pad = [ctypes.c_void_p(0)] * (4 - n)
+    if torch.is_tensor(layer_weights):
+        _need(layer_weights, "layer_weights", torch.float32)
+        _lib.call("adaface_sbg_head_bwd_dev", *([_ptr(h) for h in hs] + pad), _ptr(layer_weights), n, C, _ptr(w), _ptr(dout), dout.stride(0),
+                  *([_ptr(d) for d in dhs] + pad), _ptr(dwl), _ptr(dw), _ptr(db), M, C, float(eps), _stream())
+        return dhs, dwl[:n], dw, db
+    wl = (ctypes.c_float * n)(*[float(x) for x in layer_weights])
     _lib.call("adaface_sbg_head_bwd", *([_ptr(h) for h in hs] + pad), wl, n, C, _ptr(w), _ptr(dout), dout.stride(0),
               *([_ptr(d) for d in dhs] + pad), _ptr(dwl), _ptr(dw), _ptr(db), M, C, float(eps), _stream())
     return dhs, dwl[:n], dw, db

@@ -142,6 +142,8 @@ class GradBucketer:
         self._touched = torch.zeros(len(self.params), dtype=torch.int32)
         self._index = {id(p): i for i, p in enumerate(self.params)}
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self.defer = False                       # True: hooks only record which parameters received a gradient (graph capture)
+        self._frozen_touched = None
         self.zero()
 
     def _add_bucket(self, plist):
@@ -155,9 +157,16 @@ class GradBucketer:
             off += p.numel()
         self.buckets.append(b)
 
+    def freeze_touched(self):
+        """After capturing a training step into a CUDA graph (hooks do not run on replay): remember which parameters the captured
+        step gives a gradient to; zero() then restores that set every iteration."""
+        self._frozen_touched = self._touched.clone()
+
     def zero(self):
         """Zero the buckets and point every .grad back at its view (call instead of optimizer.zero_grad())."""
         self._touched.zero_()
+        if self._frozen_touched is not None:
+            self._touched.copy_(self._frozen_touched)
         self._count = {}
         for b in self.buckets:
             b["flat"].zero_()
@@ -167,6 +176,8 @@ class GradBucketer:
 
     def _on_grad(self, p):
         self._touched[self._index[id(p)]] = 1
+        if self.defer:                           # CUDA-graph capture / replay mode: nothing is launched from the hooks
+            return
         c = self._count.get(id(p), 0) + 1
         self._count[id(p)] = c
         if c != self.expected:                   # a parameter used several times per iteration (e.g. 4 denoising steps) is ready

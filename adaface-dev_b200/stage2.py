@@ -53,13 +53,14 @@ class CompDistillStep:
                 "subj_indices": subj_indices, "res_hidden_states_gradscale": self.gradscale, "use_attn_lora": use_attn_lora,
                 "use_ffn_lora": use_ffn_lora, "ffn_lora_adapter_name": self.ffn_adapter if use_ffn_lora else None, "img_mask": None}
         with torch.set_grad_enabled(grad):
-            out = self.w(x[idx], t[idx], (prompt_emb[idx], None, info))
+            sl = slice(idx, idx + 1)             # (a slice, not a list index: no host index tensor, CUDA-graph-capturable)
+            out = self.w(x[sl], t[sl], (prompt_emb[sl], None, info))
         return out, info["ca_layers_activations"]
 
     def denoise(self, x_noisy, t, prompt_emb, uncond_emb, subj_indices_1b):
         """One 'subject-compos' denoising step.  x_noisy [4,4,h,w], t [4], prompt_emb [4,S,768] ordered (ss, sc, sc_rep, mc),
         uncond_emb [4,S,768].  Returns (noise_pred [4,4,h,w], acts = {'ss','sc','sr','mc': ca_layers_activations}, uncond pred)."""
-        ss, sc, sr, mc = [0], [1], [2], [3]
+        ss, sc, sr, mc = 0, 1, 2, 3
         self._consumers("none")
         n_ss, a_ss = self._call(x_noisy, t, prompt_emb, ss, False, subj_indices_1b, False, True, self.use_ffn_lora)
         self._consumers("maps")
@@ -89,7 +90,7 @@ class CompDistillStep:
             for li in L:
                 p_sc, p_sr = a_sc["attn"][li], a_sr["attn"][li]
                 flag = torch.zeros(p_sc.shape[0], p_sc.shape[3], device=p_sc.device)
-                flag[ib, it] = 1
+                flag.index_put_((ib.long(), it.long()), torch.ones(ib.numel(), device=p_sc.device))
                 sums[li] = (p_sc * flag[:, None, None, :]).sum(-1)
                 sq[li] = ((p_sc - p_sr.detach()) ** 2).sum().reshape(1)
                 shp[li] = tuple(p_sc.shape[1:])

@@ -101,6 +101,10 @@ class CLIPEncoderLayer(nn.Module):
         self.layer_norm2 = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
         self._pack_key, self._pack = None, None
 
+    def invalidate(self):
+        """Force the next pack() to rebuild the bf16 operands from the live parameters (see graphs.graphed_step)."""
+        self._pack_key = None
+
     def pack(self):
         a, m = self.self_attn, self.mlp
         ps = (a.q_proj.weight, a.q_proj.bias, a.k_proj.weight, a.k_proj.bias, a.v_proj.weight, a.v_proj.bias,

@@ -577,11 +577,8 @@ def stage2_measurement(torch, a, dev, rank, world, barrier, unet, steps=4, warm=
     pad_mask = torch.zeros(4, S2, 1, device=dev)
     pad_mask[:, 40:] = 1
 
-    def iteration(comm=True):
-        gb_lora.zero()
-        gb_sbg.zero()
-        if not comm:
-            gb_lora.world = gb_sbg.world = 1
+    def fwd_bwd():
+        """Forward + backward of the whole iteration (no collective, no host synchronisation: CUDA-graph-capturable)."""
         ada = sbg(id_embs)                                           # [1, 16, 768], differentiable
         ada_leaf = ada.detach().requires_grad_(True)
 
@@ -591,6 +588,16 @@ def stage2_measurement(torch, a, dev, rank, world, barrier, unet, steps=4, warm=
             return pe
         totals = step.step(x, ts, prompt, uncond, si, fg, emb_mask, pad_mask, sc_fg_mask_percent=0.3)
         ada.backward(ada_leaf.grad)                                  # SubjBasisGenerator backward: its buckets go out as they fill
+        return totals
+
+    replay = None
+
+    def iteration(comm=True):
+        gb_lora.zero()
+        gb_sbg.zero()
+        if not comm:
+            gb_lora.world = gb_sbg.world = 1
+        totals = replay() if replay is not None else fwd_bwd()
         gb_lora.finish()
         gb_sbg.finish()
         gb_lora.world = gb_sbg.world = world
@@ -621,22 +628,49 @@ def stage2_measurement(torch, a, dev, rank, world, barrier, unet, steps=4, warm=
                 dist.all_reduce(b_["flat"])
     t_ar = timed(allreduce_only, 3)[0] if world > 1 else 0.0
     n_par = sum(p_.numel() for p_ in lora_params + sbg_params)
-    tt = torch.tensor([t_full, t_nocomm, t_ar], device=dev, dtype=torch.float64)
+    # ---- the same iteration as ONE CUDA graph (forward + backward of all four denoising steps and the SubjBasisGenerator);
+    #      the all-reduce runs after the replay.  Gradients are compared with the eager iteration's before timing.
+    t_graph = t_graph_nocomm = None
+    graph_check = None
+    if os.environ.get("ADAFACE_BENCH_STAGE2_GRAPH", "1") != "0":
+        iteration(comm=False)
+        ref_grads = [p_.grad.clone() for p_ in (lora_params + sbg_params) if p_.grad is not None][:40]
+        gb_lora.defer = gb_sbg.defer = True
+        gb_lora.zero()
+        gb_sbg.zero()
+        replay = a.graphed_step(fwd_bwd, w, sbg)
+        gb_lora.freeze_touched()
+        gb_sbg.freeze_touched()
+        iteration(comm=False)
+        got = [p_.grad for p_ in (lora_params + sbg_params) if p_.grad is not None][:40]
+        graph_check = max(((g_ - r_).abs().max() / r_.abs().max().clamp_min(1e-20)).item() for g_, r_ in zip(got, ref_grads))
+        t_graph, totals = timed(iteration, n_it)
+        t_graph_nocomm, _ = timed(lambda: iteration(comm=False), n_it) if world > 1 else (t_graph, None)
+    tt = torch.tensor([t_full, t_nocomm, t_ar, t_graph or 0.0, t_graph_nocomm or 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_full, t_nocomm, t_ar = tt.tolist()
+    t_full, t_nocomm, t_ar, tg, tgn = tt.tolist()
+    if t_graph is not None:
+        t_graph, t_graph_nocomm = tg, tgn
     finite = all(bool(torch.isfinite(torch.as_tensor(v)).all()) for v in totals.values())
     gb_lora.close()
     gb_sbg.close()
+    best = t_graph if t_graph is not None else t_full
+    best_nocomm = t_graph_nocomm if t_graph is not None else t_nocomm
     return {"metric": "stage-2 compositional-distillation iterations/s (4 denoising steps, capture + backward, DDP all-reduce)",
-            "unit": "iterations/s", "value": world * 1e3 / t_full, "ms_per_iteration": t_full, "scaling": "weak", "n_gpus": world,
-            "ms_per_iteration_without_collectives": t_nocomm, "allreduce_alone_ms": t_ar,
-            "allreduce_exposed_share": max(0.0, (t_full - t_nocomm) / t_full) if world > 1 else 0.0,
+            "unit": "iterations/s", "value": world * 1e3 / best, "ms_per_iteration": best, "scaling": "weak", "n_gpus": world,
+            "ms_per_iteration_without_collectives": best_nocomm, "allreduce_alone_ms": t_ar,
+            "allreduce_exposed_share": max(0.0, (best - best_nocomm) / best) if world > 1 else 0.0,
+            "eager": {"ms_per_iteration": t_full, "ms_per_iteration_without_collectives": t_nocomm,
+                      "what": "the same iteration with every kernel launched from Python; its all-reduce overlaps the backward (GradBucketer hooks)"},
+            "cuda_graph": None if t_graph is None else {"ms_per_iteration": t_graph, "max_rel_grad_diff_vs_eager": graph_check,
+                                                        "what": "forward + backward of the whole iteration replayed as one CUDA graph; all-reduce after the replay"},
             "allreduce_bytes": int(n_par * 4), "trainable_params": {"lora": int(sum(p_.numel() for p_ in lora_params)),
                                                                       "subj_basis_generator": int(sum(p_.numel() for p_ in sbg_params))},
             "buckets": len(gb_lora.buckets) + len(gb_sbg.buckets), "kernels_per_iteration": int(launches),
             "config": {"denoising_steps": steps, "instances": "ss, sc, sc_rep, mc (B=1 slices) + uncond B=4", "ctx_tokens": S2, "lora_rank": 192,
-                       "captured_layers": [22, 23, 24], "fused_capture_consumers": step.fused, "launch": "eager (Python launches)"},
+                       "captured_layers": [22, 23, 24], "fused_capture_consumers": step.fused,
+                       "launch": "one CUDA graph per iteration" if t_graph is not None else "eager (Python launches)"},
             "losses": {k_: float(v_) for k_, v_ in totals.items()}, "checks": {"finite": finite}}
 
 

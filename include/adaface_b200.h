@@ -295,6 +295,22 @@ int adaface_attn_cross_consume_bwd(const void* q, int64_t q_sb, int64_t q_sn, co
 int adaface_ddim_cfg_step(const float* eps, int64_t n_images, int64_t n_per_image, int has_uncond, const float* x,
                           const float* coef, const float* noise, float* x_prev, float* x_dup, float* pred_x0, void* stream);
 
+/* adaface_sbg_head_fwd / _bwd with the (already sum-normalised) layer weights read from DEVICE memory (wl_dev: fp32
+ * [n_layers]) instead of a host array: no host read of hidden_state_layer_weights per step, so the SubjBasisGenerator
+ * training step can be captured into a CUDA graph. */
+int adaface_sbg_head_fwd_dev(const float* h0, const float* h1, const float* h2, const float* h3, const float* wl_dev, int n_layers,
+                             int64_t ldh, const float* w, const float* b, float* out, int64_t ldo, int64_t M, int64_t C, float eps,
+                             void* stream);
+int adaface_sbg_head_bwd_dev(const float* h0, const float* h1, const float* h2, const float* h3, const float* wl_dev, int n_layers,
+                             int64_t ldh, const float* w, const float* dout, int64_t lddo, float* dh0, float* dh1, float* dh2,
+                             float* dh3, float* dwl, float* dw, float* db, int64_t M, int64_t C, float eps, void* stream);
+
+/* DoRA column scale of a LoRA adapter (peft DoraLinearLayer, eval form): out[n] = m[n] / ||W[n,:] + s BA[n,:]||_2.
+ * W fp32 | bf16 [N, K] contiguous (a convolution weight flattened over cin, kh, kw); BA fp32 [N, K] with row pitch ldba = the
+ * product B.A (from adaface_proj_lora_fwd), or NULL; m, out fp32 [N]. */
+int adaface_dora_colscale(const void* W, int w_dtype, const float* BA, int64_t ldba, float s, const float* m, float* out, int64_t N,
+                          int64_t K, void* stream);
+
 /* im2col for the weight gradient of a 3x3 convolution adapter (conv-LoRA A matrix; adaface/diffusers_attn_lora_capture.py:541-591,
  * peft lora.Conv2d): x bf16 NHWC [B, H, W, C] -> col bf16 [B*H*W, 9*Kc], Kc = C rounded up to 64,
  * col[p, (ky*3+kx)*Kc + c] = x[b, y+ky-1, x+kx-1, c] (zero outside the image and for c >= C) -- the K order of the packed

@@ -183,3 +183,57 @@ def test_comp_distill_step_fused_equals_unfused():
     record("stage2", "comp_distill_step_small_unet", "fused vs unfused: worst LoRA-parameter gradient rel", worst, GRAD_TOL)
     assert worst < GRAD_TOL
     assert any("conv1_lora_A" in n_ for n_ in pf) and any("cross_attn_scale_factor" in n_ for n_ in pf)
+
+
+def test_graphed_training_step_equals_eager():
+    """graphs.graphed_step: forward + backward of the four-instance step captured into ONE CUDA graph gives the eager step's
+    gradients bit for bit (same kernels, same order), also after the adapters were updated in place (the operand packs of the
+    trainable parameters are rebuilt inside the graph)."""
+    import adaface_dev_b200 as a
+    from adaface_dev_b200.stage2 import CompDistillStep
+    x, ts, prompt, uncond, si, fg, emb, pad = _step_inputs()
+    w, _ = _small_wrapper(use_ffn_lora=True)
+    w.diffusion_model.captured_layer_indices = (7, 8)
+    gen = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for n_, p_ in w.unet_lora_modules.named_parameters():
+            if "lora_B" in n_ or "lora_A" in n_:
+                p_.copy_((torch.randn(p_.shape, generator=gen) * (0.02 if "lora_B" in n_ else p_[0].numel() ** -0.5)).to(p_.device))
+    step = CompDistillStep(w, fused_consumers=True, use_ffn_lora=True)
+    step.align_layers = (7, 8)
+    params = w.trainable_parameters()
+    gb = a.parallel.GradBucketer(params, expected_uses=len(ts))
+    pe = prompt.cuda()
+    pe_grad = torch.zeros_like(pe)
+
+    def fwd_bwd():
+        leaf = pe.detach().clone().requires_grad_(True)
+        tot = step.step(x, ts, lambda: leaf * 1.0, uncond, si, fg, emb, pad, sc_fg_mask_percent=0.3)
+        pe_grad.copy_(leaf.grad)
+        return tot
+
+    def run(replay=None):
+        gb.zero()
+        tot = replay() if replay is not None else fwd_bwd()
+        gb.finish()
+        return {k_: float(v_) for k_, v_ in tot.items()}, pe_grad.clone(), [None if p_.grad is None else p_.grad.clone() for p_ in params]
+
+    t0, g0, p0 = run()
+    gb.defer = True
+    gb.zero()
+    replay = a.graphed_step(fwd_bwd, w)
+    gb.freeze_touched()
+    t1, g1, p1 = run(replay)
+    assert t0 == t1 and torch.equal(g0, g1)
+    assert all((u is None) == (v is None) and (u is None or torch.equal(u, v)) for u, v in zip(p0, p1))
+    with torch.no_grad():                                   # an "optimiser step" in place, then both paths again
+        for p_ in params:
+            if p_.grad is not None:
+                p_.add_(p_.grad, alpha=-1e-2)
+    t2, g2, p2 = run(replay)
+    gb.defer = False
+    gb._frozen_touched = None
+    t3, g3, p3 = run()
+    assert t2 != t1 and t2 == t3 and torch.equal(g2, g3)
+    assert all((u is None) == (v is None) and (u is None or torch.equal(u, v)) for u, v in zip(p2, p3))
+    gb.close()
