@@ -366,6 +366,31 @@ def build_sbg_case(name):
     return case
 
 
+# The two CLIP text encoders around the path, pinned to the reference's own functions:
+#   "arc2face_id2img": Arc2Face_ID2AdaPrompt.map_init_id_to_img_prompt_embs (adaface/face_id_to_ada_prompt.py:680-724)
+#   "sd_text_encoder": text_model_forward / encoder_forward / embeddings_forward (ldm/modules/encoders/modules.py:180-338)
+# Both reuse the seeded 12-layer CLIP weights of the "sbg_m1" case.
+TEXT_CASES = {
+    "arc2face_id2img": dict(seed=91, N=3),
+    "sd_text_encoder": dict(seed=92, B=2),
+}
+ARC2FACE_PROMPT_IDS = [49406, 1125, 539, 320, 1014, 2533] + [49407] * 16          # <bos> photo of a id person <eos> + padding -> 22
+
+
+def build_text_case(name):
+    sp = TEXT_CASES[name]
+    rng = np.random.default_rng(sp["seed"])
+    case = dict(spec=sp)
+    case["w"] = build_sbg_case("sbg_m1")["w"]
+    if name == "arc2face_id2img":
+        case["extra_rows"] = {1014: normal(rng, (E,), 0.02), 2533: normal(rng, (E,), 0.02)}       # "id", "person"
+        ids = rng.standard_normal((sp["N"], 512)).astype(np.float32)
+        case["init_id_embs"] = bf16r(ids / np.linalg.norm(ids, axis=1, keepdims=True))
+    else:
+        case["ada"] = normal(rng, (sp["B"], 16, E), 0.5)
+    return case
+
+
 def checksum(obj):
     """Order-stable float64 checksum of every array in a (nested) case dict."""
     if obj is None:

@@ -442,6 +442,97 @@ def run_sbg_cases():
         save(name, case, {"out": out})
 
 
+def run_text_cases():
+    """the reference's own Arc2Face ID -> image-prompt mapping and its patched SD text-encoder forward."""
+    import torch.nn.functional as F2  # noqa: F401
+    # ---- Arc2Face_ID2AdaPrompt.map_init_id_to_img_prompt_embs, run verbatim on an instance built without the network-bound __init__
+    _mod("ConsistentID")
+    _mod("ConsistentID.lib")
+    _mod("ConsistentID.lib.pipeline_ConsistentID", ConsistentIDPipeline=type("ConsistentIDPipeline", (), {}))
+    _mod("insightface")
+    _mod("insightface.app", FaceAnalysis=type("FaceAnalysis", (), {}))
+    if "cv2" not in sys.modules:
+        try:
+            import cv2  # noqa: F401
+        except Exception:
+            _mod("cv2")
+    import adaface.util as au
+    for nm in ("pad_image_obj_to_square", "calc_stats", "patch_clip_image_encoder_with_mask"):
+        setattr(au, nm, lambda *a, **k: None)
+    au.CLIPVisionModelWithMask = type("CLIPVisionModelWithMask", (), {})
+    import adaface.face_id_to_ada_prompt as f2a
+
+    case = C.build_text_case("arc2face_id2img")
+    w = case["w"]
+    rows = dict(w["token_emb_rows"])
+    rows.update(case["extra_rows"])
+    w2 = dict(w)
+    w2["token_emb_rows"] = rows
+    enc = f2a.Arc2Face_ID2AdaPrompt.__new__(f2a.Arc2Face_ID2AdaPrompt)
+    nn.Module.__init__(enc)
+    enc.dtype, enc.id_img_prompt_max_length = torch.float32, 22
+    enc.text_to_image_prompt_encoder = build_ref_text_model(w2, [1] * 12)
+    ids22 = torch.tensor(C.ARC2FACE_PROMPT_IDS)
+
+    class _Tok:
+        def encode(self, text, add_special_tokens=False):
+            assert text == "id"
+            return [1014]
+
+        def __call__(self, text, **kw):
+            assert text == "photo of a id person" and kw.get("max_length") == 22
+            return types.SimpleNamespace(input_ids=ids22.unsqueeze(0))
+    enc.tokenizer = _Tok()
+    with torch.no_grad():
+        out = enc.map_init_id_to_img_prompt_embs(T(case["init_id_embs"]))
+    save("arc2face_id2img", case, {"out": out})
+
+    # ---- the patched CLIP text model of FrozenCLIPEmbedder (modules.py:180-338): embeddings_forward / encoder_forward /
+    #      text_model_forward verbatim.  HF's CLIPEncoderLayer (transformers >= 4.44 API, absent here in that form) is stood in by
+    #      a pre-LN residual block over HF's own LayerNorm / CLIPMLP and the reference's CLIPAttentionMKV(multiplier=1), whose
+    #      arithmetic at M = 1 is HF CLIPAttention's (RESTATED call signature only).
+    import ldm.modules.encoders.modules as M
+    case = C.build_text_case("sd_text_encoder")
+    w = case["w"]
+    ref = build_ref_text_model(w, [1] * 12)
+    tm = ref.text_model
+    layers = tm.encoder.layers
+
+    class _Layer444(nn.Module):
+        def __init__(self, layer):
+            super().__init__()
+            self.l = layer
+
+        def forward(self, hidden_states, attention_mask, causal_attention_mask, output_attentions=False):
+            r = hidden_states
+            h = r + self.l.self_attn(self.l.layer_norm1(hidden_states), attention_mask, causal_attention_mask, False)[0]
+            return (h + self.l.mlp(self.l.layer_norm2(h)),)
+
+    class _Enc(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.layers = nn.ModuleList([_Layer444(l_) for l_ in layers])
+            self.config = types.SimpleNamespace(output_attentions=False, output_hidden_states=False, use_return_dict=True)
+    enc_mod = _Enc()
+    enc_mod.forward = types.MethodType(M.encoder_forward, enc_mod)
+    emb = tm.embeddings
+    if not hasattr(emb, "position_ids"):
+        emb.position_ids = torch.arange(C.NPOS).unsqueeze(0)
+    emb.forward = types.MethodType(M.embeddings_forward, emb)
+    text_model = types.SimpleNamespace(config=enc_mod.config, embeddings=emb, encoder=enc_mod, final_layer_norm=tm.final_layer_norm,
+                                       last_layers_skip_weights=[0.5, 0.5])
+    ada = T(case["ada"])
+
+    def splice(input_ids, embs):
+        embs = embs.clone()
+        embs[:, 4:20] = ada
+        return embs
+    ids = torch.tensor([C.TEMPLATE_IDS] * case["spec"]["B"])
+    with torch.no_grad():
+        out = M.text_model_forward(text_model, input_ids=ids, embedding_manager=splice)
+    save("sd_text_encoder", case, {"out": out})
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_grad_enabled(True)
@@ -463,3 +554,5 @@ if __name__ == "__main__":
         run_closs_cases()
     if only in ("", "sbg"):
         run_sbg_cases()
+    if only in ("", "text"):
+        run_text_cases()

@@ -293,3 +293,36 @@ def test_chan_major_and_sbg_head():
     out = ops().sbg_head(hs, wl, w, b)
     ref = F.layer_norm(sum(a * h for a, h in zip(wl, hs)), (768,), w, b, 1e-5)
     assert maxerr(out, ref) < 1e-4
+
+
+def test_dora_pack_matches_peft_formula():
+    """LoraDoraLinear.pack(): A, s*B and colscale = m / ||W + s B A||_row reproduce the oracle's
+    lora_dora_linear when applied as y = colscale o (x W^T + (x A^T)(sB)^T) + b."""
+    torch.manual_seed(0)
+    import oracle
+    import adaface_dev_b200 as a
+    base = torch.nn.Linear(48, 32).cuda()
+    lora = a.LoraDoraLinear(base, r=8, lora_alpha=2).cuda()
+    with torch.no_grad():
+        lora.lora_B["default"].weight.normal_(std=0.05)
+        lora.lora_magnitude_vector["default"].weight.mul_(1.1)
+    A16, Bs16, cs = lora.pack()
+    assert A16.dtype == torch.bfloat16 and Bs16.dtype == torch.bfloat16 and cs.dtype == torch.float32
+    x = torch.randn(5, 48).cuda()
+    y = cs * (x @ base.weight.T + (x @ A16.float().T) @ Bs16.float().T) + base.bias
+    c_ = lambda t_: t_.detach().cpu()
+    ref = oracle.lora_dora_linear(c_(x), c_(base.weight), c_(base.bias), c_(lora.lora_A["default"].weight), c_(lora.lora_B["default"].weight),
+                                  c_(lora.lora_magnitude_vector["default"].weight), lora.scaling)
+    assert (y.detach().cpu() - ref).abs().max().item() < 2e-2          # bf16 rounding of A and s*B only
+    # the DoRA column scale itself (adaface_dora_colscale + B.A on the projection GEMM) against fp32 torch
+    wn = torch.linalg.norm(base.weight.float() + lora.scaling * lora.lora_B["default"].weight.float() @ lora.lora_A["default"].weight.float(), dim=1)
+    assert ((cs - lora.lora_magnitude_vector["default"].weight.float() / wn).abs().max() / cs.abs().max()).item() < 2e-3
+    # identity at init (peft: B = 0, m = ||W||_row)
+    fresh = a.LoraDoraLinear(torch.nn.Linear(48, 32).cuda(), r=8, lora_alpha=2).cuda()
+    _, Bs0, cs0 = fresh.pack()
+    assert Bs0.abs().max().item() == 0 and (cs0 - 1).abs().max().item() < 1e-6
+    # the pack is cached until a parameter changes
+    assert lora.pack()[0] is A16
+    with torch.no_grad():
+        lora.lora_A["default"].weight.add_(1.0)
+    assert lora.pack()[0] is not A16

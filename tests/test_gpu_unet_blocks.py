@@ -12,15 +12,23 @@ import torch
 import cases as C
 from oracle import unet_blocks_oracle as ub
 from mirror_utils import _T
-from parity_log import record
+from parity_log import record, log_err
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
+def serr(a, ref):
+    """max-abs error per unit of output scale, err / max(1, max|ref|) -- see tests/test_gpu_parity.py::serr."""
+    r = torch.from_numpy(ref) if isinstance(ref, np.ndarray) else ref
+    return err(a, ref) / max(1.0, r.float().abs().max().item())
+
+
 def err(a, ref):
     ref = torch.from_numpy(ref) if isinstance(ref, np.ndarray) else ref
-    return (a.detach().float().cpu() - ref.float()).abs().max().item()
+    e_ = (a.detach().float().cpu() - ref.float()).abs().max().item()
+    log_err(e_, ref)
+    return e_
 
 
 def rnd(shape, seed, scale=1.0):
@@ -167,7 +175,7 @@ def test_unet_block_vs_reference_golden(name):
             conv.bias.copy_(_T(w["conv_b"]))
             out = m(_T(case["x"]))
     assert out.dtype == torch.float32 and tuple(out.shape) == g["out"].shape
-    assert err(out, g["out"]) < 3e-2          # bf16 activations between the two convolutions, output magnitude ~2
+    assert serr(out, g["out"]) < 2e-2         # outputs reach |5.3|: bf16 half-ulp 1.6e-2 there
 
 
 def test_resblock_tokens_entry_and_full_size():
@@ -185,7 +193,7 @@ def test_resblock_tokens_entry_and_full_size():
     _load_res(m, {k: v.numpy() for k, v in w.items()})
     with torch.no_grad():
         out = m.forward_tokens(nhwc(x), emb.cuda(), (h, wd))
-    assert out.dtype == torch.bfloat16 and err(nchw(out, (h, wd)), ref) < 3e-2
+    assert out.dtype == torch.bfloat16 and serr(nchw(out, (h, wd)), ref) < 2e-2
 
 
 def test_timestep_embedding_vs_oracle():
@@ -219,9 +227,9 @@ def test_unet_vs_reference_golden(name):
     assert out.dtype == torch.float32 and tuple(out.shape) == g["out"].shape
     ref = torch.from_numpy(g["out"])
     rel = ((out.cpu() - ref).norm() / ref.norm()).item()
-    record("unet", name, "eps [B,4,h,w]", err(out, ref), 6e-2, f"rel-L2 {rel:.2e}; ref max-abs {ref.abs().max().item():.2f}")
+    record("unet", name, "eps [B,4,h,w]: max-abs err / max(1, max|ref|)", serr(out, ref), 2e-2, f"abs {err(out, ref):.3f}; rel-L2 {rel:.2e}; ref max-abs {ref.abs().max().item():.2f}")
     # eight (small) / 25 (SD-1.5) bf16 blocks deep (the reference runs fp16 under autocast): output std 0.56, max 2.4
-    assert err(out, ref) < 6e-2 and rel < 2e-2, (err(out, ref), rel)
+    assert serr(out, ref) < 2e-2 and rel < 2e-2, (err(out, ref), rel)
     if sp_big:
         # SD-1.5 itself (BASELINE config 3's size): captured layers are the reference's own 22, 23, 24 (openaimodel.py:853)
         info = {"capture_ca_activations": True}
@@ -270,7 +278,7 @@ def test_lora_dora_conv_vs_oracle(k):
     with torch.no_grad():
         out = m(x.cuda())
     assert out.dtype == torch.float32 and tuple(out.shape) == (B, cout, h, w)
-    assert err(out, ref) < 3e-2                      # bf16 adapter branch T = conv(x, A) feeding the rank-192 tail
+    assert serr(out, ref) < 2e-2                     # bf16 adapter branch T = conv(x, A) feeding the rank-192 tail
     assert {"base_layer.weight", "lora_A.default.weight", "lora_B.default.weight", "lora_magnitude_vector.default.weight"} <= set(m.state_dict())
     # identity at init (peft: B = 0, magnitude = ||W||): the adapter reproduces the base convolution
     fresh = a.LoraDoraConv2d(base, r=192, lora_alpha=16).cuda().eval()
@@ -406,3 +414,31 @@ def test_spatial_transformer_context_gradient_vs_oracle():
     assert out.requires_grad and err(out, g["out"]) < 3e-2
     out.backward(G.cuda())
     assert gerr(ctx.grad, ref) < 3e-2
+
+
+def test_conv_dora_pack_matches_peft_formula():
+    """LoraDoraConv2d.pack(): packed W / A, s*B and colscale = m / ||W + s B.A|| reproduce the oracle's lora_dora_conv when
+    applied as y = colscale o (conv(x, W) + conv1x1(conv(x, A), sB)) + b; identity at initialisation."""
+    from oracle import unet_blocks_oracle as ub
+    import adaface_dev_b200 as a
+    torch.manual_seed(0)
+    for k in (3, 1):
+        base = torch.nn.Conv2d(16, 24, k, padding=k // 2).cuda()
+        lora = a.LoraDoraConv2d(base, r=8, lora_alpha=4).cuda()
+        wp0, ap0, bs0, cs0, b0 = lora.pack()
+        assert bs0.abs().max().item() == 0 and (cs0 - 1).abs().max().item() < 1e-5 and lora.pack()[0] is wp0
+        with torch.no_grad():
+            lora.lora_B["default"].weight.normal_(std=0.2)
+            lora.lora_magnitude_vector["default"].weight.mul_(1.2)
+        wp, ap, bs, cs, b = lora.pack()
+        assert wp is not wp0 and wp.dtype == torch.bfloat16 and cs.dtype == torch.float32
+        assert tuple(wp.shape) == ((24, 9 * 64) if k == 3 else (24, 16)) and tuple(ap.shape) == ((8, 9 * 64) if k == 3 else (8, 16))
+        x = torch.randn(2, 16, 5, 4)
+        c_ = lambda t_: t_.detach().float().cpu()
+        A, B = c_(lora.lora_A["default"].weight), c_(lora.lora_B["default"].weight)
+        conv = (lambda t, w: ub.conv3x3(t, w, None)) if k == 3 else (lambda t, w: torch.einsum("bchw,oc->bohw", t, w[:, :, 0, 0]))
+        y = c_(cs)[None, :, None, None] * (conv(x, c_(base.weight)) + torch.einsum("bchw,oc->bohw", conv(x, A), c_(bs))) + c_(b)[None, :, None, None]
+        ref = ub.lora_dora_conv(x, c_(base.weight), c_(base.bias), A, B, c_(lora.lora_magnitude_vector["default"].weight), lora.scaling)
+        assert (y - ref).abs().max().item() < 2e-2          # bf16 rounding of s*B only
+    with pytest.raises(NotImplementedError):
+        a.LoraDoraConv2d(torch.nn.Conv2d(8, 8, 3, stride=2, padding=1))

@@ -13,33 +13,6 @@ import oracle
 import adaface_dev_b200 as a
 
 
-def test_dora_pack_matches_peft_formula():
-    """LoraDoraLinear.pack(): A, s*B and colscale = m / ||W + s B A||_row reproduce the oracle's
-    lora_dora_linear when applied as y = colscale o (x W^T + (x A^T)(sB)^T) + b."""
-    torch.manual_seed(0)
-    base = torch.nn.Linear(48, 32)
-    lora = a.LoraDoraLinear(base, r=8, lora_alpha=2)
-    with torch.no_grad():
-        lora.lora_B["default"].weight.normal_(std=0.05)
-        lora.lora_magnitude_vector["default"].weight.mul_(1.1)
-    A16, Bs16, cs = lora.pack()
-    assert A16.dtype == torch.bfloat16 and Bs16.dtype == torch.bfloat16 and cs.dtype == torch.float32
-    x = torch.randn(5, 48)
-    y = cs * (x @ base.weight.T + (x @ A16.float().T) @ Bs16.float().T) + base.bias
-    ref = oracle.lora_dora_linear(x, base.weight, base.bias, lora.lora_A["default"].weight, lora.lora_B["default"].weight,
-                                  lora.lora_magnitude_vector["default"].weight, lora.scaling)
-    assert (y - ref).abs().max().item() < 2e-2          # bf16 rounding of A and s*B only
-    # identity at init (peft: B = 0, m = ||W||_row)
-    fresh = a.LoraDoraLinear(torch.nn.Linear(48, 32), r=8, lora_alpha=2)
-    _, Bs0, cs0 = fresh.pack()
-    assert Bs0.abs().max().item() == 0 and (cs0 - 1).abs().max().item() < 1e-6
-    # the pack is cached until a parameter changes
-    assert lora.pack()[0] is A16
-    with torch.no_grad():
-        lora.lora_A["default"].weight.add_(1.0)
-    assert lora.pack()[0] is not A16
-
-
 def test_img_mask_to_key_mask_follows_dalc_254_273():
     """Nearest resize to sqrt(N) x sqrt(N), key mask, dropped for the WHOLE batch if any instance's mask is all zero."""
     rng = np.random.default_rng(3)
@@ -199,32 +172,6 @@ def test_unet_mirror_structure_matches_reference_layout():
     x = torch.zeros(1, 4, 8, 8)
     with pytest.raises(RuntimeError):
         m(x, torch.zeros(1), context=torch.zeros(1, 77, 768))            # CPU tensors: there is no fallback
-
-
-def test_conv_dora_pack_matches_peft_formula():
-    """LoraDoraConv2d.pack(): packed W / A, s*B and colscale = m / ||W + s B.A|| reproduce the oracle's lora_dora_conv when
-    applied as y = colscale o (conv(x, W) + conv1x1(conv(x, A), sB)) + b; identity at initialisation."""
-    from oracle import unet_blocks_oracle as ub
-    torch.manual_seed(0)
-    for k in (3, 1):
-        base = torch.nn.Conv2d(16, 24, k, padding=k // 2)
-        lora = a.LoraDoraConv2d(base, r=8, lora_alpha=4)
-        wp0, ap0, bs0, cs0, b0 = lora.pack()
-        assert bs0.abs().max().item() == 0 and (cs0 - 1).abs().max().item() < 1e-6 and lora.pack()[0] is wp0
-        with torch.no_grad():
-            lora.lora_B["default"].weight.normal_(std=0.2)
-            lora.lora_magnitude_vector["default"].weight.mul_(1.2)
-        wp, ap, bs, cs, b = lora.pack()
-        assert wp is not wp0 and wp.dtype == torch.bfloat16 and cs.dtype == torch.float32
-        assert tuple(wp.shape) == ((24, 9 * 64) if k == 3 else (24, 16)) and tuple(ap.shape) == ((8, 9 * 64) if k == 3 else (8, 16))
-        x = torch.randn(2, 16, 5, 4)
-        A, B = lora.lora_A["default"].weight.detach(), lora.lora_B["default"].weight.detach()
-        conv = (lambda t, w: ub.conv3x3(t, w, None)) if k == 3 else (lambda t, w: torch.einsum("bchw,oc->bohw", t, w[:, :, 0, 0]))
-        y = cs[None, :, None, None] * (conv(x, base.weight.detach()) + torch.einsum("bchw,oc->bohw", conv(x, A), bs.float())) + b[None, :, None, None]
-        ref = ub.lora_dora_conv(x, base.weight.detach(), base.bias.detach(), A, B, lora.lora_magnitude_vector["default"].weight.detach(), lora.scaling)
-        assert (y - ref).abs().max().item() < 2e-2          # bf16 rounding of s*B only
-    with pytest.raises(NotImplementedError):
-        a.LoraDoraConv2d(torch.nn.Conv2d(8, 8, 3, stride=2, padding=1))
 
 
 def test_unet_loads_the_unet_part_of_an_ldm_checkpoint():

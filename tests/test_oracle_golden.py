@@ -221,3 +221,32 @@ def test_ddim_oracle_matches_reference_sampler(name):
     assert np.array_equal(pred.numpy(), g["pred_x0_last"])
     if sp["steps"] == 50:
         assert list(sched["timesteps"][:3]) == [1, 21, 41] and sched["timesteps"][-1] == 981        # ddim.py:29-35
+
+
+def test_arc2face_oracle_matches_reference_function():
+    """SURVEY 8f row 3 (first half) PINNED: oracle.arc2face_id_to_img_prompt against the reference's own
+    Arc2Face_ID2AdaPrompt.map_init_id_to_img_prompt_embs (adaface/face_id_to_ada_prompt.py:680-724), run verbatim by make_golden.py."""
+    case = C.build_text_case("arc2face_id2img")
+    g = load("arc2face_id2img", case)
+    t = C.to_torch({k: v for k, v in case.items() if k != "spec"})
+    w = t["w"]
+    rows = {int(k): v for k, v in w["token_emb_rows"].items()}
+    rows.update({int(k): v for k, v in t["extra_rows"].items()})
+    prompt = torch.stack([rows[i] for i in C.ARC2FACE_PROMPT_IDS])
+    assert list(oracle.ARC2FACE_PROMPT_IDS) == list(C.ARC2FACE_PROMPT_IDS)
+    out = oracle.arc2face_id_to_img_prompt(w, t["init_id_embs"], prompt_embs=prompt)
+    close(out, g["out"], atol=1e-4, what="arc2face id -> image prompt")
+
+
+def test_sd_text_encoder_oracle_matches_reference_function():
+    """SURVEY 8f row 3 (second half) PINNED: the oracle's CLIP loop with the [0.5, 0.5] last-layers weighting against the reference's
+    patched text_model_forward / encoder_forward / embeddings_forward (ldm/modules/encoders/modules.py:180-338) with an
+    EmbeddingManager-style splice of 16 ada tokens."""
+    case = C.build_text_case("sd_text_encoder")
+    g = load("sd_text_encoder", case)
+    t = C.to_torch({k: v for k, v in case.items() if k != "spec"})
+    w = t["w"]
+    tok = w["template_embs"].unsqueeze(0).repeat(case["spec"]["B"], 1, 1)
+    tok[:, 4:20] = t["ada"]
+    out = oracle.clip_text_wrapper_forward(w, tok, torch.tensor([[0.5], [0.5]]))
+    close(out, g["out"], atol=1e-4, what="SD text encoder")
