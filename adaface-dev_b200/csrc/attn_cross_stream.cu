@@ -367,14 +367,24 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_cross_stream_kernel(const Ca
         }
       }
       if (p.ref_prob) {
+        // the reference rows of this warp tile are one contiguous block of nrows * S floats: bring it in with coalesced
+        // 16-byte loads through the warp's staging slab (per-thread 4-byte loads at stride S ran at 1/3 of the speed)
         const float* ref = p.ref_prob + (((long long)b0 * p.H + h) * p.Lq + row0) * S;
+        const int n = nrows * S;
+        __syncwarp();                          // the slab's previous contents (prob staging) have been stored
+        if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(ref) & 15) == 0) {
+          for (int x = lane; x < n / 4; x += 32) reinterpret_cast<float4*>(st)[x] = __ldg(reinterpret_cast<const float4*>(ref) + x);
+        } else {
+          for (int x = lane; x < n; x += 32) st[x] = __ldg(ref + x);
+        }
+        __syncwarp();
 #pragma unroll
         for (int nt = 0; nt < NTS; ++nt) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int c = nt * 8 + 2 * t + (e & 1), r = g + (e >> 1) * 8;
             if (c < S && r < nrows) {
-              const float df = acc_s[nt][e] - __ldg(ref + r * S + c);
+              const float df = acc_s[nt][e] - st[r * S + c];
               sq_acc += df * df;
             }
           }
@@ -439,7 +449,7 @@ template <int D, int NTS, bool MIX, bool F32IN>
 static int launch_cs(CapParams& p, cudaStream_t stream) {
   using A = AttDims<D>;
   constexpr int NI = MIX ? 2 : 1, NP = F32IN ? 2 : 1, KROWS = NTS * 8;
-  const bool maps = p.prob || p.score || p.prob_subj;
+  const bool maps = p.prob || p.score || p.prob_subj || p.ref_prob;      // needs the per-warp fp32 staging slab
   const int smem = ((NP + 1) * NI * KROWS + 4 * NP * NI * 16) * A::LD * 2 + KROWS * 4 + 2 * KROWS + (maps ? 4 * 16 * p.S * 4 : 0) + 16;
   AF_CHECK(smem <= 227 * 1024, "attn_cross_stream: %d bytes of shared memory exceed the SM", smem);
   static int configured_smem[AF_MAX_DEV] = {0}, ctas_per_sm[AF_MAX_DEV][2] = {{0, 0}};      // per device

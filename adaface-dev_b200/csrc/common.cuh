@@ -68,6 +68,8 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 // 4-D view {d, heads, tokens, batch} of a bf16 tensor (element strides: head = sh, token = sn, batch = sb;
 // sh = d, sn = H*d for the reference layout [B, L, H*d]; sh = L*d, sn = d for a head-major [B, H, L, d] buffer) with a {64, 1, box_rows, 1} box and 128-byte swizzle.  Columns >= d inside the 64-wide box are
 // out of bounds and therefore ZERO-filled by TMA: head dims 40 / 80 / 160 need no padding in HBM.
+// bf16 row-major [rows, cols] OUTPUT, {32 x 32} boxes, 64-byte swizzle: the target of the GEMM epilogue's TMA stores.
+int make_tmap_bf16_store32(CUtensorMap* out, void* base, uint64_t rows, uint64_t cols, uint64_t ld);
 int make_tmap_bf16_heads(CUtensorMap* out, const void* base, uint64_t d, uint64_t heads, uint64_t L, uint64_t B,
                          uint64_t sh, uint64_t sn, uint64_t sb, uint32_t box_rows);
 
@@ -158,6 +160,19 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// TMA store (shared -> global, bulk async group): the issuing thread commits a group per store and later waits until the
+// source slab may be overwritten (.read) or until everything has been written (kernel exit).
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(

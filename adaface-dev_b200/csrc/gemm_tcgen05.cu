@@ -48,6 +48,9 @@ struct GemmEpilogue {
   // then sums the partials in fixed order and applies the epilogue terms.
   int splits, kb_per_split;
   float* splitk_ws;
+  int stages_a;       // BRES instantiation only: depth of the A-only ring behind the resident W slice
+  int dbg;            // diagnosis only (env ADAFACE_GEMM_DBG): 1 = epilogue skips the global stores, 2 = epilogue skips everything
+  int tma_store;      // FULL bf16 chunks leave through TMA bulk stores of the warp's swizzled slab (tmY: plain row-major output)
 };
 
 // Tensor maps of the CONV A operand: one for stride 1; one per input parity (py, px) for stride 2.
@@ -68,9 +71,9 @@ template <int BN>
 struct GemmCfg {
   static constexpr int B_STAGE_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);   // 64:8 128:6 160:5 192:5 256:4
+  static constexpr int STAGES = (192 * 1024 / STAGE_BYTES) > 8 ? 8 : (192 * 1024 / STAGE_BYTES);   // 64:8 128:6 160:5 192:4 256:4
   static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;   // two accumulator buffers
-  static constexpr int STORE_STAGE_BYTES = 8 * 2048;   // one 32-row x 64-byte transposition slab per epilogue warp
+  static constexpr int STORE_STAGE_BYTES = 8 * 4096;   // two 32-row x 64-byte transposition slabs per epilogue warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -99,7 +102,7 @@ __device__ __forceinline__ uint4 unstage_piece(const uint8_t* slab, int r, int p
 template <int BN, bool FULL>
 __device__ __forceinline__ void epilogue_chunk32(const GemmEpilogue& ep, const uint32_t (&v)[32], const uint32_t (&g)[32], int row,
                                                  bool row_ok, int row_end, const float* rowbias, int n_blk, int c0, uint8_t* slab,
-                                                 int lane) {
+                                                 int lane, const CUtensorMap* tmY, uint32_t& st_cnt) {
   const int n0 = n_blk * BN;
   const bool geglu = ep.act == ADAFACE_ACT_GEGLU;
   const int col0 = n0 + c0;
@@ -139,6 +142,7 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmEpilogue& ep, const u
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.f + __expf(-1.702f * f[j]));
   }
+  if (ep.dbg & 1) return;
   const bool staged = FULL && !ep.y_f32 && (ep.hs_d > 0 || ((ep.ldy & 7) == 0 && (out_col0 & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.y) & 15) == 0));   // warp-uniform
   if (!row_ok && !staged) return;
   if (ep.residual && row_ok) {
@@ -163,6 +167,21 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmEpilogue& ep, const u
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (FULL || out_col0 + j < out_n) y[j] = f[j];
+    }
+  } else if (staged && ep.tma_store) {
+    // One elected lane hands the swizzled slab to the TMA unit and the warp moves on to its next chunk: the store of chunk k
+    // drains while chunk k + 1 is read from TMEM and converted (measured on the level-A QKV shape: the LDS + STG.128 loop
+    // below was 15 of the kernel's 37 us).  Two slabs per warp; a slab is rewritten only after the bulk group that reads it
+    // has finished reading.  Rows >= M are clipped by the tensor map.
+    uint8_t* sl = slab + (st_cnt & 1) * 2048;
+    ++st_cnt;
+    if (lane == 0) tma_store_wait_read<1>();
+    __syncwarp();
+    stage_row64(sl, lane, f);                        // (ends with __syncwarp after the generic-proxy writes ...)
+    if (lane == 0) {
+      fence_proxy_async_smem();                      // ... which this fence orders before the async-proxy read
+      tma_store_2d(tmY, sl, out_col0, row - lane);
+      tma_store_commit();
     }
   } else if (staged) {
     stage_row64(slab, lane, f);
@@ -238,31 +257,50 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmEpilogue& ep, const u
 // displaced by the tap offset -- rows / columns outside the image arrive as zeros (the padding) -- and lands in shared
 // memory exactly like a [128, 64] K-major tile, so the MMA and epilogue code is the GEMM's.  A stride-2 convolution
 // reads through four tensor maps, one per input parity (y & 1, x & 1), each a stride-2 view of the activation.
-template <int BN, bool CONV>
+//
+// BRES = W-STATIONARY schedule for short-K projections (level A: K = 320).  ncu on the level-A QKV GEMM (M = 32768, N = 960,
+// K = 320) showed 262 MB crossing L2 -> SM for 21.7 MB of operands: every 128-row tile re-fetched its whole [BN, K] weight
+// slice (256 M tiles x 614 KB = 157 MB of W alone) and the kernel ran at the L2 bandwidth, not at the tensor or HBM roof.
+// Here a CTA is pinned to ONE column block: its weight slice (num_kb x [BN, 64] swizzled slabs, <= 164 KB) is loaded once and
+// stays in shared memory, the ring carries only A tiles (16 KB per K step), and the CTA walks down the M tiles of its column
+// block.  L2 -> SM traffic falls to (N / BN) x |X| + grid x |W slice| (QKV: 280 MB -> ~140 MB).
+template <int BN, bool CONV, bool BRES = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                            const __grid_constant__ CUtensorMap tmB,
                                                                            const __grid_constant__ CUtensorMap tmA2,
                                                                            const __grid_constant__ CUtensorMap tmB2,
                                                                            const __grid_constant__ typename ConvArg<CONV>::type cmaps,
+                                                                           const __grid_constant__ CUtensorMap tmY,
                                                                            const GemmEpilogue ep) {
   using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+  static_assert(!(BRES && CONV), "the W-stationary schedule is built for the plain projection GEMM");
+  constexpr int MAXST = BRES ? 8 : Cfg::STAGES;                    // barrier slots
   constexpr int kTma = 8, kMma = 9;
+  const int num_kb = ep.num_kb1 + ep.num_kb2;
+  const int STAGES = BRES ? ep.stages_a : Cfg::STAGES;             // ring depth (BRES: runtime, A tiles only)
+  constexpr int RING_STAGE_BYTES = BRES ? A_STAGE_BYTES : Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte alignment.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* store_stage = smem + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* smem0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sBres = smem0;                                          // BRES: num_kb resident [BN, 64] slabs of W
+  uint8_t* smem = smem0 + (BRES ? num_kb * Cfg::B_STAGE_BYTES : 0);   // the ring
+  uint8_t* store_stage = smem + STAGES * RING_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(store_stage + Cfg::STORE_STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* acc_full = empty_bar + STAGES;     // [2]
+  uint64_t* empty_bar = full_bar + MAXST;
+  uint64_t* acc_full = empty_bar + MAXST;      // [2]
   uint64_t* acc_empty = acc_full + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* b_full = acc_empty + 2;            // BRES: the resident W slice has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_kb = ep.num_kb1 + ep.num_kb2;
   const int num_n = (ep.N + BN - 1) / BN;
   const int num_tiles = ep.num_m * num_n * (CONV ? ep.splits : 1);
+  // tile walk: default = tiles c, c + grid, ... with n fastest; BRES = fixed column block, M tiles base, base + step, ...
+  const int t_first = BRES ? (int)(blockIdx.x / num_n) : (int)blockIdx.x;
+  const int t_step = BRES ? (int)(gridDim.x / num_n) : (int)gridDim.x;
+  const int t_end = BRES ? ep.num_m : num_tiles;
+  const int n_fixed = BRES ? (int)(blockIdx.x % num_n) : 0;
 
   if (warp == kTma && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -272,7 +310,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
       tma_prefetch_desc(&tmB2);
     }
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < MAXST; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -280,6 +318,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 256);
     }
+    mbar_init(b_full, 1);
     fence_barrier_init();
   } else if (warp == kMma) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -294,7 +333,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if constexpr (BRES) {
+        mbar_arrive_expect_tx(b_full, (uint32_t)(num_kb * Cfg::B_STAGE_BYTES));
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sBres + kb * Cfg::B_STAGE_BYTES, &tmB, b_full, kb * GEMM_BK, n_fixed * BN);
+        for (int m_blk = t_first; m_blk < t_end; m_blk += t_step) {
+          for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const int s = it % STAGES;
+            mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+            mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES);
+            tma_load_2d(smem + s * RING_STAGE_BYTES, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
+          }
+        }
+      }
+      for (int tile = BRES ? t_end : t_first; tile < t_end; tile += t_step) {
         int tile_mn = tile, kb_lo = 0, kb_hi = num_kb;
         if constexpr (CONV) {
           if (ep.splits > 1) {
@@ -356,7 +407,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16_f32(GEMM_BM, BN);
       uint32_t it = 0, t = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      if constexpr (BRES) {
+        mbar_wait(b_full, 0);
+        tc_fence_after();
+      }
+      for (int tile = t_first; tile < t_end; tile += t_step, ++t) {
         const uint32_t buf = t & 1;
         mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1);      // epilogue drained this accumulator (2 tiles ago)
         tc_fence_after();
@@ -372,8 +427,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
           const int s = it % STAGES;
           mbar_wait(&full_bar[s], (it / STAGES) & 1);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint32_t sa = smem_u32(smem + s * RING_STAGE_BYTES);
+          const uint32_t sb = BRES ? smem_u32(sBres + kb * Cfg::B_STAGE_BYTES) : sa + A_STAGE_BYTES;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // advancing 16 K-elements inside the swizzle span = +32 bytes on the start address
@@ -390,10 +445,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int half = warp >> 2;         // which alternate 32-column chunks this warp owns
     const bool geglu = ep.act == ADAFACE_ACT_GEGLU;
-    uint32_t t = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+    uint32_t t = 0, st_cnt = 0;
+    for (int tile = t_first; tile < t_end; tile += t_step, ++t) {
       const uint32_t buf = t & 1;
-      int tile_mn = tile, split = 0;
+      int tile_mn = BRES ? tile * num_n + n_fixed : tile, split = 0;
       if constexpr (CONV) {
         if (ep.splits > 1) {
           split = tile / (ep.num_m * num_n);
@@ -429,6 +484,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
         mbar_arrive(&acc_empty[buf]);
         arrived = true;
       }
+      if (ep.dbg & 2) {
+        if (!arrived) {
+          tc_fence_before();
+          mbar_arrive(&acc_empty[buf]);
+        }
+        continue;
+      }
       {
 #pragma unroll 1
         for (int ci = half; ci < n_chunks; ci += 2) {
@@ -461,11 +523,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
             }
           }
           const bool full = geglu || (n_blk * BN + c0 + 32 <= ep.N);
-          if (full) epilogue_chunk32<BN, true>(ep, v, g, row, row_ok, row_end, rowbias, n_blk, c0, store_stage + warp * 2048, lane);
-          else epilogue_chunk32<BN, false>(ep, v, g, row, row_ok, row_end, rowbias, n_blk, c0, store_stage + warp * 2048, lane);
+          if (full) epilogue_chunk32<BN, true>(ep, v, g, row, row_ok, row_end, rowbias, n_blk, c0, store_stage + warp * 4096, lane, &tmY, st_cnt);
+          else epilogue_chunk32<BN, false>(ep, v, g, row, row_ok, row_end, rowbias, n_blk, c0, store_stage + warp * 4096, lane, &tmY, st_cnt);
         }
       }
     }
+    if (ep.tma_store && lane == 0) tma_store_wait_all();      // the slabs must outlive the bulk stores that read them
   }
   pdl_launch_dependents();     // late trigger: the successor's CTAs are scheduled while this one tears down
   tc_fence_before();
@@ -481,7 +544,7 @@ extern long long g_launch_count;
 
 template <int BN, bool CONV = false>
 static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tA2, const CUtensorMap& tB2,
-                       const GemmEpilogue& ep, int n_tiles, cudaStream_t stream,
+                       const CUtensorMap& tY, const GemmEpilogue& ep, int n_tiles, cudaStream_t stream,
                        const typename ConvArg<CONV>::type& cmaps = typename ConvArg<CONV>::type()) {
   using Cfg = GemmCfg<BN>;
   static DevOnce configured;
@@ -489,15 +552,50 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   if (!configured.done(cfg_dev)) {
     AF_CUDA(cudaFuncSetAttribute(gemm_tn_tcgen05_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg::SMEM_BYTES));
+    if constexpr (!CONV)
+      AF_CUDA(cudaFuncSetAttribute((gemm_tn_tcgen05_kernel<BN, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured.set(cfg_dev);
   }
   const int num_sms = af_num_sms();
+  if constexpr (!CONV) {
+    // W-stationary schedule: short K, no LoRA tail, the [BN, K] weight slice + >= 3 A stages fit, and every CTA gets >= 4 M tiles
+    static int bres_on = -1;
+    if (bres_on < 0) {
+      const char* e = getenv("ADAFACE_GEMM_BRES");      // A/B switch (default on)
+      bres_on = (e && e[0] == '0') ? 0 : 1;
+    }
+    const int num_kb = ep.num_kb1;
+    const long long resident = (long long)num_kb * Cfg::B_STAGE_BYTES;
+    const long long fixed = Cfg::STORE_STAGE_BYTES + 1024 + 512;
+    int stages_a = (int)((227 * 1024 - fixed - resident) / A_STAGE_BYTES);
+    if (stages_a > 8) stages_a = 8;
+    const int per_col = num_sms / n_tiles;               // CTAs per column block
+    if (bres_on && ep.num_kb2 == 0 && n_tiles <= num_sms && stages_a >= 3 && per_col >= 1 && ep.num_m >= 4 * per_col) {
+      GemmEpilogue e2 = ep;
+      e2.stages_a = stages_a;
+      const int smem = (int)(resident + (long long)stages_a * A_STAGE_BYTES + fixed);
+      AF_CUDA(launch_pdl(1, gemm_tn_tcgen05_kernel<BN, false, true>, dim3(per_col * n_tiles), dim3(GEMM_THREADS), smem, stream, tA, tB, tA2,
+                         tB2, cmaps, tY, e2));
+      AF_CUDA(cudaGetLastError());
+      ++g_launch_count;
+      return 0;
+    }
+  }
   const int tiles = n_tiles * ep.num_m * (CONV ? ep.splits : 1);
   dim3 grid(tiles < num_sms ? tiles : num_sms);
-  AF_CUDA(launch_pdl(1, gemm_tn_tcgen05_kernel<BN, CONV>, grid, dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tA, tB, tA2, tB2, cmaps, ep));
+  AF_CUDA(launch_pdl(1, gemm_tn_tcgen05_kernel<BN, CONV>, grid, dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tA, tB, tA2, tB2, cmaps, tY, ep));
   AF_CUDA(cudaGetLastError());
   ++g_launch_count;
   return 0;
+}
+
+static bool tma_store_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("ADAFACE_GEMM_TMA_STORE");      // A/B switch (default on)
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
 }
 
 // Tile width: the widest of {256, 192, 160, 128, 64} that wastes no column and still gives every SM a tile.
@@ -598,13 +696,24 @@ int proj_lora_fwd(const void* x, int64_t ldx, const void* w, const void* t, int6
   ep.splits = 1;
   ep.kb_per_split = 0;
   ep.splitk_ws = nullptr;
+  ep.stages_a = 0;
+  {
+    const char* e = getenv("ADAFACE_GEMM_DBG");
+    ep.dbg = e ? atoi(e) : 0;
+  }
   const int n_tiles = (int)((N + BN - 1) / BN);
+  CUtensorMap tY = tA;
+  ep.tma_store = 0;
+  if (tma_store_enabled() && hs_d == 0 && y_dtype == ADAFACE_BF16 && ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    if (make_tmap_bf16_store32(&tY, y, (uint64_t)M, (uint64_t)(act == ADAFACE_ACT_GEGLU ? N / 2 : N), (uint64_t)ldy)) return 3;
+    ep.tma_store = 1;
+  }
   switch (BN) {
-    case 64: return launch_gemm<64>(tA, tB, tA2, tB2, ep, n_tiles, stream);
-    case 128: return launch_gemm<128>(tA, tB, tA2, tB2, ep, n_tiles, stream);
-    case 160: return launch_gemm<160>(tA, tB, tA2, tB2, ep, n_tiles, stream);
-    case 192: return launch_gemm<192>(tA, tB, tA2, tB2, ep, n_tiles, stream);
-    case 256: return launch_gemm<256>(tA, tB, tA2, tB2, ep, n_tiles, stream);
+    case 64: return launch_gemm<64>(tA, tB, tA2, tB2, tY, ep, n_tiles, stream);
+    case 128: return launch_gemm<128>(tA, tB, tA2, tB2, tY, ep, n_tiles, stream);
+    case 160: return launch_gemm<160>(tA, tB, tA2, tB2, tY, ep, n_tiles, stream);
+    case 192: return launch_gemm<192>(tA, tB, tA2, tB2, tY, ep, n_tiles, stream);
+    case 256: return launch_gemm<256>(tA, tB, tA2, tB2, tY, ep, n_tiles, stream);
   }
   set_error("proj_lora_fwd: unreachable tile width %d", BN);
   return 1;
@@ -734,6 +843,8 @@ int conv3x3_fwd(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, con
   ep.splits = 1;
   ep.kb_per_split = 0;
   ep.splitk_ws = nullptr;
+  ep.stages_a = 0;
+  ep.dbg = 0;
 
   int BN = pick_tile_width(Cout, ep.num_m, act);
   // The tile-width cost model is the projection GEMM's (short K, per-tile overhead matters).  With K = 9 Cin the main loop
@@ -794,13 +905,21 @@ int conv3x3_fwd(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, con
     tB2 = tB;
   }
   const int n_tiles = (int)((Cout + BN - 1) / BN);
+  // TMA-store epilogue: only when every tile is 128 real output rows (no rows of the tile fall outside its image)
+  CUtensorMap tY = tB;
+  ep.tma_store = 0;
+  const bool full_tiles = imgs > 1 ? (imgs * Ho * Wo == GEMM_BM) : (Wo * rh == GEMM_BM && Ho % rh == 0);
+  if (tma_store_enabled() && ep.splits == 1 && full_tiles && y_dtype == ADAFACE_BF16 && ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    if (make_tmap_bf16_store32(&tY, y, (uint64_t)M, (uint64_t)Cout, (uint64_t)ldy)) return 3;
+    ep.tma_store = 1;
+  }
   int rc;
   switch (BN) {
-    case 64: rc = launch_gemm<64, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm); break;
-    case 128: rc = launch_gemm<128, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm); break;
-    case 160: rc = launch_gemm<160, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm); break;
-    case 192: rc = launch_gemm<192, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm); break;
-    case 256: rc = launch_gemm<256, true>(tB, tB, tA2, tB2, ep, n_tiles, stream, cm); break;
+    case 64: rc = launch_gemm<64, true>(tB, tB, tA2, tB2, tY, ep, n_tiles, stream, cm); break;
+    case 128: rc = launch_gemm<128, true>(tB, tB, tA2, tB2, tY, ep, n_tiles, stream, cm); break;
+    case 160: rc = launch_gemm<160, true>(tB, tB, tA2, tB2, tY, ep, n_tiles, stream, cm); break;
+    case 192: rc = launch_gemm<192, true>(tB, tB, tA2, tB2, tY, ep, n_tiles, stream, cm); break;
+    case 256: rc = launch_gemm<256, true>(tB, tB, tA2, tB2, tY, ep, n_tiles, stream, cm); break;
     default:
       set_error("conv3x3_fwd: unreachable tile width %d", BN);
       return 1;
