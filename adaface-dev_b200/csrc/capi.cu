@@ -77,8 +77,8 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return 0;
 }
 
-// Store-side map of a bf16 row-major [rows, cols] output (row pitch `ld` elements): {32 columns x 32 rows} boxes with the 64-byte
-// swizzle -- the layout the GEMM epilogue's per-warp transposition slab already has (16-byte piece j of row r at j ^ ((r >> 1) & 3)).
+// Store-side map of a bf16 row-major [rows, cols] output (row pitch `ld` elements): {32 columns x 128 rows} boxes with the 64-byte
+// swizzle -- the layout of the GEMM epilogue's output slabs (16-byte piece j of row r at j ^ ((r >> 1) & 3)).
 int make_tmap_bf16_store32(CUtensorMap* out, void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
@@ -87,7 +87,7 @@ int make_tmap_bf16_store32(CUtensorMap* out, void* base, uint64_t rows, uint64_t
   }
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {ld * 2};
-  cuuint32_t box[2] = {32, 32};
+  cuuint32_t box[2] = {32, 128};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

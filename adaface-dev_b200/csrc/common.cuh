@@ -68,7 +68,7 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 // 4-D view {d, heads, tokens, batch} of a bf16 tensor (element strides: head = sh, token = sn, batch = sb;
 // sh = d, sn = H*d for the reference layout [B, L, H*d]; sh = L*d, sn = d for a head-major [B, H, L, d] buffer) with a {64, 1, box_rows, 1} box and 128-byte swizzle.  Columns >= d inside the 64-wide box are
 // out of bounds and therefore ZERO-filled by TMA: head dims 40 / 80 / 160 need no padding in HBM.
-// bf16 row-major [rows, cols] OUTPUT, {32 x 32} boxes, 64-byte swizzle: the target of the GEMM epilogue's TMA stores.
+// bf16 row-major [rows, cols] OUTPUT, {32 columns x 128 rows} boxes, 64-byte swizzle: the target of the GEMM epilogue's TMA stores.
 int make_tmap_bf16_store32(CUtensorMap* out, void* base, uint64_t rows, uint64_t cols, uint64_t ld);
 int make_tmap_bf16_heads(CUtensorMap* out, const void* base, uint64_t d, uint64_t heads, uint64_t L, uint64_t B,
                          uint64_t sh, uint64_t sn, uint64_t sb, uint32_t box_rows);
@@ -296,6 +296,16 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32_wait(uint32_t taddr, uint32_t
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
+}
+// Split form (software pipelining of an epilogue): issue now, consume after tmem_ld_wait_x32(v).
+__device__ __forceinline__ void tmem_ld_32x32b_x32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_x32(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]) : : "memory");
 }
 // registers -> TMEM, same shape as tmem_ld_32x32b_x16
 __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {

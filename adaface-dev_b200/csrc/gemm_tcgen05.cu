@@ -6,6 +6,7 @@
 // epilogue of one tile overlaps the main loop of the next (details at the kernel).
 // Reference arithmetic: nn.Linear / peft lora.Linear(+DoRA) call sites dalc:235-249, 280-288, 328-331
 // (SURVEY.md 8a rows A1, A4); ldm/modules/attention.py:31-58, 156-164; HF CLIP q/k/v/out_proj, fc1, fc2.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -15,7 +16,7 @@ namespace adaface {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;          // 64 bf16 = 128 B = one swizzle span
-constexpr int GEMM_THREADS = 320;     // 8 epilogue warps + TMA warp + MMA warp
+constexpr int GEMM_THREADS = 352;     // 8 epilogue warps + TMA warp + MMA warp + store warp
 constexpr int A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;
 
 struct GemmEpilogue {
@@ -48,9 +49,9 @@ struct GemmEpilogue {
   // then sums the partials in fixed order and applies the epilogue terms.
   int splits, kb_per_split;
   float* splitk_ws;
-  int stages_a;       // BRES instantiation only: depth of the A-only ring behind the resident W slice
   int dbg;            // diagnosis only (env ADAFACE_GEMM_DBG): 1 = epilogue skips the global stores, 2 = epilogue skips everything
-  int tma_store;      // FULL bf16 chunks leave through TMA bulk stores of the warp's swizzled slab (tmY: plain row-major output)
+  int tma_store;      // FULL bf16 chunks leave through TMA bulk stores issued by the store warp (tmY: plain row-major output)
+  long long* trace;   // diagnosis only (env ADAFACE_GEMM_TRACE): CTA 0 records clock64 stamps of its producer / MMA / epilogue hand-offs
 };
 
 // Tensor maps of the CONV A operand: one for stride 1; one per input parity (py, px) for stride 2.
@@ -67,14 +68,24 @@ struct ConvArg<true> {
   using type = ConvMaps;
 };
 
-template <int BN>
+// BRES = W-STATIONARY schedule for short-K projections (K <= 320: level A).  The operand feed, not the tensor pipe, bounds these
+// GEMMs: a 128 x BN tile pulls (128 + BN) x 128 bytes per 64-wide K block out of L2 for 2 BN tensor cycles (BN = 192: 107 B/clk per
+// SM, ~30 TB/s over the chip; traced: the MMA thread waits on the full barriers, 470 clk per K block against the 384 clk floor, 680
+// with the epilogue's traffic on top).  Here a CTA is pinned to ONE column block: its [BN, K] weight slice (<= 5 swizzled slabs) is
+// loaded once and stays in shared memory, the ring carries only A tiles (16 KB per K block) and the CTA walks down the M tiles of
+// its column block: 43 B/clk per SM at BN = 192.
+constexpr int BRES_KB = 5;            // resident K blocks (K <= 320)
+template <int BN, bool BRES = false>
 struct GemmCfg {
   static constexpr int B_STAGE_BYTES = BN * GEMM_BK * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (192 * 1024 / STAGE_BYTES) > 8 ? 8 : (192 * 1024 / STAGE_BYTES);   // 64:8 128:6 160:5 192:4 256:4
+  static constexpr int STAGE_BYTES = BRES ? A_STAGE_BYTES : A_STAGE_BYTES + B_STAGE_BYTES;      // ring stage
+  static constexpr int RESIDENT_BYTES = BRES ? BRES_KB * B_STAGE_BYTES : 0;
+  static constexpr int ST_NS = (BN == 192 && !BRES) ? 4 : 2;   // output slabs (128 rows x 32 columns bf16, 8 KB) per epilogue half: what the ring leaves free
+  static constexpr int STORE_STAGE_BYTES = 2 * ST_NS * 8192;   // (>= 4 KB per warp for the non-TMA path)
+  static constexpr int RING_BUDGET = (BRES ? 227 * 1024 - 1536 - STORE_STAGE_BYTES - RESIDENT_BYTES : 192 * 1024);
+  static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);   // 64:8 128:6 160:5 192:4 256:4; BRES 128:7 160:5 192:4
   static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;   // two accumulator buffers
-  static constexpr int STORE_STAGE_BYTES = 8 * 4096;   // two 32-row x 64-byte transposition slabs per epilogue warp
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = RESIDENT_BYTES + STAGES * STAGE_BYTES + STORE_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
@@ -99,10 +110,10 @@ __device__ __forceinline__ uint4 unstage_piece(const uint8_t* slab, int r, int p
   return *reinterpret_cast<const uint4*>(slab + r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
 }
 
-template <int BN, bool FULL>
+template <int BN, bool FULL, int ST_NS>
 __device__ __forceinline__ void epilogue_chunk32(const GemmEpilogue& ep, const uint32_t (&v)[32], const uint32_t (&g)[32], int row,
                                                  bool row_ok, int row_end, const float* rowbias, int n_blk, int c0, uint8_t* slab,
-                                                 int lane, const CUtensorMap* tmY, uint32_t& st_cnt) {
+                                                 int lane, uint8_t* slab_half, uint64_t* st_full, uint64_t* st_free, int qrow, uint32_t& st_cnt) {
   const int n0 = n_blk * BN;
   const bool geglu = ep.act == ADAFACE_ACT_GEGLU;
   const int col0 = n0 + c0;
@@ -169,20 +180,29 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmEpilogue& ep, const u
         if (FULL || out_col0 + j < out_n) y[j] = f[j];
     }
   } else if (staged && ep.tma_store) {
-    // One elected lane hands the swizzled slab to the TMA unit and the warp moves on to its next chunk: the store of chunk k
-    // drains while chunk k + 1 is read from TMEM and converted (measured on the level-A QKV shape: the LDS + STG.128 loop
-    // below was 15 of the kernel's 37 us).  Two slabs per warp; a slab is rewritten only after the bulk group that reads it
-    // has finished reading.  Rows >= M are clipped by the tensor map.
-    uint8_t* sl = slab + (st_cnt & 1) * 2048;
-    ++st_cnt;
-    if (lane == 0) tma_store_wait_read<1>();
+    // The four warps of this epilogue half (TMEM lane quarters 0..3) drop their 32 rows of the chunk into ONE 128-row slab in the
+    // 64-byte-swizzle layout and arrive on its `full` barrier; the STORE WARP turns the slab into one 8 KB TMA bulk store.
+    // (Measured: a thread that issues cp.async.bulk.tensor stores is throttled to the store engine's 32 B/clk/SM -- with each
+    // epilogue warp issuing its own 2 KB boxes the warps spent 2/3 of a chunk blocked in the issue: 1150 clk per chunk against
+    // 390 clk of TMEM read + conversion.  Issued from a dedicated thread, the engine drains under the next chunk's work.)
+    const uint32_t seq = st_cnt++;                   // == this half's count of staged chunks (its four warps stage the same chunks)
+    const int slot = (int)(seq % ST_NS);
+    const bool xtr = ep.trace && blockIdx.x == 0 && threadIdx.x == 0 && seq < 12;
+    if (xtr) ep.trace[1800 + seq * 5] = clock64();
+    if (seq >= ST_NS) mbar_wait(&st_free[slot], ((seq / ST_NS) - 1) & 1);      // the store that read this slab has finished reading
+    if (xtr) ep.trace[1800 + seq * 5 + 1] = clock64();
+    uint8_t* sl = slab_half + slot * 8192 + qrow * 64;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(sl + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+          make_uint4(pack_bf16(f[j * 8 + 0], f[j * 8 + 1]), pack_bf16(f[j * 8 + 2], f[j * 8 + 3]), pack_bf16(f[j * 8 + 4], f[j * 8 + 5]),
+                     pack_bf16(f[j * 8 + 6], f[j * 8 + 7]));
+    if (xtr) ep.trace[1800 + seq * 5 + 2] = clock64();
+    fence_proxy_async_smem();                        // every writer orders its generic-proxy writes before the async-proxy read
+    if (xtr) ep.trace[1800 + seq * 5 + 3] = clock64();
     __syncwarp();
-    stage_row64(sl, lane, f);                        // (ends with __syncwarp after the generic-proxy writes ...)
-    if (lane == 0) {
-      fence_proxy_async_smem();                      // ... which this fence orders before the async-proxy read
-      tma_store_2d(tmY, sl, out_col0, row - lane);
-      tma_store_commit();
-    }
+    if (lane == 0) mbar_arrive(&st_full[slot]);
+    if (xtr) ep.trace[1800 + seq * 5 + 4] = clock64();
   } else if (staged) {
     stage_row64(slab, lane, f);
     const int row_base = row - lane;                 // first row of this warp's 32-row slice
@@ -257,14 +277,7 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmEpilogue& ep, const u
 // displaced by the tap offset -- rows / columns outside the image arrive as zeros (the padding) -- and lands in shared
 // memory exactly like a [128, 64] K-major tile, so the MMA and epilogue code is the GEMM's.  A stride-2 convolution
 // reads through four tensor maps, one per input parity (y & 1, x & 1), each a stride-2 view of the activation.
-//
-// BRES = W-STATIONARY schedule for short-K projections (level A: K = 320).  ncu on the level-A QKV GEMM (M = 32768, N = 960,
-// K = 320) showed 262 MB crossing L2 -> SM for 21.7 MB of operands: every 128-row tile re-fetched its whole [BN, K] weight
-// slice (256 M tiles x 614 KB = 157 MB of W alone) and the kernel ran at the L2 bandwidth, not at the tensor or HBM roof.
-// Here a CTA is pinned to ONE column block: its weight slice (num_kb x [BN, 64] swizzled slabs, <= 164 KB) is loaded once and
-// stays in shared memory, the ring carries only A tiles (16 KB per K step), and the CTA walks down the M tiles of its column
-// block.  L2 -> SM traffic falls to (N / BN) x |X| + grid x |W slice| (QKV: 280 MB -> ~140 MB).
-template <int BN, bool CONV, bool BRES = false>
+template <int BN, bool CONV, bool LEAN = false, bool BRES = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                            const __grid_constant__ CUtensorMap tmB,
                                                                            const __grid_constant__ CUtensorMap tmA2,
@@ -272,35 +285,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
                                                                            const __grid_constant__ typename ConvArg<CONV>::type cmaps,
                                                                            const __grid_constant__ CUtensorMap tmY,
                                                                            const GemmEpilogue ep) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, BRES>;
   static_assert(!(BRES && CONV), "the W-stationary schedule is built for the plain projection GEMM");
-  constexpr int MAXST = BRES ? 8 : Cfg::STAGES;                    // barrier slots
-  constexpr int kTma = 8, kMma = 9;
+  static_assert(Cfg::STAGES >= 3 && Cfg::SMEM_BYTES <= 227 * 1024, "GEMM shared-memory plan");
+  constexpr int STAGES = Cfg::STAGES, ST_NS = Cfg::ST_NS;
+  constexpr int kTma = 8, kMma = 9, kStore = 10;
   const int num_kb = ep.num_kb1 + ep.num_kb2;
-  const int STAGES = BRES ? ep.stages_a : Cfg::STAGES;             // ring depth (BRES: runtime, A tiles only)
-  constexpr int RING_STAGE_BYTES = BRES ? A_STAGE_BYTES : Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte alignment.
-  uint8_t* smem0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sBres = smem0;                                          // BRES: num_kb resident [BN, 64] slabs of W
-  uint8_t* smem = smem0 + (BRES ? num_kb * Cfg::B_STAGE_BYTES : 0);   // the ring
-  uint8_t* store_stage = smem + STAGES * RING_STAGE_BYTES;
+  uint8_t* sW = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));   // BRES: resident W slabs
+  uint8_t* smem = sW + Cfg::RESIDENT_BYTES;                                                                       // the ring
+  uint8_t* store_stage = smem + STAGES * Cfg::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(store_stage + Cfg::STORE_STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + MAXST;
-  uint64_t* acc_full = empty_bar + MAXST;      // [2]
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_full = empty_bar + STAGES;     // [2]
   uint64_t* acc_empty = acc_full + 2;          // [2]
-  uint64_t* b_full = acc_empty + 2;            // BRES: the resident W slice has landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  uint64_t* st_full = acc_empty + 2;           // [2][ST_NS]: the four warps of an epilogue half have filled an output slab
+  uint64_t* st_free = st_full + 2 * ST_NS;     // [2][ST_NS]: the bulk store that read the slab has finished reading it
+  uint64_t* w_full = st_free + 2 * ST_NS;      // BRES: the resident W slice has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_n = (ep.N + BN - 1) / BN;
   const int num_tiles = ep.num_m * num_n * (CONV ? ep.splits : 1);
-  // tile walk: default = tiles c, c + grid, ... with n fastest; BRES = fixed column block, M tiles base, base + step, ...
-  const int t_first = BRES ? (int)(blockIdx.x / num_n) : (int)blockIdx.x;
-  const int t_step = BRES ? (int)(gridDim.x / num_n) : (int)gridDim.x;
-  const int t_end = BRES ? ep.num_m : num_tiles;
+  // tile walk: c, c + grid, ... (n fastest); BRES: CTA c owns column block c % num_n and walks M tiles c / num_n, + grid / num_n, ...
+  // (expressed in the same linear tile index: tile = m * num_n + n)
   const int n_fixed = BRES ? (int)(blockIdx.x % num_n) : 0;
+  const int t_first = BRES ? (int)(blockIdx.x / num_n) * num_n + n_fixed : (int)blockIdx.x;
+  const int t_step = BRES ? (int)(gridDim.x / num_n) * num_n : (int)gridDim.x;
+  const int t_end = num_tiles;
 
   if (warp == kTma && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -310,7 +324,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
       tma_prefetch_desc(&tmB2);
     }
 #pragma unroll
-    for (int s = 0; s < MAXST; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -318,7 +332,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 256);
     }
-    mbar_init(b_full, 1);
+    for (int i = 0; i < 2 * ST_NS; ++i) {
+      mbar_init(&st_full[i], 4);
+      mbar_init(&st_free[i], 1);
+    }
+    mbar_init(w_full, 1);
     fence_barrier_init();
   } else if (warp == kMma) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -334,14 +352,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
     if (elect_one()) {
       uint32_t it = 0;
       if constexpr (BRES) {
-        mbar_arrive_expect_tx(b_full, (uint32_t)(num_kb * Cfg::B_STAGE_BYTES));
-        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sBres + kb * Cfg::B_STAGE_BYTES, &tmB, b_full, kb * GEMM_BK, n_fixed * BN);
-        for (int m_blk = t_first; m_blk < t_end; m_blk += t_step) {
+        mbar_arrive_expect_tx(w_full, (uint32_t)(num_kb * Cfg::B_STAGE_BYTES));
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sW + kb * Cfg::B_STAGE_BYTES, &tmB, w_full, kb * GEMM_BK, n_fixed * BN);
+        for (int tile = t_first; tile < t_end; tile += t_step) {
+          const int m0 = (tile / num_n) * GEMM_BM;
           for (int kb = 0; kb < num_kb; ++kb, ++it) {
             const int s = it % STAGES;
+            const bool tr = ep.trace && blockIdx.x == 0 && it < 128;
+            if (tr) ep.trace[it * 2] = clock64();
             mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+            if (tr) ep.trace[it * 2 + 1] = clock64();
             mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES);
-            tma_load_2d(smem + s * RING_STAGE_BYTES, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
+            tma_load_2d(smem + s * Cfg::STAGE_BYTES, &tmA, &full_bar[s], kb * GEMM_BK, m0);
           }
         }
       }
@@ -370,7 +392,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
         }
         for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const int s = it % STAGES;
+          const bool tr = ep.trace && blockIdx.x == 0 && it < 128;
+          if (tr) ep.trace[it * 2] = clock64();
           mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          if (tr) ep.trace[it * 2 + 1] = clock64();
           uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
           if (CONV && kb < ep.num_kb1) {
@@ -408,12 +433,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
       constexpr uint32_t idesc = make_idesc_bf16_f32(GEMM_BM, BN);
       uint32_t it = 0, t = 0;
       if constexpr (BRES) {
-        mbar_wait(b_full, 0);
+        mbar_wait(w_full, 0);
         tc_fence_after();
       }
       for (int tile = t_first; tile < t_end; tile += t_step, ++t) {
         const uint32_t buf = t & 1;
+        if (ep.trace && blockIdx.x == 0 && t < 32) ep.trace[1024 + t * 2] = clock64();
         mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1);      // epilogue drained this accumulator (2 tiles ago)
+        if (ep.trace && blockIdx.x == 0 && t < 32) ep.trace[1024 + t * 2 + 1] = clock64();
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
         int kb_lo = 0, kb_hi = num_kb;
@@ -425,10 +452,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
         }
         for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const int s = it % STAGES;
+          const bool tr = ep.trace && blockIdx.x == 0 && it < 128;
+          if (tr) ep.trace[256 + it * 3] = clock64();
           mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          if (tr) ep.trace[256 + it * 3 + 1] = clock64();
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * RING_STAGE_BYTES);
-          const uint32_t sb = BRES ? smem_u32(sBres + kb * Cfg::B_STAGE_BYTES) : sa + A_STAGE_BYTES;
+          const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t sb = BRES ? smem_u32(sW + kb * Cfg::B_STAGE_BYTES) : sa + A_STAGE_BYTES;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // advancing 16 K-elements inside the swizzle span = +32 bytes on the start address
@@ -436,9 +466,49 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
                       (kb > kb_lo || k != 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);   // smem stage reusable once these MMAs have read it
+          if (tr) ep.trace[256 + it * 3 + 2] = clock64();
         }
         umma_commit(&acc_full[buf]);    // accumulator complete
       }
+    }
+  } else if (warp == kStore) {
+    // ------------------------------------------------------------------ store warp: one thread turns filled slabs into TMA stores
+    if (ep.tma_store && !ep.dbg && elect_one()) {
+      const bool geglu = ep.act == ADAFACE_ACT_GEGLU;
+      uint32_t seq[2] = {0, 0};
+      int prev = -1;
+      for (int tile = t_first; tile < t_end; tile += t_step) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;      // (tma_store implies splits == 1)
+        int row0 = m_blk * GEMM_BM;
+        if constexpr (CONV) {
+          if (ep.cv_imgs > 1) {
+            row0 = m_blk * ep.cv_imgs * ep.cv_HW;
+          } else {
+            const int img = m_blk / ep.cv_tpi, yc = m_blk - img * ep.cv_tpi;
+            row0 = img * ep.cv_HW + yc * ep.cv_img_rows;
+          }
+        }
+        const int cols_here = min(BN, ep.N - n_blk * BN);
+        const int n_chunks = geglu ? BN / 64 : (cols_here + 31) / 32;
+        for (int ci = 0; ci < n_chunks; ++ci) {
+          if (!geglu && n_blk * BN + ci * 32 + 32 > ep.N) continue;      // ragged chunk: stored by its warps directly
+          const int h = ci & 1, slot = (int)(seq[h] % ST_NS), id = h * ST_NS + slot;
+          const int bx = (int)(seq[0] + seq[1]);
+          const bool str_ = ep.trace && blockIdx.x == 0 && bx < 48;
+          if (str_) ep.trace[1600 + bx * 4] = clock64();
+          mbar_wait(&st_full[id], (seq[h] / ST_NS) & 1);
+          if (str_) ep.trace[1600 + bx * 4 + 1] = clock64();
+          ++seq[h];
+          tma_store_2d(&tmY, store_stage + id * 8192, (geglu ? n_blk * (BN / 2) : n_blk * BN) + ci * 32, row0);
+          tma_store_commit();
+          if (str_) ep.trace[1600 + bx * 4 + 2] = clock64();
+          tma_store_wait_read<1>();                  // every store but the one just issued has read its slab
+          if (str_) ep.trace[1600 + bx * 4 + 3] = clock64();
+          if (prev >= 0) mbar_arrive(&st_free[prev]);
+          prev = id;
+        }
+      }
+      tma_store_wait_all();                          // the slabs must outlive the bulk stores that read them
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0..7)
@@ -448,7 +518,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
     uint32_t t = 0, st_cnt = 0;
     for (int tile = t_first; tile < t_end; tile += t_step, ++t) {
       const uint32_t buf = t & 1;
-      int tile_mn = BRES ? tile * num_n + n_fixed : tile, split = 0;
+      int tile_mn = tile, split = 0;
       if constexpr (CONV) {
         if (ep.splits > 1) {
           split = tile / (ep.num_m * num_n);
@@ -473,7 +543,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
         if (ep.rowbias) rowbias = ep.rowbias + (long long)(min(row, ep.M - 1) / ep.cv_HW) * ep.N;
       }
       const bool row_ok = row < row_end;
+      const bool etr = ep.trace && blockIdx.x == 0 && t < 32 && (warp == 0 || warp == 7) && lane == 0;
+      if (etr) ep.trace[1200 + (warp ? 100 : 0) + t * 3] = clock64();
       mbar_wait(&acc_full[buf], (t >> 1) & 1);
+      if (etr) ep.trace[1200 + (warp ? 100 : 0) + t * 3 + 1] = clock64();
       tc_fence_after();
       const uint32_t t_acc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
       const int cols_here = min(BN, ep.N - n_blk * BN);                       // real columns of this tile
@@ -491,44 +564,120 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
         }
         continue;
       }
-      {
+      if constexpr (LEAN) {
+        // LEAN instantiation (chosen per launch): Y = bf16(X W^T [+ bias]), every chunk full, output through the store warp.
+        // The general epilogue below carries every option as a warp-uniform branch (~120 issued instructions per chunk at
+        // ~9.5 clk per instruction with two epilogue warps per scheduler: 1150 clk per chunk, 3500 per 128 x 192 tile against
+        // 1920 clk of MMA at K = 320); this one is the ~50 instructions the plain projection needs.
+        uint8_t* slab_half = store_stage + half * (ST_NS * 8192) + q * 32 * 64 + lane * 64;
+        uint64_t* stf = st_full + half * ST_NS;
+        uint64_t* stfree = st_free + half * ST_NS;
+        const int swz = (lane >> 1) & 3;
+        auto lean_chunk = [&](uint32_t (&v)[32], int ci) {
+          if (ep.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n_blk * BN + ci * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
+              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
+              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
+              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+            }
+          }
+          const uint32_t seq = st_cnt++;
+          const int slot = (int)(seq % ST_NS);
+          if (seq >= ST_NS) mbar_wait(&stfree[slot], ((seq / ST_NS) - 1) & 1);
+          uint8_t* sl = slab_half + slot * 8192;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(sl + ((j ^ swz) << 4)) =
+                make_uint4(pack_bf16(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1])), pack_bf16(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3])),
+                           pack_bf16(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5])), pack_bf16(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7])));
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&stf[slot]);
+        };
+        uint32_t va[32], vb[32];
+        int ci = half;
+        if (ci < n_chunks) tmem_ld_32x32b_x32_nowait(t_acc + (uint32_t)(ci * 32), va);
 #pragma unroll 1
-        for (int ci = half; ci < n_chunks; ci += 2) {
-          const int c0 = ci * 32;
-          uint32_t v[32], g[32];
-          tmem_ld_32x32b_x32_wait(t_acc + (uint32_t)c0, v);
-          if (geglu) tmem_ld_32x32b_x32_wait(t_acc + (uint32_t)(c0 + BN / 2), g);
-          if (ci + 2 >= n_chunks && !arrived) {
-            // last TMEM read of this warp for this tile: hand the accumulator back before the global stores
+        while (ci < n_chunks) {
+          tmem_ld_wait_x32(va);
+          if (ci + 2 < n_chunks) tmem_ld_32x32b_x32_nowait(t_acc + (uint32_t)((ci + 2) * 32), vb);
+          else if (!arrived) {
             tc_fence_before();
             mbar_arrive(&acc_empty[buf]);
             arrived = true;
           }
-          if constexpr (CONV) {
-            if (ep.splits > 1) {      // raw fp32 partial tile: the epilogue terms are applied by the reduce kernel
-              if (row_ok) {
-                float* dst = ep.splitk_ws + ((long long)split * ep.M + row) * ep.N + n_blk * BN + c0;
-                const int nv = min(32, ep.N - (n_blk * BN + c0));
-                if (nv == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-#pragma unroll
-                  for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j)
-                    if (j < nv) dst[j] = __uint_as_float(v[j]);
-                }
-              }
-              continue;
-            }
+          lean_chunk(va, ci);
+          ci += 2;
+          if (ci >= n_chunks) break;
+          tmem_ld_wait_x32(vb);
+          if (ci + 2 < n_chunks) tmem_ld_32x32b_x32_nowait(t_acc + (uint32_t)((ci + 2) * 32), va);
+          else if (!arrived) {
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);
+            arrived = true;
           }
-          const bool full = geglu || (n_blk * BN + c0 + 32 <= ep.N);
-          if (full) epilogue_chunk32<BN, true>(ep, v, g, row, row_ok, row_end, rowbias, n_blk, c0, store_stage + warp * 4096, lane, &tmY, st_cnt);
-          else epilogue_chunk32<BN, false>(ep, v, g, row, row_ok, row_end, rowbias, n_blk, c0, store_stage + warp * 4096, lane, &tmY, st_cnt);
+          lean_chunk(vb, ci);
+          ci += 2;
+        }
+        if (etr) ep.trace[1200 + (warp ? 100 : 0) + t * 3 + 2] = clock64();
+        continue;
+      }
+      // General epilogue: one chunk = 32 accumulator columns of this warp's 32 rows.
+      auto process = [&](const uint32_t (&v)[32], const uint32_t (&g)[32], int ci) {
+        const int c0 = ci * 32;
+        if constexpr (CONV) {
+          if (ep.splits > 1) {      // raw fp32 partial tile: the epilogue terms are applied by the reduce kernel
+            if (row_ok) {
+              float* dst = ep.splitk_ws + ((long long)split * ep.M + row) * ep.N + n_blk * BN + c0;
+              const int nv = min(32, ep.N - (n_blk * BN + c0));
+              if (nv == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nv) dst[j] = __uint_as_float(v[j]);
+              }
+            }
+            return;
+          }
+        }
+        const bool full = geglu || (n_blk * BN + c0 + 32 <= ep.N);
+        if (full) epilogue_chunk32<BN, true, ST_NS>(ep, v, g, row, row_ok, row_end, rowbias, n_blk, c0, store_stage + warp * 4096, lane, store_stage + half * (ST_NS * 8192), st_full + half * ST_NS, st_free + half * ST_NS, q * 32, st_cnt);
+        else epilogue_chunk32<BN, false, ST_NS>(ep, v, g, row, row_ok, row_end, rowbias, n_blk, c0, store_stage + warp * 4096, lane, store_stage + half * (ST_NS * 8192), st_full + half * ST_NS, st_free + half * ST_NS, q * 32, st_cnt);
+      };
+      auto release_acc = [&]() {
+        // last TMEM read of this warp for this tile has landed: hand the accumulator back before the stores
+        tc_fence_before();
+        mbar_arrive(&acc_empty[buf]);
+        arrived = true;
+      };
+      if (geglu) {
+#pragma unroll 1
+        for (int ci = half; ci < n_chunks; ci += 2) {
+          uint32_t v[32], g[32];
+          tmem_ld_32x32b_x32_nowait(t_acc + (uint32_t)(ci * 32), v);
+          tmem_ld_32x32b_x32_wait(t_acc + (uint32_t)(ci * 32 + BN / 2), g);
+          tmem_ld_wait_x32(v);
+          if (ci + 2 >= n_chunks && !arrived) release_acc();
+          process(v, g, ci);
+        }
+      } else {
+#pragma unroll 1
+        for (int ci = half; ci < n_chunks; ci += 2) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32_wait(t_acc + (uint32_t)(ci * 32), v);
+          if (ci + 2 >= n_chunks && !arrived) release_acc();
+          process(v, v, ci);
         }
       }
+      if (etr) ep.trace[1200 + (warp ? 100 : 0) + t * 3 + 2] = clock64();
     }
-    if (ep.tma_store && lane == 0) tma_store_wait_all();      // the slabs must outlive the bulk stores that read them
   }
   pdl_launch_dependents();     // late trigger: the successor's CTAs are scheduled while this one tears down
   tc_fence_before();
@@ -547,43 +696,50 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
                        const CUtensorMap& tY, const GemmEpilogue& ep, int n_tiles, cudaStream_t stream,
                        const typename ConvArg<CONV>::type& cmaps = typename ConvArg<CONV>::type()) {
   using Cfg = GemmCfg<BN>;
+  constexpr bool HAS_BRES = !CONV && (BN == 128 || BN == 160 || BN == 192);
+  using CfgR = GemmCfg<BN, HAS_BRES>;
   static DevOnce configured;
   const int cfg_dev = af_device();
   if (!configured.done(cfg_dev)) {
-    AF_CUDA(cudaFuncSetAttribute(gemm_tn_tcgen05_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg::SMEM_BYTES));
-    if constexpr (!CONV)
-      AF_CUDA(cudaFuncSetAttribute((gemm_tn_tcgen05_kernel<BN, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AF_CUDA(cudaFuncSetAttribute((gemm_tn_tcgen05_kernel<BN, CONV, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    AF_CUDA(cudaFuncSetAttribute((gemm_tn_tcgen05_kernel<BN, CONV, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    if constexpr (HAS_BRES) {
+      AF_CUDA(cudaFuncSetAttribute((gemm_tn_tcgen05_kernel<BN, CONV, false, HAS_BRES>), cudaFuncAttributeMaxDynamicSharedMemorySize, CfgR::SMEM_BYTES));
+      AF_CUDA(cudaFuncSetAttribute((gemm_tn_tcgen05_kernel<BN, CONV, true, HAS_BRES>), cudaFuncAttributeMaxDynamicSharedMemorySize, CfgR::SMEM_BYTES));
+    }
     configured.set(cfg_dev);
   }
   const int num_sms = af_num_sms();
-  if constexpr (!CONV) {
-    // W-stationary schedule: short K, no LoRA tail, the [BN, K] weight slice + >= 3 A stages fit, and every CTA gets >= 4 M tiles
-    static int bres_on = -1;
-    if (bres_on < 0) {
-      const char* e = getenv("ADAFACE_GEMM_BRES");      // A/B switch (default on)
-      bres_on = (e && e[0] == '0') ? 0 : 1;
-    }
-    const int num_kb = ep.num_kb1;
-    const long long resident = (long long)num_kb * Cfg::B_STAGE_BYTES;
-    const long long fixed = Cfg::STORE_STAGE_BYTES + 1024 + 512;
-    int stages_a = (int)((227 * 1024 - fixed - resident) / A_STAGE_BYTES);
-    if (stages_a > 8) stages_a = 8;
-    const int per_col = num_sms / n_tiles;               // CTAs per column block
-    if (bres_on && ep.num_kb2 == 0 && n_tiles <= num_sms && stages_a >= 3 && per_col >= 1 && ep.num_m >= 4 * per_col) {
-      GemmEpilogue e2 = ep;
-      e2.stages_a = stages_a;
-      const int smem = (int)(resident + (long long)stages_a * A_STAGE_BYTES + fixed);
-      AF_CUDA(launch_pdl(1, gemm_tn_tcgen05_kernel<BN, false, true>, dim3(per_col * n_tiles), dim3(GEMM_THREADS), smem, stream, tA, tB, tA2,
-                         tB2, cmaps, tY, e2));
+  const int tiles = n_tiles * ep.num_m * (CONV ? ep.splits : 1);
+  dim3 grid(tiles < num_sms ? tiles : num_sms);
+  // LEAN epilogue: plain bf16 projection (optional bias) whose every 32-column chunk is full and leaves through the store warp
+  static int lean_on = -1, bres_on = -1;
+  if (lean_on < 0) {
+    const char* e = getenv("ADAFACE_GEMM_LEAN");      // A/B switches (default on)
+    lean_on = (e && e[0] == '0') ? 0 : 1;
+    e = getenv("ADAFACE_GEMM_BRES");
+    bres_on = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool lean = lean_on && ep.tma_store && !ep.dbg && !ep.colscale && !ep.rowbias && !ep.residual && ep.act == ADAFACE_ACT_NONE && !ep.y_f32 &&
+                    ep.hs_d == 0 && ep.splits == 1 && ep.N % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0;
+  if constexpr (HAS_BRES) {
+    // W-stationary schedule: short K, no LoRA tail, whole column blocks, and every CTA gets >= 4 M tiles
+    const int per_col = num_sms / n_tiles;
+    if (bres_on && ep.num_kb2 == 0 && ep.num_kb1 <= BRES_KB && n_tiles <= num_sms && per_col >= 1 && ep.num_m >= 4 * per_col) {
+      const dim3 g2(per_col * n_tiles);
+      if (lean)
+        AF_CUDA(launch_pdl(1, gemm_tn_tcgen05_kernel<BN, CONV, true, HAS_BRES>, g2, dim3(GEMM_THREADS), CfgR::SMEM_BYTES, stream, tA, tB, tA2, tB2, cmaps, tY, ep));
+      else
+        AF_CUDA(launch_pdl(1, gemm_tn_tcgen05_kernel<BN, CONV, false, HAS_BRES>, g2, dim3(GEMM_THREADS), CfgR::SMEM_BYTES, stream, tA, tB, tA2, tB2, cmaps, tY, ep));
       AF_CUDA(cudaGetLastError());
       ++g_launch_count;
       return 0;
     }
   }
-  const int tiles = n_tiles * ep.num_m * (CONV ? ep.splits : 1);
-  dim3 grid(tiles < num_sms ? tiles : num_sms);
-  AF_CUDA(launch_pdl(1, gemm_tn_tcgen05_kernel<BN, CONV>, grid, dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tA, tB, tA2, tB2, cmaps, tY, ep));
+  if (lean)
+    AF_CUDA(launch_pdl(1, gemm_tn_tcgen05_kernel<BN, CONV, true>, grid, dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tA, tB, tA2, tB2, cmaps, tY, ep));
+  else
+    AF_CUDA(launch_pdl(1, gemm_tn_tcgen05_kernel<BN, CONV, false>, grid, dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tA, tB, tA2, tB2, cmaps, tY, ep));
   AF_CUDA(cudaGetLastError());
   ++g_launch_count;
   return 0;
@@ -696,27 +852,61 @@ int proj_lora_fwd(const void* x, int64_t ldx, const void* w, const void* t, int6
   ep.splits = 1;
   ep.kb_per_split = 0;
   ep.splitk_ws = nullptr;
-  ep.stages_a = 0;
   {
     const char* e = getenv("ADAFACE_GEMM_DBG");
     ep.dbg = e ? atoi(e) : 0;
   }
   const int n_tiles = (int)((N + BN - 1) / BN);
+  ep.trace = nullptr;
+  static long long* trace_buf = nullptr;
+  if (getenv("ADAFACE_GEMM_TRACE")) {
+    if (!trace_buf) cudaMalloc(&trace_buf, 2048 * 8);
+    cudaMemset(trace_buf, 0, 2048 * 8);
+    ep.trace = trace_buf;
+  }
   CUtensorMap tY = tA;
   ep.tma_store = 0;
   if (tma_store_enabled() && hs_d == 0 && y_dtype == ADAFACE_BF16 && ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
     if (make_tmap_bf16_store32(&tY, y, (uint64_t)M, (uint64_t)(act == ADAFACE_ACT_GEGLU ? N / 2 : N), (uint64_t)ldy)) return 3;
     ep.tma_store = 1;
   }
+  int rc = -1;
   switch (BN) {
-    case 64: return launch_gemm<64>(tA, tB, tA2, tB2, tY, ep, n_tiles, stream);
-    case 128: return launch_gemm<128>(tA, tB, tA2, tB2, tY, ep, n_tiles, stream);
-    case 160: return launch_gemm<160>(tA, tB, tA2, tB2, tY, ep, n_tiles, stream);
-    case 192: return launch_gemm<192>(tA, tB, tA2, tB2, tY, ep, n_tiles, stream);
-    case 256: return launch_gemm<256>(tA, tB, tA2, tB2, tY, ep, n_tiles, stream);
+    case 64: rc = launch_gemm<64>(tA, tB, tA2, tB2, tY, ep, n_tiles, stream); break;
+    case 128: rc = launch_gemm<128>(tA, tB, tA2, tB2, tY, ep, n_tiles, stream); break;
+    case 160: rc = launch_gemm<160>(tA, tB, tA2, tB2, tY, ep, n_tiles, stream); break;
+    case 192: rc = launch_gemm<192>(tA, tB, tA2, tB2, tY, ep, n_tiles, stream); break;
+    case 256: rc = launch_gemm<256>(tA, tB, tA2, tB2, tY, ep, n_tiles, stream); break;
   }
-  set_error("proj_lora_fwd: unreachable tile width %d", BN);
-  return 1;
+  if (rc < 0) {
+    set_error("proj_lora_fwd: unreachable tile width %d", BN);
+    return 1;
+  }
+  if (ep.trace && rc == 0) {      // diagnosis: dump CTA 0's hand-off stamps (relative to its first stamp)
+    static long long h[2048];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, ep.trace, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long t0 = h[0];
+    fprintf(stderr, "GEMM trace M=%lld N=%lld K=%lld BN=%d kb=%d\n", (long long)M, (long long)N, (long long)K, BN, ep.num_kb1 + ep.num_kb2);
+    for (int i = 0; i < 64; ++i)
+      fprintf(stderr, "it %3d  tma: wait %6lld..%6lld | mma: wait %6lld..%6lld issued %6lld\n", i, h[i * 2] - t0, h[i * 2 + 1] - t0, h[256 + i * 3] - t0,
+              h[256 + i * 3 + 1] - t0, h[256 + i * 3 + 2] - t0);
+    for (int t = 0; t < 12; ++t)
+      fprintf(stderr, "tile %2d  mma acc_empty wait %6lld..%6lld | epi w0: acc_full wait %6lld..%6lld done %6lld | epi w7: %6lld..%6lld done %6lld\n", t,
+              h[1024 + t * 2] - t0, h[1024 + t * 2 + 1] - t0, h[1200 + t * 3] - t0, h[1200 + t * 3 + 1] - t0, h[1200 + t * 3 + 2] - t0, h[1300 + t * 3] - t0,
+              h[1300 + t * 3 + 1] - t0, h[1300 + t * 3 + 2] - t0);
+    for (int t = 0; t < 4; ++t)
+      for (int c = 0; c < 3; ++c)
+        fprintf(stderr, "tile %d chunk %d (warp 0): begin %6lld  tmem read %6lld  staged %6lld\n", t, 2 * c, h[1400 + (t * 8 + c) * 3] - t0, h[1400 + (t * 8 + c) * 3 + 1] - t0,
+                h[1400 + (t * 8 + c) * 3 + 2] - t0);
+    for (int b = 0; b < 12; ++b)
+      fprintf(stderr, "staging %2d (warp 0): enter %6lld  slab free %6lld  written %6lld  fenced %6lld  arrived %6lld\n", b, h[1800 + b * 5] - t0, h[1800 + b * 5 + 1] - t0,
+              h[1800 + b * 5 + 2] - t0, h[1800 + b * 5 + 3] - t0, h[1800 + b * 5 + 4] - t0);
+    for (int b = 0; b < 30; ++b)
+      fprintf(stderr, "store box %2d: wait full %6lld..%6lld  issued %6lld  prev read done %6lld\n", b, h[1600 + b * 4] - t0, h[1600 + b * 4 + 1] - t0, h[1600 + b * 4 + 2] - t0,
+              h[1600 + b * 4 + 3] - t0);
+  }
+  return rc;
 }
 
 // y[row, c] = act(colscale[c] * sum_s ws[s][row][c] + bias[c] + rowbias[row / HW][c]) + residual[row, c]: the epilogue of a
@@ -843,8 +1033,8 @@ int conv3x3_fwd(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, con
   ep.splits = 1;
   ep.kb_per_split = 0;
   ep.splitk_ws = nullptr;
-  ep.stages_a = 0;
   ep.dbg = 0;
+  ep.trace = nullptr;
 
   int BN = pick_tile_width(Cout, ep.num_m, act);
   // The tile-width cost model is the projection GEMM's (short K, per-tile overhead matters).  With K = 9 Cin the main loop
