@@ -131,6 +131,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                  // global memory is touched only after the predecessor kernel has completed
+  AF_PDL_TRIGGER_EARLY();
 
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
@@ -313,7 +314,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
     }
   }
-  pdl_launch_dependents();     // late trigger: the successor's CTAs are scheduled while this one tears down
+  AF_PDL_TRIGGER_LATE();
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
@@ -377,6 +378,7 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                  // global memory is touched only after the predecessor kernel has completed
+  AF_PDL_TRIGGER_EARLY();
 
   if (warp == kTmaWarp) {
     if (elect_one()) {
@@ -527,7 +529,7 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       }
     }
   }
-  pdl_launch_dependents();     // late trigger: the successor's CTAs are scheduled while this one tears down
+  AF_PDL_TRIGGER_LATE();
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
@@ -622,6 +624,7 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                  // global memory is touched only after the predecessor kernel has completed
+  AF_PDL_TRIGGER_EARLY();
 
   if (warp == kTma) {
     // The whole warp runs this loop: one elected lane issues the TMA loads (two tiles ahead), then all 32 lanes write
@@ -847,7 +850,7 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
       }
     }
   }
-  pdl_launch_dependents();     // late trigger: the successor's CTAs are scheduled while this one tears down
+  AF_PDL_TRIGGER_LATE();
   tc_fence_before();
   __syncthreads();
   if (warp == kMma) {
@@ -1009,6 +1012,7 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                  // global memory is touched only after the predecessor kernel has completed
+  AF_PDL_TRIGGER_EARLY();
 
   if (warp == kTmaWarp) {
     // whole warp: one elected lane issues the TMA loads; when a new (batch, head) arrives all lanes write the ONES
@@ -1177,7 +1181,7 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_arrive(o_free);
     }
   }
-  pdl_launch_dependents();     // late trigger: the successor's CTAs are scheduled while this one tears down
+  AF_PDL_TRIGGER_LATE();
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {

@@ -99,6 +99,17 @@ __device__ __forceinline__ bool elect_one() {
 // touch; pdl_launch_dependents() lets the successor's CTAs be scheduled as soon as resources free up.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Trigger placement.  LATE (default): at the end of the kernel body, the successor's CTAs are scheduled while this one tears down.
+// -DAF_PDL_EARLY moves it right behind this kernel's own pdl_wait (successor CTAs become resident on every SM a CTA of this kernel
+// has left and park in griddepcontrol.wait).  Measured on the 117-kernel step graph: 2.886 ms early vs 2.879 ms late -- no gain,
+// the launch + prologue of a kernel is already hidden.
+#ifdef AF_PDL_EARLY
+#define AF_PDL_TRIGGER_EARLY() pdl_launch_dependents()
+#define AF_PDL_TRIGGER_LATE()
+#else
+#define AF_PDL_TRIGGER_EARLY()
+#define AF_PDL_TRIGGER_LATE() pdl_launch_dependents()
+#endif
 
 // ---- mbarrier -------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -346,6 +346,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                  // this kernel touches global memory only after its predecessor has completed
+  AF_PDL_TRIGGER_EARLY();
 
   if (warp == kTma) {
     // ------------------------------------------------------------------ TMA producer
@@ -679,7 +680,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
       if (etr) ep.trace[1200 + (warp ? 100 : 0) + t * 3 + 2] = clock64();
     }
   }
-  pdl_launch_dependents();     // late trigger: the successor's CTAs are scheduled while this one tears down
+  AF_PDL_TRIGGER_LATE();
   tc_fence_before();
   __syncthreads();
   if (warp == kMma) {

@@ -95,7 +95,7 @@ int main() {
   printf("%-28s %4s %5s %10s %12s\n", "mode", "N", "nacc", "cyc/mma", "FLOP/clk/SM");
   for (int pair = 0; pair < 2; ++pair)
     for (int nacc : {1, 2})
-      for (int N : {128, 160, 192, 256}) {
+      for (int N : {16, 32, 48, 64, 96, 128, 160, 192, 256}) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(148);
         cfg.blockDim = dim3(128);
