@@ -232,7 +232,7 @@ static int check_view(const char* what, const void* ptr, int64_t sb, int64_t sn,
 
 int attn_fwd_tcgen05(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, const void*, int64_t,
                      int64_t, int64_t, void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
-                     float, float*, cudaStream_t);
+                     float, float*, const uint8_t*, cudaStream_t);
 
 static bool legacy_attention_forced() {
   static int v = -1;
@@ -254,9 +254,9 @@ int attn_fwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k
            (long long)H, (long long)Lq, (long long)Lk);
   AF_CHECK(B <= 65535 && H <= 65535, "attn_fwd: B/H exceed grid limits");
   AF_CHECK(causal_mult >= 0, "attn_fwd: causal_mult must be >= 0");
-  if (!key_mask && causal_mult == 0 && !legacy_attention_forced()) {
-    // unmasked attention: tcgen05 / TMEM kernel (attn_tcgen05.cu)
-    const int rc = attn_fwd_tcgen05(q, q_sb, d, q_sn, k, k_sb, d, k_sn, v, v_sb, d, v_sn, o, o_sb, o_sn, B, H, Lq, Lk, d, d, d, scale, lse, stream);
+  if (causal_mult == 0 && !legacy_attention_forced()) {
+    // tcgen05 / TMEM kernels (attn_tcgen05.cu): unmasked attention, and key masks at d = 40 / long sequences (level A)
+    const int rc = attn_fwd_tcgen05(q, q_sb, d, q_sn, k, k_sb, d, k_sn, v, v_sb, d, v_sn, o, o_sb, o_sn, B, H, Lq, Lk, d, d, d, scale, lse, key_mask, stream);
     if (rc >= 0) return rc;
   }
   AttnParams p;

@@ -10,6 +10,7 @@ struct TaParams {
   int Lq, Lk;
   float scale_log2;
   float* lse;              // optional [B, H, Lq]: log2-domain log-sum-exp of each row, kept for the backward pass
+  const uint8_t* key_mask; // optional [B, Lk]: 0 = key masked out (four-tile kernel only; every row keeps >= 1 key)
 };
 
 }  // namespace adaface

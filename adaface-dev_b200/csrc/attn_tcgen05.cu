@@ -564,7 +564,12 @@ constexpr int TQ_ST = 3;                      // K/V ring: tiles j and j+1 are l
 // half g % 2); each slot runs the same online softmax over its half and the two partial results of a tile are merged
 // in the epilogue through shared memory (O = 2^(m0-m) O0 + 2^(m1-m) O1 -- the row sum rides along as column D).  A
 // tail CTA then has the full 16 softmax warps for half as long, instead of 8 warps for the whole key range.
-template <int D, int G, int EMU, bool SPLIT>
+// MASK (key mask, dalc:254-273 img_mask): the head dim is zero-padded from D to the 64-wide MMA K, so column D of Q and K is free:
+// the TMA warp sets Q[:, D] = 1 once and K[j, D] = 0 / -65536 (kept / masked key) in every K tile it lands -- next to the ones
+// column it already writes into V -- and the tensor core adds the mask bias to the scores: S = q.k + 1 * bias.  The softmax warps
+// run the unmasked code (a masked key's exp2 underflows to exactly 0; a tile of only masked keys is erased by the next rescale,
+// whose factor 2^(-65536 scale) is 0); the issuer waits for the patched tiles (q_ready, v_ready) instead of the raw TMA barriers.
+template <int D, int G, int EMU, bool SPLIT, bool MASK = false>
 __global__ void __launch_bounds__((4 * G + 2) * 32, 1)
 attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                              const __grid_constant__ CUtensorMap tmV, const TaParams p, const int unit0, const int H) {
@@ -589,7 +594,8 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
   uint64_t* p_full = s_full + G;                                  // [G]
   uint64_t* o_full = p_full + G;
   uint64_t* v_ready = o_full + 1;                                 // [ST]: the ones column has been written into V stage s
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_ready + ST);
+  uint64_t* q_ready = v_ready + ST;                               // MASK: column D of the Q tiles has been set to 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // unit = (batch, head, block of G query tiles), linearised with the query block fastest
@@ -615,6 +621,7 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
       mbar_init(&p_full[g], 128);
     }
     mbar_init(o_full, 1);
+    mbar_init(q_ready, 1);
     fence_barrier_init();
   } else if (warp == kMma) {
     tmem_alloc(tmem_slot, G * TMEM_G);
@@ -648,19 +655,59 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
       issue_kv(0);
       if (n_tiles > 1) issue_kv(1);
     }
-    for (int j = 0; j < n_tiles; ++j) {
+    // MASK: bias of this lane's K rows (r = lane, lane + 32, ...) of tile j, fetched one tile ahead
+    const uint8_t* mrow = MASK ? p.key_mask + (long long)b * p.Lk : nullptr;
+    auto mask_bias = [&](int j, int r) -> uint16_t {
+      const int key = (j + (r / TA_BN) * n_tiles) * TA_BN + (r % TA_BN);
+      return (key < p.Lk && __ldg(mrow + key) == 0) ? (uint16_t)0xC780 : (uint16_t)0;      // bf16 -65536 | 0
+    };
+    uint16_t kb[KH * TA_BN / 32];
+    if constexpr (MASK) {
+#pragma unroll
+      for (int i = 0; i < KH * TA_BN / 32; ++i) kb[i] = mask_bias(0, lane + 32 * i);
+      mbar_wait(q_full, 0);
+      for (int r = lane; r < NQ * TA_BM; r += 32)
+        *reinterpret_cast<uint16_t*>(sQ + r * 128 + ((((D >> 3) ^ (r & 7)) << 4) | ((D & 7) << 1))) = 0x3F80;
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (leader) mbar_arrive(q_ready);
+    }
+    auto patch = [&](int j) {
       const int s = j % ST;
       mbar_wait(&kv_full[s], (j / ST) & 1);
 #pragma unroll
       for (int r = lane; r < KH * TA_BN; r += 32)  // 128B-swizzled tile: element D of row r sits in chunk (D/8) ^ (r & 7)
         *reinterpret_cast<uint16_t*>(sV + s * KH * Cfg::V_BYTES + r * 128 + ((((D >> 3) ^ (r & 7)) << 4) | ((D & 7) << 1))) = 0x3F80;
+      if constexpr (MASK) {
+#pragma unroll
+        for (int i = 0; i < KH * TA_BN / 32; ++i) {
+          const int r = lane + 32 * i;
+          *reinterpret_cast<uint16_t*>(sK + s * KH * Cfg::K_BYTES + r * 128 + ((((D >> 3) ^ (r & 7)) << 4) | ((D & 7) << 1))) = kb[i];
+        }
+        if (j + 1 < n_tiles) {
+#pragma unroll
+          for (int i = 0; i < KH * TA_BN / 32; ++i) kb[i] = mask_bias(j + 1, lane + 32 * i);
+        }
+      }
       fence_proxy_async_smem();
       __syncwarp();
-      if (leader) {
-        mbar_arrive(&v_ready[s]);
-        if (j + 2 < n_tiles) issue_kv(j + 2);
+      if (leader) mbar_arrive(&v_ready[s]);
+    };
+    if constexpr (MASK) {
+      // the issuer needs the PATCHED K tile j + 1 while it works on tile j: patch one tile ahead of the load that may block on a
+      // ring slot (tile j + 2 waits for tile j - 1 to be consumed)
+      patch(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) patch(j + 1);
+        if (leader && j + 2 < n_tiles) issue_kv(j + 2);
+        __syncwarp();
       }
-      __syncwarp();
+    } else {
+      for (int j = 0; j < n_tiles; ++j) {
+        patch(j);
+        if (leader && j + 2 < n_tiles) issue_kv(j + 2);
+        __syncwarp();
+      }
     }
   } else if (warp == kMma) {
     if (elect_one()) {
@@ -677,8 +724,8 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
         }
         umma_commit(&s_full[g]);
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
+      mbar_wait(MASK ? q_ready : q_full, 0);
+      mbar_wait(MASK ? &v_ready[0] : &kv_full[0], 0);
       tc_fence_after();
       // PING-PONG: the tiles form two halves; the second half's first scores are only produced once the first half
       // has finished its first softmax.  From then on the blocking round-robin below keeps the halves half a period
@@ -693,7 +740,7 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
         const int s = j % ST;
         const bool more = j + 1 < n_tiles;
         mbar_wait(&v_ready[s], (j / ST) & 1);                     // V_j carries its ones column
-        if (more) mbar_wait(&kv_full[(j + 1) % ST], ((j + 1) / ST) & 1);
+        if (more) mbar_wait(MASK ? &v_ready[(j + 1) % ST] : &kv_full[(j + 1) % ST], ((j + 1) / ST) & 1);
         tc_fence_after();
 #pragma unroll
         for (int g = 0; g < G; ++g) {
@@ -860,7 +907,7 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
 }
 
 // tQ4 / tQ2: Q maps are identical (128-row boxes); the tail launch only changes the unit size.
-template <int D, int EMU>
+template <int D, int EMU, bool MASK = false>
 static int launch_ta_quad(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtensorMap& tV, const TaParams& p, int B, int H,
                           cudaStream_t stream) {
   using Cfg = TaCfg<D>;
@@ -871,9 +918,9 @@ static int launch_ta_quad(const CUtensorMap& tQ, const CUtensorMap& tK, const CU
   static DevOnce configured;
   const int cfg_dev = af_device();
   if (!configured.done(cfg_dev)) {
-    AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 4, EMU, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
-    AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 2, EMU, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-    AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 4, EMU, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smemS));
+    AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 4, EMU, false, MASK>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+    AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 2, EMU, false, MASK>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 4, EMU, true, MASK>), cudaFuncAttributeMaxDynamicSharedMemorySize, smemS));
     configured.set(cfg_dev);
   }
   static int tail_mode = -1;
@@ -889,14 +936,14 @@ static int launch_ta_quad(const CUtensorMap& tQ, const CUtensorMap& tK, const CU
   int bulk = (units4 / n_sm) * n_sm;
   if (p.Lq % (4 * TA_BM) != 0 || bulk == 0) bulk = units4;
   if (bulk > 0) {
-    AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_quad_kernel<D, 4, EMU, false>, dim3(bulk), dim3(18 * 32), smem4, stream, tQ, tK, tV, p, 0, H));
+    AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_quad_kernel<D, 4, EMU, false, MASK>, dim3(bulk), dim3(18 * 32), smem4, stream, tQ, tK, tV, p, 0, H));
     ++g_launch_count;
   }
   if (units4 > bulk) {
     if (tail_mode == 1 && n_ktiles % 2 == 0 && p.Lk % TA_BN == 0)
-      AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_quad_kernel<D, 4, EMU, true>, dim3(2 * (units4 - bulk)), dim3(18 * 32), smemS, stream, tQ, tK, tV, p, 2 * bulk, H));
+      AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_quad_kernel<D, 4, EMU, true, MASK>, dim3(2 * (units4 - bulk)), dim3(18 * 32), smemS, stream, tQ, tK, tV, p, 2 * bulk, H));
     else
-      AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_quad_kernel<D, 2, EMU, false>, dim3(2 * (units4 - bulk)), dim3(10 * 32), smem2, stream, tQ, tK, tV, p, 2 * bulk, H));
+      AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_quad_kernel<D, 2, EMU, false, MASK>, dim3(2 * (units4 - bulk)), dim3(10 * 32), smem2, stream, tQ, tK, tV, p, 2 * bulk, H));
     ++g_launch_count;
   }
   AF_CUDA(cudaGetLastError());
@@ -1236,8 +1283,10 @@ static int launch_tc_cross(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_
 int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sh,
                      int64_t k_sn, const void* v, int64_t v_sb, int64_t v_sh, int64_t v_sn, void* o, int64_t o_sb,
                      int64_t o_sn, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t d, int64_t drow_q, int64_t drow_kv,
-                     float scale, float* lse, cudaStream_t stream) {
+                     float scale, float* lse, const uint8_t* key_mask, cudaStream_t stream) {
   if (!(d == 40 || d == 80 || d == 160)) return -1;
+  // a key mask runs on the four-tile kernel only (d = 40, level A: the case that costs 3.5x on the warp-MMA kernel)
+  if (key_mask && !(d == 40 && drow_q == 40 && drow_kv == 40 && Lq >= 2 * TQ_G * TA_BM && Lk > 128)) return -1;
   // drow_* = elements that exist in a row: d, or the zero-padded width of a head-major buffer
   if (drow_q < d) drow_q = d;
   if (drow_kv < d) drow_kv = d;
@@ -1264,6 +1313,7 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, co
   p.Lk = (int)Lk;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse;
+  p.key_mask = key_mask;
   static int emu = -1, psmem = 0, mc = 1;
   static bool emu_set = false;
   if (emu < 0) {
@@ -1281,6 +1331,7 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, co
     const char* e = getenv("ADAFACE_ATTN_QUAD");    // 1 (default): four query tiles per CTA, one in-order MMA issuer (d = 40)
     quad = (e && e[0] == '0') ? 0 : 1;
   }
+  if (key_mask) return (quad && mc && !psmem) ? launch_ta_quad<40, 5, true>(tQ, tK, tV, p, ib, ih, stream) : -1;
   if (quad && mc && !psmem && d == 40 && Lq >= 2 * TQ_G * TA_BM && Lk > 128) {
     switch (emu_set ? emu : 5) {      // default: 2 of every 8 exp2 pairs on the FMA pipe, degree-2 polynomial (round 2, us: EMU 2: 298.0, 3: 311.3,
                                       // 5 (= 2 pairs, degree 2): 294.9, 6: 306.2, 7: 310.3; round 1: 366 / 349 / 333 / 334 / 342 for 0..4)

@@ -151,7 +151,7 @@ int attn_fwd(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const
              int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, const uint8_t*, int, float, float*, cudaStream_t);
 int attn_fwd_tcgen05(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, const void*, int64_t,
                      int64_t, int64_t, void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
-                     float, float*, cudaStream_t);
+                     float, float*, const uint8_t*, cudaStream_t);
 int attn_bwd(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t,
              int64_t, const void*, int64_t, int64_t, const float*, float*, void*, int64_t, int64_t, void*, int64_t, int64_t,
              void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, const uint8_t*, int, float, cudaStream_t);
@@ -243,7 +243,7 @@ int adaface_attn_headmajor_fwd(const void* q, int64_t q_sb, int64_t q_sh, int64_
                                int64_t o_sb, int64_t o_sn, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t d,
                                int64_t drow_q, int64_t drow_kv, float scale, float* lse, void* stream) {
   const int rc = attn_fwd_tcgen05(q, q_sb, q_sh, q_sn, k, k_sb, k_sh, k_sn, v, v_sb, v_sh, v_sn, o, o_sb, o_sn, B, H, Lq, Lk,
-                                  d, drow_q, drow_kv, scale, lse, (cudaStream_t)stream);
+                                  d, drow_q, drow_kv, scale, lse, nullptr, (cudaStream_t)stream);
   if (rc < 0) set_error("adaface_attn_headmajor_fwd: unsupported head dim %lld (40, 80, 160)", (long long)d);
   return rc < 0 ? 1 : rc;
 }

@@ -16,6 +16,11 @@ def ops():
     return a.ops
 
 
+def a_lib():
+    import adaface_dev_b200 as a
+    return a._lib
+
+
 def rnd(*shape, std=1.0, seed=0, dtype=BF):
     g = torch.Generator().manual_seed(seed)
     return (torch.randn(*shape, generator=g) * std).to(dtype).cuda()
@@ -162,6 +167,42 @@ def test_attention_fused_qkv_views_and_key_mask():
     o = ops().attention(q, k, v, H, d ** -0.5, key_mask=mask)
     ref, _, _ = ref_attn(q, k, v, H, d ** -0.5, key_mask=mask)
     assert maxerr(o, ref) < 2e-2
+
+
+@pytest.mark.parametrize("B,Lq,Lk,pattern", [(2, 4096, 4096, "random"), (2, 2048, 1111, "random"), (5, 2048, 2048, "lead"), (3, 4096, 4096, "blocks"),
+                                             (1, 1024, 129, "last_only")])
+def test_attention_key_mask_on_tcgen05(B, Lq, Lk, pattern):
+    """img_mask self-attention at level A (dalc:254-273) on the four-tile tcgen05 kernel: the mask rides in the spare K column of
+    the zero-padded head dim.  Patterns: random keys, the first key tiles entirely masked (their partial results must be erased by
+    the first rescale), whole 64-key tiles masked here and there, a single surviving key in the ragged last tile; bulk + tail
+    launches (B = 5 / 3) and the log-sum-exp of the training path."""
+    import math
+    H, d = 8, 40
+    C = H * d
+    qkv = rnd(B, max(Lq, Lk), 3 * C, seed=11)
+    q, k, v = qkv[:, :Lq, :C], qkv[:, :Lk, C:2 * C], qkv[:, :Lk, 2 * C:]
+    g = torch.Generator().manual_seed(5)
+    if pattern == "random":
+        mask = torch.rand(B, Lk, generator=g) > 0.4
+    elif pattern == "lead":
+        mask = torch.ones(B, Lk, dtype=torch.bool)
+        mask[:, :200] = False
+        mask[0, :1500] = False
+    elif pattern == "blocks":
+        mask = (torch.rand(B, Lk // 64, generator=g) > 0.5).repeat_interleave(64, dim=1)
+        mask[:, -1] = True
+    else:
+        mask = torch.zeros(B, Lk, dtype=torch.bool)
+        mask[:, -1] = True
+    mask = mask.to(torch.uint8).cuda()
+    lse = torch.empty(B, H, Lq, device="cuda")
+    n0 = a_lib().launch_count()
+    o = ops().attention(q, k, v, H, d ** -0.5, key_mask=mask, lse=lse)
+    ref, s, _ = ref_attn(q, k, v, H, d ** -0.5, key_mask=mask)
+    assert maxerr(o, ref) < 2e-2
+    rlse = torch.logsumexp(s, dim=-1) * math.log2(math.e)
+    assert (lse.cpu() - rlse).abs().max().item() < 2e-2
+    assert a_lib().launch_count() - n0 <= 2      # bulk (+ tail) launch of the four-tile kernel: the mask no longer falls to the warp-MMA kernel
 
 
 @pytest.mark.parametrize("mult,T", [(1, 20), (2, 20), (4, 24), (1, 77), (2, 77), (8, 77)])
