@@ -88,7 +88,26 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = RESIDENT_BYTES + STAGES * STAGE_BYTES + STORE_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// Exact (erf) GELU, F.gelu's default (ldm/modules/attention.py:31-41 GEGLU).  The GEGLU epilogue evaluates it 32 times per chunk and
+// is instruction-bound (erff(): ~30 instructions and a MUFU each; an Abramowitz-Stegun form with a reciprocal and an exp2 was
+// SLOWER: two quarter-rate MUFU ops per element).  Here erf(z), z = |x| / sqrt 2 clamped to 3, is an odd degree-17 polynomial
+// (least-squares fit on Chebyshev nodes, max |error| 2e-5 in fp32 -- two orders below the bf16 rounding of the product that
+// follows): 8 FMAs on the FMA pipe, no MUFU, no branch.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fminf(fabsf(x) * 0.70710678118654752f, 3.0f);
+  const float u = z * z;
+  float p = fmaf(3.912539625616773e-08f, u, -1.883036475192057e-06f);
+  p = fmaf(p, u, 4.008835821878165e-05f);
+  p = fmaf(p, u, -0.000502921873703599f);
+  p = fmaf(p, u, 0.004196857567876577f);
+  p = fmaf(p, u, -0.024998901411890984f);
+  p = fmaf(p, u, 0.11093080043792725f);
+  p = fmaf(p, u, -0.3752196431159973f);
+  p = fmaf(p, u, 1.1282505989074707f);
+  const float erf_abs = fminf(p * z, 1.f);                    // erf(|x| / sqrt 2)
+  const float h = 0.5f * x;
+  return fmaf(fabsf(h), erf_abs, h);                          // 0.5 x (1 + sign(x) erf(|x| / sqrt 2))
+}
 
 // Epilogue of one 32-column chunk of one row: scale / bias / activation / residual / convert / store.
 // `c0` = first tile-local column of the chunk, `g` = the matching gate values when ACT == GEGLU.
@@ -120,24 +139,32 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmEpilogue& ep, const u
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-  auto affine = [&](float (&x)[32], int cbase) {
-    if (ep.colscale) {
+  // per-column vectors: a FULL chunk reads its 32 floats as eight 16-byte loads (the scalar form issued 32 loads per vector and
+  // chunk -- a third of the general epilogue's instructions)
+  auto vec_op = [&](float (&x)[32], const float* vec, int cbase, bool mul) {
+    if (FULL && (reinterpret_cast<uintptr_t>(vec + cbase) & 15) == 0) {
+      const float4* v4 = reinterpret_cast<const float4*>(vec + cbase);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(v4 + j);
+        if (mul) {
+          x[4 * j] *= b.x; x[4 * j + 1] *= b.y; x[4 * j + 2] *= b.z; x[4 * j + 3] *= b.w;
+        } else {
+          x[4 * j] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
+        }
+      }
+    } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (FULL || cbase + j < ep.N) x[j] *= __ldg(ep.colscale + cbase + j);
-    }
-    if (ep.bias) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (FULL || cbase + j < ep.N) x[j] += __ldg(ep.bias + cbase + j);
+        if (FULL || cbase + j < ep.N) x[j] = mul ? x[j] * __ldg(vec + cbase + j) : x[j] + __ldg(vec + cbase + j);
     }
   };
+  auto affine = [&](float (&x)[32], int cbase) {
+    if (ep.colscale) vec_op(x, ep.colscale, cbase, true);
+    if (ep.bias) vec_op(x, ep.bias, cbase, false);
+  };
   affine(f, col0);
-  if (rowbias) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (FULL || col0 + j < ep.N) f[j] += __ldg(rowbias + col0 + j);
-  }
+  if (rowbias) vec_op(f, rowbias, col0, false);
   int out_col0 = col0;
   int out_n = ep.N;
   if (geglu) {
@@ -159,14 +186,35 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmEpilogue& ep, const u
   if (ep.residual && row_ok) {
     if (ep.res_f32) {
       const float* r = reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + out_col0;
+      if (FULL && (reinterpret_cast<uintptr_t>(r) & 15) == 0) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (FULL || out_col0 + j < out_n) f[j] += r[j];
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = *reinterpret_cast<const float4*>(r + 4 * j);
+          f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (FULL || out_col0 + j < out_n) f[j] += r[j];
+      }
     } else {
       const bf16* r = reinterpret_cast<const bf16*>(ep.residual) + (long long)row * ep.ldr + out_col0;
+      if (FULL && (reinterpret_cast<uintptr_t>(r) & 15) == 0) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (FULL || out_col0 + j < out_n) f[j] += __bfloat162float(r[j]);
+        for (int j = 0; j < 4; ++j) {
+          const uint4 b = *reinterpret_cast<const uint4*>(r + 8 * j);
+          const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            f[8 * j + 2 * u] += __uint_as_float(w[u] << 16);
+            f[8 * j + 2 * u + 1] += __uint_as_float(w[u] & 0xffff0000u);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (FULL || out_col0 + j < out_n) f[j] += __bfloat162float(r[j]);
+      }
     }
   }
   if (ep.y_f32) {
