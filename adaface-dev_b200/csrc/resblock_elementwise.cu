@@ -131,7 +131,15 @@ __global__ void __launch_bounds__(GN_STATS_THREADS) gn_tokens_stats_kernel(const
   }
 }
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
+// SiLU.  The GroupNorm + SiLU apply pass is MUFU-bound, not HBM-bound: v / (1 + exp(-v)) costs an ex2 AND a reciprocal on the
+// 16-lane special-function unit (B = 8, 64 x 64, 320 channels: 84 M elements x 2 = 36 us of MUFU time against 6.5 us of HBM time).
+// x sigmoid(x) = 0.5 x (1 + tanh(x / 2)) needs ONE MUFU op (tanh.approx.f32, relative error 2^-11: below the bf16 rounding of y).
+__device__ __forceinline__ float silu_f(float v) {
+  float t;
+  const float h = 0.5f * v;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 // y[b, r, c] = act(x[b, r, c] * a[b, c] + s[b, c]); 8 channels (16 bytes) per thread, a / s of the image in shared memory.
 template <int ACT>
@@ -155,12 +163,15 @@ __global__ void __launch_bounds__(256) gn_tokens_apply_kernel(const bf16* __rest
     const int c0 = (i % vec) << 3;
     const uint4 u = xv[i];
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    const float4 a0 = *reinterpret_cast<const float4*>(as_s + c0), a1 = *reinterpret_cast<const float4*>(as_s + c0 + 4);
+    const float4 s0 = *reinterpret_cast<const float4*>(as_s + C + c0), s1 = *reinterpret_cast<const float4*>(as_s + C + c0 + 4);
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
     uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xffff0000u);
-      lo = lo * as_s[c0 + 2 * j] + as_s[C + c0 + 2 * j];
-      hi = hi * as_s[c0 + 2 * j + 1] + as_s[C + c0 + 2 * j + 1];
+      lo = lo * av[2 * j] + sv[2 * j];
+      hi = hi * av[2 * j + 1] + sv[2 * j + 1];
       if (ACT == 1) {
         lo = silu_f(lo);
         hi = silu_f(hi);
