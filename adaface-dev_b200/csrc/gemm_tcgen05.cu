@@ -439,6 +439,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
             m0 = img0 * ep.cv_HW + yc * ep.cv_img_rows;
           }
         }
+        // (tap, channel chunk) of the K block, advanced incrementally: the producer thread was the convolution's bottleneck -- 500 clk
+        // per K block against 320 clk of MMA at BN = 160 (traced), a good part of it two integer divisions by run-time values
+        int cv_ch = 0, cv_kx = 0, cv_ky = 0;
+        uint32_t cv_tx = 0;
+        if constexpr (CONV) {
+          const int tap0 = kb_lo / ep.cv_kc;
+          cv_ch = kb_lo - tap0 * ep.cv_kc;
+          cv_ky = tap0 / 3;
+          cv_kx = tap0 - cv_ky * 3;
+          cv_tx = (uint32_t)(ep.cv_img_rows * ep.cv_imgs * 128 + Cfg::B_STAGE_BYTES);   // the A box holds cv_img_rows * cv_imgs pixels x 128 bytes (zero-filled parts included)
+        }
+        const int cv_kc = CONV ? ep.cv_kc : 1, cv_stride = CONV ? ep.cv_stride : 1, kb1 = ep.num_kb1;
         for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const int s = it % STAGES;
           const bool tr = ep.trace && blockIdx.x == 0 && it < 128;
@@ -447,21 +459,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_tcgen05_kernel(const 
           if (tr) ep.trace[it * 2 + 1] = clock64();
           uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          if (CONV && kb < ep.num_kb1) {
+          if (CONV && kb < kb1) {
             if constexpr (CONV) {
-              // the A box holds cv_img_rows * cv_imgs pixels x 128 bytes (zero-filled parts included)
-              mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(ep.cv_img_rows * ep.cv_imgs * 128 + Cfg::B_STAGE_BYTES));
-              const int tap = kb / ep.cv_kc, ch = kb - tap * ep.cv_kc;
-              const int ky = tap / 3, kx = tap - ky * 3;
-              if (ep.cv_stride == 1) {
-                tma_load_4d(sa, &cmaps.m[0], &full_bar[s], ch * GEMM_BK, kx - 1, y0 + ky - 1, img0);
+              mbar_arrive_expect_tx(&full_bar[s], cv_tx);
+              if (cv_stride == 1) {
+                tma_load_4d(sa, &cmaps.m[0], &full_bar[s], cv_ch * GEMM_BK, cv_kx - 1, y0 + cv_ky - 1, img0);
               } else {
                 // input (2 y + ky - 1, 2 x + kx - 1): parity 1 / index -1 for k = 0, parity 0 / index 0 for k = 1,
                 // parity 1 / index 0 for k = 2
-                const int py = ky != 1, px = kx != 1;
-                tma_load_4d(sa, &cmaps.m[py * 2 + px], &full_bar[s], ch * GEMM_BK, kx == 0 ? -1 : 0, y0 + (ky == 0 ? -1 : 0), img0);
+                const int py = cv_ky != 1, px = cv_kx != 1;
+                tma_load_4d(sa, &cmaps.m[py * 2 + px], &full_bar[s], cv_ch * GEMM_BK, cv_kx == 0 ? -1 : 0, y0 + (cv_ky == 0 ? -1 : 0), img0);
               }
               tma_load_2d(sb, &tmB, &full_bar[s], kb * GEMM_BK, n0);
+              if (++cv_ch == cv_kc) {
+                cv_ch = 0;
+                if (++cv_kx == 3) {
+                  cv_kx = 0;
+                  ++cv_ky;
+                }
+              }
             }
             continue;
           }
@@ -794,6 +810,35 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   return 0;
 }
 
+// Diagnosis (env ADAFACE_GEMM_TRACE): CTA 0 stamps clock64 at its producer / MMA / epilogue / store hand-offs; dumped to stderr.
+static long long* trace_begin() {
+  static long long* trace_buf = nullptr;
+  if (!getenv("ADAFACE_GEMM_TRACE")) return nullptr;
+  if (!trace_buf) cudaMalloc(&trace_buf, 2048 * 8);
+  cudaMemset(trace_buf, 0, 2048 * 8);
+  return trace_buf;
+}
+static void trace_dump(const long long* dev, const char* what, long long M, long long N, long long K, int BN, int num_kb) {
+  static long long h[2048];
+  cudaDeviceSynchronize();
+  cudaMemcpy(h, dev, sizeof(h), cudaMemcpyDeviceToHost);
+  const long long t0 = h[0];
+  fprintf(stderr, "%s trace M=%lld N=%lld K=%lld BN=%d kb=%d\n", what, M, N, K, BN, num_kb);
+  for (int i = 0; i < 64; ++i)
+    fprintf(stderr, "it %3d  tma: wait %6lld..%6lld | mma: wait %6lld..%6lld issued %6lld\n", i, h[i * 2] - t0, h[i * 2 + 1] - t0, h[256 + i * 3] - t0,
+            h[256 + i * 3 + 1] - t0, h[256 + i * 3 + 2] - t0);
+  for (int t = 0; t < 12; ++t)
+    fprintf(stderr, "tile %2d  mma acc_empty wait %6lld..%6lld | epi w0: acc_full wait %6lld..%6lld done %6lld | epi w7: %6lld..%6lld done %6lld\n", t,
+            h[1024 + t * 2] - t0, h[1024 + t * 2 + 1] - t0, h[1200 + t * 3] - t0, h[1200 + t * 3 + 1] - t0, h[1200 + t * 3 + 2] - t0, h[1300 + t * 3] - t0,
+            h[1300 + t * 3 + 1] - t0, h[1300 + t * 3 + 2] - t0);
+  for (int b = 0; b < 12; ++b)
+    fprintf(stderr, "staging %2d (warp 0): enter %6lld  slab free %6lld  written %6lld  fenced %6lld  arrived %6lld\n", b, h[1800 + b * 5] - t0, h[1800 + b * 5 + 1] - t0,
+            h[1800 + b * 5 + 2] - t0, h[1800 + b * 5 + 3] - t0, h[1800 + b * 5 + 4] - t0);
+  for (int b = 0; b < 30; ++b)
+    fprintf(stderr, "store box %2d: wait full %6lld..%6lld  issued %6lld  prev read done %6lld\n", b, h[1600 + b * 4] - t0, h[1600 + b * 4 + 1] - t0, h[1600 + b * 4 + 2] - t0,
+            h[1600 + b * 4 + 3] - t0);
+}
+
 static bool tma_store_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -906,13 +951,7 @@ int proj_lora_fwd(const void* x, int64_t ldx, const void* w, const void* t, int6
     ep.dbg = e ? atoi(e) : 0;
   }
   const int n_tiles = (int)((N + BN - 1) / BN);
-  ep.trace = nullptr;
-  static long long* trace_buf = nullptr;
-  if (getenv("ADAFACE_GEMM_TRACE")) {
-    if (!trace_buf) cudaMalloc(&trace_buf, 2048 * 8);
-    cudaMemset(trace_buf, 0, 2048 * 8);
-    ep.trace = trace_buf;
-  }
+  ep.trace = trace_begin();
   CUtensorMap tY = tA;
   ep.tma_store = 0;
   if (tma_store_enabled() && hs_d == 0 && y_dtype == ADAFACE_BF16 && ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
@@ -931,30 +970,7 @@ int proj_lora_fwd(const void* x, int64_t ldx, const void* w, const void* t, int6
     set_error("proj_lora_fwd: unreachable tile width %d", BN);
     return 1;
   }
-  if (ep.trace && rc == 0) {      // diagnosis: dump CTA 0's hand-off stamps (relative to its first stamp)
-    static long long h[2048];
-    cudaDeviceSynchronize();
-    cudaMemcpy(h, ep.trace, sizeof(h), cudaMemcpyDeviceToHost);
-    const long long t0 = h[0];
-    fprintf(stderr, "GEMM trace M=%lld N=%lld K=%lld BN=%d kb=%d\n", (long long)M, (long long)N, (long long)K, BN, ep.num_kb1 + ep.num_kb2);
-    for (int i = 0; i < 64; ++i)
-      fprintf(stderr, "it %3d  tma: wait %6lld..%6lld | mma: wait %6lld..%6lld issued %6lld\n", i, h[i * 2] - t0, h[i * 2 + 1] - t0, h[256 + i * 3] - t0,
-              h[256 + i * 3 + 1] - t0, h[256 + i * 3 + 2] - t0);
-    for (int t = 0; t < 12; ++t)
-      fprintf(stderr, "tile %2d  mma acc_empty wait %6lld..%6lld | epi w0: acc_full wait %6lld..%6lld done %6lld | epi w7: %6lld..%6lld done %6lld\n", t,
-              h[1024 + t * 2] - t0, h[1024 + t * 2 + 1] - t0, h[1200 + t * 3] - t0, h[1200 + t * 3 + 1] - t0, h[1200 + t * 3 + 2] - t0, h[1300 + t * 3] - t0,
-              h[1300 + t * 3 + 1] - t0, h[1300 + t * 3 + 2] - t0);
-    for (int t = 0; t < 4; ++t)
-      for (int c = 0; c < 3; ++c)
-        fprintf(stderr, "tile %d chunk %d (warp 0): begin %6lld  tmem read %6lld  staged %6lld\n", t, 2 * c, h[1400 + (t * 8 + c) * 3] - t0, h[1400 + (t * 8 + c) * 3 + 1] - t0,
-                h[1400 + (t * 8 + c) * 3 + 2] - t0);
-    for (int b = 0; b < 12; ++b)
-      fprintf(stderr, "staging %2d (warp 0): enter %6lld  slab free %6lld  written %6lld  fenced %6lld  arrived %6lld\n", b, h[1800 + b * 5] - t0, h[1800 + b * 5 + 1] - t0,
-              h[1800 + b * 5 + 2] - t0, h[1800 + b * 5 + 3] - t0, h[1800 + b * 5 + 4] - t0);
-    for (int b = 0; b < 30; ++b)
-      fprintf(stderr, "store box %2d: wait full %6lld..%6lld  issued %6lld  prev read done %6lld\n", b, h[1600 + b * 4] - t0, h[1600 + b * 4 + 1] - t0, h[1600 + b * 4 + 2] - t0,
-              h[1600 + b * 4 + 3] - t0);
-  }
+  if (ep.trace && rc == 0) trace_dump(ep.trace, "GEMM", (long long)M, (long long)N, (long long)K, BN, ep.num_kb1 + ep.num_kb2);
   return rc;
 }
 
@@ -1083,7 +1099,7 @@ int conv3x3_fwd(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, con
   ep.kb_per_split = 0;
   ep.splitk_ws = nullptr;
   ep.dbg = 0;
-  ep.trace = nullptr;
+  ep.trace = trace_begin();
 
   int BN = pick_tile_width(Cout, ep.num_m, act);
   // The tile-width cost model is the projection GEMM's (short K, per-tile overhead matters).  With K = 9 Cin the main loop
@@ -1163,6 +1179,7 @@ int conv3x3_fwd(const void* x, int64_t B, int64_t H, int64_t W, int64_t Cin, con
       set_error("conv3x3_fwd: unreachable tile width %d", BN);
       return 1;
   }
+  if (ep.trace && rc == 0) trace_dump(ep.trace, "conv3x3", (long long)M, (long long)Cout, (long long)(9 * kc * GEMM_BK), BN, ep.num_kb1 + ep.num_kb2);
   if (rc || ep.splits == 1) return rc;
   const long long n_thr = (long long)M * (Cout / 4);
   conv_splitk_reduce_kernel<<<(unsigned)((n_thr + 255) / 256), 256, 0, stream>>>(ep);
