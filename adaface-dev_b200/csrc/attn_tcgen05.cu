@@ -14,6 +14,7 @@
 //              in the swizzled K-major layout, final O / l epilogue.
 // Reference arithmetic: F.scaled_dot_product_attention at dalc:321 / ldm attention.py:181-204 (no mask).
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -21,6 +22,12 @@
 #include "../../include/adaface_b200.h"
 
 namespace adaface {
+
+#ifdef AF_ATTN_TRACE
+#define AF_ATTN_TR(...) __VA_ARGS__
+#else
+#define AF_ATTN_TR(...)
+#endif
 
 extern long long g_launch_count;
 
@@ -569,8 +576,13 @@ constexpr int TQ_ST = 3;                      // K/V ring: tiles j and j+1 are l
 // column it already writes into V -- and the tensor core adds the mask bias to the scores: S = q.k + 1 * bias.  The softmax warps
 // run the unmasked code (a masked key's exp2 underflows to exactly 0; a tile of only masked keys is erased by the next rescale,
 // whose factor 2^(-65536 scale) is 0); the issuer waits for the patched tiles (q_ready, v_ready) instead of the raw TMA barriers.
-template <int D, int G, int EMU, bool SPLIT, bool MASK = false>
-__global__ void __launch_bounds__((4 * G + 2) * 32, 1)
+// NI = MMA-issuing warps (1 | 2).  Traced (-DAF_ATTN_TRACE build, ADAFACE_ATTN_TRACE=1): per 64-key step (2150 clk) the single
+// issuer spends ~300 clk in two K/V barrier waits, then per tile a p_full wait (>= 100 clk even when complete) and 130-260 clk for
+// 4 P.V + 3 Q.K issues + commit; a softmax warp works ~1100 clk (TMEM read + max 255, exp2 + pack 840) and waits ~900 clk for its
+// next scores.  Giving each ping-pong half its own issuer (NI = 2) halves the issuer's chain but does NOT shorten the step (297.0 vs
+// 295.9 us): the period is one tile's own dependency chain (softmax -> P.V / Q.K -> hand-offs) with the MUFU pipe 71 % busy.
+template <int D, int G, int EMU, bool SPLIT, bool MASK = false, int NI = 1>
+__global__ void __launch_bounds__((4 * G + 1 + NI) * 32, 1)
 attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                              const __grid_constant__ CUtensorMap tmV, const TaParams p, const int unit0, const int H) {
   using Cfg = TaCfg<D>;
@@ -613,14 +625,14 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
     mbar_init(q_full, 1);
     for (int s = 0; s < ST; ++s) {
       mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&kv_empty[s], NI);
       mbar_init(&v_ready[s], 1);
     }
     for (int g = 0; g < G; ++g) {
       mbar_init(&s_full[g], 1);
       mbar_init(&p_full[g], 128);
     }
-    mbar_init(o_full, 1);
+    mbar_init(o_full, NI);
     mbar_init(q_ready, 1);
     fence_barrier_init();
   } else if (warp == kMma) {
@@ -709,8 +721,11 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
         __syncwarp();
       }
     }
-  } else if (warp == kMma) {
+  } else if (warp >= kMma) {
     if (elect_one()) {
+      static_assert(NI == 1 || (NI == 2 && G % 2 == 0), "one issuer, or one per ping-pong half");
+      constexpr int GPI = G / NI;                                 // tiles per issuer
+      const int g_lo = (warp - kMma) * GPI;
       constexpr uint32_t idesc_qk = make_idesc_bf16_f32(TA_BM, TA_BN, false);
       constexpr uint32_t idesc_pv = make_idesc_bf16_f32(TA_BM, DO, true);
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
@@ -730,21 +745,35 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
       // PING-PONG: the tiles form two halves; the second half's first scores are only produced once the first half
       // has finished its first softmax.  From then on the blocking round-robin below keeps the halves half a period
       // apart: while one half exponentiates (XU), the other half's P.V / Q.K run on the tensor pipe.
+      if constexpr (NI == 1) {
 #pragma unroll
-      for (int g = 0; g < G / 2; ++g) issue_qk(g, 0);
+        for (int g = 0; g < G / 2; ++g) issue_qk(g, 0);
 #pragma unroll
-      for (int g = 0; g < G / 2; ++g) mbar_wait(&p_full[g], 0);
+        for (int g = 0; g < G / 2; ++g) mbar_wait(&p_full[g], 0);
 #pragma unroll
-      for (int g = G / 2; g < G; ++g) issue_qk(g, 0);
+        for (int g = G / 2; g < G; ++g) issue_qk(g, 0);
+      } else {
+        if (g_lo != 0) {          // second issuer: starts when the first half's P_0 exist (their next phase is > 1000 clk away)
+#pragma unroll
+          for (int g = 0; g < GPI; ++g) mbar_wait(&p_full[g], 0);
+        }
+#pragma unroll
+        for (int g = 0; g < GPI; ++g) issue_qk(g_lo + g, 0);
+      }
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j % ST;
         const bool more = j + 1 < n_tiles;
+        AF_ATTN_TR(const bool tr = p.trace && blockIdx.x == 0 && g_lo == 0 && j >= 8 && j < 16; if (tr) p.trace[(j - 8) * 16] = clock64();)
         mbar_wait(&v_ready[s], (j / ST) & 1);                     // V_j carries its ones column
         if (more) mbar_wait(MASK ? &v_ready[(j + 1) % ST] : &kv_full[(j + 1) % ST], ((j + 1) / ST) & 1);
         tc_fence_after();
+        AF_ATTN_TR(if (tr) p.trace[(j - 8) * 16 + 1] = clock64();)
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
+        for (int gi = 0; gi < GPI; ++gi) {
+          const int g = g_lo + gi;
+          AF_ATTN_TR(if (tr) p.trace[(j - 8) * 16 + 2 + gi * 3] = clock64();)
           mbar_wait(&p_full[g], j & 1);                           // tile g's P_j is in TMEM
+          AF_ATTN_TR(if (tr) p.trace[(j - 8) * 16 + 3 + gi * 3] = clock64();)
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < TA_BN / 16; ++k) {
@@ -753,8 +782,9 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
                          (j | k) != 0 ? 1u : 0u);
           }
           if (more) issue_qk(g, j + 1);                           // overwrites P_j: executes after the P.V above (in order)
+          AF_ATTN_TR(if (tr) p.trace[(j - 8) * 16 + 4 + gi * 3] = clock64();)
         }
-        umma_commit(&kv_empty[s]);                                // every tile's P.V_j has been issued
+        umma_commit(&kv_empty[s]);                                // this issuer's P.V_j have been issued
       }
       umma_commit(o_full);
     }
@@ -764,7 +794,10 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
     const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(g * TMEM_G);
     float m_ref = -INFINITY;
     for (int j = 0; j < n_tiles; ++j) {
+      AF_ATTN_TR(const bool str_ = p.trace && blockIdx.x == 0 && lane == 0 && qd == 0 && j >= 8 && j < 16; long long* tp = p.trace + 256 + g * 64 + (j - 8) * 8;
+                 if (str_) tp[0] = clock64();)
       mbar_wait(&s_full[g], j & 1);          // also implies P V_{j-1} of this tile has retired
+      AF_ATTN_TR(if (str_) tp[1] = clock64();)
       tc_fence_after();
       const int valid = p.Lk - (j + (SPLIT ? (g & 1) * n_tiles : 0)) * TA_BN;
       // the 64 scores of this row are read from TMEM ONCE and stay in registers for both the max and the exp pass
@@ -783,6 +816,7 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
         for (int u = 0; u < 4; ++u) m4[u] = fmaxf(m4[u], __uint_as_float(v[i + u]));
       }
       const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
+      AF_ATTN_TR(if (str_) tp[2] = clock64() + (mx > 1e30f ? 1 : 0);)       // (after the row maximum: the TMEM load has landed)
       if (j == 0) {
         m_ref = (mx == -INFINITY) ? 0.f : mx;
       } else {
@@ -816,9 +850,11 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
         }
         tmem_st_32x32b_x16(t_lane + (uint32_t)(hf * 16), pk);
       }
+      AF_ATTN_TR(if (str_) tp[3] = clock64();)
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[g]);
+      AF_ATTN_TR(if (str_) tp[4] = clock64();)
     }
     mbar_wait(o_full, 0);
     tc_fence_after();
@@ -907,7 +943,7 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
 }
 
 // tQ4 / tQ2: Q maps are identical (128-row boxes); the tail launch only changes the unit size.
-template <int D, int EMU, bool MASK = false>
+template <int D, int EMU, bool MASK = false, int NI = 1>
 static int launch_ta_quad(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtensorMap& tV, const TaParams& p, int B, int H,
                           cudaStream_t stream) {
   using Cfg = TaCfg<D>;
@@ -918,9 +954,9 @@ static int launch_ta_quad(const CUtensorMap& tQ, const CUtensorMap& tK, const CU
   static DevOnce configured;
   const int cfg_dev = af_device();
   if (!configured.done(cfg_dev)) {
-    AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 4, EMU, false, MASK>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
-    AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 2, EMU, false, MASK>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-    AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 4, EMU, true, MASK>), cudaFuncAttributeMaxDynamicSharedMemorySize, smemS));
+    AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 4, EMU, false, MASK, NI>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+    AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 2, EMU, false, MASK, NI>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    AF_CUDA(cudaFuncSetAttribute((attn_fwd_tcgen05_quad_kernel<D, 4, EMU, true, MASK, NI>), cudaFuncAttributeMaxDynamicSharedMemorySize, smemS));
     configured.set(cfg_dev);
   }
   static int tail_mode = -1;
@@ -936,17 +972,33 @@ static int launch_ta_quad(const CUtensorMap& tQ, const CUtensorMap& tK, const CU
   int bulk = (units4 / n_sm) * n_sm;
   if (p.Lq % (4 * TA_BM) != 0 || bulk == 0) bulk = units4;
   if (bulk > 0) {
-    AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_quad_kernel<D, 4, EMU, false, MASK>, dim3(bulk), dim3(18 * 32), smem4, stream, tQ, tK, tV, p, 0, H));
+    AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_quad_kernel<D, 4, EMU, false, MASK, NI>, dim3(bulk), dim3((17 + NI) * 32), smem4, stream, tQ, tK, tV, p, 0, H));
     ++g_launch_count;
   }
   if (units4 > bulk) {
     if (tail_mode == 1 && n_ktiles % 2 == 0 && p.Lk % TA_BN == 0)
-      AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_quad_kernel<D, 4, EMU, true, MASK>, dim3(2 * (units4 - bulk)), dim3(18 * 32), smemS, stream, tQ, tK, tV, p, 2 * bulk, H));
+      AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_quad_kernel<D, 4, EMU, true, MASK, NI>, dim3(2 * (units4 - bulk)), dim3((17 + NI) * 32), smemS, stream, tQ, tK, tV, p, 2 * bulk, H));
     else
-      AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_quad_kernel<D, 2, EMU, false, MASK>, dim3(2 * (units4 - bulk)), dim3(10 * 32), smem2, stream, tQ, tK, tV, p, 2 * bulk, H));
+      AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_quad_kernel<D, 2, EMU, false, MASK, NI>, dim3(2 * (units4 - bulk)), dim3((9 + NI) * 32), smem2, stream, tQ, tK, tV, p, 2 * bulk, H));
     ++g_launch_count;
   }
   AF_CUDA(cudaGetLastError());
+  if (p.trace) {      // diagnosis: CTA 0 of the bulk launch, key tiles 8..15
+    static long long h[1024];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long t0 = h[0];
+    for (int j = 0; j < 8; ++j) {
+      fprintf(stderr, "issuer j=%2d: kv wait %6lld..%6lld |", j + 8, h[j * 16] - t0, h[j * 16 + 1] - t0);
+      for (int g = 0; g < 4; ++g) fprintf(stderr, " g%d p_full wait %6lld..%6lld issued %6lld |", g, h[j * 16 + 2 + g * 3] - t0, h[j * 16 + 3 + g * 3] - t0, h[j * 16 + 4 + g * 3] - t0);
+      fprintf(stderr, "\n");
+    }
+    for (int g = 0; g < 4; ++g)
+      for (int j = 0; j < 8; ++j) {
+        const long long* tp = h + 256 + g * 64 + j * 8;
+        fprintf(stderr, "softmax g=%d j=%2d: s_full wait %6lld..%6lld  max done %6lld  exp+pack done %6lld  arrived %6lld\n", g, j + 8, tp[0] - t0, tp[1] - t0, tp[2] - t0, tp[3] - t0, tp[4] - t0);
+      }
+  }
   return 0;
 }
 
@@ -1314,6 +1366,13 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, co
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse;
   p.key_mask = key_mask;
+  p.trace = nullptr;
+  if (getenv("ADAFACE_ATTN_TRACE")) {
+    static long long* tbuf = nullptr;
+    if (!tbuf) cudaMalloc(&tbuf, 1024 * 8);
+    cudaMemset(tbuf, 0, 1024 * 8);
+    p.trace = tbuf;
+  }
   static int emu = -1, psmem = 0, mc = 1;
   static bool emu_set = false;
   if (emu < 0) {
@@ -1333,6 +1392,12 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, co
   }
   if (key_mask) return (quad && mc && !psmem) ? launch_ta_quad<40, 5, true>(tQ, tK, tV, p, ib, ih, stream) : -1;
   if (quad && mc && !psmem && d == 40 && Lq >= 2 * TQ_G * TA_BM && Lk > 128) {
+    static int issuers = -1;
+    if (issuers < 0) {
+      const char* e = getenv("ADAFACE_ATTN_ISSUERS");      // A/B switch: 1 (default) = single MMA-issuing thread, 2 = one per ping-pong half
+      issuers = (e && e[0] == '2') ? 2 : 1;                // (measured: 297.0 us with two, 295.9 us with one -- the issuer is not the bound)
+    }
+    if (issuers == 2 && !emu_set) return launch_ta_quad<40, 5, false, 2>(tQ, tK, tV, p, ib, ih, stream);
     switch (emu_set ? emu : 5) {      // default: 2 of every 8 exp2 pairs on the FMA pipe, degree-2 polynomial (round 2, us: EMU 2: 298.0, 3: 311.3,
                                       // 5 (= 2 pairs, degree 2): 294.9, 6: 306.2, 7: 310.3; round 1: 366 / 349 / 333 / 334 / 342 for 0..4)
       case 0: return launch_ta_quad<40, 0>(tQ, tK, tV, p, ib, ih, stream);
