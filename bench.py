@@ -259,9 +259,9 @@ def build_stack(torch, a, device):
 # kernels of libadaface_b200.so per step: 16 blocks x (self: QKV GEMM, attention, out GEMM; cross: q GEMM, kv GEMM,
 # attention, out GEMM) = 112 + the tail launch of the 5 level-A self-attention calls; COUNTED LIVE in main_gpu on one eager step.
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel, from the ncu --set full capture
-# summarised in profiles/r01_ncu_full_attn_quad.txt (algorithmic: 4 * B * N * C * 2 = 83.9 MB; the 21 MB of output leave L2 after the kernel)
-ROOFLINE_TRAFFIC_BYTES = 66132224   # 64.4 MB read + 1.7 MB written inside the two launches (outputs are still in L2)
-ROOFLINE_TRAFFIC_SOURCE = "ncu --set full capture, profiles/r01_ncu_full_attn_quad.txt (dram__bytes_read.sum + dram__bytes_write.sum; not measurable inside bench.py)"
+# summarised in profiles/r02_ncu_full_attn_quad.txt (algorithmic: 4 * B * N * C * 2 = 83.9 MB; the 21 MB of output leave L2 after the kernel)
+ROOFLINE_TRAFFIC_BYTES = 67349760   # bulk 55.08 MB read + 2.94 MB written, tail 9.32 MB read, inside the two launches (outputs are still in L2)
+ROOFLINE_TRAFFIC_SOURCE = "ncu --set full capture, profiles/r02_ncu_full_attn_quad.txt (dram__bytes_read.sum + dram__bytes_write.sum; not measurable inside bench.py)"
 
 
 def run_stack(mods, xs, ctx):
@@ -333,6 +333,42 @@ def secondary_measurements(torch, a, dev, flush, pk, unet):
         out["cross_attn_fast"] = {"kernel": "attn_fwd_tcgen05_mc_kernel<40>, 77 keys", "shape": f"B={B} N={N} C={C} S={S}", "us": us,
                                   "algorithmic_bytes": by, "achieved_gbs": by / us / 1e3, "peak_gbs": hbm,
                                   "frac": by / us / 1e3 / hbm}
+        # -- img_mask self-attention at level A (dalc:254-273): key mask on the four-tile tcgen05 kernel (was the warp-MMA kernel)
+        qkv = torch.randn(B, N, 3 * C, device=dev).to(torch.bfloat16)
+        km = (torch.rand(B, N, device=dev) > 0.3).to(torch.uint8)
+        o_ = torch.empty(B, N, C, device=dev, dtype=torch.bfloat16)
+        fl = 4.0 * B * H * N * N * d
+        for nm, mask in (("self_attn_levelA_unmasked", None), ("self_attn_levelA_key_mask", km)):
+            us = _time_us(torch, flush, lambda: ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], H, d ** -0.5, key_mask=mask, out=o_))
+            out[nm] = {"kernel": "attn_fwd_tcgen05_quad_kernel<40>" + (" + key mask in the spare K column" if mask is not None else ""),
+                       "shape": f"B={B} N={N} H={H} d={d}", "us": us, "tflops": fl / us / 1e6, "peak_tflops": pk["bf16_tflops"], "frac": fl / us / 1e6 / pk["bf16_tflops"]}
+        del qkv, km, o_
+        # -- projection GEMMs as the step graph sees them: 20 back-to-back launches in one CUDA graph over rotating buffers
+        #    (inputs recently written by another launch, no host launch cost), us per launch
+        gl = {}
+        for nm, M_, N_, K_ in (("A_qkv", 32768, 960, 320), ("A_out", 32768, 320, 320), ("B_qkv", 8192, 1920, 640), ("C_qkv", 2048, 3840, 1280)):
+            xs_ = [torch.randn(M_, K_, device=dev).to(torch.bfloat16) for _ in range(4)]
+            w_ = (torch.randn(N_, K_, device=dev) * K_ ** -0.5).to(torch.bfloat16)
+            b_ = torch.zeros(N_, device=dev)
+            ys_ = [torch.empty(M_, N_, device=dev, dtype=torch.bfloat16) for _ in range(4)]
+            for i in range(3):
+                ops.proj(xs_[i], w_, bias=b_, out=ys_[i])
+            torch.cuda.synchronize()
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_):
+                for i in range(20):
+                    ops.proj(xs_[i % 4], w_, bias=b_, out=ys_[i % 4])
+            g_.replay()
+            torch.cuda.synchronize()
+            ts_ = []
+            for _ in range(5):
+                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_.record(); g_.replay(); e_.record(); torch.cuda.synchronize()
+                ts_.append(s_.elapsed_time(e_) * 1e3 / 20)
+            us = statistics.median(ts_)
+            gl[nm] = {"M": M_, "N": N_, "K": K_, "us_per_launch": us, "tflops": 2.0 * M_ * N_ * K_ / us / 1e6, "frac": 2.0 * M_ * N_ * K_ / us / 1e6 / pk["bf16_tflops"]}
+            del xs_, ys_, g_
+        out["proj_gemm_in_graph"] = {"kernel": "gemm_tn_tcgen05_kernel<BN, LEAN> (bias, bf16 out through the store warp)", "peak_tflops": pk["bf16_tflops"], **gl}
         # -- capture path, config 1 (B = 2, fp32 q/k/v in, bf16 O + fp32 prob [+ score] out)
         B = 2
         qf, kf, vf = (torch.randn(B, n_, C, device=dev) for n_ in (N, S, S))
