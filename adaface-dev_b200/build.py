@@ -8,7 +8,7 @@ from concurrent.futures import ThreadPoolExecutor
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libadaface_b200.so")
 OBJ = os.path.join(CSRC, "_obj")
-SOURCES = ["capi.cu", "gemm_tcgen05.cu", "attn_tcgen05.cu", "attn_mma.cu", "attn_bwd_mma.cu", "attn_bwd_tcgen05.cu", "attn_cross_bwd.cu", "attn_cross_stream.cu",
+SOURCES = ["capi.cu", "gemm_tcgen05.cu", "attn_tcgen05.cu", "attn_tcgen05_tri.cu", "attn_mma.cu", "attn_bwd_mma.cu", "attn_bwd_tcgen05.cu", "attn_cross_bwd.cu", "attn_cross_stream.cu",
            "elementwise.cu", "elementwise_bwd.cu", "resblock_elementwise.cu", "sampler.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC", "-diag-suppress", "128"]

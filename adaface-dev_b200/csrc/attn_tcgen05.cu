@@ -30,6 +30,9 @@ namespace adaface {
 #endif
 
 extern long long g_launch_count;
+int attn_fwd_tcgen05_tri(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sh, int64_t k_sn,
+                         const void* v, int64_t v_sb, int64_t v_sh, int64_t v_sn, int64_t B, int64_t H, int64_t Lq, int64_t Lk,
+                         int64_t drow_q, int64_t drow_kv, const TaParams& p, cudaStream_t stream);
 
 constexpr int TA_BM = 128;
 constexpr int TA_BN = 64;
@@ -855,6 +858,7 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
       tc_fence_before();
       mbar_arrive(&p_full[g]);
       AF_ATTN_TR(if (str_) tp[4] = clock64();)
+      AF_ATTN_TR(if (p.trace && blockIdx.x == 0 && lane == 0 && j >= 8 && j < 16) p.trace[512 + qd * 32 + g * 8 + (j - 8)] = clock64();)
     }
     mbar_wait(o_full, 0);
     tc_fence_after();
@@ -996,7 +1000,8 @@ static int launch_ta_quad(const CUtensorMap& tQ, const CUtensorMap& tK, const CU
     for (int g = 0; g < 4; ++g)
       for (int j = 0; j < 8; ++j) {
         const long long* tp = h + 256 + g * 64 + j * 8;
-        fprintf(stderr, "softmax g=%d j=%2d: s_full wait %6lld..%6lld  max done %6lld  exp+pack done %6lld  arrived %6lld\n", g, j + 8, tp[0] - t0, tp[1] - t0, tp[2] - t0, tp[3] - t0, tp[4] - t0);
+        fprintf(stderr, "softmax g=%d j=%2d: s_full wait %6lld..%6lld  max done %6lld  exp+pack done %6lld  arrived %6lld  (warps 0..3: %6lld %6lld %6lld %6lld)\n", g, j + 8, tp[0] - t0, tp[1] - t0, tp[2] - t0, tp[3] - t0, tp[4] - t0,
+                h[512 + g * 8 + j] - t0, h[512 + 32 + g * 8 + j] - t0, h[512 + 64 + g * 8 + j] - t0, h[512 + 96 + g * 8 + j] - t0);
       }
   }
   return 0;
@@ -1391,6 +1396,15 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, co
     quad = (e && e[0] == '0') ? 0 : 1;
   }
   if (key_mask) return (quad && mc && !psmem) ? launch_ta_quad<40, 5, true>(tQ, tK, tV, p, ib, ih, stream) : -1;
+  {
+    static int tri = -1;
+    if (tri < 0) {
+      const char* e = getenv("ADAFACE_ATTN_TRI");     // 1: three-tile kernel with decoupled S / P regions and Q in TMEM (attn_tcgen05_tri.cu)
+      tri = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (tri && d == 40 && Lq >= 1024 && Lk > 128)
+      return attn_fwd_tcgen05_tri(q, q_sb, q_sh, q_sn, k, k_sb, k_sh, k_sn, v, v_sb, v_sh, v_sn, B, H, Lq, Lk, drow_q, drow_kv, p, stream);
+  }
   if (quad && mc && !psmem && d == 40 && Lq >= 2 * TQ_G * TA_BM && Lk > 128) {
     static int issuers = -1;
     if (issuers < 0) {
