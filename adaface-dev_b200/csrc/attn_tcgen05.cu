@@ -742,6 +742,16 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
         }
         umma_commit(&s_full[g]);
       };
+      // issuer-side wait: a non-blocking test first (traced: the suspending try_wait of mbar_wait needs ~130 clk even for a completed phase,
+      // six of them per 64-key step were 800 of the issuer's 2150 clk)
+      auto iss_wait = [&](uint64_t* bar, uint32_t parity) {
+#ifndef AF_ATTN_ISSUER_SLOW_WAIT
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred P;\n\tmbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+#endif
+        mbar_wait(bar, parity);
+      };
       mbar_wait(MASK ? q_ready : q_full, 0);
       mbar_wait(MASK ? &v_ready[0] : &kv_full[0], 0);
       tc_fence_after();
@@ -767,15 +777,15 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
         const int s = j % ST;
         const bool more = j + 1 < n_tiles;
         AF_ATTN_TR(const bool tr = p.trace && blockIdx.x == 0 && g_lo == 0 && j >= 8 && j < 16; if (tr) p.trace[(j - 8) * 16] = clock64();)
-        mbar_wait(&v_ready[s], (j / ST) & 1);                     // V_j carries its ones column
-        if (more) mbar_wait(MASK ? &v_ready[(j + 1) % ST] : &kv_full[(j + 1) % ST], ((j + 1) / ST) & 1);
+        iss_wait(&v_ready[s], (j / ST) & 1);                      // V_j carries its ones column
+        if (more) iss_wait(MASK ? &v_ready[(j + 1) % ST] : &kv_full[(j + 1) % ST], ((j + 1) / ST) & 1);
         tc_fence_after();
         AF_ATTN_TR(if (tr) p.trace[(j - 8) * 16 + 1] = clock64();)
 #pragma unroll
         for (int gi = 0; gi < GPI; ++gi) {
           const int g = g_lo + gi;
           AF_ATTN_TR(if (tr) p.trace[(j - 8) * 16 + 2 + gi * 3] = clock64();)
-          mbar_wait(&p_full[g], j & 1);                           // tile g's P_j is in TMEM
+          iss_wait(&p_full[g], j & 1);                            // tile g's P_j is in TMEM
           AF_ATTN_TR(if (tr) p.trace[(j - 8) * 16 + 3 + gi * 3] = clock64();)
           tc_fence_after();
 #pragma unroll
@@ -799,6 +809,7 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
     for (int j = 0; j < n_tiles; ++j) {
       AF_ATTN_TR(const bool str_ = p.trace && blockIdx.x == 0 && lane == 0 && qd == 0 && j >= 8 && j < 16; long long* tp = p.trace + 256 + g * 64 + (j - 8) * 8;
                  if (str_) tp[0] = clock64();)
+#ifndef AF_ATTN_OPTIMISTIC
       mbar_wait(&s_full[g], j & 1);          // also implies P V_{j-1} of this tile has retired
       AF_ATTN_TR(if (str_) tp[1] = clock64();)
       tc_fence_after();
@@ -853,6 +864,85 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
         }
         tmem_st_32x32b_x16(t_lane + (uint32_t)(hf * 16), pk);
       }
+#else
+      // (-DAF_ATTN_OPTIMISTIC; measured SLOWER, 327 vs 296 us: the scores' wait shrinks, so 2.6 instead of 2 warps per scheduler sit in their exp2
+      // phase at once and each takes 1550 instead of 1000 clk -- profiles/r02_attn_trace_quad_optimistic.txt.  Kept as a record.)
+      // OPTIMISTIC softmax step.  The reference maximum m_ref sits 7 octaves ABOVE the largest score seen so far, so every probability is
+      // <= 2^-7 until a score outgrows the old maximum by 2^8 -- exactly then some bf16 P has its top exponent bit set (P >= 2).  The
+      // exponentials therefore start against the running reference as soon as the scores are in registers; instead of a row-maximum
+      // pass in front of them (30 FMNMX3 on the critical path) the packed P words are OR-ed together (LOP3, beside the MUFU work) and one
+      // bit test decides whether the tile has to be redone against a new reference (first tile, then rare).
+      {
+        uint32_t ok;      // non-blocking test first: a completed phase answers in tens of clocks, the suspending try_wait was traced at ~130
+        asm volatile("{\n\t.reg .pred P;\n\tmbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(ok) : "r"(smem_u32(&s_full[g])), "r"((uint32_t)(j & 1)) : "memory");
+        if (!ok) mbar_wait(&s_full[g], j & 1);          // also implies P V_{j-1} of this tile has retired
+      }
+      AF_ATTN_TR(if (str_) tp[1] = clock64();)
+      tc_fence_after();
+      const int valid = p.Lk - (j + (SPLIT ? (g & 1) * n_tiles : 0)) * TA_BN;
+      uint32_t v[TA_BN];
+      tmem_ld_32x32b_x64_wait(t_lane, v);
+      if (valid < TA_BN) {
+#pragma unroll
+        for (int i = 0; i < TA_BN; ++i)
+          if (i >= valid) v[i] = 0xff800000u;
+      }
+      AF_ATTN_TR(if (str_) tp[2] = clock64();)
+      constexpr int EMU_N = EMU <= 4 ? EMU : EMU - 3, EMU_DEG = EMU <= 4 ? 3 : 2;
+      auto exp_tile = [&](float mr) -> uint32_t {      // P = 2^(s * scale - mr) -> bf16 -> TMEM (over the scores); returns the OR of the packed words
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-mr, -mr);
+        uint32_t any = 0;
+        float mxe = -INFINITY;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float2 t = __ffma2_rn(make_float2(__uint_as_float(v[hf * 32 + 2 * i]), __uint_as_float(v[hf * 32 + 2 * i + 1])), sc2, nm2);
+            float2 e;
+            if ((i & 7) < EMU_N) {
+              mxe = fmaxf(mxe, fmaxf(t.x, t.y));      // the polynomial path wraps its exponent on overflow: its arguments are checked directly
+              e = exp2_emu2<EMU_DEG>(t);
+            } else {
+              e = make_float2(fast_exp2(t.x), fast_exp2(t.y));
+            }
+            pk[i] = __byte_perm(__float_as_uint(e.x), __float_as_uint(e.y), 0x7632);   // truncate to bf16; the row sum comes from the MMA
+          }
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) any |= pk[i] | pk[i + 1];
+          tmem_st_32x32b_x16(t_lane + (uint32_t)(hf * 16), pk);
+        }
+        return any | (mxe >= 1.f ? 0x4000u : 0u);
+      };
+      bool redo = j == 0;
+      if (j > 0) redo = (exp_tile(m_ref) & 0x40004000u) != 0;      // some P >= 2 (or inf / NaN)
+      if (__any_sync(0xffffffffu, redo)) {
+        float m4[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
+#pragma unroll
+        for (int i = 4; i < TA_BN; i += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) m4[u] = fmaxf(m4[u], __uint_as_float(v[i + u]));
+        }
+        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
+        if (j == 0) {
+          m_ref = (mx == -INFINITY) ? 0.f : mx + 7.f;
+        } else {
+          const float m_new = redo ? mx + 7.f : m_ref;      // rows that stayed below the threshold keep their reference (factor 1)
+          const float f = fast_exp2(m_ref - m_new);
+          m_ref = m_new;
+#pragma unroll
+          for (int c = 0; c < DO / 16; ++c) {
+            uint32_t ov[16];
+            tmem_ld_32x32b_x16(t_lane + (uint32_t)(TMEM_O + c * 16), ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
+            tmem_st_32x32b_x16(t_lane + (uint32_t)(TMEM_O + c * 16), ov);
+          }
+        }
+        exp_tile(m_ref);
+      }
+#endif
       AF_ATTN_TR(if (str_) tp[3] = clock64();)
       tmem_st_wait();
       tc_fence_before();

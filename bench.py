@@ -232,6 +232,40 @@ class ClockSampler:
         return out
 
 
+def bind_host_memory_to_gpu_node(torch, local):
+    """Multi-rank runs: every rank's pinned host buffers should live on the NUMA node its GPU hangs off (round 1: eight ranks on node 0
+    lost a third of the end-to-end rate to cross-socket copies).  Best effort: set this thread's memory policy to PREFERRED(node of the
+    GPU) before the pinned allocations, and move the thread to that node's CPUs when the cpuset allows it.  Returns what was done."""
+    import ctypes
+    info = {"gpu_node": None, "mempolicy": "unchanged", "cpus": "unchanged"}
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        info["gpu_node"] = node
+        if node < 0:
+            return info
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        rc = libc.syscall(238, 1, ctypes.byref(mask), 65)       # set_mempolicy(MPOL_PREFERRED, {node})  (x86-64 syscall number)
+        info["mempolicy"] = f"preferred node {node}" if rc == 0 else f"refused (errno {ctypes.get_errno()})"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"] = f"{len(allowed)} CPUs of node {node}"
+        else:
+            info["cpus"] = f"node {node} is outside this process's cpuset"
+    except Exception as ex:      # placement is an optimisation, never a failure
+        info["error"] = f"{type(ex).__name__}: {ex}"
+    return info
+
+
 def build_stack(torch, a, device):
     g = torch.Generator().manual_seed(0)
     mods, xs = [], []
@@ -722,6 +756,8 @@ def main_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     a._lib.load()
+    # only multi-rank runs are placed (at N = 1 the CPU baseline of this same process keeps every core)
+    host_numa = bind_host_memory_to_gpu_node(torch, local) if world > 1 and os.environ.get("ADAFACE_BENCH_NUMA", "1") != "0" else None
     sampler = ClockSampler(local)      # nvidia-smi needs ~1 s to start: launch it before the set-up work
 
     mods, xs_cpu, ctx_cpu = build_stack(torch, a, dev)
@@ -926,6 +962,7 @@ def main_gpu(args):
             "gpu_launches": int(launches), "gpu_launches_per_step": int(launches_per_step),
             "check": check,
             "clocks": clocks,
+            "host_numa": host_numa,
             "roofline": {"kernel": "attn_fwd_tcgen05_quad_kernel<40> (level-A self-attention core, B=8, 4096 tok, 8x40; bulk + tail launch)",
                          "bound": "tensor", "achieved": k_flops / (k_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops"],
                          "unit": "TFLOP/s", "frac": k_flops / (k_ms * 1e-3) / 1e12 / pk["bf16_tflops"],
