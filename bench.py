@@ -883,6 +883,40 @@ def main_gpu(args):
         barrier()
         t_e2e_ms = sum(s.elapsed_time(e) for s, e in ee) / e2e_steps
 
+        # ---- what the box's host links give all ranks AT ONCE (plain pinned-memory copies, both directions concurrently): the ceiling of
+        #      the end-to-end number at this N.  128 MB each way per rank, three rounds, barrier in front.
+        link = None
+        try:
+            hb = torch.empty(128 << 20, dtype=torch.uint8).pin_memory()
+            hb2 = torch.empty(128 << 20, dtype=torch.uint8).pin_memory()
+            db, db2 = torch.empty(128 << 20, dtype=torch.uint8, device=dev), torch.empty(128 << 20, dtype=torch.uint8, device=dev)
+            lt = []
+            for _ in range(4):
+                barrier()
+                s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                with torch.cuda.stream(s_in):
+                    s_in.wait_event(s0)
+                    db.copy_(hb, non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(s0)
+                    hb2.copy_(db2, non_blocking=True)
+                comp.wait_stream(s_in)
+                comp.wait_stream(s_out)
+                e0.record()
+                torch.cuda.synchronize()
+                lt.append(s0.elapsed_time(e0))
+            lms = torch.tensor([min(lt[1:])], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(lms, op=dist.ReduceOp.MAX)
+            link = {"what": "128 MB H2D + 128 MB D2H per rank, all ranks at once, pinned memory", "ms": lms.item(),
+                    "aggregate_gbs_both_directions": world * 2 * (128 << 20) / (lms.item() * 1e-3) / 1e9,
+                    "step_needs_gb": world * (h2d + d2h) / 1e9}
+            link["copy_floor_ms_per_step"] = link["step_needs_gb"] / link["aggregate_gbs_both_directions"] * 1e3
+            del hb, hb2, db, db2
+        except Exception as ex:
+            link = {"error": f"{type(ex).__name__}: {ex}"}
+
         # ---- roofline of the dominant kernel: level-A self-attention core, in the layout the processor feeds it
         #      (q/k/v = column slices of the fused [B, N, 3C] projection buffer), timed alone with L2 flushed
         _, N, C, _ = LEVELS[0]
@@ -958,6 +992,7 @@ def main_gpu(args):
             "frac_of_bf16_peak": value / world / pk["bf16_tflops_sustained"],
             "e2e": {"value": world * fl_step / (t_e2e_ms * 1e-3) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e_ms,
+                    "host_link": link,
                     "how": f"{len(units)} CUDA-graph units (levels D, C, B, A; the last level-A block per batch slice so that its D2H overlaps); H2D / kernels / D2H on three streams"},
             "gpu_launches": int(launches), "gpu_launches_per_step": int(launches_per_step),
             "check": check,
