@@ -1147,6 +1147,7 @@ struct TcParams {
   int Lq, Lk, H, NK, n_qtiles, n_units, tmem_cols;
   float scale_log2;
   float* lse;
+  long long* trace;        // diagnosis only (-DAF_ATTN_TRACE build, env ADAFACE_ATTN_TRACE): CTA 0 stamps its hand-offs
 };
 
 // NKT = compile-time number of staged keys (80: the 77-token prompt; 128: anything up to 128, e.g. 97 in training):
@@ -1260,8 +1261,11 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           prev_bh = bh;
         }
         const int s = i & 1;
+        AF_ATTN_TR(const bool tr = p.trace && blockIdx.x == 0 && i < 4; if (tr) p.trace[i * 8] = clock64();)
         mbar_wait(&q_full[s], (i >> 1) & 1);
+        AF_ATTN_TR(if (tr) p.trace[i * 8 + 1] = clock64();)
         if (i >= 1) mbar_wait(o_free, (i - 1) & 1);          // the softmax warps have drained S / P / O of the previous unit
+        AF_ATTN_TR(if (tr) p.trace[i * 8 + 2] = clock64();)
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < KT; ++kk) {
@@ -1271,7 +1275,9 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         umma_commit(s_full);
         umma_commit(&q_empty[s]);                            // the Q tile is free once S has been produced
+        AF_ATTN_TR(if (tr) p.trace[i * 8 + 3] = clock64();)
         mbar_wait(p_full, i & 1);
+        AF_ATTN_TR(if (tr) p.trace[i * 8 + 4] = clock64();)
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < NK / 16; ++k) {
@@ -1279,6 +1285,7 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           umma_bf16_ts(tmem_base + (uint32_t)TMEM_O, tmem_base + (uint32_t)(k * 8), db, idesc_pv, k != 0 ? 1u : 0u);
         }
         umma_commit(o_full);
+        AF_ATTN_TR(if (tr) p.trace[i * 8 + 5] = clock64();)
         const int next_bh = (u + 1 < u1) ? (u + 1) / p.n_qtiles : -1;
         if (next_bh != bh) umma_commit(kv_empty);
       }
@@ -1290,7 +1297,9 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     for (int u = u0, i = 0; u < u1; ++u, ++i) {
       const int bh = u / p.n_qtiles, qt = u - bh * p.n_qtiles;
       const int b = bh / p.H, h = bh - b * p.H;
+      AF_ATTN_TR(const bool str_ = p.trace && blockIdx.x == 0 && warp == 0 && lane == 0 && i < 4; long long* tp = p.trace + 64 + i * 8; if (str_) tp[0] = clock64();)
       mbar_wait(s_full, i & 1);
+      AF_ATTN_TR(if (str_) tp[1] = clock64();)
       tc_fence_after();
       // ---- pass 1: row max of the raw scores (keys >= Lk are zero rows of K: masked out)
       float mxr = -INFINITY;
@@ -1313,6 +1322,7 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mxr = fmaxf(mxr, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
       }
       const float m_ref = mxr * p.scale_log2;
+      AF_ATTN_TR(if (str_) tp[2] = clock64() + (m_ref > 1e30f ? 1 : 0);)
       // ---- pass 2: P = exp2(s * scale - max) truncated to bf16, written over the scores it came from
       const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
 #pragma unroll
@@ -1337,8 +1347,10 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_full);
+      AF_ATTN_TR(if (str_) tp[3] = clock64();)
       // ---- epilogue: O / l -> bf16 -> [B, Lq, H*d]
       mbar_wait(o_full, i & 1);
+      AF_ATTN_TR(if (str_) tp[4] = clock64();)
       tc_fence_after();
       float l_run;                                             // row sum of P = column D of the accumulator
       {
@@ -1373,6 +1385,7 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       tc_fence_before();
       mbar_arrive(o_free);
+      AF_ATTN_TR(if (str_) tp[5] = clock64();)
     }
   }
   AF_PDL_TRIGGER_LATE();
@@ -1404,6 +1417,13 @@ static int launch_tc_cross(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_
   p.tmem_cols = (NK + DO_S <= 128) ? 128 : 256;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse;
+  p.trace = nullptr;
+  if (getenv("ADAFACE_ATTN_TRACE")) {
+    static long long* tbuf = nullptr;
+    if (!tbuf) cudaMalloc(&tbuf, 1024 * 8);
+    cudaMemset(tbuf, 0, 1024 * 8);
+    p.trace = tbuf;
+  }
   const int smem = 2 * Cfg::Q_BYTES + 2 * Cfg::NA * NK * 128 + 1024 + 128;
   static int configured[AF_MAX_DEV] = {0};                 // per device
   const int cfg_dev = af_device();
@@ -1421,6 +1441,19 @@ static int launch_tc_cross(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_
   AF_CUDA(launch_pdl(2, attn_cross_tc_kernel<D, NKT>, dim3(grid), dim3(TA_THREADS), smem, stream, tQ, tK, tV, p));
   AF_CUDA(cudaGetLastError());
   ++g_launch_count;
+  if (p.trace) {      // diagnosis: CTA 0, its first four tiles
+    static long long h[1024];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long t0 = h[0];
+    fprintf(stderr, "cross: grid %d, units %d\n", grid, p.n_units);
+    for (int i = 0; i < 4; ++i)
+      fprintf(stderr, "issuer tile %d: q_full wait %6lld..%6lld  o_free seen %6lld  QK issued %6lld  p_full seen %6lld  PV issued %6lld\n", i, h[i * 8] - t0, h[i * 8 + 1] - t0,
+              h[i * 8 + 2] - t0, h[i * 8 + 3] - t0, h[i * 8 + 4] - t0, h[i * 8 + 5] - t0);
+    for (int i = 0; i < 4; ++i)
+      fprintf(stderr, "softmax tile %d: s_full wait %6lld..%6lld  max done %6lld  P arrived %6lld  o_full seen %6lld  stored %6lld\n", i, h[64 + i * 8] - t0, h[64 + i * 8 + 1] - t0,
+              h[64 + i * 8 + 2] - t0, h[64 + i * 8 + 3] - t0, h[64 + i * 8 + 4] - t0, h[64 + i * 8 + 5] - t0);
+  }
   return 0;
 }
 

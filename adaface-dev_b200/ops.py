@@ -146,6 +146,7 @@ _HEADS_WS = {}
 # path of the interleaved layout no longer matters and the padded head-major detour (60 % more QKV store bytes) is
 # off by default: measured 470 vs 459 TFLOP/s on the whole stack.
 _SELF_HEADMAJOR = __import__("os").environ.get("ADAFACE_SELF_HEADMAJOR", "0") == "1"
+_CROSS_HEADMAJOR = __import__("os").environ.get("ADAFACE_CROSS_HEADMAJOR", "0") == "1"    # measured in-graph, level A: 49.8 us per block head-major vs 40.0 us plain
 
 
 def heads_workspace(n_which, B, H, L, dpad, device):
@@ -574,7 +575,7 @@ def cross_attention_fused(x2d, wq, bq, ctx2d, wkv, bkv, B, N, S, heads, scale):
     C = wq.shape[0]
     d = C // heads
     kv = proj(ctx2d, wkv, bias=bkv).view(B, S, 2 * C)
-    if d == 40:
+    if d == 40 and _CROSS_HEADMAJOR:
         q = proj_heads(x2d, wq, heads, d, N, bias=bq)[0]                     # [B, H, N, 64]
         k = kv[:, :, :C].unflatten(2, (heads, d)).transpose(1, 2)             # views [B, H, S, d] of the interleaved buffer
         v = kv[:, :, C:].unflatten(2, (heads, d)).transpose(1, 2)
