@@ -1145,6 +1145,7 @@ struct TcParams {
   bf16* o;
   long long o_sb, o_sn;
   int Lq, Lk, H, NK, n_qtiles, n_units, tmem_cols;
+  int q_wide;              // Q map spans whole [B, Lq, H*d] rows: the box of head h starts at column h * d (see launch_tc_cross)
   float scale_log2;
   float* lse;
   long long* trace;        // diagnosis only (-DAF_ATTN_TRACE build, env ADAFACE_ATTN_TRACE): CTA 0 stamps its hand-offs
@@ -1232,7 +1233,8 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (i >= 2) mbar_wait(&q_empty[s], ((i >> 1) - 1) & 1);
         mbar_arrive_expect_tx(&q_full[s], Cfg::Q_BYTES);
 #pragma unroll
-        for (int a = 0; a < NA; ++a) tma_load_4d(sQ + s * Cfg::Q_BYTES + a * (TA_BM * 128), &tmQ, &q_full[s], a * 64, h, qt * TA_BM, b);
+        for (int a = 0; a < NA; ++a)
+          tma_load_4d(sQ + s * Cfg::Q_BYTES + a * (TA_BM * 128), &tmQ, &q_full[s], p.q_wide ? h * D + a * 64 : a * 64, p.q_wide ? 0 : h, qt * TA_BM, b);
       }
       if (new_kv) {
         mbar_wait(kv_full, kv_loads & 1);
@@ -1252,6 +1254,11 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       constexpr uint32_t idesc_qk = make_idesc_bf16_f32(TA_BM, NK, false);
       constexpr uint32_t idesc_pv = make_idesc_bf16_f32(TA_BM, DO, true);
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
+      auto tc_wait = [&](uint64_t* bar, uint32_t parity) {      // non-blocking test first: the suspending try_wait costs ~130 clk even on a completed phase
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred P;\n\tmbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!ok) mbar_wait(bar, parity);
+      };
       int prev_bh = -1, kv_loads = 0;
       for (int u = u0, i = 0; u < u1; ++u, ++i) {
         const int bh = u / p.n_qtiles;
@@ -1262,9 +1269,9 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         const int s = i & 1;
         AF_ATTN_TR(const bool tr = p.trace && blockIdx.x == 0 && i < 4; if (tr) p.trace[i * 8] = clock64();)
-        mbar_wait(&q_full[s], (i >> 1) & 1);
+        tc_wait(&q_full[s], (i >> 1) & 1);
         AF_ATTN_TR(if (tr) p.trace[i * 8 + 1] = clock64();)
-        if (i >= 1) mbar_wait(o_free, (i - 1) & 1);          // the softmax warps have drained S / P / O of the previous unit
+        if (i >= 1) tc_wait(o_free, (i - 1) & 1);            // the softmax warps have drained S / P / O of the previous unit
         AF_ATTN_TR(if (tr) p.trace[i * 8 + 2] = clock64();)
         tc_fence_after();
 #pragma unroll
@@ -1276,7 +1283,7 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         umma_commit(s_full);
         umma_commit(&q_empty[s]);                            // the Q tile is free once S has been produced
         AF_ATTN_TR(if (tr) p.trace[i * 8 + 3] = clock64();)
-        mbar_wait(p_full, i & 1);
+        tc_wait(p_full, i & 1);
         AF_ATTN_TR(if (tr) p.trace[i * 8 + 4] = clock64();)
         tc_fence_after();
 #pragma unroll
@@ -1301,48 +1308,69 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_wait(s_full, i & 1);
       AF_ATTN_TR(if (str_) tp[1] = clock64();)
       tc_fence_after();
-      // ---- pass 1: row max of the raw scores (keys >= Lk are zero rows of K: masked out)
+      // ---- pass 1: row max of the raw scores (keys >= Lk are zero rows of K: masked out).  The scores are read in the widest chunks
+      //      the register budget allows (32 columns; 80 registers per thread at four CTAs per SM): every tcgen05.ld round trip costs ~170 clk
+      //      there (traced: ten 16-column round trips were 2000 of a tile's 4600 clk).
       float mxr = -INFINITY;
+      auto chunk_max = [&](auto& v, int c0) {
+        constexpr int W = sizeof(v) / sizeof(v[0]);
+        if (c0 + W > p.Lk) {
 #pragma unroll
-      for (int c = 0; c < NK; c += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(t_lane + (uint32_t)c, v);
-        tmem_ld_wait();
-        if (c + 16 > p.Lk) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c + j >= p.Lk) v[j] = 0xff800000u;
+          for (int j = 0; j < W; ++j)
+            if (c0 + j >= p.Lk) v[j] = 0xff800000u;
         }
         float m4[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
 #pragma unroll
-        for (int j = 4; j < 16; j += 4) {
+        for (int j = 4; j < W; j += 4) {
 #pragma unroll
           for (int x = 0; x < 4; ++x) m4[x] = fmaxf(m4[x], __uint_as_float(v[j + x]));
         }
         mxr = fmaxf(mxr, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+      };
+#pragma unroll
+      for (int c = 0; c + 32 <= NK; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32_wait(t_lane + (uint32_t)c, v);
+        chunk_max(v, c);
+      }
+      if constexpr (NK % 32 != 0) {
+        static_assert(NK % 32 == 16, "staged keys: 80 or 128");
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_lane + (uint32_t)(NK - 16), v);
+        tmem_ld_wait();
+        chunk_max(v, NK - 16);
       }
       const float m_ref = mxr * p.scale_log2;
       AF_ATTN_TR(if (str_) tp[2] = clock64() + (m_ref > 1e30f ? 1 : 0);)
-      // ---- pass 2: P = exp2(s * scale - max) truncated to bf16, written over the scores it came from
+      // ---- pass 2: P = exp2(s * scale - max) truncated to bf16, written over the scores it came from (32-column chunks; the tail 16)
       const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
+      auto chunk_exp = [&](auto& v, auto& pk, int c0) {
+        constexpr int W = sizeof(v) / sizeof(v[0]);
+        if (c0 + W > p.Lk) {
 #pragma unroll
-      for (int c = 0; c < NK; c += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(t_lane + (uint32_t)c, v);
-        tmem_ld_wait();
-        if (c + 16 > p.Lk) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c + j >= p.Lk) v[j] = 0xff800000u;
+          for (int j = 0; j < W; ++j)
+            if (c0 + j >= p.Lk) v[j] = 0xff800000u;
         }
-        uint32_t pk[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < W / 2; ++j) {
           const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), sc2, nm2);
           const float2 e = make_float2(fast_exp2(t.x), fast_exp2(t.y));
           pk[j] = __byte_perm(__float_as_uint(e.x), __float_as_uint(e.y), 0x7632);   // truncate; the row sum comes from the MMA
         }
-        tmem_st_32x32b_x8(t_lane + (uint32_t)(c >> 1), pk);     // columns [c/2, c/2 + 8): already consumed
+      };
+#pragma unroll
+      for (int c = 0; c + 32 <= NK; c += 32) {
+        uint32_t v[32], pk[16];
+        tmem_ld_32x32b_x32_wait(t_lane + (uint32_t)c, v);
+        chunk_exp(v, pk, c);
+        tmem_st_32x32b_x16(t_lane + (uint32_t)(c >> 1), pk);      // columns [c/2, c/2 + 16): already consumed
+      }
+      if constexpr (NK % 32 != 0) {
+        uint32_t v[16], pk[8];
+        tmem_ld_32x32b_x16(t_lane + (uint32_t)(NK - 16), v);
+        tmem_ld_wait();
+        chunk_exp(v, pk, NK - 16);
+        tmem_st_32x32b_x8(t_lane + (uint32_t)((NK - 16) >> 1), pk);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -1352,35 +1380,35 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_wait(o_full, i & 1);
       AF_ATTN_TR(if (str_) tp[4] = clock64();)
       tc_fence_after();
-      float l_run;                                             // row sum of P = column D of the accumulator
-      {
-        uint32_t v8[8];
-        tmem_ld_32x32b_x8(t_lane + (uint32_t)(TMEM_O + (D & ~7)), v8);
-        tmem_ld_wait();
-        l_run = __uint_as_float(v8[D & 7]);
+      // the whole accumulator row in ONE round trip (32-column loads, one wait): row sum of P = column D
+      uint32_t acc[DO];
+#pragma unroll
+      for (int c = 0; c + 32 <= DO; c += 32) {
+        uint32_t (&blk)[32] = *reinterpret_cast<uint32_t (*)[32]>(&acc[c]);
+        tmem_ld_32x32b_x32_nowait(t_lane + (uint32_t)(TMEM_O + c), blk);
       }
+      if constexpr (DO % 32 != 0) {
+        uint32_t (&blk)[16] = *reinterpret_cast<uint32_t (*)[16]>(&acc[DO - 16]);
+        tmem_ld_32x32b_x16(t_lane + (uint32_t)(TMEM_O + DO - 16), blk);
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < DO; ++c) asm volatile("" : "+r"(acc[c]));      // nothing is consumed before the wait
+      const float l_run = __uint_as_float(acc[D]);
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
       const int grow = qt * TA_BM + row;
       if (p.lse && grow < p.Lq)
         p.lse[((long long)b * p.H + h) * p.Lq + grow] = l_run > 0.f ? m_ref + log2f(l_run) : INFINITY;
       bf16* orow = p.o + (long long)b * p.o_sb + (long long)grow * p.o_sn + h * D;
+      if (grow < p.Lq) {
 #pragma unroll
-      for (int c = 0; c < (D + 15) / 16; ++c) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(t_lane + (uint32_t)(TMEM_O + c * 16), v);
-        tmem_ld_wait();
-        if (grow < p.Lq) {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            if (c * 16 + half * 8 < D) {
-              uint4 pk;
-              pk.x = pack_bf16(__uint_as_float(v[half * 8 + 0]) * inv, __uint_as_float(v[half * 8 + 1]) * inv);
-              pk.y = pack_bf16(__uint_as_float(v[half * 8 + 2]) * inv, __uint_as_float(v[half * 8 + 3]) * inv);
-              pk.z = pack_bf16(__uint_as_float(v[half * 8 + 4]) * inv, __uint_as_float(v[half * 8 + 5]) * inv);
-              pk.w = pack_bf16(__uint_as_float(v[half * 8 + 6]) * inv, __uint_as_float(v[half * 8 + 7]) * inv);
-              *reinterpret_cast<uint4*>(orow + c * 16 + half * 8) = pk;
-            }
-          }
+        for (int c8 = 0; c8 < D / 8; ++c8) {
+          uint4 pk;
+          pk.x = pack_bf16(__uint_as_float(acc[c8 * 8 + 0]) * inv, __uint_as_float(acc[c8 * 8 + 1]) * inv);
+          pk.y = pack_bf16(__uint_as_float(acc[c8 * 8 + 2]) * inv, __uint_as_float(acc[c8 * 8 + 3]) * inv);
+          pk.z = pack_bf16(__uint_as_float(acc[c8 * 8 + 4]) * inv, __uint_as_float(acc[c8 * 8 + 5]) * inv);
+          pk.w = pack_bf16(__uint_as_float(acc[c8 * 8 + 6]) * inv, __uint_as_float(acc[c8 * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c8 * 8) = pk;
         }
       }
       tc_fence_before();
@@ -1405,10 +1433,26 @@ static int launch_tc_cross(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_
   using Cfg = TaCfg<D>;
   constexpr int NK = NKT;
   CUtensorMap tQ, tK, tV;
-  if (make_tmap_bf16_heads(&tQ, q, (uint64_t)drow_q, (uint64_t)H, (uint64_t)Lq, (uint64_t)B, (uint64_t)q_sh, (uint64_t)q_sn, (uint64_t)q_sb, TA_BM)) return 3;
+  // Q in the reference layout [B, Lq, H*d] (heads side by side in a row): a box over ONE head's d columns makes the TMA unit fetch 80-byte
+  // row pieces and fill the rest of the 128-byte swizzle row itself -- 16 useful B/clk/SM (profiles/r01_microbench.md), and the traced
+  // kernel waited ~950 clk per tile for its Q.  Instead the map spans whole rows and the box of head h starts at column h*d and is 64
+  // columns wide: full 128-byte rows at 73 B/clk/SM.  Columns d..63 of the tile then hold the NEXT head's values (zeros past the row end);
+  // they meet K's columns d..63, which ARE zero (K keeps its per-head map with out-of-bounds fill), so the scores are unchanged.
+  static int wide_on = -1;
+  if (wide_on < 0) {
+    const char* e = getenv("ADAFACE_CROSS_QWIDE");      // A/B switch (default on)
+    wide_on = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool q_wide = wide_on && q_sh == (int64_t)D && drow_q == (int64_t)D && q_sn >= H * (int64_t)D;
+  if (q_wide) {
+    if (make_tmap_bf16_heads(&tQ, q, (uint64_t)(H * D), 1, (uint64_t)Lq, (uint64_t)B, (uint64_t)(H * D), (uint64_t)q_sn, (uint64_t)q_sb, TA_BM)) return 3;
+  } else {
+    if (make_tmap_bf16_heads(&tQ, q, (uint64_t)drow_q, (uint64_t)H, (uint64_t)Lq, (uint64_t)B, (uint64_t)q_sh, (uint64_t)q_sn, (uint64_t)q_sb, TA_BM)) return 3;
+  }
   if (make_tmap_bf16_heads(&tK, k, (uint64_t)drow_kv, (uint64_t)H, (uint64_t)Lk, (uint64_t)B, (uint64_t)k_sh, (uint64_t)k_sn, (uint64_t)k_sb, (uint32_t)NK)) return 3;
   if (make_tmap_bf16_heads(&tV, v, (uint64_t)drow_kv, (uint64_t)H, (uint64_t)Lk, (uint64_t)B, (uint64_t)v_sh, (uint64_t)v_sn, (uint64_t)v_sb, (uint32_t)NK)) return 3;
   TcParams p;
+  p.q_wide = q_wide ? 1 : 0;
   p.o = (bf16*)o; p.o_sb = o_sb; p.o_sn = o_sn;
   p.Lq = (int)Lq; p.Lk = (int)Lk; p.H = (int)H; p.NK = NK;
   p.n_qtiles = (int)((Lq + TA_BM - 1) / TA_BM);
