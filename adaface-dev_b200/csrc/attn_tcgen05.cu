@@ -1153,6 +1153,10 @@ struct TcParams {
 
 // NKT = compile-time number of staged keys (80: the 77-token prompt; 128: anything up to 128, e.g. 97 in training):
 // the score loops unroll completely and only the chunk that straddles Lk pays for masking.
+#ifndef AF_TC_EMU
+#define AF_TC_EMU 0      // measured at level A: 36.5 us (0) / 36.1 (2) / 35.9 (3) per cross block -- not MUFU-bound, left off
+#endif
+constexpr int TC_EMU = AF_TC_EMU;
 template <int D, int NKT>
 __global__ void __launch_bounds__(TA_THREADS, (D <= 64) ? 4 : 2)
 attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -1354,7 +1358,8 @@ attn_cross_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
         for (int j = 0; j < W / 2; ++j) {
           const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), sc2, nm2);
-          const float2 e = make_float2(fast_exp2(t.x), fast_exp2(t.y));
+          // (TC_EMU of every 8 pairs on the FMA-pipe polynomial: A/B knob, see AF_TC_EMU)
+          const float2 e = ((j & 7) < TC_EMU) ? exp2_emu2<2>(t) : make_float2(fast_exp2(t.x), fast_exp2(t.y));
           pk[j] = __byte_perm(__float_as_uint(e.x), __float_as_uint(e.y), 0x7632);   // truncate; the row sum comes from the MMA
         }
       };
