@@ -363,7 +363,7 @@ static int launch_delta(const BwdParams& p, cudaStream_t stream) {
 
 int attn_bwd_tcgen05(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*,
                      int64_t, int64_t, const float*, const float*, void*, int64_t, int64_t, void*, int64_t, int64_t, void*, int64_t,
-                     int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, float, cudaStream_t);
+                     int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, float, const uint8_t*, cudaStream_t);
 
 int attn_bwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn, const void* v, int64_t v_sb,
              int64_t v_sn, const void* o, int64_t o_sb, int64_t o_sn, const void* dout, int64_t do_sb, int64_t do_sn,
@@ -398,10 +398,10 @@ int attn_bwd(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k
       return 1;
   }
   if (rc) return rc;
-  if (!key_mask && causal_mult == 0) {
-    // unmasked attention: tcgen05 / TMEM kernels (attn_bwd_tcgen05.cu)
+  if (causal_mult == 0) {
+    // non-causal attention (key mask or none): tcgen05 / TMEM kernels (attn_bwd_tcgen05.cu)
     rc = attn_bwd_tcgen05(q, q_sb, q_sn, k, k_sb, k_sn, v, v_sb, v_sn, dout, do_sb, do_sn, lse, delta, dq, dq_sb, dq_sn, dk, dk_sb,
-                          dk_sn, dv, dv_sb, dv_sn, B, H, Lq, Lk, d, scale, stream);
+                          dk_sn, dv, dv_sb, dv_sn, B, H, Lq, Lk, d, scale, key_mask, stream);
     if (rc >= 0) return rc;
   }
   switch (d) {

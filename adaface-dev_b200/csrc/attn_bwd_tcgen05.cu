@@ -1,4 +1,4 @@
-// K5 (tensor-core variant): flash-attention backward on tcgen05 / TMEM for unmasked self- / cross-attention with head
+// K5 (tensor-core variant): flash-attention backward on tcgen05 / TMEM for self- / cross-attention (optional key mask) with head
 // dims 40 / 80 -- the same recompute-form two-pass scheme as attn_bwd_mma.cu (no atomics, deterministic), with every
 // GEMM on the 5th-generation tensor cores:
 //
@@ -50,6 +50,7 @@ struct TbParams {
   long long dq_sb, dq_sn, dk_sb, dk_sn, dv_sb, dv_sn;
   int Lq, Lk, H;
   float scale, scale_log2;
+  const uint8_t* key_mask;   // optional [B, Lk] (0 = key masked out, dalc:254-273 img_mask); needs Lk % 64 == 0
 };
 
 // ------------------------------------------------------------------------------------------------ dq pass
@@ -191,6 +192,17 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             if (hf * 32 + 2 * i + 1 >= valid) gy = 0;
           }
           pk[i] = __byte_perm(gx, gy, 0x7632);
+        }
+        if (p.key_mask) {      // masked keys: P = 0, hence dS = 0 (32 mask bytes of this half, the same for every row: broadcast loads)
+          const uint4* mp = reinterpret_cast<const uint4*>(p.key_mask + (long long)b * p.Lk + j * BN + hf * 32);
+          const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+          for (int w = 0; w < 8; ++w) {
+            const uint32_t nz = __vcmpne4(mw[w], 0u);               // 0xff per kept key (4 keys per word)
+            pk[2 * w] &= __byte_perm(nz, 0u, 0x1100);               // keys 4w, 4w + 1 -> the two bf16 halves of a packed pair
+            pk[2 * w + 1] &= __byte_perm(nz, 0u, 0x3322);           // keys 4w + 2, 4w + 3
+          }
         }
         tmem_st_32x32b_x16(t_lane + (uint32_t)(hf * 16), pk);     // columns [16 hf, 16 hf + 16) of S: already consumed
       }
@@ -345,6 +357,9 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16);
     const long long stat0 = ((long long)b * p.H + h) * p.Lq;
     const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), ss2 = make_float2(p.scale, p.scale);
+    // key mask: this thread's key is the TMEM lane; a masked key has P^T = dS^T = 0 for every query
+    uint32_t kmask = 0xffffffffu;
+    if (p.key_mask && n0 + row < p.Lk && p.key_mask[(long long)b * p.Lk + n0 + row] == 0) kmask = 0u;
     for (int j = 0; j < n_tiles; ++j) {
       // per-query statistics of this tile -> shared memory (double-buffered: the barrier below is the only sync)
       float* st = sStat + (j & 1) * 2 * TB_BN;
@@ -373,8 +388,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           const float2 pr = make_float2(fast_exp2(t.x), fast_exp2(t.y));
           float2 g = __fadd2_rn(make_float2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1])), make_float2(-d2.x, -d2.y));
           g = __fmul2_rn(__fmul2_rn(pr, g), ss2);
-          pp[i] = __byte_perm(__float_as_uint(pr.x), __float_as_uint(pr.y), 0x7632);
-          pd[i] = __byte_perm(__float_as_uint(g.x), __float_as_uint(g.y), 0x7632);
+          pp[i] = __byte_perm(__float_as_uint(pr.x), __float_as_uint(pr.y), 0x7632) & kmask;
+          pd[i] = __byte_perm(__float_as_uint(g.x), __float_as_uint(g.y), 0x7632) & kmask;
         }
         tmem_st_32x32b_x16(t_lane + (uint32_t)(hf * 16), pp);             // P^T over S^T
         tmem_st_32x32b_x16(t_lane + (uint32_t)(TB_BN + hf * 16), pd);     // dS^T over dP^T
@@ -443,20 +458,21 @@ static int launch_bwd_tc(const CUtensorMap& tQb, const CUtensorMap& tKs32, const
   return 0;
 }
 
-// Unmasked, non-causal backward on the tensor cores.  Returns -1 when the problem is not eligible (the caller then
-// runs the warp-MMA kernels, which handle key masks, causal multi-KV, d = 64 / 160 and tiny shapes).  delta must
+// Non-causal backward on the tensor cores, with an optional key mask.  Returns -1 when the problem is not eligible (the caller then
+// runs the warp-MMA kernels, which handle causal multi-KV, d = 64 / 160, ragged masked lengths and tiny shapes).  delta must
 // already hold rowsum(dO o O).
 int attn_bwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sn, const void* k, int64_t k_sb, int64_t k_sn, const void* v,
                      int64_t v_sb, int64_t v_sn, const void* dout, int64_t do_sb, int64_t do_sn, const float* lse,
                      const float* delta, void* dq, int64_t dq_sb, int64_t dq_sn, void* dk, int64_t dk_sb, int64_t dk_sn, void* dv,
                      int64_t dv_sb, int64_t dv_sn, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t d, float scale,
-                     cudaStream_t stream) {
+                     const uint8_t* key_mask, cudaStream_t stream) {
   static int enabled = -1;
   if (enabled < 0) {
     const char* e = getenv("ADAFACE_BWD_TC");          // 1 (default): tcgen05 backward where eligible
     enabled = (e && e[0] == '0') ? 0 : 1;
   }
   if (!enabled || !(d == 40 || d == 80) || Lq < 256 || Lk < 64) return -1;
+  if (key_mask && Lk % 64 != 0) return -1;      // the dq pass reads the mask in 32-byte pieces per key tile
   CUtensorMap tQb, tKs, tVs, tdOb, tQs, tKb, tVb, tdOs;
   const uint64_t ud = (uint64_t)d, uH = (uint64_t)H, uB = (uint64_t)B;
   if (make_tmap_bf16_heads(&tQb, q, ud, uH, (uint64_t)Lq, uB, ud, (uint64_t)q_sn, (uint64_t)q_sb, TB_BM)) return 3;
@@ -475,6 +491,7 @@ int attn_bwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sn, const void* k, i
   p.Lq = (int)Lq; p.Lk = (int)Lk; p.H = (int)H;
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.key_mask = key_mask;
   return d == 40 ? launch_bwd_tc<40>(tQb, tKs, tVs, tdOb, tQs, tKb, tVb, tdOs, p, (int)B, (int)H, stream)
                  : launch_bwd_tc<80>(tQb, tKs, tVs, tdOb, tQs, tKb, tVb, tdOs, p, (int)B, (int)H, stream);
 }

@@ -96,6 +96,31 @@ def test_attention_bwd_fused_views_and_key_mask():
     assert dqkv[:, :, Cc:2 * Cc][dead].abs().max().item() == 0 and dqkv[:, :, 2 * Cc:][dead].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("d,N", [(40, 1024), (80, 512), (40, 4096)])
+def test_attention_bwd_key_mask_on_tcgen05(d, N):
+    """img_mask self-attention backward (dalc:254-273) on the tensor-core kernels: random masks, a masked leading block, a single kept
+    key, and one unmasked instance in the same batch; masked keys receive exactly zero dK / dV."""
+    B, H = 4, 8
+    Cc = H * d
+    qkv, do = rnd(B, N, 3 * Cc, seed=11), rnd(B, N, Cc, seed=12)
+    km = (torch.rand(B, N, generator=torch.Generator().manual_seed(6)) > 0.4).to(torch.uint8)
+    km[1, :200] = 0
+    km[2] = 0
+    km[2, 333] = 1
+    km[3] = 1
+    km = km.cuda()
+    q, k, v = qkv[:, :, :Cc], qkv[:, :, Cc:2 * Cc], qkv[:, :, 2 * Cc:]
+    lse = torch.empty(B, H, N, device="cuda")
+    o = ops().attention(q, k, v, H, d ** -0.5, key_mask=km, lse=lse)
+    ro, rq, rk, rv = ref_attn_grads(q, k, v, do, H, d ** -0.5, key_mask=km)
+    assert rel(o, ro) < 2e-2
+    dqkv = torch.empty_like(qkv)
+    ops().attention_bwd(q, k, v, o, do, lse, H, d ** -0.5, dqkv[:, :, :Cc], dqkv[:, :, Cc:2 * Cc], dqkv[:, :, 2 * Cc:], key_mask=km)
+    assert rel(dqkv[:, :, :Cc], rq) < GRAD_TOL and rel(dqkv[:, :, Cc:2 * Cc], rk) < GRAD_TOL and rel(dqkv[:, :, 2 * Cc:], rv) < GRAD_TOL
+    dead = (km == 0)[:, :, None].expand(B, N, Cc)
+    assert dqkv[:, :, Cc:2 * Cc][dead].abs().max().item() == 0 and dqkv[:, :, 2 * Cc:][dead].abs().max().item() == 0
+
+
 @pytest.mark.parametrize("mult,T", [(1, 20), (2, 20), (4, 24), (2, 77)])
 def test_attention_bwd_causal_multi_kv(mult, T):
     """CLIPAttentionMKV (arc2face_models.py:145-231): token t carries its M keys back to back."""
