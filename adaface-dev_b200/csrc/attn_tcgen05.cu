@@ -440,6 +440,17 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     const int row = qd * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16);
     float m_ref = -INFINITY, l_run = 0.f;
+    // key mask (dalc:254-273 img_mask; Lk % 64 == 0): the 32 mask bytes of a half tile are the same for every row (broadcast loads);
+    // a masked key's score becomes -inf before both passes.  A tile of only masked keys leaves P = exp2(-inf - m_ref) = 0 once a kept key
+    // has set the reference; before that (m_ref = 0 from an all-masked first tile) it contributes exactly 0 as well.
+    auto mask_half = [&](uint32_t (&v)[32], int j, int hf) {
+      const uint4* mp = reinterpret_cast<const uint4*>(p.key_mask + (long long)b * p.Lk + j * TA_BN + hf * 32);
+      const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+      const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (((mw[i >> 2] >> ((i & 3) * 8)) & 0xffu) == 0) v[i] = 0xff800000u;
+    };
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full, j & 1);          // also implies P V_{j-1} has retired (commit covers all earlier MMAs)
       tc_fence_after();
@@ -455,6 +466,7 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
           for (int i = 0; i < 32; ++i)
             if (hf * 32 + i >= valid) v[i] = 0xff800000u;
         }
+        if (p.key_mask) mask_half(v, j, hf);
         float m4[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
 #pragma unroll
         for (int i = 4; i < 32; i += 4) {
@@ -496,6 +508,7 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
           for (int i = 0; i < 32; ++i)
             if (hf * 32 + i >= valid) v[i] = 0xff800000u;
         }
+        if (p.key_mask) mask_half(v, j, hf);
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -1515,7 +1528,10 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, co
                      float scale, float* lse, const uint8_t* key_mask, cudaStream_t stream) {
   if (!(d == 40 || d == 80 || d == 160)) return -1;
   // a key mask runs on the four-tile kernel only (d = 40, level A: the case that costs 3.5x on the warp-MMA kernel)
-  if (key_mask && !(d == 40 && drow_q == 40 && drow_kv == 40 && Lq >= 2 * TQ_G * TA_BM && Lk > 128)) return -1;
+  const bool mask_quad = key_mask && d == 40 && drow_q == 40 && drow_kv == 40 && Lq >= 2 * TQ_G * TA_BM && Lk > 128;
+  // other masked shapes (level B: d = 80; short d = 40 maps): the small-CTA kernel masks the scores in registers
+  const bool mask_mc = key_mask && !mask_quad && (d == 40 || d == 80) && Lk % 64 == 0 && Lk > 128 && Lq >= 128;
+  if (key_mask && !mask_quad && !mask_mc) return -1;
   // drow_* = elements that exist in a row: d, or the zero-padded width of a head-major buffer
   if (drow_q < d) drow_q = d;
   if (drow_kv < d) drow_kv = d;
@@ -1567,7 +1583,11 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, co
     const char* e = getenv("ADAFACE_ATTN_QUAD");    // 1 (default): four query tiles per CTA, one in-order MMA issuer (d = 40)
     quad = (e && e[0] == '0') ? 0 : 1;
   }
-  if (key_mask) return (quad && mc && !psmem) ? launch_ta_quad<40, 5, true>(tQ, tK, tV, p, ib, ih, stream) : -1;
+  if (mask_quad) return (quad && mc && !psmem) ? launch_ta_quad<40, 5, true>(tQ, tK, tV, p, ib, ih, stream) : -1;
+  if (mask_mc) {
+    if (!mc || psmem) return -1;
+    return d == 40 ? launch_ta_mc<40, 2>(tQ, tK, tV, p, ib, ih, stream) : launch_ta_mc<80, 0>(tQ, tK, tV, p, ib, ih, stream);
+  }
   {
     static int tri = -1;
     if (tri < 0) {

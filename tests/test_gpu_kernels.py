@@ -205,6 +205,36 @@ def test_attention_key_mask_on_tcgen05(B, Lq, Lk, pattern):
     assert a_lib().launch_count() - n0 <= 2      # bulk (+ tail) launch of the four-tile kernel: the mask no longer falls to the warp-MMA kernel
 
 
+@pytest.mark.parametrize("d,B,N,pattern", [(80, 3, 1024, "random"), (80, 2, 1024, "lead"), (40, 2, 512, "random"), (80, 1, 256, "last_only")])
+def test_attention_key_mask_small_cta_kernel(d, B, N, pattern):
+    """img_mask self-attention at level B (d = 80, 1024 tokens) and on short d = 40 maps: the small-CTA tcgen05 kernel masks the scores
+    in registers (mask bytes of the key tile, broadcast loads).  Leading key tiles entirely masked, a single surviving key, lse."""
+    import math
+    H = 8
+    C = H * d
+    qkv = rnd(B, N, 3 * C, seed=13)
+    q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+    g = torch.Generator().manual_seed(7)
+    if pattern == "random":
+        mask = torch.rand(B, N, generator=g) > 0.4
+    elif pattern == "lead":
+        mask = torch.ones(B, N, dtype=torch.bool)
+        mask[:, :130] = False
+        mask[0, :700] = False
+    else:
+        mask = torch.zeros(B, N, dtype=torch.bool)
+        mask[:, -1] = True
+    mask = mask.to(torch.uint8).cuda()
+    lse = torch.empty(B, H, N, device="cuda")
+    n0 = a_lib().launch_count()
+    o = ops().attention(q, k, v, H, d ** -0.5, key_mask=mask, lse=lse)
+    assert a_lib().launch_count() - n0 == 1
+    ref, s, _ = ref_attn(q, k, v, H, d ** -0.5, key_mask=mask)
+    assert maxerr(o, ref) < 2e-2
+    rlse = torch.logsumexp(s, dim=-1) * math.log2(math.e)
+    assert (lse.cpu() - rlse).abs().max().item() < 2e-2
+
+
 @pytest.mark.parametrize("mult,T", [(1, 20), (2, 20), (4, 24), (1, 77), (2, 77), (8, 77)])
 def test_attention_causal_multi_kv(mult, T):
     """CLIPAttentionMKV: each token carries `mult` keys back to back; key j visible iff j // mult <= i."""
