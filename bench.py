@@ -885,7 +885,7 @@ def main_gpu(args):
 
         # ---- the same step as ONE CUDA graph: the pinned-memory copies become memcpy nodes on two side branches of the graph (forked from and
         #      joined to the kernel branch by events), so the host launches one graph per step instead of eight graphs plus the copies and
-        #      events between them.  Same units, same order, same buffers; kept only if it captures and is not slower.
+        #      events between them.  Same units, same order, same buffers; kept only if it captures, reproduces the multi-graph output and is not slower.
         if use_graph and os.environ.get("ADAFACE_BENCH_E2E_ONEGRAPH", "1") != "0":
             prev = a._lib.set_pdl(int(os.environ.get("ADAFACE_BENCH_E2E_PDL", "3")))
             try:
@@ -896,6 +896,7 @@ def main_gpu(args):
                     cand = [ui for ui, u in enumerate(units) if u["li"] == 0 and u["up"] is None and u["host_out"] is None and len(u["blocks"]) > 1]
                     head_ui = cand[0] if cand else -1
                 hb = BATCH // head_split if head_ui >= 0 else BATCH
+                tail_full_self = os.environ.get("ADAFACE_BENCH_TAIL_FULL_SELF", "0") != "0"      # measured: on 3.30 ms, off 3.12 ms (the slices' D2H then has nothing to hide behind)
 
                 def one_graph_body():
                     cs = torch.cuda.current_stream()
@@ -917,6 +918,7 @@ def main_gpu(args):
                                 ev_in[ui] = torch.cuda.Event()
                                 ev_in[ui].record(s_in)
                     outs = {}
+                    tail_y1 = {}
                     forked_out = False
                     for ui, u in enumerate(units):
                         if ui == head_ui:
@@ -933,8 +935,15 @@ def main_gpu(args):
                         if u["up"] is None:
                             out = bodies[ui](*u["dev_in"])
                         else:
+                            # tail units (the level's last block, one per batch slice): the self-attention module runs ONCE on the whole
+                            # batch (the four-tile kernel wants >= 3 waves of tiles), only the cheap cross-attention module runs per slice
                             up = units[u["up"]]
-                            out = bodies[ui](outs[u["up"]][u["sl"]], up["dev_in"][1][u["sl"]])
+                            if tail_full_self and len(u["blocks"]) == 1:
+                                if u["up"] not in tail_y1:
+                                    tail_y1[u["up"]] = u["blocks"][0][0](outs[u["up"]])
+                                out = u["blocks"][0][1](tail_y1[u["up"]][u["sl"]], encoder_hidden_states=up["dev_in"][1][u["sl"]])
+                            else:
+                                out = bodies[ui](outs[u["up"]][u["sl"]], up["dev_in"][1][u["sl"]])
                         outs[ui] = out
                         if u["host_out"] is not None:
                             ev = torch.cuda.Event()
@@ -968,14 +977,15 @@ def main_gpu(args):
                 ref_host = chk_unit["host_out"].clone()
                 e2e_step()
                 torch.cuda.synchronize()
-                same = torch.equal(ref_host, chk_unit["host_out"])
+                # (bf16 outputs of O(1) values; the whole-batch self-attention may sum a row's keys in another order than the per-slice launch)
+                same = bool((ref_host.float() - chk_unit["host_out"].float()).abs().max().item() <= 2e-2)
                 if same and t_one < t_e2e_ms:
                     e2e_how = (f"ONE CUDA graph per step: {len(units)} kernel units on the main branch, the pinned-memory H2D / D2H copies as memcpy nodes on two side "
                                f"branches" + (f"; level A's input arrives in {head_split} batch slices and its first block runs per slice" if head_ui >= 0 else "") +
                                f" (the multi-graph form of the same step: {t_e2e_ms:.3f} ms)")
                     t_e2e_ms = t_one
                 else:
-                    e2e_how += f"; the one-graph form measured {t_one:.3f} ms (bit-identical output: {same})"
+                    e2e_how += f"; the one-graph form measured {t_one:.3f} ms (same output: {same})"
             except Exception as ex:
                 e2e_how += f"; one-graph capture failed ({type(ex).__name__}: {ex})"
             finally:
