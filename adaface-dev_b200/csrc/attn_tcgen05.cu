@@ -724,11 +724,36 @@ attn_fwd_tcgen05_quad_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
     if constexpr (MASK) {
       // the issuer needs the PATCHED K tile j + 1 while it works on tile j: patch one tile ahead of the load that may block on a
       // ring slot (tile j + 2 waits for tile j - 1 to be consumed)
-      patch(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) patch(j + 1);
-        if (leader && j + 2 < n_tiles) issue_kv(j + 2);
-        __syncwarp();
+      // Two independent event streams -- "ring slot free -> issue the next load" and "tile landed -> patch it" -- served by polling, whichever is
+      // ready first.  (Traced: with the fixed order patch(j + 1); issue_kv(j + 2) the load of tile j + 2 was only issued after tile j + 1 had
+      // LANDED, one load in flight at a time, and the issuer waited ~1800 clk per step for its next patched K tile.)
+      int next_load = n_tiles > 1 ? 2 : 1, next_patch = 0;
+      while (next_patch < n_tiles) {
+        int did = 0;
+        if (next_load < n_tiles) {
+          int ok = 0;
+          if (leader) {
+            uint32_t t;
+            asm volatile("{\n\t.reg .pred P;\n\tmbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
+                         : "=r"(t) : "r"(smem_u32(&kv_empty[next_load % ST])), "r"((uint32_t)(((next_load / ST) & 1) ^ 1)) : "memory");
+            ok = (int)t;
+            if (ok) issue_kv(next_load);
+          }
+          ok = __any_sync(0xffffffffu, ok);
+          if (ok) { ++next_load; did = 1; }
+        }
+        if (next_patch < next_load) {
+          int ok = 0;
+          if (leader) {
+            uint32_t t;
+            asm volatile("{\n\t.reg .pred P;\n\tmbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
+                         : "=r"(t) : "r"(smem_u32(&kv_full[next_patch % ST])), "r"((uint32_t)((next_patch / ST) & 1)) : "memory");
+            ok = (int)t;
+          }
+          ok = __any_sync(0xffffffffu, ok);
+          if (ok) { patch(next_patch); ++next_patch; did = 1; }
+        }
+        if (!did) __nanosleep(32);
       }
     } else {
       for (int j = 0; j < n_tiles; ++j) {
