@@ -349,6 +349,12 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
   constexpr int NA = Cfg::NA, KT = Cfg::KT, DO = Cfg::DO, ST = 2;
   constexpr int TMEM_O = TA_BN;                                   // S/P at column 0, O behind it
   constexpr int TMEM_COLS = (TMEM_O + DO <= 128) ? 128 : 256;
+  // DB (d = 80: 64 + 96 + 64 = 224 of the 256 allocated columns): a SECOND score buffer behind O.  Q.K^T(j+1) is issued before the issuer
+  // waits for P(j), so the next scores are ready when the softmax warps finish tile j -- the serial chain Q.K^T -> softmax -> P.V of a
+  // CTA (2050 clk per 64 keys at d = 80 against ~575 clk of tensor work and ~1100 of softmax) becomes softmax-bound.  K and V tiles then
+  // have separate rings: a K stage is free after its Q.K^T, i.e. a whole softmax earlier than the V stage.
+  constexpr bool DB = TMEM_O + DO + TA_BN <= TMEM_COLS && TMEM_COLS == 256;
+  constexpr int TMEM_S1 = TMEM_O + DO;
   extern __shared__ uint8_t smem_raw_mc[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_mc) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -356,12 +362,15 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
   uint8_t* sV = sK + ST * Cfg::K_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * Cfg::V_BYTES);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_full = bars + 1;                                   // DB: K tiles only
   uint64_t* kv_empty = kv_full + ST;
-  uint64_t* s_full = kv_empty + ST;
-  uint64_t* p_full = s_full + 1;
-  uint64_t* o_full = p_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* s_full = kv_empty + ST;                               // [2] (DB: one per score buffer)
+  uint64_t* p_full = s_full + 2;                                  // [2]
+  uint64_t* o_full = p_full + 2;
+  uint64_t* v_full = o_full + 1;                                  // [ST] DB only
+  uint64_t* v_empty = v_full + ST;                                // [ST] DB only
+  uint64_t* pv_done = v_empty + ST;                               // DB only: P.V(j) has retired (O may be rescaled)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TA_BM, h = blockIdx.y, b = blockIdx.z;
@@ -375,10 +384,15 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     for (int s = 0; s < ST; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+    }
     mbar_init(o_full, 1);
+    mbar_init(pv_done, 1);
     fence_barrier_init();
   } else if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, TMEM_COLS);
@@ -393,16 +407,40 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
   if (warp == kTmaWarp) {
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
+      const int c0 = p.wide ? h * D : 0, hh = p.wide ? 0 : h;      // wide maps: whole rows, the head's box starts at column h*d
 #pragma unroll
-      for (int a = 0; a < NA; ++a) tma_load_4d(sQ + a * (TA_BM * 128), &tmQ, q_full, a * 64, h, m0, b);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % ST;
-        mbar_wait(&kv_empty[s], ((j / ST) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], Cfg::K_BYTES + Cfg::V_BYTES);
+      for (int a = 0; a < NA; ++a) tma_load_4d(sQ + a * (TA_BM * 128), &tmQ, q_full, c0 + a * 64, hh, m0, b);
+      if constexpr (DB) {
+        auto load_k = [&](int j) {
+          const int s = j % ST;
+          mbar_wait(&kv_empty[s], ((j / ST) & 1) ^ 1);
+          mbar_arrive_expect_tx(&kv_full[s], Cfg::K_BYTES);
 #pragma unroll
-        for (int a = 0; a < NA; ++a) {
-          tma_load_4d(sK + s * Cfg::K_BYTES + a * Cfg::KV_ATOM, &tmK, &kv_full[s], a * 64, h, j * TA_BN, b);
-          tma_load_4d(sV + s * Cfg::V_BYTES + a * Cfg::KV_ATOM, &tmV, &kv_full[s], a * 64, h, j * TA_BN, b);
+          for (int a = 0; a < NA; ++a) tma_load_4d(sK + s * Cfg::K_BYTES + a * Cfg::KV_ATOM, &tmK, &kv_full[s], c0 + a * 64, hh, j * TA_BN, b);
+        };
+        auto load_v = [&](int j) {
+          const int s = j % ST;
+          mbar_wait(&v_empty[s], ((j / ST) & 1) ^ 1);
+          mbar_arrive_expect_tx(&v_full[s], Cfg::V_BYTES);
+#pragma unroll
+          for (int a = 0; a < NA; ++a) tma_load_4d(sV + s * Cfg::V_BYTES + a * Cfg::KV_ATOM, &tmV, &v_full[s], c0 + a * 64, hh, j * TA_BN, b);
+        };
+        // K runs one tile ahead of V: K(j + 1) only waits for Q.K^T(j - 1), V(j) for P.V(j - 2)
+        load_k(0);
+        for (int j = 0; j < n_tiles; ++j) {
+          if (j + 1 < n_tiles) load_k(j + 1);
+          load_v(j);
+        }
+      } else {
+        for (int j = 0; j < n_tiles; ++j) {
+          const int s = j % ST;
+          mbar_wait(&kv_empty[s], ((j / ST) & 1) ^ 1);
+          mbar_arrive_expect_tx(&kv_full[s], Cfg::K_BYTES + Cfg::V_BYTES);
+#pragma unroll
+          for (int a = 0; a < NA; ++a) {
+            tma_load_4d(sK + s * Cfg::K_BYTES + a * Cfg::KV_ATOM, &tmK, &kv_full[s], c0 + a * 64, hh, j * TA_BN, b);
+            tma_load_4d(sV + s * Cfg::V_BYTES + a * Cfg::KV_ATOM, &tmV, &kv_full[s], c0 + a * 64, hh, j * TA_BN, b);
+          }
         }
       }
     }
@@ -412,6 +450,36 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       constexpr uint32_t idesc_pv = make_idesc_bf16_f32(TA_BM, DO, true);
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
       mbar_wait(q_full, 0);
+      if constexpr (DB) {
+        auto issue_qk = [&](int j) {      // S_j -> score buffer j & 1 (it overwrites P_{j-2}, whose P.V was issued earlier: in order)
+          const int s = j % ST;
+          mbar_wait(&kv_full[s], (j / ST) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < KT; ++kk) {
+            const uint64_t da = make_smem_desc_sw128(aQ + (kk >> 2) * (TA_BM * 128) + (kk & 3) * 32);
+            const uint64_t db = make_smem_desc_sw128(aK + s * Cfg::K_BYTES + (kk >> 2) * Cfg::KV_ATOM + (kk & 3) * 32);
+            umma_bf16(tmem_base + (uint32_t)((j & 1) ? TMEM_S1 : 0), da, db, idesc_qk, kk > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[j & 1]);
+          umma_commit(&kv_empty[s]);      // the K stage is free once S_j exists
+        };
+        issue_qk(0);
+        for (int j = 0; j < n_tiles; ++j) {
+          const int s = j % ST;
+          if (j + 1 < n_tiles) issue_qk(j + 1);
+          mbar_wait(&v_full[s], (j / ST) & 1);
+          mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < TA_BN / 16; ++k) {
+            const uint64_t db = make_smem_desc_sw128_mn(aV + s * Cfg::V_BYTES + k * 2048, Cfg::KV_ATOM);
+            umma_bf16_ts(tmem_base + (uint32_t)TMEM_O, tmem_base + (uint32_t)(((j & 1) ? TMEM_S1 : 0) + k * 8), db, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&v_empty[s]);
+          umma_commit(pv_done);
+        }
+      } else {
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j % ST;
         mbar_wait(&kv_full[s], (j / ST) & 1);
@@ -423,8 +491,8 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
           const uint64_t db = make_smem_desc_sw128(aK + s * Cfg::K_BYTES + (kk >> 2) * Cfg::KV_ATOM + (kk & 3) * 32);
           umma_bf16(tmem_base, da, db, idesc_qk, kk > 0 ? 1u : 0u);
         }
-        umma_commit(s_full);
-        mbar_wait(p_full, j & 1);
+        umma_commit(&s_full[0]);
+        mbar_wait(&p_full[0], j & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < TA_BN / 16; ++k) {
@@ -432,6 +500,7 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
           umma_bf16_ts(tmem_base + (uint32_t)TMEM_O, tmem_base + (uint32_t)(k * 8), db, idesc_pv, (j | k) != 0 ? 1u : 0u);
         }
         umma_commit(&kv_empty[s]);
+      }
       }
       umma_commit(o_full);
     }
@@ -452,7 +521,9 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         if (((mw[i >> 2] >> ((i & 3) * 8)) & 0xffu) == 0) v[i] = 0xff800000u;
     };
     for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(s_full, j & 1);          // also implies P V_{j-1} has retired (commit covers all earlier MMAs)
+      // single buffer: s_full also implies P V_{j-1} has retired (commit covers all earlier MMAs); DB: see pv_done below
+      const uint32_t t_s = t_lane + (uint32_t)((DB && (j & 1)) ? TMEM_S1 : 0);
+      mbar_wait(&s_full[DB ? (j & 1) : 0], DB ? ((j >> 1) & 1) : (j & 1));
       tc_fence_after();
       const int valid = p.Lk - j * TA_BN;
       // ---- pass 1: row max of the raw scores
@@ -460,7 +531,7 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32_wait(t_lane + (uint32_t)(hf * 32), v);
+        tmem_ld_32x32b_x32_wait(t_s + (uint32_t)(hf * 32), v);
         if (valid < TA_BN) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
@@ -481,6 +552,10 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       } else {
         const bool need = mx > m_ref + 8.f;
         if (__any_sync(0xffffffffu, need)) {
+          if constexpr (DB) {             // Q.K^T(j) was issued BEFORE P.V(j-1): the accumulator is only ours once that MMA has retired
+            mbar_wait(pv_done, (j - 1) & 1);
+            tc_fence_after();
+          }
           const float m_new = need ? mx : m_ref;
           const float f = fast_exp2(m_ref - m_new);
           m_ref = m_new;
@@ -502,7 +577,7 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32_wait(t_lane + (uint32_t)(hf * 32), v);
+        tmem_ld_32x32b_x32_wait(t_s + (uint32_t)(hf * 32), v);
         if (valid < TA_BN) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
@@ -518,12 +593,12 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
           ls[i & 1] = __fadd2_rn(ls[i & 1], make_float2(__uint_as_float(ex), __uint_as_float(ey)));
           pk[i] = __byte_perm(ex, ey, 0x7632);
         }
-        tmem_st_32x32b_x16(t_lane + (uint32_t)(hf * 16), pk);   // columns [16 hf, 16 hf + 16): already consumed
+        tmem_st_32x32b_x16(t_s + (uint32_t)(hf * 16), pk);      // columns [16 hf, 16 hf + 16): already consumed
       }
       tmem_st_wait();
       l_run += (ls[0].x + ls[0].y) + (ls[1].x + ls[1].y);
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[DB ? (j & 1) : 0]);
     }
     mbar_wait(o_full, 0);
     tc_fence_after();
@@ -1584,6 +1659,7 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, co
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse;
   p.key_mask = key_mask;
+  p.wide = 0;
   p.trace = nullptr;
   if (getenv("ADAFACE_ATTN_TRACE")) {
     static long long* tbuf = nullptr;
@@ -1591,6 +1667,27 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, co
     cudaMemset(tbuf, 0, 1024 * 8);
     p.trace = tbuf;
   }
+  // d = 80 in the reference layout [B, L, H*d] (also the q / k / v column blocks of a fused projection buffer): per-head boxes make the TMA unit
+  // fetch 160-byte row pieces and fill the rest of its two 128-byte swizzle rows itself (16 useful B/clk/SM in the microbenchmark; suspected
+  // to bound the small-CTA kernel at level B -- 2 CTAs x 20 KB of K / V per 64-key step -- but the A/B below says it does not).  Maps over whole rows with the head's box starting at column
+  // h*d move full 128-byte rows; 80 = 5 x 16, so neither Q.K^T (five k16 steps) nor P.V (N = 80) ever touches the neighbour head's columns
+  // that ride along in the second swizzle atom.
+  CUtensorMap tQw, tKw, tVw;
+  auto wide80 = [&]() -> bool {
+    static int on = -1;
+    if (on < 0) {
+      const char* e = getenv("ADAFACE_ATTN_WIDE80");      // A/B switch, default OFF: measured no change at level B (48.1 us either way)
+      on = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!on || d != 80 || q_sh != 80 || k_sh != 80 || v_sh != 80 || drow_q != 80 || drow_kv != 80) return false;
+    const uint64_t W = (uint64_t)(H * 80);
+    if ((uint64_t)q_sn < W || (uint64_t)k_sn < W || (uint64_t)v_sn < W) return false;
+    if (make_tmap_bf16_heads(&tQw, q, W, 1, (uint64_t)Lq, (uint64_t)B, W, (uint64_t)q_sn, (uint64_t)q_sb, TA_BM)) return false;
+    if (make_tmap_bf16_heads(&tKw, k, W, 1, (uint64_t)Lk, (uint64_t)B, W, (uint64_t)k_sn, (uint64_t)k_sb, TA_BN)) return false;
+    if (make_tmap_bf16_heads(&tVw, v, W, 1, (uint64_t)Lk, (uint64_t)B, W, (uint64_t)v_sn, (uint64_t)v_sb, TA_BN)) return false;
+    p.wide = 1;
+    return true;
+  };
   static int emu = -1, psmem = 0, mc = 1;
   static bool emu_set = false;
   if (emu < 0) {
@@ -1611,6 +1708,7 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, co
   if (mask_quad) return (quad && mc && !psmem) ? launch_ta_quad<40, 5, true>(tQ, tK, tV, p, ib, ih, stream) : -1;
   if (mask_mc) {
     if (!mc || psmem) return -1;
+    if (d == 80 && wide80()) return launch_ta_mc<80, 0>(tQw, tKw, tVw, p, ib, ih, stream);
     return d == 40 ? launch_ta_mc<40, 2>(tQ, tK, tV, p, ib, ih, stream) : launch_ta_mc<80, 0>(tQ, tK, tV, p, ib, ih, stream);
   }
   {
@@ -1650,7 +1748,10 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, co
       default: return launch_ta_mc<40, 4>(tQ, tK, tV, p, ib, ih, stream);
     }
   }
-  if (mc && !psmem && d == 80) return emu ? launch_ta_mc<80, 2>(tQ, tK, tV, p, ib, ih, stream) : launch_ta_mc<80, 0>(tQ, tK, tV, p, ib, ih, stream);
+  if (mc && !psmem && d == 80) {
+    if (wide80()) return launch_ta_mc<80, 0>(tQw, tKw, tVw, p, ib, ih, stream);
+    return emu ? launch_ta_mc<80, 2>(tQ, tK, tV, p, ib, ih, stream) : launch_ta_mc<80, 0>(tQ, tK, tV, p, ib, ih, stream);
+  }
   switch (d) {
     case 40:
       if (psmem) return launch_ta<40, 0, false>(tQ, tK, tV, p, ib, ih, stream);
