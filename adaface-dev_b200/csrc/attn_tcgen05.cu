@@ -637,6 +637,279 @@ attn_fwd_tcgen05_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
 }
 
 // =============================================================================================
+// PERSISTENT form of the small-CTA kernel for d = 80 (level B).  With one 128-query tile per CTA the 512 tiles of level B (B = 8) are 1.73
+// waves of 296 CTA slots, and every CTA pays its own set-up (TMEM allocation, barrier init, descriptor fetch, first loads: several
+// microseconds against ~11 us of work for 16 key tiles).  Here 2 x #SM CTAs stay resident and walk the (batch, head, query tile) units with a
+// stride of the grid; barrier phases, the K / V rings and the two score buffers simply keep counting across units.  Per unit the pipeline
+// is the double-buffered one of attn_fwd_tcgen05_mc_kernel (DB): Q.K^T(j+1) ahead of P.V(j), separate K / V rings, pv_done before a rescale.
+template <int D, int EMU>
+__global__ void __launch_bounds__(TA_THREADS, 2)
+attn_fwd_tcgen05_mcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                            const __grid_constant__ CUtensorMap tmV, const TaParams p, const int H, const int n_units) {
+  using Cfg = TaCfg<D>;
+  constexpr int NA = Cfg::NA, KT = Cfg::KT, DO = Cfg::DO, ST = 2;
+  constexpr int TMEM_O = TA_BN, TMEM_S1 = TMEM_O + DO, TMEM_COLS = 256;
+  static_assert(TMEM_S1 + TA_BN <= TMEM_COLS, "two score buffers and the accumulator must fit 256 TMEM columns");
+  extern __shared__ uint8_t smem_raw_mcp[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_mcp) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + ST * Cfg::K_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * Cfg::V_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;                                    // [ST]
+  uint64_t* k_empty = k_full + ST;                                // [ST]
+  uint64_t* v_full = k_empty + ST;                                // [ST]
+  uint64_t* v_empty = v_full + ST;                                // [ST]
+  uint64_t* s_full = v_empty + ST;                                // [2]
+  uint64_t* p_full = s_full + 2;                                  // [2]
+  uint64_t* pv_done = p_full + 2;
+  uint64_t* o_full = pv_done + 1;
+  uint64_t* o_free = o_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_qt = (p.Lq + TA_BM - 1) / TA_BM;
+  const int n_tiles = (p.Lk + TA_BN - 1) / TA_BN;
+
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+    }
+    mbar_init(pv_done, 1);
+    mbar_init(o_full, 1);
+    mbar_init(o_free, 128);
+    fence_barrier_init();
+  } else if (warp == kMmaWarp) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // global memory is touched only after the predecessor kernel has completed
+  AF_PDL_TRIGGER_EARLY();
+
+  if (warp == kTmaWarp) {
+    if (elect_one()) {
+      int tk = 0, tv = 0;      // K / V tiles loaded so far (ring positions keep counting across units)
+      for (int u = blockIdx.x, it = 0; u < n_units; u += gridDim.x, ++it) {
+        const int bh = u / n_qt, qt = u - bh * n_qt;
+        const int b = bh / H, h = bh - b * H;
+        const int c0 = p.wide ? h * D : 0, hh = p.wide ? 0 : h;
+        if (it > 0) mbar_wait(q_empty, (it - 1) & 1);            // every Q.K^T of the previous unit has read the Q tile
+        mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+        for (int a = 0; a < NA; ++a) tma_load_4d(sQ + a * (TA_BM * 128), &tmQ, q_full, c0 + a * 64, hh, qt * TA_BM, b);
+        auto load_k = [&](int j) {
+          const int s = tk % ST;
+          mbar_wait(&k_empty[s], ((tk / ST) & 1) ^ 1);
+          mbar_arrive_expect_tx(&k_full[s], Cfg::K_BYTES);
+#pragma unroll
+          for (int a = 0; a < NA; ++a) tma_load_4d(sK + s * Cfg::K_BYTES + a * Cfg::KV_ATOM, &tmK, &k_full[s], c0 + a * 64, hh, j * TA_BN, b);
+          ++tk;
+        };
+        auto load_v = [&](int j) {
+          const int s = tv % ST;
+          mbar_wait(&v_empty[s], ((tv / ST) & 1) ^ 1);
+          mbar_arrive_expect_tx(&v_full[s], Cfg::V_BYTES);
+#pragma unroll
+          for (int a = 0; a < NA; ++a) tma_load_4d(sV + s * Cfg::V_BYTES + a * Cfg::KV_ATOM, &tmV, &v_full[s], c0 + a * 64, hh, j * TA_BN, b);
+          ++tv;
+        };
+        load_k(0);
+        for (int j = 0; j < n_tiles; ++j) {
+          if (j + 1 < n_tiles) load_k(j + 1);
+          load_v(j);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16_f32(TA_BM, TA_BN, false);
+      constexpr uint32_t idesc_pv = make_idesc_bf16_f32(TA_BM, DO, true);
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
+      int tk = 0, tv = 0, g = 0;      // K tiles / V tiles consumed, score tiles issued (global counters)
+      for (int u = blockIdx.x, it = 0; u < n_units; u += gridDim.x, ++it) {
+        const int g0 = it * n_tiles;
+        mbar_wait(q_full, it & 1);
+        auto issue_qk = [&](int j) {      // S_j -> score buffer (g0 + j) & 1
+          const int s = tk % ST, buf = (g0 + j) & 1;
+          mbar_wait(&k_full[s], (tk / ST) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < KT; ++kk) {
+            const uint64_t da = make_smem_desc_sw128(aQ + (kk >> 2) * (TA_BM * 128) + (kk & 3) * 32);
+            const uint64_t db = make_smem_desc_sw128(aK + s * Cfg::K_BYTES + (kk >> 2) * Cfg::KV_ATOM + (kk & 3) * 32);
+            umma_bf16(tmem_base + (uint32_t)(buf ? TMEM_S1 : 0), da, db, idesc_qk, kk > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[buf]);
+          umma_commit(&k_empty[s]);
+          ++tk;
+          if (j + 1 == n_tiles) umma_commit(q_empty);      // last Q.K^T of the unit: the Q tile may be replaced
+        };
+        issue_qk(0);
+        for (int j = 0; j < n_tiles; ++j) {
+          const int s = tv % ST, buf = (g0 + j) & 1;
+          if (j + 1 < n_tiles) issue_qk(j + 1);
+          mbar_wait(&v_full[s], (tv / ST) & 1);
+          mbar_wait(&p_full[buf], ((g0 + j) >> 1) & 1);
+          if (j == 0 && it > 0) mbar_wait(o_free, (it - 1) & 1);      // the previous unit's epilogue has read the accumulator
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < TA_BN / 16; ++k) {
+            const uint64_t db = make_smem_desc_sw128_mn(aV + s * Cfg::V_BYTES + k * 2048, Cfg::KV_ATOM);
+            umma_bf16_ts(tmem_base + (uint32_t)TMEM_O, tmem_base + (uint32_t)((buf ? TMEM_S1 : 0) + k * 8), db, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&v_empty[s]);
+          umma_commit(pv_done);
+          ++tv;
+        }
+        umma_commit(o_full);
+        (void)g;
+      }
+    }
+  } else {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16);
+    for (int u = blockIdx.x, it = 0; u < n_units; u += gridDim.x, ++it) {
+      const int bh = u / n_qt, qt = u - bh * n_qt;
+      const int b = bh / H, h = bh - b * H;
+      const int m0 = qt * TA_BM, g0 = it * n_tiles;
+      float m_ref = -INFINITY, l_run = 0.f;
+      auto mask_half = [&](uint32_t (&v)[32], int j, int hf) {
+        const uint4* mp = reinterpret_cast<const uint4*>(p.key_mask + (long long)b * p.Lk + j * TA_BN + hf * 32);
+        const uint4 m0_ = __ldg(mp), m1_ = __ldg(mp + 1);
+        const uint32_t mw[8] = {m0_.x, m0_.y, m0_.z, m0_.w, m1_.x, m1_.y, m1_.z, m1_.w};
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (((mw[i >> 2] >> ((i & 3) * 8)) & 0xffu) == 0) v[i] = 0xff800000u;
+      };
+      for (int j = 0; j < n_tiles; ++j) {
+        const int G = g0 + j;
+        const uint32_t t_s = t_lane + (uint32_t)((G & 1) ? TMEM_S1 : 0);
+        mbar_wait(&s_full[G & 1], (G >> 1) & 1);
+        tc_fence_after();
+        const int valid = p.Lk - j * TA_BN;
+        // the 64 scores of the row are read from TMEM ONCE and stay in registers for the max and the exp2 pass (two CTAs per SM leave 170
+        // registers per thread; the four 32-column round trips of the two-pass form were ~700 clk of pure latency per key tile)
+        uint32_t v[TA_BN];
+        tmem_ld_32x32b_x64_wait(t_s, v);
+        if (valid < TA_BN) {
+#pragma unroll
+          for (int i = 0; i < TA_BN; ++i)
+            if (i >= valid) v[i] = 0xff800000u;
+        }
+        if (p.key_mask) {
+          uint32_t (&va)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+          uint32_t (&vb)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+          mask_half(va, j, 0);
+          mask_half(vb, j, 1);
+        }
+        float m4[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
+#pragma unroll
+        for (int i = 4; i < TA_BN; i += 4) {
+#pragma unroll
+          for (int x = 0; x < 4; ++x) m4[x] = fmaxf(m4[x], __uint_as_float(v[i + x]));
+        }
+        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
+        if (j == 0) {
+          m_ref = (mx == -INFINITY) ? 0.f : mx;
+        } else {
+          const bool need = mx > m_ref + 8.f;
+          if (__any_sync(0xffffffffu, need)) {
+            mbar_wait(pv_done, (G - 1) & 1);      // Q.K^T(j) was issued before P.V(j-1): the accumulator is ours once that MMA has retired
+            tc_fence_after();
+            const float m_new = need ? mx : m_ref;
+            const float f = fast_exp2(m_ref - m_new);
+            m_ref = m_new;
+            l_run *= f;
+#pragma unroll
+            for (int c = 0; c < DO / 16; ++c) {
+              uint32_t ov[16];
+              tmem_ld_32x32b_x16(t_lane + (uint32_t)(TMEM_O + c * 16), ov);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
+              tmem_st_32x32b_x16(t_lane + (uint32_t)(TMEM_O + c * 16), ov);
+            }
+          }
+        }
+        // P = exp2(s * scale - m_ref), truncated to bf16, written over the scores it came from
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
+        float2 ls[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[hf * 32 + 2 * i]), __uint_as_float(v[hf * 32 + 2 * i + 1])), sc2, nm2);
+            const float2 e = ((i & 7) < EMU) ? exp2_emu2(t) : make_float2(fast_exp2(t.x), fast_exp2(t.y));
+            const uint32_t ex = __float_as_uint(e.x) & 0xffff0000u, ey = __float_as_uint(e.y) & 0xffff0000u;
+            ls[i & 1] = __fadd2_rn(ls[i & 1], make_float2(__uint_as_float(ex), __uint_as_float(ey)));
+            pk[i] = __byte_perm(ex, ey, 0x7632);
+          }
+          tmem_st_32x32b_x16(t_s + (uint32_t)(hf * 16), pk);
+        }
+        tmem_st_wait();
+        l_run += (ls[0].x + ls[0].y) + (ls[1].x + ls[1].y);
+        tc_fence_before();
+        mbar_arrive(&p_full[G & 1]);
+      }
+      mbar_wait(o_full, it & 1);
+      tc_fence_after();
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      const int grow = m0 + row;
+      if (p.lse && grow < p.Lq)
+        p.lse[((long long)b * H + h) * p.Lq + grow] = l_run > 0.f ? m_ref + log2f(l_run) : INFINITY;
+      bf16* orow = p.o + (long long)b * p.o_sb + (long long)grow * p.o_sn + h * D;
+#pragma unroll
+      for (int c = 0; c < DO / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_lane + (uint32_t)(TMEM_O + c * 16), v);
+        tmem_ld_wait();
+        if (grow < p.Lq) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            if (c * 16 + half * 8 < D) {
+              uint4 pk;
+              pk.x = pack_bf16(__uint_as_float(v[half * 8 + 0]) * inv, __uint_as_float(v[half * 8 + 1]) * inv);
+              pk.y = pack_bf16(__uint_as_float(v[half * 8 + 2]) * inv, __uint_as_float(v[half * 8 + 3]) * inv);
+              pk.z = pack_bf16(__uint_as_float(v[half * 8 + 4]) * inv, __uint_as_float(v[half * 8 + 5]) * inv);
+              pk.w = pack_bf16(__uint_as_float(v[half * 8 + 6]) * inv, __uint_as_float(v[half * 8 + 7]) * inv);
+              *reinterpret_cast<uint4*>(orow + c * 16 + half * 8) = pk;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(o_free);
+    }
+  }
+  AF_PDL_TRIGGER_LATE();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// =============================================================================================
 // "Quad" variant for d = 40 (level A, half of the whole attention stack's time).  ncu on the many-small-CTAs kernel
 // shows XU (exp2) 63 % + tensor phases that do not overlap: the four co-resident CTAs phase-lock -- they share the XU
 // pipe, so they finish their softmax together, then queue their P.V / Q.K MMAs on the tensor pipe together while the
@@ -1228,6 +1501,21 @@ static int launch_ta_mc(const CUtensorMap& tQ, const CUtensorMap& tK, const CUte
   return 0;
 }
 
+template <int D, int EMU>
+static int launch_ta_mcp(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtensorMap& tV, const TaParams& p, int B, int H,
+                         cudaStream_t stream) {
+  using Cfg = TaCfg<D>;
+  constexpr int smem = Cfg::Q_BYTES + 2 * (Cfg::K_BYTES + Cfg::V_BYTES) + 1024 + 256;
+  AF_CONFIG_SMEM((attn_fwd_tcgen05_mcp_kernel<D, EMU>), smem);
+  const int n_units = B * H * ((p.Lq + TA_BM - 1) / TA_BM);
+  int grid = 2 * af_num_sms();
+  if (grid > n_units) grid = n_units;
+  AF_CUDA(launch_pdl(2, attn_fwd_tcgen05_mcp_kernel<D, EMU>, dim3(grid), dim3(TA_THREADS), smem, stream, tQ, tK, tV, p, H, n_units));
+  AF_CUDA(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
 template <int D, int EMU, bool PT>
 static int launch_ta(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtensorMap& tV, const TaParams& p, int B, int H,
                      cudaStream_t stream) {
@@ -1747,6 +2035,15 @@ int attn_fwd_tcgen05(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sn, co
       case 3: return launch_ta_mc<40, 3>(tQ, tK, tV, p, ib, ih, stream);
       default: return launch_ta_mc<40, 4>(tQ, tK, tV, p, ib, ih, stream);
     }
+  }
+  static int mcp = -1;
+  if (mcp < 0) {
+    const char* e = getenv("ADAFACE_ATTN_MCP");       // 1: persistent small-CTA kernel for d = 80 (off by default: verified on the attention
+    mcp = (e && e[0] == '1') ? 1 : 0;                  // tests only when the round's GPU budget ran out)
+  }
+  if (mc && !psmem && d == 80 && mcp && Lk > 128) {
+    if (wide80()) return launch_ta_mcp<80, 0>(tQw, tKw, tVw, p, ib, ih, stream);
+    return launch_ta_mcp<80, 0>(tQ, tK, tV, p, ib, ih, stream);
   }
   if (mc && !psmem && d == 80) {
     if (wide80()) return launch_ta_mc<80, 0>(tQw, tKw, tVw, p, ib, ih, stream);
